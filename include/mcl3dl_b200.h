@@ -1,0 +1,187 @@
+/*
+ * mcl3dl_b200.h — C ABI of the B200-native measurement-update engine for mcl_3dl.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no STL, no torch
+ * types, no exceptions.  Every entry point names the reference interface it replaces
+ * (paths relative to the at-wat/mcl_3dl tree, v0.7.0).
+ *
+ * The engine is NOT thread-safe; the reference calls this path from the single
+ * ros::spin() thread (src/mcl_3dl.cpp:1466) and so must the caller.
+ *
+ * There is no CPU fallback: if no CUDA device is usable every call fails with
+ * MCL3DL_ERR_CUDA / MCL3DL_ERR_NO_DEVICE.
+ */
+#ifndef MCL3DL_B200_H
+#define MCL3DL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCL3DL_ABI_VERSION 1
+
+/* ---- error codes (the reference has none: degenerate inputs yield (1,0); the only
+ *      exception is ChunkedKdtree::radiusSearch's runtime_error, chunked_kdtree.h:224) */
+enum
+{
+  MCL3DL_OK = 0,
+  MCL3DL_ERR_INVALID_ARG = -1,  /* null pointer / bad size / label out of origins range */
+  MCL3DL_ERR_NO_MAP = -2,       /* measure() before set_map() */
+  MCL3DL_ERR_CUDA = -3,         /* a CUDA runtime call failed; see mcl3dl_last_error_detail */
+  MCL3DL_ERR_NO_DEVICE = -4,    /* no usable sm_100 device */
+  MCL3DL_ERR_TOO_LARGE = -5,    /* grid would exceed 2^31-1 cells (int point_total, raycast_using_dda.h:176) */
+  MCL3DL_ERR_RADIUS = -6        /* match_dist_min > chunk length semantics (chunked_kdtree.h:224-225) */
+};
+
+/* One map / scan point.  Packed from mcl_3dl::PointXYZIL (include/mcl_3dl/point_types.h:40-55:
+ * x,y,z at byte 0/4/8, label at byte 20 of a 32-byte struct) by the adapter. */
+typedef struct
+{
+  float x, y, z;
+  uint32_t label;
+} mcl3dl_point;
+
+/* One particle pose = State6DOF::pos_ / rot_ (include/mcl_3dl/state_6dof.h:55-56).
+ * q is the RAW rot_; the engine normalises it exactly where the reference does
+ * (State6DOF::transform, state_6dof.h:217) and uses it raw where the reference does
+ * (beam origin, src/lidar_measurement_model_beam.cpp:145). */
+typedef struct
+{
+  float px, py, pz, _pad;
+  float qx, qy, qz, qw;
+} mcl3dl_pose;
+
+/* LidarMeasurementModelLikelihoodParameters (include/mcl_3dl/parameters.h:64-89) fields used by
+ * LidarMeasurementModelLikelihood::measure (src/lidar_measurement_model_likelihood.cpp:105-139)
+ * plus the kd-tree metric rescale (src/mcl_3dl.cpp:1270, Parameters::dist_weight_). */
+typedef struct
+{
+  float match_weight;
+  float match_dist_min;
+  float match_dist_flat;
+  float dist_weight[3]; /* (1,1,1) == no PointRepresentation rescale */
+} mcl3dl_lik_params;
+
+/* What LidarMeasurementModelBeam::refreshParameters (src/lidar_measurement_model_beam.cpp:58-80)
+ * derives and hands to RaycastUsingDDA's constructor (raycast_using_dda.h:56-64).  The doubles are
+ * doubles because the constructor takes doubles (the node passes floats promoted to double).
+ * Fill it with mcl3dl_beam_params_from_reference() to get the exact same derivation. */
+typedef struct
+{
+  double map_grid_size[3]; /* ctor args 1-3 -> min_dist_thr_sq_ (uses y twice, :59) */
+  double dda_grid_size;    /* ctor arg 4 */
+  double ray_angle_half;   /* ctor arg 5 */
+  double hit_tolerance;    /* ctor arg 6 (= hit_range_) */
+  float hit_range_sq;      /* hit_range_sq_ = pow(hit_range_,2) stored as float (:64) */
+  float sin_total_ref;     /* sinf(ang_total_ref_) (:66) */
+  float beam_likelihood;   /* pow(beam_likelihood_min_, 1/num_points_default) (:65) */
+  float beam_likelihood_min;
+  uint32_t filter_label_max;
+  int32_t add_penalty_short_only_mode;
+} mcl3dl_beam_params;
+
+/* Per-particle result record (24 B).
+ *   likelihood model : LidarMeasurementResult{score_like, match_cnt / (float)n_lik}
+ *   beam model       : LidarMeasurementResult{score_beam, 1.0f}
+ * n_short/n_hit/n_long are the BeamStatus tallies (lidar_measurement_model_beam.h:64-70) over the
+ * particle's rays; TOTAL_REFLECTION = n_beam - (n_short+n_hit+n_long).  They are the bit-exact
+ * contract of the beam kernel. */
+typedef struct
+{
+  float score_like;
+  uint32_t match_cnt;
+  float score_beam;
+  uint32_t n_short;
+  uint32_t n_hit;
+  uint32_t n_long;
+} mcl3dl_result;
+
+/* Sizes / footprint of the staged map (for logging, tests and the roofline arithmetic). */
+typedef struct
+{
+  uint64_t n_points;
+  int32_t nn_dims[3];    /* likelihood search grid (rescaled space), cells per axis */
+  float nn_cell;         /* cell edge in the rescaled space */
+  float nn_origin[3];
+  int32_t dda_dims[3];   /* RaycastUsingDDA::map_size_ */
+  float dda_min[3];      /* min_p_ */
+  float dda_max[3];      /* max_p_ */
+  uint64_t device_bytes; /* per device */
+  double build_ms;       /* device build time of the last set_map */
+} mcl3dl_map_info;
+
+typedef struct mcl3dl_engine mcl3dl_engine;
+
+/* Create an engine on the given CUDA devices (n_devices >= 1; device_ids == NULL means 0..n-1).
+ * Particles of one measure() call are split into n_devices contiguous blocks; the map is replicated. */
+int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices);
+void mcl3dl_destroy(mcl3dl_engine*);
+
+/* The "setMap" event.  Replaces ChunkedKdtree::setInputCloud (include/mcl_3dl/chunked_kdtree.h:124-216)
+ * and RaycastUsingDDA::updatePointCloud (raycast_using_dda.h:162-190): builds, on every device,
+ * the exact-nearest-neighbour cell grid (likelihood) and the DDA occupancy bits + per-cell point
+ * lists in map order (beam).  `stamp` is the cloud's header.stamp, the reference's rebuild trigger
+ * (raycast_using_dda.h:168); calling again with the same stamp and n is a no-op.
+ * Either params pointer may be NULL if that model is never used.  pts are only read during the call. */
+int mcl3dl_set_map(mcl3dl_engine*, const mcl3dl_point* pts, size_t n, uint64_t stamp,
+                   const mcl3dl_lik_params* lik, const mcl3dl_beam_params* beam);
+
+/* Scalar parameters may change between updates without restaging the map
+ * (refreshParameters(), lidar_measurement_model_likelihood.cpp:56-61 / _beam.cpp:58-80), as long as
+ * match_dist_min, dist_weight and dda_grid_size are unchanged; otherwise returns INVALID_ARG. */
+int mcl3dl_set_params(mcl3dl_engine*, const mcl3dl_lik_params* lik, const mcl3dl_beam_params* beam);
+
+/* One measurement update for P particles: replaces the P x {beam, likelihood} calls
+ *   lm.second->measure(kdtree_, pc_locals[name], origins, s)     (src/mcl_3dl.cpp:409-415)
+ * that pf::ParticleFilter::measure makes one particle at a time (include/mcl_3dl/pf.h:256-260).
+ * All pointers are HOST pointers; the call is synchronous and `out[0..P)` is valid on return.
+ *   n_lik  == 0 -> score_like = 1, match_cnt = 0   (likelihood.cpp:111-114, quality 0)
+ *   n_beam == 0 -> score_beam = 1, counts 0        (beam.cpp:130-133)
+ *   beam_pts[i].label indexes origins (beam.cpp:142); out of range -> MCL3DL_ERR_INVALID_ARG. */
+int mcl3dl_measure(mcl3dl_engine*, const mcl3dl_pose* poses, size_t n_particles,
+                   const mcl3dl_point* lik_pts, size_t n_lik,
+                   const mcl3dl_point* beam_pts, size_t n_beam,
+                   const float* origins_xyz, size_t n_origins,
+                   mcl3dl_result* out);
+
+/* Same computation with every buffer already resident on engine device 0 (DEVICE pointers) and
+ * the kernels enqueued on the caller's CUDA stream (a cudaStream_t cast to void*, NULL = legacy
+ * default stream); asynchronous.  Used by the bench's device-resident arm and by callers that
+ * all-gather the records with NCCL before reading them.  Single-device engines only. */
+int mcl3dl_measure_device(mcl3dl_engine*, const mcl3dl_pose* d_poses, size_t n_particles,
+                          const mcl3dl_point* d_lik_pts, size_t n_lik,
+                          const mcl3dl_point* d_beam_pts, size_t n_beam,
+                          const float* d_origins_xyz, size_t n_origins,
+                          mcl3dl_result* d_out, void* cuda_stream);
+
+/* Derive mcl3dl_beam_params exactly as LidarMeasurementModelBeam::refreshParameters does from
+ * LidarMeasurementModelBeamParameters (include/mcl_3dl/parameters.h:91-132). */
+void mcl3dl_beam_params_from_reference(mcl3dl_beam_params* out,
+                                       float map_grid_x, float map_grid_y, float map_grid_z,
+                                       size_t num_points_default, float beam_likelihood_min,
+                                       float ang_total_ref, uint32_t filter_label_max, float hit_range,
+                                       int add_penalty_short_only_mode,
+                                       float ray_angle_half, float dda_grid_size);
+
+int mcl3dl_get_map_info(const mcl3dl_engine*, mcl3dl_map_info* out);
+
+/* Device times of the last mcl3dl_measure call (CUDA events on the engine's stream, max over
+ * devices): host->device copies, the two kernels, device->host copy. */
+int mcl3dl_last_timing(const mcl3dl_engine*, double* h2d_ms, double* lik_kernel_ms, double* beam_kernel_ms,
+                       double* d2h_ms);
+
+/* Number of this library's kernels launched since create (the bench's gpu_launches counter). */
+uint64_t mcl3dl_kernel_launches(const mcl3dl_engine*);
+
+const char* mcl3dl_strerror(int code);
+/* Text of the last CUDA failure seen by this engine ("" if none). */
+const char* mcl3dl_last_error_detail(const mcl3dl_engine*);
+int mcl3dl_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCL3DL_B200_H */

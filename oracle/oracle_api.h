@@ -1,0 +1,87 @@
+/*
+ * oracle_api.h — C ABI shared by the two CPU checkers.  TEST INFRASTRUCTURE ONLY.
+ *
+ *   oracle/libmcl3dl_oracle.so      "port"      : repo-owned restatement (oracle/mcl3dl_oracle.cpp)
+ *   oracle/_ref/libmcl3dl_ref.so    "reference" : the reference's own unmodified sources compiled
+ *                                                 against oracle/shim/ (oracle/ref_driver.cpp)
+ *
+ * Both export exactly these symbols so tests can run the same vectors through either.  Nothing
+ * in the product path (mcl_3dl_b200/) may include, link or load this.
+ */
+#ifndef MCL3DL_ORACLE_API_H
+#define MCL3DL_ORACLE_API_H
+
+#include "../include/mcl3dl_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* LidarMeasurementModelBeamParameters as the node fills it (include/mcl_3dl/parameters.h:91-132). */
+typedef struct
+{
+  float map_grid_x, map_grid_y, map_grid_z;
+  uint64_t num_points_default;
+  float beam_likelihood_min;
+  float ang_total_ref;
+  uint32_t filter_label_max;
+  float hit_range;
+  int32_t add_penalty_short_only_mode;
+  int32_t use_raycast_using_dda; /* must be 1 for parity with the GPU beam kernel */
+  float ray_angle_half;
+  float dda_grid_size;
+} mcl3dl_cpu_beam_raw;
+
+typedef struct mcl3dl_cpu mcl3dl_cpu;
+
+const char* mcl3dl_cpu_kind(void); /* "port" or "reference" */
+
+/* Build the CPU map index (ChunkedKdtree(chunk_length, max_search_radius) + setInputCloud, and a
+ * LidarMeasurementModelBeam / Likelihood pair).  lik or beam may be NULL -> reference defaults. */
+mcl3dl_cpu* mcl3dl_cpu_create(const mcl3dl_point* pts, size_t n, const mcl3dl_lik_params* lik,
+                              const mcl3dl_cpu_beam_raw* beam, float chunk_length, float max_search_radius);
+void mcl3dl_cpu_destroy(mcl3dl_cpu*);
+
+/* pf.measure()'s per-particle body (mcl_3dl.cpp:409-415) for P particles; n_threads > 1 is the
+ * "not reference behaviour" all-core variant (one raycaster per thread). */
+int mcl3dl_cpu_measure(mcl3dl_cpu*, const mcl3dl_pose* poses, size_t n_particles,
+                       const mcl3dl_point* lik_pts, size_t n_lik,
+                       const mcl3dl_point* beam_pts, size_t n_beam,
+                       const float* origins_xyz, size_t n_origins, mcl3dl_result* out, int n_threads);
+
+/* enable (default) / disable the extra per-ray getBeamStatus pass that fills n_short/n_hit/n_long;
+ * bench.py disables it so the timed CPU work is exactly pf.measure()'s. */
+int mcl3dl_cpu_set_tally(mcl3dl_cpu*, int enable);
+
+/* BeamStatus per (particle, ray), row-major [P][n_beam]: 0 SHORT, 1 HIT, 2 LONG, 3 TOTAL_REFLECTION. */
+int mcl3dl_cpu_beam_status(mcl3dl_cpu*, const mcl3dl_pose* poses, size_t n_particles,
+                           const mcl3dl_point* beam_pts, size_t n_beam,
+                           const float* origins_xyz, size_t n_origins, uint8_t* status);
+
+/* The derived beam parameters (refreshParameters) this checker uses. */
+int mcl3dl_cpu_beam_params(mcl3dl_cpu*, mcl3dl_beam_params* out);
+
+/* ChunkedKdtree::radiusSearch(q, radius, id, d2, 1) -> original id or -1; *d2 in the rescaled space. */
+int mcl3dl_cpu_radius_search(mcl3dl_cpu*, const float q[3], float radius, float* d2);
+
+/* Stand-alone RaycastUsingDDA<PointXYZ>(gx,gy,gz,dda,ray_angle_half,hit_tol) over
+ * ChunkedKdtree(10.0, 1.0): setRay(begin,end) then getNextCastResult until exhausted
+ * (or until the first collision when stop_at_collision).  Writes voxel centres (3 floats each) and
+ * collision flags; returns the number of cast results (<= max_out) or <0 on error.
+ * collided_id (may be NULL) receives the map index of the first colliding point or -1. */
+int mcl3dl_cpu_dda_walk(const mcl3dl_point* pts, size_t n, const double ctor[6],
+                        const float begin[3], const float end[3], int stop_at_collision,
+                        float* centres, uint8_t* collision, int max_out, int* collided_id);
+
+/* Quat * Vec3 (quat.h:139-143) and State6DOF::transform of one point (state_6dof.h:214-225). */
+void mcl3dl_cpu_quat_rotate(const float q[4], const float v[3], float out[3]);
+void mcl3dl_cpu_transform_point(const mcl3dl_pose* pose, const float v[3], float out[3]);
+
+/* pf::ParticleFilter::measure's weight update (pf.h:252-279) given per-particle likelihood values:
+ * prob[i] *= lik[i]; normalise; entropy; returns 1 if sum > 0 else 0 (restore -> prob untouched). */
+int mcl3dl_cpu_pf_update(float* prob, const float* lik, size_t n, float* entropy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,4 @@
+#ifndef ORACLE_SHIM_PCL_ROS_POINT_CLOUD_H
+#define ORACLE_SHIM_PCL_ROS_POINT_CLOUD_H
+#include <pcl/point_cloud.h>
+#endif
