@@ -157,6 +157,13 @@ int mcl3dl_measure_device(mcl3dl_engine*, const mcl3dl_pose* d_poses, size_t n_p
                           const float* d_origins_xyz, size_t n_origins,
                           mcl3dl_result* d_out, void* cuda_stream);
 
+/* Batched LidarMeasurementModelBeam::getBeamStatus (src/lidar_measurement_model_beam.cpp:157-192; the
+ * node calls it for the mean pose's rays to colour its rviz markers, src/mcl_3dl.cpp:471-478).
+ * status is row-major [n_particles][n_beam]: 0 SHORT, 1 HIT, 2 LONG, 3 TOTAL_REFLECTION (HOST buffers). */
+int mcl3dl_beam_status(mcl3dl_engine*, const mcl3dl_pose* poses, size_t n_particles,
+                       const mcl3dl_point* beam_pts, size_t n_beam,
+                       const float* origins_xyz, size_t n_origins, uint8_t* status);
+
 /* Derive mcl3dl_beam_params exactly as LidarMeasurementModelBeam::refreshParameters does from
  * LidarMeasurementModelBeamParameters (include/mcl_3dl/parameters.h:91-132). */
 void mcl3dl_beam_params_from_reference(mcl3dl_beam_params* out,

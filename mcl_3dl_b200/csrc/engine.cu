@@ -1,0 +1,971 @@
+// engine.cu — host side of the C ABI (include/mcl3dl_b200.h): map staging on the device, the
+// per-update launch sequence, multi-device sharding.  No CPU compute path exists here: every entry
+// point either runs on a CUDA device or fails with an error code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "kernels.cuh"
+
+using namespace mcl3dl;
+
+namespace
+{
+constexpr int kMaxStagedBytes = 200 * 1024;
+
+// ---------------------------------------------------------------- device build kernels
+__device__ __forceinline__ uint32_t f2ord(float f)
+{
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+inline float ord2f(uint32_t o)
+{
+  const uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  float f;
+  std::memcpy(&f, &b, 4);
+  return f;
+}
+
+// bbox[0..2] = min raw, [3..5] = max raw, [6..8] = min rescaled, [9..11] = max rescaled (ordered-uint encoding)
+__global__ void bbox_kernel(const mcl3dl_point* __restrict__ pts, size_t n, float wx, float wy, float wz,
+                            uint32_t* __restrict__ bbox)
+{
+  float mn[6], mx[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+  {
+    mn[k] = __int_as_float(0x7f800000);
+    mx[k] = __int_as_float(0xff800000);
+  }
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+  {
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pts) + i);
+    const float v[6] = {p.x, p.y, p.z, fmul(p.x, wx), fmul(p.y, wy), fmul(p.z, wz)};
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+    {
+      mn[k] = fminf(mn[k], v[k]);
+      mx[k] = fmaxf(mx[k], v[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+  {
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+      mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0)
+  {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+      atomicMin(bbox + k, f2ord(mn[k]));
+      atomicMax(bbox + 3 + k, f2ord(mx[k]));
+      atomicMin(bbox + 6 + k, f2ord(mn[3 + k]));
+      atomicMax(bbox + 9 + k, f2ord(mx[3 + k]));
+    }
+  }
+}
+
+// Likelihood grid: cell of a rescaled point.  MUST stay the same expression as nn_dist2's window bounds.
+__global__ void nn_key_kernel(const mcl3dl_point* __restrict__ pts, uint32_t n, NnGridDev g,
+                              uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                              uint32_t* __restrict__ counts)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const float4 p = __ldg(reinterpret_cast<const float4*>(pts) + i);
+  int cx = __float2int_rd(fmul(fsub(fmul(p.x, g.wx), g.ox), g.inv_cell));
+  int cy = __float2int_rd(fmul(fsub(fmul(p.y, g.wy), g.oy), g.inv_cell));
+  int cz = __float2int_rd(fmul(fsub(fmul(p.z, g.wz), g.oz), g.inv_cell));
+  cx = min(max(cx, 0), g.nx - 1);
+  cy = min(max(cy, 0), g.ny - 1);
+  cz = min(max(cz, 0), g.nz - 1);
+  const uint32_t c = static_cast<uint32_t>((cz * g.ny + cy) * g.nx + cx);
+  keys[i] = c;
+  vals[i] = i;
+  atomicAdd(counts + c + 1, 1u);
+}
+
+__global__ void nn_gather_kernel(const mcl3dl_point* __restrict__ pts, uint32_t n, const uint32_t* __restrict__ order,
+                                 float wx, float wy, float wz, float4* __restrict__ out)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n)
+    return;
+  const uint32_t i = order[k];
+  const float4 p = __ldg(reinterpret_cast<const float4*>(pts) + i);
+  out[k] = make_float4(fmul(p.x, wx), fmul(p.y, wy), fmul(p.z, wz), __uint_as_float(i));
+}
+
+// DDA grid: RaycastUsingDDA::setExists (raycast_using_dda.h:230-235) for every map point.
+__global__ void dda_key_kernel(const mcl3dl_point* __restrict__ pts, uint32_t n, DdaGridDev g,
+                               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                               uint32_t* __restrict__ counts, uint32_t* __restrict__ occ)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const float4 p = __ldg(reinterpret_cast<const float4*>(pts) + i);
+  const int cx = dda_to_index(p.x, g.min_x, g.grid);
+  const int cy = dda_to_index(p.y, g.min_y, g.grid);
+  const int cz = dda_to_index(p.z, g.min_z, g.grid);
+  const uint32_t c = static_cast<uint32_t>(cx + cy * g.nx + cz * (g.nx * g.ny));
+  keys[i] = c;
+  vals[i] = i;
+  atomicAdd(counts + c + 1, 1u);
+  atomicOr(occ + (c >> 5), 1u << (c & 31));
+}
+
+__global__ void dda_gather_kernel(const mcl3dl_point* __restrict__ pts, uint32_t n, const uint32_t* __restrict__ order,
+                                  float4* __restrict__ out)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n)
+    return;
+  out[k] = __ldg(reinterpret_cast<const float4*>(pts) + order[k]);  // xyz + label bits, map order kept by the stable sort
+}
+
+__global__ void pack_origins_kernel(const float* __restrict__ xyz, int n, float4* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0f);
+}
+
+struct DevBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct DeviceCtx
+{
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  // map
+  DevBuf nn_cell_start, nn_pts, dda_occ, dda_cell_start, dda_pts;
+  NnGridDev nn{};
+  DdaGridDev dda{};
+  size_t map_bytes = 0;
+  // per-update I/O
+  DevBuf d_poses, d_lik, d_beam, d_origins_raw, d_origins, d_out, d_status;
+  void* h_pinned = nullptr;
+  size_t h_pinned_cap = 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+}  // namespace
+
+struct mcl3dl_engine
+{
+  std::vector<DeviceCtx> devs;
+  bool has_map = false;
+  bool has_lik = false, has_beam = false;
+  uint64_t stamp = 0;
+  size_t n_points = 0;
+  mcl3dl_lik_params lik{};
+  mcl3dl_beam_params beam{};
+  LikDev likdev{};
+  mcl3dl_map_info info{};
+  double t_h2d = 0, t_lik = 0, t_beam = 0, t_d2h = 0;
+  uint64_t launches = 0;
+  std::string err;
+  float nn_cell_factor = 1.0f;
+};
+
+namespace
+{
+#define CK(call)                                                                                     \
+  do                                                                                                 \
+  {                                                                                                  \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+    {                                                                                                \
+      eng->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"; \
+      return MCL3DL_ERR_CUDA;                                                                        \
+    }                                                                                                \
+  } while (0)
+
+int reserve(mcl3dl_engine* eng, DevBuf& b, size_t bytes)
+{
+  if (bytes <= b.cap && b.p)
+    return MCL3DL_OK;
+  if (b.p)
+    CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = std::max<size_t>(bytes, 256);
+  CK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return MCL3DL_OK;
+}
+
+int reserve_pinned(mcl3dl_engine* eng, DeviceCtx& c, size_t bytes)
+{
+  if (bytes <= c.h_pinned_cap)
+    return MCL3DL_OK;
+  if (c.h_pinned)
+    CK(cudaFreeHost(c.h_pinned));
+  c.h_pinned = nullptr;
+  c.h_pinned_cap = 0;
+  CK(cudaMallocHost(&c.h_pinned, bytes));
+  c.h_pinned_cap = bytes;
+  return MCL3DL_OK;
+}
+
+void free_buf(DevBuf& b)
+{
+  if (b.p)
+    cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+int pick_tpp(size_t P, size_t N, int sm_count)
+{
+  // Enough threads to fill the chip (>= ~1024 per SM) but never more lanes than points.
+  int tpp = 32;
+  while (tpp < kBlockThreads && P * static_cast<size_t>(tpp) < static_cast<size_t>(sm_count) * 1024 &&
+         static_cast<size_t>(tpp) < N)
+    tpp *= 2;
+  return tpp;
+}
+
+template <int TPP>
+int launch_lik_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int P, const float4* scan, int N,
+                 mcl3dl_result* out, int beam_defaults, cudaStream_t st)
+{
+  constexpr int PPB = kBlockThreads / TPP;
+  const int groups = (P + PPB - 1) / PPB;
+  const int grid = std::max(1, std::min(groups, c.sm_count * 8));
+  const size_t bytes = static_cast<size_t>(N) * 16;
+  if (bytes <= static_cast<size_t>(kMaxStagedBytes))
+  {
+    CK(cudaFuncSetAttribute(lik_kernel<TPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStagedBytes));
+    lik_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults);
+  }
+  else
+  {
+    lik_kernel<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults);
+  }
+  CK(cudaGetLastError());
+  eng->launches++;
+  return MCL3DL_OK;
+}
+
+template <int TPP>
+int launch_beam_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int P, const float4* scan, int N,
+                  const float4* origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
+{
+  constexpr int PPB = kBlockThreads / TPP;
+  const int groups = (P + PPB - 1) / PPB;
+  const int grid = std::max(1, std::min(groups, c.sm_count * 8));
+  const size_t bytes = static_cast<size_t>(N) * 16;
+  if (bytes <= static_cast<size_t>(kMaxStagedBytes))
+  {
+    CK(cudaFuncSetAttribute(beam_kernel<TPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStagedBytes));
+    beam_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, origins, c.dda, out, status, lik_defaults);
+  }
+  else
+  {
+    beam_kernel<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, origins, c.dda, out, status, lik_defaults);
+  }
+  CK(cudaGetLastError());
+  eng->launches++;
+  return MCL3DL_OK;
+}
+
+int launch_lik(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
+               mcl3dl_result* out, int beam_defaults, cudaStream_t st)
+{
+  const float4* s4 = reinterpret_cast<const float4*>(scan);
+  switch (pick_tpp(P, N, c.sm_count))
+  {
+    case 32: return launch_lik_t<32>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), out, beam_defaults, st);
+    case 64: return launch_lik_t<64>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), out, beam_defaults, st);
+    case 128: return launch_lik_t<128>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), out, beam_defaults, st);
+    default: return launch_lik_t<256>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), out, beam_defaults, st);
+  }
+}
+
+int launch_beam(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
+                const float4* origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
+{
+  const float4* s4 = reinterpret_cast<const float4*>(scan);
+  switch (pick_tpp(P, N, c.sm_count))
+  {
+    case 32: return launch_beam_t<32>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), origins, out, status, lik_defaults, st);
+    case 64: return launch_beam_t<64>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), origins, out, status, lik_defaults, st);
+    case 128: return launch_beam_t<128>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), origins, out, status, lik_defaults, st);
+    default: return launch_beam_t<256>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), origins, out, status, lik_defaults, st);
+  }
+}
+
+void derive_lik(mcl3dl_engine* eng)
+{
+  const float R = eng->lik.match_dist_min;
+  eng->likdev.match_dist_min = R;
+  eng->likdev.match_dist_flat = eng->lik.match_dist_flat;
+  eng->likdev.match_weight = eng->lik.match_weight;
+  eng->likdev.r2 = static_cast<float>(static_cast<double>(R) * static_cast<double>(R));
+  eng->likdev.rpad = R * 1.0001f + 1e-6f;
+}
+
+void fill_dda_scalars(const mcl3dl_beam_params& b, DdaGridDev& g)
+{
+  g.grid = b.dda_grid_size;
+  g.ray_angle_half = b.ray_angle_half;
+  // ctor, raycast_using_dda.h:59 — y is used twice, as the reference does
+  g.min_dist_thr_sq = b.map_grid_size[0] * b.map_grid_size[0] + b.map_grid_size[1] * b.map_grid_size[1] +
+                      b.map_grid_size[1] * b.map_grid_size[1];
+  g.hit_tolerance = static_cast<float>(b.hit_tolerance);
+  g.hit_range_sq = b.hit_range_sq;
+  g.sin_total_ref = b.sin_total_ref;
+  g.beam_likelihood = b.beam_likelihood;
+  g.beam_likelihood_min = b.beam_likelihood_min;
+  g.filter_label_max = b.filter_label_max;
+  g.short_only = b.add_penalty_short_only_mode ? 1 : 0;
+}
+
+// Build both grids on one device from the uploaded points.
+int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_pts, size_t n)
+{
+  CK(cudaSetDevice(c.dev));
+  cudaStream_t st = c.stream;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  DevBuf d_pts, d_bbox, d_keys, d_vals, d_keys2, d_vals2, d_tmp;
+  int rc = MCL3DL_OK;
+  auto cleanup = [&]() {
+    free_buf(d_pts);
+    free_buf(d_bbox);
+    free_buf(d_keys);
+    free_buf(d_vals);
+    free_buf(d_keys2);
+    free_buf(d_vals2);
+    free_buf(d_tmp);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  };
+#define CKB(x)            \
+  do                      \
+  {                       \
+    rc = (x);             \
+    if (rc != MCL3DL_OK)  \
+    {                     \
+      cleanup();          \
+      return rc;          \
+    }                     \
+  } while (0)
+#define CKC(call)                                                                       \
+  do                                                                                    \
+  {                                                                                     \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess)                                                             \
+    {                                                                                   \
+      eng->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+      cleanup();                                                                        \
+      return MCL3DL_ERR_CUDA;                                                           \
+    }                                                                                   \
+  } while (0)
+
+  const uint32_t n32 = static_cast<uint32_t>(n);
+  const int tb = 256;
+  const int nb = static_cast<int>((n + tb - 1) / tb);
+  CKB(reserve(eng, d_pts, n * sizeof(mcl3dl_point)));
+  CKB(reserve(eng, d_bbox, 12 * sizeof(uint32_t)));
+  CKB(reserve(eng, d_keys, n * 4));
+  CKB(reserve(eng, d_vals, n * 4));
+  CKB(reserve(eng, d_keys2, n * 4));
+  CKB(reserve(eng, d_vals2, n * 4));
+  CKC(cudaMemcpyAsync(d_pts.p, h_pts, n * sizeof(mcl3dl_point), cudaMemcpyHostToDevice, st));
+  CKC(cudaEventRecord(e0, st));
+  const mcl3dl_point* pts = static_cast<const mcl3dl_point*>(d_pts.p);
+
+  // ---- bounding boxes (raw: pcl::getMinMax3D, raycast_using_dda.h:175; rescaled: likelihood grid)
+  uint32_t h_bbox[12];
+  for (int k = 0; k < 3; ++k)
+  {
+    h_bbox[k] = 0xffffffffu;
+    h_bbox[3 + k] = 0u;
+    h_bbox[6 + k] = 0xffffffffu;
+    h_bbox[9 + k] = 0u;
+  }
+  CKC(cudaMemcpyAsync(d_bbox.p, h_bbox, sizeof(h_bbox), cudaMemcpyHostToDevice, st));
+  const float wx = eng->has_lik ? eng->lik.dist_weight[0] : 1.0f;
+  const float wy = eng->has_lik ? eng->lik.dist_weight[1] : 1.0f;
+  const float wz = eng->has_lik ? eng->lik.dist_weight[2] : 1.0f;
+  bbox_kernel<<<std::min(nb, c.sm_count * 8), tb, 0, st>>>(pts, n, wx, wy, wz, static_cast<uint32_t*>(d_bbox.p));
+  CKC(cudaGetLastError());
+  eng->launches++;
+  CKC(cudaMemcpyAsync(h_bbox, d_bbox.p, sizeof(h_bbox), cudaMemcpyDeviceToHost, st));
+  CKC(cudaStreamSynchronize(st));
+  float raw_min[3], raw_max[3], sc_min[3], sc_max[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    raw_min[k] = ord2f(h_bbox[k]);
+    raw_max[k] = ord2f(h_bbox[3 + k]);
+    sc_min[k] = ord2f(h_bbox[6 + k]);
+    sc_max[k] = ord2f(h_bbox[9 + k]);
+  }
+  c.map_bytes = 0;
+
+  // ---- likelihood search grid
+  if (eng->has_lik)
+  {
+    NnGridDev g{};
+    const float cell = eng->lik.match_dist_min * eng->nn_cell_factor;
+    if (!(cell > 0.0f))
+    {
+      cleanup();
+      return MCL3DL_ERR_INVALID_ARG;
+    }
+    g.inv_cell = 1.0f / cell;
+    g.wx = wx;
+    g.wy = wy;
+    g.wz = wz;
+    int64_t total = 1;
+    int dims[3];
+    float org[3];
+    for (int k = 0; k < 3; ++k)
+    {
+      org[k] = sc_min[k] - 0.5f * cell;
+      dims[k] = static_cast<int>(std::floor((static_cast<double>(sc_max[k]) - org[k]) / cell)) + 2;
+      total *= dims[k];
+    }
+    if (total >= (int64_t(1) << 31))
+    {
+      cleanup();
+      return MCL3DL_ERR_TOO_LARGE;
+    }
+    g.nx = dims[0];
+    g.ny = dims[1];
+    g.nz = dims[2];
+    g.ox = org[0];
+    g.oy = org[1];
+    g.oz = org[2];
+    const size_t cells = static_cast<size_t>(total);
+    CKB(reserve(eng, c.nn_cell_start, (cells + 1) * 4));
+    CKB(reserve(eng, c.nn_pts, n * 16));
+    CKC(cudaMemsetAsync(c.nn_cell_start.p, 0, (cells + 1) * 4, st));
+    nn_key_kernel<<<nb, tb, 0, st>>>(pts, n32, g, static_cast<uint32_t*>(d_keys.p), static_cast<uint32_t*>(d_vals.p),
+                                     static_cast<uint32_t*>(c.nn_cell_start.p));
+    CKC(cudaGetLastError());
+    eng->launches++;
+    size_t tmp_sort = 0, tmp_scan = 0;
+    int end_bit = 1;
+    while ((int64_t(1) << end_bit) < total && end_bit < 32) ++end_bit;
+    CKC(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, static_cast<uint32_t*>(d_keys.p),
+                                        static_cast<uint32_t*>(d_keys2.p), static_cast<uint32_t*>(d_vals.p),
+                                        static_cast<uint32_t*>(d_vals2.p), n32, 0, end_bit, st));
+    CKC(cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, static_cast<uint32_t*>(c.nn_cell_start.p),
+                                      static_cast<uint32_t*>(c.nn_cell_start.p), static_cast<int>(cells + 1), st));
+    CKB(reserve(eng, d_tmp, std::max(tmp_sort, tmp_scan)));
+    size_t tsz = d_tmp.cap;
+    CKC(cub::DeviceRadixSort::SortPairs(d_tmp.p, tsz, static_cast<uint32_t*>(d_keys.p), static_cast<uint32_t*>(d_keys2.p),
+                                        static_cast<uint32_t*>(d_vals.p), static_cast<uint32_t*>(d_vals2.p), n32, 0,
+                                        end_bit, st));
+    tsz = d_tmp.cap;
+    CKC(cub::DeviceScan::InclusiveSum(d_tmp.p, tsz, static_cast<uint32_t*>(c.nn_cell_start.p),
+                                      static_cast<uint32_t*>(c.nn_cell_start.p), static_cast<int>(cells + 1), st));
+    nn_gather_kernel<<<nb, tb, 0, st>>>(pts, n32, static_cast<uint32_t*>(d_vals2.p), wx, wy, wz,
+                                        static_cast<float4*>(c.nn_pts.p));
+    CKC(cudaGetLastError());
+    eng->launches += 3;
+    g.cell_start = static_cast<const uint32_t*>(c.nn_cell_start.p);
+    g.pts = static_cast<const float4*>(c.nn_pts.p);
+    c.nn = g;
+    c.map_bytes += (cells + 1) * 4 + n * 16;
+    eng->info.nn_dims[0] = g.nx;
+    eng->info.nn_dims[1] = g.ny;
+    eng->info.nn_dims[2] = g.nz;
+    eng->info.nn_cell = cell;
+    eng->info.nn_origin[0] = g.ox;
+    eng->info.nn_origin[1] = g.oy;
+    eng->info.nn_origin[2] = g.oz;
+  }
+
+  // ---- DDA grid: updatePointCloud, raycast_using_dda.h:162-190
+  if (eng->has_beam)
+  {
+    DdaGridDev g{};
+    fill_dda_scalars(eng->beam, g);
+    if (!(g.grid > 0.0))
+    {
+      cleanup();
+      return MCL3DL_ERR_INVALID_ARG;
+    }
+    int64_t total = 1;
+    int dims[3];
+    for (int k = 0; k < 3; ++k)
+    {
+      // map_size_[i] = static_cast<size_t>((max_p_[i] - min_p_[i]) / dda_grid_size_) + 1  (:179)
+      const float diff = raw_max[k] - raw_min[k];
+      dims[k] = static_cast<int>(static_cast<size_t>(static_cast<double>(diff) / g.grid) + 1);
+      total *= dims[k];
+    }
+    if (total >= (int64_t(1) << 31))  // `int point_total` (:176)
+    {
+      cleanup();
+      return MCL3DL_ERR_TOO_LARGE;
+    }
+    g.nx = dims[0];
+    g.ny = dims[1];
+    g.nz = dims[2];
+    g.min_x = raw_min[0];
+    g.min_y = raw_min[1];
+    g.min_z = raw_min[2];
+    g.max_x = raw_max[0];
+    g.max_y = raw_max[1];
+    g.max_z = raw_max[2];
+    const size_t cells = static_cast<size_t>(total);
+    const size_t occ_words = (cells + 31) / 32 + 1;
+    CKB(reserve(eng, c.dda_cell_start, (cells + 2) * 4));
+    CKB(reserve(eng, c.dda_occ, occ_words * 4));
+    CKB(reserve(eng, c.dda_pts, n * 16));
+    CKC(cudaMemsetAsync(c.dda_cell_start.p, 0, (cells + 2) * 4, st));
+    CKC(cudaMemsetAsync(c.dda_occ.p, 0, occ_words * 4, st));
+    dda_key_kernel<<<nb, tb, 0, st>>>(pts, n32, g, static_cast<uint32_t*>(d_keys.p), static_cast<uint32_t*>(d_vals.p),
+                                      static_cast<uint32_t*>(c.dda_cell_start.p), static_cast<uint32_t*>(c.dda_occ.p));
+    CKC(cudaGetLastError());
+    size_t tmp_sort = 0, tmp_scan = 0;
+    int end_bit = 1;
+    while ((int64_t(1) << end_bit) < total && end_bit < 32) ++end_bit;
+    CKC(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, static_cast<uint32_t*>(d_keys.p),
+                                        static_cast<uint32_t*>(d_keys2.p), static_cast<uint32_t*>(d_vals.p),
+                                        static_cast<uint32_t*>(d_vals2.p), n32, 0, end_bit, st));
+    CKC(cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, static_cast<uint32_t*>(c.dda_cell_start.p),
+                                      static_cast<uint32_t*>(c.dda_cell_start.p), static_cast<int>(cells + 1), st));
+    CKB(reserve(eng, d_tmp, std::max(tmp_sort, tmp_scan)));
+    size_t tsz = d_tmp.cap;
+    CKC(cub::DeviceRadixSort::SortPairs(d_tmp.p, tsz, static_cast<uint32_t*>(d_keys.p), static_cast<uint32_t*>(d_keys2.p),
+                                        static_cast<uint32_t*>(d_vals.p), static_cast<uint32_t*>(d_vals2.p), n32, 0,
+                                        end_bit, st));
+    tsz = d_tmp.cap;
+    CKC(cub::DeviceScan::InclusiveSum(d_tmp.p, tsz, static_cast<uint32_t*>(c.dda_cell_start.p),
+                                      static_cast<uint32_t*>(c.dda_cell_start.p), static_cast<int>(cells + 1), st));
+    dda_gather_kernel<<<nb, tb, 0, st>>>(pts, n32, static_cast<uint32_t*>(d_vals2.p), static_cast<float4*>(c.dda_pts.p));
+    CKC(cudaGetLastError());
+    eng->launches += 4;
+    g.occ = static_cast<const uint32_t*>(c.dda_occ.p);
+    g.cell_start = static_cast<const uint32_t*>(c.dda_cell_start.p);
+    g.pts = static_cast<const float4*>(c.dda_pts.p);
+    c.dda = g;
+    c.map_bytes += (cells + 2) * 4 + occ_words * 4 + n * 16;
+    for (int k = 0; k < 3; ++k) eng->info.dda_dims[k] = dims[k];
+    for (int k = 0; k < 3; ++k)
+    {
+      eng->info.dda_min[k] = raw_min[k];
+      eng->info.dda_max[k] = raw_max[k];
+    }
+  }
+  CKC(cudaEventRecord(e1, st));
+  CKC(cudaStreamSynchronize(st));
+  float ms = 0;
+  CKC(cudaEventElapsedTime(&ms, e0, e1));
+  eng->info.build_ms = std::max(eng->info.build_ms, static_cast<double>(ms));
+  eng->info.device_bytes = c.map_bytes;
+  cleanup();
+  return MCL3DL_OK;
+#undef CKB
+#undef CKC
+}
+}  // namespace
+
+extern "C" {
+
+int mcl3dl_abi_version(void)
+{
+  return MCL3DL_ABI_VERSION;
+}
+
+const char* mcl3dl_strerror(int code)
+{
+  switch (code)
+  {
+    case MCL3DL_OK: return "ok";
+    case MCL3DL_ERR_INVALID_ARG: return "invalid argument";
+    case MCL3DL_ERR_NO_MAP: return "measure() before set_map()";
+    case MCL3DL_ERR_CUDA: return "CUDA runtime error";
+    case MCL3DL_ERR_NO_DEVICE: return "no usable CUDA device";
+    case MCL3DL_ERR_TOO_LARGE: return "grid exceeds 2^31-1 cells";
+    case MCL3DL_ERR_RADIUS: return "search radius exceeds the supported range";
+    default: return "unknown error";
+  }
+}
+
+const char* mcl3dl_last_error_detail(const mcl3dl_engine* eng)
+{
+  return eng ? eng->err.c_str() : "";
+}
+
+uint64_t mcl3dl_kernel_launches(const mcl3dl_engine* eng)
+{
+  return eng ? eng->launches : 0;
+}
+
+int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
+{
+  if (!out || n_devices < 1)
+    return MCL3DL_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1)
+    return MCL3DL_ERR_NO_DEVICE;
+  mcl3dl_engine* eng = new mcl3dl_engine;
+  if (const char* f = std::getenv("MCL3DL_NN_CELL_FACTOR"))
+  {
+    const float v = static_cast<float>(std::atof(f));
+    if (v >= 0.25f && v <= 4.0f)
+      eng->nn_cell_factor = v;
+  }
+  eng->devs.resize(n_devices);
+  for (int i = 0; i < n_devices; ++i)
+  {
+    DeviceCtx& c = eng->devs[i];
+    c.dev = device_ids ? device_ids[i] : i;
+    if (c.dev < 0 || c.dev >= count)
+    {
+      delete eng;
+      return MCL3DL_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(c.dev) != cudaSuccess || cudaGetDeviceProperties(&prop, c.dev) != cudaSuccess ||
+        prop.major < 10)
+    {
+      delete eng;  // built for sm_100a only; anything else cannot run these kernels
+      return MCL3DL_ERR_NO_DEVICE;
+    }
+    c.sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+      delete eng;
+      return MCL3DL_ERR_CUDA;
+    }
+    for (auto& e : c.ev)
+      if (cudaEventCreate(&e) != cudaSuccess)
+      {
+        delete eng;
+        return MCL3DL_ERR_CUDA;
+      }
+  }
+  *out = eng;
+  return MCL3DL_OK;
+}
+
+void mcl3dl_destroy(mcl3dl_engine* eng)
+{
+  if (!eng)
+    return;
+  for (DeviceCtx& c : eng->devs)
+  {
+    cudaSetDevice(c.dev);
+    if (c.stream)
+      cudaStreamSynchronize(c.stream);
+    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.d_poses, &c.d_lik,
+                      &c.d_beam, &c.d_origins_raw, &c.d_origins, &c.d_out, &c.d_status})
+      free_buf(*b);
+    if (c.h_pinned)
+      cudaFreeHost(c.h_pinned);
+    for (auto& e : c.ev)
+      if (e)
+        cudaEventDestroy(e);
+    if (c.stream)
+      cudaStreamDestroy(c.stream);
+  }
+  delete eng;
+}
+
+int mcl3dl_set_map(mcl3dl_engine* eng, const mcl3dl_point* pts, size_t n, uint64_t stamp, const mcl3dl_lik_params* lik,
+                   const mcl3dl_beam_params* beam)
+{
+  if (!eng || !pts || n == 0 || (!lik && !beam))
+    return MCL3DL_ERR_INVALID_ARG;
+  if (n >= (size_t(1) << 31))
+    return MCL3DL_ERR_TOO_LARGE;
+  // the reference's rebuild trigger: same header.stamp (and a non-empty index) -> nothing to do
+  // (raycast_using_dda.h:168)
+  if (eng->has_map && eng->stamp == stamp && eng->n_points == n &&
+      (!lik || (eng->has_lik && std::memcmp(lik, &eng->lik, sizeof(*lik)) == 0)) &&
+      (!beam || (eng->has_beam && std::memcmp(beam, &eng->beam, sizeof(*beam)) == 0)))
+    return MCL3DL_OK;
+  if (lik)
+  {
+    if (!(lik->match_dist_min > 0.0f) || !(lik->dist_weight[0] > 0.0f) || !(lik->dist_weight[1] > 0.0f) ||
+        !(lik->dist_weight[2] > 0.0f))
+      return MCL3DL_ERR_INVALID_ARG;
+    eng->lik = *lik;
+  }
+  if (beam)
+    eng->beam = *beam;
+  eng->has_lik = lik != nullptr;
+  eng->has_beam = beam != nullptr;
+  derive_lik(eng);
+  eng->has_map = false;
+  std::memset(&eng->info, 0, sizeof(eng->info));
+  eng->info.n_points = n;
+  for (DeviceCtx& c : eng->devs)
+  {
+    const int rc = build_map_on_device(eng, c, pts, n);
+    if (rc != MCL3DL_OK)
+      return rc;
+  }
+  eng->has_map = true;
+  eng->stamp = stamp;
+  eng->n_points = n;
+  return MCL3DL_OK;
+}
+
+int mcl3dl_set_params(mcl3dl_engine* eng, const mcl3dl_lik_params* lik, const mcl3dl_beam_params* beam)
+{
+  if (!eng || !eng->has_map)
+    return MCL3DL_ERR_NO_MAP;
+  if (lik)
+  {
+    if (!eng->has_lik || lik->match_dist_min != eng->lik.match_dist_min ||
+        std::memcmp(lik->dist_weight, eng->lik.dist_weight, sizeof(lik->dist_weight)) != 0)
+      return MCL3DL_ERR_INVALID_ARG;  // these fix the staged grid
+    eng->lik = *lik;
+    derive_lik(eng);
+  }
+  if (beam)
+  {
+    if (!eng->has_beam || beam->dda_grid_size != eng->beam.dda_grid_size)
+      return MCL3DL_ERR_INVALID_ARG;
+    eng->beam = *beam;
+    for (DeviceCtx& c : eng->devs) fill_dda_scalars(eng->beam, c.dda);
+  }
+  return MCL3DL_OK;
+}
+
+int mcl3dl_get_map_info(const mcl3dl_engine* eng, mcl3dl_map_info* out)
+{
+  if (!eng || !out)
+    return MCL3DL_ERR_INVALID_ARG;
+  if (!eng->has_map)
+    return MCL3DL_ERR_NO_MAP;
+  *out = eng->info;
+  return MCL3DL_OK;
+}
+
+int mcl3dl_last_timing(const mcl3dl_engine* eng, double* h2d_ms, double* lik_ms, double* beam_ms, double* d2h_ms)
+{
+  if (!eng)
+    return MCL3DL_ERR_INVALID_ARG;
+  if (h2d_ms) *h2d_ms = eng->t_h2d;
+  if (lik_ms) *lik_ms = eng->t_lik;
+  if (beam_ms) *beam_ms = eng->t_beam;
+  if (d2h_ms) *d2h_ms = eng->t_d2h;
+  return MCL3DL_OK;
+}
+
+static int validate_measure(mcl3dl_engine* eng, size_t P, size_t n_lik, size_t n_beam, size_t n_origins)
+{
+  if (!eng)
+    return MCL3DL_ERR_INVALID_ARG;
+  if (!eng->has_map)
+    return MCL3DL_ERR_NO_MAP;
+  if (P >= (size_t(1) << 31) || n_lik >= (size_t(1) << 24) || n_beam >= (size_t(1) << 24))
+    return MCL3DL_ERR_TOO_LARGE;
+  if ((n_lik && !eng->has_lik) || (n_beam && !eng->has_beam))
+    return MCL3DL_ERR_INVALID_ARG;  // that model's grid was never staged
+  if (n_beam && n_origins == 0)
+    return MCL3DL_ERR_INVALID_ARG;
+  return MCL3DL_OK;
+}
+
+int mcl3dl_measure_device(mcl3dl_engine* eng, const mcl3dl_pose* d_poses, size_t P, const mcl3dl_point* d_lik, size_t n_lik,
+                          const mcl3dl_point* d_beam, size_t n_beam, const float* d_origins_xyz, size_t n_origins,
+                          mcl3dl_result* d_out, void* cuda_stream)
+{
+  int rc = validate_measure(eng, P, n_lik, n_beam, n_origins);
+  if (rc != MCL3DL_OK)
+    return rc;
+  if (eng->devs.size() != 1 || (P && (!d_poses || !d_out)) || (n_lik && !d_lik) || (n_beam && (!d_beam || !d_origins_xyz)))
+    return MCL3DL_ERR_INVALID_ARG;
+  if (P == 0)
+    return MCL3DL_OK;
+  DeviceCtx& c = eng->devs[0];
+  CK(cudaSetDevice(c.dev));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const float4* origins4 = nullptr;
+  if (n_beam)
+  {
+    rc = reserve(eng, c.d_origins, n_origins * 16);
+    if (rc != MCL3DL_OK)
+      return rc;
+    pack_origins_kernel<<<static_cast<int>((n_origins + 127) / 128), 128, 0, st>>>(d_origins_xyz, static_cast<int>(n_origins),
+                                                                                  static_cast<float4*>(c.d_origins.p));
+    CK(cudaGetLastError());
+    eng->launches++;
+    origins4 = static_cast<const float4*>(c.d_origins.p);
+  }
+  // node order: "beam" then "likelihood" (src/mcl_3dl.cpp:409-415); the records are disjoint fields
+  // (a model without a scan this update costs no launch: the other kernel writes its (1, 0))
+  if (n_beam)
+  {
+    rc = launch_beam(eng, c, d_poses, P, d_beam, n_beam, origins4, d_out, nullptr, n_lik == 0, st);
+    if (rc != MCL3DL_OK)
+      return rc;
+  }
+  if (n_lik || !n_beam)
+    rc = launch_lik(eng, c, d_poses, P, d_lik, n_lik, d_out, n_beam == 0, st);
+  return rc;
+}
+
+static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts, size_t n_lik,
+                        const mcl3dl_point* beam_pts, size_t n_beam, const float* origins_xyz, size_t n_origins,
+                        mcl3dl_result* out, uint8_t* status)
+{
+  int rc = validate_measure(eng, P, n_lik, n_beam, n_origins);
+  if (rc != MCL3DL_OK)
+    return rc;
+  if ((P && (!poses || (!out && !status))) || (n_lik && !lik_pts) || (n_beam && (!beam_pts || !origins_xyz)))
+    return MCL3DL_ERR_INVALID_ARG;
+  for (size_t j = 0; j < n_beam; ++j)
+    if (beam_pts[j].label >= n_origins)  // origins[p.label], beam.cpp:142-145
+      return MCL3DL_ERR_INVALID_ARG;
+  if (P == 0)
+    return MCL3DL_OK;
+  const size_t G = eng->devs.size();
+  std::vector<size_t> p0(G + 1);
+  for (size_t d = 0; d <= G; ++d) p0[d] = P * d / G;
+  // enqueue everything on every device, then wait
+  for (size_t d = 0; d < G; ++d)
+  {
+    DeviceCtx& c = eng->devs[d];
+    const size_t Pd = p0[d + 1] - p0[d];
+    if (Pd == 0)
+      continue;
+    CK(cudaSetDevice(c.dev));
+    cudaStream_t st = c.stream;
+    const size_t b_poses = Pd * sizeof(mcl3dl_pose), b_lik = n_lik * 16, b_beam = n_beam * 16, b_org = n_origins * 16;
+    const size_t b_out = Pd * sizeof(mcl3dl_result), b_status = status ? Pd * n_beam : 0;
+    const size_t o_lik = b_poses, o_beam = o_lik + b_lik, o_org = o_beam + b_beam, o_out = o_org + b_org;
+    const size_t o_status = o_out + b_out;
+    rc = reserve_pinned(eng, c, o_status + b_status + 64);
+    if (rc != MCL3DL_OK) return rc;
+    if ((rc = reserve(eng, c.d_poses, b_poses)) || (rc = reserve(eng, c.d_lik, b_lik)) || (rc = reserve(eng, c.d_beam, b_beam)) ||
+        (rc = reserve(eng, c.d_origins, b_org)) || (rc = reserve(eng, c.d_out, b_out)) || (rc = reserve(eng, c.d_status, b_status)))
+      return rc;
+    char* hp = static_cast<char*>(c.h_pinned);
+    std::memcpy(hp, poses + p0[d], b_poses);
+    if (b_lik) std::memcpy(hp + o_lik, lik_pts, b_lik);
+    if (b_beam) std::memcpy(hp + o_beam, beam_pts, b_beam);
+    float* ho = reinterpret_cast<float*>(hp + o_org);
+    for (size_t k = 0; k < n_origins; ++k)
+    {
+      ho[4 * k + 0] = origins_xyz[3 * k + 0];
+      ho[4 * k + 1] = origins_xyz[3 * k + 1];
+      ho[4 * k + 2] = origins_xyz[3 * k + 2];
+      ho[4 * k + 3] = 0.0f;
+    }
+    CK(cudaEventRecord(c.ev[0], st));
+    CK(cudaMemcpyAsync(c.d_poses.p, hp, b_poses, cudaMemcpyHostToDevice, st));
+    if (b_lik) CK(cudaMemcpyAsync(c.d_lik.p, hp + o_lik, b_lik, cudaMemcpyHostToDevice, st));
+    if (b_beam) CK(cudaMemcpyAsync(c.d_beam.p, hp + o_beam, b_beam, cudaMemcpyHostToDevice, st));
+    if (b_org) CK(cudaMemcpyAsync(c.d_origins.p, hp + o_org, b_org, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(c.ev[1], st));
+    if (n_beam)
+    {
+      rc = launch_beam(eng, c, static_cast<const mcl3dl_pose*>(c.d_poses.p), Pd, static_cast<const mcl3dl_point*>(c.d_beam.p),
+                       n_beam, static_cast<const float4*>(c.d_origins.p), static_cast<mcl3dl_result*>(c.d_out.p),
+                       status ? static_cast<uint8_t*>(c.d_status.p) : nullptr, n_lik == 0, st);
+      if (rc != MCL3DL_OK) return rc;
+    }
+    CK(cudaEventRecord(c.ev[2], st));
+    if (n_lik || !n_beam)
+    {
+      rc = launch_lik(eng, c, static_cast<const mcl3dl_pose*>(c.d_poses.p), Pd, static_cast<const mcl3dl_point*>(c.d_lik.p), n_lik,
+                      static_cast<mcl3dl_result*>(c.d_out.p), n_beam == 0, st);
+      if (rc != MCL3DL_OK) return rc;
+    }
+    CK(cudaEventRecord(c.ev[3], st));
+    CK(cudaMemcpyAsync(hp + o_out, c.d_out.p, b_out, cudaMemcpyDeviceToHost, st));
+    if (b_status) CK(cudaMemcpyAsync(hp + o_status, c.d_status.p, b_status, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c.ev[4], st));
+  }
+  eng->t_h2d = eng->t_lik = eng->t_beam = eng->t_d2h = 0;
+  for (size_t d = 0; d < G; ++d)
+  {
+    DeviceCtx& c = eng->devs[d];
+    const size_t Pd = p0[d + 1] - p0[d];
+    if (Pd == 0)
+      continue;
+    CK(cudaSetDevice(c.dev));
+    CK(cudaStreamSynchronize(c.stream));
+    const size_t o_out = Pd * sizeof(mcl3dl_pose) + n_lik * 16 + n_beam * 16 + n_origins * 16;
+    const size_t o_status = o_out + Pd * sizeof(mcl3dl_result);
+    const char* hp = static_cast<const char*>(c.h_pinned);
+    if (out) std::memcpy(out + p0[d], hp + o_out, Pd * sizeof(mcl3dl_result));
+    if (status) std::memcpy(status + p0[d] * n_beam, hp + o_status, Pd * n_beam);
+    float ms[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 4; ++k) CK(cudaEventElapsedTime(&ms[k], c.ev[k], c.ev[k + 1]));
+    eng->t_h2d = std::max(eng->t_h2d, static_cast<double>(ms[0]));
+    eng->t_beam = std::max(eng->t_beam, static_cast<double>(ms[1]));
+    eng->t_lik = std::max(eng->t_lik, static_cast<double>(ms[2]));
+    eng->t_d2h = std::max(eng->t_d2h, static_cast<double>(ms[3]));
+  }
+  return MCL3DL_OK;
+}
+
+int mcl3dl_measure(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts, size_t n_lik,
+                   const mcl3dl_point* beam_pts, size_t n_beam, const float* origins_xyz, size_t n_origins,
+                   mcl3dl_result* out)
+{
+  if (P && !out)
+    return MCL3DL_ERR_INVALID_ARG;
+  return measure_host(eng, poses, P, lik_pts, n_lik, beam_pts, n_beam, origins_xyz, n_origins, out, nullptr);
+}
+
+int mcl3dl_beam_status(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* beam_pts, size_t n_beam,
+                       const float* origins_xyz, size_t n_origins, uint8_t* status)
+{
+  if (P && n_beam && !status)
+    return MCL3DL_ERR_INVALID_ARG;
+  if (n_beam == 0)
+    return MCL3DL_OK;
+  return measure_host(eng, poses, P, nullptr, 0, beam_pts, n_beam, origins_xyz, n_origins, nullptr, status);
+}
+
+void mcl3dl_beam_params_from_reference(mcl3dl_beam_params* o, float map_grid_x, float map_grid_y, float map_grid_z,
+                                       size_t num_points_default, float beam_likelihood_min, float ang_total_ref,
+                                       uint32_t filter_label_max, float hit_range, int add_penalty_short_only_mode,
+                                       float ray_angle_half, float dda_grid_size)
+{
+  // LidarMeasurementModelBeam::refreshParameters, src/lidar_measurement_model_beam.cpp:58-80: the
+  // float parameters are promoted to double where the RaycastUsingDDA constructor takes doubles.
+  o->map_grid_size[0] = map_grid_x;
+  o->map_grid_size[1] = map_grid_y;
+  o->map_grid_size[2] = map_grid_z;
+  o->dda_grid_size = dda_grid_size;
+  o->ray_angle_half = ray_angle_half;
+  o->hit_tolerance = hit_range;
+  o->hit_range_sq = static_cast<float>(std::pow(static_cast<double>(hit_range), 2.0));
+  o->sin_total_ref = sinf(ang_total_ref);
+  o->beam_likelihood = static_cast<float>(
+      std::pow(static_cast<double>(beam_likelihood_min), 1.0 / static_cast<double>(static_cast<float>(num_points_default))));
+  o->beam_likelihood_min = beam_likelihood_min;
+  o->filter_label_max = filter_label_max;
+  o->add_penalty_short_only_mode = add_penalty_short_only_mode ? 1 : 0;
+}
+
+}  // extern "C"

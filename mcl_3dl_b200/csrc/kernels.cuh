@@ -1,0 +1,485 @@
+// kernels.cuh — the two hot kernels of the measurement update, hand-written for sm_100a.
+//
+//   lik_kernel   LidarMeasurementModelLikelihood::measure  (src/lidar_measurement_model_likelihood.cpp:105-139)
+//                + ChunkedKdtree::radiusSearch semantics   (include/mcl_3dl/chunked_kdtree.h:217-237)
+//   beam_kernel  LidarMeasurementModelBeam::measure / getBeamStatus (src/lidar_measurement_model_beam.cpp:124-192)
+//                + RaycastUsingDDA                          (include/mcl_3dl/raycasts/raycast_using_dda.h:66-270)
+//
+// Layout: particle-major.  A group of TPP threads (1..8 warps) owns one particle; its lanes stride
+// the sampled scan points, which the CTA stages once into shared memory with a TMA bulk copy
+// (cp.async.bulk + mbarrier).  Per-particle partials are reduced with warp shuffles and a fixed-order
+// shared-memory pass, so results are deterministic run to run.  No tensor cores: there is no dense
+// contraction anywhere on this path (HBM/L2 gather bound).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mcl3dl_b200.h"
+#include "device_math.cuh"
+
+namespace mcl3dl
+{
+constexpr int kBlockThreads = 256;
+
+// ---- likelihood search grid: cubic cells over the RESCALED map points (p * dist_weight), CSR of
+// cell -> contiguous run in `pts` (x fastest, so an x-row of cells is one contiguous run).
+struct NnGridDev
+{
+  const uint32_t* cell_start;  // [nx*ny*nz + 1]
+  const float4* pts;           // rescaled xyz, w = original map index (bits)
+  int nx, ny, nz;
+  float ox, oy, oz;  // grid origin in the rescaled space
+  float inv_cell;
+  float wx, wy, wz;  // dist_weight
+};
+
+struct LikDev
+{
+  float match_dist_min;   // R
+  float match_dist_flat;  // F
+  float match_weight;     // W
+  float r2;               // float(double(R)*double(R)): what pcl::KdTreeFLANN::radiusSearch hands to FLANN
+  float rpad;             // window half-width, R plus a rounding guard
+};
+
+// ---- DDA grid: exactly RaycastUsingDDA's lattice (min_p_, dda_grid_size_, map_size_), occupancy as
+// one bit per cell + CSR of per-cell points in map order.
+struct DdaGridDev
+{
+  const uint32_t* occ;         // bit c of word c>>5
+  const uint32_t* cell_start;  // [cells + 1]
+  const float4* pts;           // raw xyz, w = label bits; sorted by cell, map order inside a cell
+  int nx, ny, nz;
+  float min_x, min_y, min_z;
+  float max_x, max_y, max_z;
+  double grid;             // dda_grid_size_
+  double ray_angle_half;   // ray_angle_half_
+  double min_dist_thr_sq;  // min_dist_thr_sq_
+  float hit_tolerance;     // float(hit_tolerance_): Vec3 * double narrows to float (vec3.h:119)
+  float hit_range_sq;
+  float sin_total_ref;
+  float beam_likelihood;
+  float beam_likelihood_min;
+  uint32_t filter_label_max;
+  int short_only;
+};
+
+enum
+{
+  ST_SHORT = 0,
+  ST_HIT = 1,
+  ST_LONG = 2,
+  ST_TOTAL_REFLECTION = 3
+};
+
+// --------------------------------------------------------------------------------------------
+// Stage `bytes` (multiple of 16) from global to shared with one TMA bulk copy; all threads wait.
+__device__ __forceinline__ void stage_tile(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+  const uint32_t bar_a = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  const uint32_t dst_a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  if (threadIdx.x == 0)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+        "l"(gsrc), "r"(bytes), "r"(bar_a)
+        : "memory");
+  }
+  uint32_t done = 0;
+  while (!done)
+  {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar_a)
+        : "memory");
+  }
+}
+
+// Fixed-order reduction of one value per thread over the TPP threads that own a particle.
+// red must hold kBlockThreads/32 entries per quantity.
+template <int TPP>
+__device__ __forceinline__ void group_reduce(float& f, uint32_t& a, uint32_t& b, uint32_t& c, float* red_f,
+                                             uint32_t* red_u)
+{
+  f = warp_sum(f);
+  a = warp_sum_u32(a);
+  b = warp_sum_u32(b);
+  c = warp_sum_u32(c);
+  if (TPP > 32)
+  {
+    constexpr int WPP = TPP / 32;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0)
+    {
+      red_f[warp] = f;
+      red_u[warp * 3 + 0] = a;
+      red_u[warp * 3 + 1] = b;
+      red_u[warp * 3 + 2] = c;
+    }
+    __syncthreads();
+    const int w0 = (warp / WPP) * WPP;
+    float sf = red_f[w0];
+    uint32_t sa = red_u[w0 * 3], sb = red_u[w0 * 3 + 1], sc = red_u[w0 * 3 + 2];
+#pragma unroll
+    for (int k = 1; k < WPP; ++k)
+    {
+      sf = fadd(sf, red_f[w0 + k]);
+      sa += red_u[(w0 + k) * 3];
+      sb += red_u[(w0 + k) * 3 + 1];
+      sc += red_u[(w0 + k) * 3 + 2];
+    }
+    f = sf;
+    a = sa;
+    b = sb;
+    c = sc;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Exact nearest-neighbour distance^2 (rescaled metric) within the radius; returns r2 if none.
+__device__ __forceinline__ float nn_dist2(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz)
+{
+  // Same cell function as the build kernel (monotone in its argument), applied to q -/+ rpad.
+  int lx = __float2int_rd(fmul(fsub(fsub(qx, lp.rpad), g.ox), g.inv_cell));
+  int ly = __float2int_rd(fmul(fsub(fsub(qy, lp.rpad), g.oy), g.inv_cell));
+  int lz = __float2int_rd(fmul(fsub(fsub(qz, lp.rpad), g.oz), g.inv_cell));
+  int hx = __float2int_rd(fmul(fsub(fadd(qx, lp.rpad), g.ox), g.inv_cell));
+  int hy = __float2int_rd(fmul(fsub(fadd(qy, lp.rpad), g.oy), g.inv_cell));
+  int hz = __float2int_rd(fmul(fsub(fadd(qz, lp.rpad), g.oz), g.inv_cell));
+  lx = max(lx, 0);
+  ly = max(ly, 0);
+  lz = max(lz, 0);
+  hx = min(hx, g.nx - 1);
+  hy = min(hy, g.ny - 1);
+  hz = min(hz, g.nz - 1);
+  float best = lp.r2;
+  if (lx > hx || ly > hy || lz > hz)
+    return best;
+  for (int iz = lz; iz <= hz; ++iz)
+  {
+    for (int iy = ly; iy <= hy; ++iy)
+    {
+      const int row = (iz * g.ny + iy) * g.nx;
+      const uint32_t s0 = __ldg(g.cell_start + row + lx);
+      const uint32_t s1 = __ldg(g.cell_start + row + hx + 1);
+      for (uint32_t s = s0; s < s1; ++s)
+      {
+        const float4 m = __ldg(g.pts + s);
+        // flann::L2_Simple: sequential float accumulate of squared differences
+        const float dx = fsub(qx, m.x);
+        const float dy = fsub(qy, m.y);
+        const float dz = fsub(qz, m.z);
+        const float d = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+        best = fminf(best, d);  // KNNRadiusResultSet: keep d < worst
+      }
+    }
+  }
+  return best;
+}
+
+template <int TPP, bool STAGED>
+__global__ void __launch_bounds__(kBlockThreads)
+    lik_kernel(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N, NnGridDev g,
+               LikDev lp, mcl3dl_result* __restrict__ out, int write_beam_defaults)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ float red_f[kBlockThreads / 32];
+  __shared__ uint32_t red_u[3 * kBlockThreads / 32];
+  const float4* pts = scan;
+  if (STAGED && N > 0)
+  {
+    stage_tile(smem_raw, scan, static_cast<uint32_t>(N) * 16u, &bar);
+    pts = reinterpret_cast<const float4*>(smem_raw);
+  }
+  constexpr int PPB = kBlockThreads / TPP;
+  const int sub = threadIdx.x / TPP;
+  const int l = threadIdx.x % TPP;
+  const int n_groups = (P + PPB - 1) / PPB;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
+  {
+    const int p = grp * PPB + sub;
+    const bool live = p < P;
+    float score = 0.0f;
+    uint32_t cnt = 0, z0 = 0, z1 = 0;
+    if (live)
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(poses + p));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(poses + p) + 1);
+      F3 pos;
+      pos.x = a.x;
+      pos.y = a.y;
+      pos.z = a.z;
+      Q4 q;
+      q.x = b.x;
+      q.y = b.y;
+      q.z = b.z;
+      q.w = b.w;
+      const Q4 rn = qnormalized(q);  // state_6dof.h:217
+      for (int j = l; j < N; j += TPP)
+      {
+        const float4 sp = pts[j];
+        F3 v;
+        v.x = sp.x;
+        v.y = sp.y;
+        v.z = sp.z;
+        const F3 t = transform_point(rn, pos, v);
+        // PointRepresentation::vectorize with rescale values (mcl_3dl.cpp:1270)
+        const float d2 = nn_dist2(g, lp, fmul(t.x, g.wx), fmul(t.y, g.wy), fmul(t.z, g.wz));
+        if (d2 < lp.r2)
+        {
+          // likelihood.cpp:128-133
+          const float dist = fsub(lp.match_dist_min, fmaxf(__fsqrt_rn(d2), lp.match_dist_flat));
+          if (!(dist < 0.0f))
+          {
+            score = fadd(score, fmul(dist, lp.match_weight));
+            cnt++;
+          }
+        }
+      }
+    }
+    group_reduce<TPP>(score, cnt, z0, z1, red_f, red_u);
+    if (live && l == 0)
+    {
+      // empty scan -> LidarMeasurementResult(1, 0), likelihood.cpp:111-114
+      out[p].score_like = (N == 0) ? 1.0f : score;
+      out[p].match_cnt = cnt;
+      if (write_beam_defaults)
+      {
+        // no beam scan this update: LidarMeasurementResult(1, 0), beam.cpp:130-133
+        out[p].score_beam = 1.0f;
+        out[p].n_short = 0;
+        out[p].n_hit = 0;
+        out[p].n_long = 0;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// One ray: RaycastUsingDDA::setRay + getNextCastResult loop + getBeamStatus's decision.
+__device__ __forceinline__ int dda_to_index(float v, float mn, double grid)
+{
+  // toIndex, raycast_using_dda.h:205-210: float difference, double division, truncation
+  return __double2int_rz(ddiv(static_cast<double>(fsub(v, mn)), grid));
+}
+
+__device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const F3& e)
+{
+  // isPointWithinMap, :260-270
+  if (b.x < g.min_x || g.max_x < b.x || b.y < g.min_y || g.max_y < b.y || b.z < g.min_z || g.max_z < b.z)
+    return ST_LONG;
+  // setRay, :66-104
+  F3 d;
+  d.x = fsub(e.x, b.x);
+  d.y = fsub(e.y, b.y);
+  d.z = fsub(e.z, b.z);
+  const float nrm = __fsqrt_rn(dot3(d, d));
+  F3 dir;
+  dir.x = fdiv(d.x, nrm);
+  dir.y = fdiv(d.y, nrm);
+  dir.z = fdiv(d.z, nrm);
+  const float ex = fadd(e.x, fmul(dir.x, g.hit_tolerance));
+  const float ey = fadd(e.y, fmul(dir.y, g.hit_tolerance));
+  const float ez = fadd(e.z, fmul(dir.z, g.hit_tolerance));
+  const int bx = dda_to_index(b.x, g.min_x, g.grid);
+  const int by = dda_to_index(b.y, g.min_y, g.grid);
+  const int bz = dda_to_index(b.z, g.min_z, g.grid);
+  const int dix = dda_to_index(ex, g.min_x, g.grid) - bx;
+  const int diy = dda_to_index(ey, g.min_y, g.grid) - by;
+  const int diz = dda_to_index(ez, g.min_z, g.grid) - bz;
+  const int max_movement = abs(dix) + abs(diy) + abs(diz);
+  const int sx = dix < 0 ? -1 : 1, sy = diy < 0 ? -1 : 1, sz = diz < 0 ? -1 : 1;
+  const float inf = __int_as_float(0x7f800000);
+  float e0x = inf, e0y = inf, e0z = inf, tdx = inf, tdy = inf, tdz = inf;
+  if (dix != 0)
+  {
+    const double nearest = dadd(dmul(static_cast<double>(dir.x < 0 ? bx : bx + 1), g.grid), static_cast<double>(g.min_x));
+    e0x = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.x)), static_cast<double>(dir.x))));
+    tdx = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.x))));
+  }
+  if (diy != 0)
+  {
+    const double nearest = dadd(dmul(static_cast<double>(dir.y < 0 ? by : by + 1), g.grid), static_cast<double>(g.min_y));
+    e0y = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.y)), static_cast<double>(dir.y))));
+    tdy = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.y))));
+  }
+  if (diz != 0)
+  {
+    const double nearest = dadd(dmul(static_cast<double>(dir.z < 0 ? bz : bz + 1), g.grid), static_cast<double>(g.min_z));
+    e0z = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.z)), static_cast<double>(dir.z))));
+    tdz = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.z))));
+  }
+  float tx = e0x, ty = e0y, tz = e0z;
+  int cx = bx, cy = by, cz = bz;
+  const int nxy = g.nx * g.ny;
+  // getNextCastResult, :106-159: at most max_movement-1 cells; begin and end cells are never tested
+  for (int pos = 1; pos < max_movement; ++pos)
+  {
+    // strict-'<' ladder (:114-147); on ties z beats y beats x.  incrementIndex (:192-203) recomputes
+    // t_max from the start: float * float(int) + float.
+    if (tx < ty ? tx < tz : false)
+    {
+      cx += sx;
+      tx = fadd(e0x, fmul(tdx, static_cast<float>(abs(cx - bx))));
+      if (cx < 0 || g.nx <= cx)
+        return ST_LONG;
+    }
+    else if (!(tx < ty) && ty < tz)
+    {
+      cy += sy;
+      ty = fadd(e0y, fmul(tdy, static_cast<float>(abs(cy - by))));
+      if (cy < 0 || g.ny <= cy)
+        return ST_LONG;
+    }
+    else
+    {
+      cz += sz;
+      tz = fadd(e0z, fmul(tdz, static_cast<float>(abs(cz - bz))));
+      if (cz < 0 || g.nz <= cz)
+        return ST_LONG;
+    }
+    const int cell = cx + cy * g.nx + cz * nxy;
+    if (!((__ldg(g.occ + (cell >> 5)) >> (cell & 31)) & 1u))
+      continue;
+    // hasIntersection, :237-258: first point of the cell, in map order, inside the cone
+    const uint32_t s0 = __ldg(g.cell_start + cell);
+    const uint32_t s1 = __ldg(g.cell_start + cell + 1);
+    for (uint32_t s = s0; s < s1; ++s)
+    {
+      const float4 m = __ldg(g.pts + s);
+      F3 rel;
+      rel.x = fsub(m.x, b.x);
+      rel.y = fsub(m.y, b.y);
+      rel.z = fsub(m.z, b.z);
+      const double foot = static_cast<double>(fabsf(dot3(rel, dir)));
+      const double a0 = dmul(g.ray_angle_half, foot);
+      const double thr = fmax(dmul(a0, a0), g.min_dist_thr_sq);
+      const double dsq = dsub(static_cast<double>(dot3(rel, rel)), dmul(foot, foot));
+      if (dsq < thr)
+      {
+        // getBeamStatus, beam.cpp:164-189
+        if (__float_as_uint(m.w) > g.filter_label_max)
+          break;  // this cell's collision is filtered; the walk continues with the next cell
+        if (1.0f > g.sin_total_ref)
+        {
+          const double ddx = static_cast<double>(fsub(e.x, m.x));
+          const double ddy = static_cast<double>(fsub(e.y, m.y));
+          const double ddz = static_cast<double>(fsub(e.z, m.z));
+          const float dist_sq = __double2float_rn(dadd(dadd(dmul(ddx, ddx), dmul(ddy, ddy)), dmul(ddz, ddz)));
+          return dist_sq < g.hit_range_sq ? ST_HIT : ST_SHORT;
+        }
+        return ST_TOTAL_REFLECTION;
+      }
+    }
+  }
+  return ST_LONG;
+}
+
+template <int TPP, bool STAGED>
+__global__ void __launch_bounds__(kBlockThreads)
+    beam_kernel(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N,
+                const float4* __restrict__ origins, DdaGridDev g, mcl3dl_result* __restrict__ out,
+                uint8_t* __restrict__ status, int write_lik_defaults)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ float red_f[kBlockThreads / 32];
+  __shared__ uint32_t red_u[3 * kBlockThreads / 32];
+  const float4* pts = scan;
+  if (STAGED && N > 0)
+  {
+    stage_tile(smem_raw, scan, static_cast<uint32_t>(N) * 16u, &bar);
+    pts = reinterpret_cast<const float4*>(smem_raw);
+  }
+  constexpr int PPB = kBlockThreads / TPP;
+  const int sub = threadIdx.x / TPP;
+  const int l = threadIdx.x % TPP;
+  const int n_groups = (P + PPB - 1) / PPB;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
+  {
+    const int p = grp * PPB + sub;
+    const bool live = p < P;
+    float unused = 0.0f;
+    uint32_t n_short = 0, n_hit = 0, n_long = 0;
+    if (live)
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(poses + p));
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(poses + p) + 1);
+      F3 pos;
+      pos.x = a.x;
+      pos.y = a.y;
+      pos.z = a.z;
+      Q4 q;
+      q.x = bq.x;
+      q.y = bq.y;
+      q.z = bq.z;
+      q.w = bq.w;
+      const Q4 rn = qnormalized(q);
+      for (int j = l; j < N; j += TPP)
+      {
+        const float4 sp = pts[j];
+        F3 v;
+        v.x = sp.x;
+        v.y = sp.y;
+        v.z = sp.z;
+        const F3 end = transform_point(rn, pos, v);  // beam.cpp:138-139
+        const float4 o4 = __ldg(origins + __float_as_uint(sp.w));
+        F3 o;
+        o.x = o4.x;
+        o.y = o4.y;
+        o.z = o4.z;
+        const F3 ro = qrot(q, o);  // RAW rot_, beam.cpp:145
+        F3 begin;
+        begin.x = fadd(pos.x, ro.x);
+        begin.y = fadd(pos.y, ro.y);
+        begin.z = fadd(pos.z, ro.z);
+        const int st = cast_ray(g, begin, end);
+        n_short += (st == ST_SHORT);
+        n_hit += (st == ST_HIT);
+        n_long += (st == ST_LONG);
+        if (status)
+          status[static_cast<size_t>(p) * N + j] = static_cast<uint8_t>(st);
+      }
+    }
+    group_reduce<TPP>(unused, n_short, n_hit, n_long, red_f, red_u);
+    if (live && l == 0)
+    {
+      // beam.cpp:146-152: the same factor multiplied in sequentially, then the floor
+      float score = 1.0f;
+      if (N > 0)
+      {
+        const uint32_t k = n_short + (g.short_only ? 0u : n_long);
+        for (uint32_t i = 0; i < k; ++i) score = fmul(score, g.beam_likelihood);
+        if (score < g.beam_likelihood_min)
+          score = g.beam_likelihood_min;
+      }
+      out[p].score_beam = score;
+      out[p].n_short = n_short;
+      out[p].n_hit = n_hit;
+      out[p].n_long = n_long;
+      if (write_lik_defaults)
+      {
+        // no likelihood scan this update: LidarMeasurementResult(1, 0), likelihood.cpp:111-114
+        out[p].score_like = 1.0f;
+        out[p].match_cnt = 0;
+      }
+    }
+  }
+}
+
+}  // namespace mcl3dl

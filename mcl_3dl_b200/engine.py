@@ -1,0 +1,196 @@
+"""ctypes binding of include/mcl3dl_b200.h (the C ABI of the CUDA engine).
+
+`Engine` is the C-ABI handle (set_map / measure / measure_device / beam_status).  The Python
+mirror of the reference's plugin classes lives in mcl_3dl_b200/models.py on top of this.
+
+There is no fallback: if the CUDA library is missing or no device is usable, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from .synth import POINT, POSE, RESULT
+
+ERR = {0: "ok", -1: "invalid argument", -2: "measure() before set_map()", -3: "CUDA runtime error",
+       -4: "no usable CUDA device", -5: "grid exceeds 2^31-1 cells", -6: "search radius out of range"}
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__("mcl3dl error %d (%s) %s" % (code, ERR.get(code, "?"), detail))
+
+
+class LikParams(C.Structure):
+    """mcl3dl_lik_params; defaults = include/mcl_3dl/parameters.h:74-76."""
+    _fields_ = [("match_weight", C.c_float), ("match_dist_min", C.c_float), ("match_dist_flat", C.c_float),
+                ("dist_weight", C.c_float * 3)]
+
+    def __init__(self, match_weight=5.0, match_dist_min=0.2, match_dist_flat=0.05, dist_weight=(1.0, 1.0, 1.0)):
+        super().__init__()
+        self.match_weight, self.match_dist_min, self.match_dist_flat = match_weight, match_dist_min, match_dist_flat
+        self.dist_weight[:] = dist_weight
+
+
+class BeamParams(C.Structure):
+    """mcl3dl_beam_params (derived; fill through beam_params_from_reference)."""
+    _fields_ = [("map_grid_size", C.c_double * 3), ("dda_grid_size", C.c_double), ("ray_angle_half", C.c_double),
+                ("hit_tolerance", C.c_double), ("hit_range_sq", C.c_float), ("sin_total_ref", C.c_float),
+                ("beam_likelihood", C.c_float), ("beam_likelihood_min", C.c_float),
+                ("filter_label_max", C.c_uint32), ("add_penalty_short_only_mode", C.c_int32)]
+
+    def as_tuple(self):
+        return (tuple(self.map_grid_size), self.dda_grid_size, self.ray_angle_half, self.hit_tolerance,
+                self.hit_range_sq, self.sin_total_ref, self.beam_likelihood, self.beam_likelihood_min,
+                self.filter_label_max, self.add_penalty_short_only_mode)
+
+
+class MapInfo(C.Structure):
+    _fields_ = [("n_points", C.c_uint64), ("nn_dims", C.c_int32 * 3), ("nn_cell", C.c_float),
+                ("nn_origin", C.c_float * 3), ("dda_dims", C.c_int32 * 3), ("dda_min", C.c_float * 3),
+                ("dda_max", C.c_float * 3), ("device_bytes", C.c_uint64), ("build_ms", C.c_double)]
+
+
+EXPORTED_SYMBOLS = ["mcl3dl_abi_version", "mcl3dl_create", "mcl3dl_destroy", "mcl3dl_set_map", "mcl3dl_set_params",
+                    "mcl3dl_measure", "mcl3dl_measure_device", "mcl3dl_beam_status",
+                    "mcl3dl_beam_params_from_reference", "mcl3dl_get_map_info", "mcl3dl_last_timing",
+                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail"]
+
+_LIB = None
+
+
+def load_library():
+    """Load (building if stale and nvcc is present) the in-tree CUDA library.  Raises if unavailable."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if _build.stale():
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.exists(path):
+                raise
+    L = C.CDLL(path)
+    vp, sz = C.c_void_p, C.c_size_t
+    L.mcl3dl_abi_version.restype = C.c_int
+    L.mcl3dl_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    L.mcl3dl_destroy.argtypes = [vp]
+    L.mcl3dl_destroy.restype = None
+    L.mcl3dl_set_map.argtypes = [vp, vp, sz, C.c_uint64, vp, vp]
+    L.mcl3dl_set_params.argtypes = [vp, vp, vp]
+    L.mcl3dl_measure.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp]
+    L.mcl3dl_measure_device.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp]
+    L.mcl3dl_beam_status.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp]
+    L.mcl3dl_beam_params_from_reference.argtypes = [vp, C.c_float, C.c_float, C.c_float, sz, C.c_float, C.c_float,
+                                                    C.c_uint32, C.c_float, C.c_int, C.c_float, C.c_float]
+    L.mcl3dl_beam_params_from_reference.restype = None
+    L.mcl3dl_get_map_info.argtypes = [vp, vp]
+    L.mcl3dl_last_timing.argtypes = [vp] + [C.POINTER(C.c_double)] * 4
+    L.mcl3dl_kernel_launches.argtypes = [vp]
+    L.mcl3dl_kernel_launches.restype = C.c_uint64
+    L.mcl3dl_strerror.argtypes = [C.c_int]
+    L.mcl3dl_strerror.restype = C.c_char_p
+    L.mcl3dl_last_error_detail.argtypes = [vp]
+    L.mcl3dl_last_error_detail.restype = C.c_char_p
+    assert L.mcl3dl_abi_version() == 1
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+def beam_params_from_reference(map_grid=(0.1, 0.1, 0.1), num_points_default=3, beam_likelihood_min=0.2,
+                               ang_total_ref=np.pi / 6.0, filter_label_max=0xFFFFFFFF, hit_range=0.3,
+                               add_penalty_short_only_mode=True, ray_angle_half=0.25 * np.pi / 180.0,
+                               dda_grid_size=0.2):
+    """LidarMeasurementModelBeamParameters (parameters.h:95-111) -> derived mcl3dl_beam_params."""
+    L = load_library()
+    bp = BeamParams()
+    L.mcl3dl_beam_params_from_reference(C.byref(bp), map_grid[0], map_grid[1], map_grid[2], num_points_default,
+                                        beam_likelihood_min, ang_total_ref, filter_label_max, hit_range,
+                                        1 if add_penalty_short_only_mode else 0, ray_angle_half, dda_grid_size)
+    return bp
+
+
+class Engine:
+    """Handle on mcl3dl_engine.  devices: list of CUDA ordinals (map replicated, particles split)."""
+
+    def __init__(self, devices=(0,)):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        ids = (C.c_int * len(devices))(*devices)
+        rc = self.L.mcl3dl_create(C.byref(self.h), ids, len(devices))
+        if rc != 0:
+            self.h = None
+            raise EngineError(rc)
+        self.devices = tuple(devices)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(rc, self.L.mcl3dl_last_error_detail(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mcl3dl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_map(self, map_pts, lik=None, beam=None, stamp=1):
+        map_pts = np.ascontiguousarray(map_pts, dtype=POINT)
+        self._check(self.L.mcl3dl_set_map(self.h, _ptr(map_pts), len(map_pts), stamp,
+                                          C.byref(lik) if lik is not None else None,
+                                          C.byref(beam) if beam is not None else None))
+
+    def set_params(self, lik=None, beam=None):
+        self._check(self.L.mcl3dl_set_params(self.h, C.byref(lik) if lik is not None else None,
+                                             C.byref(beam) if beam is not None else None))
+
+    def map_info(self):
+        mi = MapInfo()
+        self._check(self.L.mcl3dl_get_map_info(self.h, C.byref(mi)))
+        return mi
+
+    def measure(self, poses, lik_pts=None, beam_pts=None, origins=None, out=None):
+        poses = np.ascontiguousarray(poses, dtype=POSE)
+        lik_pts = np.ascontiguousarray(lik_pts if lik_pts is not None else np.zeros(0, POINT), dtype=POINT)
+        beam_pts = np.ascontiguousarray(beam_pts if beam_pts is not None else np.zeros(0, POINT), dtype=POINT)
+        origins = np.ascontiguousarray(origins if origins is not None else np.zeros((0, 3)), dtype=np.float32)
+        origins = origins.reshape(-1, 3)
+        if out is None:
+            out = np.zeros(len(poses), dtype=RESULT)
+        self._check(self.L.mcl3dl_measure(self.h, _ptr(poses), len(poses), _ptr(lik_pts), len(lik_pts),
+                                          _ptr(beam_pts), len(beam_pts), _ptr(origins), len(origins), _ptr(out)))
+        return out
+
+    def measure_device(self, d_poses, n_particles, d_lik, n_lik, d_beam, n_beam, d_origins, n_origins, d_out,
+                       stream=0):
+        """All d_* are raw device addresses (ints, e.g. torch.Tensor.data_ptr()); async on `stream`."""
+        self._check(self.L.mcl3dl_measure_device(self.h, d_poses, n_particles, d_lik, n_lik, d_beam, n_beam,
+                                                 d_origins, n_origins, d_out, stream))
+
+    def beam_status(self, poses, beam_pts, origins):
+        poses = np.ascontiguousarray(poses, dtype=POSE)
+        beam_pts = np.ascontiguousarray(beam_pts, dtype=POINT)
+        origins = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        st = np.zeros((len(poses), len(beam_pts)), dtype=np.uint8)
+        self._check(self.L.mcl3dl_beam_status(self.h, _ptr(poses), len(poses), _ptr(beam_pts), len(beam_pts),
+                                              _ptr(origins), len(origins), _ptr(st)))
+        return st
+
+    def last_timing(self):
+        v = [C.c_double(0) for _ in range(4)]
+        self.L.mcl3dl_last_timing(self.h, *[C.byref(x) for x in v])
+        return {"h2d_ms": v[0].value, "lik_ms": v[1].value, "beam_ms": v[2].value, "d2h_ms": v[3].value}
+
+    def kernel_launches(self):
+        return int(self.L.mcl3dl_kernel_launches(self.h))

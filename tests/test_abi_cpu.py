@@ -1,0 +1,82 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds, loads, exports every symbol that
+include/mcl3dl_b200.h declares, derives the beam parameters like the reference, and fails loudly
+(no CPU fallback) when there is no CUDA device.  No compute calls are made here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "mcl3dl_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcl3dl_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mcl_3dl_b200 import engine
+    L = engine.load_library()
+    names = declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(engine.EXPORTED_SYMBOLS) == names
+    assert L.mcl3dl_abi_version() == 1
+    assert L.mcl3dl_strerror(-2).decode().startswith("measure()")
+
+
+def test_struct_layouts_match_header():
+    import ctypes as C
+    from mcl_3dl_b200 import engine, synth
+    assert synth.POINT.itemsize == 16 and synth.POSE.itemsize == 32 and synth.RESULT.itemsize == 24
+    assert C.sizeof(engine.LikParams) == 24
+    assert C.sizeof(engine.BeamParams) == 72
+    assert C.sizeof(engine.MapInfo) == 88
+
+
+@pytest.mark.parametrize("kw", [
+    dict(),
+    dict(num_points_default=27, hit_range=0.0, add_penalty_short_only_mode=False, dda_grid_size=0.1),
+    dict(map_grid=(0.05, 0.1, 0.2), num_points_default=1024, beam_likelihood_min=0.35, hit_range=1.0,
+         filter_label_max=1, ang_total_ref=1.2),
+])
+def test_beam_params_derivation_matches_oracle(port, kw):
+    """mcl3dl_beam_params_from_reference == refreshParameters (beam.cpp:58-80) as restated by the oracle
+    (which tests/test_oracle_golden.py pins to the reference build)."""
+    from mcl_3dl_b200 import engine
+    from oracle import cpu_checker as cc
+    mine = engine.beam_params_from_reference(**kw)
+    m = port.create(cc.points([[0, 0, 0], [1, 1, 1]]), None, cc.beam_raw(**kw))
+    assert mine.as_tuple() == m.beam_params().as_tuple()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    from mcl_3dl_b200 import engine
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(engine.EngineError) as ei:
+        engine.Engine((0,))
+    assert ei.value.code == -4
+
+
+def test_product_package_never_touches_the_oracle():
+    """The product path must not import, link or load anything under oracle/."""
+    pkg = os.path.join(ROOT, "mcl_3dl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.replace("the oracle", "").replace("# oracle", ""), os.path.join(dirpath, f)
+    import subprocess
+    out = subprocess.run(["ldd", os.path.join(pkg, "libmcl3dl_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "mcl3dl_ref" not in out
+
+
+def test_bench_byte_model():
+    import bench
+    assert bench.bytes_per_eval_model() == (1200, 75)            # 5*5*3 cells at w=(1,1,5)
+    assert bench.bytes_per_eval_model(w=(1, 1, 1)) == (2000, 125)

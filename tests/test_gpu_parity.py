@@ -1,0 +1,266 @@
+"""GPU parity: the CUDA engine, called through the C ABI, against the CPU oracle and the committed
+golden outputs of the reference's own sources.  Everything here needs a B200 (`-m gpu`).
+
+Bars (BASELINE.json north_star): beam HIT/SHORT/LONG tallies and per-ray BeamStatus bit-exact;
+match counts bit-exact; likelihood scores within 1e-4 relative (the per-particle float sum is
+reduced in a different order than the reference's sequential loop).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+from mcl_3dl_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+LIK_RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def eng_mod():
+    from mcl_3dl_b200 import engine
+    engine.load_library()
+    return engine
+
+
+@pytest.fixture()
+def eng(eng_mod):
+    e = eng_mod.Engine((0,))
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def cc():
+    from oracle import cpu_checker
+    cpu_checker.build("port")
+    return cpu_checker
+
+
+def check_records(got, want, n_beam):
+    for f in ("match_cnt", "n_short", "n_hit", "n_long"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(got["score_beam"], want["score_beam"])
+    assert np.allclose(got["score_like"], want["score_like"], rtol=LIK_RTOL, atol=1e-6)
+    assert ((got["n_short"] + got["n_hit"] + got["n_long"]) <= n_beam).all()
+
+
+# ------------------------------------------------------------------ committed reference outputs
+@pytest.mark.parametrize("name", ["room_iso", "room_aniso", "room_spread"])
+def test_golden_rooms(eng_mod, eng, name):
+    g = golden(name + ".npz")
+    n_beam, flm, short_only = [int(v) for v in g["beam_cfg"]]
+    lik = eng_mod.LikParams(dist_weight=tuple(float(v) for v in g["dist_weight"]))
+    beam = eng_mod.beam_params_from_reference(num_points_default=n_beam, filter_label_max=flm,
+                                              add_penalty_short_only_mode=bool(short_only),
+                                              dda_grid_size=float(g["dda_grid"]))
+    eng.set_map(g["map"], lik, beam)
+    res = eng.measure(g["particles"], g["lik"], g["beam"], g["origins"])
+    check_records(res, g["result"], n_beam)
+    assert np.array_equal(eng.beam_status(g["particles"], g["beam"], g["origins"]), g["status"])
+
+
+def test_golden_beam_likelihood_world(eng_mod, eng):
+    """World + sweep of test/src/test_beam_likelihood.cpp:81-210 (DDA caster)."""
+    g = golden("beam_likelihood_world.npz")
+    pc_map, pc, xs = synth.make_points(g["map"]), synth.make_points(g["scan"]), g["xs"]
+    k = 0
+    for mode in (0, 1):
+        for hr in g["hit_ranges"]:
+            beam = eng_mod.beam_params_from_reference(map_grid=(0.1, 0.1, 0.1), num_points_default=len(pc) + 2,
+                                                      beam_likelihood_min=0.2, hit_range=float(hr),
+                                                      add_penalty_short_only_mode=(mode == 1), dda_grid_size=0.1)
+            eng.set_map(pc_map, None, beam, stamp=100 + k)
+            # every x is its own update in the reference test: origin = pose position, identity rotation
+            for i, x in enumerate(xs):
+                r = eng.measure(synth.make_poses([[x, 0, 0]], [[0, 0, 0, 1]]), None, pc,
+                                np.array([[x, 0, 0]], np.float32))
+                assert r["score_beam"][0] == g["likelihood"][k, i], (mode, hr, i)
+            ident = synth.make_poses([[0, 0, 0]], [[0, 0, 0, 1]])
+            st = np.array([eng.beam_status(ident, synth.make_points([[x, 0, 0]]), np.zeros((1, 3), np.float32))[0, 0]
+                           for x in xs])
+            assert np.array_equal(st, g["status"][k]), (mode, hr)
+            k += 1
+
+
+# ------------------------------------------------------------------ seeded scenes vs the oracle
+def run_both(eng_mod, eng, cc, s, w, n_beam_default, dda_grid=0.2, flm=0xFFFFFFFF, short_only=True, hit_range=0.3):
+    port = cc.CpuChecker("port")
+    lik_c = cc.lik_params(dist_weight=w)
+    braw = cc.beam_raw(num_points_default=n_beam_default, dda_grid_size=dda_grid, filter_label_max=flm,
+                       add_penalty_short_only_mode=short_only, hit_range=hit_range)
+    cpu = port.create(s["map"], lik_c, braw, 20.0, 0.4)
+    lik = eng_mod.LikParams(dist_weight=w)
+    beam = eng_mod.beam_params_from_reference(num_points_default=n_beam_default, dda_grid_size=dda_grid,
+                                              filter_label_max=flm, add_penalty_short_only_mode=short_only,
+                                              hit_range=hit_range)
+    assert beam.as_tuple() == cpu.beam_params().as_tuple()
+    eng.set_map(s["map"], lik, beam, stamp=int(np.random.default_rng().integers(1, 2 ** 40)))
+    return cpu
+
+
+@pytest.mark.parametrize("seed,w,spread,P,n_lik,n_beam", [
+    (11, (1, 1, 1), False, 64, 96, 3),      # BASELINE config 1: the reference's default operating point
+    (12, (1, 1, 5), False, 64, 96, 3),      # ... with the node's anisotropic metric (parameters.cpp:108-111)
+    (13, (1, 1, 5), True, 333, 257, 65),    # ragged sizes, spread particles (many outside / LONG rays)
+    (14, (1, 1, 5), False, 1000, 33, 200),  # more rays than likelihood points
+    (15, (2, 1, 3), False, 97, 1, 1),       # single-point scans
+])
+def test_scene_vs_oracle(eng_mod, eng, cc, seed, w, spread, P, n_lik, n_beam):
+    s = synth.scene(50_000, P, n_lik, n_beam, spread=spread, seed=seed)
+    cpu = run_both(eng_mod, eng, cc, s, w, n_beam, dda_grid=0.2 if seed % 2 else 0.1,
+                   flm=1 if seed == 13 else 0xFFFFFFFF, short_only=seed != 14)
+    want = cpu.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+    got = eng.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+    check_records(got, want, n_beam)
+    assert np.array_equal(eng.beam_status(s["particles"], s["beam"], s["origins"]),
+                          cpu.beam_status(s["particles"], s["beam"], s["origins"]))
+    if not spread:
+        assert want["match_cnt"].sum() > 0 and want["n_hit"].sum() + want["n_short"].sum() > 0
+
+
+def test_edge_cases(eng_mod, eng, cc):
+    s = synth.scene(20_000, 40, 64, 16, seed=21)
+    cpu = run_both(eng_mod, eng, cc, s, (1, 1, 5), 16)
+    P = s["particles"]
+    # empty scans -> LidarMeasurementResult(1, 0) for that model (likelihood.cpp:111-114, beam.cpp:130-133)
+    r = eng.measure(P, None, None, s["origins"])
+    assert (r["score_like"] == 1).all() and (r["match_cnt"] == 0).all() and (r["score_beam"] == 1).all()
+    r = eng.measure(P, s["lik"], None, None)
+    w = cpu.measure(P, s["lik"], None, s["origins"])
+    assert (r["score_beam"] == 1).all() and np.array_equal(r["match_cnt"], w["match_cnt"])
+    r = eng.measure(P, None, s["beam"], s["origins"])
+    w = cpu.measure(P, None, s["beam"], s["origins"])
+    assert (r["score_like"] == 1).all() and np.array_equal(r["score_beam"], w["score_beam"])
+    # zero particles
+    assert len(eng.measure(P[:0], s["lik"], s["beam"], s["origins"])) == 0
+    # one particle, particle far outside the map (every ray LONG: begin outside the AABB, raycast_using_dda.h:70-75)
+    far = synth.make_poses([[1e4, 1e4, 1e4]], [[0, 0, 0, 1]])
+    r = eng.measure(far, s["lik"], s["beam"], s["origins"])
+    assert r["n_long"][0] == 16 and r["match_cnt"][0] == 0 and r["score_like"][0] == 0
+    # beam label out of the origins range is rejected, not read out of bounds
+    bad = s["beam"].copy()
+    bad["label"][3] = 7
+    with pytest.raises(eng_mod.EngineError) as ei:
+        eng.measure(P, s["lik"], bad, s["origins"])
+    assert ei.value.code == -1
+    # non-unit and negated quaternions behave like the reference (normalised for points, raw for origins)
+    Q = P.copy()
+    for f in ("qx", "qy", "qz", "qw"):
+        Q[f] *= np.float32(-1.7)
+    check_records(eng.measure(Q, s["lik"], s["beam"], s["origins"]), cpu.measure(Q, s["lik"], s["beam"], s["origins"]), 16)
+
+
+def test_errors_without_map(eng_mod):
+    e = eng_mod.Engine((0,))
+    with pytest.raises(eng_mod.EngineError) as ei:
+        e.measure(synth.make_poses([[0, 0, 0]], [[0, 0, 0, 1]]), synth.make_points([[1, 0, 0]]), None, None)
+    assert ei.value.code == -2
+    e.close()
+
+
+def test_large_scan_unstaged_path(eng_mod, eng, cc):
+    """More scan points than fit the shared-memory tile (> 200 KiB): the direct-from-global variant."""
+    s = synth.scene(30_000, 6, 13_500, 13_000, seed=31)
+    cpu = run_both(eng_mod, eng, cc, s, (1, 1, 5), 64)
+    check_records(eng.measure(s["particles"], s["lik"], s["beam"], s["origins"]),
+                  cpu.measure(s["particles"], s["lik"], s["beam"], s["origins"]), 13_000)
+
+
+def test_set_params_and_restage(eng_mod, eng, cc):
+    s = synth.scene(20_000, 32, 64, 32, seed=41)
+    cpu = run_both(eng_mod, eng, cc, s, (1, 1, 5), 32)
+    a = eng.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+    # scalar refresh without restaging (refreshParameters)
+    lik2 = eng_mod.LikParams(match_weight=2.5, match_dist_flat=0.1, dist_weight=(1, 1, 5))
+    eng.set_params(lik2, None)
+    b = eng.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+    assert np.array_equal(a["n_hit"], b["n_hit"]) and not np.array_equal(a["score_like"], b["score_like"])
+    port = cc.CpuChecker("port")
+    cpu2 = port.create(s["map"], cc.lik_params(2.5, 0.2, 0.1, (1, 1, 5)), cc.beam_raw(num_points_default=32), 20.0, 0.4)
+    check_records(b, cpu2.measure(s["particles"], s["lik"], s["beam"], s["origins"]), 32)
+    # changing the radius needs a restage
+    with pytest.raises(eng_mod.EngineError):
+        eng.set_params(eng_mod.LikParams(match_dist_min=0.3, dist_weight=(1, 1, 5)), None)
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE configs 2 and 3)
+@pytest.fixture(scope="module")
+def big_scene():
+    return synth.scene(1_000_000, 4096, 512, 256, seed=51)
+
+
+def test_full_size_properties(eng_mod, eng, cc, big_scene):
+    s = big_scene
+    lik = eng_mod.LikParams(dist_weight=(1, 1, 5))
+    beam = eng_mod.beam_params_from_reference(num_points_default=256, dda_grid_size=0.2)
+    eng.set_map(s["map"], lik, beam)
+    P = s["particles"]
+    full = eng.measure(P[:1024], s["lik"], None, None)            # config 2: 1024 x 512 likelihood
+    beam_full = eng.measure(P, None, s["beam"], s["origins"])     # config 3: 4096 x 256 beam DDA
+    # (1) permutation equivariance over particles, bit-exact (deterministic reductions)
+    perm = np.random.default_rng(5).permutation(1024)
+    assert np.array_equal(eng.measure(P[:1024][perm], s["lik"], None, None), full[perm])
+    # (2) scan additivity: counts add exactly, scores to rounding
+    a = eng.measure(P[:1024], s["lik"][:200], None, None)
+    b = eng.measure(P[:1024], s["lik"][200:], None, None)
+    assert np.array_equal(a["match_cnt"] + b["match_cnt"], full["match_cnt"])
+    assert np.allclose(a["score_like"] + b["score_like"], full["score_like"], rtol=1e-5, atol=1e-5)
+    # (3) every ray is classified exactly once; beam tallies add over a split of the rays
+    assert ((beam_full["n_short"] + beam_full["n_hit"] + beam_full["n_long"]) == 256).all()
+    h1 = eng.measure(P, None, s["beam"][:100], s["origins"])
+    h2 = eng.measure(P, None, s["beam"][100:], s["origins"])
+    for f in ("n_short", "n_hit", "n_long"):
+        assert np.array_equal(h1[f] + h2[f], beam_full[f])
+    # (4) duplicated particles give identical records; idempotence of repeated calls
+    dup = np.concatenate([P[:7], P[:7]])
+    d = eng.measure(dup, s["lik"], s["beam"], s["origins"])
+    assert np.array_equal(d[:7], d[7:])
+    assert np.array_equal(eng.measure(P[:1024], s["lik"], None, None), full)
+    # (5) a strided sample of the full-size job against the oracle
+    port = cc.CpuChecker("port")
+    cpu = port.create(s["map"], cc.lik_params(dist_weight=(1, 1, 5)), cc.beam_raw(num_points_default=256), 20.0, 0.4)
+    idx = np.arange(0, 4096, 128)
+    want = cpu.measure(P[idx], s["lik"], s["beam"], s["origins"])
+    got = eng.measure(P[idx], s["lik"], s["beam"], s["origins"])
+    check_records(got, want, 256)
+    assert np.array_equal(got["n_hit"], beam_full["n_hit"][idx])
+
+
+def test_device_resident_entry_matches_host_entry(eng_mod, eng, big_scene):
+    import torch
+    s = big_scene
+    lik = eng_mod.LikParams(dist_weight=(1, 1, 5))
+    beam = eng_mod.beam_params_from_reference(num_points_default=256, dda_grid_size=0.2)
+    eng.set_map(s["map"], lik, beam)
+    P = s["particles"][:777]
+    want = eng.measure(P, s["lik"], s["beam"], s["origins"])
+    dev = torch.device("cuda:0")
+
+    def up(a):
+        return torch.from_numpy(np.frombuffer(np.ascontiguousarray(a).tobytes(), dtype=np.uint8).copy()).to(dev)
+    d_p, d_l, d_b = up(P), up(s["lik"]), up(s["beam"])
+    d_o = torch.from_numpy(np.ascontiguousarray(s["origins"], dtype=np.float32)).to(dev)
+    d_out = torch.zeros(len(P) * 24, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    eng.measure_device(d_p.data_ptr(), len(P), d_l.data_ptr(), len(s["lik"]), d_b.data_ptr(), len(s["beam"]),
+                       d_o.data_ptr(), len(s["origins"]), d_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    got = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=synth.RESULT)
+    assert np.array_equal(got, want)
+
+
+def test_multi_device_engine_matches_single(eng_mod, big_scene):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = big_scene
+    lik = eng_mod.LikParams(dist_weight=(1, 1, 5))
+    beam = eng_mod.beam_params_from_reference(num_points_default=256, dda_grid_size=0.2)
+    e1, e2 = eng_mod.Engine((0,)), eng_mod.Engine((0, 1))
+    e1.set_map(s["map"], lik, beam)
+    e2.set_map(s["map"], lik, beam)
+    P = s["particles"][:1001]
+    assert np.array_equal(e1.measure(P, s["lik"], s["beam"], s["origins"]), e2.measure(P, s["lik"], s["beam"], s["origins"]))
+    e1.close()
+    e2.close()
