@@ -39,6 +39,7 @@ WORKLOADS = {
     "c4": (10_000_000, 16384, 1024, 1024, False, 0.1, "strong"),
     "c5": (1_000_000, 65536, 64, 8, True, 0.2, "strong"),
 }
+FORCE_SPREAD = False
 DIST_WEIGHT = (1.0, 1.0, 5.0)  # the node's default metric (src/parameters.cpp:108-111)
 MAP_VOXEL = 0.1
 
@@ -111,6 +112,7 @@ def as_u8(a):
 
 def build_scene(workload, rank, world):
     n_map, P, n_lik, n_beam, spread, dda, scaling = WORKLOADS[workload]
+    spread = spread or FORCE_SPREAD
     P_rank = P if scaling == "weak" else P // world
     s = synth.scene(n_map, P, n_lik, n_beam, spread=spread, n_origins=2, seed=1000)
     if scaling == "weak":
@@ -148,12 +150,14 @@ def cpu_arm(workload, s, dda, n_lik, n_beam, target_s, threads, want_kind=None):
     rate = len(probe) * per_particle / dt
     n_sample = int(min(len(s["particles"]), max(len(probe), rate * target_s / per_particle)))
     sample = s["particles"][:n_sample]
+    reps = int(max(1, min(200, round(target_s / max(n_sample * per_particle / rate, 1e-6)))))
     t0 = time.perf_counter()
-    cpu.measure(sample, s["lik"], s["beam"], s["origins"], n_threads=threads)
-    dt = time.perf_counter() - t0
-    meta = {"kind": kind, "cores": threads, "index_build_s": round(build_s, 3), "seconds": round(dt, 3),
-            "sample": "%d of %d particles x (%d lik + %d beam) pts, same map/scan, %d thread(s)"
-                      % (n_sample, len(s["particles"]), n_lik, n_beam, threads)}
+    for _ in range(reps):
+        cpu.measure(sample, s["lik"], s["beam"], s["origins"], n_threads=threads)
+    dt = (time.perf_counter() - t0) / reps
+    meta = {"kind": kind, "cores": threads, "index_build_s": round(build_s, 3), "seconds": round(dt * reps, 3),
+            "sample": "%d of %d particles x (%d lik + %d beam) pts x %d repeats, same map/scan, %d thread(s)"
+                      % (n_sample, len(s["particles"]), n_lik, n_beam, reps, threads)}
     return n_sample, dt, cpu, meta
 
 
@@ -212,8 +216,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spread", action="store_true", help="spread (global-localisation style) particles: the HBM-bound variant")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global FORCE_SPREAD
+    FORCE_SPREAD = args.spread
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -232,6 +239,7 @@ def main():
     dev = torch.device("cuda", local)
 
     n_map, P, n_lik, n_beam, spread, _, _ = WORKLOADS[args.workload]
+    spread = spread or args.spread
     s, dda, scaling, P_rank = build_scene(args.workload, rank, world)
     eng = engine.Engine((local,))  # no fallback: raises without the CUDA library / device
     lik = engine.LikParams(dist_weight=DIST_WEIGHT)
@@ -305,18 +313,28 @@ def main():
         kern["beam"] = timed(beam_only, args.steps) / args.steps
     peak, peak_src = peaks()
     dom = max(kern, key=kern.get)
+    # exact work counters of one (untimed) step: what this layout's algorithm must read, no reuse assumed
+    eng.collect_stats(True)
+    step()
+    ws = eng.read_stats()
+    eng.collect_stats(False)
+    io_bytes = P_rank * 32 + P_rank * 24
     bpe, cells = bytes_per_eval_model()
     if dom == "lik":
-        alg_bytes = P_rank * n_lik * bpe + P_rank * 32 + n_lik * 16 + P_rank * 24
-        note = "%d B/eval = 16 B x %d cells (SURVEY 8d exact mode) + poses/scan/records" % (bpe, cells)
+        alg_bytes = ws["lik_index_rows"] * 8 + ws["lik_points_scanned"] * 16 + io_bytes + n_lik * 16
+        note = ("counted: %.1f CSR rows x 8 B + %.1f map points x 16 B per eval (+ poses/scan/records)"
+                % (ws["lik_index_rows"] / max(P_rank * n_lik, 1), ws["lik_points_scanned"] / max(P_rank * n_lik, 1)))
+        survey_bytes = P_rank * n_lik * bpe + io_bytes + n_lik * 16
+        survey_note = "SURVEY 8d exact mode, dense float4 voxel grid: %d B/eval = 16 B x %d cells" % (bpe, cells)
     else:
-        # per ray: 1 bit... the model of SURVEY 8d: 1 B per cell stepped + 24 B per occupied cell tested;
-        # steps ~ 1.5 * L / g with L ~ mean ray length
-        ends = np.stack([s["beam"]["x"], s["beam"]["y"], s["beam"]["z"]], 1)
-        mean_len = float(np.linalg.norm(ends, axis=1).mean()) + 0.3
-        steps = 1.5 * mean_len / dda
-        alg_bytes = P_rank * n_beam * (steps * 1.0 + 24.0) + P_rank * 32 + n_beam * 16 + P_rank * 24
-        note = "per ray ~%.0f cells x 1 B occupancy + 24 B hit test (SURVEY 8d beam model)" % steps
+        alg_bytes = (ws["beam_cells_stepped"] * 4 + ws["beam_cells_occupied"] * 8 + ws["beam_points_tested"] * 16
+                     + io_bytes + n_beam * 16)
+        note = ("counted: %.1f cells stepped x 4 B occupancy word + %.2f occupied x 8 B CSR + %.2f pts x 16 B per ray"
+                % (ws["beam_cells_stepped"] / max(P_rank * n_beam, 1), ws["beam_cells_occupied"] / max(P_rank * n_beam, 1),
+                   ws["beam_points_tested"] / max(P_rank * n_beam, 1)))
+        survey_bytes = (ws["beam_cells_stepped"] * 1 + ws["beam_cells_occupied"] * 8 + ws["beam_points_tested"] * 16
+                        + io_bytes + n_beam * 16)
+        survey_note = "SURVEY 8d beam: 1 B per cell stepped + 8 B CSR + 16 B per point tested"
     achieved = alg_bytes / (kern[dom] * 1e-3) / 1e9
     traffic = None
     try:
@@ -327,7 +345,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                 "kernel_ms": kern[dom], "algorithmic_bytes_per_launch": alg_bytes, "model": note,
-                "kernel_ms_all": kern}
+                "kernel_ms_all": kern, "work_counters_per_step": ws,
+                "survey_8d_model": {"bytes_per_launch": survey_bytes, "achieved": survey_bytes / (kern[dom] * 1e-3) / 1e9,
+                                    "frac": survey_bytes / (kern[dom] * 1e-3) / 1e9 / peak, "note": survey_note}}
 
     # ---- e2e: the host-buffer C-ABI call (pinned staging + H2D + kernels + D2H inside the call)
     out_host = np.zeros(P_rank, dtype=synth.RESULT)

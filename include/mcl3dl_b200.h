@@ -113,6 +113,17 @@ typedef struct
   double build_ms;       /* device build time of the last set_map */
 } mcl3dl_map_info;
 
+/* Work counters accumulated over every measure call while collection is enabled (the reference logs
+ * only a wall time, src/mcl_3dl.cpp:827-829; these feed the status path and the roofline arithmetic). */
+typedef struct
+{
+  uint64_t lik_index_rows;      /* x-rows of the search grid whose two CSR bounds were read (8 B each) */
+  uint64_t lik_points_scanned;  /* map points distance-tested (16 B each) */
+  uint64_t beam_cells_stepped;  /* DDA cells visited (1 occupancy bit each) */
+  uint64_t beam_cells_occupied; /* occupied cells whose point list was opened (8 B CSR each) */
+  uint64_t beam_points_tested;  /* map points cone-tested (16 B each) */
+} mcl3dl_work_stats;
+
 typedef struct mcl3dl_engine mcl3dl_engine;
 
 /* Create an engine on the given CUDA devices (n_devices >= 1; device_ids == NULL means 0..n-1).
@@ -174,6 +185,10 @@ void mcl3dl_beam_params_from_reference(mcl3dl_beam_params* out,
                                        float ray_angle_half, float dda_grid_size);
 
 int mcl3dl_get_map_info(const mcl3dl_engine*, mcl3dl_map_info* out);
+
+/* Enable (and zero) / disable the work counters; read them (synchronises the devices). */
+int mcl3dl_collect_stats(mcl3dl_engine*, int enable);
+int mcl3dl_read_stats(mcl3dl_engine*, mcl3dl_work_stats* out);
 
 /* Device times of the last mcl3dl_measure call (CUDA events on the engine's stream, max over
  * devices): host->device copies, the two kernels, device->host copy. */

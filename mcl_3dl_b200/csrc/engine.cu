@@ -170,6 +170,9 @@ struct DeviceCtx
   void* h_pinned = nullptr;
   size_t h_pinned_cap = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  DevBuf d_stats;            // 5 x uint64 work counters, only written while stats collection is on
+  bool stats_on = false;
+  unsigned long long* stats_ptr() const { return stats_on ? static_cast<unsigned long long*>(d_stats.p) : nullptr; }
 };
 }  // namespace
 
@@ -259,11 +262,11 @@ int launch_lik_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int
   if (bytes <= static_cast<size_t>(kMaxStagedBytes))
   {
     CK(cudaFuncSetAttribute(lik_kernel<TPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStagedBytes));
-    lik_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults);
+    lik_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
   }
   else
   {
-    lik_kernel<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults);
+    lik_kernel<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
   }
   CK(cudaGetLastError());
   eng->launches++;
@@ -281,11 +284,11 @@ int launch_beam_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, in
   if (bytes <= static_cast<size_t>(kMaxStagedBytes))
   {
     CK(cudaFuncSetAttribute(beam_kernel<TPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStagedBytes));
-    beam_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, origins, c.dda, out, status, lik_defaults);
+    beam_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, origins, c.dda, out, status, lik_defaults, c.stats_ptr());
   }
   else
   {
-    beam_kernel<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, origins, c.dda, out, status, lik_defaults);
+    beam_kernel<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, origins, c.dda, out, status, lik_defaults, c.stats_ptr());
   }
   CK(cudaGetLastError());
   eng->launches++;
@@ -681,7 +684,7 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     if (c.stream)
       cudaStreamSynchronize(c.stream);
     for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.d_poses, &c.d_lik,
-                      &c.d_beam, &c.d_origins_raw, &c.d_origins, &c.d_out, &c.d_status})
+                      &c.d_beam, &c.d_origins_raw, &c.d_origins, &c.d_out, &c.d_status, &c.d_stats})
       free_buf(*b);
     if (c.h_pinned)
       cudaFreeHost(c.h_pinned);
@@ -944,6 +947,44 @@ int mcl3dl_beam_status(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, c
   if (n_beam == 0)
     return MCL3DL_OK;
   return measure_host(eng, poses, P, nullptr, 0, beam_pts, n_beam, origins_xyz, n_origins, nullptr, status);
+}
+
+int mcl3dl_collect_stats(mcl3dl_engine* eng, int enable)
+{
+  if (!eng)
+    return MCL3DL_ERR_INVALID_ARG;
+  for (DeviceCtx& c : eng->devs)
+  {
+    CK(cudaSetDevice(c.dev));
+    int rc = reserve(eng, c.d_stats, 5 * sizeof(unsigned long long));
+    if (rc != MCL3DL_OK)
+      return rc;
+    CK(cudaMemset(c.d_stats.p, 0, 5 * sizeof(unsigned long long)));
+    c.stats_on = enable != 0;
+  }
+  return MCL3DL_OK;
+}
+
+int mcl3dl_read_stats(mcl3dl_engine* eng, mcl3dl_work_stats* out)
+{
+  if (!eng || !out)
+    return MCL3DL_ERR_INVALID_ARG;
+  std::memset(out, 0, sizeof(*out));
+  for (DeviceCtx& c : eng->devs)
+  {
+    if (!c.d_stats.p)
+      continue;
+    unsigned long long h[5];
+    CK(cudaSetDevice(c.dev));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h, c.d_stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+    out->lik_index_rows += h[0];
+    out->lik_points_scanned += h[1];
+    out->beam_cells_stepped += h[2];
+    out->beam_cells_occupied += h[3];
+    out->beam_points_tested += h[4];
+  }
+  return MCL3DL_OK;
 }
 
 void mcl3dl_beam_params_from_reference(mcl3dl_beam_params* o, float map_grid_x, float map_grid_y, float map_grid_z,

@@ -151,7 +151,8 @@ __device__ __forceinline__ void group_reduce(float& f, uint32_t& a, uint32_t& b,
 
 // --------------------------------------------------------------------------------------------
 // Exact nearest-neighbour distance^2 (rescaled metric) within the radius; returns r2 if none.
-__device__ __forceinline__ float nn_dist2(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz)
+__device__ __forceinline__ float nn_dist2(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz,
+                                          uint32_t& n_rows, uint32_t& n_pts)
 {
   // Same cell function as the build kernel (monotone in its argument), applied to q -/+ rpad.
   int lx = __float2int_rd(fmul(fsub(fsub(qx, lp.rpad), g.ox), g.inv_cell));
@@ -169,6 +170,7 @@ __device__ __forceinline__ float nn_dist2(const NnGridDev& g, const LikDev& lp, 
   float best = lp.r2;
   if (lx > hx || ly > hy || lz > hz)
     return best;
+  n_rows += static_cast<uint32_t>((hz - lz + 1) * (hy - ly + 1));
   for (int iz = lz; iz <= hz; ++iz)
   {
     for (int iy = ly; iy <= hy; ++iy)
@@ -176,6 +178,7 @@ __device__ __forceinline__ float nn_dist2(const NnGridDev& g, const LikDev& lp, 
       const int row = (iz * g.ny + iy) * g.nx;
       const uint32_t s0 = __ldg(g.cell_start + row + lx);
       const uint32_t s1 = __ldg(g.cell_start + row + hx + 1);
+      n_pts += s1 - s0;
       for (uint32_t s = s0; s < s1; ++s)
       {
         const float4 m = __ldg(g.pts + s);
@@ -194,7 +197,8 @@ __device__ __forceinline__ float nn_dist2(const NnGridDev& g, const LikDev& lp, 
 template <int TPP, bool STAGED>
 __global__ void __launch_bounds__(kBlockThreads)
     lik_kernel(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N, NnGridDev g,
-               LikDev lp, mcl3dl_result* __restrict__ out, int write_beam_defaults)
+               LikDev lp, mcl3dl_result* __restrict__ out, int write_beam_defaults,
+               unsigned long long* __restrict__ stats)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
@@ -210,6 +214,7 @@ __global__ void __launch_bounds__(kBlockThreads)
   const int sub = threadIdx.x / TPP;
   const int l = threadIdx.x % TPP;
   const int n_groups = (P + PPB - 1) / PPB;
+  uint32_t st_rows = 0, st_pts = 0;
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
   {
     const int p = grp * PPB + sub;
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(kBlockThreads)
         v.z = sp.z;
         const F3 t = transform_point(rn, pos, v);
         // PointRepresentation::vectorize with rescale values (mcl_3dl.cpp:1270)
-        const float d2 = nn_dist2(g, lp, fmul(t.x, g.wx), fmul(t.y, g.wy), fmul(t.z, g.wz));
+        const float d2 = nn_dist2(g, lp, fmul(t.x, g.wx), fmul(t.y, g.wy), fmul(t.z, g.wz), st_rows, st_pts);
         if (d2 < lp.r2)
         {
           // likelihood.cpp:128-133
@@ -268,6 +273,16 @@ __global__ void __launch_bounds__(kBlockThreads)
       }
     }
   }
+  if (stats)
+  {
+    // per-call counters (the node's status path wants evals/steps): index rows read, map points scanned
+    const uint32_t r = warp_sum_u32(st_rows), q = warp_sum_u32(st_pts);
+    if ((threadIdx.x & 31) == 0)
+    {
+      atomicAdd(stats + 0, static_cast<unsigned long long>(r));
+      atomicAdd(stats + 1, static_cast<unsigned long long>(q));
+    }
+  }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -278,7 +293,8 @@ __device__ __forceinline__ int dda_to_index(float v, float mn, double grid)
   return __double2int_rz(ddiv(static_cast<double>(fsub(v, mn)), grid));
 }
 
-__device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const F3& e)
+__device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const F3& e, uint32_t& n_steps,
+                                        uint32_t& n_occ, uint32_t& n_tested)
 {
   // isPointWithinMap, :260-270
   if (b.x < g.min_x || g.max_x < b.x || b.y < g.min_y || g.max_y < b.y || b.z < g.min_z || g.max_z < b.z)
@@ -330,6 +346,7 @@ __device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const 
   // getNextCastResult, :106-159: at most max_movement-1 cells; begin and end cells are never tested
   for (int pos = 1; pos < max_movement; ++pos)
   {
+    ++n_steps;
     // strict-'<' ladder (:114-147); on ties z beats y beats x.  incrementIndex (:192-203) recomputes
     // t_max from the start: float * float(int) + float.
     if (tx < ty ? tx < tz : false)
@@ -359,8 +376,10 @@ __device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const 
     // hasIntersection, :237-258: first point of the cell, in map order, inside the cone
     const uint32_t s0 = __ldg(g.cell_start + cell);
     const uint32_t s1 = __ldg(g.cell_start + cell + 1);
+    ++n_occ;
     for (uint32_t s = s0; s < s1; ++s)
     {
+      ++n_tested;
       const float4 m = __ldg(g.pts + s);
       F3 rel;
       rel.x = fsub(m.x, b.x);
@@ -394,7 +413,7 @@ template <int TPP, bool STAGED>
 __global__ void __launch_bounds__(kBlockThreads)
     beam_kernel(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N,
                 const float4* __restrict__ origins, DdaGridDev g, mcl3dl_result* __restrict__ out,
-                uint8_t* __restrict__ status, int write_lik_defaults)
+                uint8_t* __restrict__ status, int write_lik_defaults, unsigned long long* __restrict__ stats)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
@@ -410,6 +429,7 @@ __global__ void __launch_bounds__(kBlockThreads)
   const int sub = threadIdx.x / TPP;
   const int l = threadIdx.x % TPP;
   const int n_groups = (P + PPB - 1) / PPB;
+  uint32_t st_steps = 0, st_occ = 0, st_tested = 0;
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
   {
     const int p = grp * PPB + sub;
@@ -448,7 +468,7 @@ __global__ void __launch_bounds__(kBlockThreads)
         begin.x = fadd(pos.x, ro.x);
         begin.y = fadd(pos.y, ro.y);
         begin.z = fadd(pos.z, ro.z);
-        const int st = cast_ray(g, begin, end);
+        const int st = cast_ray(g, begin, end, st_steps, st_occ, st_tested);
         n_short += (st == ST_SHORT);
         n_hit += (st == ST_HIT);
         n_long += (st == ST_LONG);
@@ -478,6 +498,16 @@ __global__ void __launch_bounds__(kBlockThreads)
         out[p].score_like = 1.0f;
         out[p].match_cnt = 0;
       }
+    }
+  }
+  if (stats)
+  {
+    const uint32_t a = warp_sum_u32(st_steps), b = warp_sum_u32(st_occ), c = warp_sum_u32(st_tested);
+    if ((threadIdx.x & 31) == 0)
+    {
+      atomicAdd(stats + 2, static_cast<unsigned long long>(a));
+      atomicAdd(stats + 3, static_cast<unsigned long long>(b));
+      atomicAdd(stats + 4, static_cast<unsigned long long>(c));
     }
   }
 }

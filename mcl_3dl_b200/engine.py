@@ -53,7 +53,16 @@ class MapInfo(C.Structure):
                 ("dda_max", C.c_float * 3), ("device_bytes", C.c_uint64), ("build_ms", C.c_double)]
 
 
-EXPORTED_SYMBOLS = ["mcl3dl_abi_version", "mcl3dl_create", "mcl3dl_destroy", "mcl3dl_set_map", "mcl3dl_set_params",
+class WorkStats(C.Structure):
+    _fields_ = [("lik_index_rows", C.c_uint64), ("lik_points_scanned", C.c_uint64),
+                ("beam_cells_stepped", C.c_uint64), ("beam_cells_occupied", C.c_uint64),
+                ("beam_points_tested", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+EXPORTED_SYMBOLS = ["mcl3dl_collect_stats", "mcl3dl_read_stats", "mcl3dl_abi_version", "mcl3dl_create", "mcl3dl_destroy", "mcl3dl_set_map", "mcl3dl_set_params",
                     "mcl3dl_measure", "mcl3dl_measure_device", "mcl3dl_beam_status",
                     "mcl3dl_beam_params_from_reference", "mcl3dl_get_map_info", "mcl3dl_last_timing",
                     "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail"]
@@ -88,6 +97,8 @@ def load_library():
                                                     C.c_uint32, C.c_float, C.c_int, C.c_float, C.c_float]
     L.mcl3dl_beam_params_from_reference.restype = None
     L.mcl3dl_get_map_info.argtypes = [vp, vp]
+    L.mcl3dl_collect_stats.argtypes = [vp, C.c_int]
+    L.mcl3dl_read_stats.argtypes = [vp, vp]
     L.mcl3dl_last_timing.argtypes = [vp] + [C.POINTER(C.c_double)] * 4
     L.mcl3dl_kernel_launches.argtypes = [vp]
     L.mcl3dl_kernel_launches.restype = C.c_uint64
@@ -186,6 +197,14 @@ class Engine:
         self._check(self.L.mcl3dl_beam_status(self.h, _ptr(poses), len(poses), _ptr(beam_pts), len(beam_pts),
                                               _ptr(origins), len(origins), _ptr(st)))
         return st
+
+    def collect_stats(self, enable=True):
+        self._check(self.L.mcl3dl_collect_stats(self.h, 1 if enable else 0))
+
+    def read_stats(self):
+        ws = WorkStats()
+        self._check(self.L.mcl3dl_read_stats(self.h, C.byref(ws)))
+        return ws.as_dict()
 
     def last_timing(self):
         v = [C.c_double(0) for _ in range(4)]
