@@ -227,7 +227,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from mcl_3dl_b200 import engine
+    from mcl_3dl_b200 import engine, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -262,7 +262,7 @@ def main():
                            d_o.data_ptr(), len(s["origins"]), d_out.data_ptr(), stream)
         if world > 1:
             # the one exchange of the path: all-gather of the per-particle records over NVLink (NCCL)
-            dist.all_gather_into_tensor(d_all, d_out)
+            sharding.gather_records_device(d_out, d_all)
 
     def barrier():
         if world > 1:
@@ -381,6 +381,7 @@ def main():
         meta["value"] = n_sample * unit_pts / dt
         meta["unit"] = "evals/s"
         # parity spot check of this very workload against the checker (first particles of rank 0)
+        cpu.set_tally(True)
         chk = cpu.measure(particles[:16], s["lik"], s["beam"], s["origins"])
         ok = all(np.array_equal(chk[f], out_host[:16][f]) for f in ("match_cnt", "n_short", "n_hit", "n_long"))
         ok = ok and np.allclose(chk["score_like"], out_host[:16]["score_like"], rtol=1e-4, atol=1e-6)

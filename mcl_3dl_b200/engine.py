@@ -1,7 +1,8 @@
 """ctypes binding of include/mcl3dl_b200.h (the C ABI of the CUDA engine).
 
-`Engine` is the C-ABI handle (set_map / measure / measure_device / beam_status).  The Python
-mirror of the reference's plugin classes lives in mcl_3dl_b200/models.py on top of this.
+`Engine` is the C-ABI handle (set_map / measure / measure_device / beam_status).  The reference is
+compiled C++, so the host-side mirror of its plugin classes is C++ too:
+mcl_3dl_b200/host/lidar_measurement_model_b200.h.  This module is what tests and bench.py call.
 
 There is no fallback: if the CUDA library is missing or no device is usable, construction raises.
 """

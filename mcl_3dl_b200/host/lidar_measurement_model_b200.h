@@ -1,0 +1,318 @@
+// lidar_measurement_model_b200.h — host C++ adapter: the reference's own plugin classes with
+// measure() re-routed to the B200 engine through the C ABI (include/mcl3dl_b200.h).
+//
+// Drop-in rule: the ROS node keeps calling exactly what it calls today
+//   setGlobalLocalizationStatus / filter      once per model per update  (src/mcl_3dl.cpp:378-383)
+//   measure(kdtree, pc, origins, state)       once per particle per model, from inside
+//                                             pf_->measure(lambda)        (:402-426, pf.h:252-260)
+// and gets the same LidarMeasurementResult values.  The classes below DERIVE from the reference's
+// LidarMeasurementModelLikelihood / LidarMeasurementModelBeam, so everything except measure()
+// (refreshParameters, filter, setGlobalLocalizationStatus, getMaxSearchRange, getBeamStatus for the
+// rviz markers, and the node's dynamic_pointer_cast<LidarMeasurementModelBeam> at :471) is literally
+// the reference's code.  Only measure() changes: the first call of an update cycle batches ALL
+// particles of the attached pf::ParticleFilter into one mcl3dl_measure() call; later calls return
+// the cached record of the matching particle.
+//
+// This header needs the reference's headers (it lives in the node's build); in
+// this repository it is compiled only by oracle/adapter_parity_test.cpp against oracle/shim/.
+#ifndef MCL_3DL_B200_LIDAR_MEASUREMENT_MODEL_B200_H
+#define MCL_3DL_B200_LIDAR_MEASUREMENT_MODEL_B200_H
+
+#include <cstring>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <mcl_3dl/chunked_kdtree.h>
+#include <mcl_3dl/lidar_measurement_model_base.h>
+#include <mcl_3dl/lidar_measurement_models/lidar_measurement_model_beam.h>
+#include <mcl_3dl/lidar_measurement_models/lidar_measurement_model_likelihood.h>
+#include <mcl_3dl/parameters.h>
+#include <mcl_3dl/pf.h>
+#include <mcl_3dl/state_6dof.h>
+
+#include "mcl3dl_b200.h"
+
+namespace mcl_3dl_b200
+{
+using mcl_3dl::ChunkedKdtree;
+using mcl_3dl::LidarMeasurementResult;
+using mcl_3dl::State6DOF;
+using mcl_3dl::Vec3;
+using PointType = mcl_3dl::LidarMeasurementModelBase::PointType;
+using Cloud = pcl::PointCloud<PointType>;
+// the filter type the node instantiates (src/mcl_3dl.cpp:107)
+using ParticleFilter =
+    mcl_3dl::pf::ParticleFilter<State6DOF, float, mcl_3dl::ParticleWeightedMeanQuat, std::default_random_engine>;
+
+// State shared by the two model adapters of one node: the engine handle, the particle filter whose
+// particles are batched, the clouds of the current cycle and the cached per-particle records.
+class MeasurementBatcher
+{
+public:
+  using Ptr = std::shared_ptr<MeasurementBatcher>;
+
+  MeasurementBatcher(ParticleFilter* pf, const std::vector<int>& devices,
+                     const std::shared_ptr<mcl_3dl::LidarMeasurementModelLikelihoodParameters>& lik_params,
+                     const std::shared_ptr<mcl_3dl::LidarMeasurementModelBeamParameters>& beam_params,
+                     const float* dist_weight_xyz)
+    : pf_(pf), lik_params_(lik_params), beam_params_(beam_params), engine_(nullptr)
+  {
+    for (int k = 0; k < 3; ++k) dist_weight_[k] = dist_weight_xyz ? dist_weight_xyz[k] : 1.0f;
+    const int rc = mcl3dl_create(&engine_, devices.empty() ? nullptr : devices.data(),
+                                 devices.empty() ? 1 : static_cast<int>(devices.size()));
+    if (rc != MCL3DL_OK)  // no CPU fallback: the node must not start without its device
+      throw std::runtime_error(std::string("mcl3dl_create: ") + mcl3dl_strerror(rc));
+  }
+  ~MeasurementBatcher()
+  {
+    mcl3dl_destroy(engine_);
+  }
+  MeasurementBatcher(const MeasurementBatcher&) = delete;
+  MeasurementBatcher& operator=(const MeasurementBatcher&) = delete;
+
+  // filter() of either model ran: a new update cycle is being prepared.
+  void noteFiltered(bool is_beam, const Cloud::ConstPtr& pc)
+  {
+    (is_beam ? beam_cloud_ : lik_cloud_) = pc;
+    valid_ = false;
+  }
+
+  // The record of state `s`; batches on the first call of a cycle.
+  const mcl3dl_result& lookup(ChunkedKdtree<PointType>::Ptr& kdtree, bool is_beam, const Cloud::ConstPtr& pc,
+                              const std::vector<Vec3>& origins, const State6DOF& s)
+  {
+    const Cloud::ConstPtr& expected = is_beam ? beam_cloud_ : lik_cloud_;
+    if (pc != expected)
+    {
+      // measure() was handed a cloud that did not come from this model's last filter(): honour it
+      (is_beam ? beam_cloud_ : lik_cloud_) = pc;
+      valid_ = false;
+    }
+    if (!valid_ || !sameOrigins(origins))
+      runBatch(kdtree, origins);
+    // pf::ParticleFilter::measure walks particles_ in index order (pf.h:256); each model is called once
+    // per particle, so a per-model cursor finds the record in O(1).
+    size_t& cur = is_beam ? cursor_beam_ : cursor_lik_;
+    for (size_t tries = 0; tries < 2; ++tries)
+    {
+      if (cur < poses_.size() && samePose(poses_[cur], s))
+        return results_[cur++];
+      cur = 0;
+      for (; cur < poses_.size(); ++cur)
+        if (samePose(poses_[cur], s))
+          return results_[cur++];
+    }
+    // a state that is not one of the filter's particles (e.g. the mean pose): one-particle call
+    single_pose_ = toPose(s);
+    callEngine(&single_pose_, 1, origins, &single_result_);
+    return single_result_;
+  }
+  size_t likPoints() const { return lik_cloud_ ? lik_cloud_->size() : 0; }
+  mcl3dl_engine* engine() { return engine_; }
+
+private:
+  static mcl3dl_pose toPose(const State6DOF& s)
+  {
+    mcl3dl_pose p;
+    p.px = s.pos_.x_;
+    p.py = s.pos_.y_;
+    p.pz = s.pos_.z_;
+    p._pad = 0.0f;
+    p.qx = s.rot_.x_;
+    p.qy = s.rot_.y_;
+    p.qz = s.rot_.z_;
+    p.qw = s.rot_.w_;
+    return p;
+  }
+  static bool samePose(const mcl3dl_pose& p, const State6DOF& s)
+  {
+    const mcl3dl_pose q = toPose(s);
+    return std::memcmp(&p, &q, sizeof(p)) == 0;  // bitwise, as the records are per exact state
+  }
+  bool sameOrigins(const std::vector<Vec3>& o) const
+  {
+    if (o.size() * 3 != origins_.size())
+      return false;
+    for (size_t k = 0; k < o.size(); ++k)
+      if (o[k].x_ != origins_[3 * k] || o[k].y_ != origins_[3 * k + 1] || o[k].z_ != origins_[3 * k + 2])
+        return false;
+    return true;
+  }
+  static void pack(const Cloud::ConstPtr& pc, std::vector<mcl3dl_point>& out)
+  {
+    out.clear();
+    if (!pc)
+      return;
+    out.reserve(pc->size());
+    for (const auto& p : pc->points)  // PointXYZIL (32 B) -> 16 B, point_types.h:40-55
+      out.push_back(mcl3dl_point{p.x, p.y, p.z, p.label});
+  }
+  void check(int rc, const char* what) const
+  {
+    if (rc != MCL3DL_OK)
+      throw std::runtime_error(std::string(what) + ": " + mcl3dl_strerror(rc) + " " + mcl3dl_last_error_detail(engine_));
+  }
+  void stageMap(ChunkedKdtree<PointType>::Ptr& kdtree)
+  {
+    const Cloud::ConstPtr& map = kdtree->getInputCloud();
+    if (!map || map->empty())
+      throw std::runtime_error("mcl_3dl_b200: measure() without a map cloud");
+    // same trigger as RaycastUsingDDA::updatePointCloud (raycast_using_dda.h:162-171): cloud + header.stamp
+    if (map.get() == staged_map_ && map->header.stamp == staged_stamp_ && map->size() == staged_size_)
+    {
+      refreshScalars();
+      return;
+    }
+    std::vector<mcl3dl_point> pts;
+    pack(map, pts);
+    deriveParams();
+    check(mcl3dl_set_map(engine_, pts.data(), pts.size(), ++stamp_counter_, &lik_c_, &beam_c_), "mcl3dl_set_map");
+    staged_map_ = map.get();
+    staged_stamp_ = map->header.stamp;
+    staged_size_ = map->size();
+  }
+  void deriveParams()
+  {
+    lik_c_.match_weight = lik_params_->match_weight_;
+    lik_c_.match_dist_min = lik_params_->match_dist_min_;
+    lik_c_.match_dist_flat = lik_params_->match_dist_flat_;
+    for (int k = 0; k < 3; ++k) lik_c_.dist_weight[k] = dist_weight_[k];
+    const auto& b = *beam_params_;
+    mcl3dl_beam_params_from_reference(&beam_c_, b.map_grid_x_, b.map_grid_y_, b.map_grid_z_, b.num_points_default_,
+                                      b.beam_likelihood_min_, b.ang_total_ref_, b.filter_label_max_, b.hit_range_,
+                                      b.add_penalty_short_only_mode_ ? 1 : 0, b.ray_angle_half_, b.dda_grid_size_);
+  }
+  void refreshScalars()
+  {
+    // parameters are shared_ptr'd with the node and may be edited between updates (refreshParameters())
+    const mcl3dl_lik_params l0 = lik_c_;
+    const mcl3dl_beam_params b0 = beam_c_;
+    deriveParams();
+    if (std::memcmp(&l0, &lik_c_, sizeof(l0)) == 0 && std::memcmp(&b0, &beam_c_, sizeof(b0)) == 0)
+      return;
+    if (mcl3dl_set_params(engine_, &lik_c_, &beam_c_) != MCL3DL_OK)
+      staged_map_ = nullptr;  // a grid-shaping parameter changed: restage on the next call
+  }
+  void callEngine(const mcl3dl_pose* poses, size_t n, const std::vector<Vec3>& origins, mcl3dl_result* out)
+  {
+    std::vector<float> o(origins.size() * 3);
+    for (size_t k = 0; k < origins.size(); ++k)
+    {
+      o[3 * k] = origins[k].x_;
+      o[3 * k + 1] = origins[k].y_;
+      o[3 * k + 2] = origins[k].z_;
+    }
+    check(mcl3dl_measure(engine_, poses, n, lik_pts_.data(), lik_pts_.size(), beam_pts_.data(), beam_pts_.size(),
+                         o.data(), origins.size(), out),
+          "mcl3dl_measure");
+  }
+  void runBatch(ChunkedKdtree<PointType>::Ptr& kdtree, const std::vector<Vec3>& origins)
+  {
+    stageMap(kdtree);
+    if (!staged_map_)
+      stageMap(kdtree);
+    pack(lik_cloud_, lik_pts_);
+    pack(beam_cloud_, beam_pts_);
+    poses_.clear();
+    for (auto it = pf_->begin(); it != pf_->end(); ++it) poses_.push_back(toPose(it->state_));
+    results_.assign(poses_.size(), mcl3dl_result());
+    callEngine(poses_.data(), poses_.size(), origins, results_.data());
+    origins_.resize(origins.size() * 3);
+    for (size_t k = 0; k < origins.size(); ++k)
+    {
+      origins_[3 * k] = origins[k].x_;
+      origins_[3 * k + 1] = origins[k].y_;
+      origins_[3 * k + 2] = origins[k].z_;
+    }
+    cursor_lik_ = cursor_beam_ = 0;
+    valid_ = true;
+  }
+
+  ParticleFilter* pf_;
+  std::shared_ptr<mcl_3dl::LidarMeasurementModelLikelihoodParameters> lik_params_;
+  std::shared_ptr<mcl_3dl::LidarMeasurementModelBeamParameters> beam_params_;
+  float dist_weight_[3];
+  mcl3dl_engine* engine_;
+  mcl3dl_lik_params lik_c_;
+  mcl3dl_beam_params beam_c_;
+  const Cloud* staged_map_ = nullptr;
+  decltype(pcl::PCLHeader().stamp) staged_stamp_ = 0;
+  size_t staged_size_ = 0;
+  uint64_t stamp_counter_ = 0;
+  Cloud::ConstPtr lik_cloud_, beam_cloud_;
+  std::vector<mcl3dl_point> lik_pts_, beam_pts_;
+  std::vector<mcl3dl_pose> poses_;
+  std::vector<mcl3dl_result> results_;
+  std::vector<float> origins_;
+  size_t cursor_lik_ = 0, cursor_beam_ = 0;
+  bool valid_ = false;
+  mcl3dl_pose single_pose_;
+  mcl3dl_result single_result_;
+};
+
+// LidarMeasurementModelLikelihood with measure() served by the engine
+// (replaces src/lidar_measurement_model_likelihood.cpp:105-139).
+class LidarMeasurementModelLikelihoodB200 : public mcl_3dl::LidarMeasurementModelLikelihood
+{
+public:
+  LidarMeasurementModelLikelihoodB200(const std::shared_ptr<mcl_3dl::LidarMeasurementModelLikelihoodParameters>& params,
+                                      const MeasurementBatcher::Ptr& batcher)
+    : mcl_3dl::LidarMeasurementModelLikelihood(params), batcher_(batcher)
+  {
+  }
+  Cloud::Ptr filter(const Cloud::ConstPtr& pc, const mcl_3dl::PointCloudRandomSampler<PointType>& sampler) const override
+  {
+    Cloud::Ptr out = mcl_3dl::LidarMeasurementModelLikelihood::filter(pc, sampler);  // reference code, unchanged
+    batcher_->noteFiltered(false, out);
+    return out;
+  }
+  LidarMeasurementResult measure(ChunkedKdtree<PointType>::Ptr& kdtree, const Cloud::ConstPtr& pc,
+                                 const std::vector<Vec3>& origins, const State6DOF& s) const override
+  {
+    if (!pc || pc->size() == 0)  // likelihood.cpp:111-114
+      return LidarMeasurementResult(1, 0);
+    const mcl3dl_result& r = batcher_->lookup(kdtree, false, pc, origins, s);
+    const float match_ratio = static_cast<float>(r.match_cnt) / pc->points.size();  // :136
+    return LidarMeasurementResult(r.score_like, match_ratio);
+  }
+
+private:
+  MeasurementBatcher::Ptr batcher_;
+};
+
+// LidarMeasurementModelBeam with measure() served by the engine
+// (replaces src/lidar_measurement_model_beam.cpp:124-155; requires use_raycast_using_dda_ = true).
+class LidarMeasurementModelBeamB200 : public mcl_3dl::LidarMeasurementModelBeam
+{
+public:
+  LidarMeasurementModelBeamB200(const std::shared_ptr<mcl_3dl::LidarMeasurementModelBeamParameters>& params,
+                                const MeasurementBatcher::Ptr& batcher)
+    : mcl_3dl::LidarMeasurementModelBeam(params), batcher_(batcher)
+  {
+    if (!params->use_raycast_using_dda_)
+      throw std::runtime_error("mcl_3dl_b200: the GPU beam model implements RaycastUsingDDA; set beam/use_raycast_using_dda");
+  }
+  Cloud::Ptr filter(const Cloud::ConstPtr& pc, const mcl_3dl::PointCloudRandomSampler<PointType>& sampler) const override
+  {
+    Cloud::Ptr out = mcl_3dl::LidarMeasurementModelBeam::filter(pc, sampler);
+    batcher_->noteFiltered(true, out);
+    return out;
+  }
+  LidarMeasurementResult measure(ChunkedKdtree<PointType>::Ptr& kdtree, const Cloud::ConstPtr& pc,
+                                 const std::vector<Vec3>& origins, const State6DOF& s) const override
+  {
+    if (!pc || pc->size() == 0)  // beam.cpp:130-133
+      return LidarMeasurementResult(1, 0);
+    const mcl3dl_result& r = batcher_->lookup(kdtree, true, pc, origins, s);
+    return LidarMeasurementResult(r.score_beam, 1.0);  // :154
+  }
+
+private:
+  MeasurementBatcher::Ptr batcher_;
+};
+
+}  // namespace mcl_3dl_b200
+#endif  // MCL_3DL_B200_LIDAR_MEASUREMENT_MODEL_B200_H

@@ -1,0 +1,247 @@
+// adapter_parity_test.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Drives the host C++ adapter (mcl_3dl_b200/host/lidar_measurement_model_b200.h) exactly the way
+// MCL3dlNode::measure does (src/mcl_3dl.cpp:376-426) and compares it, particle by particle, with the
+// reference's own LidarMeasurementModelLikelihood / LidarMeasurementModelBeam running on the CPU in
+// the same process.  Built only where /root/reference exists (make -C oracle adapter), against
+// oracle/shim/; the binary lands in oracle/_ref/ and travels to the GPU box, where
+// tests/test_gpu_adapter.py runs it.
+#include <cmath>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <random>
+#include <string>
+#include <vector>
+
+#include <mcl_3dl/chunked_kdtree.h>
+#include <mcl_3dl/lidar_measurement_models/lidar_measurement_model_beam.h>
+#include <mcl_3dl/lidar_measurement_models/lidar_measurement_model_likelihood.h>
+#include <mcl_3dl/pf.h>
+#include <mcl_3dl/point_cloud_random_sampler.h>
+#include <mcl_3dl/state_6dof.h>
+
+#include "../mcl_3dl_b200/host/lidar_measurement_model_b200.h"
+
+using namespace mcl_3dl;
+using PointType = LidarMeasurementModelBase::PointType;
+using Cloud = pcl::PointCloud<PointType>;
+using PF = mcl_3dl_b200::ParticleFilter;
+
+namespace
+{
+// same idea as DummySampler in test/src/test_beam_likelihood.cpp:47-76, but keeps at most `num` points
+class HeadSampler : public PointCloudRandomSampler<PointType>
+{
+public:
+  Cloud::Ptr sample(const Cloud::ConstPtr& pc, const size_t num) const final
+  {
+    Cloud::Ptr out(new Cloud);
+    out->header = pc->header;
+    for (size_t i = 0; i < pc->points.size() && i < num; ++i) out->push_back(pc->points[i]);
+    return out;
+  }
+};
+
+class XyzRep : public pcl::PointRepresentation<PointType>
+{
+public:
+  XyzRep()
+  {
+    nr_dimensions_ = 3;
+    trivial_ = true;
+  }
+  void copyToFloatArray(const PointType& p, float* out) const override
+  {
+    out[0] = p.x;
+    out[1] = p.y;
+    out[2] = p.z;
+  }
+};
+
+PointType pt(float x, float y, float z, uint32_t label = 0)
+{
+  PointType p;
+  p.x = x;
+  p.y = y;
+  p.z = z;
+  p.label = label;
+  return p;
+}
+
+int g_fail = 0;
+#define EXPECT(cond, ...)                      \
+  do                                           \
+  {                                            \
+    if (!(cond))                               \
+    {                                          \
+      ++g_fail;                                \
+      if (g_fail < 20)                         \
+      {                                        \
+        std::fprintf(stderr, "FAIL %s: ", #cond); \
+        std::fprintf(stderr, __VA_ARGS__);     \
+        std::fprintf(stderr, "\n");            \
+      }                                        \
+    }                                          \
+  } while (0)
+
+struct Models
+{
+  std::map<std::string, LidarMeasurementModelBase::Ptr> lm;
+};
+
+// MCL3dlNode::measure's body from filter to pf_->measure (src/mcl_3dl.cpp:376-426), for one model set.
+void runCycle(Models& m, PF& pf, ChunkedKdtree<PointType>::Ptr& kdtree, const Cloud::ConstPtr& pc_local_full,
+              const PointCloudRandomSampler<PointType>& sampler, const std::vector<Vec3>& origins, size_t num_particles,
+              std::vector<float>* per_particle, float* ratio_min, float* ratio_max)
+{
+  std::map<std::string, Cloud::Ptr> pc_locals;
+  for (const auto& lm : m.lm)
+  {
+    lm.second->setGlobalLocalizationStatus(num_particles, pf.getParticleSize());
+    pc_locals[lm.first] = lm.second->filter(pc_local_full, sampler);
+  }
+  float match_ratio_min = 1.0, match_ratio_max = 0.0;
+  const auto measure_func = [&](const State6DOF& s) -> float
+  {
+    float likelihood = 1;
+    std::map<std::string, float> qualities;
+    for (const auto& lm : m.lm)
+    {
+      const LidarMeasurementResult result = lm.second->measure(kdtree, pc_locals[lm.first], origins, s);
+      likelihood *= result.likelihood;
+      qualities[lm.first] = result.quality;
+    }
+    if (match_ratio_min > qualities["likelihood"]) match_ratio_min = qualities["likelihood"];
+    if (match_ratio_max < qualities["likelihood"]) match_ratio_max = qualities["likelihood"];
+    per_particle->push_back(likelihood);
+    return likelihood;
+  };
+  pf.measure(measure_func);
+  *ratio_min = match_ratio_min;
+  *ratio_max = match_ratio_max;
+}
+}  // namespace
+
+int main(int argc, char** argv)
+{
+  const int n_particles = argc > 1 ? std::atoi(argv[1]) : 300;
+  std::mt19937 rng(42);
+  std::normal_distribution<float> n01(0.f, 1.f);
+  std::uniform_real_distribution<float> u01(0.f, 1.f);
+
+  // ---- map: 12 x 12 m floor, two walls, one labelled wall (label 2), ~0.1 m spacing
+  Cloud::Ptr map(new Cloud);
+  for (float x = 0.05f; x < 12.f; x += 0.1f)
+    for (float y = 0.05f; y < 12.f; y += 0.1f)
+      map->push_back(pt(x + 0.02f * n01(rng), y + 0.02f * n01(rng), 0.03f + 0.01f * n01(rng)));
+  for (float y = 0.05f; y < 12.f; y += 0.1f)
+    for (float z = 0.05f; z < 3.f; z += 0.1f)
+    {
+      map->push_back(pt(0.03f + 0.01f * n01(rng), y, z));
+      map->push_back(pt(11.97f + 0.01f * n01(rng), y, z, 2));
+    }
+  for (float x = 4.f; x < 6.f; x += 0.1f)
+    for (float z = 0.05f; z < 2.f; z += 0.1f)
+      map->push_back(pt(x, 7.03f + 0.01f * n01(rng), z));
+  map->header.stamp = 1234;
+
+  // ---- node configure(): kd-tree with the (1,1,5) rescale (src/mcl_3dl.cpp:1270,1326-1329)
+  const float dist_weight[4] = {1.f, 1.f, 5.f, 0.f};
+  auto rep = std::make_shared<XyzRep>();
+  rep->setRescaleValues(dist_weight);
+  ChunkedKdtree<PointType>::Ptr kdtree(new ChunkedKdtree<PointType>(20.0, 0.4));
+  kdtree->setPointRepresentation(rep);
+  kdtree->setInputCloud(map);
+
+  auto lik_params = std::make_shared<LidarMeasurementModelLikelihoodParameters>();
+  lik_params->num_points_default_ = 96;
+  auto beam_params = std::make_shared<LidarMeasurementModelBeamParameters>();
+  beam_params->num_points_default_ = 12;
+  beam_params->use_raycast_using_dda_ = true;
+  beam_params->filter_label_max_ = 1;
+
+  // ---- scan in the base frame: points of the map seen from (6, 4, 0.5) yaw 0.3, + noise; labels = sensor id
+  const Vec3 truth_pos(6.f, 4.f, 0.5f);
+  const Quat truth_rot(Vec3(0, 0, 1), 0.3f);
+  Cloud::Ptr scan(new Cloud);
+  std::uniform_int_distribution<size_t> pick(0, map->size() - 1);
+  while (scan->size() < 400)
+  {
+    const PointType& mp = map->points[pick(rng)];
+    const Vec3 local = truth_rot.inv() * (Vec3(mp.x, mp.y, mp.z) - truth_pos);
+    scan->push_back(pt(local.x_ + 0.02f * n01(rng), local.y_ + 0.02f * n01(rng), local.z_ + 0.02f * n01(rng),
+                       scan->size() % 2));
+  }
+  const std::vector<Vec3> origins = {Vec3(0.f, 0.f, 0.3f), Vec3(0.2f, -0.1f, 0.25f)};
+  const HeadSampler sampler;
+
+  // ---- two identical particle filters (same seed): one per model set
+  PF pf_ref(n_particles, 7), pf_gpu(n_particles, 7);
+  const State6DOF mean(truth_pos, truth_rot);
+  const State6DOF sigma(Vec3(0.2f, 0.2f, 0.05f), Vec3(0.02f, 0.02f, 0.1f));
+  pf_ref.init(mean, sigma);
+  pf_gpu.init(mean, sigma);
+
+  Models ref, gpu;
+  ref.lm["likelihood"] = std::make_shared<LidarMeasurementModelLikelihood>(lik_params);
+  ref.lm["beam"] = std::make_shared<LidarMeasurementModelBeam>(beam_params);
+  auto batcher = std::make_shared<mcl_3dl_b200::MeasurementBatcher>(&pf_gpu, std::vector<int>{0}, lik_params, beam_params,
+                                                                   dist_weight);
+  gpu.lm["likelihood"] = std::make_shared<mcl_3dl_b200::LidarMeasurementModelLikelihoodB200>(lik_params, batcher);
+  gpu.lm["beam"] = std::make_shared<mcl_3dl_b200::LidarMeasurementModelBeamB200>(beam_params, batcher);
+  // the node's marker path must keep working (src/mcl_3dl.cpp:471)
+  EXPECT(std::dynamic_pointer_cast<LidarMeasurementModelBeam>(gpu.lm["beam"]) != nullptr, "dynamic_pointer_cast");
+
+  for (int cycle = 0; cycle < 3; ++cycle)
+  {
+    std::vector<float> a, b;
+    float amin, amax, bmin, bmax;
+    // cycle 2 emulates global localisation: more particles than num_particles shrink the scan (likelihood.cpp:63-77)
+    const size_t nominal = cycle == 2 ? n_particles / 4 : n_particles;
+    runCycle(ref, pf_ref, kdtree, scan, sampler, origins, nominal, &a, &amin, &amax);
+    runCycle(gpu, pf_gpu, kdtree, scan, sampler, origins, nominal, &b, &bmin, &bmax);
+    EXPECT(a.size() == b.size() && a.size() == static_cast<size_t>(n_particles), "sizes %zu %zu", a.size(), b.size());
+    double worst = 0;
+    for (size_t i = 0; i < a.size() && i < b.size(); ++i)
+    {
+      const double rel = std::fabs(a[i] - b[i]) / std::max(1e-6, static_cast<double>(std::fabs(a[i])));
+      worst = std::max(worst, rel);
+      EXPECT(rel <= 1e-4, "cycle %d particle %zu: ref %.9g gpu %.9g", cycle, i, a[i], b[i]);
+    }
+    EXPECT(amin == bmin && amax == bmax, "match ratio min/max %g/%g vs %g/%g", amin, amax, bmin, bmax);
+    // posterior weights and entropy after pf.measure (pf.h:252-279)
+    auto ir = pf_ref.begin();
+    auto ig = pf_gpu.begin();
+    for (; ir != pf_ref.end(); ++ir, ++ig)
+      EXPECT(std::fabs(ir->probability_ - ig->probability_) <= 1e-4 * std::fabs(ir->probability_) + 1e-9,
+             "posterior %g vs %g", ir->probability_, ig->probability_);
+    EXPECT(std::fabs(pf_ref.getEntropy() - pf_gpu.getEntropy()) <= 1e-4 * std::fabs(pf_ref.getEntropy()) + 1e-6,
+           "entropy %g vs %g", pf_ref.getEntropy(), pf_gpu.getEntropy());
+    std::printf("cycle %d: %zu particles, worst relative diff %.3g, match ratio [%g, %g], entropy %g\n", cycle, a.size(),
+                worst, amin, amax, pf_ref.getEntropy());
+    // resample both filters identically (same engine seed and same weights up to 1e-4 can still diverge;
+    // so copy the reference filter's particles into the GPU one to keep the comparison per-particle)
+    pf_ref.resample(State6DOF(Vec3(0.05f, 0.05f, 0.01f), Vec3(0.005f, 0.005f, 0.02f)));
+    ir = pf_ref.begin();
+    ig = pf_gpu.begin();
+    for (; ir != pf_ref.end(); ++ir, ++ig) *ig = *ir;
+  }
+  // a state that is not a particle (mean pose): served by a one-particle engine call
+  {
+    const State6DOF e = pf_ref.expectation(1.0);
+    Cloud::Ptr pcl = ref.lm["likelihood"]->filter(scan, sampler);
+    Cloud::Ptr pcg = gpu.lm["likelihood"]->filter(scan, sampler);
+    const LidarMeasurementResult r1 = ref.lm["likelihood"]->measure(kdtree, pcl, origins, e);
+    const LidarMeasurementResult r2 = gpu.lm["likelihood"]->measure(kdtree, pcg, origins, e);
+    EXPECT(std::fabs(r1.likelihood - r2.likelihood) <= 1e-4 * std::fabs(r1.likelihood) && r1.quality == r2.quality,
+           "mean pose: %g/%g vs %g/%g", r1.likelihood, r1.quality, r2.likelihood, r2.quality);
+  }
+  if (g_fail)
+  {
+    std::fprintf(stderr, "ADAPTER PARITY FAILED (%d)\n", g_fail);
+    return 1;
+  }
+  std::printf("ADAPTER PARITY OK\n");
+  return 0;
+}
