@@ -25,17 +25,19 @@ def stale():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an experiment variant (e.g. defines=["MCL_FAST_DIV=0"], out="/tmp/x.so")."""
+    if not force and not stale() and out is None:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = ([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines]
+           + ["-o", out or LIB] + SOURCES)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (r.stdout, r.stderr))
     if verbose:
         print(r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -22,6 +22,7 @@ using namespace mcl3dl;
 namespace
 {
 constexpr int kMaxStagedBytes = 200 * 1024;
+constexpr int kMaxStagedSorted = 160 * 1024;  // the sorted kernel also holds ~26 KB of static shared memory
 
 // ---------------------------------------------------------------- device build kernels
 __device__ __forceinline__ uint32_t f2ord(float f)
@@ -170,6 +171,8 @@ struct DeviceCtx
   void* h_pinned = nullptr;
   size_t h_pinned_cap = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  DevBuf d_partial, d_tickets;  // lane-per-particle kernels: per-CTA partials + per-group ticket counters
+  size_t tickets_zeroed = 0;
   DevBuf d_stats;            // 5 x uint64 work counters, only written while stats collection is on
   bool stats_on = false;
   unsigned long long* stats_ptr() const { return stats_on ? static_cast<unsigned long long*>(d_stats.p) : nullptr; }
@@ -191,6 +194,7 @@ struct mcl3dl_engine
   uint64_t launches = 0;
   std::string err;
   float nn_cell_factor = 1.0f;
+  int mapping = 1;  // 1 = tuned kernels (lik_kernel_wi + beam_kernel_pl); 0 = the plain group kernels (MCL3DL_MAPPING=group)
 };
 
 namespace
@@ -259,7 +263,19 @@ int launch_lik_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int
   const int groups = (P + PPB - 1) / PPB;
   const int grid = std::max(1, std::min(groups, c.sm_count * 8));
   const size_t bytes = static_cast<size_t>(N) * 16;
-  if (bytes <= static_cast<size_t>(kMaxStagedBytes))
+  if (eng->mapping != 0)
+  {
+    if (bytes <= static_cast<size_t>(kMaxStagedSorted))
+    {
+      CK(cudaFuncSetAttribute(lik_kernel_wi<TPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStagedSorted));
+      lik_kernel_wi<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
+    }
+    else
+    {
+      lik_kernel_wi<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
+    }
+  }
+  else if (bytes <= static_cast<size_t>(kMaxStagedBytes))
   {
     CK(cudaFuncSetAttribute(lik_kernel<TPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStagedBytes));
     lik_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
@@ -295,6 +311,55 @@ int launch_beam_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, in
   return MCL3DL_OK;
 }
 
+
+PlShape pick_pl_shape(size_t P, size_t N, int sm_count)
+{
+  // enough warps to fill the chip (~48 per SM), each lane walking `ppl` consecutive scan points
+  const size_t groups = (P + 31) / 32;
+  const size_t target = static_cast<size_t>(sm_count) * 48;
+  size_t ppl = (N * groups) / std::max<size_t>(target, 1);
+  ppl = std::min<size_t>(std::max<size_t>(ppl, 1), 64);
+  const size_t chunks = std::max<size_t>((N + ppl - 1) / ppl, 1);
+  PlShape sh;
+  sh.ppl = static_cast<int>(ppl);
+  sh.cb = static_cast<int>((chunks + kPlWarps - 1) / kPlWarps);
+  return sh;
+}
+
+int prepare_pl_scratch(mcl3dl_engine* eng, DeviceCtx& c, size_t P, const PlShape& sh, cudaStream_t st)
+{
+  const size_t groups = (P + 31) / 32;
+  int rc = reserve(eng, c.d_partial, std::max<size_t>(P, 1) * sh.cb * 12);
+  if (rc != MCL3DL_OK)
+    return rc;
+  if (groups * 4 > c.d_tickets.cap || !c.d_tickets.p)
+  {
+    rc = reserve(eng, c.d_tickets, std::max<size_t>(groups * 4, 4096));
+    if (rc != MCL3DL_OK)
+      return rc;
+    CK(cudaMemsetAsync(c.d_tickets.p, 0, c.d_tickets.cap, st));  // the kernels leave them at zero afterwards
+  }
+  return MCL3DL_OK;
+}
+
+int launch_beam_pl(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
+                   const float4* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
+{
+  const PlShape sh = pick_pl_shape(P, N, c.sm_count);
+  int rc = prepare_pl_scratch(eng, c, P, sh, st);
+  if (rc != MCL3DL_OK)
+    return rc;
+  const int groups = static_cast<int>((P + 31) / 32);
+  const size_t smem = static_cast<size_t>(kPlWarps) * sh.ppl * 16;
+  beam_kernel_pl<<<groups * sh.cb, kBlockThreads, smem, st>>>(poses, static_cast<int>(P), reinterpret_cast<const float4*>(scan),
+                                                             static_cast<int>(N), origins, c.dda, out, status, lik_defaults,
+                                                             c.stats_ptr(), sh, static_cast<uint32_t*>(c.d_partial.p),
+                                                             static_cast<unsigned int*>(c.d_tickets.p));
+  CK(cudaGetLastError());
+  eng->launches++;
+  return MCL3DL_OK;
+}
+
 int launch_lik(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
                mcl3dl_result* out, int beam_defaults, cudaStream_t st)
 {
@@ -309,8 +374,10 @@ int launch_lik(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_
 }
 
 int launch_beam(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
-                const float4* origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
+                const float4* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
 {
+  if (eng->mapping != 0)
+    return launch_beam_pl(eng, c, poses, P, scan, N, origins, n_origins, out, status, lik_defaults, st);
   const float4* s4 = reinterpret_cast<const float4*>(scan);
   switch (pick_tpp(P, N, c.sm_count))
   {
@@ -435,7 +502,8 @@ int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_
   if (eng->has_lik)
   {
     NnGridDev g{};
-    const float cell = eng->lik.match_dist_min * eng->nn_cell_factor;
+    // the window (q -/+ rpad) must span at most 3 cells per axis: cell edge strictly above rpad
+    const float cell = std::max(eng->lik.match_dist_min * eng->nn_cell_factor, eng->likdev.rpad * 1.0005f);
     if (!(cell > 0.0f))
     {
       cleanup();
@@ -637,9 +705,11 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
   if (const char* f = std::getenv("MCL3DL_NN_CELL_FACTOR"))
   {
     const float v = static_cast<float>(std::atof(f));
-    if (v >= 0.25f && v <= 4.0f)
+    if (v >= 1.0f && v <= 4.0f)
       eng->nn_cell_factor = v;
   }
+  if (const char* m = std::getenv("MCL3DL_MAPPING"))
+    eng->mapping = (std::strcmp(m, "group") == 0) ? 0 : 1;
   eng->devs.resize(n_devices);
   for (int i = 0; i < n_devices; ++i)
   {
@@ -684,7 +754,7 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     if (c.stream)
       cudaStreamSynchronize(c.stream);
     for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.d_poses, &c.d_lik,
-                      &c.d_beam, &c.d_origins_raw, &c.d_origins, &c.d_out, &c.d_status, &c.d_stats})
+                      &c.d_beam, &c.d_origins_raw, &c.d_origins, &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets})
       free_buf(*b);
     if (c.h_pinned)
       cudaFreeHost(c.h_pinned);
@@ -825,7 +895,7 @@ int mcl3dl_measure_device(mcl3dl_engine* eng, const mcl3dl_pose* d_poses, size_t
   // (a model without a scan this update costs no launch: the other kernel writes its (1, 0))
   if (n_beam)
   {
-    rc = launch_beam(eng, c, d_poses, P, d_beam, n_beam, origins4, d_out, nullptr, n_lik == 0, st);
+    rc = launch_beam(eng, c, d_poses, P, d_beam, n_beam, origins4, static_cast<int>(n_origins), d_out, nullptr, n_lik == 0, st);
     if (rc != MCL3DL_OK)
       return rc;
   }
@@ -890,7 +960,8 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     if (n_beam)
     {
       rc = launch_beam(eng, c, static_cast<const mcl3dl_pose*>(c.d_poses.p), Pd, static_cast<const mcl3dl_point*>(c.d_beam.p),
-                       n_beam, static_cast<const float4*>(c.d_origins.p), static_cast<mcl3dl_result*>(c.d_out.p),
+                       n_beam, static_cast<const float4*>(c.d_origins.p), static_cast<int>(n_origins),
+                       static_cast<mcl3dl_result*>(c.d_out.p),
                        status ? static_cast<uint8_t*>(c.d_status.p) : nullptr, n_lik == 0, st);
       if (rc != MCL3DL_OK) return rc;
     }

@@ -286,13 +286,253 @@ __global__ void __launch_bounds__(kBlockThreads)
 }
 
 // --------------------------------------------------------------------------------------------
-// One ray: RaycastUsingDDA::setRay + getNextCastResult loop + getBeamStatus's decision.
+// Warp-item likelihood kernel.
+//
+// ncu on the straightforward kernel above (profiles/r01a_ncu_lik_c2.txt): 9.7 of 32 lanes active and
+// ~70 % of the stall samples sit on the map-point loads of the inner loop, which runs with ~5 live
+// lanes — an eval next to a surface scans ~30 map points, one that misses scans ~2, and every lane
+// waits for the slowest one, one dependent load at a time.  (A CTA-wide sort by candidate count was
+// tried, profiles/r01d_*: it halves the issued instructions but trades them for barrier stalls,
+// because the heavy evals all land in one warp.)  Here each warp works on 32 evals at a time in two
+// warp-synchronous phases, no CTA barrier:
+//   phase 1 (lane = eval, uniform): transform, window, ALL row bounds of the <=3x3 window issued back
+//            to back (18 independent loads in flight per lane); the non-empty [s0,s1) runs go to
+//            this warp's shared-memory slab;
+//   phase 2 (lane = item): the warp's non-empty runs are enumerated with one prefix sum and dealt to
+//            the lanes round-robin, so a lane that owns a surface-hugging eval gets help from the
+//            lanes whose evals had nothing to scan; each item is one contiguous run of map points,
+//            read 4 at a time; minima are merged with shared-memory atomicMin on the float bits
+//            (order independent -> deterministic).
+// The eval's owner lane then adds its contribution to its running sum exactly as before, so results
+// are bit-identical to the plain kernel.  Requires cell edge > window half-width (<= 3 cells/axis).
+constexpr int kMaxWinRows = 9;
+// map points fetched per batch of an item; measured 1/2/4/8 -> 90/56/52/59 us on c2 (profiles/r01i_variants.txt);
+// capping registers for more resident CTAs only spills and loses (66-149 us)
+constexpr int kWiUnroll = 4;
+
+struct LikWarpSmem
+{
+  uint2 rows[kMaxWinRows][32];  // non-empty runs of each lane's eval, compacted
+  float qx[32], qy[32], qz[32];
+  uint32_t best[32];                  // float bits of the running min d^2 (non-negative floats order as uints)
+  uint16_t items[kMaxWinRows * 32];   // lane | run << 5
+};
+
+template <int TPP, bool STAGED>
+__global__ void __launch_bounds__(kBlockThreads)
+    lik_kernel_wi(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N, NnGridDev g,
+                  LikDev lp, mcl3dl_result* __restrict__ out, int write_beam_defaults,
+                  unsigned long long* __restrict__ stats)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ float red_f[kBlockThreads / 32];
+  __shared__ uint32_t red_u[3 * kBlockThreads / 32];
+  __shared__ LikWarpSmem wsm_all[kBlockThreads / 32];
+  const float4* pts = scan;
+  if (STAGED && N > 0)
+  {
+    stage_tile(smem_raw, scan, static_cast<uint32_t>(N) * 16u, &bar);
+    pts = reinterpret_cast<const float4*>(smem_raw);
+  }
+  constexpr int PPB = kBlockThreads / TPP;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  LikWarpSmem& sm = wsm_all[tid >> 5];
+  const int sub = tid / TPP;
+  const int l = tid % TPP;
+  const int n_groups = (P + PPB - 1) / PPB;
+  const uint32_t r2_bits = __float_as_uint(lp.r2);
+  uint32_t st_rows = 0, st_pts = 0;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
+  {
+    const int p = grp * PPB + sub;
+    const bool live = p < P;
+    float score = 0.0f;
+    uint32_t cnt = 0, z0 = 0, z1 = 0;
+    F3 pos;
+    Q4 rn;
+    pos.x = pos.y = pos.z = 0.0f;
+    rn.x = rn.y = rn.z = 0.0f;
+    rn.w = 1.0f;
+    if (live)
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(poses + p));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(poses + p) + 1);
+      pos.x = a.x;
+      pos.y = a.y;
+      pos.z = a.z;
+      Q4 q;
+      q.x = b.x;
+      q.y = b.y;
+      q.z = b.z;
+      q.w = b.w;
+      rn = qnormalized(q);  // state_6dof.h:217
+    }
+    // a warp's 32 lanes always belong to one particle (TPP >= 32), so the trip count is warp-uniform
+    for (int jbase = 0; jbase < N; jbase += TPP)
+    {
+      const int j = jbase + l;
+      const bool valid = live && j < N;
+      // ---------------- phase 1: lane = eval
+      int nr = 0;
+      sm.best[lane] = r2_bits;
+      if (valid)
+      {
+        const float4 sp = pts[j];
+        F3 v;
+        v.x = sp.x;
+        v.y = sp.y;
+        v.z = sp.z;
+        const F3 t = transform_point(rn, pos, v);
+        // PointRepresentation::vectorize with rescale values (mcl_3dl.cpp:1270)
+        const float qx = fmul(t.x, g.wx), qy = fmul(t.y, g.wy), qz = fmul(t.z, g.wz);
+        sm.qx[lane] = qx;
+        sm.qy[lane] = qy;
+        sm.qz[lane] = qz;
+        // same cell function as the build kernel (monotone), applied to q -/+ rpad
+        int lx = __float2int_rd(fmul(fsub(fsub(qx, lp.rpad), g.ox), g.inv_cell));
+        int ly = __float2int_rd(fmul(fsub(fsub(qy, lp.rpad), g.oy), g.inv_cell));
+        int lz = __float2int_rd(fmul(fsub(fsub(qz, lp.rpad), g.oz), g.inv_cell));
+        int hx = __float2int_rd(fmul(fsub(fadd(qx, lp.rpad), g.ox), g.inv_cell));
+        int hy = __float2int_rd(fmul(fsub(fadd(qy, lp.rpad), g.oy), g.inv_cell));
+        int hz = __float2int_rd(fmul(fsub(fadd(qz, lp.rpad), g.oz), g.inv_cell));
+        lx = max(lx, 0);
+        ly = max(ly, 0);
+        lz = max(lz, 0);
+        hx = min(hx, g.nx - 1);
+        hy = min(hy, min(g.ny - 1, ly + 2));
+        hz = min(hz, min(g.nz - 1, lz + 2));
+        if (lx <= hx && ly <= hy && lz <= hz)
+        {
+          st_rows += static_cast<uint32_t>((hz - lz + 1) * (hy - ly + 1));
+          uint32_t s0[kMaxWinRows], s1[kMaxWinRows];
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+            {
+              const int iy = ly + dy, iz = lz + dz;
+              const bool ok = iy <= hy && iz <= hz;
+              const int row = (iz * g.ny + iy) * g.nx;
+              s0[dz * 3 + dy] = ok ? __ldg(g.cell_start + row + lx) : 0u;
+              s1[dz * 3 + dy] = ok ? __ldg(g.cell_start + row + hx + 1) : 0u;
+            }
+#pragma unroll
+          for (int k = 0; k < kMaxWinRows; ++k)
+            if (s1[k] > s0[k])
+            {
+              sm.rows[nr][lane] = make_uint2(s0[k], s1[k]);
+              ++nr;
+              st_pts += s1[k] - s0[k];
+            }
+        }
+      }
+      // ---------------- deal the warp's runs to its lanes
+      uint32_t incl = static_cast<uint32_t>(nr);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const uint32_t nbr = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+          incl += nbr;
+      }
+      const int n_items = static_cast<int>(__shfl_sync(0xffffffffu, incl, 31));
+      const int first = static_cast<int>(incl) - nr;
+      for (int k = 0; k < nr; ++k) sm.items[first + k] = static_cast<uint16_t>(lane | (k << 5));
+      __syncwarp();
+      // ---------------- phase 2: lane = item (one contiguous run of map points)
+      for (int it = lane; it < n_items; it += 32)
+      {
+        const uint32_t iv = sm.items[it];
+        const int e = iv & 31;
+        const uint2 run = sm.rows[iv >> 5][e];
+        const float qx = sm.qx[e], qy = sm.qy[e], qz = sm.qz[e];
+        float best = lp.r2;
+        for (uint32_t s = run.x; s < run.y; s += kWiUnroll)
+        {
+          float4 mp[kWiUnroll];
+#pragma unroll
+          for (int u = 0; u < kWiUnroll; ++u)
+            if (s + u < run.y)
+              mp[u] = __ldg(g.pts + s + u);
+#pragma unroll
+          for (int u = 0; u < kWiUnroll; ++u)
+            if (s + u < run.y)
+            {
+              // flann::L2_Simple: sequential float accumulate of squared differences
+              const float dx = fsub(qx, mp[u].x);
+              const float dy = fsub(qy, mp[u].y);
+              const float dz = fsub(qz, mp[u].z);
+              best = fminf(best, fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz)));  // keep d < worst
+            }
+        }
+        if (best < lp.r2)
+          atomicMin(&sm.best[e], __float_as_uint(best));
+      }
+      __syncwarp();
+      // ---------------- owner lane: likelihood.cpp:128-133
+      if (valid)
+      {
+        const float d2 = __uint_as_float(sm.best[lane]);
+        if (d2 < lp.r2)
+        {
+          const float dist = fsub(lp.match_dist_min, fmaxf(__fsqrt_rn(d2), lp.match_dist_flat));
+          if (!(dist < 0.0f))
+          {
+            score = fadd(score, fmul(dist, lp.match_weight));
+            cnt++;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    group_reduce<TPP>(score, cnt, z0, z1, red_f, red_u);
+    if (live && l == 0)
+    {
+      // empty scan -> LidarMeasurementResult(1, 0), likelihood.cpp:111-114
+      out[p].score_like = (N == 0) ? 1.0f : score;
+      out[p].match_cnt = cnt;
+      if (write_beam_defaults)
+      {
+        // no beam scan this update: LidarMeasurementResult(1, 0), beam.cpp:130-133
+        out[p].score_beam = 1.0f;
+        out[p].n_short = 0;
+        out[p].n_hit = 0;
+        out[p].n_long = 0;
+      }
+    }
+  }
+  if (stats)
+  {
+    const uint32_t r = warp_sum_u32(st_rows), q = warp_sum_u32(st_pts);
+    if ((threadIdx.x & 31) == 0)
+    {
+      atomicAdd(stats + 0, static_cast<unsigned long long>(r));
+      atomicAdd(stats + 1, static_cast<unsigned long long>(q));
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
 __device__ __forceinline__ int dda_to_index(float v, float mn, double grid)
 {
   // toIndex, raycast_using_dda.h:205-210: float difference, double division, truncation
   return __double2int_rz(ddiv(static_cast<double>(fsub(v, mn)), grid));
 }
 
+// One ray: RaycastUsingDDA::setRay + getNextCastResult loop + getBeamStatus's decision.
+//
+// Measured choices (profiles/r01g_variants.txt, r01h_variants.txt; all variants bit-exact):
+//   * the axis choice is evaluated branch-free (selects): 200 -> 177 us on c3, the 3-way branch
+//     diverges whenever the lanes of a warp cross different faces;
+//   * t_max needs float(|index - begin|): kept as a float counter (+1.0f per step) instead of an
+//     int->float conversion per step;
+//   * the occupancy word is re-read only when the cell leaves the current 32-cell word;
+//   * replacing the twelve fp64 divisions of the set-up by guarded reciprocal multiplications, caching
+//     the per-sensor ray origin, or screening the cone test in float changed nothing measurable
+//     (the kernel is latency/occupancy bound, not fp64 bound) and were dropped again;
+//   * occupancy matters most: __launch_bounds__(256, 4) (<= 64 registers) 200 -> 165 us.
 __device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const F3& e, uint32_t& n_steps,
                                         uint32_t& n_occ, uint32_t& n_tested)
 {
@@ -324,6 +564,7 @@ __device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const 
   float e0x = inf, e0y = inf, e0z = inf, tdx = inf, tdy = inf, tdz = inf;
   if (dix != 0)
   {
+    // nearest = index * grid + min_p in double; |(nearest - begin) / dir| and |grid / dir| stored as float (:94-99)
     const double nearest = dadd(dmul(static_cast<double>(dir.x < 0 ? bx : bx + 1), g.grid), static_cast<double>(g.min_x));
     e0x = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.x)), static_cast<double>(dir.x))));
     tdx = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.x))));
@@ -342,36 +583,41 @@ __device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const 
   }
   float tx = e0x, ty = e0y, tz = e0z;
   int cx = bx, cy = by, cz = bz;
+  float kx = 0.0f, ky = 0.0f, kz = 0.0f;  // float(|current - begin|): small integers, exact in float
   const int nxy = g.nx * g.ny;
+  int last_w = -1;
+  uint32_t word = 0;
   // getNextCastResult, :106-159: at most max_movement-1 cells; begin and end cells are never tested
   for (int pos = 1; pos < max_movement; ++pos)
   {
     ++n_steps;
-    // strict-'<' ladder (:114-147); on ties z beats y beats x.  incrementIndex (:192-203) recomputes
-    // t_max from the start: float * float(int) + float.
-    if (tx < ty ? tx < tz : false)
-    {
-      cx += sx;
-      tx = fadd(e0x, fmul(tdx, static_cast<float>(abs(cx - bx))));
-      if (cx < 0 || g.nx <= cx)
-        return ST_LONG;
-    }
-    else if (!(tx < ty) && ty < tz)
-    {
-      cy += sy;
-      ty = fadd(e0y, fmul(tdy, static_cast<float>(abs(cy - by))));
-      if (cy < 0 || g.ny <= cy)
-        return ST_LONG;
-    }
-    else
-    {
-      cz += sz;
-      tz = fadd(e0z, fmul(tdz, static_cast<float>(abs(cz - bz))));
-      if (cz < 0 || g.nz <= cz)
-        return ST_LONG;
-    }
+    // strict-'<' ladder (:114-147): x if tx<ty && tx<tz; y if !(tx<ty) && ty<tz; else z (on ties z beats
+    // y beats x).  incrementIndex (:192-203) recomputes t_max from the start:
+    // float(edge0) + float(t_delta) * float(|index - begin|).
+    const bool lt_xy = tx < ty;
+    const bool ax = lt_xy && (tx < tz);
+    const bool ay = !lt_xy && (ty < tz);
+    const bool az = !ax && !ay;
+    cx += ax ? sx : 0;
+    cy += ay ? sy : 0;
+    cz += az ? sz : 0;
+    kx = ax ? fadd(kx, 1.0f) : kx;
+    ky = ay ? fadd(ky, 1.0f) : ky;
+    kz = az ? fadd(kz, 1.0f) : kz;
+    tx = ax ? fadd(e0x, fmul(tdx, kx)) : tx;
+    ty = ay ? fadd(e0y, fmul(tdy, ky)) : ty;
+    tz = az ? fadd(e0z, fmul(tdz, kz)) : tz;
+    if (static_cast<unsigned>(cx) >= static_cast<unsigned>(g.nx) || static_cast<unsigned>(cy) >= static_cast<unsigned>(g.ny) ||
+        static_cast<unsigned>(cz) >= static_cast<unsigned>(g.nz))
+      return ST_LONG;  // left the grid (:197-201)
     const int cell = cx + cy * g.nx + cz * nxy;
-    if (!((__ldg(g.occ + (cell >> 5)) >> (cell & 31)) & 1u))
+    const int w = cell >> 5;
+    if (w != last_w)
+    {
+      word = __ldg(g.occ + w);
+      last_w = w;
+    }
+    if (!((word >> (cell & 31)) & 1u))
       continue;
     // hasIntersection, :237-258: first point of the cell, in map order, inside the cone
     const uint32_t s0 = __ldg(g.cell_start + cell);
@@ -407,6 +653,21 @@ __device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const 
     }
   }
   return ST_LONG;
+}
+
+// begin = s.pos_ + s.rot_ * origins[label] with the RAW rot_ (beam.cpp:145)
+__device__ __forceinline__ F3 ray_origin(const F3& pos, const Q4& q_raw, const float4& o4)
+{
+  F3 o;
+  o.x = o4.x;
+  o.y = o4.y;
+  o.z = o4.z;
+  const F3 ro = qrot(q_raw, o);
+  F3 begin;
+  begin.x = fadd(pos.x, ro.x);
+  begin.y = fadd(pos.y, ro.y);
+  begin.z = fadd(pos.z, ro.z);
+  return begin;
 }
 
 template <int TPP, bool STAGED>
@@ -458,16 +719,7 @@ __global__ void __launch_bounds__(kBlockThreads)
         v.y = sp.y;
         v.z = sp.z;
         const F3 end = transform_point(rn, pos, v);  // beam.cpp:138-139
-        const float4 o4 = __ldg(origins + __float_as_uint(sp.w));
-        F3 o;
-        o.x = o4.x;
-        o.y = o4.y;
-        o.z = o4.z;
-        const F3 ro = qrot(q, o);  // RAW rot_, beam.cpp:145
-        F3 begin;
-        begin.x = fadd(pos.x, ro.x);
-        begin.y = fadd(pos.y, ro.y);
-        begin.z = fadd(pos.z, ro.z);
+        const F3 begin = ray_origin(pos, q, __ldg(origins + __float_as_uint(sp.w)));
         const int st = cast_ray(g, begin, end, st_steps, st_occ, st_tested);
         n_short += (st == ST_SHORT);
         n_hit += (st == ST_HIT);
@@ -508,6 +760,162 @@ __global__ void __launch_bounds__(kBlockThreads)
       atomicAdd(stats + 2, static_cast<unsigned long long>(a));
       atomicAdd(stats + 3, static_cast<unsigned long long>(b));
       atomicAdd(stats + 4, static_cast<unsigned long long>(c));
+    }
+  }
+}
+
+
+
+// ============================================================================================
+// Lane-per-particle mapping for the beam model ("pl" kernel).
+//
+// A warp takes 32 consecutive particles (one per lane) and a chunk of consecutive rays; every lane
+// casts the SAME scan ray at the same time.  In tracking mode the 32 poses are within a few
+// decimetres of each other, so the lanes walk nearly the same voxels for nearly the same number of
+// steps: the occupancy words coalesce and the trip counts agree (measured: c3 204 -> 162 us).  With
+// spread particles nothing is lost relative to the group mapping.  (The same mapping was measured
+// for the likelihood model and lost to the warp-item kernel: profiles/r01c_*.)  A CTA = one particle group x 8 chunks (8 warps); when a scan needs more than
+// 8 chunks to fill the chip, several CTAs share a particle group and the last one to finish (ticket
+// counter) folds the per-CTA partials in chunk order, so the result is still deterministic.
+constexpr int kPlWarps = kBlockThreads / 32;
+
+struct PlShape
+{
+  int ppl;  // scan points per lane (chunk length)
+  int cb;   // CTAs per particle group (each covers kPlWarps chunks)
+};
+
+__global__ void __launch_bounds__(kBlockThreads, 4)
+    beam_kernel_pl(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N,
+                   const float4* __restrict__ origins, DdaGridDev g, mcl3dl_result* __restrict__ out,
+                   uint8_t* __restrict__ status, int write_lik_defaults, unsigned long long* __restrict__ stats,
+                   PlShape sh, uint32_t* __restrict__ partial, unsigned int* __restrict__ tickets)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t red[kPlWarps][3][32];
+  __shared__ unsigned int s_ticket;
+  const int group = blockIdx.x / sh.cb;
+  const int cblk = blockIdx.x % sh.cb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int base = cblk * kPlWarps * sh.ppl;
+  const int slice = max(0, min(N - base, kPlWarps * sh.ppl));
+  const float4* tile = reinterpret_cast<const float4*>(smem_raw);
+  if (slice > 0)
+    stage_tile(smem_raw, scan + base, static_cast<uint32_t>(slice) * 16u, &bar);
+  const int j0 = warp * sh.ppl;
+  const int j1 = min(slice, j0 + sh.ppl);
+  const int p = group * 32 + lane;
+  const bool live = p < P;
+  uint32_t n_short = 0, n_hit = 0, n_long = 0, st_steps = 0, st_occ = 0, st_tested = 0;
+  if (live && j0 < j1)
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(poses + p));
+    const float4 bq = __ldg(reinterpret_cast<const float4*>(poses + p) + 1);
+    F3 pos;
+    pos.x = a.x;
+    pos.y = a.y;
+    pos.z = a.z;
+    Q4 q;
+    q.x = bq.x;
+    q.y = bq.y;
+    q.z = bq.z;
+    q.w = bq.w;
+    const Q4 rn = qnormalized(q);
+    for (int j = j0; j < j1; ++j)
+    {
+      const float4 sp = tile[j];
+      F3 v;
+      v.x = sp.x;
+      v.y = sp.y;
+      v.z = sp.z;
+      const F3 end = transform_point(rn, pos, v);  // beam.cpp:138-139
+      const F3 begin = ray_origin(pos, q, __ldg(origins + __float_as_uint(sp.w)));
+      const int st = cast_ray(g, begin, end, st_steps, st_occ, st_tested);
+      n_short += (st == ST_SHORT);
+      n_hit += (st == ST_HIT);
+      n_long += (st == ST_LONG);
+      if (status)
+        status[static_cast<size_t>(p) * N + base + j] = static_cast<uint8_t>(st);
+    }
+  }
+  red[warp][0][lane] = n_short;
+  red[warp][1][lane] = n_hit;
+  red[warp][2][lane] = n_long;
+  __syncthreads();
+  if (warp == 0)
+  {
+    uint32_t a = 0, b = 0, c = 0;
+#pragma unroll
+    for (int k = 0; k < kPlWarps; ++k)
+    {
+      a += red[k][0][lane];
+      b += red[k][1][lane];
+      c += red[k][2][lane];
+    }
+    bool writer = sh.cb == 1;
+    if (sh.cb > 1)
+    {
+      if (live)
+      {
+        uint32_t* dst = partial + (static_cast<size_t>(p) * sh.cb + cblk) * 3;
+        dst[0] = a;
+        dst[1] = b;
+        dst[2] = c;
+      }
+      __threadfence();
+      if (lane == 0)
+        s_ticket = atomicAdd(tickets + group, 1u);
+      __syncwarp();
+      if (s_ticket == static_cast<unsigned int>(sh.cb - 1))
+      {
+        __threadfence();
+        writer = true;
+        if (live)
+        {
+          a = b = c = 0;
+          for (int k = 0; k < sh.cb; ++k)
+          {
+            const uint32_t* src = partial + (static_cast<size_t>(p) * sh.cb + k) * 3;
+            a += __ldcg(src);
+            b += __ldcg(src + 1);
+            c += __ldcg(src + 2);
+          }
+        }
+        if (lane == 0)
+          tickets[group] = 0;
+      }
+    }
+    if (writer && live)
+    {
+      // beam.cpp:146-152: the same factor multiplied in sequentially, then the floor
+      float score = 1.0f;
+      if (N > 0)
+      {
+        const uint32_t k = a + (g.short_only ? 0u : c);
+        for (uint32_t i = 0; i < k; ++i) score = fmul(score, g.beam_likelihood);
+        if (score < g.beam_likelihood_min)
+          score = g.beam_likelihood_min;
+      }
+      out[p].score_beam = score;
+      out[p].n_short = a;
+      out[p].n_hit = b;
+      out[p].n_long = c;
+      if (write_lik_defaults)
+      {
+        out[p].score_like = 1.0f;
+        out[p].match_cnt = 0;
+      }
+    }
+  }
+  if (stats)
+  {
+    const uint32_t x = warp_sum_u32(st_steps), y = warp_sum_u32(st_occ), z = warp_sum_u32(st_tested);
+    if (lane == 0)
+    {
+      atomicAdd(stats + 2, static_cast<unsigned long long>(x));
+      atomicAdd(stats + 3, static_cast<unsigned long long>(y));
+      atomicAdd(stats + 4, static_cast<unsigned long long>(z));
     }
   }
 }

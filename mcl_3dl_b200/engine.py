@@ -76,8 +76,8 @@ def load_library():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if _build.stale():
+    path = os.environ.get("MCL3DL_LIB") or _build.LIB  # MCL3DL_LIB: an experiment variant built by build.build(out=...)
+    if path == _build.LIB and _build.stale():
         try:
             _build.build()
         except Exception:
