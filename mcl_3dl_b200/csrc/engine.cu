@@ -167,7 +167,7 @@ struct DeviceCtx
   DdaGridDev dda{};
   size_t map_bytes = 0;
   // per-update I/O
-  DevBuf d_poses, d_lik, d_beam, d_origins_raw, d_origins, d_out, d_status;
+  DevBuf d_poses /* whole input block of the host path */, d_origins, d_out, d_status;
   void* h_pinned = nullptr;
   size_t h_pinned_cap = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -753,8 +753,8 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     cudaSetDevice(c.dev);
     if (c.stream)
       cudaStreamSynchronize(c.stream);
-    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.d_poses, &c.d_lik,
-                      &c.d_beam, &c.d_origins_raw, &c.d_origins, &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets})
+    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.d_poses,
+                      &c.d_origins, &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets})
       free_buf(*b);
     if (c.h_pinned)
       cudaFreeHost(c.h_pinned);
@@ -936,8 +936,8 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     const size_t o_status = o_out + b_out;
     rc = reserve_pinned(eng, c, o_status + b_status + 64);
     if (rc != MCL3DL_OK) return rc;
-    if ((rc = reserve(eng, c.d_poses, b_poses)) || (rc = reserve(eng, c.d_lik, b_lik)) || (rc = reserve(eng, c.d_beam, b_beam)) ||
-        (rc = reserve(eng, c.d_origins, b_org)) || (rc = reserve(eng, c.d_out, b_out)) || (rc = reserve(eng, c.d_status, b_status)))
+    // one staging block, one H2D copy: [poses | likelihood scan | beam scan | origins] (all 16-byte multiples)
+    if ((rc = reserve(eng, c.d_poses, o_out)) || (rc = reserve(eng, c.d_out, b_out)) || (rc = reserve(eng, c.d_status, b_status)))
       return rc;
     char* hp = static_cast<char*>(c.h_pinned);
     std::memcpy(hp, poses + p0[d], b_poses);
@@ -952,15 +952,16 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
       ho[4 * k + 3] = 0.0f;
     }
     CK(cudaEventRecord(c.ev[0], st));
-    CK(cudaMemcpyAsync(c.d_poses.p, hp, b_poses, cudaMemcpyHostToDevice, st));
-    if (b_lik) CK(cudaMemcpyAsync(c.d_lik.p, hp + o_lik, b_lik, cudaMemcpyHostToDevice, st));
-    if (b_beam) CK(cudaMemcpyAsync(c.d_beam.p, hp + o_beam, b_beam, cudaMemcpyHostToDevice, st));
-    if (b_org) CK(cudaMemcpyAsync(c.d_origins.p, hp + o_org, b_org, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c.d_poses.p, hp, o_out, cudaMemcpyHostToDevice, st));
+    const char* d_in = static_cast<const char*>(c.d_poses.p);
+    const mcl3dl_pose* d_poses = reinterpret_cast<const mcl3dl_pose*>(d_in);
+    const mcl3dl_point* d_lik = reinterpret_cast<const mcl3dl_point*>(d_in + o_lik);
+    const mcl3dl_point* d_beam = reinterpret_cast<const mcl3dl_point*>(d_in + o_beam);
+    const float4* d_org = reinterpret_cast<const float4*>(d_in + o_org);
     CK(cudaEventRecord(c.ev[1], st));
     if (n_beam)
     {
-      rc = launch_beam(eng, c, static_cast<const mcl3dl_pose*>(c.d_poses.p), Pd, static_cast<const mcl3dl_point*>(c.d_beam.p),
-                       n_beam, static_cast<const float4*>(c.d_origins.p), static_cast<int>(n_origins),
+      rc = launch_beam(eng, c, d_poses, Pd, d_beam, n_beam, d_org, static_cast<int>(n_origins),
                        static_cast<mcl3dl_result*>(c.d_out.p),
                        status ? static_cast<uint8_t*>(c.d_status.p) : nullptr, n_lik == 0, st);
       if (rc != MCL3DL_OK) return rc;
@@ -968,7 +969,7 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     CK(cudaEventRecord(c.ev[2], st));
     if (n_lik || !n_beam)
     {
-      rc = launch_lik(eng, c, static_cast<const mcl3dl_pose*>(c.d_poses.p), Pd, static_cast<const mcl3dl_point*>(c.d_lik.p), n_lik,
+      rc = launch_lik(eng, c, d_poses, Pd, d_lik, n_lik,
                       static_cast<mcl3dl_result*>(c.d_out.p), n_beam == 0, st);
       if (rc != MCL3DL_OK) return rc;
     }
