@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MCL3DL_ABI_VERSION 1
+#define MCL3DL_ABI_VERSION 2
 
 /* ---- error codes (the reference has none: degenerate inputs yield (1,0); the only
  *      exception is ChunkedKdtree::radiusSearch's runtime_error, chunked_kdtree.h:224) */
@@ -81,6 +81,11 @@ typedef struct
   float beam_likelihood_min;
   uint32_t filter_label_max;
   int32_t add_penalty_short_only_mode;
+  int32_t use_raycast_using_dda; /* 1: RaycastUsingDDA; 0: RaycastUsingKDTree, the node's default (parameters.h:109).
+                                  * The KD-tree caster is built from float(map_grid_size[]) and float(hit_tolerance)
+                                  * (raycast_using_kdtree.h:48-55) and searches the likelihood grid, so lik params
+                                  * must be given to mcl3dl_set_map as well. */
+  int32_t _reserved;
 } mcl3dl_beam_params;
 
 /* Per-particle result record (24 B).
@@ -181,7 +186,7 @@ void mcl3dl_beam_params_from_reference(mcl3dl_beam_params* out,
                                        float map_grid_x, float map_grid_y, float map_grid_z,
                                        size_t num_points_default, float beam_likelihood_min,
                                        float ang_total_ref, uint32_t filter_label_max, float hit_range,
-                                       int add_penalty_short_only_mode,
+                                       int add_penalty_short_only_mode, int use_raycast_using_dda,
                                        float ray_angle_half, float dda_grid_size);
 
 int mcl3dl_get_map_info(const mcl3dl_engine*, mcl3dl_map_info* out);

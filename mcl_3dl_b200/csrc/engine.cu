@@ -165,6 +165,8 @@ struct DeviceCtx
   DevBuf nn_cell_start, nn_pts, dda_occ, dda_cell_start, dda_pts;
   NnGridDev nn{};
   DdaGridDev dda{};
+  KdRayDev kd{};
+  DevBuf raw_pts;  // map points in original order (KD-tree raycaster only)
   size_t map_bytes = 0;
   // per-update I/O
   DevBuf d_poses /* whole input block of the host path */, d_origins, d_out, d_status;
@@ -351,10 +353,14 @@ int launch_beam_pl(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, s
     return rc;
   const int groups = static_cast<int>((P + 31) / 32);
   const size_t smem = static_cast<size_t>(kPlWarps) * sh.ppl * 16;
-  beam_kernel_pl<<<groups * sh.cb, kBlockThreads, smem, st>>>(poses, static_cast<int>(P), reinterpret_cast<const float4*>(scan),
-                                                             static_cast<int>(N), origins, c.dda, out, status, lik_defaults,
-                                                             c.stats_ptr(), sh, static_cast<uint32_t*>(c.d_partial.p),
-                                                             static_cast<unsigned int*>(c.d_tickets.p));
+  if (eng->beam.use_raycast_using_dda)
+    beam_kernel_pl<false><<<groups * sh.cb, kBlockThreads, smem, st>>>(
+        poses, static_cast<int>(P), reinterpret_cast<const float4*>(scan), static_cast<int>(N), origins, c.dda, c.kd, c.nn, out,
+        status, lik_defaults, c.stats_ptr(), sh, static_cast<uint32_t*>(c.d_partial.p), static_cast<unsigned int*>(c.d_tickets.p));
+  else
+    beam_kernel_pl<true><<<groups * sh.cb, kBlockThreads, smem, st>>>(
+        poses, static_cast<int>(P), reinterpret_cast<const float4*>(scan), static_cast<int>(N), origins, c.dda, c.kd, c.nn, out,
+        status, lik_defaults, c.stats_ptr(), sh, static_cast<uint32_t*>(c.d_partial.p), static_cast<unsigned int*>(c.d_tickets.p));
   CK(cudaGetLastError());
   eng->launches++;
   return MCL3DL_OK;
@@ -376,7 +382,7 @@ int launch_lik(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_
 int launch_beam(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
                 const float4* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
 {
-  if (eng->mapping != 0)
+  if (eng->mapping != 0 || !eng->beam.use_raycast_using_dda)  // the KD-tree caster exists in the pl kernel only
     return launch_beam_pl(eng, c, poses, P, scan, N, origins, n_origins, out, status, lik_defaults, st);
   const float4* s4 = reinterpret_cast<const float4*>(scan);
   switch (pick_tpp(P, N, c.sm_count))
@@ -412,6 +418,23 @@ void fill_dda_scalars(const mcl3dl_beam_params& b, DdaGridDev& g)
   g.beam_likelihood_min = b.beam_likelihood_min;
   g.filter_label_max = b.filter_label_max;
   g.short_only = b.add_penalty_short_only_mode ? 1 : 0;
+}
+
+void fill_kd_scalars(const mcl3dl_beam_params& b, KdRayDev& k)
+{
+  // RaycastUsingKDTree ctor takes floats (raycast_using_kdtree.h:48-55); refreshParameters passes the float params
+  const float gx = static_cast<float>(b.map_grid_size[0]), gy = static_cast<float>(b.map_grid_size[1]),
+              gz = static_cast<float>(b.map_grid_size[2]);
+  const float gmin = std::min(gx, std::min(gy, gz)), gmax = std::max(gx, std::max(gy, gz));
+  k.grid_min = gmin;
+  k.hit_tolerance = static_cast<float>(b.hit_tolerance);
+  k.r1 = static_cast<float>(std::sqrt(2.0) * gmax / 2.0);             // :83, narrowed by radiusSearch(const float radius)
+  k.r2 = static_cast<float>(gmin * 2 + std::sqrt(2.0) * gmax / 2.0);  // :95
+  k.r1_sq = static_cast<float>(static_cast<double>(k.r1) * static_cast<double>(k.r1));
+  k.r2_sq = static_cast<float>(static_cast<double>(k.r2) * static_cast<double>(k.r2));
+  k.r1_pad = k.r1 * 1.0001f + 1e-6f;
+  k.r2_pad = k.r2 * 1.0001f + 1e-6f;
+  k.sin_den = gmin * 2.0;  // :98
 }
 
 // Build both grids on one device from the uploaded points.
@@ -574,8 +597,24 @@ int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_
     eng->info.nn_origin[2] = g.oz;
   }
 
+  // ---- KD-tree raycaster: marches over the likelihood grid; needs the raw points by original index
+  if (eng->has_beam && !eng->beam.use_raycast_using_dda)
+  {
+    if (!eng->has_lik)
+    {
+      cleanup();
+      return MCL3DL_ERR_INVALID_ARG;
+    }
+    fill_dda_scalars(eng->beam, c.dda);
+    fill_kd_scalars(eng->beam, c.kd);
+    free_buf(c.raw_pts);
+    c.raw_pts = d_pts;  // keep the upload
+    d_pts = DevBuf();
+    c.kd.raw_pts = static_cast<const float4*>(c.raw_pts.p);
+    c.map_bytes += n * 16;
+  }
   // ---- DDA grid: updatePointCloud, raycast_using_dda.h:162-190
-  if (eng->has_beam)
+  if (eng->has_beam && eng->beam.use_raycast_using_dda)
   {
     DdaGridDev g{};
     fill_dda_scalars(eng->beam, g);
@@ -753,7 +792,7 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     cudaSetDevice(c.dev);
     if (c.stream)
       cudaStreamSynchronize(c.stream);
-    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.d_poses,
+    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.d_poses,
                       &c.d_origins, &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets})
       free_buf(*b);
     if (c.h_pinned)
@@ -821,10 +860,17 @@ int mcl3dl_set_params(mcl3dl_engine* eng, const mcl3dl_lik_params* lik, const mc
   }
   if (beam)
   {
-    if (!eng->has_beam || beam->dda_grid_size != eng->beam.dda_grid_size)
+    if (!eng->has_beam || beam->dda_grid_size != eng->beam.dda_grid_size ||
+        beam->use_raycast_using_dda != eng->beam.use_raycast_using_dda)
       return MCL3DL_ERR_INVALID_ARG;
     eng->beam = *beam;
-    for (DeviceCtx& c : eng->devs) fill_dda_scalars(eng->beam, c.dda);
+    for (DeviceCtx& c : eng->devs)
+    {
+      fill_dda_scalars(eng->beam, c.dda);
+      const float4* keep = c.kd.raw_pts;
+      fill_kd_scalars(eng->beam, c.kd);
+      c.kd.raw_pts = keep;
+    }
   }
   return MCL3DL_OK;
 }
@@ -1062,7 +1108,7 @@ int mcl3dl_read_stats(mcl3dl_engine* eng, mcl3dl_work_stats* out)
 void mcl3dl_beam_params_from_reference(mcl3dl_beam_params* o, float map_grid_x, float map_grid_y, float map_grid_z,
                                        size_t num_points_default, float beam_likelihood_min, float ang_total_ref,
                                        uint32_t filter_label_max, float hit_range, int add_penalty_short_only_mode,
-                                       float ray_angle_half, float dda_grid_size)
+                                       int use_raycast_using_dda, float ray_angle_half, float dda_grid_size)
 {
   // LidarMeasurementModelBeam::refreshParameters, src/lidar_measurement_model_beam.cpp:58-80: the
   // float parameters are promoted to double where the RaycastUsingDDA constructor takes doubles.
@@ -1079,6 +1125,8 @@ void mcl3dl_beam_params_from_reference(mcl3dl_beam_params* o, float map_grid_x, 
   o->beam_likelihood_min = beam_likelihood_min;
   o->filter_label_max = filter_label_max;
   o->add_penalty_short_only_mode = add_penalty_short_only_mode ? 1 : 0;
+  o->use_raycast_using_dda = use_raycast_using_dda ? 1 : 0;
+  o->_reserved = 0;
 }
 
 }  // extern "C"

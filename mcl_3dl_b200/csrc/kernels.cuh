@@ -64,6 +64,18 @@ struct DdaGridDev
   int short_only;
 };
 
+// ---- KD-tree raycaster (RaycastUsingKDTree, the node's default caster): marches over the likelihood
+// search grid; the colliding map point's raw coordinates / label are fetched by original index.
+struct KdRayDev
+{
+  const float4* raw_pts;  // map points as handed to set_map: xyz + label bits, original order
+  float grid_min;         // map_grid_min_ (raycast_using_kdtree.h:50)
+  float hit_tolerance;    // hit_tolerance_ (:52)
+  float r1, r1_sq, r1_pad;  // radius sqrt(2)*grid_max/2 narrowed to float (:83), float(double r * double r), window half-width
+  float r2, r2_sq, r2_pad;  // radius grid_min*2 + sqrt(2)*grid_max/2 (:95)
+  double sin_den;           // map_grid_min_ * 2.0 (:98)
+};
+
 enum
 {
   ST_SHORT = 0,
@@ -655,6 +667,112 @@ __device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const 
   return ST_LONG;
 }
 
+// 1-NN within a radius with the index of the winner (ChunkedKdtree::radiusSearch(p, r, id, d2, 1)); ties go to
+// the lowest original index, like the CPU checkers.  General window (any radius below a few cells).
+__device__ __forceinline__ bool nn_search_arg(const NnGridDev& g, float qx, float qy, float qz, float rpad, float r_sq,
+                                              float& best, uint32_t& best_orig, uint32_t& n_tested)
+{
+  int lx = __float2int_rd(fmul(fsub(fsub(qx, rpad), g.ox), g.inv_cell));
+  int ly = __float2int_rd(fmul(fsub(fsub(qy, rpad), g.oy), g.inv_cell));
+  int lz = __float2int_rd(fmul(fsub(fsub(qz, rpad), g.oz), g.inv_cell));
+  int hx = __float2int_rd(fmul(fsub(fadd(qx, rpad), g.ox), g.inv_cell));
+  int hy = __float2int_rd(fmul(fsub(fadd(qy, rpad), g.oy), g.inv_cell));
+  int hz = __float2int_rd(fmul(fsub(fadd(qz, rpad), g.oz), g.inv_cell));
+  lx = max(lx, 0);
+  ly = max(ly, 0);
+  lz = max(lz, 0);
+  hx = min(hx, g.nx - 1);
+  hy = min(hy, g.ny - 1);
+  hz = min(hz, g.nz - 1);
+  best = r_sq;
+  best_orig = 0xffffffffu;
+  for (int iz = lz; iz <= hz; ++iz)
+    for (int iy = ly; iy <= hy; ++iy)
+    {
+      if (lx > hx)
+        break;
+      const int row = (iz * g.ny + iy) * g.nx;
+      const uint32_t s0 = __ldg(g.cell_start + row + lx);
+      const uint32_t s1 = __ldg(g.cell_start + row + hx + 1);
+      for (uint32_t s = s0; s < s1; ++s)
+      {
+        ++n_tested;
+        const float4 m = __ldg(g.pts + s);
+        const float dx = fsub(qx, m.x);
+        const float dy = fsub(qy, m.y);
+        const float dz = fsub(qz, m.z);
+        const float d = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));  // flann::L2_Simple
+        const uint32_t orig = __float_as_uint(m.w);
+        if (d < best || (d == best && orig < best_orig && best_orig != 0xffffffffu))
+        {
+          best = d;
+          best_orig = orig;
+        }
+      }
+    }
+  return best_orig != 0xffffffffu;
+}
+
+// One ray with RaycastUsingKDTree (raycasts/raycast_using_kdtree.h:57-110) + getBeamStatus (beam.cpp:157-192).
+__device__ __forceinline__ int cast_ray_kd(const KdRayDev& k, const NnGridDev& nn, const DdaGridDev& g, const F3& b,
+                                           const F3& e, uint32_t& n_steps, uint32_t& n_occ, uint32_t& n_tested)
+{
+  // setRay, :57-64
+  F3 d;
+  d.x = fsub(e.x, b.x);
+  d.y = fsub(e.y, b.y);
+  d.z = fsub(e.z, b.z);
+  const float nrm = __fsqrt_rn(dot3(d, d));
+  const int length = __float2int_rz(floorf(fdiv(fadd(nrm, k.hit_tolerance), k.grid_min)));
+  F3 inc;
+  inc.x = fmul(fdiv(d.x, nrm), k.grid_min);
+  inc.y = fmul(fdiv(d.y, nrm), k.grid_min);
+  inc.z = fmul(fdiv(d.z, nrm), k.grid_min);
+  F3 pos;
+  pos.x = fadd(b.x, inc.x);
+  pos.y = fadd(b.y, inc.y);
+  pos.z = fadd(b.z, inc.z);
+  // getNextCastResult, :66-110
+  for (int count = 1; count < length; ++count)
+  {
+    ++n_steps;
+    float d2;
+    uint32_t id;
+    if (nn_search_arg(nn, fmul(pos.x, nn.wx), fmul(pos.y, nn.wy), fmul(pos.z, nn.wz), k.r1_pad, k.r1_sq, d2, id, n_tested))
+    {
+      ++n_occ;
+      const float4 m = __ldg(k.raw_pts + id);
+      if (!(__float_as_uint(m.w) > g.filter_label_max))  // beam.cpp:168
+      {
+        const float d0 = __fsqrt_rn(d2);
+        // pos_prev = pos_ - inc_ * 2.0 (:91), second search radius grid_min*2 + sqrt(2)*grid_max/2 (:95)
+        const float px = fsub(pos.x, fmul(inc.x, 2.0f)), py = fsub(pos.y, fmul(inc.y, 2.0f)), pz = fsub(pos.z, fmul(inc.z, 2.0f));
+        float d2b;
+        uint32_t idb;
+        float sin_ang = 1.0f;
+        if (nn_search_arg(nn, fmul(px, nn.wx), fmul(py, nn.wy), fmul(pz, nn.wz), k.r2_pad, k.r2_sq, d2b, idb, n_tested))
+        {
+          const float d1 = __fsqrt_rn(d2b);
+          sin_ang = __double2float_rn(ddiv(fabs(static_cast<double>(fsub(d1, d0))), k.sin_den));  // :98
+        }
+        if (sin_ang > g.sin_total_ref)
+        {
+          const double ddx = static_cast<double>(fsub(e.x, m.x));
+          const double ddy = static_cast<double>(fsub(e.y, m.y));
+          const double ddz = static_cast<double>(fsub(e.z, m.z));
+          const float dist_sq = __double2float_rn(dadd(dadd(dmul(ddx, ddx), dmul(ddy, ddy)), dmul(ddz, ddz)));
+          return dist_sq < g.hit_range_sq ? ST_HIT : ST_SHORT;
+        }
+        return ST_TOTAL_REFLECTION;
+      }
+    }
+    pos.x = fadd(pos.x, inc.x);
+    pos.y = fadd(pos.y, inc.y);
+    pos.z = fadd(pos.z, inc.z);
+  }
+  return ST_LONG;
+}
+
 // begin = s.pos_ + s.rot_ * origins[label] with the RAW rot_ (beam.cpp:145)
 __device__ __forceinline__ F3 ray_origin(const F3& pos, const Q4& q_raw, const float4& o4)
 {
@@ -785,9 +903,11 @@ struct PlShape
   int cb;   // CTAs per particle group (each covers kPlWarps chunks)
 };
 
+template <bool KD>
 __global__ void __launch_bounds__(kBlockThreads, 4)
     beam_kernel_pl(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N,
-                   const float4* __restrict__ origins, DdaGridDev g, mcl3dl_result* __restrict__ out,
+                   const float4* __restrict__ origins, DdaGridDev g, KdRayDev kd, NnGridDev nn,
+                   mcl3dl_result* __restrict__ out,
                    uint8_t* __restrict__ status, int write_lik_defaults, unsigned long long* __restrict__ stats,
                    PlShape sh, uint32_t* __restrict__ partial, unsigned int* __restrict__ tickets)
 {
@@ -831,7 +951,8 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
       v.z = sp.z;
       const F3 end = transform_point(rn, pos, v);  // beam.cpp:138-139
       const F3 begin = ray_origin(pos, q, __ldg(origins + __float_as_uint(sp.w)));
-      const int st = cast_ray(g, begin, end, st_steps, st_occ, st_tested);
+      const int st = KD ? cast_ray_kd(kd, nn, g, begin, end, st_steps, st_occ, st_tested) :
+                          cast_ray(g, begin, end, st_steps, st_occ, st_tested);
       n_short += (st == ST_SHORT);
       n_hit += (st == ST_HIT);
       n_long += (st == ST_LONG);

@@ -40,12 +40,13 @@ class BeamParams(C.Structure):
     _fields_ = [("map_grid_size", C.c_double * 3), ("dda_grid_size", C.c_double), ("ray_angle_half", C.c_double),
                 ("hit_tolerance", C.c_double), ("hit_range_sq", C.c_float), ("sin_total_ref", C.c_float),
                 ("beam_likelihood", C.c_float), ("beam_likelihood_min", C.c_float),
-                ("filter_label_max", C.c_uint32), ("add_penalty_short_only_mode", C.c_int32)]
+                ("filter_label_max", C.c_uint32), ("add_penalty_short_only_mode", C.c_int32),
+                ("use_raycast_using_dda", C.c_int32), ("_reserved", C.c_int32)]
 
     def as_tuple(self):
         return (tuple(self.map_grid_size), self.dda_grid_size, self.ray_angle_half, self.hit_tolerance,
                 self.hit_range_sq, self.sin_total_ref, self.beam_likelihood, self.beam_likelihood_min,
-                self.filter_label_max, self.add_penalty_short_only_mode)
+                self.filter_label_max, self.add_penalty_short_only_mode, self.use_raycast_using_dda)
 
 
 class MapInfo(C.Structure):
@@ -95,7 +96,7 @@ def load_library():
     L.mcl3dl_measure_device.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp]
     L.mcl3dl_beam_status.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp]
     L.mcl3dl_beam_params_from_reference.argtypes = [vp, C.c_float, C.c_float, C.c_float, sz, C.c_float, C.c_float,
-                                                    C.c_uint32, C.c_float, C.c_int, C.c_float, C.c_float]
+                                                    C.c_uint32, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float]
     L.mcl3dl_beam_params_from_reference.restype = None
     L.mcl3dl_get_map_info.argtypes = [vp, vp]
     L.mcl3dl_collect_stats.argtypes = [vp, C.c_int]
@@ -107,7 +108,7 @@ def load_library():
     L.mcl3dl_strerror.restype = C.c_char_p
     L.mcl3dl_last_error_detail.argtypes = [vp]
     L.mcl3dl_last_error_detail.restype = C.c_char_p
-    assert L.mcl3dl_abi_version() == 1
+    assert L.mcl3dl_abi_version() == 2
     _LIB = L
     return L
 
@@ -119,13 +120,15 @@ def _ptr(a):
 def beam_params_from_reference(map_grid=(0.1, 0.1, 0.1), num_points_default=3, beam_likelihood_min=0.2,
                                ang_total_ref=np.pi / 6.0, filter_label_max=0xFFFFFFFF, hit_range=0.3,
                                add_penalty_short_only_mode=True, ray_angle_half=0.25 * np.pi / 180.0,
-                               dda_grid_size=0.2):
-    """LidarMeasurementModelBeamParameters (parameters.h:95-111) -> derived mcl3dl_beam_params."""
+                               dda_grid_size=0.2, use_raycast_using_dda=True):
+    """LidarMeasurementModelBeamParameters (parameters.h:95-111) -> derived mcl3dl_beam_params.
+    (use_raycast_using_dda defaults to True here; the reference's default is False = the KD-tree caster.)"""
     L = load_library()
     bp = BeamParams()
     L.mcl3dl_beam_params_from_reference(C.byref(bp), map_grid[0], map_grid[1], map_grid[2], num_points_default,
                                         beam_likelihood_min, ang_total_ref, filter_label_max, hit_range,
-                                        1 if add_penalty_short_only_mode else 0, ray_angle_half, dda_grid_size)
+                                        1 if add_penalty_short_only_mode else 0, 1 if use_raycast_using_dda else 0,
+                                        ray_angle_half, dda_grid_size)
     return bp
 
 

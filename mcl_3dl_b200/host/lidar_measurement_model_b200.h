@@ -183,7 +183,8 @@ private:
     const auto& b = *beam_params_;
     mcl3dl_beam_params_from_reference(&beam_c_, b.map_grid_x_, b.map_grid_y_, b.map_grid_z_, b.num_points_default_,
                                       b.beam_likelihood_min_, b.ang_total_ref_, b.filter_label_max_, b.hit_range_,
-                                      b.add_penalty_short_only_mode_ ? 1 : 0, b.ray_angle_half_, b.dda_grid_size_);
+                                      b.add_penalty_short_only_mode_ ? 1 : 0, b.use_raycast_using_dda_ ? 1 : 0, b.ray_angle_half_,
+                                      b.dda_grid_size_);
   }
   void refreshScalars()
   {
@@ -284,7 +285,8 @@ private:
 };
 
 // LidarMeasurementModelBeam with measure() served by the engine
-// (replaces src/lidar_measurement_model_beam.cpp:124-155; requires use_raycast_using_dda_ = true).
+// (replaces src/lidar_measurement_model_beam.cpp:124-155 with either raycaster: RaycastUsingKDTree, the
+// node's default, or RaycastUsingDDA when beam/use_raycast_using_dda is set).
 class LidarMeasurementModelBeamB200 : public mcl_3dl::LidarMeasurementModelBeam
 {
 public:
@@ -292,8 +294,6 @@ public:
                                 const MeasurementBatcher::Ptr& batcher)
     : mcl_3dl::LidarMeasurementModelBeam(params), batcher_(batcher)
   {
-    if (!params->use_raycast_using_dda_)
-      throw std::runtime_error("mcl_3dl_b200: the GPU beam model implements RaycastUsingDDA; set beam/use_raycast_using_dda");
   }
   Cloud::Ptr filter(const Cloud::ConstPtr& pc, const mcl_3dl::PointCloudRandomSampler<PointType>& sampler) const override
   {

@@ -126,6 +126,7 @@ void runCycle(Models& m, PF& pf, ChunkedKdtree<PointType>::Ptr& kdtree, const Cl
 int main(int argc, char** argv)
 {
   const int n_particles = argc > 1 ? std::atoi(argv[1]) : 300;
+  const bool use_dda = !(argc > 2 && std::string(argv[2]) == "kd");  // "kd": the node's default RaycastUsingKDTree
   std::mt19937 rng(42);
   std::normal_distribution<float> n01(0.f, 1.f);
   std::uniform_real_distribution<float> u01(0.f, 1.f);
@@ -158,7 +159,7 @@ int main(int argc, char** argv)
   lik_params->num_points_default_ = 96;
   auto beam_params = std::make_shared<LidarMeasurementModelBeamParameters>();
   beam_params->num_points_default_ = 12;
-  beam_params->use_raycast_using_dda_ = true;
+  beam_params->use_raycast_using_dda_ = use_dda;
   beam_params->filter_label_max_ = 1;
 
   // ---- scan in the base frame: points of the map seen from (6, 4, 0.5) yaw 0.3, + noise; labels = sensor id

@@ -31,12 +31,13 @@ class BeamParams(C.Structure):
     _fields_ = [("map_grid_size", C.c_double * 3), ("dda_grid_size", C.c_double), ("ray_angle_half", C.c_double),
                 ("hit_tolerance", C.c_double), ("hit_range_sq", C.c_float), ("sin_total_ref", C.c_float),
                 ("beam_likelihood", C.c_float), ("beam_likelihood_min", C.c_float),
-                ("filter_label_max", C.c_uint32), ("add_penalty_short_only_mode", C.c_int32)]
+                ("filter_label_max", C.c_uint32), ("add_penalty_short_only_mode", C.c_int32),
+                ("use_raycast_using_dda", C.c_int32), ("_reserved", C.c_int32)]
 
     def as_tuple(self):
         return (tuple(self.map_grid_size), self.dda_grid_size, self.ray_angle_half, self.hit_tolerance,
                 self.hit_range_sq, self.sin_total_ref, self.beam_likelihood, self.beam_likelihood_min,
-                self.filter_label_max, self.add_penalty_short_only_mode)
+                self.filter_label_max, self.add_penalty_short_only_mode, self.use_raycast_using_dda)
 
 
 class BeamRaw(C.Structure):
@@ -57,8 +58,9 @@ def lik_params(match_weight=5.0, match_dist_min=0.2, match_dist_flat=0.05, dist_
 
 def beam_raw(map_grid=(0.1, 0.1, 0.1), num_points_default=3, beam_likelihood_min=0.2,
              ang_total_ref=np.pi / 6.0, filter_label_max=0xFFFFFFFF, hit_range=0.3,
-             add_penalty_short_only_mode=True, ray_angle_half=0.25 * np.pi / 180.0, dda_grid_size=0.2):
-    """Defaults: include/mcl_3dl/parameters.h:95-111 (with use_raycast_using_dda forced true)."""
+             add_penalty_short_only_mode=True, ray_angle_half=0.25 * np.pi / 180.0, dda_grid_size=0.2,
+             use_raycast_using_dda=True):
+    """Defaults: include/mcl_3dl/parameters.h:95-111, except use_raycast_using_dda (reference default: false)."""
     r = BeamRaw()
     r.map_grid_x, r.map_grid_y, r.map_grid_z = map_grid
     r.num_points_default = num_points_default
@@ -67,7 +69,7 @@ def beam_raw(map_grid=(0.1, 0.1, 0.1), num_points_default=3, beam_likelihood_min
     r.filter_label_max = filter_label_max
     r.hit_range = hit_range
     r.add_penalty_short_only_mode = 1 if add_penalty_short_only_mode else 0
-    r.use_raycast_using_dda = 1
+    r.use_raycast_using_dda = 1 if use_raycast_using_dda else 0
     r.ray_angle_half = ray_angle_half
     r.dda_grid_size = dda_grid_size
     return r
@@ -142,6 +144,8 @@ class CpuChecker:
         L.mcl3dl_cpu_radius_search.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
         L.mcl3dl_cpu_dda_walk.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.mcl3dl_cpu_kd_walk.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.mcl3dl_cpu_quat_rotate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcl3dl_cpu_transform_point.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcl3dl_cpu_pf_update.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -163,6 +167,23 @@ class CpuChecker:
                                          C.byref(cid))
         assert 0 <= n <= max_out
         return centres[:n].copy(), coll[:n].astype(bool), cid.value
+
+    def kd_walk(self, map_pts, ctor, begin, end, stop_at_collision=True, max_out=4096):
+        """RaycastUsingKDTree(gx, gy, gz, hit_tolerance) walk -> (positions, collision flags, sin_angle, first id)."""
+        map_pts = np.ascontiguousarray(map_pts, dtype=POINT)
+        ctor = np.asarray(ctor, dtype=np.float32)
+        assert ctor.shape == (4,)
+        b = np.asarray(begin, dtype=np.float32)
+        e = np.asarray(end, dtype=np.float32)
+        pos = np.zeros((max_out, 3), dtype=np.float32)
+        coll = np.zeros(max_out, dtype=np.uint8)
+        sa = np.zeros(max_out, dtype=np.float32)
+        cid = C.c_int(-1)
+        n = self.lib.mcl3dl_cpu_kd_walk(_ptr(map_pts), len(map_pts), _ptr(ctor), _ptr(b), _ptr(e),
+                                        1 if stop_at_collision else 0, _ptr(pos), _ptr(coll), _ptr(sa), max_out,
+                                        C.byref(cid))
+        assert 0 <= n <= max_out
+        return pos[:n].copy(), coll[:n].astype(bool), sa[:n].copy(), cid.value
 
     def quat_rotate(self, q, v):
         q = np.asarray(q, dtype=np.float32)

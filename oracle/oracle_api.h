@@ -73,6 +73,12 @@ int mcl3dl_cpu_dda_walk(const mcl3dl_point* pts, size_t n, const double ctor[6],
                         const float begin[3], const float end[3], int stop_at_collision,
                         float* centres, uint8_t* collision, int max_out, int* collided_id);
 
+/* Stand-alone RaycastUsingKDTree<PointXYZ>(gx,gy,gz,hit_tol) over ChunkedKdtree(10.0, 1.0)
+ * (test/src/test_raycast.cpp): positions (pos_), collision flags and sin_angle_ of every cast result. */
+int mcl3dl_cpu_kd_walk(const mcl3dl_point* pts, size_t n, const float ctor[4], const float begin[3], const float end[3],
+                       int stop_at_collision, float* positions, uint8_t* collision, float* sin_angle, int max_out,
+                       int* collided_id);
+
 /* Quat * Vec3 (quat.h:139-143) and State6DOF::transform of one point (state_6dof.h:214-225). */
 void mcl3dl_cpu_quat_rotate(const float q[4], const float v[3], float out[3]);
 void mcl3dl_cpu_transform_point(const mcl3dl_pose* pose, const float v[3], float out[3]);

@@ -25,6 +25,7 @@
 #include <mcl_3dl/point_types.h>
 #include <mcl_3dl/quat.h>
 #include <mcl_3dl/raycasts/raycast_using_dda.h>
+#include <mcl_3dl/raycasts/raycast_using_kdtree.h>
 #include <mcl_3dl/state_6dof.h>
 #include <mcl_3dl/vec3.h>
 
@@ -274,6 +275,8 @@ int mcl3dl_cpu_beam_params(mcl3dl_cpu* h, mcl3dl_beam_params* out)
   out->beam_likelihood_min = p.beam_likelihood_min_;
   out->filter_label_max = h->beams[0]->getFilterLabelMax();
   out->add_penalty_short_only_mode = p.add_penalty_short_only_mode_ ? 1 : 0;
+  out->use_raycast_using_dda = p.use_raycast_using_dda_ ? 1 : 0;
+  out->_reserved = 0;
   return MCL3DL_OK;
 }
 
@@ -329,6 +332,41 @@ int mcl3dl_cpu_dda_walk(const mcl3dl_point* pts, size_t n, const double c[6], co
     {
       if (collided_id && *collided_id < 0)
         *collided_id = static_cast<int>(r.point_ - &shared->points[0]);
+      if (stop_at_collision) break;
+    }
+  }
+  return k;
+}
+
+int mcl3dl_cpu_kd_walk(const mcl3dl_point* pts, size_t n, const float c[4], const float begin[3], const float end[3],
+                       int stop_at_collision, float* positions, uint8_t* collision, float* sin_angle, int max_out,
+                       int* collided_id)
+{
+  pcl::PointCloud<pcl::PointXYZ> pc;
+  for (size_t i = 0; i < n; ++i)
+    pc.push_back(pcl::PointXYZ(pts[i].x, pts[i].y, pts[i].z));
+  mcl_3dl::ChunkedKdtree<pcl::PointXYZ>::Ptr kdtree(new mcl_3dl::ChunkedKdtree<pcl::PointXYZ>(10.0, 1.0));
+  const pcl::PointCloud<pcl::PointXYZ>::ConstPtr shared = pc.makeShared();
+  kdtree->setInputCloud(shared);
+  mcl_3dl::RaycastUsingKDTree<pcl::PointXYZ> raycaster(c[0], c[1], c[2], c[3]);
+  raycaster.setRay(kdtree, Vec3(begin[0], begin[1], begin[2]), Vec3(end[0], end[1], end[2]));
+  mcl_3dl::Raycast<pcl::PointXYZ>::CastResult r;
+  int k = 0;
+  if (collided_id) *collided_id = -1;
+  while (raycaster.getNextCastResult(r))
+  {
+    if (k < max_out)
+    {
+      positions[3 * k + 0] = r.pos_.x_;
+      positions[3 * k + 1] = r.pos_.y_;
+      positions[3 * k + 2] = r.pos_.z_;
+      collision[k] = r.collision_ ? 1 : 0;
+      sin_angle[k] = r.sin_angle_;
+    }
+    ++k;
+    if (r.collision_)
+    {
+      if (collided_id && *collided_id < 0) *collided_id = static_cast<int>(r.point_ - &shared->points[0]);
       if (stop_at_collision) break;
     }
   }

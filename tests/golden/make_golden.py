@@ -7,8 +7,9 @@ The committed .npz files hold inputs AND the reference outputs, so the GPU box (
 
 Fixtures
   beam_likelihood_world.npz  the world and parameter sweep of test/src/test_beam_likelihood.cpp:81-138
-                             (DDA caster): the 100-position likelihood row and the 100 BeamStatus codes
-                             the reference test only prints.
+                             (both casters; rows 0-11 DDA, 12-23 KD-tree): the 100-position likelihood row and
+                             the 100 BeamStatus codes the reference test only prints.
+  room_kd_iso / room_kd_aniso  rooms measured with the KD-tree raycaster (the node's default).
   room_iso.npz / room_aniso.npz / room_spread.npz
                              synthetic room scenes (mcl_3dl_b200.synth) -> per-particle records + per-ray status.
   chunked_radius_search.npz  random ChunkedKdtree::radiusSearch queries (ids + d2), incl. chunk borders.
@@ -60,11 +61,12 @@ def gen_beam_likelihood(ref):
         hrs.append(hr)
         hr += 0.2
     out["hit_ranges"] = np.array(hrs, dtype=np.float64)
-    lik_rows, status_rows, modes = [], [], []
-    for mode in (0, 1):
+    lik_rows, status_rows, modes, methods = [], [], [], []
+    for method, mode in ((1, 0), (1, 1), (0, 0), (0, 1)):  # DDA rows first (kept at indices 0..11), then the KD-tree caster
         for hr in hrs:
             braw = cc.beam_raw(map_grid=(0.1, 0.1, 0.1), num_points_default=len(raw_pc), beam_likelihood_min=0.2,
-                               hit_range=hr, add_penalty_short_only_mode=(mode == 1), dda_grid_size=0.1)
+                               hit_range=hr, add_penalty_short_only_mode=(mode == 1), dda_grid_size=0.1,
+                               use_raycast_using_dda=(method == 1))
             m = ref.create(cc.points(pc_map), None, braw, chunk_length=10.0, max_search_radius=1.0)
             row = []
             for x in xs:
@@ -81,20 +83,22 @@ def gen_beam_likelihood(ref):
                 st.append(int(s[0, 0]))
             status_rows.append(st)
             modes.append(mode)
+            methods.append(method)
             m.close()
     out["likelihood"] = np.array(lik_rows, dtype=np.float32)
     out["status"] = np.array(status_rows, dtype=np.uint8)
     out["mode"] = np.array(modes, dtype=np.int32)
+    out["method"] = np.array(methods, dtype=np.int32)  # 1 = RaycastUsingDDA, 0 = RaycastUsingKDTree
     np.savez_compressed(os.path.join(OUT, "beam_likelihood_world.npz"), **out)
     print("beam_likelihood_world", out["likelihood"].shape)
 
 
 def gen_room(ref, name, dist_weight, spread, seed, n_map=12000, P=48, n_lik=64, n_beam=24, filter_label_max=0xFFFFFFFF,
-             short_only=True, dda_grid=0.2):
+             short_only=True, dda_grid=0.2, use_dda=True):
     s = synth.scene(n_map, P, n_lik, n_beam, spread=spread, n_origins=2, seed=seed)
     lik = cc.lik_params(dist_weight=dist_weight)
     braw = cc.beam_raw(num_points_default=n_beam, filter_label_max=filter_label_max,
-                       add_penalty_short_only_mode=short_only, dda_grid_size=dda_grid)
+                       add_penalty_short_only_mode=short_only, dda_grid_size=dda_grid, use_raycast_using_dda=use_dda)
     m = ref.create(s["map"], lik, braw, chunk_length=20.0, max_search_radius=0.4)
     res = m.measure(s["particles"], s["lik"], s["beam"], s["origins"])
     st = m.beam_status(s["particles"], s["beam"], s["origins"])
@@ -102,9 +106,10 @@ def gen_room(ref, name, dist_weight, spread, seed, n_map=12000, P=48, n_lik=64, 
                         beam=s["beam"], origins=s["origins"], result=res, status=st,
                         dist_weight=np.array(dist_weight, dtype=np.float32),
                         beam_cfg=np.array([n_beam, filter_label_max, 1 if short_only else 0], dtype=np.uint64),
+                        use_dda=np.int32(1 if use_dda else 0),
                         dda_grid=np.float32(dda_grid))
-    print(name, len(s["map"]), "matched", res["match_cnt"].mean(), "short/hit/long",
-          res["n_short"].mean(), res["n_hit"].mean(), res["n_long"].mean())
+    print(name, len(s["map"]), "matched", res["match_cnt"].mean(), "short/hit/long/total_ref",
+          res["n_short"].mean(), res["n_hit"].mean(), res["n_long"].mean(), (st == 3).sum(axis=1).mean())
     m.close()
 
 
@@ -148,5 +153,7 @@ if __name__ == "__main__":
     gen_room(ref, "room_iso", (1, 1, 1), False, seed=100)
     gen_room(ref, "room_aniso", (1, 1, 5), False, seed=200, filter_label_max=1, short_only=False)
     gen_room(ref, "room_spread", (1, 1, 5), True, seed=300, dda_grid=0.1)
+    gen_room(ref, "room_kd_iso", (1, 1, 1), False, seed=400, use_dda=False)
+    gen_room(ref, "room_kd_aniso", (1, 1, 5), False, seed=500, use_dda=False, filter_label_max=1, short_only=False)
     gen_radius_search(ref)
     gen_transform(ref)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert sorted(engine.EXPORTED_SYMBOLS) == names
-    assert L.mcl3dl_abi_version() == 1
+    assert L.mcl3dl_abi_version() == 2
     assert L.mcl3dl_strerror(-2).decode().startswith("measure()")
 
 
@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     from mcl_3dl_b200 import engine, synth
     assert synth.POINT.itemsize == 16 and synth.POSE.itemsize == 32 and synth.RESULT.itemsize == 24
     assert C.sizeof(engine.LikParams) == 24
-    assert C.sizeof(engine.BeamParams) == 72
+    assert C.sizeof(engine.BeamParams) == 80
     assert C.sizeof(engine.MapInfo) == 88
 
 
@@ -42,6 +42,7 @@ def test_struct_layouts_match_header():
     dict(num_points_default=27, hit_range=0.0, add_penalty_short_only_mode=False, dda_grid_size=0.1),
     dict(map_grid=(0.05, 0.1, 0.2), num_points_default=1024, beam_likelihood_min=0.35, hit_range=1.0,
          filter_label_max=1, ang_total_ref=1.2),
+    dict(use_raycast_using_dda=False, num_points_default=7),
 ])
 def test_beam_params_derivation_matches_oracle(port, kw):
     """mcl3dl_beam_params_from_reference == refreshParameters (beam.cpp:58-80) as restated by the oracle

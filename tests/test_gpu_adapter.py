@@ -15,10 +15,10 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "adapter_parity_test")
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_particles", [300, 64, 2049])
-def test_cpp_adapter_matches_reference_models(n_particles):
+@pytest.mark.parametrize("n_particles,caster", [(300, "dda"), (64, "dda"), (2049, "dda"), (300, "kd"), (64, "kd")])
+def test_cpp_adapter_matches_reference_models(n_particles, caster):
     if not os.path.exists(BIN):
         pytest.skip("oracle/_ref/adapter_parity_test not built (needs /root/reference at build time)")
-    r = subprocess.run([BIN, str(n_particles)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([BIN, str(n_particles), caster], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ADAPTER PARITY OK" in r.stdout

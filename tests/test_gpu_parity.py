@@ -23,8 +23,13 @@ def eng_mod():
     return engine
 
 
-@pytest.fixture()
-def eng(eng_mod):
+@pytest.fixture(params=["tuned", "group"])
+def eng(eng_mod, request, monkeypatch):
+    """Both kernel generations (csrc/kernels.cuh): the tuned default and the plain MCL3DL_MAPPING=group ones."""
+    if request.param == "group":
+        monkeypatch.setenv("MCL3DL_MAPPING", "group")
+    else:
+        monkeypatch.delenv("MCL3DL_MAPPING", raising=False)
     e = eng_mod.Engine((0,))
     yield e
     e.close()
@@ -46,14 +51,15 @@ def check_records(got, want, n_beam):
 
 
 # ------------------------------------------------------------------ committed reference outputs
-@pytest.mark.parametrize("name", ["room_iso", "room_aniso", "room_spread"])
+@pytest.mark.parametrize("name", ["room_iso", "room_aniso", "room_spread", "room_kd_iso", "room_kd_aniso"])
 def test_golden_rooms(eng_mod, eng, name):
     g = golden(name + ".npz")
     n_beam, flm, short_only = [int(v) for v in g["beam_cfg"]]
     lik = eng_mod.LikParams(dist_weight=tuple(float(v) for v in g["dist_weight"]))
     beam = eng_mod.beam_params_from_reference(num_points_default=n_beam, filter_label_max=flm,
                                               add_penalty_short_only_mode=bool(short_only),
-                                              dda_grid_size=float(g["dda_grid"]))
+                                              dda_grid_size=float(g["dda_grid"]),
+                                              use_raycast_using_dda=bool(int(g["use_dda"])))
     eng.set_map(g["map"], lik, beam)
     res = eng.measure(g["particles"], g["lik"], g["beam"], g["origins"])
     check_records(res, g["result"], n_beam)
@@ -61,39 +67,42 @@ def test_golden_rooms(eng_mod, eng, name):
 
 
 def test_golden_beam_likelihood_world(eng_mod, eng):
-    """World + sweep of test/src/test_beam_likelihood.cpp:81-210 (DDA caster)."""
+    """World + sweep of test/src/test_beam_likelihood.cpp:81-210, both raycasters."""
     g = golden("beam_likelihood_world.npz")
     pc_map, pc, xs = synth.make_points(g["map"]), synth.make_points(g["scan"]), g["xs"]
     k = 0
-    for mode in (0, 1):
+    for method, mode in ((1, 0), (1, 1), (0, 0), (0, 1)):
         for hr in g["hit_ranges"]:
             beam = eng_mod.beam_params_from_reference(map_grid=(0.1, 0.1, 0.1), num_points_default=len(pc) + 2,
                                                       beam_likelihood_min=0.2, hit_range=float(hr),
-                                                      add_penalty_short_only_mode=(mode == 1), dda_grid_size=0.1)
-            eng.set_map(pc_map, None, beam, stamp=100 + k)
+                                                      add_penalty_short_only_mode=(mode == 1), dda_grid_size=0.1,
+                                                      use_raycast_using_dda=(method == 1))
+            # the KD-tree caster searches the likelihood grid: it needs the (default, isotropic) lik params too
+            eng.set_map(pc_map, eng_mod.LikParams() if method == 0 else None, beam, stamp=100 + k)
             # every x is its own update in the reference test: origin = pose position, identity rotation
             for i, x in enumerate(xs):
                 r = eng.measure(synth.make_poses([[x, 0, 0]], [[0, 0, 0, 1]]), None, pc,
                                 np.array([[x, 0, 0]], np.float32))
-                assert r["score_beam"][0] == g["likelihood"][k, i], (mode, hr, i)
+                assert r["score_beam"][0] == g["likelihood"][k, i], (method, mode, hr, i)
             ident = synth.make_poses([[0, 0, 0]], [[0, 0, 0, 1]])
             st = np.array([eng.beam_status(ident, synth.make_points([[x, 0, 0]]), np.zeros((1, 3), np.float32))[0, 0]
                            for x in xs])
-            assert np.array_equal(st, g["status"][k]), (mode, hr)
+            assert np.array_equal(st, g["status"][k]), (method, mode, hr)
             k += 1
 
 
 # ------------------------------------------------------------------ seeded scenes vs the oracle
-def run_both(eng_mod, eng, cc, s, w, n_beam_default, dda_grid=0.2, flm=0xFFFFFFFF, short_only=True, hit_range=0.3):
+def run_both(eng_mod, eng, cc, s, w, n_beam_default, dda_grid=0.2, flm=0xFFFFFFFF, short_only=True, hit_range=0.3,
+             use_dda=True):
     port = cc.CpuChecker("port")
     lik_c = cc.lik_params(dist_weight=w)
     braw = cc.beam_raw(num_points_default=n_beam_default, dda_grid_size=dda_grid, filter_label_max=flm,
-                       add_penalty_short_only_mode=short_only, hit_range=hit_range)
+                       add_penalty_short_only_mode=short_only, hit_range=hit_range, use_raycast_using_dda=use_dda)
     cpu = port.create(s["map"], lik_c, braw, 20.0, 0.4)
     lik = eng_mod.LikParams(dist_weight=w)
     beam = eng_mod.beam_params_from_reference(num_points_default=n_beam_default, dda_grid_size=dda_grid,
                                               filter_label_max=flm, add_penalty_short_only_mode=short_only,
-                                              hit_range=hit_range)
+                                              hit_range=hit_range, use_raycast_using_dda=use_dda)
     assert beam.as_tuple() == cpu.beam_params().as_tuple()
     eng.set_map(s["map"], lik, beam, stamp=int(np.random.default_rng().integers(1, 2 ** 40)))
     return cpu
@@ -117,6 +126,24 @@ def test_scene_vs_oracle(eng_mod, eng, cc, seed, w, spread, P, n_lik, n_beam):
                           cpu.beam_status(s["particles"], s["beam"], s["origins"]))
     if not spread:
         assert want["match_cnt"].sum() > 0 and want["n_hit"].sum() + want["n_short"].sum() > 0
+
+
+@pytest.mark.parametrize("seed,w,spread,P,n_beam,flm", [
+    (61, (1, 1, 5), False, 64, 3, 0xFFFFFFFF),   # the node's defaults: KD-tree caster, 3 rays
+    (62, (1, 1, 1), False, 200, 48, 1),          # label filter + TOTAL_REFLECTION paths
+    (63, (1, 1, 5), True, 129, 33, 0xFFFFFFFF),  # spread particles
+])
+def test_kdtree_raycaster_vs_oracle(eng_mod, eng, cc, seed, w, spread, P, n_beam, flm):
+    """RaycastUsingKDTree (raycasts/raycast_using_kdtree.h), the reference's default raycaster (parameters.h:109)."""
+    s = synth.scene(50_000, P, 64, n_beam, spread=spread, seed=seed)
+    cpu = run_both(eng_mod, eng, cc, s, w, n_beam, flm=flm, short_only=seed != 62, use_dda=False)
+    want = cpu.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+    got = eng.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+    check_records(got, want, n_beam)
+    st_want = cpu.beam_status(s["particles"], s["beam"], s["origins"])
+    assert np.array_equal(eng.beam_status(s["particles"], s["beam"], s["origins"]), st_want)
+    if seed == 62:
+        assert (st_want == 3).sum() > 0 and (st_want == 1).sum() > 0 and (st_want == 0).sum() > 0
 
 
 def test_edge_cases(eng_mod, eng, cc):

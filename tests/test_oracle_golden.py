@@ -105,6 +105,41 @@ def test_dda_collision_tolerance(port):
     assert not coll.any()
 
 
+# ---------------------------------------------------------------- test_raycast.cpp:40-147 (KD-tree caster)
+def plain_wall(ystep, zstep):
+    return cc.points([(0.5, y, z) for y in frange(-1.0, 1.0, ystep) for z in frange(-1.0, 1.0, zstep)])
+
+
+def test_kd_raycast_collision(port):
+    m = plain_wall(0.1, 0.1)
+    hit_range = float(np.float32(0.1) * np.sqrt(np.float32(3.0)))
+    ctor = [0.1, 0.1, 0.1, hit_range]
+    for y in frange(-0.8, 0.8, 0.11):
+        for z in frange(-0.8, 0.8, 0.13):
+            end = (1.0, float(np.float32(y * 2.0)), float(np.float32(z * 2.0)))
+            pos, coll, _, _ = port.kd_walk(m, ctor, (0, 0, 0), end, stop_at_collision=True)
+            assert coll.any(), (y, z)
+            assert np.linalg.norm(pos[np.argmax(coll)] - np.array([0.5, y, z])) <= 0.2
+    for y in frange(-1.0, 1.0, 0.11):
+        for z in frange(-1.0, 1.0, 0.13):
+            end = (float(np.float32(0.5 - hit_range * 2.0)), y, z)
+            _, coll, _, _ = port.kd_walk(m, ctor, (0, 0, 0), end, stop_at_collision=False)
+            assert not coll.any(), (y, z)
+    _, coll, _, _ = port.kd_walk(m, ctor, (0, 0, 0), (0.5, 3.0, 0.0), stop_at_collision=False)
+    assert not coll.any()
+
+
+# ---------------------------------------------------------------- test_raycast.cpp:149-208 (SinAng)
+def test_kd_raycast_sin_angle(port):
+    m = plain_wall(0.1, 0.1)
+    ctor = [0.1, 0.1, 0.1, float(np.float32(0.1) * np.sqrt(np.float32(3.0)))]
+    for begin, end, want, tol in [((0, 0, 0), (1, 0, 0), 1.0, 0.1), ((0, 5, 0), (1, -5, 0), math.sin(0.5 / 5.0), 0.05),
+                                  ((0, 3, 0), (1, -3, 0), math.sin(0.5 / 3.0), 0.05)]:
+        pos, coll, sa, _ = port.kd_walk(m, ctor, begin, end, stop_at_collision=True)
+        assert coll.any()
+        assert abs(sa[np.argmax(coll)] - want) <= tol
+
+
 # ---------------------------------------------------------------- test_chunked_kdtree.cpp:38-88
 def test_chunked_kdtree_radius_search(port):
     pts = cc.points([(0.5, 0.5, 0.5), (0.8, 0.0, 0.0), (1.3, 0.0, 0.0), (0.0, 0.2, 0.0), (0.0, -0.3, 0.0)])
@@ -163,11 +198,12 @@ def test_golden_beam_likelihood_world(port):
     g = golden("beam_likelihood_world.npz")
     pc_map, pc, xs = cc.points(g["map"]), cc.points(g["scan"]), g["xs"]
     k = 0
-    for mode in (0, 1):
+    for method, mode in ((1, 0), (1, 1), (0, 0), (0, 1)):
         for hr in g["hit_ranges"]:
-            assert g["mode"][k] == mode
+            assert g["mode"][k] == mode and g["method"][k] == method
             braw = cc.beam_raw(map_grid=(0.1, 0.1, 0.1), num_points_default=len(pc) + 2, beam_likelihood_min=0.2,
-                               hit_range=float(hr), add_penalty_short_only_mode=(mode == 1), dda_grid_size=0.1)
+                               hit_range=float(hr), add_penalty_short_only_mode=(mode == 1), dda_grid_size=0.1,
+                               use_raycast_using_dda=(method == 1))
             m = port.create(pc_map, None, braw, chunk_length=10.0, max_search_radius=1.0)
             ident = cc.poses([[0, 0, 0]], [[0, 0, 0, 1]])
             for i, x in enumerate(xs):
@@ -179,13 +215,13 @@ def test_golden_beam_likelihood_world(port):
             k += 1
 
 
-@pytest.mark.parametrize("name", ["room_iso", "room_aniso", "room_spread"])
+@pytest.mark.parametrize("name", ["room_iso", "room_aniso", "room_spread", "room_kd_iso", "room_kd_aniso"])
 def test_golden_rooms(port, name):
     g = golden(name + ".npz")
     n_beam, flm, short_only = [int(v) for v in g["beam_cfg"]]
     lik = cc.lik_params(dist_weight=tuple(float(v) for v in g["dist_weight"]))
     braw = cc.beam_raw(num_points_default=n_beam, filter_label_max=flm, add_penalty_short_only_mode=bool(short_only),
-                       dda_grid_size=float(g["dda_grid"]))
+                       dda_grid_size=float(g["dda_grid"]), use_raycast_using_dda=bool(int(g["use_dda"])))
     m = port.create(g["map"], lik, braw)
     res = m.measure(g["particles"], g["lik"], g["beam"], g["origins"])
     for f in res.dtype.names:
@@ -193,6 +229,8 @@ def test_golden_rooms(port, name):
     assert np.array_equal(m.beam_status(g["particles"], g["beam"], g["origins"]), g["status"])
     # sanity: the fixture exercises every branch
     assert g["result"]["n_short"].sum() and g["result"]["n_hit"].sum() and g["result"]["n_long"].sum()
+    if not int(g["use_dda"]):
+        assert (g["status"] == 3).sum() > 0  # TOTAL_REFLECTION is live with the KD-tree caster (beam.cpp:186-189)
 
 
 @pytest.mark.parametrize("tag", ["iso", "aniso"])
@@ -217,13 +255,16 @@ def test_golden_transform(port):
 
 
 # ---------------------------------------------------------------- live cross-check with oracle/_ref
-@pytest.mark.parametrize("seed,w,spread", [(1, (1, 1, 1), False), (2, (1, 1, 5), False), (3, (1, 1, 5), True),
-                                           (4, (2, 0.5, 3), False)])
-def test_port_equals_reference_build(port, reference, seed, w, spread):
+@pytest.mark.parametrize("seed,w,spread,use_dda", [(1, (1, 1, 1), False, True), (2, (1, 1, 5), False, True),
+                                                   (3, (1, 1, 5), True, True), (4, (2, 0.5, 3), False, True),
+                                                   (5, (1, 1, 1), False, False), (6, (1, 1, 5), False, False),
+                                                   (7, (1, 1, 5), True, False)])
+def test_port_equals_reference_build(port, reference, seed, w, spread, use_dda):
     s = synth.scene(30_000, 96, 128, 48, spread=spread, seed=seed)
     lik = cc.lik_params(dist_weight=w)
     braw = cc.beam_raw(num_points_default=48, dda_grid_size=0.2 if seed % 2 else 0.1,
-                       filter_label_max=1 if seed == 2 else 0xFFFFFFFF, add_penalty_short_only_mode=seed != 3)
+                       filter_label_max=1 if seed in (2, 6) else 0xFFFFFFFF, add_penalty_short_only_mode=seed != 3,
+                       use_raycast_using_dda=use_dda)
     # max_search_radius as the node derives it: max(match_dist_min, 4*map_grid) = 0.4 (mcl_3dl.cpp:1320-1326);
     # the (2,0.5,3) weights need a larger halo for the chunk search to stay complete.
     msr = 0.4 if min(w) >= 1 else 1.0
