@@ -126,6 +126,9 @@ def build_scene(workload, rank, world):
     return s, dda, scaling, P_rank
 
 
+USE_DDA = True
+
+
 def cpu_arm(workload, s, dda, n_lik, n_beam, target_s, threads, want_kind=None):
     """Time the reference CPU path on a bounded particle sample.  Returns (evals/s, meta)."""
     from oracle import cpu_checker as cc
@@ -137,7 +140,8 @@ def cpu_arm(workload, s, dda, n_lik, n_beam, target_s, threads, want_kind=None):
     chk = cc.CpuChecker(kind)
     t0 = time.perf_counter()
     cpu = chk.create(s["map"], cc.lik_params(dist_weight=DIST_WEIGHT),
-                     cc.beam_raw(num_points_default=max(n_beam, 1), dda_grid_size=dda), 20.0, 0.4)
+                     cc.beam_raw(num_points_default=max(n_beam, 1), dda_grid_size=dda, use_raycast_using_dda=USE_DDA),
+                     20.0, 0.4)
     build_s = time.perf_counter() - t0
     cpu.set_tally(False)
     per_particle = max(n_lik + n_beam, 1)
@@ -198,6 +202,7 @@ def config_dict(workload, s, P, n_lik, n_beam, spread, dda, info):
     d = {"workload": "%s: %d particles x (%d likelihood pts + %d beam rays), %d-pt map @%.1f m voxel, %s particles"
                      % (workload, P, n_lik, n_beam, len(s["map"]), MAP_VOXEL, "spread" if spread else "tracking"),
          "dist_weight": list(DIST_WEIGHT), "dda_grid_size": dda, "match_dist_min": 0.2,
+         "raycaster": "RaycastUsingDDA" if USE_DDA else "RaycastUsingKDTree",
          "l2": "flushed (256 MiB write) before every timed step"}
     if info is not None:
         d["nn_grid"] = list(info.nn_dims)
@@ -216,11 +221,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--raycaster", default="dda", choices=["dda", "kd"],
+                    help="beam raycaster: RaycastUsingDDA (north_star) or RaycastUsingKDTree (the node's default)")
     ap.add_argument("--spread", action="store_true", help="spread (global-localisation style) particles: the HBM-bound variant")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    global FORCE_SPREAD
+    global FORCE_SPREAD, USE_DDA
     FORCE_SPREAD = args.spread
+    USE_DDA = args.raycaster == "dda"
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -234,6 +242,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("MCL3DL_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -243,8 +252,10 @@ def main():
     s, dda, scaling, P_rank = build_scene(args.workload, rank, world)
     eng = engine.Engine((local,))  # no fallback: raises without the CUDA library / device
     lik = engine.LikParams(dist_weight=DIST_WEIGHT)
-    beam = engine.beam_params_from_reference(num_points_default=max(n_beam, 1), dda_grid_size=dda)
-    eng.set_map(s["map"], lik if n_lik else None, beam if n_beam else None)
+    use_dda = args.raycaster == "dda"
+    beam = engine.beam_params_from_reference(num_points_default=max(n_beam, 1), dda_grid_size=dda,
+                                             use_raycast_using_dda=use_dda)
+    eng.set_map(s["map"], lik if (n_lik or not use_dda) else None, beam if n_beam else None)
     info = eng.map_info()
 
     particles = s["particles"]
