@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -215,7 +215,7 @@ def config_dict(workload, s, P, n_lik, n_beam, spread, dda, info):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -295,16 +295,17 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # clocks are sampled from the warm-up to the end of the e2e loop: the timed region alone lasts a few
+    # milliseconds, shorter than one nvidia-smi sampling period
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     l0 = eng.kernel_launches()
     total_ms = timed(step, args.steps)
     launches = eng.kernel_launches() - l0
-    clk = clocks.stop() if rank == 0 else None
 
     unit_pts = n_lik if n_lik else n_beam
     evals_step = world * P_rank * unit_pts
@@ -380,6 +381,8 @@ def main():
            "h2d_bytes_per_step": world * (P_rank * 32 + n_lik * 16 + n_beam * 16 + len(s["origins"]) * 16),
            "d2h_bytes_per_step": world * P_rank * 24, "ms_per_step": 1e3 * e2e_s / args.steps,
            "timing": "host wall clock around the synchronous call", "last_call_device_ms": eng.last_timing()}
+
+    clk = clocks.stop() if rank == 0 else None
 
     # ---- sanity: device-resident records == host-path records
     got = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=synth.RESULT)
