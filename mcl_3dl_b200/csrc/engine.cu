@@ -173,6 +173,10 @@ struct DeviceCtx
   void* h_pinned = nullptr;
   size_t h_pinned_cap = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // the two models are independent (disjoint fields of the record): the beam kernel runs on a side stream,
+  // forked from / joined to the caller's stream with events
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
   DevBuf d_partial, d_tickets;  // lane-per-particle kernels: per-CTA partials + per-group ticket counters
   size_t tickets_zeroed = 0;
   DevBuf d_stats;            // 5 x uint64 work counters, only written while stats collection is on
@@ -196,6 +200,7 @@ struct mcl3dl_engine
   uint64_t launches = 0;
   std::string err;
   float nn_cell_factor = 1.0f;
+  int overlap = 1;  // run the beam and likelihood kernels concurrently (MCL3DL_OVERLAP=0 serialises them)
   int mapping = 1;  // 1 = tuned kernels (lik_kernel_wi + beam_kernel_pl); 0 = the plain group kernels (MCL3DL_MAPPING=group)
 };
 
@@ -747,6 +752,8 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     if (v >= 1.0f && v <= 4.0f)
       eng->nn_cell_factor = v;
   }
+  if (const char* o = std::getenv("MCL3DL_OVERLAP"))
+    eng->overlap = std::atoi(o) != 0;
   if (const char* m = std::getenv("MCL3DL_MAPPING"))
     eng->mapping = (std::strcmp(m, "group") == 0) ? 0 : 1;
   eng->devs.resize(n_devices);
@@ -778,6 +785,14 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
         delete eng;
         return MCL3DL_ERR_CUDA;
       }
+    if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&c.ev_b0) != cudaSuccess || cudaEventCreate(&c.ev_b1) != cudaSuccess)
+    {
+      delete eng;
+      return MCL3DL_ERR_CUDA;
+    }
   }
   *out = eng;
   return MCL3DL_OK;
@@ -800,6 +815,14 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     for (auto& e : c.ev)
       if (e)
         cudaEventDestroy(e);
+    for (cudaEvent_t e : {c.ev_fork, c.ev_join, c.ev_b0, c.ev_b1})
+      if (e)
+        cudaEventDestroy(e);
+    if (c.side)
+    {
+      cudaStreamSynchronize(c.side);
+      cudaStreamDestroy(c.side);
+    }
     if (c.stream)
       cudaStreamDestroy(c.stream);
   }
@@ -911,6 +934,43 @@ static int validate_measure(mcl3dl_engine* eng, size_t P, size_t n_lik, size_t n
   return MCL3DL_OK;
 }
 
+// Enqueue both models of one update for the particles [poses, poses+P) of one device.  Node order is "beam"
+// then "likelihood" (src/mcl_3dl.cpp:409-415) but the two write disjoint fields, so when both have a scan the
+// beam kernel goes to the side stream and overlaps the likelihood kernel.  A model without a scan costs no
+// launch: the other kernel writes its (1, 0).  `timed` records ev[2]/ev[3] (likelihood) and ev_b0/ev_b1 (beam).
+static int launch_models(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik,
+                         size_t n_lik, const mcl3dl_point* beam, size_t n_beam, const float4* origins, size_t n_origins,
+                         mcl3dl_result* out, uint8_t* status, cudaStream_t st, bool timed)
+{
+  int rc = MCL3DL_OK;
+  const bool both = n_beam && n_lik && eng->overlap;
+  cudaStream_t sb = both ? c.side : st;
+  if (n_beam)
+  {
+    if (both)
+    {
+      CK(cudaEventRecord(c.ev_fork, st));
+      CK(cudaStreamWaitEvent(sb, c.ev_fork, 0));
+    }
+    if (timed) CK(cudaEventRecord(c.ev_b0, sb));
+    rc = launch_beam(eng, c, poses, P, beam, n_beam, origins, static_cast<int>(n_origins), out, status, n_lik == 0, sb);
+    if (rc != MCL3DL_OK)
+      return rc;
+    if (timed) CK(cudaEventRecord(c.ev_b1, sb));
+    if (both) CK(cudaEventRecord(c.ev_join, sb));
+  }
+  if (timed) CK(cudaEventRecord(c.ev[2], st));
+  if (n_lik || !n_beam)
+  {
+    rc = launch_lik(eng, c, poses, P, lik, n_lik, out, n_beam == 0, st);
+    if (rc != MCL3DL_OK)
+      return rc;
+  }
+  if (timed) CK(cudaEventRecord(c.ev[3], st));
+  if (both) CK(cudaStreamWaitEvent(st, c.ev_join, 0));
+  return rc;
+}
+
 int mcl3dl_measure_device(mcl3dl_engine* eng, const mcl3dl_pose* d_poses, size_t P, const mcl3dl_point* d_lik, size_t n_lik,
                           const mcl3dl_point* d_beam, size_t n_beam, const float* d_origins_xyz, size_t n_origins,
                           mcl3dl_result* d_out, void* cuda_stream)
@@ -937,17 +997,7 @@ int mcl3dl_measure_device(mcl3dl_engine* eng, const mcl3dl_pose* d_poses, size_t
     eng->launches++;
     origins4 = static_cast<const float4*>(c.d_origins.p);
   }
-  // node order: "beam" then "likelihood" (src/mcl_3dl.cpp:409-415); the records are disjoint fields
-  // (a model without a scan this update costs no launch: the other kernel writes its (1, 0))
-  if (n_beam)
-  {
-    rc = launch_beam(eng, c, d_poses, P, d_beam, n_beam, origins4, static_cast<int>(n_origins), d_out, nullptr, n_lik == 0, st);
-    if (rc != MCL3DL_OK)
-      return rc;
-  }
-  if (n_lik || !n_beam)
-    rc = launch_lik(eng, c, d_poses, P, d_lik, n_lik, d_out, n_beam == 0, st);
-  return rc;
+  return launch_models(eng, c, d_poses, P, d_lik, n_lik, d_beam, n_beam, origins4, n_origins, d_out, nullptr, st, false);
 }
 
 static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts, size_t n_lik,
@@ -1005,21 +1055,10 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     const mcl3dl_point* d_beam = reinterpret_cast<const mcl3dl_point*>(d_in + o_beam);
     const float4* d_org = reinterpret_cast<const float4*>(d_in + o_org);
     CK(cudaEventRecord(c.ev[1], st));
-    if (n_beam)
-    {
-      rc = launch_beam(eng, c, d_poses, Pd, d_beam, n_beam, d_org, static_cast<int>(n_origins),
-                       static_cast<mcl3dl_result*>(c.d_out.p),
-                       status ? static_cast<uint8_t*>(c.d_status.p) : nullptr, n_lik == 0, st);
-      if (rc != MCL3DL_OK) return rc;
-    }
-    CK(cudaEventRecord(c.ev[2], st));
-    if (n_lik || !n_beam)
-    {
-      rc = launch_lik(eng, c, d_poses, Pd, d_lik, n_lik,
-                      static_cast<mcl3dl_result*>(c.d_out.p), n_beam == 0, st);
-      if (rc != MCL3DL_OK) return rc;
-    }
-    CK(cudaEventRecord(c.ev[3], st));
+    rc = launch_models(eng, c, d_poses, Pd, d_lik, n_lik, d_beam, n_beam, d_org, n_origins, static_cast<mcl3dl_result*>(c.d_out.p),
+                       status ? static_cast<uint8_t*>(c.d_status.p) : nullptr, st, true);
+    if (rc != MCL3DL_OK) return rc;
+    CK(cudaEventRecord(c.ev[5], st));
     CK(cudaMemcpyAsync(hp + o_out, c.d_out.p, b_out, cudaMemcpyDeviceToHost, st));
     if (b_status) CK(cudaMemcpyAsync(hp + o_status, c.d_status.p, b_status, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(c.ev[4], st));
@@ -1038,12 +1077,15 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     const char* hp = static_cast<const char*>(c.h_pinned);
     if (out) std::memcpy(out + p0[d], hp + o_out, Pd * sizeof(mcl3dl_result));
     if (status) std::memcpy(status + p0[d] * n_beam, hp + o_status, Pd * n_beam);
-    float ms[4] = {0, 0, 0, 0};
-    for (int k = 0; k < 4; ++k) CK(cudaEventElapsedTime(&ms[k], c.ev[k], c.ev[k + 1]));
-    eng->t_h2d = std::max(eng->t_h2d, static_cast<double>(ms[0]));
-    eng->t_beam = std::max(eng->t_beam, static_cast<double>(ms[1]));
-    eng->t_lik = std::max(eng->t_lik, static_cast<double>(ms[2]));
-    eng->t_d2h = std::max(eng->t_d2h, static_cast<double>(ms[3]));
+    float ms_h2d = 0, ms_lik = 0, ms_beam = 0, ms_d2h = 0;
+    CK(cudaEventElapsedTime(&ms_h2d, c.ev[0], c.ev[1]));
+    CK(cudaEventElapsedTime(&ms_lik, c.ev[2], c.ev[3]));
+    if (n_beam) CK(cudaEventElapsedTime(&ms_beam, c.ev_b0, c.ev_b1));
+    CK(cudaEventElapsedTime(&ms_d2h, c.ev[5], c.ev[4]));
+    eng->t_h2d = std::max(eng->t_h2d, static_cast<double>(ms_h2d));
+    eng->t_beam = std::max(eng->t_beam, static_cast<double>(ms_beam));
+    eng->t_lik = std::max(eng->t_lik, static_cast<double>(ms_lik));
+    eng->t_d2h = std::max(eng->t_d2h, static_cast<double>(ms_d2h));
   }
   return MCL3DL_OK;
 }
