@@ -115,6 +115,30 @@ __global__ void nn_gather_kernel(const mcl3dl_point* __restrict__ pts, uint32_t 
   out[k] = make_float4(fmul(p.x, wx), fmul(p.y, wy), fmul(p.z, wz), __uint_as_float(i));
 }
 
+// Window table of the likelihood grid (NnGridDev::row3), from the finished CSR.
+__global__ void nn_row3_kernel(NnGridDev g, uint2* __restrict__ row3, size_t total)
+{
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total)
+    return;
+  const int y = static_cast<int>(i % g.nyp);
+  const size_t zx = i / g.nyp;
+  const int x = static_cast<int>(zx % g.nx);
+  const int z = static_cast<int>(zx / g.nx);
+  uint2 e = make_uint2(0u, 0u);
+  if (y < g.ny)
+  {
+    const size_t cell = (static_cast<size_t>(z) * g.ny + y) * g.nx + x;
+    const uint32_t s0 = g.cell_start[cell];
+    const uint32_t c1 = g.cell_start[cell + min(1, g.nx - x)] - s0;
+    const uint32_t c2 = g.cell_start[cell + min(2, g.nx - x)] - s0;
+    const uint32_t c3 = g.cell_start[cell + min(3, g.nx - x)] - s0;
+    e.x = s0;
+    e.y = min(c1, 0x3ffu) | (min(c2, 0x7ffu) << 10) | (min(c3, 0x7ffu) << 21);  // all-ones field = "read the CSR"
+  }
+  row3[i] = e;
+}
+
 // DDA grid: RaycastUsingDDA::setExists (raycast_using_dda.h:230-235) for every map point.
 __global__ void dda_key_kernel(const mcl3dl_point* __restrict__ pts, uint32_t n, DdaGridDev g,
                                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
@@ -162,7 +186,7 @@ struct DeviceCtx
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   // map
-  DevBuf nn_cell_start, nn_pts, dda_occ, dda_cell_start, dda_pts;
+  DevBuf nn_cell_start, nn_pts, nn_row3, dda_occ, dda_cell_start, dda_pts;
   NnGridDev nn{};
   DdaGridDev dda{};
   KdRayDev kd{};
@@ -591,8 +615,15 @@ int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_
     eng->launches += 3;
     g.cell_start = static_cast<const uint32_t*>(c.nn_cell_start.p);
     g.pts = static_cast<const float4*>(c.nn_pts.p);
+    g.nyp = (g.ny + 4) & ~1;  // even pitch with room for the 4-entry fetch starting at (ly & ~1)
+    const size_t row3_total = static_cast<size_t>(g.nz) * g.nx * g.nyp;
+    CKB(reserve(eng, c.nn_row3, (row3_total + 2) * sizeof(uint2)));
+    g.row3 = static_cast<const uint2*>(c.nn_row3.p);
+    nn_row3_kernel<<<static_cast<unsigned>((row3_total + 255) / 256), 256, 0, st>>>(g, static_cast<uint2*>(c.nn_row3.p), row3_total);
+    CKC(cudaGetLastError());
+    eng->launches++;
     c.nn = g;
-    c.map_bytes += (cells + 1) * 4 + n * 16;
+    c.map_bytes += (cells + 1) * 4 + n * 16 + row3_total * sizeof(uint2);
     eng->info.nn_dims[0] = g.nx;
     eng->info.nn_dims[1] = g.ny;
     eng->info.nn_dims[2] = g.nz;
@@ -807,7 +838,7 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     cudaSetDevice(c.dev);
     if (c.stream)
       cudaStreamSynchronize(c.stream);
-    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.d_poses,
+    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.d_poses,
                       &c.d_origins, &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets})
       free_buf(*b);
     if (c.h_pinned)

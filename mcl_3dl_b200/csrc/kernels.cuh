@@ -27,6 +27,12 @@ struct NnGridDev
 {
   const uint32_t* cell_start;  // [nx*ny*nz + 1]
   const float4* pts;           // rescaled xyz, w = original map index (bits)
+  // Window table for the likelihood kernel: entry (x, y, z) at ((z*nx + x)*nyp + y) = {start of cell (x,y,z),
+  // packed point counts of the 1 / 2 / 3 cells starting there along x (10 | 11 | 11 bits, all-ones = overflow)}.
+  // y is the fastest index, so the three y-rows of a query window are adjacent and one eval fetches its whole
+  // 3x3 window with 6 aligned 16-byte loads instead of 18 scattered 4-byte ones (L1 wavefronts).
+  const uint2* row3;
+  int nyp;  // padded (even) y pitch of row3
   int nx, ny, nz;
   float ox, oy, oz;  // grid origin in the rescaled space
   float inv_cell;
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(kBlockThreads)
 // are bit-identical to the plain kernel.  Requires cell edge > window half-width (<= 3 cells/axis).
 constexpr int kMaxWinRows = 9;
 // map points fetched per batch of an item; measured 1/2/4/8 -> 90/56/52/59 us on c2 (profiles/r01i_variants.txt);
-// capping registers for more resident CTAs only spills and loses (66-149 us)
+// (before the window table) capping registers below 64 for more resident CTAs only spilled and lost (66-149 us)
 constexpr int kWiUnroll = 4;
 
 struct LikWarpSmem
@@ -330,8 +336,10 @@ struct LikWarpSmem
   uint16_t items[kMaxWinRows * 32];   // lane | run << 5
 };
 
+// __launch_bounds__(256, 4): with the window table the kernel wants 72 registers (3 CTAs/SM); capping at 64
+// costs 24 bytes of spill and wins (c2 55 -> 48 us, c5 373 -> 320 us; profiles/r01n_*).
 template <int TPP, bool STAGED>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, 4)
     lik_kernel_wi(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N, NnGridDev g,
                   LikDev lp, mcl3dl_result* __restrict__ out, int write_beam_defaults,
                   unsigned long long* __restrict__ stats)
@@ -418,25 +426,60 @@ __global__ void __launch_bounds__(kBlockThreads)
         if (lx <= hx && ly <= hy && lz <= hz)
         {
           st_rows += static_cast<uint32_t>((hz - lz + 1) * (hy - ly + 1));
-          uint32_t s0[kMaxWinRows], s1[kMaxWinRows];
+          // the whole 3x3 window from the y-fastest window table: 2 aligned 16-byte loads per z layer
+          const int width = hx - lx + 1;  // 1..3 cells along x
+          const int yb = ly & ~1;
+          const int odd = ly & 1;
+          uint4 ea[3], eb[3];
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz)
+          {
+            const int iz = min(lz + dz, hz);
+            const uint4* src = reinterpret_cast<const uint4*>(g.row3 + (static_cast<size_t>(iz) * g.nx + lx) * g.nyp + yb);
+            ea[dz] = __ldg(src);
+            eb[dz] = __ldg(src + 1);
+          }
 #pragma unroll
           for (int dz = 0; dz < 3; ++dz)
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
             {
               const int iy = ly + dy, iz = lz + dz;
-              const bool ok = iy <= hy && iz <= hz;
-              const int row = (iz * g.ny + iy) * g.nx;
-              s0[dz * 3 + dy] = ok ? __ldg(g.cell_start + row + lx) : 0u;
-              s1[dz * 3 + dy] = ok ? __ldg(g.cell_start + row + hx + 1) : 0u;
-            }
-#pragma unroll
-          for (int k = 0; k < kMaxWinRows; ++k)
-            if (s1[k] > s0[k])
-            {
-              sm.rows[nr][lane] = make_uint2(s0[k], s1[k]);
-              ++nr;
-              st_pts += s1[k] - s0[k];
+              if (iy <= hy && iz <= hz)
+              {
+                // entry (iy - yb) of the four fetched ones
+                uint32_t start, packed;
+                if (dy == 0)
+                {
+                  start = odd ? ea[dz].z : ea[dz].x;
+                  packed = odd ? ea[dz].w : ea[dz].y;
+                }
+                else if (dy == 1)
+                {
+                  start = odd ? eb[dz].x : ea[dz].z;
+                  packed = odd ? eb[dz].y : ea[dz].w;
+                }
+                else
+                {
+                  start = odd ? eb[dz].z : eb[dz].x;
+                  packed = odd ? eb[dz].w : eb[dz].y;
+                }
+                uint32_t cnt = width == 3 ? (packed >> 21) : (width == 2 ? ((packed >> 10) & 0x7ffu) : (packed & 0x3ffu));
+                const uint32_t sat = width == 3 ? 0x7ffu : (width == 2 ? 0x7ffu : 0x3ffu);
+                if (cnt == sat)
+                {
+                  // count did not fit the packed field (very dense cells): read the CSR bounds themselves
+                  const int row = (iz * g.ny + iy) * g.nx;
+                  start = __ldg(g.cell_start + row + lx);
+                  cnt = __ldg(g.cell_start + row + hx + 1) - start;
+                }
+                if (cnt)
+                {
+                  sm.rows[nr][lane] = make_uint2(start, start + cnt);
+                  ++nr;
+                  st_pts += cnt;
+                }
+              }
             }
         }
       }
