@@ -496,7 +496,8 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
       const int first = static_cast<int>(incl) - nr;
       for (int k = 0; k < nr; ++k) sm.items[first + k] = static_cast<uint16_t>(lane | (k << 5));
       __syncwarp();
-      // ---------------- phase 2: lane = item (one contiguous run of map points)
+      // ---------------- phase 2: lane = item (one contiguous run of map points); a 4-lanes-per-item variant that
+      // coalesces the point loads was measured and lost (c2 48 -> 57 us, profiles/r01o_*)
       for (int it = lane; it < n_items; it += 32)
       {
         const uint32_t iv = sm.items[it];
