@@ -180,6 +180,32 @@ int mcl3dl_beam_status(mcl3dl_engine*, const mcl3dl_pose* poses, size_t n_partic
                        const mcl3dl_point* beam_pts, size_t n_beam,
                        const float* origins_xyz, size_t n_origins, uint8_t* status);
 
+/* Summary of one fused weight update (row f2 of the scope table). */
+typedef struct
+{
+  float weight_sum;      /* sum of prior * likelihood before normalisation (include/mcl_3dl/pf.h:255-260) */
+  float entropy;         /* -sum p ln p over p > 0 (pf.h:263-272); 0 when !kept */
+  float match_ratio_min; /* min / max over particles of the likelihood model's quality, started at 1 / 0 as the */
+  float match_ratio_max; /*   node does (src/mcl_3dl.cpp:398-399,416-419) */
+  int32_t kept;          /* 1: weights replaced; 0: every weight was zero, the prior is returned (pf.h:274-278) */
+  uint32_t max_index;    /* particle with the largest posterior (first one on ties), pf::ParticleFilter::max */
+} mcl3dl_update_summary;
+
+/* mcl3dl_measure + the weight update that pf::ParticleFilter::measure performs with the node's lambda
+ * (src/mcl_3dl.cpp:402-426, include/mcl_3dl/pf.h:252-279), fused on the device:
+ *   likelihood_i = ((1 * score_beam_i) * score_like_i) [* extra_likelihood_i]     (map-key order, float)
+ *   w_i = prior_i * likelihood_i;  posterior_i = w_i / sum(w)  if sum(w) > 0,  else posterior = prior
+ * Only 4 bytes per particle come back (instead of the 24-byte records, which are optional: records may be NULL).
+ * extra_likelihood (may be NULL) carries per-particle factors the host owns, e.g. the odometry-error term
+ * (src/mcl_3dl.cpp:422-424).  The sum is accumulated in double with a fixed reduction tree (the reference
+ * accumulates sequentially in float), so posteriors agree with the reference to ~1e-5 relative, not bitwise. */
+int mcl3dl_measure_update(mcl3dl_engine*, const mcl3dl_pose* poses, size_t n_particles,
+                          const mcl3dl_point* lik_pts, size_t n_lik,
+                          const mcl3dl_point* beam_pts, size_t n_beam,
+                          const float* origins_xyz, size_t n_origins,
+                          const float* prior, const float* extra_likelihood,
+                          float* posterior, mcl3dl_result* records, mcl3dl_update_summary* summary);
+
 /* Derive mcl3dl_beam_params exactly as LidarMeasurementModelBeam::refreshParameters does from
  * LidarMeasurementModelBeamParameters (include/mcl_3dl/parameters.h:91-132). */
 void mcl3dl_beam_params_from_reference(mcl3dl_beam_params* out,

@@ -201,6 +201,7 @@ struct DeviceCtx
   // forked from / joined to the caller's stream with events
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
+  DevBuf d_w, d_post, d_wpart;   // fused weight update: w_i, posterior, per-CTA partials
   DevBuf d_partial, d_tickets;  // lane-per-particle kernels: per-CTA partials + per-group ticket counters
   size_t tickets_zeroed = 0;
   DevBuf d_stats;            // 5 x uint64 work counters, only written while stats collection is on
@@ -839,7 +840,7 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     if (c.stream)
       cudaStreamSynchronize(c.stream);
     for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.d_poses,
-                      &c.d_origins, &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets})
+                      &c.d_origins, &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart})
       free_buf(*b);
     if (c.h_pinned)
       cudaFreeHost(c.h_pinned);
@@ -1118,6 +1119,170 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     eng->t_lik = std::max(eng->t_lik, static_cast<double>(ms_lik));
     eng->t_d2h = std::max(eng->t_d2h, static_cast<double>(ms_d2h));
   }
+  return MCL3DL_OK;
+}
+
+int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts, size_t n_lik,
+                          const mcl3dl_point* beam_pts, size_t n_beam, const float* origins_xyz, size_t n_origins,
+                          const float* prior, const float* extra, float* posterior, mcl3dl_result* records,
+                          mcl3dl_update_summary* summary)
+{
+  int rc = validate_measure(eng, P, n_lik, n_beam, n_origins);
+  if (rc != MCL3DL_OK)
+    return rc;
+  if (!summary || (P && (!poses || !prior || !posterior)) || (n_lik && !lik_pts) || (n_beam && (!beam_pts || !origins_xyz)))
+    return MCL3DL_ERR_INVALID_ARG;
+  for (size_t j = 0; j < n_beam; ++j)
+    if (beam_pts[j].label >= n_origins)
+      return MCL3DL_ERR_INVALID_ARG;
+  std::memset(summary, 0, sizeof(*summary));
+  summary->match_ratio_min = 1.0f;
+  if (P == 0)
+    return MCL3DL_OK;
+  const size_t G = eng->devs.size();
+  std::vector<size_t> p0(G + 1);
+  for (size_t d = 0; d <= G; ++d) p0[d] = P * d / G;
+  struct Lay
+  {
+    size_t o_lik, o_beam, o_org, o_prior, o_extra, in_bytes, o_post, o_rec, o_part, total;
+    int nblk;
+  };
+  std::vector<Lay> lay(G);
+  // ---- pass 1 on every device: inputs up, both models, w_i and its reduction
+  for (size_t d = 0; d < G; ++d)
+  {
+    DeviceCtx& c = eng->devs[d];
+    const size_t Pd = p0[d + 1] - p0[d];
+    if (Pd == 0)
+      continue;
+    CK(cudaSetDevice(c.dev));
+    cudaStream_t st = c.stream;
+    Lay& L = lay[d];
+    L.o_lik = Pd * sizeof(mcl3dl_pose);
+    L.o_beam = L.o_lik + n_lik * 16;
+    L.o_org = L.o_beam + n_beam * 16;
+    L.o_prior = L.o_org + n_origins * 16;
+    L.o_extra = L.o_prior + ((Pd * 4 + 15) & ~size_t(15));
+    L.in_bytes = L.o_extra + (extra ? ((Pd * 4 + 15) & ~size_t(15)) : 0);
+    L.o_post = L.in_bytes;
+    L.o_rec = L.o_post + ((Pd * 4 + 15) & ~size_t(15));
+    L.o_part = L.o_rec + (records ? Pd * sizeof(mcl3dl_result) : 0);
+    L.total = L.o_part + 2 * sizeof(WeightPartial) + 64;
+    L.nblk = static_cast<int>(std::min<size_t>((Pd + kBlockThreads - 1) / kBlockThreads, static_cast<size_t>(c.sm_count) * 4));
+    if ((rc = reserve_pinned(eng, c, L.total)) || (rc = reserve(eng, c.d_poses, L.in_bytes)) ||
+        (rc = reserve(eng, c.d_out, Pd * sizeof(mcl3dl_result))) || (rc = reserve(eng, c.d_w, Pd * 4)) ||
+        (rc = reserve(eng, c.d_post, Pd * 4)) || (rc = reserve(eng, c.d_wpart, (L.nblk + 1) * sizeof(WeightPartial))))
+      return rc;
+    char* hp = static_cast<char*>(c.h_pinned);
+    std::memcpy(hp, poses + p0[d], Pd * sizeof(mcl3dl_pose));
+    if (n_lik) std::memcpy(hp + L.o_lik, lik_pts, n_lik * 16);
+    if (n_beam) std::memcpy(hp + L.o_beam, beam_pts, n_beam * 16);
+    float* ho = reinterpret_cast<float*>(hp + L.o_org);
+    for (size_t k = 0; k < n_origins; ++k)
+    {
+      ho[4 * k + 0] = origins_xyz[3 * k + 0];
+      ho[4 * k + 1] = origins_xyz[3 * k + 1];
+      ho[4 * k + 2] = origins_xyz[3 * k + 2];
+      ho[4 * k + 3] = 0.0f;
+    }
+    std::memcpy(hp + L.o_prior, prior + p0[d], Pd * 4);
+    if (extra) std::memcpy(hp + L.o_extra, extra + p0[d], Pd * 4);
+    CK(cudaMemcpyAsync(c.d_poses.p, hp, L.in_bytes, cudaMemcpyHostToDevice, st));
+    const char* d_in = static_cast<const char*>(c.d_poses.p);
+    rc = launch_models(eng, c, reinterpret_cast<const mcl3dl_pose*>(d_in), Pd, reinterpret_cast<const mcl3dl_point*>(d_in + L.o_lik),
+                       n_lik, reinterpret_cast<const mcl3dl_point*>(d_in + L.o_beam), n_beam,
+                       reinterpret_cast<const float4*>(d_in + L.o_org), n_origins, static_cast<mcl3dl_result*>(c.d_out.p),
+                       nullptr, st, false);
+    if (rc != MCL3DL_OK)
+      return rc;
+    WeightPartial* parts = static_cast<WeightPartial*>(c.d_wpart.p);
+    weight_kernel<<<L.nblk, kBlockThreads, 0, st>>>(static_cast<const mcl3dl_result*>(c.d_out.p),
+                                                   reinterpret_cast<const float*>(d_in + L.o_prior),
+                                                   extra ? reinterpret_cast<const float*>(d_in + L.o_extra) : nullptr,
+                                                   static_cast<int>(Pd), static_cast<int>(n_lik), static_cast<float*>(c.d_w.p), parts);
+    weight_finish_kernel<<<1, 32, 0, st>>>(parts, L.nblk);
+    CK(cudaGetLastError());
+    eng->launches += 2;
+    CK(cudaMemcpyAsync(hp + L.o_part, parts + L.nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+  }
+  double total = 0.0;
+  float qmin = 1.0f, qmax = 0.0f;
+  for (size_t d = 0; d < G; ++d)
+  {
+    DeviceCtx& c = eng->devs[d];
+    if (p0[d + 1] == p0[d])
+      continue;
+    CK(cudaSetDevice(c.dev));
+    CK(cudaStreamSynchronize(c.stream));
+    WeightPartial wp;
+    std::memcpy(&wp, static_cast<const char*>(c.h_pinned) + lay[d].o_part, sizeof(wp));
+    total += wp.sum;  // device order: deterministic
+    qmin = std::min(qmin, wp.qmin);
+    qmax = std::max(qmax, wp.qmax);
+  }
+  const float total_f = static_cast<float>(total);
+  summary->weight_sum = total_f;
+  summary->match_ratio_min = qmin;
+  summary->match_ratio_max = qmax;
+  summary->kept = total_f > 0.0f ? 1 : 0;
+  // ---- pass 2: normalise (or restore), entropy, arg max; only 4 B per particle come back
+  for (size_t d = 0; d < G; ++d)
+  {
+    DeviceCtx& c = eng->devs[d];
+    const size_t Pd = p0[d + 1] - p0[d];
+    if (Pd == 0)
+      continue;
+    CK(cudaSetDevice(c.dev));
+    cudaStream_t st = c.stream;
+    Lay& L = lay[d];
+    char* hp = static_cast<char*>(c.h_pinned);
+    WeightPartial* parts = static_cast<WeightPartial*>(c.d_wpart.p);
+    if (summary->kept)
+    {
+      normalize_kernel<<<L.nblk, kBlockThreads, 0, st>>>(static_cast<const float*>(c.d_w.p), static_cast<int>(Pd), total_f,
+                                                        static_cast<int>(p0[d]), static_cast<float*>(c.d_post.p), parts);
+      weight_finish_kernel<<<1, 32, 0, st>>>(parts, L.nblk);
+      CK(cudaGetLastError());
+      eng->launches += 2;
+      CK(cudaMemcpyAsync(hp + L.o_post, c.d_post.p, Pd * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(hp + L.o_part, parts + L.nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+    }
+    if (records)
+      CK(cudaMemcpyAsync(hp + L.o_rec, c.d_out.p, Pd * sizeof(mcl3dl_result), cudaMemcpyDeviceToHost, st));
+  }
+  double ent = 0.0;
+  float best = -1.0f;
+  uint32_t best_i = 0;
+  for (size_t d = 0; d < G; ++d)
+  {
+    DeviceCtx& c = eng->devs[d];
+    const size_t Pd = p0[d + 1] - p0[d];
+    if (Pd == 0)
+      continue;
+    CK(cudaSetDevice(c.dev));
+    CK(cudaStreamSynchronize(c.stream));
+    const char* hp = static_cast<const char*>(c.h_pinned);
+    if (summary->kept)
+    {
+      std::memcpy(posterior + p0[d], hp + lay[d].o_post, Pd * 4);
+      WeightPartial wp;
+      std::memcpy(&wp, hp + lay[d].o_part, sizeof(wp));
+      ent += wp.sum;
+      if (wp.best > best)  // lower device = lower indices, so strict '>' keeps the first maximum
+      {
+        best = wp.best;
+        best_i = wp.best_i;
+      }
+    }
+    else
+    {
+      std::memcpy(posterior + p0[d], prior + p0[d], Pd * 4);  // "No Particle alive, restoring." pf.h:274-278
+    }
+    if (records)
+      std::memcpy(records + p0[d], hp + lay[d].o_rec, Pd * sizeof(mcl3dl_result));
+  }
+  summary->entropy = summary->kept ? static_cast<float>(-ent) : 0.0f;
+  summary->max_index = best_i;
   return MCL3DL_OK;
 }
 

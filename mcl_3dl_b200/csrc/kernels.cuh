@@ -1085,4 +1085,133 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
   }
 }
 
+
+// ============================================================================================
+// Fused weight update (scope row f2): pf::ParticleFilter::measure's arithmetic on the records that
+// the two kernels above left on the device.  Deterministic: every reduction has a fixed tree
+// (warp shuffles -> per-CTA slot -> one finishing CTA walks the slots in order).
+struct WeightPartial
+{
+  double sum;       // sum of w (pass 1) or of p*ln p (pass 2)
+  float qmin, qmax; // likelihood-model quality extremes (pass 1)
+  float best;       // largest posterior seen (pass 2)
+  uint32_t best_i;  // its particle index (lowest index on ties)
+};
+
+__device__ __forceinline__ void weight_block_reduce(WeightPartial v, WeightPartial* slot, WeightPartial* sm)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    v.sum = dadd(v.sum, __shfl_xor_sync(0xffffffffu, v.sum, o));
+    v.qmin = fminf(v.qmin, __shfl_xor_sync(0xffffffffu, v.qmin, o));
+    v.qmax = fmaxf(v.qmax, __shfl_xor_sync(0xffffffffu, v.qmax, o));
+    const float ob = __shfl_xor_sync(0xffffffffu, v.best, o);
+    const uint32_t oi = __shfl_xor_sync(0xffffffffu, v.best_i, o);
+    if (ob > v.best || (ob == v.best && oi < v.best_i))
+    {
+      v.best = ob;
+      v.best_i = oi;
+    }
+  }
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0)
+    sm[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    WeightPartial t = sm[0];
+    for (int k = 1; k < kBlockThreads / 32; ++k)
+    {
+      t.sum = dadd(t.sum, sm[k].sum);
+      t.qmin = fminf(t.qmin, sm[k].qmin);
+      t.qmax = fmaxf(t.qmax, sm[k].qmax);
+      if (sm[k].best > t.best || (sm[k].best == t.best && sm[k].best_i < t.best_i))
+      {
+        t.best = sm[k].best;
+        t.best_i = sm[k].best_i;
+      }
+    }
+    *slot = t;
+  }
+}
+
+// pass 1: w_i = prior_i * (((1 * beam) * like) * extra)   (src/mcl_3dl.cpp:406-424, pf.h:258)
+__global__ void __launch_bounds__(kBlockThreads)
+    weight_kernel(const mcl3dl_result* __restrict__ rec, const float* __restrict__ prior, const float* __restrict__ extra,
+                  int P, int n_lik, float* __restrict__ w, WeightPartial* __restrict__ partials)
+{
+  __shared__ WeightPartial sm[kBlockThreads / 32];
+  WeightPartial v;
+  v.sum = 0.0;
+  v.qmin = 1.0f;
+  v.qmax = 0.0f;
+  v.best = -1.0f;
+  v.best_i = 0xffffffffu;
+  for (int i = blockIdx.x * kBlockThreads + threadIdx.x; i < P; i += gridDim.x * kBlockThreads)
+  {
+    const mcl3dl_result r = rec[i];
+    float lk = fmul(1.0f, r.score_beam);  // map-key order: "beam" then "likelihood"
+    lk = fmul(lk, r.score_like);
+    if (extra)
+      lk = fmul(lk, extra[i]);
+    const float wi = fmul(prior[i], lk);
+    w[i] = wi;
+    v.sum = dadd(v.sum, static_cast<double>(wi));
+    // quality of the likelihood model: match_cnt / N, (0 for an empty scan: likelihood.cpp:111-114)
+    const float q = n_lik > 0 ? fdiv(static_cast<float>(r.match_cnt), static_cast<float>(n_lik)) : 0.0f;
+    v.qmin = fminf(v.qmin, q);
+    v.qmax = fmaxf(v.qmax, q);
+  }
+  weight_block_reduce(v, partials + blockIdx.x, sm);
+}
+
+// pass 2: p_i = w_i / sum (pf.h:266), entropy terms p ln p (pf.h:267-270), arg max
+__global__ void __launch_bounds__(kBlockThreads)
+    normalize_kernel(const float* __restrict__ w, int P, float total, int index_offset, float* __restrict__ post,
+                     WeightPartial* __restrict__ partials)
+{
+  __shared__ WeightPartial sm[kBlockThreads / 32];
+  WeightPartial v;
+  v.sum = 0.0;
+  v.qmin = 1.0f;
+  v.qmax = 0.0f;
+  v.best = -1.0f;
+  v.best_i = 0xffffffffu;
+  for (int i = blockIdx.x * kBlockThreads + threadIdx.x; i < P; i += gridDim.x * kBlockThreads)
+  {
+    const float p = fdiv(w[i], total);
+    post[i] = p;
+    if (p > 0.0f)
+      v.sum = dadd(v.sum, static_cast<double>(fmul(p, logf(p))));
+    const uint32_t gi = static_cast<uint32_t>(index_offset + i);
+    if (p > v.best || (p == v.best && gi < v.best_i))
+    {
+      v.best = p;
+      v.best_i = gi;
+    }
+  }
+  weight_block_reduce(v, partials + blockIdx.x, sm);
+}
+
+// fold the per-CTA slots in order into slot [n]
+__global__ void weight_finish_kernel(WeightPartial* __restrict__ partials, int n)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  WeightPartial t = partials[0];
+  for (int k = 1; k < n; ++k)
+  {
+    t.sum = dadd(t.sum, partials[k].sum);
+    t.qmin = fminf(t.qmin, partials[k].qmin);
+    t.qmax = fmaxf(t.qmax, partials[k].qmax);
+    if (partials[k].best > t.best || (partials[k].best == t.best && partials[k].best_i < t.best_i))
+    {
+      t.best = partials[k].best;
+      t.best_i = partials[k].best_i;
+    }
+  }
+  partials[n] = t;
+}
+
 }  // namespace mcl3dl

@@ -55,6 +55,14 @@ class MapInfo(C.Structure):
                 ("dda_max", C.c_float * 3), ("device_bytes", C.c_uint64), ("build_ms", C.c_double)]
 
 
+class UpdateSummary(C.Structure):
+    _fields_ = [("weight_sum", C.c_float), ("entropy", C.c_float), ("match_ratio_min", C.c_float),
+                ("match_ratio_max", C.c_float), ("kept", C.c_int32), ("max_index", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class WorkStats(C.Structure):
     _fields_ = [("lik_index_rows", C.c_uint64), ("lik_points_scanned", C.c_uint64),
                 ("beam_cells_stepped", C.c_uint64), ("beam_cells_occupied", C.c_uint64),
@@ -64,7 +72,7 @@ class WorkStats(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
-EXPORTED_SYMBOLS = ["mcl3dl_collect_stats", "mcl3dl_read_stats", "mcl3dl_abi_version", "mcl3dl_create", "mcl3dl_destroy", "mcl3dl_set_map", "mcl3dl_set_params",
+EXPORTED_SYMBOLS = ["mcl3dl_measure_update", "mcl3dl_collect_stats", "mcl3dl_read_stats", "mcl3dl_abi_version", "mcl3dl_create", "mcl3dl_destroy", "mcl3dl_set_map", "mcl3dl_set_params",
                     "mcl3dl_measure", "mcl3dl_measure_device", "mcl3dl_beam_status",
                     "mcl3dl_beam_params_from_reference", "mcl3dl_get_map_info", "mcl3dl_last_timing",
                     "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail"]
@@ -93,6 +101,7 @@ def load_library():
     L.mcl3dl_set_map.argtypes = [vp, vp, sz, C.c_uint64, vp, vp]
     L.mcl3dl_set_params.argtypes = [vp, vp, vp]
     L.mcl3dl_measure.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp]
+    L.mcl3dl_measure_update.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp, vp]
     L.mcl3dl_measure_device.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp]
     L.mcl3dl_beam_status.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp]
     L.mcl3dl_beam_params_from_reference.argtypes = [vp, C.c_float, C.c_float, C.c_float, sz, C.c_float, C.c_float,
@@ -186,6 +195,25 @@ class Engine:
         self._check(self.L.mcl3dl_measure(self.h, _ptr(poses), len(poses), _ptr(lik_pts), len(lik_pts),
                                           _ptr(beam_pts), len(beam_pts), _ptr(origins), len(origins), _ptr(out)))
         return out
+
+    def measure_update(self, poses, lik_pts, beam_pts, origins, prior, extra_likelihood=None, want_records=False):
+        """Fused measurement + weight update (pf::ParticleFilter::measure with the node's lambda).
+        Returns (posterior float32[P], summary dict, records or None)."""
+        poses = np.ascontiguousarray(poses, dtype=POSE)
+        lik_pts = np.ascontiguousarray(lik_pts if lik_pts is not None else np.zeros(0, POINT), dtype=POINT)
+        beam_pts = np.ascontiguousarray(beam_pts if beam_pts is not None else np.zeros(0, POINT), dtype=POINT)
+        origins = np.ascontiguousarray(origins if origins is not None else np.zeros((0, 3)), dtype=np.float32)
+        origins = origins.reshape(-1, 3)
+        prior = np.ascontiguousarray(prior, dtype=np.float32)
+        extra = np.ascontiguousarray(extra_likelihood, dtype=np.float32) if extra_likelihood is not None else None
+        post = np.zeros(len(poses), dtype=np.float32)
+        rec = np.zeros(len(poses), dtype=RESULT) if want_records else None
+        summ = UpdateSummary()
+        self._check(self.L.mcl3dl_measure_update(self.h, _ptr(poses), len(poses), _ptr(lik_pts), len(lik_pts),
+                                                 _ptr(beam_pts), len(beam_pts), _ptr(origins), len(origins),
+                                                 _ptr(prior), _ptr(extra) if extra is not None else None,
+                                                 _ptr(post), _ptr(rec) if rec is not None else None, C.byref(summ)))
+        return post, summ.as_dict(), rec
 
     def measure_device(self, d_poses, n_particles, d_lik, n_lik, d_beam, n_beam, d_origins, n_origins, d_out,
                        stream=0):

@@ -291,3 +291,45 @@ def test_multi_device_engine_matches_single(eng_mod, big_scene):
     assert np.array_equal(e1.measure(P, s["lik"], s["beam"], s["origins"]), e2.measure(P, s["lik"], s["beam"], s["origins"]))
     e1.close()
     e2.close()
+
+
+# ------------------------------------------------------------------ scope row f2: fused weight update
+@pytest.mark.parametrize("P,seed,with_extra", [(64, 71, False), (1000, 72, True), (65536, 73, True)])
+def test_fused_weight_update_vs_pf_measure(eng_mod, eng, cc, P, seed, with_extra):
+    """mcl3dl_measure_update == pf::ParticleFilter::measure driven by the node's lambda (pf.h:252-279,
+    mcl_3dl.cpp:402-426).  Tolerance 1e-4 relative on posteriors / entropy: the reference sums sequentially
+    in float, the device sums in double with a fixed tree."""
+    n_lik, n_beam = (96, 3) if P <= 1000 else (16, 2)
+    s = synth.scene(50_000, P, n_lik, n_beam, seed=seed)
+    cpu = run_both(eng_mod, eng, cc, s, (1, 1, 5), n_beam)
+    rng = np.random.default_rng(seed)
+    prior = rng.uniform(0.1, 1.0, P).astype(np.float32)
+    prior /= prior.sum(dtype=np.float64).astype(np.float32)
+    extra = rng.uniform(0.5, 1.0, P).astype(np.float32) if with_extra else None
+    post, summ, rec = eng.measure_update(s["particles"], s["lik"], s["beam"], s["origins"], prior, extra, want_records=True)
+    want_rec = eng.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+    assert np.array_equal(rec, want_rec)
+    like = (np.float32(1.0) * want_rec["score_beam"]).astype(np.float32)
+    like = (like * want_rec["score_like"]).astype(np.float32)
+    if extra is not None:
+        like = (like * extra).astype(np.float32)
+    port = cc.CpuChecker("port")
+    ref_post, ref_ent, ref_kept = port.pf_update(prior, like)
+    assert bool(summ["kept"]) == ref_kept and ref_kept
+    assert np.allclose(post, ref_post, rtol=1e-4, atol=1e-12)
+    assert abs(summ["entropy"] - ref_ent) <= 1e-4 * abs(ref_ent) + 1e-6
+    q = want_rec["match_cnt"].astype(np.float32) / np.float32(n_lik)
+    assert summ["match_ratio_min"] == min(np.float32(1.0), q.min()) and summ["match_ratio_max"] == max(np.float32(0.0), q.max())
+    assert post[summ["max_index"]] == post.max()
+    assert abs(float(post.sum(dtype=np.float64)) - 1.0) < 1e-4
+
+
+def test_fused_weight_update_restores_when_no_particle_survives(eng_mod, eng, cc):
+    s = synth.scene(20_000, 50, 32, 4, seed=81)
+    run_both(eng_mod, eng, cc, s, (1, 1, 5), 4)
+    far = s["particles"].copy()
+    far["px"] += np.float32(1e4)  # nothing matches: score_like = 0 for every particle
+    prior = np.full(50, 0.02, np.float32)
+    post, summ, _ = eng.measure_update(far, s["lik"], s["beam"], s["origins"], prior)
+    assert summ["kept"] == 0 and np.array_equal(post, prior) and summ["weight_sum"] == 0.0
+    assert summ["match_ratio_max"] == 0.0
