@@ -382,6 +382,25 @@ def main():
            "d2h_bytes_per_step": world * P_rank * 24, "ms_per_step": 1e3 * e2e_s / args.steps,
            "timing": "host wall clock around the synchronous call", "last_call_device_ms": eng.last_timing()}
 
+    # ---- e2e with the fused weight update (scope row f2): priors up, posteriors (4 B/particle) back
+    prior = np.full(P_rank, 1.0 / max(P_rank, 1), dtype=np.float32)
+    for _ in range(3):
+        eng.measure_update(particles, s["lik"], s["beam"], s["origins"], prior)
+    fused_tot = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        post, summ, _ = eng.measure_update(particles, s["lik"], s["beam"], s["origins"], prior)
+        fused_tot += time.perf_counter() - t0
+    t = torch.tensor([fused_tot], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e["fused_weight_update"] = {"value": evals_step * args.steps / float(t.item()), "unit": "evals/s",
+                                  "ms_per_step": 1e3 * float(t.item()) / args.steps,
+                                  "h2d_bytes_per_step": e2e["h2d_bytes_per_step"] + world * P_rank * 4,
+                                  "d2h_bytes_per_step": world * P_rank * 4,
+                                  "entropy": summ["entropy"], "kept": summ["kept"]}
     clk = clocks.stop() if rank == 0 else None
 
     # ---- sanity: device-resident records == host-path records
