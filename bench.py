@@ -174,6 +174,10 @@ def run_reference_arm(args):
     s, dda, scaling, P_rank = build_scene(args.workload, 0, 1)
     threads = os.cpu_count() or 1
     unit_pts = n_lik if n_lik else n_beam
+    # give every thread enough particles to amortise its start-up: tile the particle set to >= 64 per thread
+    need = threads * 64
+    if len(s["particles"]) < need:
+        s["particles"] = np.tile(s["particles"], (need + len(s["particles"]) - 1) // len(s["particles"]))
     n_sample, dt, cpu, meta = cpu_arm(args.workload, s, dda, n_lik, n_beam, 2.0, threads)
     sample = s["particles"][:n_sample]
     for _ in range(args.warmup):

@@ -167,13 +167,6 @@ __global__ void dda_gather_kernel(const mcl3dl_point* __restrict__ pts, uint32_t
   out[k] = __ldg(reinterpret_cast<const float4*>(pts) + order[k]);  // xyz + label bits, map order kept by the stable sort
 }
 
-__global__ void pack_origins_kernel(const float* __restrict__ xyz, int n, float4* __restrict__ out)
-{
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n)
-    out[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0f);
-}
-
 struct DevBuf
 {
   void* p = nullptr;
@@ -193,7 +186,7 @@ struct DeviceCtx
   DevBuf raw_pts;  // map points in original order (KD-tree raycaster only)
   size_t map_bytes = 0;
   // per-update I/O
-  DevBuf d_poses /* whole input block of the host path */, d_origins, d_out, d_status;
+  DevBuf d_poses /* whole input block of the host path */, d_out, d_status;
   void* h_pinned = nullptr;
   size_t h_pinned_cap = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -323,7 +316,7 @@ int launch_lik_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int
 
 template <int TPP>
 int launch_beam_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int P, const float4* scan, int N,
-                  const float4* origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
+                  const float* origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
 {
   constexpr int PPB = kBlockThreads / TPP;
   const int groups = (P + PPB - 1) / PPB;
@@ -375,7 +368,7 @@ int prepare_pl_scratch(mcl3dl_engine* eng, DeviceCtx& c, size_t P, const PlShape
 }
 
 int launch_beam_pl(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
-                   const float4* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
+                   const float* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
 {
   const PlShape sh = pick_pl_shape(P, N, c.sm_count);
   int rc = prepare_pl_scratch(eng, c, P, sh, st);
@@ -410,7 +403,7 @@ int launch_lik(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_
 }
 
 int launch_beam(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
-                const float4* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
+                const float* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
 {
   if (eng->mapping != 0 || !eng->beam.use_raycast_using_dda)  // the KD-tree caster exists in the pl kernel only
     return launch_beam_pl(eng, c, poses, P, scan, N, origins, n_origins, out, status, lik_defaults, st);
@@ -840,7 +833,7 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     if (c.stream)
       cudaStreamSynchronize(c.stream);
     for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.d_poses,
-                      &c.d_origins, &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart})
+                      &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart})
       free_buf(*b);
     if (c.h_pinned)
       cudaFreeHost(c.h_pinned);
@@ -971,7 +964,7 @@ static int validate_measure(mcl3dl_engine* eng, size_t P, size_t n_lik, size_t n
 // beam kernel goes to the side stream and overlaps the likelihood kernel.  A model without a scan costs no
 // launch: the other kernel writes its (1, 0).  `timed` records ev[2]/ev[3] (likelihood) and ev_b0/ev_b1 (beam).
 static int launch_models(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik,
-                         size_t n_lik, const mcl3dl_point* beam, size_t n_beam, const float4* origins, size_t n_origins,
+                         size_t n_lik, const mcl3dl_point* beam, size_t n_beam, const float* origins, size_t n_origins,
                          mcl3dl_result* out, uint8_t* status, cudaStream_t st, bool timed)
 {
   int rc = MCL3DL_OK;
@@ -1017,19 +1010,7 @@ int mcl3dl_measure_device(mcl3dl_engine* eng, const mcl3dl_pose* d_poses, size_t
   DeviceCtx& c = eng->devs[0];
   CK(cudaSetDevice(c.dev));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  const float4* origins4 = nullptr;
-  if (n_beam)
-  {
-    rc = reserve(eng, c.d_origins, n_origins * 16);
-    if (rc != MCL3DL_OK)
-      return rc;
-    pack_origins_kernel<<<static_cast<int>((n_origins + 127) / 128), 128, 0, st>>>(d_origins_xyz, static_cast<int>(n_origins),
-                                                                                  static_cast<float4*>(c.d_origins.p));
-    CK(cudaGetLastError());
-    eng->launches++;
-    origins4 = static_cast<const float4*>(c.d_origins.p);
-  }
-  return launch_models(eng, c, d_poses, P, d_lik, n_lik, d_beam, n_beam, origins4, n_origins, d_out, nullptr, st, false);
+  return launch_models(eng, c, d_poses, P, d_lik, n_lik, d_beam, n_beam, d_origins_xyz, n_origins, d_out, nullptr, st, false);
 }
 
 static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts, size_t n_lik,
@@ -1058,7 +1039,7 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
       continue;
     CK(cudaSetDevice(c.dev));
     cudaStream_t st = c.stream;
-    const size_t b_poses = Pd * sizeof(mcl3dl_pose), b_lik = n_lik * 16, b_beam = n_beam * 16, b_org = n_origins * 16;
+    const size_t b_poses = Pd * sizeof(mcl3dl_pose), b_lik = n_lik * 16, b_beam = n_beam * 16, b_org = (n_origins * 12 + 15) & ~size_t(15);
     const size_t b_out = Pd * sizeof(mcl3dl_result), b_status = status ? Pd * n_beam : 0;
     const size_t o_lik = b_poses, o_beam = o_lik + b_lik, o_org = o_beam + b_beam, o_out = o_org + b_org;
     const size_t o_status = o_out + b_out;
@@ -1071,21 +1052,14 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     std::memcpy(hp, poses + p0[d], b_poses);
     if (b_lik) std::memcpy(hp + o_lik, lik_pts, b_lik);
     if (b_beam) std::memcpy(hp + o_beam, beam_pts, b_beam);
-    float* ho = reinterpret_cast<float*>(hp + o_org);
-    for (size_t k = 0; k < n_origins; ++k)
-    {
-      ho[4 * k + 0] = origins_xyz[3 * k + 0];
-      ho[4 * k + 1] = origins_xyz[3 * k + 1];
-      ho[4 * k + 2] = origins_xyz[3 * k + 2];
-      ho[4 * k + 3] = 0.0f;
-    }
+    if (n_origins) std::memcpy(hp + o_org, origins_xyz, n_origins * 12);
     CK(cudaEventRecord(c.ev[0], st));
     CK(cudaMemcpyAsync(c.d_poses.p, hp, o_out, cudaMemcpyHostToDevice, st));
     const char* d_in = static_cast<const char*>(c.d_poses.p);
     const mcl3dl_pose* d_poses = reinterpret_cast<const mcl3dl_pose*>(d_in);
     const mcl3dl_point* d_lik = reinterpret_cast<const mcl3dl_point*>(d_in + o_lik);
     const mcl3dl_point* d_beam = reinterpret_cast<const mcl3dl_point*>(d_in + o_beam);
-    const float4* d_org = reinterpret_cast<const float4*>(d_in + o_org);
+    const float* d_org = reinterpret_cast<const float*>(d_in + o_org);
     CK(cudaEventRecord(c.ev[1], st));
     rc = launch_models(eng, c, d_poses, Pd, d_lik, n_lik, d_beam, n_beam, d_org, n_origins, static_cast<mcl3dl_result*>(c.d_out.p),
                        status ? static_cast<uint8_t*>(c.d_status.p) : nullptr, st, true);
@@ -1104,7 +1078,7 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
       continue;
     CK(cudaSetDevice(c.dev));
     CK(cudaStreamSynchronize(c.stream));
-    const size_t o_out = Pd * sizeof(mcl3dl_pose) + n_lik * 16 + n_beam * 16 + n_origins * 16;
+    const size_t o_out = Pd * sizeof(mcl3dl_pose) + n_lik * 16 + n_beam * 16 + ((n_origins * 12 + 15) & ~size_t(15));
     const size_t o_status = o_out + Pd * sizeof(mcl3dl_result);
     const char* hp = static_cast<const char*>(c.h_pinned);
     if (out) std::memcpy(out + p0[d], hp + o_out, Pd * sizeof(mcl3dl_result));
@@ -1161,7 +1135,7 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
     L.o_lik = Pd * sizeof(mcl3dl_pose);
     L.o_beam = L.o_lik + n_lik * 16;
     L.o_org = L.o_beam + n_beam * 16;
-    L.o_prior = L.o_org + n_origins * 16;
+    L.o_prior = L.o_org + ((n_origins * 12 + 15) & ~size_t(15));
     L.o_extra = L.o_prior + ((Pd * 4 + 15) & ~size_t(15));
     L.in_bytes = L.o_extra + (extra ? ((Pd * 4 + 15) & ~size_t(15)) : 0);
     L.o_post = L.in_bytes;
@@ -1177,21 +1151,14 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
     std::memcpy(hp, poses + p0[d], Pd * sizeof(mcl3dl_pose));
     if (n_lik) std::memcpy(hp + L.o_lik, lik_pts, n_lik * 16);
     if (n_beam) std::memcpy(hp + L.o_beam, beam_pts, n_beam * 16);
-    float* ho = reinterpret_cast<float*>(hp + L.o_org);
-    for (size_t k = 0; k < n_origins; ++k)
-    {
-      ho[4 * k + 0] = origins_xyz[3 * k + 0];
-      ho[4 * k + 1] = origins_xyz[3 * k + 1];
-      ho[4 * k + 2] = origins_xyz[3 * k + 2];
-      ho[4 * k + 3] = 0.0f;
-    }
+    if (n_origins) std::memcpy(hp + L.o_org, origins_xyz, n_origins * 12);
     std::memcpy(hp + L.o_prior, prior + p0[d], Pd * 4);
     if (extra) std::memcpy(hp + L.o_extra, extra + p0[d], Pd * 4);
     CK(cudaMemcpyAsync(c.d_poses.p, hp, L.in_bytes, cudaMemcpyHostToDevice, st));
     const char* d_in = static_cast<const char*>(c.d_poses.p);
     rc = launch_models(eng, c, reinterpret_cast<const mcl3dl_pose*>(d_in), Pd, reinterpret_cast<const mcl3dl_point*>(d_in + L.o_lik),
                        n_lik, reinterpret_cast<const mcl3dl_point*>(d_in + L.o_beam), n_beam,
-                       reinterpret_cast<const float4*>(d_in + L.o_org), n_origins, static_cast<mcl3dl_result*>(c.d_out.p),
+                       reinterpret_cast<const float*>(d_in + L.o_org), n_origins, static_cast<mcl3dl_result*>(c.d_out.p),
                        nullptr, st, false);
     if (rc != MCL3DL_OK)
       return rc;

@@ -818,12 +818,13 @@ __device__ __forceinline__ int cast_ray_kd(const KdRayDev& k, const NnGridDev& n
 }
 
 // begin = s.pos_ + s.rot_ * origins[label] with the RAW rot_ (beam.cpp:145)
-__device__ __forceinline__ F3 ray_origin(const F3& pos, const Q4& q_raw, const float4& o4)
+__device__ __forceinline__ F3 ray_origin(const F3& pos, const Q4& q_raw, const float* __restrict__ origins_xyz,
+                                         uint32_t label)
 {
   F3 o;
-  o.x = o4.x;
-  o.y = o4.y;
-  o.z = o4.z;
+  o.x = __ldg(origins_xyz + 3 * label);
+  o.y = __ldg(origins_xyz + 3 * label + 1);
+  o.z = __ldg(origins_xyz + 3 * label + 2);
   const F3 ro = qrot(q_raw, o);
   F3 begin;
   begin.x = fadd(pos.x, ro.x);
@@ -835,7 +836,7 @@ __device__ __forceinline__ F3 ray_origin(const F3& pos, const Q4& q_raw, const f
 template <int TPP, bool STAGED>
 __global__ void __launch_bounds__(kBlockThreads)
     beam_kernel(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N,
-                const float4* __restrict__ origins, DdaGridDev g, mcl3dl_result* __restrict__ out,
+                const float* __restrict__ origins, DdaGridDev g, mcl3dl_result* __restrict__ out,
                 uint8_t* __restrict__ status, int write_lik_defaults, unsigned long long* __restrict__ stats)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -881,7 +882,7 @@ __global__ void __launch_bounds__(kBlockThreads)
         v.y = sp.y;
         v.z = sp.z;
         const F3 end = transform_point(rn, pos, v);  // beam.cpp:138-139
-        const F3 begin = ray_origin(pos, q, __ldg(origins + __float_as_uint(sp.w)));
+        const F3 begin = ray_origin(pos, q, origins, __float_as_uint(sp.w));
         const int st = cast_ray(g, begin, end, st_steps, st_occ, st_tested);
         n_short += (st == ST_SHORT);
         n_hit += (st == ST_HIT);
@@ -950,7 +951,7 @@ struct PlShape
 template <bool KD>
 __global__ void __launch_bounds__(kBlockThreads, 4)
     beam_kernel_pl(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N,
-                   const float4* __restrict__ origins, DdaGridDev g, KdRayDev kd, NnGridDev nn,
+                   const float* __restrict__ origins, DdaGridDev g, KdRayDev kd, NnGridDev nn,
                    mcl3dl_result* __restrict__ out,
                    uint8_t* __restrict__ status, int write_lik_defaults, unsigned long long* __restrict__ stats,
                    PlShape sh, uint32_t* __restrict__ partial, unsigned int* __restrict__ tickets)
@@ -994,7 +995,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
       v.y = sp.y;
       v.z = sp.z;
       const F3 end = transform_point(rn, pos, v);  // beam.cpp:138-139
-      const F3 begin = ray_origin(pos, q, __ldg(origins + __float_as_uint(sp.w)));
+      const F3 begin = ray_origin(pos, q, origins, __float_as_uint(sp.w));
       const int st = KD ? cast_ray_kd(kd, nn, g, begin, end, st_steps, st_occ, st_tested) :
                           cast_ray(g, begin, end, st_steps, st_occ, st_tested);
       n_short += (st == ST_SHORT);
