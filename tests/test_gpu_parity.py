@@ -333,3 +333,25 @@ def test_fused_weight_update_restores_when_no_particle_survives(eng_mod, eng, cc
     post, summ, _ = eng.measure_update(far, s["lik"], s["beam"], s["origins"], prior)
     assert summ["kept"] == 0 and np.array_equal(post, prior) and summ["weight_sum"] == 0.0
     assert summ["match_ratio_max"] == 0.0
+
+
+def test_multi_device_fused_update_matches_single(eng_mod, big_scene):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = big_scene
+    lik = eng_mod.LikParams(dist_weight=(1, 1, 5))
+    beam = eng_mod.beam_params_from_reference(num_points_default=256, dda_grid_size=0.2)
+    e1, e2 = eng_mod.Engine((0,)), eng_mod.Engine((0, 1))
+    e1.set_map(s["map"], lik, beam)
+    e2.set_map(s["map"], lik, beam)
+    P = s["particles"][:1001]
+    prior = np.random.default_rng(9).uniform(0.1, 1.0, len(P)).astype(np.float32)
+    p1, s1, r1 = e1.measure_update(P, s["lik"], s["beam"], s["origins"], prior, want_records=True)
+    p2, s2, r2 = e2.measure_update(P, s["lik"], s["beam"], s["origins"], prior, want_records=True)
+    assert np.array_equal(r1, r2)
+    assert np.allclose(p1, p2, rtol=1e-6) and s1["kept"] == s2["kept"] == 1
+    assert abs(s1["entropy"] - s2["entropy"]) < 1e-5 and s1["max_index"] == s2["max_index"]
+    assert s1["match_ratio_min"] == s2["match_ratio_min"] and s1["match_ratio_max"] == s2["match_ratio_max"]
+    e1.close()
+    e2.close()
