@@ -549,7 +549,8 @@ int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_
   {
     NnGridDev g{};
     // the window (q -/+ rpad) must span at most 3 cells per axis: cell edge strictly above rpad
-    const float cell = std::max(eng->lik.match_dist_min * eng->nn_cell_factor, eng->likdev.rpad * 1.0005f);
+    // (1 % margin: the float cell function can be off by ~1e-7 x cells-per-axis, and the kernels rely on <= 3)
+    const float cell = std::max(eng->lik.match_dist_min * eng->nn_cell_factor, eng->likdev.rpad * 1.01f);
     if (!(cell > 0.0f))
     {
       cleanup();
@@ -788,26 +789,26 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     c.dev = device_ids ? device_ids[i] : i;
     if (c.dev < 0 || c.dev >= count)
     {
-      delete eng;
+      mcl3dl_destroy(eng);
       return MCL3DL_ERR_NO_DEVICE;
     }
     cudaDeviceProp prop;
     if (cudaSetDevice(c.dev) != cudaSuccess || cudaGetDeviceProperties(&prop, c.dev) != cudaSuccess ||
         prop.major < 10)
     {
-      delete eng;  // built for sm_100a only; anything else cannot run these kernels
+      mcl3dl_destroy(eng);  // built for sm_100a only; anything else cannot run these kernels
       return MCL3DL_ERR_NO_DEVICE;
     }
     c.sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess)
     {
-      delete eng;
+      mcl3dl_destroy(eng);
       return MCL3DL_ERR_CUDA;
     }
     for (auto& e : c.ev)
       if (cudaEventCreate(&e) != cudaSuccess)
       {
-        delete eng;
+        mcl3dl_destroy(eng);
         return MCL3DL_ERR_CUDA;
       }
     if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -815,7 +816,7 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
         cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&c.ev_b0) != cudaSuccess || cudaEventCreate(&c.ev_b1) != cudaSuccess)
     {
-      delete eng;
+      mcl3dl_destroy(eng);
       return MCL3DL_ERR_CUDA;
     }
   }

@@ -1030,6 +1030,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
         dst[2] = c;
       }
       __threadfence();
+      __syncwarp();  // every lane's partial is fenced before lane 0 takes the ticket
       if (lane == 0)
         s_ticket = atomicAdd(tickets + group, 1u);
       __syncwarp();
