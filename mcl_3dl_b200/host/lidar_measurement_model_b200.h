@@ -110,6 +110,36 @@ public:
     callEngine(&single_pose_, 1, origins, &single_result_);
     return single_result_;
   }
+  // Scope row f2: the whole pf_->measure(measure_func) of src/mcl_3dl.cpp:402-426 in one engine call.
+  // prior[i] = particle i's probability_, extra[i] = the host-owned factor of the lambda (the odometry-error
+  // pdf, :422-424); posterior receives the normalised weights (or the prior when nothing survives).
+  void measureUpdate(ChunkedKdtree<PointType>::Ptr& kdtree, const Cloud::ConstPtr& pc_lik, const Cloud::ConstPtr& pc_beam,
+                     const std::vector<Vec3>& origins, const std::vector<float>& prior, const std::vector<float>& extra,
+                     std::vector<float>& posterior, mcl3dl_update_summary* summary)
+  {
+    lik_cloud_ = pc_lik;
+    beam_cloud_ = pc_beam;
+    valid_ = false;
+    stageMap(kdtree);
+    if (!staged_map_)
+      stageMap(kdtree);
+    pack(lik_cloud_, lik_pts_);
+    pack(beam_cloud_, beam_pts_);
+    poses_.clear();
+    for (auto it = pf_->begin(); it != pf_->end(); ++it) poses_.push_back(toPose(it->state_));
+    posterior.assign(poses_.size(), 0.0f);
+    std::vector<float> o(origins.size() * 3);
+    for (size_t k = 0; k < origins.size(); ++k)
+    {
+      o[3 * k] = origins[k].x_;
+      o[3 * k + 1] = origins[k].y_;
+      o[3 * k + 2] = origins[k].z_;
+    }
+    check(mcl3dl_measure_update(engine_, poses_.data(), poses_.size(), lik_pts_.data(), lik_pts_.size(), beam_pts_.data(),
+                                beam_pts_.size(), o.data(), origins.size(), prior.data(),
+                                extra.empty() ? nullptr : extra.data(), posterior.data(), nullptr, summary),
+          "mcl3dl_measure_update");
+  }
   size_t likPoints() const { return lik_cloud_ ? lik_cloud_->size() : 0; }
   mcl3dl_engine* engine() { return engine_; }
 
@@ -312,6 +342,47 @@ public:
 
 private:
   MeasurementBatcher::Ptr batcher_;
+};
+
+// Optional deeper integration (scope row f2).  The node's particle filter with one extra method that replaces
+//   pf_->measure(measure_func);                                   (src/mcl_3dl.cpp:426)
+// by a single fused engine call: measurement of every particle, multiplication into probability_, normalisation,
+// entropy and the match-ratio extremes the lambda tracks (:416-419).  Construct the node's pf_ as this class
+// (:1272-1275) and call measureBatched() instead of measure(); everything else of pf::ParticleFilter is inherited.
+class ParticleFilterB200 : public ParticleFilter
+{
+public:
+  using ParticleFilter::ParticleFilter;
+
+  struct UpdateResult
+  {
+    float match_ratio_min, match_ratio_max;
+    bool kept;  // false: every weight was zero and the particles were left untouched (pf.h:274-278)
+  };
+
+  // extra(const State6DOF&) -> float: the part of the lambda the host owns (odom_error_lin_nd(...), :422-424)
+  template <typename EXTRA>
+  UpdateResult measureBatched(MeasurementBatcher& batcher, ChunkedKdtree<PointType>::Ptr& kdtree,
+                              const Cloud::ConstPtr& pc_likelihood, const Cloud::ConstPtr& pc_beam,
+                              const std::vector<Vec3>& origins, EXTRA extra)
+  {
+    std::vector<float> prior, factor, posterior;
+    prior.reserve(particles_.size());
+    factor.reserve(particles_.size());
+    for (const auto& p : particles_)
+    {
+      prior.push_back(p.probability_);
+      factor.push_back(extra(p.state_));
+    }
+    mcl3dl_update_summary s;
+    batcher.measureUpdate(kdtree, pc_likelihood, pc_beam, origins, prior, factor, posterior, &s);
+    if (s.kept)
+    {
+      for (size_t i = 0; i < particles_.size(); ++i) particles_[i].probability_ = posterior[i];
+      entropy_ = s.entropy;
+    }
+    return UpdateResult{s.match_ratio_min, s.match_ratio_max, s.kept != 0};
+  }
 };
 
 }  // namespace mcl_3dl_b200

@@ -228,6 +228,70 @@ int main(int argc, char** argv)
     ig = pf_gpu.begin();
     for (; ir != pf_ref.end(); ++ir, ++ig) *ig = *ir;
   }
+  // scope row f2: the fused pf update behind ParticleFilterB200::measureBatched vs pf.measure(lambda with the
+  // odometry-error term) of the reference (src/mcl_3dl.cpp:402-426)
+  {
+    mcl_3dl_b200::ParticleFilterB200 pf_fused(n_particles, 7);
+    pf_fused.init(mean, sigma);
+    auto ir = pf_ref.begin();
+    auto ig = pf_fused.begin();
+    std::uniform_real_distribution<float> uw(0.2f, 1.0f);
+    for (; ir != pf_ref.end(); ++ir, ++ig)
+    {
+      *ig = *ir;
+      ig->probability_ = ir->probability_ = uw(rng);
+      ig->state_.odom_err_integ_lin_ = ir->state_.odom_err_integ_lin_ = Vec3(0.02f * n01(rng), 0.02f * n01(rng), 0.f);
+    }
+    const float sigma_odom = 0.05f;
+    const auto odom_term = [sigma_odom](const State6DOF& s) -> float
+    {
+      // NormalLikelihood<float>(sigma)(x), include/mcl_3dl/nd.h:45-53
+      const float a = 1.0 / std::sqrt(2.0 * M_PI * sigma_odom * sigma_odom);
+      const float sq2 = sigma_odom * sigma_odom * 2.0;
+      const float x = s.odom_err_integ_lin_.norm();
+      return a * expf(-x * x / sq2);
+    };
+    std::map<std::string, Cloud::Ptr> pc_locals;
+    for (const auto& lm : ref.lm)
+    {
+      lm.second->setGlobalLocalizationStatus(n_particles, pf_ref.getParticleSize());
+      pc_locals[lm.first] = lm.second->filter(scan, sampler);
+    }
+    float rmin = 1.0, rmax = 0.0;
+    pf_ref.measure([&](const State6DOF& s) -> float
+    {
+      float likelihood = 1;
+      std::map<std::string, float> qualities;
+      for (const auto& lm : ref.lm)
+      {
+        const LidarMeasurementResult result = lm.second->measure(kdtree, pc_locals[lm.first], origins, s);
+        likelihood *= result.likelihood;
+        qualities[lm.first] = result.quality;
+      }
+      if (rmin > qualities["likelihood"]) rmin = qualities["likelihood"];
+      if (rmax < qualities["likelihood"]) rmax = qualities["likelihood"];
+      return likelihood * odom_term(s);
+    });
+    auto batcher2 = std::make_shared<mcl_3dl_b200::MeasurementBatcher>(&pf_fused, std::vector<int>{0}, lik_params, beam_params,
+                                                                      dist_weight);
+    const auto res = pf_fused.measureBatched(*batcher2, kdtree, pc_locals["likelihood"], pc_locals["beam"], origins, odom_term);
+    EXPECT(res.kept, "fused update kept");
+    EXPECT(res.match_ratio_min == rmin && res.match_ratio_max == rmax, "fused match ratio %g/%g vs %g/%g", res.match_ratio_min,
+           res.match_ratio_max, rmin, rmax);
+    ir = pf_ref.begin();
+    ig = pf_fused.begin();
+    double worst = 0;
+    for (; ir != pf_ref.end(); ++ir, ++ig)
+    {
+      const double rel = std::fabs(ir->probability_ - ig->probability_) / std::max(1e-12, static_cast<double>(ir->probability_));
+      worst = std::max(worst, rel);
+      EXPECT(rel <= 1e-4, "fused posterior %g vs %g", ir->probability_, ig->probability_);
+    }
+    EXPECT(std::fabs(pf_ref.getEntropy() - pf_fused.getEntropy()) <= 1e-4 * std::fabs(pf_ref.getEntropy()) + 1e-6,
+           "fused entropy %g vs %g", pf_ref.getEntropy(), pf_fused.getEntropy());
+    std::printf("fused update: worst relative posterior diff %.3g, entropy %g vs %g\n", worst, pf_ref.getEntropy(),
+                pf_fused.getEntropy());
+  }
   // a state that is not a particle (mean pose): served by a one-particle engine call
   {
     const State6DOF e = pf_ref.expectation(1.0);
