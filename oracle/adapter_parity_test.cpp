@@ -295,6 +295,8 @@ int main(int argc, char** argv)
   // a state that is not a particle (mean pose): served by a one-particle engine call
   {
     const State6DOF e = pf_ref.expectation(1.0);
+    ref.lm["likelihood"]->setGlobalLocalizationStatus(n_particles, n_particles);
+    gpu.lm["likelihood"]->setGlobalLocalizationStatus(n_particles, n_particles);
     Cloud::Ptr pcl = ref.lm["likelihood"]->filter(scan, sampler);
     Cloud::Ptr pcg = gpu.lm["likelihood"]->filter(scan, sampler);
     const LidarMeasurementResult r1 = ref.lm["likelihood"]->measure(kdtree, pcl, origins, e);
