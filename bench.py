@@ -414,16 +414,19 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
-        n_sample, dt, cpu, meta = cpu_arm(args.workload, s, dda, n_lik, n_beam, args.cpu_seconds, 1)
-        meta["value"] = n_sample * unit_pts / dt
-        meta["unit"] = "evals/s"
-        # parity spot check of this very workload against the checker (first particles of rank 0)
-        cpu.set_tally(True)
-        chk = cpu.measure(particles[:16], s["lik"], s["beam"], s["origins"])
-        ok = all(np.array_equal(chk[f], out_host[:16][f]) for f in ("match_cnt", "n_short", "n_hit", "n_long"))
-        ok = ok and np.allclose(chk["score_like"], out_host[:16]["score_like"], rtol=1e-4, atol=1e-6)
-        meta["parity_spot_check"] = bool(ok)
-        cpu_baseline = meta
+        try:
+            n_sample, dt, cpu, meta = cpu_arm(args.workload, s, dda, n_lik, n_beam, args.cpu_seconds, 1)
+            meta["value"] = n_sample * unit_pts / dt
+            meta["unit"] = "evals/s"
+            # parity spot check of this very workload against the checker (first particles of rank 0)
+            cpu.set_tally(True)
+            chk = cpu.measure(particles[:16], s["lik"], s["beam"], s["origins"])
+            ok = all(np.array_equal(chk[f], out_host[:16][f]) for f in ("match_cnt", "n_short", "n_hit", "n_long"))
+            ok = ok and np.allclose(chk["score_like"], out_host[:16]["score_like"], rtol=1e-4, atol=1e-6)
+            meta["parity_spot_check"] = bool(ok)
+            cpu_baseline = meta
+        except Exception as exc:  # the GPU line must still be printed if the checker cannot be built / loaded
+            cpu_baseline = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     if rank == 0:
         line = {"metric": metric_name(n_lik), "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
