@@ -197,6 +197,7 @@ struct DeviceCtx
   DevBuf d_w, d_post, d_wpart;   // fused weight update: w_i, posterior, per-CTA partials
   DevBuf d_partial, d_tickets;  // lane-per-particle kernels: per-CTA partials + per-group ticket counters
   size_t tickets_zeroed = 0;
+  std::vector<const void*> smem_opted;  // kernels already opted in to large dynamic shared memory on this device
   DevBuf d_stats;            // 5 x uint64 work counters, only written while stats collection is on
   bool stats_on = false;
   unsigned long long* stats_ptr() const { return stats_on ? static_cast<unsigned long long*>(d_stats.p) : nullptr; }
@@ -280,6 +281,21 @@ int pick_tpp(size_t P, size_t N, int sm_count)
   return tpp;
 }
 
+// cudaFuncSetAttribute is a driver call: opt each kernel instantiation in to the large dynamic shared memory
+// size once per device instead of on every launch.
+template <typename K>
+int opt_in_smem(mcl3dl_engine* eng, DeviceCtx& c, K kernel, int bytes)
+{
+  // keyed by the kernel's address: instantiations with the same signature share one function-pointer type
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (const void* k : c.smem_opted)
+    if (k == key)
+      return MCL3DL_OK;
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  c.smem_opted.push_back(key);
+  return MCL3DL_OK;
+}
+
 template <int TPP>
 int launch_lik_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int P, const float4* scan, int N,
                  mcl3dl_result* out, int beam_defaults, cudaStream_t st)
@@ -292,7 +308,7 @@ int launch_lik_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int
   {
     if (bytes <= static_cast<size_t>(kMaxStagedSorted))
     {
-      CK(cudaFuncSetAttribute(lik_kernel_wi<TPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStagedSorted));
+      if (int rc = opt_in_smem(eng, c, lik_kernel_wi<TPP, true>, kMaxStagedSorted)) return rc;
       lik_kernel_wi<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
     }
     else
@@ -302,7 +318,7 @@ int launch_lik_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int
   }
   else if (bytes <= static_cast<size_t>(kMaxStagedBytes))
   {
-    CK(cudaFuncSetAttribute(lik_kernel<TPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStagedBytes));
+    if (int rc = opt_in_smem(eng, c, lik_kernel<TPP, true>, kMaxStagedBytes)) return rc;
     lik_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
   }
   else
@@ -324,7 +340,7 @@ int launch_beam_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, in
   const size_t bytes = static_cast<size_t>(N) * 16;
   if (bytes <= static_cast<size_t>(kMaxStagedBytes))
   {
-    CK(cudaFuncSetAttribute(beam_kernel<TPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStagedBytes));
+    if (int rc = opt_in_smem(eng, c, beam_kernel<TPP, true>, kMaxStagedBytes)) return rc;
     beam_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, origins, c.dda, out, status, lik_defaults, c.stats_ptr());
   }
   else
