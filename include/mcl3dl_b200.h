@@ -166,7 +166,9 @@ int mcl3dl_measure(mcl3dl_engine*, const mcl3dl_pose* poses, size_t n_particles,
 /* Same computation with every buffer already resident on engine device 0 (DEVICE pointers) and
  * the kernels enqueued on the caller's CUDA stream (a cudaStream_t cast to void*, NULL = legacy
  * default stream); asynchronous.  Used by the bench's device-resident arm and by callers that
- * all-gather the records with NCCL before reading them.  Single-device engines only. */
+ * all-gather the records with NCCL before reading them.  Single-device engines only.  d_origins_xyz holds
+ * n_origins packed xyz triplets; beam labels are NOT range-checked here (the buffers live on the device), and the
+ * engine's scratch buffers make concurrent calls on different streams unsupported. */
 int mcl3dl_measure_device(mcl3dl_engine*, const mcl3dl_pose* d_poses, size_t n_particles,
                           const mcl3dl_point* d_lik_pts, size_t n_lik,
                           const mcl3dl_point* d_beam_pts, size_t n_beam,
