@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -103,7 +103,8 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "span": "warm-up, timed steps, ~0.5 s of the same step untimed, roofline and e2e loops (100 ms period)"}
 
 
 def as_u8(a):
@@ -310,6 +311,12 @@ def main():
     l0 = eng.kernel_launches()
     total_ms = timed(step, args.steps)
     launches = eng.kernel_launches() - l0
+    # the timed region lasts a few milliseconds, shorter than one nvidia-smi period: keep the same step running
+    # (untimed, same count on every rank) for ~0.5 s so that the clock record holds samples taken under this load
+    n_extra = int(min(20000, max(0, 500.0 / max(total_ms / args.steps, 1e-3))))
+    for _ in range(n_extra):
+        step()
+    barrier()
 
     unit_pts = n_lik if n_lik else n_beam
     evals_step = world * P_rank * unit_pts
