@@ -149,6 +149,8 @@ class CpuChecker:
         L.mcl3dl_cpu_quat_rotate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcl3dl_cpu_transform_point.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcl3dl_cpu_pf_update.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.mcl3dl_cpu_pf_resample_1d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_float, C.c_void_p,
+                                                C.c_void_p]
 
     def create(self, map_pts, lik=None, beam=None, chunk_length=20.0, max_search_radius=0.4):
         return CpuMap(self, map_pts, lik, beam, chunk_length, max_search_radius)
@@ -198,6 +200,14 @@ class CpuChecker:
         out = np.zeros(3, dtype=np.float32)
         self.lib.mcl3dl_cpu_transform_point(_ptr(pose), _ptr(v), _ptr(out))
         return out
+
+    def pf_resample_1d(self, probs, states, seed, sigma=0.0):
+        probs = np.ascontiguousarray(probs, dtype=np.float32)
+        states = np.ascontiguousarray(states, dtype=np.float32)
+        out_s = np.zeros(len(probs), dtype=np.float32)
+        out_p = np.zeros(len(probs), dtype=np.float32)
+        self.lib.mcl3dl_cpu_pf_resample_1d(_ptr(probs), _ptr(states), len(probs), seed, sigma, _ptr(out_s), _ptr(out_p))
+        return out_s, out_p
 
     def pf_update(self, prob, lik):
         prob = np.array(prob, dtype=np.float32)

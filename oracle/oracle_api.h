@@ -87,6 +87,12 @@ void mcl3dl_cpu_transform_point(const mcl3dl_pose* pose, const float v[3], float
  * prob[i] *= lik[i]; normalise; entropy; returns 1 if sum > 0 else 0 (restore -> prob untouched). */
 int mcl3dl_cpu_pf_update(float* prob, const float* lik, size_t n, float* entropy);
 
+/* pf::ParticleFilter<State1D, float>(n, seed)::resample(State1D(sigma)) (pf.h:182-225) on 1-D states, the fixture
+ * of test/src/test_pf.cpp:186-289: systematic resampling over the sorted cumulative weights, noise only on
+ * duplicates, std::default_random_engine.  Writes the resampled states and probabilities. */
+int mcl3dl_cpu_pf_resample_1d(const float* probs, const float* states, size_t n, unsigned int seed, float sigma,
+                              float* out_states, float* out_probs);
+
 #ifdef __cplusplus
 }
 #endif

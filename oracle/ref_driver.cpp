@@ -417,4 +417,40 @@ int mcl3dl_cpu_pf_update(float* prob, const float* lik, size_t n, float* entropy
   return sum > 0.0 ? 1 : 0;
 }
 
+namespace
+{
+// the 1-D state of test/src/test_pf.cpp:38-76
+class State1D : public mcl_3dl::pf::ParticleBase<float>
+{
+public:
+  float x;
+  float& operator[](const size_t) override { return x; }
+  const float& operator[](const size_t) const { return x; }
+  size_t size() const override { return 1; }
+  explicit State1D(const float v) : x(v) {}
+  State1D() : x(0) {}
+  void normalize() override {}
+};
+}  // namespace
+
+int mcl3dl_cpu_pf_resample_1d(const float* probs, const float* states, size_t n, unsigned int seed, float sigma,
+                              float* out_states, float* out_probs)
+{
+  mcl_3dl::pf::ParticleFilter<State1D, float> pf(static_cast<int>(n), seed);
+  size_t i = 0;
+  for (auto it = pf.begin(); it != pf.end(); ++it, ++i)
+  {
+    it->state_.x = states[i];
+    it->probability_ = probs[i];
+  }
+  pf.resample(State1D(sigma));
+  i = 0;
+  for (auto it = pf.begin(); it != pf.end(); ++it, ++i)
+  {
+    out_states[i] = it->state_.x;
+    out_probs[i] = it->probability_;
+  }
+  return MCL3DL_OK;
+}
+
 }  // extern "C"

@@ -193,6 +193,39 @@ def test_pf_entropy(port):
     assert not kept and np.array_equal(p, prior)
 
 
+# ---------------------------------------------------------------- test_pf.cpp:210-289 (ResampleFirstAndLastParticle)
+@pytest.mark.parametrize("probs,expected", [
+    ([1.0e-6, 0.2, 0.2, 0.2, 0.4 - 1.0e-6], [1.0, 2.0, 3.0, 4.0, 4.0]),
+    ([0.2, 0.2, 0.2, 0.4 - 1.0e-6, 1.0e-6], [0.0, 1.0, 2.0, 3.0, 3.0]),
+])
+def test_pf_resample_known_answers(port, probs, expected):
+    probs = np.array(probs, dtype=np.float64).astype(np.float32)
+    probs[np.argmax(probs)] = np.float32(0.4) - np.float32(1.0e-6)  # `0.4f - small_prob` in float, as the test writes it
+    out_s, out_p = port.pf_resample_1d(probs, [0.0, 1.0, 2.0, 3.0, 4.0], seed=12345)
+    assert np.array_equal(out_s, np.array(expected, dtype=np.float32))
+    assert np.all(out_p == np.float32(1.0 / 5))
+
+
+# test_pf.cpp:190-208 (ResampleFlatLikelihood): equal weights keep every particle where it is
+def test_pf_resample_flat_likelihood_is_identity(port):
+    rng = np.random.default_rng(3)
+    states = (12.3 + 0.45 * rng.normal(size=10)).astype(np.float32)
+    out_s, _ = port.pf_resample_1d(np.full(10, 0.1, np.float32), states, seed=99)
+    assert np.array_equal(out_s, states)
+
+
+def test_pf_resample_port_equals_reference_build(port, reference):
+    rng = np.random.default_rng(17)
+    for n in (2, 5, 64, 1000):
+        for sigma in (0.0, 0.3):
+            probs = rng.random(n).astype(np.float32) ** 4
+            probs[rng.integers(0, n, n // 4)] = 0.0
+            states = rng.normal(size=n).astype(np.float32)
+            a = reference.pf_resample_1d(probs, states, seed=12345 + n, sigma=sigma)
+            b = port.pf_resample_1d(probs, states, seed=12345 + n, sigma=sigma)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
 # ---------------------------------------------------------------- golden fixtures (reference outputs)
 def test_golden_beam_likelihood_world(port):
     g = golden("beam_likelihood_world.npz")
