@@ -355,3 +355,24 @@ def test_multi_device_fused_update_matches_single(eng_mod, big_scene):
     assert s1["match_ratio_min"] == s2["match_ratio_min"] and s1["match_ratio_max"] == s2["match_ratio_max"]
     e1.close()
     e2.close()
+
+
+def test_dense_cloud_overflows_the_window_table(eng_mod, eng, cc):
+    """A raw (not voxel-filtered) cloud: thousands of points per search-grid cell, so the packed per-cell counts of
+    the window table saturate and the kernel has to fall back to the CSR bounds; the DDA cells hold long point lists."""
+    rng = np.random.default_rng(91)
+    pts = rng.uniform(0.0, 1.0, (120_000, 3)).astype(np.float32)
+    pts = np.vstack([pts, [[-0.5, -0.5, -0.5], [1.5, 1.5, 1.5]]]).astype(np.float32)
+    s = {"map": synth.make_points(pts, (rng.random(len(pts)) < 0.3).astype(np.uint32) * 2)}
+    P, n_lik, n_beam = 9, 24, 10
+    s["particles"] = synth.make_poses(rng.uniform(0.3, 0.7, (P, 3)), synth.quat_from_rpy(rng.normal(0, 0.3, (P, 3))))
+    s["lik"] = synth.make_points(rng.uniform(-0.7, 0.7, (n_lik, 3)))
+    s["beam"] = synth.make_points(rng.uniform(-0.6, 0.6, (n_beam, 3)), rng.integers(0, 2, n_beam))
+    s["origins"] = np.array([[0.0, 0.0, 0.05], [0.02, 0.0, 0.0]], np.float32)
+    cpu = run_both(eng_mod, eng, cc, s, (1, 1, 1), n_beam, dda_grid=0.2, flm=1)
+    want = cpu.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+    got = eng.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+    check_records(got, want, n_beam)
+    assert want["match_cnt"].sum() > 0
+    assert np.array_equal(eng.beam_status(s["particles"], s["beam"], s["origins"]),
+                          cpu.beam_status(s["particles"], s["beam"], s["origins"]))
