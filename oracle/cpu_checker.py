@@ -48,6 +48,11 @@ class BeamRaw(C.Structure):
                 ("ray_angle_half", C.c_float), ("dda_grid_size", C.c_float)]
 
 
+MOTION_STATE = np.dtype([("pos", "<f4", 3), ("rot", "<f4", 4), ("noise_ll", "<f4"), ("noise_la", "<f4"),
+                         ("noise_al", "<f4"), ("noise_aa", "<f4"), ("odom_err_integ_lin", "<f4", 3),
+                         ("odom_err_integ_ang", "<f4", 3)])
+
+
 def lik_params(match_weight=5.0, match_dist_min=0.2, match_dist_flat=0.05, dist_weight=(1.0, 1.0, 1.0)):
     """Defaults: include/mcl_3dl/parameters.h:74-76."""
     p = LikParams()
@@ -149,6 +154,8 @@ class CpuChecker:
         L.mcl3dl_cpu_quat_rotate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcl3dl_cpu_transform_point.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcl3dl_cpu_pf_update.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.mcl3dl_cpu_motion_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                                C.c_size_t]
         L.mcl3dl_cpu_pf_resample_1d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_float, C.c_void_p,
                                                 C.c_void_p]
 
@@ -200,6 +207,15 @@ class CpuChecker:
         out = np.zeros(3, dtype=np.float32)
         self.lib.mcl3dl_cpu_transform_point(_ptr(pose), _ptr(v), _ptr(out))
         return out
+
+    def motion_predict(self, odom_prev, odom_current, time_diff, tc_lin, tc_ang, states):
+        """MotionPredictionModelDifferentialDrive::setOdoms + predict on a MOTION_STATE array (returns a copy)."""
+        a = np.ascontiguousarray(odom_prev, dtype=POSE).reshape(1)
+        b = np.ascontiguousarray(odom_current, dtype=POSE).reshape(1)
+        st = np.array(states, dtype=MOTION_STATE)
+        self.lib.mcl3dl_cpu_motion_predict(_ptr(a), _ptr(b), C.c_float(time_diff), C.c_float(tc_lin), C.c_float(tc_ang),
+                                           _ptr(st), len(st))
+        return st
 
     def pf_resample_1d(self, probs, states, seed, sigma=0.0):
         probs = np.ascontiguousarray(probs, dtype=np.float32)

@@ -87,6 +87,20 @@ void mcl3dl_cpu_transform_point(const mcl3dl_pose* pose, const float v[3], float
  * prob[i] *= lik[i]; normalise; entropy; returns 1 if sum > 0 else 0 (restore -> prob untouched). */
 int mcl3dl_cpu_pf_update(float* prob, const float* lik, size_t n, float* entropy);
 
+/* Groundwork for scope row f3 (not on the device yet): MotionPredictionModelDifferentialDrive::setOdoms + predict
+ * (include/mcl_3dl/motion_prediction_models/motion_prediction_model_differential_drive.h:46-67) applied to n states. */
+typedef struct
+{
+  float pos[3];
+  float rot[4]; /* x y z w */
+  float noise_ll, noise_la, noise_al, noise_aa;
+  float odom_err_integ_lin[3];
+  float odom_err_integ_ang[3];
+} mcl3dl_cpu_motion_state; /* 17 floats: the State6DOF fields predict() reads and writes (state_6dof.h:55-63) */
+int mcl3dl_cpu_motion_predict(const mcl3dl_pose* odom_prev, const mcl3dl_pose* odom_current, float time_diff,
+                              float odom_err_integ_lin_tc, float odom_err_integ_ang_tc,
+                              mcl3dl_cpu_motion_state* states, size_t n);
+
 /* pf::ParticleFilter<State1D, float>(n, seed)::resample(State1D(sigma)) (pf.h:182-225) on 1-D states, the fixture
  * of test/src/test_pf.cpp:186-289: systematic resampling over the sorted cumulative weights, noise only on
  * duplicates, std::default_random_engine.  Writes the resampled states and probabilities. */

@@ -20,6 +20,7 @@
 #include <mcl_3dl/chunked_kdtree.h>
 #include <mcl_3dl/lidar_measurement_models/lidar_measurement_model_beam.h>
 #include <mcl_3dl/lidar_measurement_models/lidar_measurement_model_likelihood.h>
+#include <mcl_3dl/motion_prediction_models/motion_prediction_model_differential_drive.h>
 #include <mcl_3dl/parameters.h>
 #include <mcl_3dl/pf.h>
 #include <mcl_3dl/point_types.h>
@@ -415,6 +416,39 @@ int mcl3dl_cpu_pf_update(float* prob, const float* lik, size_t n, float* entropy
     prob[i] = it->probability_;
   if (entropy) *entropy = pf.getEntropy();
   return sum > 0.0 ? 1 : 0;
+}
+
+int mcl3dl_cpu_motion_predict(const mcl3dl_pose* a, const mcl3dl_pose* b, float time_diff, float tc_lin, float tc_ang,
+                              mcl3dl_cpu_motion_state* st, size_t n)
+{
+  mcl_3dl::MotionPredictionModelDifferentialDrive model(tc_lin, tc_ang);
+  const State6DOF prev(Vec3(a->px, a->py, a->pz), Quat(a->qx, a->qy, a->qz, a->qw));
+  const State6DOF cur(Vec3(b->px, b->py, b->pz), Quat(b->qx, b->qy, b->qz, b->qw));
+  model.setOdoms(prev, cur, time_diff);
+  for (size_t i = 0; i < n; ++i)
+  {
+    State6DOF s(Vec3(st[i].pos[0], st[i].pos[1], st[i].pos[2]), Quat(st[i].rot[0], st[i].rot[1], st[i].rot[2], st[i].rot[3]));
+    s.noise_ll_ = st[i].noise_ll;
+    s.noise_la_ = st[i].noise_la;
+    s.noise_al_ = st[i].noise_al;
+    s.noise_aa_ = st[i].noise_aa;
+    s.odom_err_integ_lin_ = Vec3(st[i].odom_err_integ_lin[0], st[i].odom_err_integ_lin[1], st[i].odom_err_integ_lin[2]);
+    s.odom_err_integ_ang_ = Vec3(st[i].odom_err_integ_ang[0], st[i].odom_err_integ_ang[1], st[i].odom_err_integ_ang[2]);
+    model.predict(s);
+    st[i].pos[0] = s.pos_.x_;
+    st[i].pos[1] = s.pos_.y_;
+    st[i].pos[2] = s.pos_.z_;
+    st[i].rot[0] = s.rot_.x_;
+    st[i].rot[1] = s.rot_.y_;
+    st[i].rot[2] = s.rot_.z_;
+    st[i].rot[3] = s.rot_.w_;
+    for (int k = 0; k < 3; ++k)
+    {
+      st[i].odom_err_integ_lin[k] = s.odom_err_integ_lin_[k];
+      st[i].odom_err_integ_ang[k] = s.odom_err_integ_ang_[k];
+    }
+  }
+  return MCL3DL_OK;
 }
 
 namespace

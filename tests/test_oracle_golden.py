@@ -226,6 +226,33 @@ def test_pf_resample_port_equals_reference_build(port, reference):
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
+# ---------------------------------------------------------------- groundwork for scope row f3 (motion prediction)
+def test_motion_prediction_port_equals_reference_build(port, reference):
+    rng = np.random.default_rng(23)
+    for trial in range(20):
+        def pose():
+            q = rng.normal(size=4)
+            q /= np.linalg.norm(q)
+            return cc.poses([rng.uniform(-5, 5, 3)], [q])[0]
+        a, b = pose(), pose()
+        if trial % 4 == 0:
+            b = a.copy()  # no rotation: the |w| >= 1 - 1e-6 branch of getAxisAng (quat.h:224-229)
+            b["px"] += np.float32(0.3)
+        st = np.zeros(64, dtype=cc.MOTION_STATE)
+        st["pos"] = rng.uniform(-10, 10, (64, 3))
+        q = rng.normal(size=(64, 4))
+        st["rot"] = q / np.linalg.norm(q, axis=1, keepdims=True)
+        for f in ("noise_ll", "noise_la", "noise_al", "noise_aa"):
+            st[f] = rng.normal(0, 0.05, 64)
+        st["odom_err_integ_lin"] = rng.normal(0, 0.02, (64, 3))
+        st["odom_err_integ_ang"] = rng.normal(0, 0.02, (64, 3))
+        ra = reference.motion_predict(a, b, 0.05, 10.0, 10.0, st)
+        rb = port.motion_predict(a, b, 0.05, 10.0, 10.0, st)
+        for f in cc.MOTION_STATE.names:
+            assert np.array_equal(ra[f], rb[f]), (trial, f)
+        assert not np.array_equal(ra["pos"], st["pos"])
+
+
 # ---------------------------------------------------------------- golden fixtures (reference outputs)
 def test_golden_beam_likelihood_world(port):
     g = golden("beam_likelihood_world.npz")
