@@ -154,6 +154,9 @@ class CpuChecker:
         L.mcl3dl_cpu_quat_rotate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcl3dl_cpu_transform_point.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcl3dl_cpu_pf_update.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.mcl3dl_cpu_filter_clip.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        L.mcl3dl_cpu_global_localization_points.argtypes = [C.c_size_t] * 4
+        L.mcl3dl_cpu_global_localization_points.restype = C.c_size_t
         L.mcl3dl_cpu_motion_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p,
                                                 C.c_size_t]
         L.mcl3dl_cpu_pf_resample_1d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_float, C.c_void_p,
@@ -207,6 +210,16 @@ class CpuChecker:
         out = np.zeros(3, dtype=np.float32)
         self.lib.mcl3dl_cpu_transform_point(_ptr(pose), _ptr(v), _ptr(out))
         return out
+
+    def filter_clip(self, pts, clip_near=0.5, clip_far=10.0, clip_z_min=-2.0, clip_z_max=2.0):
+        pts = np.ascontiguousarray(pts, dtype=POINT)
+        keep = np.zeros(len(pts), dtype=np.uint8)
+        self.lib.mcl3dl_cpu_filter_clip(_ptr(pts), len(pts), clip_near, clip_far, clip_z_min, clip_z_max, _ptr(keep))
+        return keep.astype(bool)
+
+    def global_localization_points(self, num_points_default, num_points_global, num_particles, current):
+        return int(self.lib.mcl3dl_cpu_global_localization_points(num_points_default, num_points_global, num_particles,
+                                                                  current))
 
     def motion_predict(self, odom_prev, odom_current, time_diff, tc_lin, tc_ang, states):
         """MotionPredictionModelDifferentialDrive::setOdoms + predict on a MOTION_STATE array (returns a copy)."""

@@ -101,6 +101,15 @@ int mcl3dl_cpu_motion_predict(const mcl3dl_pose* odom_prev, const mcl3dl_pose* o
                               float odom_err_integ_lin_tc, float odom_err_integ_ang_tc,
                               mcl3dl_cpu_motion_state* states, size_t n);
 
+/* Groundwork for scope row f4: the models' filter() without the sampler (identical code in both models,
+ * src/lidar_measurement_model_likelihood.cpp:79-103 / _beam.cpp:98-122): keep[i] = 1 if point i survives the clip by
+ * planar range and z window.  num_points_after = the sample size setGlobalLocalizationStatus (:63-77) would request
+ * for (num_points_default, num_points_global, num_particles, current_num_particles). */
+int mcl3dl_cpu_filter_clip(const mcl3dl_point* pts, size_t n, float clip_near, float clip_far, float clip_z_min,
+                           float clip_z_max, uint8_t* keep);
+size_t mcl3dl_cpu_global_localization_points(size_t num_points_default, size_t num_points_global, size_t num_particles,
+                                             size_t current_num_particles);
+
 /* pf::ParticleFilter<State1D, float>(n, seed)::resample(State1D(sigma)) (pf.h:182-225) on 1-D states, the fixture
  * of test/src/test_pf.cpp:186-289: systematic resampling over the sorted cumulative weights, noise only on
  * duplicates, std::default_random_engine.  Writes the resampled states and probabilities. */

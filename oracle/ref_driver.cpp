@@ -418,6 +418,57 @@ int mcl3dl_cpu_pf_update(float* prob, const float* lik, size_t n, float* entropy
   return sum > 0.0 ? 1 : 0;
 }
 
+namespace
+{
+// pass-through sampler that reports how many points it was asked for (DummySampler of test_beam_likelihood.cpp:47-76)
+class RecordingSampler : public mcl_3dl::PointCloudRandomSampler<PointType>
+{
+public:
+  mutable size_t asked = 0;
+  Cloud::Ptr sample(const Cloud::ConstPtr& pc, const size_t num) const final
+  {
+    asked = num;
+    Cloud::Ptr out(new Cloud);
+    *out = *pc;
+    return out;
+  }
+};
+}  // namespace
+
+int mcl3dl_cpu_filter_clip(const mcl3dl_point* pts, size_t n, float clip_near, float clip_far, float clip_z_min,
+                           float clip_z_max, uint8_t* keep)
+{
+  auto params = std::make_shared<mcl_3dl::LidarMeasurementModelLikelihoodParameters>();
+  params->clip_near_ = clip_near;
+  params->clip_far_ = clip_far;
+  params->clip_z_min_ = clip_z_min;
+  params->clip_z_max_ = clip_z_max;
+  LidarMeasurementModelLikelihood model(params);
+  Cloud::Ptr pc = toCloud(pts, n);
+  for (size_t i = 0; i < n; ++i) pc->points[i].intensity = static_cast<float>(i);  // tag to recover the survivors
+  RecordingSampler sampler;
+  const Cloud::Ptr out = model.filter(pc, sampler);
+  std::memset(keep, 0, n);
+  for (const auto& p : out->points) keep[static_cast<size_t>(p.intensity)] = 1;
+  return MCL3DL_OK;
+}
+
+size_t mcl3dl_cpu_global_localization_points(size_t num_points_default, size_t num_points_global, size_t num_particles,
+                                             size_t current_num_particles)
+{
+  auto params = std::make_shared<mcl_3dl::LidarMeasurementModelLikelihoodParameters>();
+  params->num_points_default_ = num_points_default;
+  params->num_points_global_ = num_points_global;
+  LidarMeasurementModelLikelihood model(params);
+  model.setGlobalLocalizationStatus(num_particles, current_num_particles);
+  Cloud::Ptr pc(new Cloud);
+  pc->push_back(PointType());
+  pc->points[0].x = 1.0f;
+  RecordingSampler sampler;
+  model.filter(pc, sampler);
+  return sampler.asked;
+}
+
 int mcl3dl_cpu_motion_predict(const mcl3dl_pose* a, const mcl3dl_pose* b, float time_diff, float tc_lin, float tc_ang,
                               mcl3dl_cpu_motion_state* st, size_t n)
 {

@@ -253,6 +253,24 @@ def test_motion_prediction_port_equals_reference_build(port, reference):
         assert not np.array_equal(ra["pos"], st["pos"])
 
 
+# ---------------------------------------------------------------- groundwork for scope row f4 (scan filtering)
+def test_filter_clip_and_point_budget_port_equals_reference_build(port, reference):
+    rng = np.random.default_rng(29)
+    pts = cc.points(rng.uniform(-12, 12, (5000, 3)) * np.array([1, 1, 0.3]))
+    # points exactly on the clip boundaries (the comparisons are strict, likelihood.cpp:85-90)
+    pts["x"][:4], pts["y"][:4], pts["z"][:4] = [0.5, 10.0, 3.0, 3.0], 0.0, [0.0, 0.0, 2.0, -2.0]
+    for args in ((0.5, 10.0, -2.0, 2.0), (0.5, 4.0, -2.0, 2.0), (1.0, 6.5, -0.3, 4.1)):
+        ka, kb = reference.filter_clip(pts, *args), port.filter_clip(pts, *args)
+        assert np.array_equal(ka, kb) and 0 < kb.sum() < len(pts)
+    assert port.filter_clip(pts)[:4].all()  # boundary points are kept
+    # the test of test_beam_likelihood.cpp:140-146: z = +-5 is clipped with clip_z = (-0.3, 4.1)
+    two = cc.points([[0, 0, 5.0], [0, 0, -5.0], [2, 0, 0.0]])
+    assert list(port.filter_clip(two, 0.5, 4.0, -0.3, 4.1)) == [False, False, True]
+    for d, g, n, cur in ((96, 8, 64, 64), (96, 8, 64, 65), (96, 8, 64, 768), (96, 8, 64, 100000), (3, 0, 64, 1000)):
+        assert reference.global_localization_points(d, g, n, cur) == port.global_localization_points(d, g, n, cur)
+    assert port.global_localization_points(96, 8, 64, 768) == 8 and port.global_localization_points(96, 8, 64, 128) == 48
+
+
 # ---------------------------------------------------------------- golden fixtures (reference outputs)
 def test_golden_beam_likelihood_world(port):
     g = golden("beam_likelihood_world.npz")
