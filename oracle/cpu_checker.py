@@ -159,6 +159,8 @@ class CpuChecker:
         L.mcl3dl_cpu_global_localization_points.restype = C.c_size_t
         L.mcl3dl_cpu_motion_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p,
                                                 C.c_size_t]
+        L.mcl3dl_cpu_pf_resample_6dof.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p]
         L.mcl3dl_cpu_pf_resample_1d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_float, C.c_void_p,
                                                 C.c_void_p]
 
@@ -237,6 +239,17 @@ class CpuChecker:
         out_p = np.zeros(len(probs), dtype=np.float32)
         self.lib.mcl3dl_cpu_pf_resample_1d(_ptr(probs), _ptr(states), len(probs), seed, sigma, _ptr(out_s), _ptr(out_p))
         return out_s, out_p
+
+    def pf_resample_6dof(self, probs, states, seed, sigma_pos, sigma_rpy):
+        probs = np.ascontiguousarray(probs, dtype=np.float32)
+        states = np.ascontiguousarray(states, dtype=MOTION_STATE)
+        sp = np.asarray(sigma_pos, dtype=np.float32)
+        sr = np.asarray(sigma_rpy, dtype=np.float32)
+        out = np.zeros(len(probs), dtype=MOTION_STATE)
+        out_p = np.zeros(len(probs), dtype=np.float32)
+        self.lib.mcl3dl_cpu_pf_resample_6dof(_ptr(probs), _ptr(states), len(probs), seed, _ptr(sp), _ptr(sr), _ptr(out),
+                                             _ptr(out_p))
+        return out, out_p
 
     def pf_update(self, prob, lik):
         prob = np.array(prob, dtype=np.float32)

@@ -116,6 +116,14 @@ size_t mcl3dl_cpu_global_localization_points(size_t num_points_default, size_t n
 int mcl3dl_cpu_pf_resample_1d(const float* probs, const float* states, size_t n, unsigned int seed, float sigma,
                               float* out_states, float* out_probs);
 
+/* pf::ParticleFilter<State6DOF, float, ParticleWeightedMeanQuat, std::default_random_engine>(n, seed)
+ *   ::resample(State6DOF(sigma_pos, sigma_rpy))   (pf.h:182-225 with State6DOF::generateNoise / operator+,
+ * state_6dof.h:226-261): what the node runs after every measurement (src/mcl_3dl.cpp:809-815).  In/out: the
+ * 17-float states above (duplicates come back with noise_* = 0, as `ret` is a fresh State6DOF) and probabilities. */
+int mcl3dl_cpu_pf_resample_6dof(const float* probs, const mcl3dl_cpu_motion_state* states, size_t n, unsigned int seed,
+                                const float sigma_pos[3], const float sigma_rpy[3], mcl3dl_cpu_motion_state* out_states,
+                                float* out_probs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -538,4 +538,48 @@ int mcl3dl_cpu_pf_resample_1d(const float* probs, const float* states, size_t n,
   return MCL3DL_OK;
 }
 
+int mcl3dl_cpu_pf_resample_6dof(const float* probs, const mcl3dl_cpu_motion_state* st, size_t n, unsigned int seed,
+                                const float sp[3], const float sr[3], mcl3dl_cpu_motion_state* out, float* out_probs)
+{
+  mcl_3dl::pf::ParticleFilter<State6DOF, float, mcl_3dl::ParticleWeightedMeanQuat, std::default_random_engine> pf(
+      static_cast<int>(n), seed);
+  size_t i = 0;
+  for (auto it = pf.begin(); it != pf.end(); ++it, ++i)
+  {
+    State6DOF s(Vec3(st[i].pos[0], st[i].pos[1], st[i].pos[2]), Quat(st[i].rot[0], st[i].rot[1], st[i].rot[2], st[i].rot[3]));
+    s.noise_ll_ = st[i].noise_ll;
+    s.noise_la_ = st[i].noise_la;
+    s.noise_al_ = st[i].noise_al;
+    s.noise_aa_ = st[i].noise_aa;
+    s.odom_err_integ_lin_ = Vec3(st[i].odom_err_integ_lin[0], st[i].odom_err_integ_lin[1], st[i].odom_err_integ_lin[2]);
+    s.odom_err_integ_ang_ = Vec3(st[i].odom_err_integ_ang[0], st[i].odom_err_integ_ang[1], st[i].odom_err_integ_ang[2]);
+    it->state_ = s;
+    it->probability_ = probs[i];
+  }
+  pf.resample(State6DOF(Vec3(sp[0], sp[1], sp[2]), Vec3(sr[0], sr[1], sr[2])));
+  i = 0;
+  for (auto it = pf.begin(); it != pf.end(); ++it, ++i)
+  {
+    const State6DOF& s = it->state_;
+    out[i].pos[0] = s.pos_.x_;
+    out[i].pos[1] = s.pos_.y_;
+    out[i].pos[2] = s.pos_.z_;
+    out[i].rot[0] = s.rot_.x_;
+    out[i].rot[1] = s.rot_.y_;
+    out[i].rot[2] = s.rot_.z_;
+    out[i].rot[3] = s.rot_.w_;
+    out[i].noise_ll = s.noise_ll_;
+    out[i].noise_la = s.noise_la_;
+    out[i].noise_al = s.noise_al_;
+    out[i].noise_aa = s.noise_aa_;
+    for (int k = 0; k < 3; ++k)
+    {
+      out[i].odom_err_integ_lin[k] = s.odom_err_integ_lin_[k];
+      out[i].odom_err_integ_ang[k] = s.odom_err_integ_ang_[k];
+    }
+    out_probs[i] = it->probability_;
+  }
+  return MCL3DL_OK;
+}
+
 }  // extern "C"

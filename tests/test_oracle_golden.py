@@ -253,6 +253,30 @@ def test_motion_prediction_port_equals_reference_build(port, reference):
         assert not np.array_equal(ra["pos"], st["pos"])
 
 
+def test_state6dof_resample_port_equals_reference_build(port, reference):
+    """The node's resample call (src/mcl_3dl.cpp:809-815) on State6DOF particles: duplicates get position /
+    rpy noise through State6DOF::generateNoise and operator+ (state_6dof.h:226-261)."""
+    rng = np.random.default_rng(31)
+    for n, sp, sr in ((8, (0.05, 0.05, 0.0), (0.0, 0.0, 0.02)), (300, (0.05, 0.05, 0.05), (0.05, 0.05, 0.05)),
+                      (64, (0, 0, 0), (0, 0, 0))):
+        st = np.zeros(n, dtype=cc.MOTION_STATE)
+        st["pos"] = rng.uniform(-10, 10, (n, 3))
+        q = rng.normal(size=(n, 4))
+        st["rot"] = q / np.linalg.norm(q, axis=1, keepdims=True)
+        for f in ("noise_ll", "noise_la", "noise_al", "noise_aa"):
+            st[f] = rng.normal(0, 0.05, n)
+        st["odom_err_integ_lin"] = rng.normal(0, 0.02, (n, 3))
+        st["odom_err_integ_ang"] = rng.normal(0, 0.02, (n, 3))
+        probs = (rng.random(n) ** 6).astype(np.float32)   # a few heavy particles -> many duplicates
+        a = reference.pf_resample_6dof(probs, st, 4242 + n, sp, sr)
+        b = port.pf_resample_6dof(probs, st, 4242 + n, sp, sr)
+        for f in cc.MOTION_STATE.names:
+            assert np.array_equal(a[0][f], b[0][f]), (n, f)
+        assert np.array_equal(a[1], b[1])
+        if any(sp) or any(sr):
+            assert (b[0]["noise_ll"] == 0).sum() > 0   # duplicates lose their odometry-noise draw
+
+
 # ---------------------------------------------------------------- groundwork for scope row f4 (scan filtering)
 def test_filter_clip_and_point_budget_port_equals_reference_build(port, reference):
     rng = np.random.default_rng(29)
