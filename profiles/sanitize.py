@@ -3,7 +3,6 @@
 import os
 import sys
 
-import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mcl_3dl_b200 import engine, synth  # noqa: E402

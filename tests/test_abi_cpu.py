@@ -4,7 +4,6 @@ include/mcl3dl_b200.h declares, derives the beam parameters like the reference, 
 import os
 import re
 
-import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
