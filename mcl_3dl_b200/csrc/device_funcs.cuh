@@ -1,0 +1,392 @@
+// device_funcs.cuh — the per-thread device functions of the measurement update (no warp or CTA cooperation):
+// grid descriptors, the exact 1-NN searches, the DDA and KD-tree ray casts.  Kept free of anything but scalar
+// intrinsics so that tests/hostsim can compile this very file for the host (with tests/hostsim/cuda_shim.h) and
+// check every function against the oracle without a GPU.  The kernels that call them live in kernels.cuh.
+#pragma once
+#ifndef MCL3DL_HOSTSIM
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+#include "device_math.cuh"
+
+namespace mcl3dl
+{
+// ---- likelihood search grid: cubic cells over the RESCALED map points (p * dist_weight), CSR of
+// cell -> contiguous run in `pts` (x fastest, so an x-row of cells is one contiguous run).
+struct NnGridDev
+{
+  const uint32_t* cell_start;  // [nx*ny*nz + 1]
+  const float4* pts;           // rescaled xyz, w = original map index (bits)
+  // Window table for the likelihood kernel: entry (x, y, z) at ((z*nx + x)*nyp + y) = {start of cell (x,y,z),
+  // packed point counts of the 1 / 2 / 3 cells starting there along x (10 | 11 | 11 bits, all-ones = overflow)}.
+  // y is the fastest index, so the three y-rows of a query window are adjacent and one eval fetches its whole
+  // 3x3 window with 6 aligned 16-byte loads instead of 18 scattered 4-byte ones (L1 wavefronts).
+  const uint2* row3;
+  int nyp;  // padded (even) y pitch of row3
+  int nx, ny, nz;
+  float ox, oy, oz;  // grid origin in the rescaled space
+  float inv_cell;
+  float wx, wy, wz;  // dist_weight
+};
+
+struct LikDev
+{
+  float match_dist_min;   // R
+  float match_dist_flat;  // F
+  float match_weight;     // W
+  float r2;               // float(double(R)*double(R)): what pcl::KdTreeFLANN::radiusSearch hands to FLANN
+  float rpad;             // window half-width, R plus a rounding guard
+};
+
+// ---- DDA grid: exactly RaycastUsingDDA's lattice (min_p_, dda_grid_size_, map_size_), occupancy as
+// one bit per cell + CSR of per-cell points in map order.
+struct DdaGridDev
+{
+  const uint32_t* occ;         // bit c of word c>>5
+  const uint32_t* cell_start;  // [cells + 1]
+  const float4* pts;           // raw xyz, w = label bits; sorted by cell, map order inside a cell
+  int nx, ny, nz;
+  float min_x, min_y, min_z;
+  float max_x, max_y, max_z;
+  double grid;             // dda_grid_size_
+  double ray_angle_half;   // ray_angle_half_
+  double min_dist_thr_sq;  // min_dist_thr_sq_
+  float hit_tolerance;     // float(hit_tolerance_): Vec3 * double narrows to float (vec3.h:119)
+  float hit_range_sq;
+  float sin_total_ref;
+  float beam_likelihood;
+  float beam_likelihood_min;
+  uint32_t filter_label_max;
+  int short_only;
+};
+
+// ---- KD-tree raycaster (RaycastUsingKDTree, the node's default caster): marches over the likelihood
+// search grid; the colliding map point's raw coordinates / label are fetched by original index.
+struct KdRayDev
+{
+  const float4* raw_pts;  // map points as handed to set_map: xyz + label bits, original order
+  float grid_min;         // map_grid_min_ (raycast_using_kdtree.h:50)
+  float hit_tolerance;    // hit_tolerance_ (:52)
+  float r1, r1_sq, r1_pad;  // radius sqrt(2)*grid_max/2 narrowed to float (:83), float(double r * double r), window half-width
+  float r2, r2_sq, r2_pad;  // radius grid_min*2 + sqrt(2)*grid_max/2 (:95)
+  double sin_den;           // map_grid_min_ * 2.0 (:98)
+};
+
+enum
+{
+  ST_SHORT = 0,
+  ST_HIT = 1,
+  ST_LONG = 2,
+  ST_TOTAL_REFLECTION = 3
+};
+
+// --------------------------------------------------------------------------------------------
+// Exact nearest-neighbour distance^2 (rescaled metric) within the radius; returns r2 if none.
+__device__ __forceinline__ float nn_dist2(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz,
+                                          uint32_t& n_rows, uint32_t& n_pts)
+{
+  // Same cell function as the build kernel (monotone in its argument), applied to q -/+ rpad.
+  int lx = __float2int_rd(fmul(fsub(fsub(qx, lp.rpad), g.ox), g.inv_cell));
+  int ly = __float2int_rd(fmul(fsub(fsub(qy, lp.rpad), g.oy), g.inv_cell));
+  int lz = __float2int_rd(fmul(fsub(fsub(qz, lp.rpad), g.oz), g.inv_cell));
+  int hx = __float2int_rd(fmul(fsub(fadd(qx, lp.rpad), g.ox), g.inv_cell));
+  int hy = __float2int_rd(fmul(fsub(fadd(qy, lp.rpad), g.oy), g.inv_cell));
+  int hz = __float2int_rd(fmul(fsub(fadd(qz, lp.rpad), g.oz), g.inv_cell));
+  lx = max(lx, 0);
+  ly = max(ly, 0);
+  lz = max(lz, 0);
+  hx = min(hx, g.nx - 1);
+  hy = min(hy, g.ny - 1);
+  hz = min(hz, g.nz - 1);
+  float best = lp.r2;
+  if (lx > hx || ly > hy || lz > hz)
+    return best;
+  n_rows += static_cast<uint32_t>((hz - lz + 1) * (hy - ly + 1));
+  for (int iz = lz; iz <= hz; ++iz)
+  {
+    for (int iy = ly; iy <= hy; ++iy)
+    {
+      const int row = (iz * g.ny + iy) * g.nx;
+      const uint32_t s0 = __ldg(g.cell_start + row + lx);
+      const uint32_t s1 = __ldg(g.cell_start + row + hx + 1);
+      n_pts += s1 - s0;
+      for (uint32_t s = s0; s < s1; ++s)
+      {
+        const float4 m = __ldg(g.pts + s);
+        // flann::L2_Simple: sequential float accumulate of squared differences
+        const float dx = fsub(qx, m.x);
+        const float dy = fsub(qy, m.y);
+        const float dz = fsub(qz, m.z);
+        const float d = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+        best = fminf(best, d);  // KNNRadiusResultSet: keep d < worst
+      }
+    }
+  }
+  return best;
+}
+
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ int dda_to_index(float v, float mn, double grid)
+{
+  // toIndex, raycast_using_dda.h:205-210: float difference, double division, truncation
+  return __double2int_rz(ddiv(static_cast<double>(fsub(v, mn)), grid));
+}
+
+// One ray: RaycastUsingDDA::setRay + getNextCastResult loop + getBeamStatus's decision.
+//
+// Measured choices (profiles/r01g_variants.txt, r01h_variants.txt; all variants bit-exact):
+//   * the axis choice is evaluated branch-free (selects): 200 -> 177 us on c3, the 3-way branch
+//     diverges whenever the lanes of a warp cross different faces;
+//   * t_max needs float(|index - begin|): kept as a float counter (+1.0f per step) instead of an
+//     int->float conversion per step;
+//   * the occupancy word is re-read only when the cell leaves the current 32-cell word;
+//   * replacing the twelve fp64 divisions of the set-up by guarded reciprocal multiplications, caching
+//     the per-sensor ray origin, or screening the cone test in float changed nothing measurable
+//     (the kernel is latency/occupancy bound, not fp64 bound) and were dropped again;
+//   * occupancy matters most: __launch_bounds__(256, 4) (<= 64 registers) 200 -> 165 us.
+__device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const F3& e, uint32_t& n_steps,
+                                        uint32_t& n_occ, uint32_t& n_tested)
+{
+  // isPointWithinMap, :260-270
+  if (b.x < g.min_x || g.max_x < b.x || b.y < g.min_y || g.max_y < b.y || b.z < g.min_z || g.max_z < b.z)
+    return ST_LONG;
+  // setRay, :66-104
+  F3 d;
+  d.x = fsub(e.x, b.x);
+  d.y = fsub(e.y, b.y);
+  d.z = fsub(e.z, b.z);
+  const float nrm = __fsqrt_rn(dot3(d, d));
+  F3 dir;
+  dir.x = fdiv(d.x, nrm);
+  dir.y = fdiv(d.y, nrm);
+  dir.z = fdiv(d.z, nrm);
+  const float ex = fadd(e.x, fmul(dir.x, g.hit_tolerance));
+  const float ey = fadd(e.y, fmul(dir.y, g.hit_tolerance));
+  const float ez = fadd(e.z, fmul(dir.z, g.hit_tolerance));
+  const int bx = dda_to_index(b.x, g.min_x, g.grid);
+  const int by = dda_to_index(b.y, g.min_y, g.grid);
+  const int bz = dda_to_index(b.z, g.min_z, g.grid);
+  const int dix = dda_to_index(ex, g.min_x, g.grid) - bx;
+  const int diy = dda_to_index(ey, g.min_y, g.grid) - by;
+  const int diz = dda_to_index(ez, g.min_z, g.grid) - bz;
+  const int max_movement = abs(dix) + abs(diy) + abs(diz);
+  const int sx = dix < 0 ? -1 : 1, sy = diy < 0 ? -1 : 1, sz = diz < 0 ? -1 : 1;
+  const float inf = __int_as_float(0x7f800000);
+  float e0x = inf, e0y = inf, e0z = inf, tdx = inf, tdy = inf, tdz = inf;
+  if (dix != 0)
+  {
+    // nearest = index * grid + min_p in double; |(nearest - begin) / dir| and |grid / dir| stored as float (:94-99)
+    const double nearest = dadd(dmul(static_cast<double>(dir.x < 0 ? bx : bx + 1), g.grid), static_cast<double>(g.min_x));
+    e0x = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.x)), static_cast<double>(dir.x))));
+    tdx = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.x))));
+  }
+  if (diy != 0)
+  {
+    const double nearest = dadd(dmul(static_cast<double>(dir.y < 0 ? by : by + 1), g.grid), static_cast<double>(g.min_y));
+    e0y = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.y)), static_cast<double>(dir.y))));
+    tdy = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.y))));
+  }
+  if (diz != 0)
+  {
+    const double nearest = dadd(dmul(static_cast<double>(dir.z < 0 ? bz : bz + 1), g.grid), static_cast<double>(g.min_z));
+    e0z = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.z)), static_cast<double>(dir.z))));
+    tdz = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.z))));
+  }
+  float tx = e0x, ty = e0y, tz = e0z;
+  int cx = bx, cy = by, cz = bz;
+  float kx = 0.0f, ky = 0.0f, kz = 0.0f;  // float(|current - begin|): small integers, exact in float
+  const int nxy = g.nx * g.ny;
+  int last_w = -1;
+  uint32_t word = 0;
+  // getNextCastResult, :106-159: at most max_movement-1 cells; begin and end cells are never tested
+  for (int pos = 1; pos < max_movement; ++pos)
+  {
+    ++n_steps;
+    // strict-'<' ladder (:114-147): x if tx<ty && tx<tz; y if !(tx<ty) && ty<tz; else z (on ties z beats
+    // y beats x).  incrementIndex (:192-203) recomputes t_max from the start:
+    // float(edge0) + float(t_delta) * float(|index - begin|).
+    const bool lt_xy = tx < ty;
+    const bool ax = lt_xy && (tx < tz);
+    const bool ay = !lt_xy && (ty < tz);
+    const bool az = !ax && !ay;
+    cx += ax ? sx : 0;
+    cy += ay ? sy : 0;
+    cz += az ? sz : 0;
+    kx = ax ? fadd(kx, 1.0f) : kx;
+    ky = ay ? fadd(ky, 1.0f) : ky;
+    kz = az ? fadd(kz, 1.0f) : kz;
+    tx = ax ? fadd(e0x, fmul(tdx, kx)) : tx;
+    ty = ay ? fadd(e0y, fmul(tdy, ky)) : ty;
+    tz = az ? fadd(e0z, fmul(tdz, kz)) : tz;
+    if (static_cast<unsigned>(cx) >= static_cast<unsigned>(g.nx) || static_cast<unsigned>(cy) >= static_cast<unsigned>(g.ny) ||
+        static_cast<unsigned>(cz) >= static_cast<unsigned>(g.nz))
+      return ST_LONG;  // left the grid (:197-201)
+    const int cell = cx + cy * g.nx + cz * nxy;
+    const int w = cell >> 5;
+    if (w != last_w)
+    {
+      word = __ldg(g.occ + w);
+      last_w = w;
+    }
+    if (!((word >> (cell & 31)) & 1u))
+      continue;
+    // hasIntersection, :237-258: first point of the cell, in map order, inside the cone
+    const uint32_t s0 = __ldg(g.cell_start + cell);
+    const uint32_t s1 = __ldg(g.cell_start + cell + 1);
+    ++n_occ;
+    for (uint32_t s = s0; s < s1; ++s)
+    {
+      ++n_tested;
+      const float4 m = __ldg(g.pts + s);
+      F3 rel;
+      rel.x = fsub(m.x, b.x);
+      rel.y = fsub(m.y, b.y);
+      rel.z = fsub(m.z, b.z);
+      const double foot = static_cast<double>(fabsf(dot3(rel, dir)));
+      const double a0 = dmul(g.ray_angle_half, foot);
+      const double thr = fmax(dmul(a0, a0), g.min_dist_thr_sq);
+      const double dsq = dsub(static_cast<double>(dot3(rel, rel)), dmul(foot, foot));
+      if (dsq < thr)
+      {
+        // getBeamStatus, beam.cpp:164-189
+        if (__float_as_uint(m.w) > g.filter_label_max)
+          break;  // this cell's collision is filtered; the walk continues with the next cell
+        if (1.0f > g.sin_total_ref)
+        {
+          const double ddx = static_cast<double>(fsub(e.x, m.x));
+          const double ddy = static_cast<double>(fsub(e.y, m.y));
+          const double ddz = static_cast<double>(fsub(e.z, m.z));
+          const float dist_sq = __double2float_rn(dadd(dadd(dmul(ddx, ddx), dmul(ddy, ddy)), dmul(ddz, ddz)));
+          return dist_sq < g.hit_range_sq ? ST_HIT : ST_SHORT;
+        }
+        return ST_TOTAL_REFLECTION;
+      }
+    }
+  }
+  return ST_LONG;
+}
+
+// 1-NN within a radius with the index of the winner (ChunkedKdtree::radiusSearch(p, r, id, d2, 1)); ties go to
+// the lowest original index, like the CPU checkers.  General window (any radius below a few cells).
+__device__ __forceinline__ bool nn_search_arg(const NnGridDev& g, float qx, float qy, float qz, float rpad, float r_sq,
+                                              float& best, uint32_t& best_orig, uint32_t& n_tested)
+{
+  int lx = __float2int_rd(fmul(fsub(fsub(qx, rpad), g.ox), g.inv_cell));
+  int ly = __float2int_rd(fmul(fsub(fsub(qy, rpad), g.oy), g.inv_cell));
+  int lz = __float2int_rd(fmul(fsub(fsub(qz, rpad), g.oz), g.inv_cell));
+  int hx = __float2int_rd(fmul(fsub(fadd(qx, rpad), g.ox), g.inv_cell));
+  int hy = __float2int_rd(fmul(fsub(fadd(qy, rpad), g.oy), g.inv_cell));
+  int hz = __float2int_rd(fmul(fsub(fadd(qz, rpad), g.oz), g.inv_cell));
+  lx = max(lx, 0);
+  ly = max(ly, 0);
+  lz = max(lz, 0);
+  hx = min(hx, g.nx - 1);
+  hy = min(hy, g.ny - 1);
+  hz = min(hz, g.nz - 1);
+  best = r_sq;
+  best_orig = 0xffffffffu;
+  for (int iz = lz; iz <= hz; ++iz)
+    for (int iy = ly; iy <= hy; ++iy)
+    {
+      if (lx > hx)
+        break;
+      const int row = (iz * g.ny + iy) * g.nx;
+      const uint32_t s0 = __ldg(g.cell_start + row + lx);
+      const uint32_t s1 = __ldg(g.cell_start + row + hx + 1);
+      for (uint32_t s = s0; s < s1; ++s)
+      {
+        ++n_tested;
+        const float4 m = __ldg(g.pts + s);
+        const float dx = fsub(qx, m.x);
+        const float dy = fsub(qy, m.y);
+        const float dz = fsub(qz, m.z);
+        const float d = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));  // flann::L2_Simple
+        const uint32_t orig = __float_as_uint(m.w);
+        if (d < best || (d == best && orig < best_orig && best_orig != 0xffffffffu))
+        {
+          best = d;
+          best_orig = orig;
+        }
+      }
+    }
+  return best_orig != 0xffffffffu;
+}
+
+// One ray with RaycastUsingKDTree (raycasts/raycast_using_kdtree.h:57-110) + getBeamStatus (beam.cpp:157-192).
+__device__ __forceinline__ int cast_ray_kd(const KdRayDev& k, const NnGridDev& nn, const DdaGridDev& g, const F3& b,
+                                           const F3& e, uint32_t& n_steps, uint32_t& n_occ, uint32_t& n_tested)
+{
+  // setRay, :57-64
+  F3 d;
+  d.x = fsub(e.x, b.x);
+  d.y = fsub(e.y, b.y);
+  d.z = fsub(e.z, b.z);
+  const float nrm = __fsqrt_rn(dot3(d, d));
+  const int length = __float2int_rz(floorf(fdiv(fadd(nrm, k.hit_tolerance), k.grid_min)));
+  F3 inc;
+  inc.x = fmul(fdiv(d.x, nrm), k.grid_min);
+  inc.y = fmul(fdiv(d.y, nrm), k.grid_min);
+  inc.z = fmul(fdiv(d.z, nrm), k.grid_min);
+  F3 pos;
+  pos.x = fadd(b.x, inc.x);
+  pos.y = fadd(b.y, inc.y);
+  pos.z = fadd(b.z, inc.z);
+  // getNextCastResult, :66-110
+  for (int count = 1; count < length; ++count)
+  {
+    ++n_steps;
+    float d2;
+    uint32_t id;
+    if (nn_search_arg(nn, fmul(pos.x, nn.wx), fmul(pos.y, nn.wy), fmul(pos.z, nn.wz), k.r1_pad, k.r1_sq, d2, id, n_tested))
+    {
+      ++n_occ;
+      const float4 m = __ldg(k.raw_pts + id);
+      if (!(__float_as_uint(m.w) > g.filter_label_max))  // beam.cpp:168
+      {
+        const float d0 = __fsqrt_rn(d2);
+        // pos_prev = pos_ - inc_ * 2.0 (:91), second search radius grid_min*2 + sqrt(2)*grid_max/2 (:95)
+        const float px = fsub(pos.x, fmul(inc.x, 2.0f)), py = fsub(pos.y, fmul(inc.y, 2.0f)), pz = fsub(pos.z, fmul(inc.z, 2.0f));
+        float d2b;
+        uint32_t idb;
+        float sin_ang = 1.0f;
+        if (nn_search_arg(nn, fmul(px, nn.wx), fmul(py, nn.wy), fmul(pz, nn.wz), k.r2_pad, k.r2_sq, d2b, idb, n_tested))
+        {
+          const float d1 = __fsqrt_rn(d2b);
+          sin_ang = __double2float_rn(ddiv(fabs(static_cast<double>(fsub(d1, d0))), k.sin_den));  // :98
+        }
+        if (sin_ang > g.sin_total_ref)
+        {
+          const double ddx = static_cast<double>(fsub(e.x, m.x));
+          const double ddy = static_cast<double>(fsub(e.y, m.y));
+          const double ddz = static_cast<double>(fsub(e.z, m.z));
+          const float dist_sq = __double2float_rn(dadd(dadd(dmul(ddx, ddx), dmul(ddy, ddy)), dmul(ddz, ddz)));
+          return dist_sq < g.hit_range_sq ? ST_HIT : ST_SHORT;
+        }
+        return ST_TOTAL_REFLECTION;
+      }
+    }
+    pos.x = fadd(pos.x, inc.x);
+    pos.y = fadd(pos.y, inc.y);
+    pos.z = fadd(pos.z, inc.z);
+  }
+  return ST_LONG;
+}
+
+// begin = s.pos_ + s.rot_ * origins[label] with the RAW rot_ (beam.cpp:145)
+__device__ __forceinline__ F3 ray_origin(const F3& pos, const Q4& q_raw, const float* __restrict__ origins_xyz,
+                                         uint32_t label)
+{
+  F3 o;
+  o.x = __ldg(origins_xyz + 3 * label);
+  o.y = __ldg(origins_xyz + 3 * label + 1);
+  o.z = __ldg(origins_xyz + 3 * label + 2);
+  const F3 ro = qrot(q_raw, o);
+  F3 begin;
+  begin.x = fadd(pos.x, ro.x);
+  begin.y = fadd(pos.y, ro.y);
+  begin.z = fadd(pos.z, ro.z);
+  return begin;
+}
+
+}  // namespace mcl3dl

@@ -6,7 +6,9 @@
 // square root) in the operand order of the reference source it cites.  The translation unit is also
 // compiled with -fmad=false as a second line of defence.
 #pragma once
+#ifndef MCL3DL_HOSTSIM  // tests/hostsim compiles this header for the host with its own intrinsic shims
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace mcl3dl
@@ -92,14 +94,4 @@ __device__ __forceinline__ F3 transform_point(const Q4& rn, const F3& pos, const
   return t;
 }
 
-__device__ __forceinline__ float warp_sum(float v)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fadd(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v)
-{
-  return __reduce_add_sync(0xffffffffu, v);
-}
 }  // namespace mcl3dl

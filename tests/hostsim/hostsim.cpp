@@ -1,0 +1,273 @@
+// hostsim.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the product's per-thread device functions (mcl_3dl_b200/csrc/device_math.cuh, device_funcs.cuh) for the
+// HOST through cuda_shim.h and drives them over host-built copies of the two device grids, one (particle, point) at a
+// time.  tests/test_hostsim.py compares the result with the oracle: a way to check edits to cast_ray / cast_ray_kd /
+// nn_dist2 / nn_search_arg / the transform without a GPU.  The warp-cooperative parts of the kernels (staging,
+// window-table phase, reductions) are NOT covered here; the GPU parity suite covers those.
+// The grid construction below restates what engine.cu's build kernels do (same cell functions, same stable order).
+#include "cuda_shim.h"
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "../../include/mcl3dl_b200.h"
+#include "../../mcl_3dl_b200/csrc/device_funcs.cuh"
+
+using namespace mcl3dl;
+
+namespace
+{
+struct HostMap
+{
+  std::vector<uint32_t> nn_cell_start, dda_cell_start, occ;
+  std::vector<float4> nn_pts, dda_pts, raw_pts;
+  NnGridDev nn{};
+  DdaGridDev dda{};
+  KdRayDev kd{};
+  LikDev lik{};
+};
+
+void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_params* lp, const mcl3dl_beam_params* bp,
+           float cell_factor)
+{
+  const float wx = lp ? lp->dist_weight[0] : 1.0f, wy = lp ? lp->dist_weight[1] : 1.0f, wz = lp ? lp->dist_weight[2] : 1.0f;
+  float raw_min[3], raw_max[3], sc_min[3], sc_max[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    raw_min[k] = sc_min[k] = std::numeric_limits<float>::infinity();
+    raw_max[k] = sc_max[k] = -std::numeric_limits<float>::infinity();
+  }
+  m.raw_pts.resize(n);
+  for (size_t i = 0; i < n; ++i)
+  {
+    const float v[3] = {pts[i].x, pts[i].y, pts[i].z};
+    const float s[3] = {__fmul_rn(pts[i].x, wx), __fmul_rn(pts[i].y, wy), __fmul_rn(pts[i].z, wz)};
+    for (int k = 0; k < 3; ++k)
+    {
+      raw_min[k] = std::min(raw_min[k], v[k]);
+      raw_max[k] = std::max(raw_max[k], v[k]);
+      sc_min[k] = std::min(sc_min[k], s[k]);
+      sc_max[k] = std::max(sc_max[k], s[k]);
+    }
+    m.raw_pts[i] = make_float4(pts[i].x, pts[i].y, pts[i].z, __uint_as_float(pts[i].label));
+  }
+  if (lp)
+  {
+    const float R = lp->match_dist_min;
+    m.lik.match_dist_min = R;
+    m.lik.match_dist_flat = lp->match_dist_flat;
+    m.lik.match_weight = lp->match_weight;
+    m.lik.r2 = static_cast<float>(static_cast<double>(R) * static_cast<double>(R));
+    m.lik.rpad = R * 1.0001f + 1e-6f;
+    NnGridDev g{};
+    const float cell = std::max(R * cell_factor, m.lik.rpad * 1.01f);
+    g.inv_cell = 1.0f / cell;
+    g.wx = wx;
+    g.wy = wy;
+    g.wz = wz;
+    int dims[3];
+    float org[3];
+    for (int k = 0; k < 3; ++k)
+    {
+      org[k] = sc_min[k] - 0.5f * cell;
+      dims[k] = static_cast<int>(std::floor((static_cast<double>(sc_max[k]) - org[k]) / cell)) + 2;
+    }
+    g.nx = dims[0];
+    g.ny = dims[1];
+    g.nz = dims[2];
+    g.ox = org[0];
+    g.oy = org[1];
+    g.oz = org[2];
+    const size_t cells = static_cast<size_t>(g.nx) * g.ny * g.nz;
+    std::vector<uint32_t> key(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+      int cx = __float2int_rd(__fmul_rn(__fsub_rn(__fmul_rn(pts[i].x, wx), g.ox), g.inv_cell));
+      int cy = __float2int_rd(__fmul_rn(__fsub_rn(__fmul_rn(pts[i].y, wy), g.oy), g.inv_cell));
+      int cz = __float2int_rd(__fmul_rn(__fsub_rn(__fmul_rn(pts[i].z, wz), g.oz), g.inv_cell));
+      cx = min(max(cx, 0), g.nx - 1);
+      cy = min(max(cy, 0), g.ny - 1);
+      cz = min(max(cz, 0), g.nz - 1);
+      key[i] = static_cast<uint32_t>((cz * g.ny + cy) * g.nx + cx);
+    }
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    m.nn_cell_start.assign(cells + 1, 0);
+    for (size_t i = 0; i < n; ++i) m.nn_cell_start[key[i] + 1]++;
+    for (size_t c = 0; c < cells; ++c) m.nn_cell_start[c + 1] += m.nn_cell_start[c];
+    m.nn_pts.resize(n);
+    for (size_t k = 0; k < n; ++k)
+    {
+      const mcl3dl_point& p = pts[order[k]];
+      m.nn_pts[k] = make_float4(__fmul_rn(p.x, wx), __fmul_rn(p.y, wy), __fmul_rn(p.z, wz), __uint_as_float(order[k]));
+    }
+    g.cell_start = m.nn_cell_start.data();
+    g.pts = m.nn_pts.data();
+    g.row3 = nullptr;  // the window table is only read by the warp-cooperative kernel, not by these functions
+    g.nyp = 0;
+    m.nn = g;
+  }
+  if (bp)
+  {
+    DdaGridDev g{};
+    g.grid = bp->dda_grid_size;
+    g.ray_angle_half = bp->ray_angle_half;
+    g.min_dist_thr_sq = bp->map_grid_size[0] * bp->map_grid_size[0] + bp->map_grid_size[1] * bp->map_grid_size[1] +
+                        bp->map_grid_size[1] * bp->map_grid_size[1];
+    g.hit_tolerance = static_cast<float>(bp->hit_tolerance);
+    g.hit_range_sq = bp->hit_range_sq;
+    g.sin_total_ref = bp->sin_total_ref;
+    g.beam_likelihood = bp->beam_likelihood;
+    g.beam_likelihood_min = bp->beam_likelihood_min;
+    g.filter_label_max = bp->filter_label_max;
+    g.short_only = bp->add_penalty_short_only_mode ? 1 : 0;
+    g.min_x = raw_min[0];
+    g.min_y = raw_min[1];
+    g.min_z = raw_min[2];
+    g.max_x = raw_max[0];
+    g.max_y = raw_max[1];
+    g.max_z = raw_max[2];
+    if (bp->use_raycast_using_dda)
+    {
+      int dims[3];
+      for (int k = 0; k < 3; ++k)
+        dims[k] = static_cast<int>(static_cast<size_t>(static_cast<double>(raw_max[k] - raw_min[k]) / g.grid) + 1);
+      g.nx = dims[0];
+      g.ny = dims[1];
+      g.nz = dims[2];
+      const size_t cells = static_cast<size_t>(g.nx) * g.ny * g.nz;
+      std::vector<uint32_t> key(n);
+      m.occ.assign((cells + 31) / 32 + 1, 0u);
+      for (size_t i = 0; i < n; ++i)
+      {
+        const int cx = dda_to_index(pts[i].x, g.min_x, g.grid), cy = dda_to_index(pts[i].y, g.min_y, g.grid),
+                  cz = dda_to_index(pts[i].z, g.min_z, g.grid);
+        key[i] = static_cast<uint32_t>(cx + cy * g.nx + cz * (g.nx * g.ny));
+        m.occ[key[i] >> 5] |= 1u << (key[i] & 31);
+      }
+      std::vector<uint32_t> order(n);
+      std::iota(order.begin(), order.end(), 0u);
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+      m.dda_cell_start.assign(cells + 2, 0);
+      for (size_t i = 0; i < n; ++i) m.dda_cell_start[key[i] + 1]++;
+      for (size_t c = 0; c < cells; ++c) m.dda_cell_start[c + 1] += m.dda_cell_start[c];
+      m.dda_pts.resize(n);
+      for (size_t k = 0; k < n; ++k) m.dda_pts[k] = m.raw_pts[order[k]];
+      g.occ = m.occ.data();
+      g.cell_start = m.dda_cell_start.data();
+      g.pts = m.dda_pts.data();
+    }
+    else
+    {
+      const float gx = static_cast<float>(bp->map_grid_size[0]), gy = static_cast<float>(bp->map_grid_size[1]),
+                  gz = static_cast<float>(bp->map_grid_size[2]);
+      const float gmin = std::min(gx, std::min(gy, gz)), gmax = std::max(gx, std::max(gy, gz));
+      KdRayDev k{};
+      k.raw_pts = m.raw_pts.data();
+      k.grid_min = gmin;
+      k.hit_tolerance = static_cast<float>(bp->hit_tolerance);
+      k.r1 = static_cast<float>(std::sqrt(2.0) * gmax / 2.0);
+      k.r2 = static_cast<float>(gmin * 2 + std::sqrt(2.0) * gmax / 2.0);
+      k.r1_sq = static_cast<float>(static_cast<double>(k.r1) * static_cast<double>(k.r1));
+      k.r2_sq = static_cast<float>(static_cast<double>(k.r2) * static_cast<double>(k.r2));
+      k.r1_pad = k.r1 * 1.0001f + 1e-6f;
+      k.r2_pad = k.r2 * 1.0001f + 1e-6f;
+      k.sin_den = gmin * 2.0;
+      m.kd = k;
+    }
+    m.dda = g;
+  }
+}
+}  // namespace
+
+extern "C" int hostsim_measure(const mcl3dl_point* map, size_t n, const mcl3dl_lik_params* lp, const mcl3dl_beam_params* bp,
+                               float cell_factor, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts,
+                               size_t n_lik, const mcl3dl_point* beam_pts, size_t n_beam, const float* origins_xyz,
+                               size_t n_origins, mcl3dl_result* out, uint8_t* status)
+{
+  if ((n_lik && !lp) || (n_beam && !bp) || (bp && !bp->use_raycast_using_dda && !lp))
+    return -1;
+  for (size_t j = 0; j < n_beam; ++j)
+    if (beam_pts[j].label >= n_origins)
+      return -1;
+  HostMap m;
+  build(m, map, n, lp, bp, cell_factor);
+  for (size_t p = 0; p < P; ++p)
+  {
+    F3 pos;
+    pos.x = poses[p].px;
+    pos.y = poses[p].py;
+    pos.z = poses[p].pz;
+    Q4 q;
+    q.x = poses[p].qx;
+    q.y = poses[p].qy;
+    q.z = poses[p].qz;
+    q.w = poses[p].qw;
+    const Q4 rn = qnormalized(q);
+    mcl3dl_result r;
+    std::memset(&r, 0, sizeof(r));
+    // beam: the per-ray body of beam_kernel / beam_kernel_pl
+    uint32_t a = 0, b = 0, c = 0, s0 = 0, s1 = 0, s2 = 0;
+    for (size_t j = 0; j < n_beam; ++j)
+    {
+      F3 v;
+      v.x = beam_pts[j].x;
+      v.y = beam_pts[j].y;
+      v.z = beam_pts[j].z;
+      const F3 end = transform_point(rn, pos, v);
+      const F3 begin = ray_origin(pos, q, origins_xyz, beam_pts[j].label);
+      const int st = bp->use_raycast_using_dda ? cast_ray(m.dda, begin, end, s0, s1, s2) :
+                                                 cast_ray_kd(m.kd, m.nn, m.dda, begin, end, s0, s1, s2);
+      a += st == ST_SHORT;
+      b += st == ST_HIT;
+      c += st == ST_LONG;
+      if (status) status[p * n_beam + j] = static_cast<uint8_t>(st);
+    }
+    float score = 1.0f;
+    if (n_beam)
+    {
+      const uint32_t k = a + (m.dda.short_only ? 0u : c);
+      for (uint32_t i = 0; i < k; ++i) score = fmul(score, m.dda.beam_likelihood);
+      if (score < m.dda.beam_likelihood_min) score = m.dda.beam_likelihood_min;
+    }
+    r.score_beam = score;
+    r.n_short = a;
+    r.n_hit = b;
+    r.n_long = c;
+    // likelihood: the per-eval body of lik_kernel, summed in scan order
+    if (n_lik == 0)
+    {
+      r.score_like = 1.0f;
+    }
+    else
+    {
+      float sl = 0.0f;
+      uint32_t cnt = 0, rows = 0, npts = 0;
+      for (size_t j = 0; j < n_lik; ++j)
+      {
+        F3 v;
+        v.x = lik_pts[j].x;
+        v.y = lik_pts[j].y;
+        v.z = lik_pts[j].z;
+        const F3 t = transform_point(rn, pos, v);
+        const float d2 = nn_dist2(m.nn, m.lik, fmul(t.x, m.nn.wx), fmul(t.y, m.nn.wy), fmul(t.z, m.nn.wz), rows, npts);
+        if (d2 < m.lik.r2)
+        {
+          const float dist = fsub(m.lik.match_dist_min, fmaxf(__fsqrt_rn(d2), m.lik.match_dist_flat));
+          if (!(dist < 0.0f))
+          {
+            sl = fadd(sl, fmul(dist, m.lik.match_weight));
+            cnt++;
+          }
+        }
+      }
+      r.score_like = sl;
+      r.match_cnt = cnt;
+    }
+    if (out) out[p] = r;
+  }
+  return 0;
+}

@@ -1,0 +1,84 @@
+"""The product's per-thread device functions, compiled for the HOST (tests/hostsim/) and checked against the oracle.
+
+mcl_3dl_b200/csrc/device_math.cuh and device_funcs.cuh — the SE(3) transform, nn_dist2, nn_search_arg, cast_ray
+(DDA), cast_ray_kd (KD-tree caster), ray_origin — are included verbatim by tests/hostsim/hostsim.cpp through a small
+intrinsic shim, so an edit to any of them can be checked here without a GPU.  Sequential scan-order sums make even the
+likelihood score bit-exact against the oracle.  (The warp-cooperative kernel code is covered by the -m gpu suite.)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from mcl_3dl_b200 import engine, synth
+from oracle import cpu_checker as cc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HS = os.path.join(ROOT, "tests", "hostsim")
+LIB = os.path.join(HS, "libhostsim.so")
+DEPS = [os.path.join(HS, "hostsim.cpp"), os.path.join(HS, "cuda_shim.h"),
+        os.path.join(ROOT, "mcl_3dl_b200", "csrc", "device_funcs.cuh"),
+        os.path.join(ROOT, "mcl_3dl_b200", "csrc", "device_math.cuh"), os.path.join(ROOT, "include", "mcl3dl_b200.h")]
+
+
+@pytest.fixture(scope="module")
+def hostsim():
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+        r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB,
+                            os.path.join(HS, "hostsim.cpp")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    L = C.CDLL(LIB)
+    vp, sz = C.c_void_p, C.c_size_t
+    L.hostsim_measure.argtypes = [vp, sz, vp, vp, C.c_float, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp]
+
+    def run(map_pts, lik, beam, poses, lik_pts, beam_pts, origins):
+        map_pts = np.ascontiguousarray(map_pts, dtype=synth.POINT)
+        poses = np.ascontiguousarray(poses, dtype=synth.POSE)
+        lik_pts = np.ascontiguousarray(lik_pts if lik_pts is not None else np.zeros(0, synth.POINT), dtype=synth.POINT)
+        beam_pts = np.ascontiguousarray(beam_pts if beam_pts is not None else np.zeros(0, synth.POINT), dtype=synth.POINT)
+        origins = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(len(poses), dtype=synth.RESULT)
+        st = np.zeros((len(poses), max(len(beam_pts), 1)), dtype=np.uint8)
+        p = lambda a: a.ctypes.data_as(vp) if a.size else None  # noqa: E731
+        rc = L.hostsim_measure(p(map_pts), len(map_pts), C.byref(lik) if lik is not None else None,
+                               C.byref(beam) if beam is not None else None, 1.0, p(poses), len(poses), p(lik_pts),
+                               len(lik_pts), p(beam_pts), len(beam_pts), p(origins), len(origins), p(out), p(st))
+        assert rc == 0
+        return out, st[:, :len(beam_pts)]
+    return run
+
+
+@pytest.mark.parametrize("seed,w,spread,use_dda,flm", [
+    (1, (1, 1, 1), False, True, 0xFFFFFFFF), (2, (1, 1, 5), False, True, 1), (3, (1, 1, 5), True, True, 0xFFFFFFFF),
+    (4, (1, 1, 5), False, False, 0xFFFFFFFF), (5, (1, 1, 1), False, False, 1), (6, (2, 1, 3), True, False, 0xFFFFFFFF),
+])
+def test_device_functions_on_host_match_oracle(hostsim, port, seed, w, spread, use_dda, flm):
+    s = synth.scene(30_000, 40, 48, 20, spread=spread, seed=seed)
+    kw = dict(num_points_default=20, dda_grid_size=0.2 if seed % 2 else 0.1, filter_label_max=flm,
+              add_penalty_short_only_mode=seed != 3, use_raycast_using_dda=use_dda)
+    lik = engine.LikParams(dist_weight=w)
+    beam = engine.beam_params_from_reference(**kw)
+    cpu = port.create(s["map"], cc.lik_params(dist_weight=w), cc.beam_raw(**kw), 20.0, 0.4 if min(w) >= 1 else 1.0)
+    want = cpu.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+    got, st = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"])
+    for f in want.dtype.names:
+        assert np.array_equal(got[f], want[f]), f   # score_like too: same sequential sum
+    assert np.array_equal(st, cpu.beam_status(s["particles"], s["beam"], s["origins"]))
+
+
+@pytest.mark.parametrize("name", ["room_iso", "room_aniso", "room_spread", "room_kd_iso", "room_kd_aniso"])
+def test_device_functions_on_host_match_reference_goldens(hostsim, name):
+    g = golden(name + ".npz")
+    n_beam, flm, short_only = [int(v) for v in g["beam_cfg"]]
+    lik = engine.LikParams(dist_weight=tuple(float(v) for v in g["dist_weight"]))
+    beam = engine.beam_params_from_reference(num_points_default=n_beam, filter_label_max=flm,
+                                             add_penalty_short_only_mode=bool(short_only),
+                                             dda_grid_size=float(g["dda_grid"]),
+                                             use_raycast_using_dda=bool(int(g["use_dda"])))
+    got, st = hostsim(g["map"], lik, beam, g["particles"], g["lik"], g["beam"], g["origins"])
+    for f in got.dtype.names:
+        assert np.array_equal(got[f], g["result"][f]), f
+    assert np.array_equal(st, g["status"])
