@@ -167,9 +167,12 @@ __device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const 
   const int bx = dda_to_index(b.x, g.min_x, g.grid);
   const int by = dda_to_index(b.y, g.min_y, g.grid);
   const int bz = dda_to_index(b.z, g.min_z, g.grid);
-  const int dix = dda_to_index(ex, g.min_x, g.grid) - bx;
-  const int diy = dda_to_index(ey, g.min_y, g.grid) - by;
-  const int diz = dda_to_index(ez, g.min_z, g.grid) - bz;
+  // (end indices are clamped to +-2^29 so that garbage end points — infinite or 1e30 coordinates, for which the
+  // reference's own int conversion is undefined — cannot overflow the differences; the begin index is inside the grid)
+  constexpr int kIdxLim = 1 << 29;
+  const int dix = max(-kIdxLim, min(kIdxLim, dda_to_index(ex, g.min_x, g.grid))) - bx;
+  const int diy = max(-kIdxLim, min(kIdxLim, dda_to_index(ey, g.min_y, g.grid))) - by;
+  const int diz = max(-kIdxLim, min(kIdxLim, dda_to_index(ez, g.min_z, g.grid))) - bz;
   const int max_movement = abs(dix) + abs(diy) + abs(diz);
   const int sx = dix < 0 ? -1 : 1, sy = diy < 0 ? -1 : 1, sz = diz < 0 ? -1 : 1;
   const float inf = __int_as_float(0x7f800000);
@@ -323,7 +326,10 @@ __device__ __forceinline__ int cast_ray_kd(const KdRayDev& k, const NnGridDev& n
   d.y = fsub(e.y, b.y);
   d.z = fsub(e.z, b.z);
   const float nrm = __fsqrt_rn(dot3(d, d));
-  const int length = __float2int_rz(floorf(fdiv(fadd(nrm, k.hit_tolerance), k.grid_min)));
+  // The march is capped at 65 536 steps (6.5 km at the default 0.1 m step; the node clips scans at <= 10 m): an end
+  // point at 1e30 or +inf must not keep a warp busy for 2^31 steps.  (The reference's float -> int conversion of such a
+  // length is undefined; on x86 it yields INT_MIN, i.e. no march at all.)
+  const int length = min(__float2int_rz(floorf(fdiv(fadd(nrm, k.hit_tolerance), k.grid_min))), 65536);
   F3 inc;
   inc.x = fmul(fdiv(d.x, nrm), k.grid_min);
   inc.y = fmul(fdiv(d.y, nrm), k.grid_min);

@@ -82,3 +82,18 @@ def test_device_functions_on_host_match_reference_goldens(hostsim, name):
     for f in got.dtype.names:
         assert np.array_equal(got[f], g["result"][f]), f
     assert np.array_equal(st, g["status"])
+
+
+def test_device_functions_survive_garbage_inputs_under_sanitizers(tmp_path):
+    """NaN / inf / 1e30 poses and scan points, one-point maps, zero-length rays: no out-of-bounds access, no signed
+    overflow and bounded work in the per-thread device functions (ASan + UBSan build of tests/hostsim/fuzz_main.cpp)."""
+    exe = str(tmp_path / "hostsim_fuzz")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fsanitize=address,undefined",
+                        "-fno-sanitize-recover=undefined", "-o", exe, os.path.join(HS, "fuzz_main.cpp"),
+                        os.path.join(HS, "hostsim.cpp")], capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("sanitizer runtimes not available: " + r.stderr.splitlines()[0])
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "fuzz ok" in r.stdout
