@@ -219,6 +219,13 @@ void mcl3dl_beam_params_from_reference(mcl3dl_beam_params* out,
 
 int mcl3dl_get_map_info(const mcl3dl_engine*, mcl3dl_map_info* out);
 
+/* The near-field screens staged by the last set_map ([0] likelihood search, [1] KD-tree raycaster's marching search):
+ * dilation k (0 = no field staged) and bytes per device.  A screen is one bit per fine cell of the map's bounding box,
+ * "a map point may lie within the search radius"; a clear bit skips the exact search, a set bit decides nothing, so
+ * results are unchanged (no reference counterpart: ChunkedKdtree::radiusSearch, chunked_kdtree.h:218-251, always
+ * descends the tree).  Environment: MCL3DL_NEAR_K / MCL3DL_NEAR_KD_K (0 disables), MCL3DL_NEAR_MAX_MB. */
+int mcl3dl_near_field_info(const mcl3dl_engine*, int32_t k_out[2], uint64_t bytes_out[2]);
+
 /* Enable (and zero) / disable the work counters; read them (synchronises the devices). */
 int mcl3dl_collect_stats(mcl3dl_engine*, int enable);
 int mcl3dl_read_stats(mcl3dl_engine*, mcl3dl_work_stats* out);

@@ -6,12 +6,113 @@
 #ifndef MCL3DL_HOSTSIM
 #include <cuda_runtime.h>
 #endif
+#include <math.h>
 #include <stdint.h>
 
 #include "device_math.cuh"
 
+// MCL3DL_NEAR_BITS=1 compiles the near-field screen below into the searches; 0 leaves every kernel as it was
+// (build.py passes -DMCL3DL_NEAR_BITS=... for A/B builds).
+#ifndef MCL3DL_NEAR_BITS
+#define MCL3DL_NEAR_BITS 0
+#endif
+
 namespace mcl3dl
 {
+// ---- near field: one bit per FINE cubic cell (edge ef = 1.01 * r / k) of the rescaled space, set when some map
+// point's fine cell lies within k cells (Chebyshev) of it.  A query whose bit is clear has no map point within r:
+// |p - q| < r  =>  per axis |p_a - q_a| < r = 0.99 k ef  =>  the two cell indices differ by at most k (the 1 % margin
+// covers the float rounding of the shared cell function below for up to ~65 k cells per axis).  The field is a
+// conservative screen in front of the exact searches: a set bit decides nothing, a clear bit skips the search.
+struct NearBitsDev
+{
+  const uint32_t* bits;  // nullptr = no field: every query is "maybe near"
+  int nx, ny, nz;        // fine cells per axis
+  int pitch;             // 32-bit words per x-row
+  float ox, oy, oz;      // origin in the rescaled space: k + 0.5 cells below the map's bounding box
+  float inv_cell;
+};
+
+__device__ __forceinline__ int near_cell(float v, float o, float inv_cell)
+{
+  return __float2int_rd(fmul(fsub(v, o), inv_cell));
+}
+
+// false only if no map point can be within the radius the field was built for (queries outside the field's extent
+// are at least k cells away from every point's cell; a NaN coordinate lands in cell 0 and at worst runs the search)
+__device__ __forceinline__ bool near_maybe(const NearBitsDev& f, float qx, float qy, float qz)
+{
+  if (!f.bits)
+    return true;
+  const int cx = near_cell(qx, f.ox, f.inv_cell), cy = near_cell(qy, f.oy, f.inv_cell), cz = near_cell(qz, f.oz, f.inv_cell);
+  if (static_cast<unsigned>(cx) >= static_cast<unsigned>(f.nx) || static_cast<unsigned>(cy) >= static_cast<unsigned>(f.ny) ||
+      static_cast<unsigned>(cz) >= static_cast<unsigned>(f.nz))
+    return false;
+  const uint32_t w = __ldg(f.bits + (static_cast<size_t>(cz) * f.ny + cy) * f.pitch + (cx >> 5));
+  return (w >> (cx & 31)) & 1u;
+}
+
+// Build side, per map point (rescaled coordinates): set the bits of every fine cell within k cells of the point's.
+// x is the bit index inside a row, so one (dy, dz) row is a run of <= 2k+1 <= 31 bits = at most two word updates.
+__device__ __forceinline__ void near_mark_point(const NearBitsDev& f, uint32_t* bits, int k, float sx, float sy, float sz)
+{
+  const int cx = near_cell(sx, f.ox, f.inv_cell), cy = near_cell(sy, f.oy, f.inv_cell), cz = near_cell(sz, f.oz, f.inv_cell);
+  const int x0 = max(cx - k, 0), x1 = min(cx + k, f.nx - 1);
+  if (x0 > x1)
+    return;
+  const int w0 = x0 >> 5, w1 = x1 >> 5;
+  const uint32_t lo = 0xffffffffu << (x0 & 31), hi = 0xffffffffu >> (31 - (x1 & 31));
+  for (int iz = max(cz - k, 0); iz <= min(cz + k, f.nz - 1); ++iz)
+    for (int iy = max(cy - k, 0); iy <= min(cy + k, f.ny - 1); ++iy)
+    {
+      uint32_t* row = bits + (static_cast<size_t>(iz) * f.ny + iy) * f.pitch;
+      if (w0 == w1)
+        atomicOr(row + w0, lo & hi);
+      else
+      {
+        atomicOr(row + w0, lo);
+        atomicOr(row + w1, hi);
+      }
+    }
+}
+
+// Host side: extent of a field for search radius r (> 0) and dilation k (1..15) over the rescaled bounding box.
+// The cell edge is doubled until the field fits max_bytes and 65 536 cells per axis (coarser is still conservative).
+inline bool near_layout(NearBitsDev& f, float r, int k, const float sc_min[3], const float sc_max[3], size_t max_bytes)
+{
+  if (!(r > 0.0f) || k < 1 || k > 15)
+    return false;
+  float ef = 1.01f * r / static_cast<float>(k);
+  for (int tries = 0; tries < 40; ++tries, ef *= 2.0f)
+  {
+    double dims[3];
+    float org[3];
+    bool ok = true;
+    for (int a = 0; a < 3; ++a)
+    {
+      org[a] = sc_min[a] - (static_cast<float>(k) + 0.5f) * ef;
+      dims[a] = floor((static_cast<double>(sc_max[a]) - org[a]) / ef) + k + 2;
+      ok = ok && dims[a] >= 1.0 && dims[a] <= 65536.0;
+    }
+    if (!ok)
+      continue;
+    const double pitch = floor((dims[0] + 31.0) / 32.0);
+    if (pitch * dims[1] * dims[2] * 4.0 > static_cast<double>(max_bytes))
+      continue;
+    f.bits = nullptr;
+    f.nx = static_cast<int>(dims[0]);
+    f.ny = static_cast<int>(dims[1]);
+    f.nz = static_cast<int>(dims[2]);
+    f.pitch = static_cast<int>(pitch);
+    f.ox = org[0];
+    f.oy = org[1];
+    f.oz = org[2];
+    f.inv_cell = 1.0f / ef;
+    return true;
+  }
+  return false;
+}
+
 // ---- likelihood search grid: cubic cells over the RESCALED map points (p * dist_weight), CSR of
 // cell -> contiguous run in `pts` (x fastest, so an x-row of cells is one contiguous run).
 struct NnGridDev
@@ -28,6 +129,9 @@ struct NnGridDev
   float ox, oy, oz;  // grid origin in the rescaled space
   float inv_cell;
   float wx, wy, wz;  // dist_weight
+#if MCL3DL_NEAR_BITS
+  NearBitsDev near;  // built for the likelihood radius (LikDev::rpad)
+#endif
 };
 
 struct LikDev
@@ -71,6 +175,9 @@ struct KdRayDev
   float r1, r1_sq, r1_pad;  // radius sqrt(2)*grid_max/2 narrowed to float (:83), float(double r * double r), window half-width
   float r2, r2_sq, r2_pad;  // radius grid_min*2 + sqrt(2)*grid_max/2 (:95)
   double sin_den;           // map_grid_min_ * 2.0 (:98)
+#if MCL3DL_NEAR_BITS
+  NearBitsDev near;  // built for the marching search radius (r1_pad)
+#endif
 };
 
 enum
@@ -86,6 +193,10 @@ enum
 __device__ __forceinline__ float nn_dist2(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz,
                                           uint32_t& n_rows, uint32_t& n_pts)
 {
+#if MCL3DL_NEAR_BITS
+  if (!near_maybe(g.near, qx, qy, qz))
+    return lp.r2;
+#endif
   // Same cell function as the build kernel (monotone in its argument), applied to q -/+ rpad.
   int lx = __float2int_rd(fmul(fsub(fsub(qx, lp.rpad), g.ox), g.inv_cell));
   int ly = __float2int_rd(fmul(fsub(fsub(qy, lp.rpad), g.oy), g.inv_cell));
@@ -344,7 +455,13 @@ __device__ __forceinline__ int cast_ray_kd(const KdRayDev& k, const NnGridDev& n
     ++n_steps;
     float d2;
     uint32_t id;
-    if (nn_search_arg(nn, fmul(pos.x, nn.wx), fmul(pos.y, nn.wy), fmul(pos.z, nn.wz), k.r1_pad, k.r1_sq, d2, id, n_tested))
+    const float qx = fmul(pos.x, nn.wx), qy = fmul(pos.y, nn.wy), qz = fmul(pos.z, nn.wz);
+#if MCL3DL_NEAR_BITS
+    // free space: the marching search cannot find anything, skip it (most steps of most rays)
+    if (near_maybe(k.near, qx, qy, qz) && nn_search_arg(nn, qx, qy, qz, k.r1_pad, k.r1_sq, d2, id, n_tested))
+#else
+    if (nn_search_arg(nn, qx, qy, qz, k.r1_pad, k.r1_sq, d2, id, n_tested))
+#endif
     {
       ++n_occ;
       const float4 m = __ldg(k.raw_pts + id);

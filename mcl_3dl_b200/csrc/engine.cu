@@ -139,6 +139,19 @@ __global__ void nn_row3_kernel(NnGridDev g, uint2* __restrict__ row3, size_t tot
   row3[i] = e;
 }
 
+#if MCL3DL_NEAR_BITS
+// Near field (NearBitsDev): every map point sets the bits of the fine cells within k cells of its own.
+__global__ void near_mark_kernel(const mcl3dl_point* __restrict__ pts, uint32_t n, float wx, float wy, float wz, NearBitsDev f,
+                                 uint32_t* __restrict__ bits, int k)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const float4 p = __ldg(reinterpret_cast<const float4*>(pts) + i);
+  near_mark_point(f, bits, k, fmul(p.x, wx), fmul(p.y, wy), fmul(p.z, wz));
+}
+#endif
+
 // DDA grid: RaycastUsingDDA::setExists (raycast_using_dda.h:230-235) for every map point.
 __global__ void dda_key_kernel(const mcl3dl_point* __restrict__ pts, uint32_t n, DdaGridDev g,
                                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
@@ -184,6 +197,8 @@ struct DeviceCtx
   DdaGridDev dda{};
   KdRayDev kd{};
   DevBuf raw_pts;  // map points in original order (KD-tree raycaster only)
+  DevBuf near_lik, near_kd;  // near-field bits (MCL3DL_NEAR_BITS builds)
+  float near_kd_r = 0.0f;    // radius the KD field was built for
   size_t map_bytes = 0;
   // per-update I/O
   DevBuf d_poses /* whole input block of the host path */, d_out, d_status;
@@ -220,6 +235,14 @@ struct mcl3dl_engine
   std::string err;
   float nn_cell_factor = 1.0f;
   int overlap = 1;  // run the beam and likelihood kernels concurrently (MCL3DL_OVERLAP=0 serialises them)
+  int near_k = 2;     // near-field dilation of the likelihood screen (MCL3DL_NEAR_K, 0 = no field)
+  int near_kd_k = 1;  // same for the KD-tree raycaster's marching search (MCL3DL_NEAR_KD_K)
+  size_t near_max_bytes = size_t(256) << 20;  // MCL3DL_NEAR_MAX_MB
+  int near_info_k[2] = {0, 0};
+  uint64_t near_info_bytes[2] = {0, 0};
+  int timing = 1;            // record the per-call device timing events of mcl3dl_last_timing (MCL3DL_TIMING=0: skip them)
+  size_t zero_copy_max = 0;  // host path: kernels write the records of calls with <= this many particles per device
+                             // straight into the pinned result block (no D2H copy launch); MCL3DL_ZEROCOPY_OUT
   int mapping = 1;  // 1 = tuned kernels (lik_kernel_wi + beam_kernel_pl); 0 = the plain group kernels (MCL3DL_MAPPING=group)
 };
 
@@ -476,6 +499,36 @@ void fill_kd_scalars(const mcl3dl_beam_params& b, KdRayDev& k)
   k.sin_den = gmin * 2.0;  // :98
 }
 
+#if MCL3DL_NEAR_BITS
+// Near field for search radius r over the rescaled map points (device_funcs.cuh: NearBitsDev).  k == 0, or a box that
+// cannot be laid out within the byte cap, leaves `out.bits` null (the searches then run unscreened).
+int build_near_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mcl3dl_point* pts, uint32_t n, float wx,
+                     float wy, float wz, float r, int k, const float sc_min[3], const float sc_max[3], DevBuf& buf,
+                     NearBitsDev& out, int slot)
+{
+  out = NearBitsDev{};
+  eng->near_info_k[slot] = 0;
+  eng->near_info_bytes[slot] = 0;
+  NearBitsDev f{};
+  if (k <= 0 || !near_layout(f, r, k, sc_min, sc_max, eng->near_max_bytes))
+    return MCL3DL_OK;
+  const size_t bytes = static_cast<size_t>(f.pitch) * f.ny * f.nz * 4;
+  int rc = reserve(eng, buf, bytes);
+  if (rc != MCL3DL_OK)
+    return rc;
+  CK(cudaMemsetAsync(buf.p, 0, bytes, st));
+  near_mark_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, wx, wy, wz, f, static_cast<uint32_t*>(buf.p), k);
+  CK(cudaGetLastError());
+  eng->launches++;
+  f.bits = static_cast<const uint32_t*>(buf.p);
+  out = f;
+  c.map_bytes += bytes;
+  eng->near_info_k[slot] = k;
+  eng->near_info_bytes[slot] = bytes;
+  return MCL3DL_OK;
+}
+#endif
+
 // Build both grids on one device from the uploaded points.
 int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_pts, size_t n)
 {
@@ -633,6 +686,9 @@ int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_
     nn_row3_kernel<<<static_cast<unsigned>((row3_total + 255) / 256), 256, 0, st>>>(g, static_cast<uint2*>(c.nn_row3.p), row3_total);
     CKC(cudaGetLastError());
     eng->launches++;
+#if MCL3DL_NEAR_BITS
+    CKB(build_near_field(eng, c, st, pts, n32, wx, wy, wz, eng->likdev.rpad, eng->near_k, sc_min, sc_max, c.near_lik, g.near, 0));
+#endif
     c.nn = g;
     c.map_bytes += (cells + 1) * 4 + n * 16 + row3_total * sizeof(uint2);
     eng->info.nn_dims[0] = g.nx;
@@ -654,6 +710,10 @@ int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_
     }
     fill_dda_scalars(eng->beam, c.dda);
     fill_kd_scalars(eng->beam, c.kd);
+#if MCL3DL_NEAR_BITS
+    CKB(build_near_field(eng, c, st, pts, n32, wx, wy, wz, c.kd.r1_pad, eng->near_kd_k, sc_min, sc_max, c.near_kd, c.kd.near, 1));
+    c.near_kd_r = c.kd.r1_pad;
+#endif
     free_buf(c.raw_pts);
     c.raw_pts = d_pts;  // keep the upload
     d_pts = DevBuf();
@@ -794,6 +854,16 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     if (v >= 1.0f && v <= 4.0f)
       eng->nn_cell_factor = v;
   }
+  if (const char* v = std::getenv("MCL3DL_NEAR_K"))
+    eng->near_k = std::min(std::max(std::atoi(v), 0), 15);
+  if (const char* v = std::getenv("MCL3DL_NEAR_KD_K"))
+    eng->near_kd_k = std::min(std::max(std::atoi(v), 0), 15);
+  if (const char* v = std::getenv("MCL3DL_NEAR_MAX_MB"))
+    eng->near_max_bytes = static_cast<size_t>(std::max(std::atoi(v), 1)) << 20;
+  if (const char* v = std::getenv("MCL3DL_TIMING"))
+    eng->timing = std::atoi(v) != 0;
+  if (const char* v = std::getenv("MCL3DL_ZEROCOPY_OUT"))
+    eng->zero_copy_max = static_cast<size_t>(std::max(std::atol(v), 0L));
   if (const char* o = std::getenv("MCL3DL_OVERLAP"))
     eng->overlap = std::atoi(o) != 0;
   if (const char* m = std::getenv("MCL3DL_MAPPING"))
@@ -849,7 +919,7 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     cudaSetDevice(c.dev);
     if (c.stream)
       cudaStreamSynchronize(c.stream);
-    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.d_poses,
+    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.d_poses,
                       &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart})
       free_buf(*b);
     if (c.h_pinned)
@@ -935,7 +1005,23 @@ int mcl3dl_set_params(mcl3dl_engine* eng, const mcl3dl_lik_params* lik, const mc
       const float4* keep = c.kd.raw_pts;
       fill_kd_scalars(eng->beam, c.kd);
       c.kd.raw_pts = keep;
+#if MCL3DL_NEAR_BITS
+      if (c.kd.r1_pad > c.near_kd_r)
+        c.kd.near.bits = nullptr;  // the field was built for a smaller marching radius: search unscreened
+#endif
     }
+  }
+  return MCL3DL_OK;
+}
+
+int mcl3dl_near_field_info(const mcl3dl_engine* eng, int32_t k_out[2], uint64_t bytes_out[2])
+{
+  if (!eng || !k_out || !bytes_out)
+    return MCL3DL_ERR_INVALID_ARG;
+  for (int i = 0; i < 2; ++i)
+  {
+    k_out[i] = eng->near_info_k[i];
+    bytes_out[i] = eng->near_info_bytes[i];
   }
   return MCL3DL_OK;
 }
@@ -1070,21 +1156,29 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     if (b_lik) std::memcpy(hp + o_lik, lik_pts, b_lik);
     if (b_beam) std::memcpy(hp + o_beam, beam_pts, b_beam);
     if (n_origins) std::memcpy(hp + o_org, origins_xyz, n_origins * 12);
-    CK(cudaEventRecord(c.ev[0], st));
+    const bool timed = eng->timing != 0;
+    // small updates: the kernels store their records straight into the pinned block (cudaMallocHost memory is mapped
+    // into the unified address space), which saves the D2H copy launch; large ones keep the bulk copy
+    const bool zc = Pd <= eng->zero_copy_max;
+    if (timed) CK(cudaEventRecord(c.ev[0], st));
     CK(cudaMemcpyAsync(c.d_poses.p, hp, o_out, cudaMemcpyHostToDevice, st));
     const char* d_in = static_cast<const char*>(c.d_poses.p);
     const mcl3dl_pose* d_poses = reinterpret_cast<const mcl3dl_pose*>(d_in);
     const mcl3dl_point* d_lik = reinterpret_cast<const mcl3dl_point*>(d_in + o_lik);
     const mcl3dl_point* d_beam = reinterpret_cast<const mcl3dl_point*>(d_in + o_beam);
     const float* d_org = reinterpret_cast<const float*>(d_in + o_org);
-    CK(cudaEventRecord(c.ev[1], st));
-    rc = launch_models(eng, c, d_poses, Pd, d_lik, n_lik, d_beam, n_beam, d_org, n_origins, static_cast<mcl3dl_result*>(c.d_out.p),
-                       status ? static_cast<uint8_t*>(c.d_status.p) : nullptr, st, true);
+    if (timed) CK(cudaEventRecord(c.ev[1], st));
+    mcl3dl_result* k_out = zc ? reinterpret_cast<mcl3dl_result*>(hp + o_out) : static_cast<mcl3dl_result*>(c.d_out.p);
+    uint8_t* k_status = !status ? nullptr : (zc ? reinterpret_cast<uint8_t*>(hp + o_status) : static_cast<uint8_t*>(c.d_status.p));
+    rc = launch_models(eng, c, d_poses, Pd, d_lik, n_lik, d_beam, n_beam, d_org, n_origins, k_out, k_status, st, timed);
     if (rc != MCL3DL_OK) return rc;
-    CK(cudaEventRecord(c.ev[5], st));
-    CK(cudaMemcpyAsync(hp + o_out, c.d_out.p, b_out, cudaMemcpyDeviceToHost, st));
-    if (b_status) CK(cudaMemcpyAsync(hp + o_status, c.d_status.p, b_status, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(c.ev[4], st));
+    if (timed) CK(cudaEventRecord(c.ev[5], st));
+    if (!zc)
+    {
+      CK(cudaMemcpyAsync(hp + o_out, c.d_out.p, b_out, cudaMemcpyDeviceToHost, st));
+      if (b_status) CK(cudaMemcpyAsync(hp + o_status, c.d_status.p, b_status, cudaMemcpyDeviceToHost, st));
+    }
+    if (timed) CK(cudaEventRecord(c.ev[4], st));
   }
   eng->t_h2d = eng->t_lik = eng->t_beam = eng->t_d2h = 0;
   for (size_t d = 0; d < G; ++d)
@@ -1101,10 +1195,13 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     if (out) std::memcpy(out + p0[d], hp + o_out, Pd * sizeof(mcl3dl_result));
     if (status) std::memcpy(status + p0[d] * n_beam, hp + o_status, Pd * n_beam);
     float ms_h2d = 0, ms_lik = 0, ms_beam = 0, ms_d2h = 0;
-    CK(cudaEventElapsedTime(&ms_h2d, c.ev[0], c.ev[1]));
-    CK(cudaEventElapsedTime(&ms_lik, c.ev[2], c.ev[3]));
-    if (n_beam) CK(cudaEventElapsedTime(&ms_beam, c.ev_b0, c.ev_b1));
-    CK(cudaEventElapsedTime(&ms_d2h, c.ev[5], c.ev[4]));
+    if (eng->timing)
+    {
+      CK(cudaEventElapsedTime(&ms_h2d, c.ev[0], c.ev[1]));
+      CK(cudaEventElapsedTime(&ms_lik, c.ev[2], c.ev[3]));
+      if (n_beam) CK(cudaEventElapsedTime(&ms_beam, c.ev_b0, c.ev_b1));
+      CK(cudaEventElapsedTime(&ms_d2h, c.ev[5], c.ev[4]));
+    }
     eng->t_h2d = std::max(eng->t_h2d, static_cast<double>(ms_h2d));
     eng->t_beam = std::max(eng->t_beam, static_cast<double>(ms_beam));
     eng->t_lik = std::max(eng->t_lik, static_cast<double>(ms_lik));

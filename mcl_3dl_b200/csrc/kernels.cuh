@@ -322,7 +322,12 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
         hx = min(hx, g.nx - 1);
         hy = min(hy, min(g.ny - 1, ly + 2));
         hz = min(hz, min(g.nz - 1, lz + 2));
+#if MCL3DL_NEAR_BITS
+        // near-field screen: a far miss (most evals of a tracking update) costs one bit instead of the window fetch
+        if (lx <= hx && ly <= hy && lz <= hz && near_maybe(g.near, qx, qy, qz))
+#else
         if (lx <= hx && ly <= hy && lz <= hz)
+#endif
         {
           st_rows += static_cast<uint32_t>((hz - lz + 1) * (hy - ly + 1));
           // the whole 3x3 window from the y-fastest window table: 2 aligned 16-byte loads per z layer

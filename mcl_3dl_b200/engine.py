@@ -75,17 +75,17 @@ class WorkStats(C.Structure):
 EXPORTED_SYMBOLS = ["mcl3dl_measure_update", "mcl3dl_collect_stats", "mcl3dl_read_stats", "mcl3dl_abi_version", "mcl3dl_create", "mcl3dl_destroy", "mcl3dl_set_map", "mcl3dl_set_params",
                     "mcl3dl_measure", "mcl3dl_measure_device", "mcl3dl_beam_status",
                     "mcl3dl_beam_params_from_reference", "mcl3dl_get_map_info", "mcl3dl_last_timing",
-                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail"]
+                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info"]
 
-_LIB = None
+_LIBS = {}
 
 
-def load_library():
-    """Load (building if stale and nvcc is present) the in-tree CUDA library.  Raises if unavailable."""
-    global _LIB
-    if _LIB is not None:
-        return _LIB
-    path = os.environ.get("MCL3DL_LIB") or _build.LIB  # MCL3DL_LIB: an experiment variant built by build.build(out=...)
+def load_library(path=None):
+    """Load (building if stale and nvcc is present) the in-tree CUDA library.  Raises if unavailable.
+    `path` (or $MCL3DL_LIB) names an experiment variant built by build.build(out=...); libraries are cached per path."""
+    path = path or os.environ.get("MCL3DL_LIB") or _build.LIB
+    if path in _LIBS:
+        return _LIBS[path]
     if path == _build.LIB and _build.stale():
         try:
             _build.build()
@@ -117,8 +117,9 @@ def load_library():
     L.mcl3dl_strerror.restype = C.c_char_p
     L.mcl3dl_last_error_detail.argtypes = [vp]
     L.mcl3dl_last_error_detail.restype = C.c_char_p
+    L.mcl3dl_near_field_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
     assert L.mcl3dl_abi_version() == 2
-    _LIB = L
+    _LIBS[path] = L
     return L
 
 
@@ -144,8 +145,8 @@ def beam_params_from_reference(map_grid=(0.1, 0.1, 0.1), num_points_default=3, b
 class Engine:
     """Handle on mcl3dl_engine.  devices: list of CUDA ordinals (map replicated, particles split)."""
 
-    def __init__(self, devices=(0,)):
-        self.L = load_library()
+    def __init__(self, devices=(0,), lib_path=None):
+        self.L = load_library(lib_path)
         self.h = C.c_void_p()
         ids = (C.c_int * len(devices))(*devices)
         rc = self.L.mcl3dl_create(C.byref(self.h), ids, len(devices))
@@ -184,6 +185,13 @@ class Engine:
         self._check(self.L.mcl3dl_get_map_info(self.h, C.byref(mi)))
         return mi
 
+    def near_field_info(self):
+        """[(k, bytes)] of the near-field screens of the staged map: [0] likelihood search, [1] KD-tree raycaster."""
+        k = (C.c_int32 * 2)()
+        b = (C.c_uint64 * 2)()
+        self._check(self.L.mcl3dl_near_field_info(self.h, k, b))
+        return [(int(k[0]), int(b[0])), (int(k[1]), int(b[1]))]
+
     def measure(self, poses, lik_pts=None, beam_pts=None, origins=None, out=None):
         poses = np.ascontiguousarray(poses, dtype=POSE)
         lik_pts = np.ascontiguousarray(lik_pts if lik_pts is not None else np.zeros(0, POINT), dtype=POINT)
@@ -195,6 +203,34 @@ class Engine:
         self._check(self.L.mcl3dl_measure(self.h, _ptr(poses), len(poses), _ptr(lik_pts), len(lik_pts),
                                           _ptr(beam_pts), len(beam_pts), _ptr(origins), len(origins), _ptr(out)))
         return out
+
+    def bind_measure(self, poses, lik_pts, beam_pts, origins, out):
+        """A repeated update over the SAME host arrays (their contents may change between calls): resolves the buffer
+        addresses once and returns a zero-argument callable that runs mcl3dl_measure on them.  What a C++ caller does
+        anyway; it keeps ~20 us of numpy/ctypes argument marshalling out of every call.  The arrays must already have
+        the ABI dtypes and be C-contiguous (no hidden copies, or the call would read stale copies)."""
+        def chk(a, dt, name):
+            if a is None:
+                return np.zeros(0, dt)
+            if a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("%s must be a C-contiguous array of %s" % (name, dt))
+            return a
+        poses, lik_pts, beam_pts = chk(poses, POSE, "poses"), chk(lik_pts, POINT, "lik_pts"), chk(beam_pts, POINT, "beam_pts")
+        origins = chk(origins if origins is None else origins.reshape(-1, 3), np.dtype(np.float32), "origins")
+        out = chk(out, RESULT, "out")
+        if len(out) != len(poses):
+            raise ValueError("out must hold one record per particle")
+        keep = (poses, lik_pts, beam_pts, origins, out)  # the closure keeps the buffers alive
+        args = (self.h, _ptr(poses), len(poses), _ptr(lik_pts), len(lik_pts), _ptr(beam_pts), len(beam_pts), _ptr(origins),
+                len(origins.reshape(-1, 3)), _ptr(out))
+        fn = self.L.mcl3dl_measure
+
+        def call():
+            rc = fn(*args)
+            if rc != 0:
+                self._check(rc)
+            return keep[4]
+        return call
 
     def measure_update(self, poses, lik_pts, beam_pts, origins, prior, extra_likelihood=None, want_records=False):
         """Fused measurement + weight update (pf::ParticleFilter::measure with the node's lambda).

@@ -75,5 +75,11 @@ inline T __ldg(const T* p)
 {
   return *p;
 }
+inline unsigned int atomicOr(unsigned int* p, unsigned int v)  // single-threaded host build
+{
+  const unsigned int old = *p;
+  *p |= v;
+  return old;
+}
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }

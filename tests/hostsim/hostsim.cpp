@@ -7,6 +7,9 @@
 // window-table phase, reductions) are NOT covered here; the GPU parity suite covers those.
 // The grid construction below restates what engine.cu's build kernels do (same cell functions, same stable order).
 #include "cuda_shim.h"
+#ifndef MCL3DL_NEAR_BITS
+#define MCL3DL_NEAR_BITS 1  // the host build always carries the near-field screens; near_k = 0 switches them off at run time
+#endif
 
 #include <algorithm>
 #include <numeric>
@@ -23,14 +26,30 @@ struct HostMap
 {
   std::vector<uint32_t> nn_cell_start, dda_cell_start, occ;
   std::vector<float4> nn_pts, dda_pts, raw_pts;
+  std::vector<uint32_t> near_lik, near_kd;
   NnGridDev nn{};
   DdaGridDev dda{};
   KdRayDev kd{};
   LikDev lik{};
 };
 
+// engine.cu: build_near_field (same layout function, same marking function)
+void build_near(std::vector<uint32_t>& bits, NearBitsDev& out, const mcl3dl_point* pts, size_t n, float wx, float wy, float wz,
+                float r, int k, const float sc_min[3], const float sc_max[3])
+{
+  out = NearBitsDev{};
+  NearBitsDev f{};
+  if (k <= 0 || !near_layout(f, r, k, sc_min, sc_max, size_t(64) << 20))
+    return;
+  bits.assign(static_cast<size_t>(f.pitch) * f.ny * f.nz, 0u);
+  for (size_t i = 0; i < n; ++i)
+    near_mark_point(f, bits.data(), k, __fmul_rn(pts[i].x, wx), __fmul_rn(pts[i].y, wy), __fmul_rn(pts[i].z, wz));
+  f.bits = bits.data();
+  out = f;
+}
+
 void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_params* lp, const mcl3dl_beam_params* bp,
-           float cell_factor)
+           float cell_factor, int near_k, int near_kd_k)
 {
   const float wx = lp ? lp->dist_weight[0] : 1.0f, wy = lp ? lp->dist_weight[1] : 1.0f, wz = lp ? lp->dist_weight[2] : 1.0f;
   float raw_min[3], raw_max[3], sc_min[3], sc_max[3];
@@ -108,6 +127,7 @@ void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_param
     g.pts = m.nn_pts.data();
     g.row3 = nullptr;  // the window table is only read by the warp-cooperative kernel, not by these functions
     g.nyp = 0;
+    build_near(m.near_lik, g.near, pts, n, wx, wy, wz, m.lik.rpad, near_k, sc_min, sc_max);
     m.nn = g;
   }
   if (bp)
@@ -176,6 +196,7 @@ void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_param
       k.r1_pad = k.r1 * 1.0001f + 1e-6f;
       k.r2_pad = k.r2 * 1.0001f + 1e-6f;
       k.sin_den = gmin * 2.0;
+      build_near(m.near_kd, k.near, pts, n, wx, wy, wz, k.r1_pad, near_kd_k, sc_min, sc_max);
       m.kd = k;
     }
     m.dda = g;
@@ -183,10 +204,12 @@ void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_param
 }
 }  // namespace
 
-extern "C" int hostsim_measure(const mcl3dl_point* map, size_t n, const mcl3dl_lik_params* lp, const mcl3dl_beam_params* bp,
-                               float cell_factor, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts,
-                               size_t n_lik, const mcl3dl_point* beam_pts, size_t n_beam, const float* origins_xyz,
-                               size_t n_origins, mcl3dl_result* out, uint8_t* status)
+// near_k / near_kd_k: dilation of the near-field screens (0 = unscreened searches, i.e. MCL3DL_NEAR_K=0 on the device)
+extern "C" int hostsim_measure_nf(const mcl3dl_point* map, size_t n, const mcl3dl_lik_params* lp, const mcl3dl_beam_params* bp,
+                                  float cell_factor, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts,
+                                  size_t n_lik, const mcl3dl_point* beam_pts, size_t n_beam, const float* origins_xyz,
+                                  size_t n_origins, mcl3dl_result* out, uint8_t* status, int near_k, int near_kd_k,
+                                  uint64_t* work /* [5]: nn rows, nn pts, steps, occupied, tested; may be NULL */)
 {
   if ((n_lik && !lp) || (n_beam && !bp) || (bp && !bp->use_raycast_using_dda && !lp))
     return -1;
@@ -194,7 +217,8 @@ extern "C" int hostsim_measure(const mcl3dl_point* map, size_t n, const mcl3dl_l
     if (beam_pts[j].label >= n_origins)
       return -1;
   HostMap m;
-  build(m, map, n, lp, bp, cell_factor);
+  build(m, map, n, lp, bp, cell_factor, near_k, near_kd_k);
+  uint64_t wk[5] = {0, 0, 0, 0, 0};
   for (size_t p = 0; p < P; ++p)
   {
     F3 pos;
@@ -226,6 +250,9 @@ extern "C" int hostsim_measure(const mcl3dl_point* map, size_t n, const mcl3dl_l
       c += st == ST_LONG;
       if (status) status[p * n_beam + j] = static_cast<uint8_t>(st);
     }
+    wk[2] += s0;
+    wk[3] += s1;
+    wk[4] += s2;
     float score = 1.0f;
     if (n_beam)
     {
@@ -266,8 +293,21 @@ extern "C" int hostsim_measure(const mcl3dl_point* map, size_t n, const mcl3dl_l
       }
       r.score_like = sl;
       r.match_cnt = cnt;
+      wk[0] += rows;
+      wk[1] += npts;
     }
     if (out) out[p] = r;
   }
+  if (work)
+    for (int i = 0; i < 5; ++i) work[i] = wk[i];
   return 0;
+}
+
+extern "C" int hostsim_measure(const mcl3dl_point* map, size_t n, const mcl3dl_lik_params* lp, const mcl3dl_beam_params* bp,
+                               float cell_factor, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts,
+                               size_t n_lik, const mcl3dl_point* beam_pts, size_t n_beam, const float* origins_xyz,
+                               size_t n_origins, mcl3dl_result* out, uint8_t* status)
+{
+  return hostsim_measure_nf(map, n, lp, bp, cell_factor, poses, P, lik_pts, n_lik, beam_pts, n_beam, origins_xyz, n_origins, out,
+                            status, 2, 1, nullptr);
 }

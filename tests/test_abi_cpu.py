@@ -82,3 +82,40 @@ def test_bench_byte_model():
     import bench
     assert bench.bytes_per_eval_model() == (1200, 75)            # 5*5*3 cells at w=(1,1,5)
     assert bench.bytes_per_eval_model(w=(1, 1, 1)) == (2000, 125)
+
+
+def test_bound_measure_call_resolves_buffers_once():
+    """Engine.bind_measure hands mcl3dl_measure the addresses of the caller's own arrays (no hidden copies) and
+    refuses arrays that would need one."""
+    import numpy as np
+
+    from mcl_3dl_b200 import engine, synth
+
+    class FakeLib:
+        def __init__(self):
+            self.calls = []
+
+        def mcl3dl_measure(self, *a):
+            self.calls.append(a)
+            return 0
+
+    e = object.__new__(engine.Engine)
+    e.L, e.h = FakeLib(), 1
+    s = synth.scene(500, 8, 16, 4, seed=1)
+    out = np.zeros(8, dtype=synth.RESULT)
+    call = e.bind_measure(s["particles"], s["lik"], s["beam"], s["origins"], out)
+    assert call() is out and call() is out
+    a = e.L.calls[1]
+    assert (a[2], a[4], a[6], a[8]) == (8, 16, 4, len(s["origins"]))
+    assert a[1].value == s["particles"].ctypes.data and a[3].value == s["lik"].ctypes.data
+    assert a[5].value == s["beam"].ctypes.data and a[9].value == out.ctypes.data
+    lik_only = e.bind_measure(s["particles"], s["lik"], np.zeros(0, synth.POINT), None, out)
+    lik_only()
+    assert e.L.calls[-1][5] is None and e.L.calls[-1][6] == 0 and e.L.calls[-1][8] == 0
+    with pytest.raises(ValueError):
+        e.bind_measure(s["particles"][::2], s["lik"], None, None, out[:4])      # not contiguous
+    with pytest.raises(ValueError):
+        e.bind_measure(s["particles"], np.zeros(4, np.float32), None, None, out)  # wrong dtype
+    with pytest.raises(ValueError):
+        e.bind_measure(s["particles"], s["lik"], None, None, out[:4])           # one record per particle
+    e.h = None  # nothing to destroy

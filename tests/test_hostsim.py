@@ -32,9 +32,10 @@ def hostsim():
         assert r.returncode == 0, r.stderr
     L = C.CDLL(LIB)
     vp, sz = C.c_void_p, C.c_size_t
-    L.hostsim_measure.argtypes = [vp, sz, vp, vp, C.c_float, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp]
+    L.hostsim_measure_nf.argtypes = [vp, sz, vp, vp, C.c_float, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, C.c_int, C.c_int, vp]
 
-    def run(map_pts, lik, beam, poses, lik_pts, beam_pts, origins):
+    def run(map_pts, lik, beam, poses, lik_pts, beam_pts, origins, near=(2, 1), work=False):
+        """near = dilation of the (likelihood, KD-caster) near-field screens; 0 = the unscreened searches."""
         map_pts = np.ascontiguousarray(map_pts, dtype=synth.POINT)
         poses = np.ascontiguousarray(poses, dtype=synth.POSE)
         lik_pts = np.ascontiguousarray(lik_pts if lik_pts is not None else np.zeros(0, synth.POINT), dtype=synth.POINT)
@@ -42,11 +43,15 @@ def hostsim():
         origins = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
         out = np.zeros(len(poses), dtype=synth.RESULT)
         st = np.zeros((len(poses), max(len(beam_pts), 1)), dtype=np.uint8)
+        wk = np.zeros(5, dtype=np.uint64)
         p = lambda a: a.ctypes.data_as(vp) if a.size else None  # noqa: E731
-        rc = L.hostsim_measure(p(map_pts), len(map_pts), C.byref(lik) if lik is not None else None,
-                               C.byref(beam) if beam is not None else None, 1.0, p(poses), len(poses), p(lik_pts),
-                               len(lik_pts), p(beam_pts), len(beam_pts), p(origins), len(origins), p(out), p(st))
+        rc = L.hostsim_measure_nf(p(map_pts), len(map_pts), C.byref(lik) if lik is not None else None,
+                                  C.byref(beam) if beam is not None else None, 1.0, p(poses), len(poses), p(lik_pts),
+                                  len(lik_pts), p(beam_pts), len(beam_pts), p(origins), len(origins), p(out), p(st),
+                                  near[0], near[1], p(wk))
         assert rc == 0
+        if work:
+            return out, st[:, :len(beam_pts)], wk
         return out, st[:, :len(beam_pts)]
     return run
 
@@ -82,6 +87,24 @@ def test_device_functions_on_host_match_reference_goldens(hostsim, name):
     for f in got.dtype.names:
         assert np.array_equal(got[f], g["result"][f]), f
     assert np.array_equal(st, g["status"])
+
+
+@pytest.mark.parametrize("near", [(1, 1), (2, 2), (3, 1), (4, 3)])
+@pytest.mark.parametrize("seed,w,spread,use_dda", [(11, (1, 1, 1), False, False), (12, (1, 1, 5), True, False),
+                                                    (13, (2, 1, 3), False, True), (14, (1, 1, 5), True, True)])
+def test_near_field_screens_change_no_result(hostsim, near, seed, w, spread, use_dda):
+    """The near-field bits only skip searches that cannot succeed: records and per-ray status are identical with
+    and without them, for several dilations, while the work counters drop."""
+    s = synth.scene(30_000, 24, 40, 16, spread=spread, seed=seed)
+    lik = engine.LikParams(dist_weight=w, match_dist_min=0.2 if seed % 2 else 0.35)
+    beam = engine.beam_params_from_reference(num_points_default=16, use_raycast_using_dda=use_dda)
+    ref, st_ref, wk_ref = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(0, 0), work=True)
+    got, st, wk = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=near, work=True)
+    assert got.tobytes() == ref.tobytes()
+    assert np.array_equal(st, st_ref)
+    assert wk[0] < wk_ref[0] and wk[1] <= wk_ref[1]          # likelihood: fewer windows opened
+    if not use_dda:
+        assert wk[4] < wk_ref[4] and wk[3] == wk_ref[3]      # KD caster: fewer points tested, same collisions
 
 
 def test_device_functions_survive_garbage_inputs_under_sanitizers(tmp_path):
