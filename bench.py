@@ -343,10 +343,14 @@ def main():
     eng.collect_stats(False)
     io_bytes = P_rank * 32 + P_rank * 24
     bpe, cells = bytes_per_eval_model()
+    near = eng.near_field_info()  # [(k, bytes)] likelihood / KD-caster screens; k = 0: not staged
     if dom == "lik":
         alg_bytes = ws["lik_index_rows"] * 8 + ws["lik_points_scanned"] * 16 + io_bytes + n_lik * 16
         note = ("counted: %.1f CSR rows x 8 B + %.1f map points x 16 B per eval (+ poses/scan/records)"
                 % (ws["lik_index_rows"] / max(P_rank * n_lik, 1), ws["lik_points_scanned"] / max(P_rank * n_lik, 1)))
+        if near[0][0]:
+            alg_bytes += P_rank * n_lik * 4
+            note += " + one 4 B near-field word per eval (k=%d, %.0f MB)" % (near[0][0], near[0][1] / 1e6)
         survey_bytes = P_rank * n_lik * bpe + io_bytes + n_lik * 16
         survey_note = "SURVEY 8d exact mode, dense float4 voxel grid: %d B/eval = 16 B x %d cells" % (bpe, cells)
     else:

@@ -1,0 +1,174 @@
+#!/usr/bin/env python
+"""A/B sweep of engine variants on one GPU, sized for a ~1 minute box slot (no torch import).
+
+    python profiles/ab_variants.py --out gpurun_out/r01y_ab.jsonl [--budget 60]
+
+For every (workload, variant) job: create an engine from the variant's library with the variant's environment,
+stage the map, run the host-buffer call (mcl3dl_measure through Engine.bind_measure) a few dozen times and report
+  * whether the records are BYTE-IDENTICAL to the baseline variant's on the same inputs,
+  * median kernel time (CUDA events of the engine, when its timing events are on) and median e2e wall time.
+The work runs in a child process that prints one JSON line per job; if the child dies or hangs in a variant the
+parent records that and restarts it on the remaining jobs, so one bad variant cannot take the sweep down.
+Numbers: warm L2 (no flush between calls), wall clock around a synchronous call — for A/B ranking only; the
+bench.py contract numbers stay the reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PKG = os.path.join(ROOT, "mcl_3dl_b200")
+BASE_LIB = os.path.join(PKG, "libmcl3dl_b200.so")
+NB_LIB = os.path.join(PKG, "libmcl3dl_b200_nb.so")
+
+# name -> (library, environment).  "base" must come first: everything else is compared with its records.
+VARIANTS = [
+    ("base", BASE_LIB, {}),
+    ("nb", NB_LIB, {}),                                               # near-field screens, k = 2 (lik) / 1 (KD)
+    ("nb_fast_host", NB_LIB, {"MCL3DL_TIMING": "0", "MCL3DL_ZEROCOPY_OUT": "8192"}),   # the candidate default
+    ("timing_off", BASE_LIB, {"MCL3DL_TIMING": "0"}),
+    ("zerocopy", BASE_LIB, {"MCL3DL_ZEROCOPY_OUT": "1000000"}),
+    ("nb_k1", NB_LIB, {"MCL3DL_NEAR_K": "1"}),
+    ("nb_k3_kd2", NB_LIB, {"MCL3DL_NEAR_K": "3", "MCL3DL_NEAR_KD_K": "2", "MCL3DL_NEAR_MAX_MB": "512"}),
+    ("nb_group", NB_LIB, {"MCL3DL_MAPPING": "group"}),                # the plain kernels with the screens
+    ("base_group", BASE_LIB, {"MCL3DL_MAPPING": "group"}),
+]
+# workload -> (bench workload, raycaster, spread override)
+WORKLOADS = [("c2", "c2", "dda", False), ("c3kd", "c3", "kd", False), ("c5", "c5", "dda", False),
+             ("c1kd", "c1", "kd", False), ("c2s", "c2", "dda", True), ("c3", "c3", "dda", False)]
+ENV_KEYS = ["MCL3DL_TIMING", "MCL3DL_ZEROCOPY_OUT", "MCL3DL_NEAR_K", "MCL3DL_NEAR_KD_K", "MCL3DL_NEAR_MAX_MB",
+            "MCL3DL_MAPPING"]
+
+
+def jobs_all():
+    return [(w[0], v[0]) for w in WORKLOADS for v in VARIANTS]
+
+
+def child(job_names, calls):
+    import bench
+    from mcl_3dl_b200 import engine, synth
+    variants = {v[0]: v for v in VARIANTS}
+    workloads = {w[0]: w for w in WORKLOADS}
+    scenes = {}
+    for wname, vname in job_names:
+        _, bw, caster, spread = workloads[wname]
+        _, lib, env = variants[vname]
+        if wname not in scenes:
+            bench.FORCE_SPREAD = spread
+            s, dda, _, _ = bench.build_scene(bw, 0, 1)
+            bench.FORCE_SPREAD = False
+            scenes = {wname: (s, dda)}  # keep one scene in memory at a time
+        s, dda = scenes[wname]
+        n_lik, n_beam = len(s["lik"]), len(s["beam"])
+        for k in ENV_KEYS:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        rec = {"workload": wname, "variant": vname}
+        if not os.path.exists(lib):
+            rec["error"] = "library not built"
+            print(json.dumps(rec), flush=True)
+            continue
+        print(json.dumps({"start": [wname, vname]}), flush=True)
+        eng = engine.Engine((0,), lib_path=lib)
+        lik = engine.LikParams(dist_weight=bench.DIST_WEIGHT) if (n_lik or caster == "kd") else None
+        beam = (engine.beam_params_from_reference(num_points_default=max(n_beam, 1), dda_grid_size=dda,
+                                                  use_raycast_using_dda=(caster == "dda")) if n_beam else None)
+        eng.set_map(s["map"], stamp=1, lik=lik, beam=beam)
+        out = np.zeros(len(s["particles"]), dtype=synth.RESULT)
+        poses = np.ascontiguousarray(s["particles"], dtype=synth.POSE)
+        call = eng.bind_measure(poses, np.ascontiguousarray(s["lik"], dtype=synth.POINT),
+                                np.ascontiguousarray(s["beam"], dtype=synth.POINT),
+                                np.ascontiguousarray(s["origins"], dtype=np.float32).reshape(-1, 3), out)
+        for _ in range(4):
+            call()
+        wall, k_lik, k_beam = [], [], []
+        timed = env.get("MCL3DL_TIMING", "1") != "0"
+        for _ in range(calls):
+            t0 = time.perf_counter()
+            call()
+            wall.append(time.perf_counter() - t0)
+            if timed:
+                lt = eng.last_timing()
+                k_lik.append(lt["lik_ms"])
+                k_beam.append(lt["beam_ms"])
+        base_path = "/tmp/ab_base_%s.npy" % wname
+        if vname == "base":
+            np.save(base_path, out)
+            rec["identical_to_base"] = True
+        elif os.path.exists(base_path):
+            rec["identical_to_base"] = bool(np.load(base_path).tobytes() == out.tobytes())
+        else:
+            rec["identical_to_base"] = None
+        units = len(poses) * (n_lik if n_lik else n_beam)
+        rec.update({"e2e_us_median": 1e6 * float(np.median(wall)), "e2e_us_min": 1e6 * float(np.min(wall)),
+                    "e2e_units_per_s": units / float(np.median(wall)),
+                    "lik_kernel_us": 1e3 * float(np.median(k_lik)) if k_lik and n_lik else None,
+                    "beam_kernel_us": 1e3 * float(np.median(k_beam)) if k_beam and n_beam else None,
+                    "near_field": eng.near_field_info(), "build_ms": eng.map_info().build_ms,
+                    "match_cnt_sum": int(out["match_cnt"].sum()), "n_hit_sum": int(out["n_hit"].sum()), "calls": calls})
+        eng.close()
+        print(json.dumps(rec), flush=True)
+
+
+def parent(out_path, budget, calls, only):
+    t_start = time.time()
+    jobs = [j for j in jobs_all() if not only or j[0] in only]
+    os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
+    f = open(out_path, "w")
+    while jobs and time.time() - t_start < budget:
+        left = budget - (time.time() - t_start)
+        p = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--child", json.dumps(jobs), "--calls", str(calls)],
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        try:
+            so, se = p.communicate(timeout=max(left, 1.0))
+            died = p.returncode != 0
+        except subprocess.TimeoutExpired:
+            p.kill()
+            so, se = p.communicate()
+            died = True
+        started = None
+        for line in so.splitlines():
+            try:
+                r = json.loads(line)
+            except ValueError:
+                continue
+            if "start" in r:
+                started = tuple(r["start"])
+                continue
+            f.write(json.dumps(r) + "\n")
+            f.flush()
+            jobs.remove((r["workload"], r["variant"]))
+            started = None
+        if died:
+            bad = started if started in jobs else (jobs[0] if jobs else None)
+            if bad:
+                f.write(json.dumps({"workload": bad[0], "variant": bad[1], "error": "child died or timed out",
+                                    "stderr_tail": se[-600:]}) + "\n")
+                f.flush()
+                jobs.remove(bad)
+    for j in jobs:
+        f.write(json.dumps({"workload": j[0], "variant": j[1], "error": "not run (time budget)"}) + "\n")
+    f.write(json.dumps({"elapsed_s": time.time() - t_start}) + "\n")
+    f.close()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ab_variants.jsonl"))
+    ap.add_argument("--budget", type=float, default=60.0, help="seconds of wall clock for the whole sweep")
+    ap.add_argument("--calls", type=int, default=30)
+    ap.add_argument("--only", default="", help="comma-separated workload names")
+    ap.add_argument("--child", default=None)
+    a = ap.parse_args()
+    if a.child is not None:
+        child([tuple(j) for j in json.loads(a.child)], a.calls)
+    else:
+        parent(a.out, a.budget, a.calls, [w for w in a.only.split(",") if w])
