@@ -231,7 +231,10 @@ int mcl3dl_collect_stats(mcl3dl_engine*, int enable);
 int mcl3dl_read_stats(mcl3dl_engine*, mcl3dl_work_stats* out);
 
 /* Device times of the last mcl3dl_measure call (CUDA events on the engine's stream, max over
- * devices): host->device copies, the two kernels, device->host copy. */
+ * devices): host->device copies, the two kernels, device->host copy.  The events cost ~28 us per update
+ * (measured, profiles/r01y_ab_variants.txt), so they are only recorded after mcl3dl_collect_timing(eng, 1)
+ * (or with MCL3DL_TIMING=1 in the environment); otherwise the four values read 0. */
+int mcl3dl_collect_timing(mcl3dl_engine*, int enable);
 int mcl3dl_last_timing(const mcl3dl_engine*, double* h2d_ms, double* lik_kernel_ms, double* beam_kernel_ms,
                        double* d2h_ms);
 

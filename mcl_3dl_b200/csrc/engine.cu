@@ -240,9 +240,11 @@ struct mcl3dl_engine
   size_t near_max_bytes = size_t(256) << 20;  // MCL3DL_NEAR_MAX_MB
   int near_info_k[2] = {0, 0};
   uint64_t near_info_bytes[2] = {0, 0};
-  int timing = 1;            // record the per-call device timing events of mcl3dl_last_timing (MCL3DL_TIMING=0: skip them)
-  size_t zero_copy_max = 0;  // host path: kernels write the records of calls with <= this many particles per device
-                             // straight into the pinned result block (no D2H copy launch); MCL3DL_ZEROCOPY_OUT
+  // Host-path choices measured in profiles/r01y_ab_variants.txt (c2 e2e 102 -> 71 us per update with both):
+  int timing = 0;               // the per-call timing events of mcl3dl_last_timing cost ~28 us per update: off unless
+                                // mcl3dl_collect_timing(eng, 1) or MCL3DL_TIMING=1
+  size_t zero_copy_max = 8192;  // the kernels of updates with <= this many particles per device store their records
+                                // straight into the pinned result block (no D2H copy launch); MCL3DL_ZEROCOPY_OUT
   int mapping = 1;  // 1 = tuned kernels (lik_kernel_wi + beam_kernel_pl); 0 = the plain group kernels (MCL3DL_MAPPING=group)
 };
 
@@ -1159,7 +1161,7 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     const bool timed = eng->timing != 0;
     // small updates: the kernels store their records straight into the pinned block (cudaMallocHost memory is mapped
     // into the unified address space), which saves the D2H copy launch; large ones keep the bulk copy
-    const bool zc = Pd <= eng->zero_copy_max;
+    const bool zc = !status && Pd <= eng->zero_copy_max;  // (per-ray status bytes would be scattered 1-byte PCIe writes)
     if (timed) CK(cudaEventRecord(c.ev[0], st));
     CK(cudaMemcpyAsync(c.d_poses.p, hp, o_out, cudaMemcpyHostToDevice, st));
     const char* d_in = static_cast<const char*>(c.d_poses.p);
@@ -1169,7 +1171,7 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     const float* d_org = reinterpret_cast<const float*>(d_in + o_org);
     if (timed) CK(cudaEventRecord(c.ev[1], st));
     mcl3dl_result* k_out = zc ? reinterpret_cast<mcl3dl_result*>(hp + o_out) : static_cast<mcl3dl_result*>(c.d_out.p);
-    uint8_t* k_status = !status ? nullptr : (zc ? reinterpret_cast<uint8_t*>(hp + o_status) : static_cast<uint8_t*>(c.d_status.p));
+    uint8_t* k_status = status ? static_cast<uint8_t*>(c.d_status.p) : nullptr;
     rc = launch_models(eng, c, d_poses, Pd, d_lik, n_lik, d_beam, n_beam, d_org, n_origins, k_out, k_status, st, timed);
     if (rc != MCL3DL_OK) return rc;
     if (timed) CK(cudaEventRecord(c.ev[5], st));
@@ -1399,6 +1401,16 @@ int mcl3dl_collect_stats(mcl3dl_engine* eng, int enable)
     CK(cudaMemset(c.d_stats.p, 0, 5 * sizeof(unsigned long long)));
     c.stats_on = enable != 0;
   }
+  return MCL3DL_OK;
+}
+
+int mcl3dl_collect_timing(mcl3dl_engine* eng, int enable)
+{
+  if (!eng)
+    return MCL3DL_ERR_INVALID_ARG;
+  eng->timing = enable != 0;
+  if (!enable)
+    eng->t_h2d = eng->t_lik = eng->t_beam = eng->t_d2h = 0;
   return MCL3DL_OK;
 }
 

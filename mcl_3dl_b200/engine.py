@@ -75,7 +75,7 @@ class WorkStats(C.Structure):
 EXPORTED_SYMBOLS = ["mcl3dl_measure_update", "mcl3dl_collect_stats", "mcl3dl_read_stats", "mcl3dl_abi_version", "mcl3dl_create", "mcl3dl_destroy", "mcl3dl_set_map", "mcl3dl_set_params",
                     "mcl3dl_measure", "mcl3dl_measure_device", "mcl3dl_beam_status",
                     "mcl3dl_beam_params_from_reference", "mcl3dl_get_map_info", "mcl3dl_last_timing",
-                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info"]
+                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_collect_timing"]
 
 _LIBS = {}
 
@@ -117,6 +117,7 @@ def load_library(path=None):
     L.mcl3dl_strerror.restype = C.c_char_p
     L.mcl3dl_last_error_detail.argtypes = [vp]
     L.mcl3dl_last_error_detail.restype = C.c_char_p
+    L.mcl3dl_collect_timing.argtypes = [vp, C.c_int]
     L.mcl3dl_near_field_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
     assert L.mcl3dl_abi_version() == 2
     _LIBS[path] = L
@@ -273,6 +274,10 @@ class Engine:
         ws = WorkStats()
         self._check(self.L.mcl3dl_read_stats(self.h, C.byref(ws)))
         return ws.as_dict()
+
+    def collect_timing(self, enable=True):
+        """Record the per-call CUDA timing events read by last_timing() (off by default: ~28 us per update)."""
+        self._check(self.L.mcl3dl_collect_timing(self.h, 1 if enable else 0))
 
     def last_timing(self):
         v = [C.c_double(0) for _ in range(4)]

@@ -26,20 +26,22 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 PKG = os.path.join(ROOT, "mcl_3dl_b200")
-BASE_LIB = os.path.join(PKG, "libmcl3dl_b200.so")
-NB_LIB = os.path.join(PKG, "libmcl3dl_b200_nb.so")
+NB_LIB = os.path.join(PKG, "libmcl3dl_b200.so")          # the default build (near-field screens compiled in)
+BASE_LIB = os.path.join(PKG, "libmcl3dl_b200_nb0.so")    # build.build(defines=["MCL3DL_NEAR_BITS=0"], out=...)
+OLD_HOST = {"MCL3DL_TIMING": "1", "MCL3DL_ZEROCOPY_OUT": "0"}  # the host path as it was up to r01x
 
-# name -> (library, environment).  "base" must come first: everything else is compared with its records.
+# name -> (library, environment); every variant states the host-path switches explicitly, so the table does not
+# depend on the engine's defaults.  "base" (the r01x engine) must come first: everything is compared with its records.
 VARIANTS = [
-    ("base", BASE_LIB, {}),
-    ("nb", NB_LIB, {}),                                               # near-field screens, k = 2 (lik) / 1 (KD)
-    ("nb_fast_host", NB_LIB, {"MCL3DL_TIMING": "0", "MCL3DL_ZEROCOPY_OUT": "8192"}),   # the candidate default
-    ("timing_off", BASE_LIB, {"MCL3DL_TIMING": "0"}),
-    ("zerocopy", BASE_LIB, {"MCL3DL_ZEROCOPY_OUT": "1000000"}),
-    ("nb_k1", NB_LIB, {"MCL3DL_NEAR_K": "1"}),
-    ("nb_k3_kd2", NB_LIB, {"MCL3DL_NEAR_K": "3", "MCL3DL_NEAR_KD_K": "2", "MCL3DL_NEAR_MAX_MB": "512"}),
-    ("nb_group", NB_LIB, {"MCL3DL_MAPPING": "group"}),                # the plain kernels with the screens
-    ("base_group", BASE_LIB, {"MCL3DL_MAPPING": "group"}),
+    ("base", BASE_LIB, dict(OLD_HOST)),
+    ("nb", NB_LIB, dict(OLD_HOST)),                                   # near-field screens, k = 2 (lik) / 1 (KD)
+    ("nb_fast_host", NB_LIB, {"MCL3DL_TIMING": "0", "MCL3DL_ZEROCOPY_OUT": "8192"}),   # = today's defaults
+    ("timing_off", BASE_LIB, {"MCL3DL_TIMING": "0", "MCL3DL_ZEROCOPY_OUT": "0"}),
+    ("zerocopy", BASE_LIB, {"MCL3DL_TIMING": "1", "MCL3DL_ZEROCOPY_OUT": "1000000"}),
+    ("nb_k1", NB_LIB, dict(OLD_HOST, MCL3DL_NEAR_K="1")),
+    ("nb_k3_kd2", NB_LIB, dict(OLD_HOST, MCL3DL_NEAR_K="3", MCL3DL_NEAR_KD_K="2", MCL3DL_NEAR_MAX_MB="512")),
+    ("nb_group", NB_LIB, dict(OLD_HOST, MCL3DL_MAPPING="group")),     # the plain kernels with the screens
+    ("base_group", BASE_LIB, dict(OLD_HOST, MCL3DL_MAPPING="group")),
 ]
 # workload -> (bench workload, raycaster, spread override)
 WORKLOADS = [("c2", "c2", "dda", False), ("c3kd", "c3", "kd", False), ("c5", "c5", "dda", False),
@@ -90,7 +92,7 @@ def child(job_names, calls):
         for _ in range(4):
             call()
         wall, k_lik, k_beam = [], [], []
-        timed = env.get("MCL3DL_TIMING", "1") != "0"
+        timed = env.get("MCL3DL_TIMING", "0") != "0"
         for _ in range(calls):
             t0 = time.perf_counter()
             call()
