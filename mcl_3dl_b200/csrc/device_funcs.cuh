@@ -17,6 +17,14 @@
 #ifndef MCL3DL_NEAR_BITS
 #define MCL3DL_NEAR_BITS 1
 #endif
+// MCL3DL_KD_SKIP=1 adds a second, coarser field to the KD-tree raycaster that proves several marching steps clear at
+// once (cast_ray_kd).  Host-verified (tests/hostsim), not yet measured on a GPU: off by default.
+#ifndef MCL3DL_KD_SKIP
+#define MCL3DL_KD_SKIP 0
+#endif
+#if MCL3DL_KD_SKIP && !MCL3DL_NEAR_BITS
+#error "MCL3DL_KD_SKIP needs MCL3DL_NEAR_BITS"
+#endif
 
 namespace mcl3dl
 {
@@ -178,6 +186,10 @@ struct KdRayDev
   double sin_den;           // map_grid_min_ * 2.0 (:98)
 #if MCL3DL_NEAR_BITS
   NearBitsDev near;  // built for the marching search radius (r1_pad)
+#endif
+#if MCL3DL_KD_SKIP
+  NearBitsDev far;   // built for a larger radius R2: a clear bit proves the next few marching steps clear as well
+  float far_margin;  // 0.98 * (R2 - r1_pad): how far (rescaled metric) the march may move and still be covered
 #endif
 };
 
@@ -450,9 +462,38 @@ __device__ __forceinline__ int cast_ray_kd(const KdRayDev& k, const NnGridDev& n
   pos.x = fadd(b.x, inc.x);
   pos.y = fadd(b.y, inc.y);
   pos.z = fadd(b.z, inc.z);
+#if MCL3DL_KD_SKIP
+  // Steps that a clear bit of the far field covers: the march moves |inc * w| per step in the rescaled metric (plus the
+  // rounding of the sequential adds, bounded generously by 1e-5 |q| per step), and a map point within r1 of a later
+  // position would be within far_margin + r1 of this one.
+  const float step_w = __fsqrt_rn(fadd(fadd(fmul(fmul(inc.x, nn.wx), fmul(inc.x, nn.wx)), fmul(fmul(inc.y, nn.wy), fmul(inc.y, nn.wy))),
+                                      fmul(fmul(inc.z, nn.wz), fmul(inc.z, nn.wz))));
+#endif
   // getNextCastResult, :66-110
   for (int count = 1; count < length; ++count)
   {
+#if MCL3DL_KD_SKIP
+    if (k.far.bits)
+    {
+      const float fx = fmul(pos.x, nn.wx), fy = fmul(pos.y, nn.wy), fz = fmul(pos.z, nn.wz);
+      if (!near_maybe(k.far, fx, fy, fz))
+      {
+        const float per_step = fadd(step_w, fmul(1e-5f, fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fmaxf(fabsf(fz), 1.0f))));
+        // this position and the next `extra` ones cannot collide: advance over them with the same sequential adds
+        const int extra = min(__float2int_rz(fdiv(k.far_margin, per_step)), 64);
+        const int adv = min(extra + 1, length - count);
+        for (int i = 0; i < adv; ++i)
+        {
+          ++n_steps;
+          pos.x = fadd(pos.x, inc.x);
+          pos.y = fadd(pos.y, inc.y);
+          pos.z = fadd(pos.z, inc.z);
+        }
+        count += adv - 1;  // the loop header adds the last one
+        continue;
+      }
+    }
+#endif
     ++n_steps;
     float d2;
     uint32_t id;

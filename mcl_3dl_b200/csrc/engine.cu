@@ -197,8 +197,9 @@ struct DeviceCtx
   DdaGridDev dda{};
   KdRayDev kd{};
   DevBuf raw_pts;  // map points in original order (KD-tree raycaster only)
-  DevBuf near_lik, near_kd;  // near-field bits (MCL3DL_NEAR_BITS builds)
-  float near_kd_r = 0.0f;    // radius the KD field was built for
+  DevBuf near_lik, near_kd, far_kd;  // near-field bits (MCL3DL_NEAR_BITS builds; far_kd: MCL3DL_KD_SKIP builds)
+  float near_kd_r = 0.0f;            // radius the KD field was built for
+  float far_kd_r = 0.0f;             // radius of the skip-ahead field
   size_t map_bytes = 0;
   // per-update I/O
   DevBuf d_poses /* whole input block of the host path */, d_out, d_status;
@@ -238,8 +239,9 @@ struct mcl3dl_engine
   int near_k = 2;     // near-field dilation of the likelihood screen (MCL3DL_NEAR_K, 0 = no field)
   int near_kd_k = 1;  // same for the KD-tree raycaster's marching search (MCL3DL_NEAR_KD_K)
   size_t near_max_bytes = size_t(256) << 20;  // MCL3DL_NEAR_MAX_MB
-  int near_info_k[2] = {0, 0};
-  uint64_t near_info_bytes[2] = {0, 0};
+  int kd_skip_steps = 4;  // marching steps (along the least-weighted axis) the skip-ahead field covers; MCL3DL_KD_SKIP_STEPS
+  int near_info_k[3] = {0, 0, 0};  // [2]: skip-ahead field of the KD-tree raycaster
+  uint64_t near_info_bytes[3] = {0, 0, 0};
   // Host-path choices measured in profiles/r01y_ab_variants.txt (c2 e2e 102 -> 71 us per update with both):
   int timing = 0;               // the per-call timing events of mcl3dl_last_timing cost ~28 us per update: off unless
                                 // mcl3dl_collect_timing(eng, 1) or MCL3DL_TIMING=1
@@ -716,6 +718,17 @@ int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_
     CKB(build_near_field(eng, c, st, pts, n32, wx, wy, wz, c.kd.r1_pad, eng->near_kd_k, sc_min, sc_max, c.near_kd, c.kd.near, 1));
     c.near_kd_r = c.kd.r1_pad;
 #endif
+#if MCL3DL_KD_SKIP
+    {
+      // skip-ahead field: radius = marching radius + kd_skip_steps steps along the least-weighted axis
+      const float wmin = std::min(wx, std::min(wy, wz));
+      const float reach = static_cast<float>(eng->kd_skip_steps) * c.kd.grid_min * wmin;
+      c.far_kd_r = c.kd.r1_pad + reach / 0.98f;
+      CKB(build_near_field(eng, c, st, pts, n32, wx, wy, wz, c.far_kd_r, eng->kd_skip_steps > 0 ? 1 : 0, sc_min, sc_max, c.far_kd,
+                           c.kd.far, 2));
+      c.kd.far_margin = 0.98f * (c.far_kd_r - c.kd.r1_pad);
+    }
+#endif
     free_buf(c.raw_pts);
     c.raw_pts = d_pts;  // keep the upload
     d_pts = DevBuf();
@@ -860,6 +873,8 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     eng->near_k = std::min(std::max(std::atoi(v), 0), 15);
   if (const char* v = std::getenv("MCL3DL_NEAR_KD_K"))
     eng->near_kd_k = std::min(std::max(std::atoi(v), 0), 15);
+  if (const char* v = std::getenv("MCL3DL_KD_SKIP_STEPS"))
+    eng->kd_skip_steps = std::min(std::max(std::atoi(v), 0), 64);
   if (const char* v = std::getenv("MCL3DL_NEAR_MAX_MB"))
     eng->near_max_bytes = static_cast<size_t>(std::max(std::atoi(v), 1)) << 20;
   if (const char* v = std::getenv("MCL3DL_TIMING"))
@@ -921,7 +936,7 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     cudaSetDevice(c.dev);
     if (c.stream)
       cudaStreamSynchronize(c.stream);
-    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.d_poses,
+    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.far_kd, &c.d_poses,
                       &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart})
       free_buf(*b);
     if (c.h_pinned)
@@ -1010,6 +1025,11 @@ int mcl3dl_set_params(mcl3dl_engine* eng, const mcl3dl_lik_params* lik, const mc
 #if MCL3DL_NEAR_BITS
       if (c.kd.r1_pad > c.near_kd_r)
         c.kd.near.bits = nullptr;  // the field was built for a smaller marching radius: search unscreened
+#endif
+#if MCL3DL_KD_SKIP
+      c.kd.far_margin = 0.98f * (c.far_kd_r - c.kd.r1_pad);  // the step length is read per ray (grid_min may have changed)
+      if (!(c.kd.far_margin > 0.0f))
+        c.kd.far.bits = nullptr;
 #endif
     }
   }

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """A/B sweep of engine variants on one GPU, sized for a ~1 minute box slot (no torch import).
 
-    python profiles/ab_variants.py --out gpurun_out/r01y_ab.jsonl [--budget 60]
+    python profiles/ab_variants.py --build-variants                 # here (nvcc, no GPU): the variant libraries
+    python profiles/ab_variants.py --out gpurun_out/r01y_ab.jsonl [--budget 60]   # on the GPU box
 
 For every (workload, variant) job: create an engine from the variant's library with the variant's environment,
 stage the map, run the host-buffer call (mcl3dl_measure through Engine.bind_measure) a few dozen times and report
@@ -28,7 +29,9 @@ if ROOT not in sys.path:
 PKG = os.path.join(ROOT, "mcl_3dl_b200")
 NB_LIB = os.path.join(PKG, "libmcl3dl_b200.so")          # the default build (near-field screens compiled in)
 BASE_LIB = os.path.join(PKG, "libmcl3dl_b200_nb0.so")    # build.build(defines=["MCL3DL_NEAR_BITS=0"], out=...)
+KDSKIP_LIB = os.path.join(PKG, "libmcl3dl_b200_kdskip.so")  # defines=["MCL3DL_KD_SKIP=1"]: KD caster skip-ahead field
 OLD_HOST = {"MCL3DL_TIMING": "1", "MCL3DL_ZEROCOPY_OUT": "0"}  # the host path as it was up to r01x
+VARIANT_BUILDS = {BASE_LIB: ["MCL3DL_NEAR_BITS=0"], KDSKIP_LIB: ["MCL3DL_KD_SKIP=1"]}  # --build-variants (needs nvcc)
 
 # name -> (library, environment); every variant states the host-path switches explicitly, so the table does not
 # depend on the engine's defaults.  "base" (the r01x engine) must come first: everything is compared with its records.
@@ -42,12 +45,15 @@ VARIANTS = [
     ("nb_k3_kd2", NB_LIB, dict(OLD_HOST, MCL3DL_NEAR_K="3", MCL3DL_NEAR_KD_K="2", MCL3DL_NEAR_MAX_MB="512")),
     ("nb_group", NB_LIB, dict(OLD_HOST, MCL3DL_MAPPING="group")),     # the plain kernels with the screens
     ("base_group", BASE_LIB, dict(OLD_HOST, MCL3DL_MAPPING="group")),
+    # prepared in round 1 without GPU time left (host-verified only): KD-tree raycaster skip-ahead, 4 / 8 steps
+    ("kdskip4", KDSKIP_LIB, dict(OLD_HOST)),
+    ("kdskip8", KDSKIP_LIB, dict(OLD_HOST, MCL3DL_KD_SKIP_STEPS="8")),
 ]
 # workload -> (bench workload, raycaster, spread override)
 WORKLOADS = [("c2", "c2", "dda", False), ("c3kd", "c3", "kd", False), ("c5", "c5", "dda", False),
              ("c1kd", "c1", "kd", False), ("c2s", "c2", "dda", True), ("c3", "c3", "dda", False)]
 ENV_KEYS = ["MCL3DL_TIMING", "MCL3DL_ZEROCOPY_OUT", "MCL3DL_NEAR_K", "MCL3DL_NEAR_KD_K", "MCL3DL_NEAR_MAX_MB",
-            "MCL3DL_MAPPING"]
+            "MCL3DL_MAPPING", "MCL3DL_KD_SKIP_STEPS"]
 
 
 def jobs_all():
@@ -169,8 +175,13 @@ if __name__ == "__main__":
     ap.add_argument("--calls", type=int, default=30)
     ap.add_argument("--only", default="", help="comma-separated workload names")
     ap.add_argument("--child", default=None)
+    ap.add_argument("--build-variants", action="store_true", help="nvcc-build the variant libraries and exit (no GPU needed)")
     a = ap.parse_args()
-    if a.child is not None:
+    if a.build_variants:
+        from mcl_3dl_b200 import build as _build
+        for lib, defines in VARIANT_BUILDS.items():
+            print(_build.build(defines=defines, out=lib))
+    elif a.child is not None:
         child([tuple(j) for j in json.loads(a.child)], a.calls)
     else:
         parent(a.out, a.budget, a.calls, [w for w in a.only.split(",") if w])

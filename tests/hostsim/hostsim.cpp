@@ -10,6 +10,9 @@
 #ifndef MCL3DL_NEAR_BITS
 #define MCL3DL_NEAR_BITS 1  // the host build always carries the near-field screens; near_k = 0 switches them off at run time
 #endif
+#ifndef MCL3DL_KD_SKIP
+#define MCL3DL_KD_SKIP 1     // ... and the KD-tree raycaster's skip-ahead field (kd_skip_steps = 0 switches it off)
+#endif
 
 #include <algorithm>
 #include <numeric>
@@ -26,7 +29,7 @@ struct HostMap
 {
   std::vector<uint32_t> nn_cell_start, dda_cell_start, occ;
   std::vector<float4> nn_pts, dda_pts, raw_pts;
-  std::vector<uint32_t> near_lik, near_kd;
+  std::vector<uint32_t> near_lik, near_kd, far_kd;
   NnGridDev nn{};
   DdaGridDev dda{};
   KdRayDev kd{};
@@ -49,7 +52,7 @@ void build_near(std::vector<uint32_t>& bits, NearBitsDev& out, const mcl3dl_poin
 }
 
 void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_params* lp, const mcl3dl_beam_params* bp,
-           float cell_factor, int near_k, int near_kd_k)
+           float cell_factor, int near_k, int near_kd_k, int kd_skip_steps)
 {
   const float wx = lp ? lp->dist_weight[0] : 1.0f, wy = lp ? lp->dist_weight[1] : 1.0f, wz = lp ? lp->dist_weight[2] : 1.0f;
   float raw_min[3], raw_max[3], sc_min[3], sc_max[3];
@@ -197,6 +200,13 @@ void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_param
       k.r2_pad = k.r2 * 1.0001f + 1e-6f;
       k.sin_den = gmin * 2.0;
       build_near(m.near_kd, k.near, pts, n, wx, wy, wz, k.r1_pad, near_kd_k, sc_min, sc_max);
+      {
+        // engine.cu: the skip-ahead field of build_map_on_device
+        const float wmin = std::min(wx, std::min(wy, wz));
+        const float far_r = k.r1_pad + static_cast<float>(kd_skip_steps) * k.grid_min * wmin / 0.98f;
+        build_near(m.far_kd, k.far, pts, n, wx, wy, wz, far_r, kd_skip_steps > 0 ? 1 : 0, sc_min, sc_max);
+        k.far_margin = 0.98f * (far_r - k.r1_pad);
+      }
       m.kd = k;
     }
     m.dda = g;
@@ -209,7 +219,8 @@ extern "C" int hostsim_measure_nf(const mcl3dl_point* map, size_t n, const mcl3d
                                   float cell_factor, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts,
                                   size_t n_lik, const mcl3dl_point* beam_pts, size_t n_beam, const float* origins_xyz,
                                   size_t n_origins, mcl3dl_result* out, uint8_t* status, int near_k, int near_kd_k,
-                                  uint64_t* work /* [5]: nn rows, nn pts, steps, occupied, tested; may be NULL */)
+                                  uint64_t* work /* [5]: nn rows, nn pts, steps, occupied, tested; may be NULL */,
+                                  int kd_skip_steps)
 {
   if ((n_lik && !lp) || (n_beam && !bp) || (bp && !bp->use_raycast_using_dda && !lp))
     return -1;
@@ -217,7 +228,7 @@ extern "C" int hostsim_measure_nf(const mcl3dl_point* map, size_t n, const mcl3d
     if (beam_pts[j].label >= n_origins)
       return -1;
   HostMap m;
-  build(m, map, n, lp, bp, cell_factor, near_k, near_kd_k);
+  build(m, map, n, lp, bp, cell_factor, near_k, near_kd_k, kd_skip_steps);
   uint64_t wk[5] = {0, 0, 0, 0, 0};
   for (size_t p = 0; p < P; ++p)
   {
@@ -309,5 +320,5 @@ extern "C" int hostsim_measure(const mcl3dl_point* map, size_t n, const mcl3dl_l
                                size_t n_origins, mcl3dl_result* out, uint8_t* status)
 {
   return hostsim_measure_nf(map, n, lp, bp, cell_factor, poses, P, lik_pts, n_lik, beam_pts, n_beam, origins_xyz, n_origins, out,
-                            status, 2, 1, nullptr);
+                            status, 2, 1, nullptr, 4);
 }

@@ -32,10 +32,12 @@ def hostsim():
         assert r.returncode == 0, r.stderr
     L = C.CDLL(LIB)
     vp, sz = C.c_void_p, C.c_size_t
-    L.hostsim_measure_nf.argtypes = [vp, sz, vp, vp, C.c_float, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, C.c_int, C.c_int, vp]
+    L.hostsim_measure_nf.argtypes = [vp, sz, vp, vp, C.c_float, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, C.c_int, C.c_int, vp,
+                                     C.c_int]
 
-    def run(map_pts, lik, beam, poses, lik_pts, beam_pts, origins, near=(2, 1), work=False):
-        """near = dilation of the (likelihood, KD-caster) near-field screens; 0 = the unscreened searches."""
+    def run(map_pts, lik, beam, poses, lik_pts, beam_pts, origins, near=(2, 1), work=False, kd_skip=4):
+        """near = dilation of the (likelihood, KD-caster) near-field screens; 0 = the unscreened searches.
+        kd_skip = marching steps covered by the KD caster's skip-ahead field (MCL3DL_KD_SKIP builds); 0 = off."""
         map_pts = np.ascontiguousarray(map_pts, dtype=synth.POINT)
         poses = np.ascontiguousarray(poses, dtype=synth.POSE)
         lik_pts = np.ascontiguousarray(lik_pts if lik_pts is not None else np.zeros(0, synth.POINT), dtype=synth.POINT)
@@ -48,7 +50,7 @@ def hostsim():
         rc = L.hostsim_measure_nf(p(map_pts), len(map_pts), C.byref(lik) if lik is not None else None,
                                   C.byref(beam) if beam is not None else None, 1.0, p(poses), len(poses), p(lik_pts),
                                   len(lik_pts), p(beam_pts), len(beam_pts), p(origins), len(origins), p(out), p(st),
-                                  near[0], near[1], p(wk))
+                                  near[0], near[1], p(wk), kd_skip)
         assert rc == 0
         if work:
             return out, st[:, :len(beam_pts)], wk
@@ -105,6 +107,23 @@ def test_near_field_screens_change_no_result(hostsim, near, seed, w, spread, use
     assert wk[0] < wk_ref[0] and wk[1] <= wk_ref[1]          # likelihood: fewer windows opened
     if not use_dda:
         assert wk[4] < wk_ref[4] and wk[3] == wk_ref[3]      # KD caster: fewer points tested, same collisions
+
+
+@pytest.mark.parametrize("skip", [1, 4, 16])
+@pytest.mark.parametrize("seed,w,spread", [(21, (1, 1, 1), False), (22, (1, 1, 5), True), (23, (2, 1, 3), False)])
+def test_kd_skip_ahead_changes_no_result(hostsim, skip, seed, w, spread):
+    """The KD-tree raycaster's skip-ahead field (MCL3DL_KD_SKIP builds) jumps over marching steps that a coarser near
+    field proves clear: same records, same per-ray status, same step count, fewer points tested."""
+    s = synth.scene(30_000, 24, 8, 40, spread=spread, seed=seed)
+    lik = engine.LikParams(dist_weight=w)
+    beam = engine.beam_params_from_reference(num_points_default=40, use_raycast_using_dda=False)
+    ref, st_ref, wk_ref = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(0, 0),
+                                  work=True, kd_skip=0)
+    got, st, wk = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(2, 1), work=True,
+                          kd_skip=skip)
+    assert got.tobytes() == ref.tobytes()
+    assert np.array_equal(st, st_ref)
+    assert wk[2] == wk_ref[2] and wk[3] == wk_ref[3] and wk[4] < wk_ref[4]
 
 
 def test_device_functions_survive_garbage_inputs_under_sanitizers(tmp_path):
