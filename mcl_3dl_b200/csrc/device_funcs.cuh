@@ -201,31 +201,6 @@ enum
   ST_TOTAL_REFLECTION = 3
 };
 
-#ifndef MCL3DL_LIK_PRUNE
-#define MCL3DL_LIK_PRUNE 0  // 1: sphere-shaped instead of box-shaped search windows (host-verified, not yet measured)
-#endif
-// The x-cells [px0, px1] of row (iy, iz) that can hold a point within the radius of q, or false if none can: the row's
-// cells span the slab [o + i c, o + (i+1) c) in y and in z, so a point in it is at least (dy, dz) away from q, and its x
-// must lie within sqrt(r^2 - dy^2 - dz^2) of qx.  Bounds are widened by 1e-4 relative + 1e-5 absolute, far above the
-// float rounding of the cell function and of the distance sum, so no candidate with d^2 < r^2 is ever dropped.
-__device__ __forceinline__ bool lik_row_span(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz, int iy, int iz,
-                                             int lx, int hx, int& px0, int& px1)
-{
-  const float cell = fdiv(1.0f, g.inv_cell);
-  const float ylo = fadd(g.oy, fmul(static_cast<float>(iy), cell)), zlo = fadd(g.oz, fmul(static_cast<float>(iz), cell));
-  const float guard = fadd(fmul(1e-4f, fmaxf(fmaxf(fabsf(qy), fabsf(qz)), fabsf(qx))), 1e-5f);
-  const float dy = fmaxf(fmaxf(fsub(ylo, qy), fsub(qy, fadd(ylo, cell))), 0.0f);
-  const float dz = fmaxf(fmaxf(fsub(zlo, qz), fsub(qz, fadd(zlo, cell))), 0.0f);
-  const float ey = fmaxf(fsub(dy, guard), 0.0f), ez = fmaxf(fsub(dz, guard), 0.0f);
-  const float rest = fsub(lp.r2, fadd(fmul(ey, ey), fmul(ez, ez)));
-  if (!(rest > 0.0f))
-    return false;
-  const float half = fadd(fmul(__fsqrt_rn(rest), 1.0001f), guard);
-  px0 = max(lx, __float2int_rd(fmul(fsub(fsub(qx, half), g.ox), g.inv_cell)));
-  px1 = min(hx, __float2int_rd(fmul(fsub(fadd(qx, half), g.ox), g.inv_cell)));
-  return px0 <= px1;
-}
-
 // --------------------------------------------------------------------------------------------
 // Exact nearest-neighbour distance^2 (rescaled metric) within the radius; returns r2 if none.
 __device__ __forceinline__ float nn_dist2(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz,
@@ -251,25 +226,14 @@ __device__ __forceinline__ float nn_dist2(const NnGridDev& g, const LikDev& lp, 
   float best = lp.r2;
   if (lx > hx || ly > hy || lz > hz)
     return best;
-#if !MCL3DL_LIK_PRUNE
   n_rows += static_cast<uint32_t>((hz - lz + 1) * (hy - ly + 1));
-#endif
   for (int iz = lz; iz <= hz; ++iz)
   {
     for (int iy = ly; iy <= hy; ++iy)
     {
       const int row = (iz * g.ny + iy) * g.nx;
-#if MCL3DL_LIK_PRUNE
-      int px0, px1;
-      if (!lik_row_span(g, lp, qx, qy, qz, iy, iz, lx, hx, px0, px1))
-        continue;
-      ++n_rows;
-      const uint32_t s0 = __ldg(g.cell_start + row + px0);
-      const uint32_t s1 = __ldg(g.cell_start + row + px1 + 1);
-#else
       const uint32_t s0 = __ldg(g.cell_start + row + lx);
       const uint32_t s1 = __ldg(g.cell_start + row + hx + 1);
-#endif
       n_pts += s1 - s0;
       for (uint32_t s = s0; s < s1; ++s)
       {
