@@ -225,6 +225,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
+    ap.add_argument("--graph", action="store_true",
+                    help="experiment: replay the device-resident step as one CUDA graph (not part of the contract run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--raycaster", default="dda", choices=["dda", "kd"],
                     help="beam raycaster: RaycastUsingDDA (north_star) or RaycastUsingKDTree (the node's default)")
@@ -273,12 +275,24 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
-    def step():
+    def step_eager():
         eng.measure_device(d_p.data_ptr(), P_rank, d_l.data_ptr(), n_lik, d_b.data_ptr(), n_beam,
-                           d_o.data_ptr(), len(s["origins"]), d_out.data_ptr(), stream)
+                           d_o.data_ptr(), len(s["origins"]), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
         if world > 1:
             # the one exchange of the path: all-gather of the per-particle records over NVLink (NCCL)
             sharding.gather_records_device(d_out, d_all)
+
+    step = step_eager
+    if args.graph:
+        # EXPERIMENT (added without GPU time left in round 1, never run): replay the step (both kernels, their
+        # fork/join events and the NCCL all-gather) as one CUDA graph, to take the per-step launch work off the CPU
+        for _ in range(3):
+            step_eager()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step_eager()
+        step = graph.replay
 
     def barrier():
         if world > 1:
