@@ -377,14 +377,16 @@ def main():
                         + io_bytes + n_beam * 16)
         survey_note = "SURVEY 8d beam: 1 B per cell stepped + 8 B CSR + 16 B per point tested"
     achieved = alg_bytes / (kern[dom] * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dom + "_dram_bytes_per_launch")
+            ncu = json.load(f)
+        traffic = ncu.get(args.workload, {}).get(dom + "_dram_bytes_per_launch")
+        traffic_note = ncu.get("_note")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
                 "kernel_ms": kern[dom], "algorithmic_bytes_per_launch": alg_bytes, "model": note,
                 "kernel_ms_all": kern, "work_counters_per_step": ws,
                 "survey_8d_model": {"bytes_per_launch": survey_bytes, "achieved": survey_bytes / (kern[dom] * 1e-3) / 1e9,

@@ -376,3 +376,39 @@ def test_dense_cloud_overflows_the_window_table(eng_mod, eng, cc):
     assert want["match_cnt"].sum() > 0
     assert np.array_equal(eng.beam_status(s["particles"], s["beam"], s["origins"]),
                           cpu.beam_status(s["particles"], s["beam"], s["origins"]))
+
+
+# ------------------------------------------------------------------ engine options (profiles/r01y_ab_variants.txt)
+@pytest.mark.parametrize("use_dda", [True, False])
+def test_options_change_no_record(eng_mod, monkeypatch, use_dda):
+    """The near-field screens, the zero-copy record stores and the timing events are pure performance options:
+    every combination returns the records of the plainest configuration byte for byte."""
+    s = synth.scene(60_000, 300, 96, 24, seed=131)
+    lik = eng_mod.LikParams(dist_weight=(1, 1, 5))
+    beam = eng_mod.beam_params_from_reference(num_points_default=24, dda_grid_size=0.2, use_raycast_using_dda=use_dda)
+
+    def run(env, timing=False):
+        for k in ("MCL3DL_NEAR_K", "MCL3DL_NEAR_KD_K", "MCL3DL_ZEROCOPY_OUT", "MCL3DL_TIMING", "MCL3DL_MAPPING"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = eng_mod.Engine((0,))
+        e.set_map(s["map"], lik, beam)
+        if timing:
+            e.collect_timing(True)
+        out = e.measure(s["particles"], s["lik"], s["beam"], s["origins"]).copy()
+        info, t = e.near_field_info(), e.last_timing()
+        e.close()
+        return out, info, t
+
+    plain, info0, t0 = run({"MCL3DL_NEAR_K": "0", "MCL3DL_NEAR_KD_K": "0", "MCL3DL_ZEROCOPY_OUT": "0"})
+    assert info0[0][0] == 0 and info0[1][0] == 0
+    assert t0["lik_ms"] == 0.0 and t0["beam_ms"] == 0.0          # timing events are opt-in
+    dflt, info1, _ = run({})
+    assert dflt.tobytes() == plain.tobytes()
+    assert info1[0][0] == 2 and info1[0][1] > 0 and (info1[1][0] == 1) == (not use_dda)
+    timed, _, t1 = run({"MCL3DL_NEAR_K": "1", "MCL3DL_ZEROCOPY_OUT": "100"}, timing=True)   # 300 particles > 100: bulk D2H copy
+    assert timed.tobytes() == plain.tobytes()
+    assert t1["lik_ms"] > 0.0 and t1["beam_ms"] > 0.0 and t1["h2d_ms"] > 0.0
+    group, _, _ = run({"MCL3DL_MAPPING": "group", "MCL3DL_NEAR_K": "3", "MCL3DL_NEAR_KD_K": "2"})
+    assert group.tobytes() == plain.tobytes()
