@@ -247,6 +247,9 @@ struct mcl3dl_engine
                                 // mcl3dl_collect_timing(eng, 1) or MCL3DL_TIMING=1
   size_t zero_copy_max = 8192;  // the kernels of updates with <= this many particles per device store their records
                                 // straight into the pinned result block (no D2H copy launch); MCL3DL_ZEROCOPY_OUT
+  int update_one_sync = 0;  // mcl3dl_measure_update on ONE device: normalise from the device-side total, one host
+                            // synchronise instead of two (MCL3DL_UPDATE_ONE_SYNC=1; written without GPU time left in
+                            // round 1: off until the f2 parity tests have run with it)
   int mapping = 1;  // 1 = tuned kernels (lik_kernel_wi + beam_kernel_pl); 0 = the plain group kernels (MCL3DL_MAPPING=group)
 };
 
@@ -881,6 +884,8 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     eng->timing = std::atoi(v) != 0;
   if (const char* v = std::getenv("MCL3DL_ZEROCOPY_OUT"))
     eng->zero_copy_max = static_cast<size_t>(std::max(std::atol(v), 0L));
+  if (const char* v = std::getenv("MCL3DL_UPDATE_ONE_SYNC"))
+    eng->update_one_sync = std::atoi(v) != 0;
   if (const char* o = std::getenv("MCL3DL_OVERLAP"))
     eng->overlap = std::atoi(o) != 0;
   if (const char* m = std::getenv("MCL3DL_MAPPING"))
@@ -1258,6 +1263,7 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
     int nblk;
   };
   std::vector<Lay> lay(G);
+  const bool one_sync = eng->update_one_sync && G == 1;
   // ---- pass 1 on every device: inputs up, both models, w_i and its reduction
   for (size_t d = 0; d < G; ++d)
   {
@@ -1281,7 +1287,7 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
     L.nblk = static_cast<int>(std::min<size_t>((Pd + kBlockThreads - 1) / kBlockThreads, static_cast<size_t>(c.sm_count) * 4));
     if ((rc = reserve_pinned(eng, c, L.total)) || (rc = reserve(eng, c.d_poses, L.in_bytes)) ||
         (rc = reserve(eng, c.d_out, Pd * sizeof(mcl3dl_result))) || (rc = reserve(eng, c.d_w, Pd * 4)) ||
-        (rc = reserve(eng, c.d_post, Pd * 4)) || (rc = reserve(eng, c.d_wpart, (L.nblk + 1) * sizeof(WeightPartial))))
+        (rc = reserve(eng, c.d_post, Pd * 4)) || (rc = reserve(eng, c.d_wpart, 2 * (L.nblk + 1) * sizeof(WeightPartial))))
       return rc;
     char* hp = static_cast<char*>(c.h_pinned);
     std::memcpy(hp, poses + p0[d], Pd * sizeof(mcl3dl_pose));
@@ -1307,6 +1313,20 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
     CK(cudaGetLastError());
     eng->launches += 2;
     CK(cudaMemcpyAsync(hp + L.o_part, parts + L.nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+    if (one_sync)
+    {
+      // pass 2 right behind pass 1 (its partial slots live after pass 1's), everything read back after ONE synchronise
+      WeightPartial* parts2 = parts + L.nblk + 1;
+      normalize_kernel_dev<<<L.nblk, kBlockThreads, 0, st>>>(static_cast<const float*>(c.d_w.p), static_cast<int>(Pd), parts + L.nblk,
+                                                            static_cast<int>(p0[d]), static_cast<float*>(c.d_post.p), parts2);
+      weight_finish_kernel<<<1, 32, 0, st>>>(parts2, L.nblk);
+      CK(cudaGetLastError());
+      eng->launches += 2;
+      CK(cudaMemcpyAsync(hp + L.o_post, c.d_post.p, Pd * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(hp + L.o_part + sizeof(WeightPartial), parts2 + L.nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+      if (records)
+        CK(cudaMemcpyAsync(hp + L.o_rec, c.d_out.p, Pd * sizeof(mcl3dl_result), cudaMemcpyDeviceToHost, st));
+    }
   }
   double total = 0.0;
   float qmin = 1.0f, qmax = 0.0f;
@@ -1340,6 +1360,8 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
     Lay& L = lay[d];
     char* hp = static_cast<char*>(c.h_pinned);
     WeightPartial* parts = static_cast<WeightPartial*>(c.d_wpart.p);
+    if (one_sync)
+      continue;  // already enqueued behind pass 1
     if (summary->kept)
     {
       normalize_kernel<<<L.nblk, kBlockThreads, 0, st>>>(static_cast<const float*>(c.d_w.p), static_cast<int>(Pd), total_f,
@@ -1363,13 +1385,14 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
     if (Pd == 0)
       continue;
     CK(cudaSetDevice(c.dev));
-    CK(cudaStreamSynchronize(c.stream));
+    if (!one_sync)
+      CK(cudaStreamSynchronize(c.stream));
     const char* hp = static_cast<const char*>(c.h_pinned);
     if (summary->kept)
     {
       std::memcpy(posterior + p0[d], hp + lay[d].o_post, Pd * 4);
       WeightPartial wp;
-      std::memcpy(&wp, hp + lay[d].o_part, sizeof(wp));
+      std::memcpy(&wp, hp + lay[d].o_part + (one_sync ? sizeof(WeightPartial) : 0), sizeof(wp));
       ent += wp.sum;
       if (wp.best > best)  // lower device = lower indices, so strict '>' keeps the first maximum
       {

@@ -837,6 +837,39 @@ __global__ void __launch_bounds__(kBlockThreads)
   weight_block_reduce(v, partials + blockIdx.x, sm);
 }
 
+// pass 2 without a host round trip (one device): the total comes from pass 1's folded slot instead of a kernel
+// argument.  A non-positive total ("No Particle alive", pf.h:274-278) leaves `post` unwritten; the host restores the prior.
+__global__ void __launch_bounds__(kBlockThreads)
+    normalize_kernel_dev(const float* __restrict__ w, int P, const WeightPartial* __restrict__ pass1, int index_offset,
+                         float* __restrict__ post, WeightPartial* __restrict__ partials)
+{
+  __shared__ WeightPartial sm[kBlockThreads / 32];
+  const float total = __double2float_rn(pass1->sum);
+  WeightPartial v;
+  v.sum = 0.0;
+  v.qmin = 1.0f;
+  v.qmax = 0.0f;
+  v.best = -1.0f;
+  v.best_i = 0xffffffffu;
+  if (total > 0.0f)
+  {
+    for (int i = blockIdx.x * kBlockThreads + threadIdx.x; i < P; i += gridDim.x * kBlockThreads)
+    {
+      const float p = fdiv(w[i], total);
+      post[i] = p;
+      if (p > 0.0f)
+        v.sum = dadd(v.sum, static_cast<double>(fmul(p, logf(p))));
+      const uint32_t gi = static_cast<uint32_t>(index_offset + i);
+      if (p > v.best || (p == v.best && gi < v.best_i))
+      {
+        v.best = p;
+        v.best_i = gi;
+      }
+    }
+  }
+  weight_block_reduce(v, partials + blockIdx.x, sm);
+}
+
 // fold the per-CTA slots in order into slot [n]
 __global__ void weight_finish_kernel(WeightPartial* __restrict__ partials, int n)
 {

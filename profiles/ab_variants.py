@@ -46,6 +46,7 @@ VARIANTS = [
     ("nb_group", NB_LIB, dict(OLD_HOST, MCL3DL_MAPPING="group")),     # the plain kernels with the screens
     ("base_group", BASE_LIB, dict(OLD_HOST, MCL3DL_MAPPING="group")),
     # prepared in round 1 without GPU time left (host-verified only): KD-tree raycaster skip-ahead, 4 / 8 steps
+    ("one_sync", NB_LIB, dict(OLD_HOST, MCL3DL_UPDATE_ONE_SYNC="1")),  # fused weight update with one synchronise
     ("kdskip4", KDSKIP_LIB, dict(OLD_HOST)),
     ("kdskip8", KDSKIP_LIB, dict(OLD_HOST, MCL3DL_KD_SKIP_STEPS="8")),
 ]
@@ -53,7 +54,7 @@ VARIANTS = [
 WORKLOADS = [("c2", "c2", "dda", False), ("c3kd", "c3", "kd", False), ("c5", "c5", "dda", False),
              ("c1kd", "c1", "kd", False), ("c2s", "c2", "dda", True), ("c3", "c3", "dda", False)]
 ENV_KEYS = ["MCL3DL_TIMING", "MCL3DL_ZEROCOPY_OUT", "MCL3DL_NEAR_K", "MCL3DL_NEAR_KD_K", "MCL3DL_NEAR_MAX_MB",
-            "MCL3DL_MAPPING", "MCL3DL_KD_SKIP_STEPS"]
+            "MCL3DL_MAPPING", "MCL3DL_KD_SKIP_STEPS", "MCL3DL_UPDATE_ONE_SYNC"]
 
 
 def jobs_all():
@@ -115,6 +116,22 @@ def child(job_names, calls):
             rec["identical_to_base"] = bool(np.load(base_path).tobytes() == out.tobytes())
         else:
             rec["identical_to_base"] = None
+        # the fused weight update (mcl3dl_measure_update) on the same inputs: posterior compared with the base variant's
+        prior = np.full(len(poses), 1.0 / len(poses), dtype=np.float32)
+        upd = []
+        for k in range(3 + max(calls // 3, 3)):
+            t0 = time.perf_counter()
+            post, summ, _ = eng.measure_update(poses, s["lik"], s["beam"], s["origins"], prior)
+            if k >= 3:
+                upd.append(time.perf_counter() - t0)
+        post_path = "/tmp/ab_base_post_%s.npy" % wname
+        if vname == "base":
+            np.save(post_path, post)
+            rec["posterior_identical_to_base"] = True
+        elif os.path.exists(post_path):
+            rec["posterior_identical_to_base"] = bool(np.load(post_path).tobytes() == post.tobytes())
+        rec["update_us_median"] = 1e6 * float(np.median(upd))
+        rec["entropy"] = float(summ["entropy"])
         units = len(poses) * (n_lik if n_lik else n_beam)
         rec.update({"e2e_us_median": 1e6 * float(np.median(wall)), "e2e_us_min": 1e6 * float(np.min(wall)),
                     "e2e_units_per_s": units / float(np.median(wall)),
