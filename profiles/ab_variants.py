@@ -117,21 +117,24 @@ def child(job_names, calls):
         else:
             rec["identical_to_base"] = None
         # the fused weight update (mcl3dl_measure_update) on the same inputs: posterior compared with the base variant's
-        prior = np.full(len(poses), 1.0 / len(poses), dtype=np.float32)
-        upd = []
-        for k in range(3 + max(calls // 3, 3)):
-            t0 = time.perf_counter()
-            post, summ, _ = eng.measure_update(poses, s["lik"], s["beam"], s["origins"], prior)
-            if k >= 3:
-                upd.append(time.perf_counter() - t0)
-        post_path = "/tmp/ab_base_post_%s.npy" % wname
-        if vname == "base":
-            np.save(post_path, post)
-            rec["posterior_identical_to_base"] = True
-        elif os.path.exists(post_path):
-            rec["posterior_identical_to_base"] = bool(np.load(post_path).tobytes() == post.tobytes())
-        rec["update_us_median"] = 1e6 * float(np.median(upd))
-        rec["entropy"] = float(summ["entropy"])
+        try:  # (added after the r01y run: never executed on a GPU yet, so it must not take the sweep down)
+            prior = np.full(len(poses), 1.0 / len(poses), dtype=np.float32)
+            upd = []
+            for k in range(3 + max(calls // 3, 3)):
+                t0 = time.perf_counter()
+                post, summ, _ = eng.measure_update(poses, s["lik"], s["beam"], s["origins"], prior)
+                if k >= 3:
+                    upd.append(time.perf_counter() - t0)
+            post_path = "/tmp/ab_base_post_%s.npy" % wname
+            if vname == "base":
+                np.save(post_path, post)
+                rec["posterior_identical_to_base"] = True
+            elif os.path.exists(post_path):
+                rec["posterior_identical_to_base"] = bool(np.load(post_path).tobytes() == post.tobytes())
+            rec["update_us_median"] = 1e6 * float(np.median(upd))
+            rec["entropy"] = float(summ["entropy"])
+        except Exception as exc:
+            rec["update_error"] = "%s: %s" % (type(exc).__name__, exc)
         units = len(poses) * (n_lik if n_lik else n_beam)
         rec.update({"e2e_us_median": 1e6 * float(np.median(wall)), "e2e_us_min": 1e6 * float(np.min(wall)),
                     "e2e_units_per_s": units / float(np.median(wall)),
