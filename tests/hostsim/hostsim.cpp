@@ -322,3 +322,44 @@ extern "C" int hostsim_measure(const mcl3dl_point* map, size_t n, const mcl3dl_l
   return hostsim_measure_nf(map, n, lp, bp, cell_factor, poses, P, lik_pts, n_lik, beam_pts, n_beam, origins_xyz, n_origins, out,
                             status, 2, 1, nullptr, 4);
 }
+
+// The near field on its own: build it for radius r / dilation k over `map` (rescaled by w) and evaluate near_maybe for
+// `nq` rescaled query points.  layout_out = {nx, ny, nz, pitch}, cell_out = fine cell edge actually used (0 if the field
+// could not be laid out, in which case every answer is 1 = "maybe near").
+extern "C" int hostsim_near_query(const mcl3dl_point* map, size_t n, const float w[3], float r, int k, size_t max_bytes,
+                                  const float* queries_xyz, size_t nq, uint8_t* maybe_out, int32_t layout_out[4],
+                                  float* cell_out)
+{
+  float sc_min[3], sc_max[3];
+  for (int a = 0; a < 3; ++a)
+  {
+    sc_min[a] = std::numeric_limits<float>::infinity();
+    sc_max[a] = -std::numeric_limits<float>::infinity();
+  }
+  for (size_t i = 0; i < n; ++i)
+  {
+    const float s[3] = {__fmul_rn(map[i].x, w[0]), __fmul_rn(map[i].y, w[1]), __fmul_rn(map[i].z, w[2])};
+    for (int a = 0; a < 3; ++a)
+    {
+      sc_min[a] = std::min(sc_min[a], s[a]);
+      sc_max[a] = std::max(sc_max[a], s[a]);
+    }
+  }
+  NearBitsDev f{};
+  std::vector<uint32_t> bits;
+  if (k > 0 && near_layout(f, r, k, sc_min, sc_max, max_bytes))
+  {
+    bits.assign(static_cast<size_t>(f.pitch) * f.ny * f.nz, 0u);
+    for (size_t i = 0; i < n; ++i)
+      near_mark_point(f, bits.data(), k, __fmul_rn(map[i].x, w[0]), __fmul_rn(map[i].y, w[1]), __fmul_rn(map[i].z, w[2]));
+    f.bits = bits.data();
+  }
+  layout_out[0] = f.nx;
+  layout_out[1] = f.ny;
+  layout_out[2] = f.nz;
+  layout_out[3] = f.pitch;
+  *cell_out = f.bits ? 1.0f / f.inv_cell : 0.0f;
+  for (size_t q = 0; q < nq; ++q)
+    maybe_out[q] = near_maybe(f, queries_xyz[3 * q], queries_xyz[3 * q + 1], queries_xyz[3 * q + 2]) ? 1 : 0;
+  return 0;
+}

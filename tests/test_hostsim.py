@@ -139,3 +139,64 @@ def test_device_functions_survive_garbage_inputs_under_sanitizers(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "fuzz ok" in r.stdout
+
+
+def _near_query(map_xyz, w, r, k, queries, max_bytes=64 << 20):
+    hs_lib = C.CDLL(LIB)
+    vp, sz = C.c_void_p, C.c_size_t
+    hs_lib.hostsim_near_query.argtypes = [vp, sz, vp, C.c_float, C.c_int, sz, vp, sz, vp, vp, vp]
+    pts = synth.make_points(np.asarray(map_xyz, dtype=np.float32))
+    wv = np.asarray(w, dtype=np.float32)
+    q = np.ascontiguousarray(queries, dtype=np.float32)
+    out = np.zeros(len(q), dtype=np.uint8)
+    lay = np.zeros(4, dtype=np.int32)
+    cell = C.c_float(0)
+    p = lambda a: a.ctypes.data_as(vp)  # noqa: E731
+    assert hs_lib.hostsim_near_query(p(pts), len(pts), p(wv), r, k, max_bytes, p(q), len(q), p(out), p(lay), C.byref(cell)) == 0
+    return out.astype(bool), lay, cell.value
+
+
+@pytest.mark.parametrize("offset", [0.0, 37.5, 4000.0, -65000.0])
+@pytest.mark.parametrize("r,k", [(0.2, 1), (0.2, 2), (0.0707, 1), (0.45, 3), (1.5, 4), (0.01, 2)])
+def test_near_field_never_hides_a_neighbour(hostsim, r, k, offset):
+    """THE invariant of the screens: whenever a map point lies within r of a query (rescaled metric), the query's bit is
+    set — for clustered and scattered maps, anisotropic weights, maps far from the origin (float cell arithmetic),
+    radii from 1 cm to 1.5 m, and fields that had to be coarsened to fit the byte cap.  A screen that answered "clear"
+    here would silently drop a match on the device."""
+    rng = np.random.default_rng(int(1000 * r) + 7 * k + int(abs(offset)))
+    w = np.array([1.0, 1.0, 5.0] if k % 2 else [2.0, 1.0, 3.0], dtype=np.float32)
+    span = 400.0 * r                      # ~400 search radii across: several hundred fine cells per axis
+    pts = rng.uniform(0, span, (1500, 3)).astype(np.float32)
+    pts[:300] = pts[0] + rng.normal(0, r, (300, 3)).astype(np.float32)   # a dense cluster
+    pts += np.float32(offset)
+    sc = (pts * w).astype(np.float32)
+    # queries: near map points (just inside / just outside the radius), inside the box, far outside it
+    d = rng.normal(0, 1, (4000, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    near_q = sc[rng.integers(0, len(sc), 4000)] + (d * rng.uniform(0.0, 1.3 * r, (4000, 1))).astype(np.float32)
+    box_q = rng.uniform(sc.min(0) - 3 * r, sc.max(0) + 3 * r, (3000, 3)).astype(np.float32)
+    far_q = (sc.mean(0) + rng.normal(0, 50 * span, (300, 3))).astype(np.float32)
+    q = np.vstack([near_q, box_q, far_q, sc[:200]]).astype(np.float32)
+    for cap in (64 << 20, 1 << 16):       # the second cap forces the layout to coarsen the cells
+        maybe, lay, cell = _near_query(pts, w, r, k, q, max_bytes=cap)
+        assert cell >= 1.0099 * r / k
+        assert int(lay[3]) * int(lay[1]) * int(lay[2]) * 4 <= cap
+        from scipy.spatial import cKDTree
+        dist, _ = cKDTree(sc.astype(np.float64)).query(q.astype(np.float64))
+        hidden = (~maybe) & (dist < r * (1 + 1e-6))
+        assert not hidden.any(), (int(hidden.sum()), float(dist[hidden].min()))
+        # and the screen is not vacuous: far queries are reported clear
+        assert not maybe[len(near_q) + len(box_q):len(near_q) + len(box_q) + len(far_q)].all()
+
+
+def test_near_field_degenerate_maps(hostsim):
+    """One point, a flat map, and a bounding box too large for any field (the engine then searches unscreened)."""
+    one = np.array([[1.0, 2.0, 3.0]], np.float32)
+    maybe, lay, cell = _near_query(one, (1, 1, 1), 0.2, 2, [[1.0, 2.0, 3.1], [5.0, 2.0, 3.0], [np.nan, 0, 0], [np.inf, 0, 0]])
+    assert maybe[0] and not maybe[1] and not maybe[3] and cell > 0
+    flat = np.array([[x, y, 0.0] for x in range(5) for y in range(5)], np.float32)
+    maybe, _, _ = _near_query(flat, (1, 1, 5), 0.3, 1, [[2.0, 2.0, 0.25], [2.0, 2.0, 5.0]])
+    assert maybe[0] and not maybe[1]
+    huge = np.array([[0, 0, 0], [3e38, 0, 0]], np.float32)
+    maybe, lay, cell = _near_query(huge, (1, 1, 1), 0.2, 2, [[0, 0, 0], [1e30, 5, 5]])
+    assert cell == 0.0 and maybe.all()
