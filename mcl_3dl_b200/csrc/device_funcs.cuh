@@ -22,6 +22,11 @@
 #ifndef MCL3DL_KD_SKIP
 #define MCL3DL_KD_SKIP 0
 #endif
+// MCL3DL_LIK_CHUNKS=1 also builds the warp-chunk likelihood kernel (lik_kernel_wc), selected at run time with
+// MCL3DL_LIK=chunk.  Host-verified lane by lane (tests/hostsim), not yet measured on a GPU: off by default.
+#ifndef MCL3DL_LIK_CHUNKS
+#define MCL3DL_LIK_CHUNKS 0
+#endif
 #if MCL3DL_KD_SKIP && !MCL3DL_NEAR_BITS
 #error "MCL3DL_KD_SKIP needs MCL3DL_NEAR_BITS"
 #endif
@@ -248,6 +253,168 @@ __device__ __forceinline__ float nn_dist2(const NnGridDev& g, const LikDev& lp, 
     }
   }
   return best;
+}
+
+// --------------------------------------------------------------------------------------------
+// Warp-chunk likelihood kernel (lik_kernel_wc, kernels.cuh; -DMCL3DL_LIK_CHUNKS=1): the per-lane pieces.  A warp works
+// on 32 evals per round; the map points their windows contain are cut into CHUNKS of <= 4 consecutive points and the
+// chunks are dealt to the lanes, so every lane of phase 2 has the same amount of work (the run-per-lane kernel
+// lik_kernel_wi leaves half the lanes idle: runs are 1..30 points long, ncu r01x: 13.5 of 32 lanes on the load line).
+// Written as functions of (lane, shared slab) so that tests/hostsim can run the rounds lane by lane on the host.
+constexpr int kWcMaxRows = 9;
+constexpr int kWcMaxDesc = 640;       // >= 9 * 32: one descriptor per run always fits (the overflow fallback)
+constexpr int kWcMaxRunChunks = 127;  // chunk index field of a descriptor: 7 bits
+constexpr int kWcOverflow = 1023;     // a lane reports this chunk count to force the whole-run fallback for its round
+
+struct LikChunkSmem
+{
+  uint2 rows[kWcMaxRows][32];  // non-empty [start, end) runs of each lane's eval, compacted
+  float qx[32], qy[32], qz[32];
+  uint32_t best[32];           // float bits of the running min d^2 (non-negative floats order as uints)
+  uint16_t desc[kWcMaxDesc];   // run k (4 bits) | eval lane (5 bits) << 4 | chunk index (7 bits) << 9
+};
+
+// Phase 1, lane = eval: the runs of the <= 3x3 window of q, from the window table (same fetch as lik_kernel_wi).
+// Returns the number of runs stored to sm.rows[.][lane]; n_chunks = their total number of 4-point chunks, or
+// kWcOverflow if one of the runs is too long for the descriptor's chunk index (very dense cells).
+__device__ __forceinline__ int wc_window(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz, int lane,
+                                         LikChunkSmem& sm, uint32_t& st_rows, uint32_t& st_pts, int& n_chunks)
+{
+  int nr = 0;
+  n_chunks = 0;
+  int lx = __float2int_rd(fmul(fsub(fsub(qx, lp.rpad), g.ox), g.inv_cell));
+  int ly = __float2int_rd(fmul(fsub(fsub(qy, lp.rpad), g.oy), g.inv_cell));
+  int lz = __float2int_rd(fmul(fsub(fsub(qz, lp.rpad), g.oz), g.inv_cell));
+  int hx = __float2int_rd(fmul(fsub(fadd(qx, lp.rpad), g.ox), g.inv_cell));
+  int hy = __float2int_rd(fmul(fsub(fadd(qy, lp.rpad), g.oy), g.inv_cell));
+  int hz = __float2int_rd(fmul(fsub(fadd(qz, lp.rpad), g.oz), g.inv_cell));
+  lx = max(lx, 0);
+  ly = max(ly, 0);
+  lz = max(lz, 0);
+  hx = min(hx, g.nx - 1);
+  hy = min(hy, min(g.ny - 1, ly + 2));
+  hz = min(hz, min(g.nz - 1, lz + 2));
+  if (lx > hx || ly > hy || lz > hz)
+    return 0;
+#if MCL3DL_NEAR_BITS
+  if (!near_maybe(g.near, qx, qy, qz))
+    return 0;
+#endif
+  st_rows += static_cast<uint32_t>((hz - lz + 1) * (hy - ly + 1));
+  // the whole 3x3 window from the y-fastest window table: 2 aligned 16-byte loads per z layer, all issued first
+  const int width = hx - lx + 1;  // 1..3 cells along x
+  const int yb = ly & ~1;
+  const int odd = ly & 1;
+  uint4 ea[3], eb[3];
+#pragma unroll
+  for (int dz = 0; dz < 3; ++dz)
+  {
+    const int iz = min(lz + dz, hz);
+    const uint4* src = reinterpret_cast<const uint4*>(g.row3 + (static_cast<size_t>(iz) * g.nx + lx) * g.nyp + yb);
+    ea[dz] = __ldg(src);
+    eb[dz] = __ldg(src + 1);
+  }
+#pragma unroll
+  for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+    {
+      const int iy = ly + dy, iz = lz + dz;
+      if (iy <= hy && iz <= hz)
+      {
+        // entry (iy - yb) of the four fetched ones
+        uint32_t start, packed;
+        if (dy == 0)
+        {
+          start = odd ? ea[dz].z : ea[dz].x;
+          packed = odd ? ea[dz].w : ea[dz].y;
+        }
+        else if (dy == 1)
+        {
+          start = odd ? eb[dz].x : ea[dz].z;
+          packed = odd ? eb[dz].y : ea[dz].w;
+        }
+        else
+        {
+          start = odd ? eb[dz].z : eb[dz].x;
+          packed = odd ? eb[dz].w : eb[dz].y;
+        }
+        uint32_t cnt = width == 3 ? (packed >> 21) : (width == 2 ? ((packed >> 10) & 0x7ffu) : (packed & 0x3ffu));
+        const uint32_t sat = width == 1 ? 0x3ffu : 0x7ffu;
+        if (cnt == sat)
+        {
+          // the count did not fit the packed field (very dense cells): read the CSR bounds themselves
+          const int row = (iz * g.ny + iy) * g.nx;
+          start = __ldg(g.cell_start + row + lx);
+          cnt = __ldg(g.cell_start + row + hx + 1) - start;
+        }
+        if (cnt)
+        {
+          sm.rows[nr][lane] = make_uint2(start, start + cnt);
+          ++nr;
+          st_pts += cnt;
+          const uint32_t c4 = (cnt + 3u) >> 2;
+          n_chunks = (c4 > static_cast<uint32_t>(kWcMaxRunChunks) || n_chunks >= kWcOverflow) ? kWcOverflow :
+                                                                                                 n_chunks + static_cast<int>(c4);
+        }
+      }
+    }
+  return nr;
+}
+
+// After the warp's prefix sum: this lane's descriptors go to sm.desc[offset ...).  `whole` (warp-uniform): the chunk
+// list would not fit (very dense maps), so every run becomes one descriptor and offset comes from the prefix sum of nr.
+__device__ __forceinline__ void wc_write_descs(LikChunkSmem& sm, int lane, int nr, int offset, bool whole)
+{
+  int pos = offset;
+  for (int k = 0; k < nr; ++k)
+  {
+    const uint32_t id = static_cast<uint32_t>(k) | (static_cast<uint32_t>(lane) << 4);
+    if (whole)
+    {
+      sm.desc[pos++] = static_cast<uint16_t>(id);
+      continue;
+    }
+    const uint2 run = sm.rows[k][lane];
+    const uint32_t nc = (run.y - run.x + 3u) >> 2;
+    for (uint32_t c = 0; c < nc; ++c) sm.desc[pos++] = static_cast<uint16_t>(id | (c << 9));
+  }
+}
+
+// Phase 2, lane = descriptor: min d^2 over the chunk's (or, in a `whole` round, the run's) map points, merged into
+// the owner eval's slot.
+__device__ __forceinline__ void wc_process(LikChunkSmem& sm, uint32_t d, bool whole, const NnGridDev& g, const LikDev& lp)
+{
+  const int k = static_cast<int>(d & 15u), e = static_cast<int>((d >> 4) & 31u);
+  const uint2 run = sm.rows[k][e];
+  const float qx = sm.qx[e], qy = sm.qy[e], qz = sm.qz[e];
+  uint32_t s0 = run.x, s1 = run.y;
+  if (!whole)
+  {
+    s0 = run.x + 4u * (d >> 9);
+    s1 = (s0 + 4u < run.y) ? s0 + 4u : run.y;
+  }
+  float best = lp.r2;
+  for (uint32_t s = s0; s < s1; s += 4)
+  {
+    float4 mp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (s + u < s1)
+        mp[u] = __ldg(g.pts + s + u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (s + u < s1)
+      {
+        // flann::L2_Simple: sequential float accumulate of squared differences
+        const float dx = fsub(qx, mp[u].x);
+        const float dy = fsub(qy, mp[u].y);
+        const float dz = fsub(qz, mp[u].z);
+        best = fminf(best, fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz)));  // keep d < worst
+      }
+  }
+  if (best < lp.r2)
+    atomicMin(&sm.best[e], __float_as_uint(best));
 }
 
 // --------------------------------------------------------------------------------------------

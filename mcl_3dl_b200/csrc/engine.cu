@@ -250,6 +250,7 @@ struct mcl3dl_engine
   int update_one_sync = 0;  // mcl3dl_measure_update on ONE device: normalise from the device-side total, one host
                             // synchronise instead of two (MCL3DL_UPDATE_ONE_SYNC=1; written without GPU time left in
                             // round 1: off until the f2 parity tests have run with it)
+  int lik_chunks = 0;  // MCL3DL_LIK=chunk in -DMCL3DL_LIK_CHUNKS=1 builds: the warp-chunk likelihood kernel
   int mapping = 1;  // 1 = tuned kernels (lik_kernel_wi + beam_kernel_pl); 0 = the plain group kernels (MCL3DL_MAPPING=group)
 };
 
@@ -334,6 +335,21 @@ int launch_lik_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int
   const int groups = (P + PPB - 1) / PPB;
   const int grid = std::max(1, std::min(groups, c.sm_count * 8));
   const size_t bytes = static_cast<size_t>(N) * 16;
+#if MCL3DL_LIK_CHUNKS
+  if (eng->mapping != 0 && eng->lik_chunks)
+  {
+    if (bytes <= static_cast<size_t>(kMaxStagedSorted))
+    {
+      if (int rc = opt_in_smem(eng, c, lik_kernel_wc<TPP, true>, kMaxStagedSorted)) return rc;
+      lik_kernel_wc<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
+    }
+    else
+    {
+      lik_kernel_wc<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
+    }
+  }
+  else
+#endif
   if (eng->mapping != 0)
   {
     if (bytes <= static_cast<size_t>(kMaxStagedSorted))
@@ -886,6 +902,8 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     eng->zero_copy_max = static_cast<size_t>(std::max(std::atol(v), 0L));
   if (const char* v = std::getenv("MCL3DL_UPDATE_ONE_SYNC"))
     eng->update_one_sync = std::atoi(v) != 0;
+  if (const char* v = std::getenv("MCL3DL_LIK"))
+    eng->lik_chunks = std::strcmp(v, "chunk") == 0;
   if (const char* o = std::getenv("MCL3DL_OVERLAP"))
     eng->overlap = std::atoi(o) != 0;
   if (const char* m = std::getenv("MCL3DL_MAPPING"))

@@ -474,6 +474,148 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
   }
 }
 
+#if MCL3DL_LIK_CHUNKS
+// Warp-chunk likelihood kernel: lik_kernel_wi with phase 2 dealt in chunks of <= 4 map points instead of whole runs
+// (the per-lane pieces and the reasoning are in device_funcs.cuh).  Same results, bit for bit.  Host-verified lane by
+// lane (tests/hostsim: hostsim_lik_wc); not yet run on a GPU, selected with MCL3DL_LIK=chunk in builds that carry it.
+template <int TPP, bool STAGED>
+__global__ void __launch_bounds__(kBlockThreads, 4)
+    lik_kernel_wc(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N, NnGridDev g,
+                  LikDev lp, mcl3dl_result* __restrict__ out, int write_beam_defaults,
+                  unsigned long long* __restrict__ stats)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ float red_f[kBlockThreads / 32];
+  __shared__ uint32_t red_u[3 * kBlockThreads / 32];
+  __shared__ LikChunkSmem wsm_all[kBlockThreads / 32];
+  const float4* pts = scan;
+  if (STAGED && N > 0)
+  {
+    stage_tile(smem_raw, scan, static_cast<uint32_t>(N) * 16u, &bar);
+    pts = reinterpret_cast<const float4*>(smem_raw);
+  }
+  constexpr int PPB = kBlockThreads / TPP;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  LikChunkSmem& sm = wsm_all[tid >> 5];
+  const int sub = tid / TPP;
+  const int l = tid % TPP;
+  const int n_groups = (P + PPB - 1) / PPB;
+  const uint32_t r2_bits = __float_as_uint(lp.r2);
+  uint32_t st_rows = 0, st_pts = 0;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
+  {
+    const int p = grp * PPB + sub;
+    const bool live = p < P;
+    float score = 0.0f;
+    uint32_t cnt = 0, z0 = 0, z1 = 0;
+    F3 pos;
+    Q4 rn;
+    pos.x = pos.y = pos.z = 0.0f;
+    rn.x = rn.y = rn.z = 0.0f;
+    rn.w = 1.0f;
+    if (live)
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(poses + p));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(poses + p) + 1);
+      pos.x = a.x;
+      pos.y = a.y;
+      pos.z = a.z;
+      Q4 q;
+      q.x = b.x;
+      q.y = b.y;
+      q.z = b.z;
+      q.w = b.w;
+      rn = qnormalized(q);  // state_6dof.h:217
+    }
+    // a warp's 32 lanes always belong to one particle (TPP >= 32), so the trip count is warp-uniform
+    for (int jbase = 0; jbase < N; jbase += TPP)
+    {
+      const int j = jbase + l;
+      const bool valid = live && j < N;
+      // ---------------- phase 1: lane = eval (device_funcs.cuh: wc_window)
+      int nr = 0, nc = 0;
+      sm.best[lane] = r2_bits;
+      if (valid)
+      {
+        const float4 sp = pts[j];
+        F3 v;
+        v.x = sp.x;
+        v.y = sp.y;
+        v.z = sp.z;
+        const F3 t = transform_point(rn, pos, v);
+        // PointRepresentation::vectorize with rescale values (mcl_3dl.cpp:1270)
+        const float qx = fmul(t.x, g.wx), qy = fmul(t.y, g.wy), qz = fmul(t.z, g.wz);
+        sm.qx[lane] = qx;
+        sm.qy[lane] = qy;
+        sm.qz[lane] = qz;
+        nr = wc_window(g, lp, qx, qy, qz, lane, sm, st_rows, st_pts, nc);
+      }
+      // ---------------- deal the warp's 4-point chunks to its lanes: one prefix sum carries the chunk counts (low half,
+      // clamped so that 32 lanes cannot overflow it) and the run counts (high half, for the overflow fallback)
+      const uint32_t mine = static_cast<uint32_t>(min(nc, kWcOverflow)) | (static_cast<uint32_t>(nr) << 16);
+      uint32_t incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const uint32_t nbr = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+          incl += nbr;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      const bool whole = (total & 0xffffu) > static_cast<uint32_t>(kWcMaxDesc);  // warp-uniform; only very dense maps
+      const int n_desc = static_cast<int>(whole ? (total >> 16) : (total & 0xffffu));
+      const uint32_t excl = incl - mine;
+      wc_write_descs(sm, lane, nr, static_cast<int>(whole ? (excl >> 16) : (excl & 0xffffu)), whole);
+      __syncwarp();
+      // ---------------- phase 2: lane = chunk of <= 4 consecutive map points
+      for (int it = lane; it < n_desc; it += 32) wc_process(sm, sm.desc[it], whole, g, lp);
+      __syncwarp();
+      // ---------------- owner lane: likelihood.cpp:128-133
+      if (valid)
+      {
+        const float d2 = __uint_as_float(sm.best[lane]);
+        if (d2 < lp.r2)
+        {
+          const float dist = fsub(lp.match_dist_min, fmaxf(__fsqrt_rn(d2), lp.match_dist_flat));
+          if (!(dist < 0.0f))
+          {
+            score = fadd(score, fmul(dist, lp.match_weight));
+            cnt++;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    group_reduce<TPP>(score, cnt, z0, z1, red_f, red_u);
+    if (live && l == 0)
+    {
+      // empty scan -> LidarMeasurementResult(1, 0), likelihood.cpp:111-114
+      out[p].score_like = (N == 0) ? 1.0f : score;
+      out[p].match_cnt = cnt;
+      if (write_beam_defaults)
+      {
+        // no beam scan this update: LidarMeasurementResult(1, 0), beam.cpp:130-133
+        out[p].score_beam = 1.0f;
+        out[p].n_short = 0;
+        out[p].n_hit = 0;
+        out[p].n_long = 0;
+      }
+    }
+  }
+  if (stats)
+  {
+    const uint32_t r = warp_sum_u32(st_rows), q = warp_sum_u32(st_pts);
+    if ((threadIdx.x & 31) == 0)
+    {
+      atomicAdd(stats + 0, static_cast<unsigned long long>(r));
+      atomicAdd(stats + 1, static_cast<unsigned long long>(q));
+    }
+  }
+}
+#endif  // MCL3DL_LIK_CHUNKS
+
 template <int TPP, bool STAGED>
 __global__ void __launch_bounds__(kBlockThreads)
     beam_kernel(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N,

@@ -30,8 +30,10 @@ PKG = os.path.join(ROOT, "mcl_3dl_b200")
 NB_LIB = os.path.join(PKG, "libmcl3dl_b200.so")          # the default build (near-field screens compiled in)
 BASE_LIB = os.path.join(PKG, "libmcl3dl_b200_nb0.so")    # build.build(defines=["MCL3DL_NEAR_BITS=0"], out=...)
 KDSKIP_LIB = os.path.join(PKG, "libmcl3dl_b200_kdskip.so")  # defines=["MCL3DL_KD_SKIP=1"]: KD caster skip-ahead field
+LIKCHUNK_LIB = os.path.join(PKG, "libmcl3dl_b200_likchunks.so")  # defines=["MCL3DL_LIK_CHUNKS=1"]: lik_kernel_wc
 OLD_HOST = {"MCL3DL_TIMING": "1", "MCL3DL_ZEROCOPY_OUT": "0"}  # the host path as it was up to r01x
-VARIANT_BUILDS = {BASE_LIB: ["MCL3DL_NEAR_BITS=0"], KDSKIP_LIB: ["MCL3DL_KD_SKIP=1"]}  # --build-variants (needs nvcc)
+VARIANT_BUILDS = {BASE_LIB: ["MCL3DL_NEAR_BITS=0"], KDSKIP_LIB: ["MCL3DL_KD_SKIP=1"],
+                  LIKCHUNK_LIB: ["MCL3DL_LIK_CHUNKS=1"]}  # --build-variants (needs nvcc)
 
 # name -> (library, environment); every variant states the host-path switches explicitly, so the table does not
 # depend on the engine's defaults.  "base" (the r01x engine) must come first: everything is compared with its records.
@@ -49,12 +51,16 @@ VARIANTS = [
     ("one_sync", NB_LIB, dict(OLD_HOST, MCL3DL_UPDATE_ONE_SYNC="1")),  # fused weight update with one synchronise
     ("kdskip4", KDSKIP_LIB, dict(OLD_HOST)),
     ("kdskip8", KDSKIP_LIB, dict(OLD_HOST, MCL3DL_KD_SKIP_STEPS="8")),
+    # warp-chunk likelihood kernel (phase 2 dealt in 4-point chunks); host counters say chunks ~ runs on c2 (little to
+    # gain there), 275 chunks vs 192 longer runs per round with isotropic weights
+    ("lik_chunk", LIKCHUNK_LIB, dict(OLD_HOST, MCL3DL_LIK="chunk")),
 ]
 # workload -> (bench workload, raycaster, spread override)
 WORKLOADS = [("c2", "c2", "dda", False), ("c3kd", "c3", "kd", False), ("c5", "c5", "dda", False),
-             ("c1kd", "c1", "kd", False), ("c2s", "c2", "dda", True), ("c3", "c3", "dda", False)]
+             ("c1kd", "c1", "kd", False), ("c2s", "c2", "dda", True), ("c3", "c3", "dda", False), ("c2iso", "c2", "dda", False)]
+ISO_WORKLOADS = {"c2iso"}  # dist_weight (1,1,1) instead of the node's (1,1,5): ~3x more map points per eval
 ENV_KEYS = ["MCL3DL_TIMING", "MCL3DL_ZEROCOPY_OUT", "MCL3DL_NEAR_K", "MCL3DL_NEAR_KD_K", "MCL3DL_NEAR_MAX_MB",
-            "MCL3DL_MAPPING", "MCL3DL_KD_SKIP_STEPS", "MCL3DL_UPDATE_ONE_SYNC"]
+            "MCL3DL_MAPPING", "MCL3DL_KD_SKIP_STEPS", "MCL3DL_UPDATE_ONE_SYNC", "MCL3DL_LIK"]
 
 
 def jobs_all():
@@ -87,7 +93,8 @@ def child(job_names, calls):
             continue
         print(json.dumps({"start": [wname, vname]}), flush=True)
         eng = engine.Engine((0,), lib_path=lib)
-        lik = engine.LikParams(dist_weight=bench.DIST_WEIGHT) if (n_lik or caster == "kd") else None
+        dw = (1.0, 1.0, 1.0) if wname in ISO_WORKLOADS else bench.DIST_WEIGHT
+        lik = engine.LikParams(dist_weight=dw) if (n_lik or caster == "kd") else None
         beam = (engine.beam_params_from_reference(num_points_default=max(n_beam, 1), dda_grid_size=dda,
                                                   use_raycast_using_dda=(caster == "dda")) if n_beam else None)
         eng.set_map(s["map"], stamp=1, lik=lik, beam=beam)

@@ -81,5 +81,11 @@ inline unsigned int atomicOr(unsigned int* p, unsigned int v)  // single-threade
   *p |= v;
   return old;
 }
+inline unsigned int atomicMin(unsigned int* p, unsigned int v)  // single-threaded host build
+{
+  const unsigned int old = *p;
+  if (v < old) *p = v;
+  return old;
+}
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }

@@ -30,6 +30,7 @@ struct HostMap
   std::vector<uint32_t> nn_cell_start, dda_cell_start, occ;
   std::vector<float4> nn_pts, dda_pts, raw_pts;
   std::vector<uint32_t> near_lik, near_kd, far_kd;
+  std::vector<uint2> nn_row3;
   NnGridDev nn{};
   DdaGridDev dda{};
   KdRayDev kd{};
@@ -128,8 +129,22 @@ void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_param
     }
     g.cell_start = m.nn_cell_start.data();
     g.pts = m.nn_pts.data();
-    g.row3 = nullptr;  // the window table is only read by the warp-cooperative kernel, not by these functions
-    g.nyp = 0;
+    // window table (engine.cu: nn_row3_kernel), read by the lane-by-lane emulation of the warp-chunk kernel below
+    g.nyp = (g.ny + 4) & ~1;
+    m.nn_row3.assign(static_cast<size_t>(g.nz) * g.nx * g.nyp + 2, make_uint2(0u, 0u));
+    for (int z = 0; z < g.nz; ++z)
+      for (int x = 0; x < g.nx; ++x)
+        for (int y = 0; y < g.ny; ++y)
+        {
+          const size_t cell = (static_cast<size_t>(z) * g.ny + y) * g.nx + x;
+          const uint32_t s0 = m.nn_cell_start[cell];
+          const uint32_t c1 = m.nn_cell_start[cell + std::min(1, g.nx - x)] - s0;
+          const uint32_t c2 = m.nn_cell_start[cell + std::min(2, g.nx - x)] - s0;
+          const uint32_t c3 = m.nn_cell_start[cell + std::min(3, g.nx - x)] - s0;
+          m.nn_row3[(static_cast<size_t>(z) * g.nx + x) * g.nyp + y] =
+              make_uint2(s0, std::min(c1, 0x3ffu) | (std::min(c2, 0x7ffu) << 10) | (std::min(c3, 0x7ffu) << 21));
+        }
+    g.row3 = m.nn_row3.data();
     build_near(m.near_lik, g.near, pts, n, wx, wy, wz, m.lik.rpad, near_k, sc_min, sc_max);
     m.nn = g;
   }
@@ -361,5 +376,117 @@ extern "C" int hostsim_near_query(const mcl3dl_point* map, size_t n, const float
   *cell_out = f.bits ? 1.0f / f.inv_cell : 0.0f;
   for (size_t q = 0; q < nq; ++q)
     maybe_out[q] = near_maybe(f, queries_xyz[3 * q], queries_xyz[3 * q + 1], queries_xyz[3 * q + 2]) ? 1 : 0;
+  return 0;
+}
+
+
+// Lane-by-lane emulation of lik_kernel_wc (kernels.cuh, -DMCL3DL_LIK_CHUNKS=1) with TPP = 32: a warp owns a particle and
+// works on 32 evals per round; the phases between two __syncwarp()s are run for lanes 0..31 in turn, the shuffle prefix
+// sum is a loop.  The per-lane functions are the very ones the kernel calls (device_funcs.cuh: wc_window,
+// wc_write_descs, wc_process).  Scores are summed in scan order, so they must equal the oracle's bit for bit.
+// work[0..4] = window rows, map points scanned, descriptors processed, rounds, rounds that fell back to whole runs.
+extern "C" int hostsim_lik_wc(const mcl3dl_point* map, size_t n, const mcl3dl_lik_params* lp, float cell_factor,
+                              const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts, size_t n_lik,
+                              mcl3dl_result* out, int near_k, uint64_t* work)
+{
+  if (!lp || !out)
+    return -1;
+  HostMap m;
+  build(m, map, n, lp, nullptr, cell_factor, near_k, 0, 0);
+  const NnGridDev& g = m.nn;
+  const LikDev& likp = m.lik;
+  uint64_t wk[5] = {0, 0, 0, 0, 0};
+  const uint32_t r2_bits = __float_as_uint(likp.r2);
+  for (size_t p = 0; p < P; ++p)
+  {
+    F3 pos;
+    pos.x = poses[p].px;
+    pos.y = poses[p].py;
+    pos.z = poses[p].pz;
+    Q4 q;
+    q.x = poses[p].qx;
+    q.y = poses[p].qy;
+    q.z = poses[p].qz;
+    q.w = poses[p].qw;
+    const Q4 rn = qnormalized(q);
+    float score = 0.0f;
+    uint32_t cnt = 0;
+    LikChunkSmem sm;
+    for (size_t jbase = 0; jbase < n_lik; jbase += 32)
+    {
+      int nr[32], nc[32];
+      uint32_t st_rows = 0, st_pts = 0;
+      for (uint16_t& d : sm.desc) d = 0xffffu;  // (k = 15 never occurs: at most 9 runs per eval)
+      // phase 1
+      for (int lane = 0; lane < 32; ++lane)
+      {
+        nr[lane] = nc[lane] = 0;
+        sm.best[lane] = r2_bits;
+        const size_t j = jbase + lane;
+        if (j >= n_lik)
+          continue;
+        F3 v;
+        v.x = lik_pts[j].x;
+        v.y = lik_pts[j].y;
+        v.z = lik_pts[j].z;
+        const F3 t = transform_point(rn, pos, v);
+        const float qx = fmul(t.x, g.wx), qy = fmul(t.y, g.wy), qz = fmul(t.z, g.wz);
+        sm.qx[lane] = qx;
+        sm.qy[lane] = qy;
+        sm.qz[lane] = qz;
+        nr[lane] = wc_window(g, likp, qx, qy, qz, lane, sm, st_rows, st_pts, nc[lane]);
+        if (nr[lane] > kWcMaxRows)
+          return -2;
+      }
+      // the prefix sum of the kernel (chunk counts clamped to 1023 in the low half, run counts in the high half)
+      uint32_t mine[32], incl[32], acc = 0;
+      for (int lane = 0; lane < 32; ++lane)
+      {
+        mine[lane] = static_cast<uint32_t>(std::min(nc[lane], kWcOverflow)) | (static_cast<uint32_t>(nr[lane]) << 16);
+        acc += mine[lane];
+        incl[lane] = acc;
+      }
+      const uint32_t total = incl[31];
+      const bool whole = (total & 0xffffu) > static_cast<uint32_t>(kWcMaxDesc);
+      const int n_desc = static_cast<int>(whole ? (total >> 16) : (total & 0xffffu));
+      if (n_desc > kWcMaxDesc)
+        return -3;
+      for (int lane = 0; lane < 32; ++lane)
+      {
+        const uint32_t excl = incl[lane] - mine[lane];
+        wc_write_descs(sm, lane, nr[lane], static_cast<int>(whole ? (excl >> 16) : (excl & 0xffffu)), whole);
+      }
+      for (int i = 0; i < kWcMaxDesc; ++i)
+        if ((i < n_desc) == (sm.desc[i] == 0xffffu))
+          return -4;  // a hole in, or a write beyond, the descriptor list
+      // phase 2 (any order: the merge is a min)
+      for (int it = n_desc - 1; it >= 0; --it) wc_process(sm, sm.desc[it], whole, g, likp);
+      // owner lanes, in scan order
+      for (int lane = 0; lane < 32 && jbase + lane < n_lik; ++lane)
+      {
+        const float d2 = __uint_as_float(sm.best[lane]);
+        if (d2 < likp.r2)
+        {
+          const float dist = fsub(likp.match_dist_min, fmaxf(__fsqrt_rn(d2), likp.match_dist_flat));
+          if (!(dist < 0.0f))
+          {
+            score = fadd(score, fmul(dist, likp.match_weight));
+            cnt++;
+          }
+        }
+      }
+      wk[0] += st_rows;
+      wk[1] += st_pts;
+      wk[2] += static_cast<uint64_t>(n_desc);
+      wk[3] += 1;
+      wk[4] += whole ? 1 : 0;
+    }
+    std::memset(&out[p], 0, sizeof(out[p]));
+    out[p].score_like = n_lik ? score : 1.0f;
+    out[p].match_cnt = cnt;
+    out[p].score_beam = 1.0f;
+  }
+  if (work)
+    for (int i = 0; i < 5; ++i) work[i] = wk[i];
   return 0;
 }

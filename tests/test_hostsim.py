@@ -200,3 +200,62 @@ def test_near_field_degenerate_maps(hostsim):
     huge = np.array([[0, 0, 0], [3e38, 0, 0]], np.float32)
     maybe, lay, cell = _near_query(huge, (1, 1, 1), 0.2, 2, [[0, 0, 0], [1e30, 5, 5]])
     assert cell == 0.0 and maybe.all()
+
+
+def _lik_wc(map_pts, lik, poses, lik_pts, near_k=2):
+    hs_lib = C.CDLL(LIB)
+    vp, sz = C.c_void_p, C.c_size_t
+    hs_lib.hostsim_lik_wc.argtypes = [vp, sz, vp, C.c_float, vp, sz, vp, sz, vp, C.c_int, vp]
+    map_pts = np.ascontiguousarray(map_pts, dtype=synth.POINT)
+    poses = np.ascontiguousarray(poses, dtype=synth.POSE)
+    lik_pts = np.ascontiguousarray(lik_pts, dtype=synth.POINT)
+    out = np.zeros(len(poses), dtype=synth.RESULT)
+    wk = np.zeros(5, dtype=np.uint64)
+    p = lambda a: a.ctypes.data_as(vp) if a.size else None  # noqa: E731
+    rc = hs_lib.hostsim_lik_wc(p(map_pts), len(map_pts), C.byref(lik), 1.0, p(poses), len(poses), p(lik_pts), len(lik_pts),
+                               p(out), near_k, p(wk))
+    assert rc == 0, rc
+    return out, wk
+
+
+@pytest.mark.parametrize("seed,w,spread,n_lik,near_k", [(31, (1, 1, 1), False, 96, 2), (32, (1, 1, 5), False, 70, 0),
+                                                        (33, (1, 1, 5), True, 33, 2), (34, (2, 1, 3), True, 128, 1)])
+def test_warp_chunk_likelihood_rounds_match_oracle(hostsim, port, seed, w, spread, n_lik, near_k):
+    """lik_kernel_wc emulated lane by lane (window-table fetch, chunk dealing, chunk processing, owner update) against
+    the oracle: bit-exact, since the emulation sums in scan order.  n_lik not a multiple of 32 leaves idle lanes."""
+    s = synth.scene(40_000, 24, n_lik, 0, spread=spread, seed=seed)
+    lik = engine.LikParams(dist_weight=w)
+    cpu = port.create(s["map"], cc.lik_params(dist_weight=w), None, 20.0, 0.4 if min(w) >= 1 else 1.0)
+    want = cpu.measure(s["particles"], s["lik"], None, s["origins"])
+    got, wk = _lik_wc(s["map"], lik, s["particles"], s["lik"], near_k)
+    assert np.array_equal(got["match_cnt"], want["match_cnt"]) and np.array_equal(got["score_like"], want["score_like"])
+    assert want["match_cnt"].sum() > 0 and wk[4] == 0          # no overflow fallback on voxel-filtered maps
+    plain, _, wk_plain = hostsim(s["map"], lik, None, s["particles"], s["lik"], None, s["origins"], near=(near_k, 0), work=True)
+    assert np.array_equal(plain["score_like"], got["score_like"])
+    assert wk[1] == wk_plain[1]                                 # the same map points are scanned, just dealt differently
+
+
+@pytest.mark.parametrize("name", ["room_iso", "room_aniso", "room_spread"])
+def test_warp_chunk_likelihood_rounds_match_reference_goldens(hostsim, name):
+    g = golden(name + ".npz")
+    lik = engine.LikParams(dist_weight=tuple(float(v) for v in g["dist_weight"]))
+    got, _ = _lik_wc(g["map"], lik, g["particles"], g["lik"])
+    assert np.array_equal(got["match_cnt"], g["result"]["match_cnt"])
+    assert np.allclose(got["score_like"], g["result"]["score_like"], rtol=1e-6)   # the reference sums in the same order
+
+
+def test_warp_chunk_overflow_falls_back_to_whole_runs(hostsim, port):
+    """A raw cloud with thousands of points per cell: the 4-point chunk list does not fit, the round is dealt run by
+    run (and the window table's packed counts saturate, so the CSR bounds are read) — same result as the oracle."""
+    rng = np.random.default_rng(91)
+    pts = rng.uniform(0.0, 1.0, (60_000, 3)).astype(np.float32)
+    mp = synth.make_points(pts)
+    P, n_lik = 5, 40
+    poses = synth.make_poses(rng.uniform(0.3, 0.7, (P, 3)), synth.quat_from_rpy(rng.normal(0, 0.3, (P, 3))))
+    scan = synth.make_points(rng.uniform(-0.7, 0.7, (n_lik, 3)))
+    lik = engine.LikParams(dist_weight=(1, 1, 1))
+    cpu = port.create(mp, cc.lik_params(dist_weight=(1, 1, 1)), None, 20.0, 0.4)
+    want = cpu.measure(poses, scan, None, np.zeros((1, 3), np.float32))
+    got, wk = _lik_wc(mp, lik, poses, scan)
+    assert np.array_equal(got["match_cnt"], want["match_cnt"]) and np.array_equal(got["score_like"], want["score_like"])
+    assert wk[4] > 0 and want["match_cnt"].sum() > 0
