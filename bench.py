@@ -421,7 +421,9 @@ def main():
     e2e = {"value": evals_step * args.steps / e2e_s, "unit": "evals/s",
            "h2d_bytes_per_step": world * (P_rank * 32 + n_lik * 16 + n_beam * 16 + len(s["origins"]) * 16),
            "d2h_bytes_per_step": world * P_rank * 24, "ms_per_step": 1e3 * e2e_s / args.steps,
-           "timing": "host wall clock around the synchronous call", "last_call_device_ms": last_call_device_ms}
+           "timing": "host wall clock around the synchronous call", "last_call_device_ms": last_call_device_ms,
+           "d2h_mode": ("kernels store the records straight into the pinned host block" if P_rank <= 8192
+                        else "one D2H copy of the records")}
 
     # ---- e2e with the fused weight update (scope row f2): priors up, posteriors (4 B/particle) back
     prior = np.full(P_rank, 1.0 / max(P_rank, 1), dtype=np.float32)
