@@ -225,6 +225,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="N > 1: how the records are gathered: NCCL all-gather (contract run) or the engine's own "
+                         "peer-memory exchange kernel (experiment, not yet run on hardware)")
     ap.add_argument("--graph", action="store_true",
                     help="experiment: replay the device-resident step as one CUDA graph (not part of the contract run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -275,14 +278,31 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
+    peer_all = None
+    if world > 1 and args.exchange == "peer":
+        # EXPERIMENT (never run): every rank's records are stored into every rank's buffer by one kernel over NVLink;
+        # the CUDA IPC handles of the buffers are the only thing that goes through torch.distributed
+        handle, peer_all = eng.exchange_create(P_rank, world, rank)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        gathered = torch.empty(world * len(handle), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, mine)
+        eng.exchange_open(bytes(gathered.cpu().numpy().tobytes()))
+        dist.barrier()
+
     def step_eager():
+        st = torch.cuda.current_stream().cuda_stream
         eng.measure_device(d_p.data_ptr(), P_rank, d_l.data_ptr(), n_lik, d_b.data_ptr(), n_beam,
-                           d_o.data_ptr(), len(s["origins"]), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                           d_o.data_ptr(), len(s["origins"]), d_out.data_ptr(), st)
         if world > 1:
-            # the one exchange of the path: all-gather of the per-particle records over NVLink (NCCL)
-            sharding.gather_records_device(d_out, d_all)
+            if peer_all is not None:
+                eng.exchange_records(d_out.data_ptr(), P_rank, st)
+            else:
+                # the one exchange of the path: all-gather of the per-particle records over NVLink (NCCL)
+                sharding.gather_records_device(d_out, d_all)
 
     step = step_eager
+    if args.graph and peer_all is not None:
+        raise SystemExit("--graph cannot replay --exchange peer: the step counter is a kernel argument")
     if args.graph:
         # EXPERIMENT (added without GPU time left in round 1, never run): replay the step (both kernels, their
         # fork/join events and the NCCL all-gather) as one CUDA graph, to take the per-step launch work off the CPU
@@ -331,6 +351,21 @@ def main():
     for _ in range(n_extra):
         step()
     barrier()
+
+    exchange_info = None
+    if world > 1:
+        exchange_info = {"mode": args.exchange, "graph": bool(args.graph)}
+        if peer_all is not None:
+            # check the experiment against NCCL on the same records (outside every timed region)
+            class _DevView:  # raw device memory as a torch tensor (CUDA array interface)
+                def __init__(self, ptr, nbytes):
+                    self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+            step_eager()
+            sharding.gather_records_device(d_out, d_all)
+            torch.cuda.synchronize()
+            t_peer = torch.as_tensor(_DevView(peer_all, world * P_rank * 24), device=dev)
+            exchange_info["matches_nccl"] = bool(torch.equal(t_peer, d_all))
+            exchange_info["peer_wait_timed_out"] = eng.exchange_failed()
 
     unit_pts = n_lik if n_lik else n_beam
     evals_step = world * P_rank * unit_pts
@@ -474,7 +509,7 @@ def main():
                 "config": config_dict(args.workload, s, P if scaling == "strong" else P_rank * world, n_lik, n_beam,
                                       spread, dda, info),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu_baseline,
+                "cpu_baseline": cpu_baseline, "exchange": exchange_info,
                 "match_ratio_mean": float(out_host["match_cnt"].mean() / max(n_lik, 1)),
                 "beam_tallies_mean": [float(out_host[f].mean()) for f in ("n_short", "n_hit", "n_long")]}
         print(json.dumps(line))

@@ -214,6 +214,13 @@ struct DeviceCtx
   DevBuf d_partial, d_tickets;  // lane-per-particle kernels: per-CTA partials + per-group ticket counters
   size_t tickets_zeroed = 0;
   std::vector<const void*> smem_opted;  // kernels already opted in to large dynamic shared memory on this device
+  // record exchange over peer memory (one process per GPU, mcl3dl_exchange_*): [world * n_local records | world flags]
+  DevBuf xchg, x_ticket;
+  PeerTable xt{};
+  void* x_opened[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t x_local = 0;   // records per rank
+  uint32_t x_step = 0;
+  bool x_ready = false;
   DevBuf d_stats;            // 5 x uint64 work counters, only written while stats collection is on
   bool stats_on = false;
   unsigned long long* stats_ptr() const { return stats_on ? static_cast<unsigned long long*>(d_stats.p) : nullptr; }
@@ -959,6 +966,14 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     cudaSetDevice(c.dev);
     if (c.stream)
       cudaStreamSynchronize(c.stream);
+    for (void*& o : c.x_opened)
+      if (o)
+      {
+        cudaIpcCloseMemHandle(o);
+        o = nullptr;
+      }
+    free_buf(c.xchg);
+    free_buf(c.x_ticket);
     for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.far_kd, &c.d_poses,
                       &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart})
       free_buf(*b);
@@ -1159,6 +1174,104 @@ int mcl3dl_measure_device(mcl3dl_engine* eng, const mcl3dl_pose* d_poses, size_t
   CK(cudaSetDevice(c.dev));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   return launch_models(eng, c, d_poses, P, d_lik, n_lik, d_beam, n_beam, d_origins_xyz, n_origins, d_out, nullptr, st, false);
+}
+
+// ---- record exchange over peer memory (bench.py --exchange peer; one process per GPU, one device per engine)
+static size_t xchg_flags_offset(size_t n_local, int world)
+{
+  return (static_cast<size_t>(world) * n_local * sizeof(mcl3dl_result) + 255) & ~size_t(255);
+}
+
+int mcl3dl_exchange_create(mcl3dl_engine* eng, size_t n_local, int world, int rank, void* ipc_handle_out, void** d_all_out)
+{
+  if (!eng || eng->devs.size() != 1 || n_local == 0 || world < 1 || world > kMaxPeers || rank < 0 || rank >= world ||
+      !ipc_handle_out || !d_all_out)
+    return MCL3DL_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == MCL3DL_IPC_HANDLE_BYTES, "ipc handle size");
+  DeviceCtx& c = eng->devs[0];
+  CK(cudaSetDevice(c.dev));
+  const size_t flags_off = xchg_flags_offset(n_local, world);
+  const size_t bytes = flags_off + 256;
+  for (void*& o : c.x_opened)
+    if (o)
+    {
+      cudaIpcCloseMemHandle(o);
+      o = nullptr;
+    }
+  free_buf(c.xchg);  // a fresh cudaMalloc: IPC handles name whole allocations
+  int rc = reserve(eng, c.xchg, bytes);
+  if (rc != MCL3DL_OK || (rc = reserve(eng, c.x_ticket, 256)) != MCL3DL_OK)
+    return rc;
+  CK(cudaMemset(c.xchg.p, 0, c.xchg.cap));
+  CK(cudaMemset(c.x_ticket.p, 0, 256));
+  CK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c.xchg.p));
+  std::memcpy(ipc_handle_out, &h, sizeof(h));
+  c.xt = PeerTable{};
+  c.xt.world = world;
+  c.xt.rank = rank;
+  c.x_local = n_local;
+  c.x_step = 0;
+  c.x_ready = false;
+  *d_all_out = c.xchg.p;
+  return MCL3DL_OK;
+}
+
+int mcl3dl_exchange_open(mcl3dl_engine* eng, const void* ipc_handles /* world x MCL3DL_IPC_HANDLE_BYTES, rank order */)
+{
+  if (!eng || eng->devs.size() != 1 || !ipc_handles)
+    return MCL3DL_ERR_INVALID_ARG;
+  DeviceCtx& c = eng->devs[0];
+  if (!c.xchg.p || c.xt.world < 1)
+    return MCL3DL_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c.dev));
+  const size_t flags_off = xchg_flags_offset(c.x_local, c.xt.world);
+  for (int g = 0; g < c.xt.world; ++g)
+  {
+    void* base = c.xchg.p;
+    if (g != c.xt.rank)
+    {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, static_cast<const char*>(ipc_handles) + static_cast<size_t>(g) * sizeof(h), sizeof(h));
+      CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+      c.x_opened[g] = base;
+    }
+    c.xt.records[g] = static_cast<uint2*>(base);
+    c.xt.flags[g] = reinterpret_cast<uint32_t*>(static_cast<char*>(base) + flags_off);
+  }
+  c.x_ready = true;
+  return MCL3DL_OK;
+}
+
+int mcl3dl_exchange_records(mcl3dl_engine* eng, const mcl3dl_result* d_local, size_t n_local, void* cuda_stream)
+{
+  if (!eng || eng->devs.size() != 1 || !d_local)
+    return MCL3DL_ERR_INVALID_ARG;
+  DeviceCtx& c = eng->devs[0];
+  if (!c.x_ready || n_local != c.x_local)
+    return MCL3DL_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c.dev));
+  const size_t n_units = n_local * (sizeof(mcl3dl_result) / sizeof(uint2));
+  const int grid = static_cast<int>(std::min<size_t>((n_units + kBlockThreads - 1) / kBlockThreads, static_cast<size_t>(c.sm_count)));
+  ++c.x_step;
+  exchange_kernel<<<grid, kBlockThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      reinterpret_cast<const uint2*>(d_local), n_units, c.xt, c.x_step, static_cast<unsigned int*>(c.x_ticket.p));
+  CK(cudaGetLastError());
+  eng->launches++;
+  return MCL3DL_OK;
+}
+
+int mcl3dl_exchange_failed(mcl3dl_engine* eng, int* failed_out)
+{
+  if (!eng || eng->devs.size() != 1 || !failed_out || !eng->devs[0].x_ticket.p)
+    return MCL3DL_ERR_INVALID_ARG;
+  DeviceCtx& c = eng->devs[0];
+  CK(cudaSetDevice(c.dev));
+  unsigned int w[2] = {0, 0};
+  CK(cudaMemcpy(w, c.x_ticket.p, sizeof(w), cudaMemcpyDeviceToHost));  // synchronises with the exchanges enqueued so far
+  *failed_out = w[1] != 0;
+  return MCL3DL_OK;
 }
 
 static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts, size_t n_lik,

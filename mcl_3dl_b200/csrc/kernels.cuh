@@ -1032,4 +1032,70 @@ __global__ void weight_finish_kernel(WeightPartial* __restrict__ partials, int n
   partials[n] = t;
 }
 
+// --------------------------------------------------------------------------------------------
+// Record exchange over peer memory (one process per GPU; replaces the NCCL all-gather of the 24-byte records).
+// Every rank owns a buffer [G * n_local records | G flags] that its peers have mapped (CUDA IPC over NVLink/NVSwitch).
+// One launch per rank and step: (1) store the rank's records into slot `rank` of EVERY rank's buffer (plain 8-byte
+// stores, P2P writes for the peers); (2) the last CTA to finish releases flag[rank] = step in every buffer and then
+// spins until all G flags of its OWN buffer show this step — so when the kernel retires, this rank's copy of the whole
+// record array is complete, with no host involvement and no second launch.
+// Ordering: data stores -> __threadfence_system() -> CTA barrier -> ticket -> st.release.sys of the flag; the consumer
+// side is ld.acquire.sys in the spin loop.  Not yet run on hardware (written after round 1's GPU budget was spent).
+constexpr int kMaxPeers = 8;
+struct PeerTable
+{
+  uint2* records[kMaxPeers];    // base of every rank's record array (this rank's own pointer at [rank])
+  uint32_t* flags[kMaxPeers];   // base of every rank's flag array
+  int world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kBlockThreads)
+    exchange_kernel(const uint2* __restrict__ local, size_t n_units /* n_local * 3 */, PeerTable t, uint32_t step,
+                    unsigned int* __restrict__ ticket /* [0] ticket, [1] set to 1 if a peer never showed up */)
+{
+  const size_t base = static_cast<size_t>(t.rank) * n_units;
+  for (size_t i = blockIdx.x * static_cast<size_t>(kBlockThreads) + threadIdx.x; i < n_units;
+       i += static_cast<size_t>(gridDim.x) * kBlockThreads)
+  {
+    const uint2 v = local[i];
+    for (int g = 0; g < t.world; ++g) t.records[g][base + i] = v;
+  }
+  __threadfence_system();
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last)
+    return;
+  if (threadIdx.x == 0)
+    *ticket = 0;  // ready for the next launch (stream order)
+  if (threadIdx.x < t.world)
+  {
+    __threadfence_system();
+    st_release_sys(t.flags[threadIdx.x] + t.rank, step);
+    const uint32_t* mine = t.flags[t.rank] + threadIdx.x;
+    // steps increase monotonically; the difference is taken modulo 2^32
+    // (bounded: a peer that died must not hang this GPU — a few seconds at ~1 us per poll, then the error word is set)
+    long polls = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(mine) - step) < 0)
+      if (++polls > (1L << 22))
+      {
+        atomicExch(ticket + 1, 1u);
+        break;
+      }
+  }
+}
+
 }  // namespace mcl3dl

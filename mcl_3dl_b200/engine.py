@@ -75,7 +75,8 @@ class WorkStats(C.Structure):
 EXPORTED_SYMBOLS = ["mcl3dl_measure_update", "mcl3dl_collect_stats", "mcl3dl_read_stats", "mcl3dl_abi_version", "mcl3dl_create", "mcl3dl_destroy", "mcl3dl_set_map", "mcl3dl_set_params",
                     "mcl3dl_measure", "mcl3dl_measure_device", "mcl3dl_beam_status",
                     "mcl3dl_beam_params_from_reference", "mcl3dl_get_map_info", "mcl3dl_last_timing",
-                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_collect_timing"]
+                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_collect_timing",
+                    "mcl3dl_exchange_create", "mcl3dl_exchange_open", "mcl3dl_exchange_records", "mcl3dl_exchange_failed"]
 
 _LIBS = {}
 
@@ -118,6 +119,10 @@ def load_library(path=None):
     L.mcl3dl_last_error_detail.argtypes = [vp]
     L.mcl3dl_last_error_detail.restype = C.c_char_p
     L.mcl3dl_collect_timing.argtypes = [vp, C.c_int]
+    L.mcl3dl_exchange_create.argtypes = [vp, sz, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.mcl3dl_exchange_open.argtypes = [vp, vp]
+    L.mcl3dl_exchange_records.argtypes = [vp, vp, sz, vp]
+    L.mcl3dl_exchange_failed.argtypes = [vp, C.POINTER(C.c_int)]
     L.mcl3dl_near_field_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
     assert L.mcl3dl_abi_version() == 2
     _LIBS[path] = L
@@ -274,6 +279,29 @@ class Engine:
         ws = WorkStats()
         self._check(self.L.mcl3dl_read_stats(self.h, C.byref(ws)))
         return ws.as_dict()
+
+    # ---- record exchange over peer memory (one process per GPU; see include/mcl3dl_b200.h)
+    IPC_HANDLE_BYTES = 64
+
+    def exchange_create(self, n_local, world, rank):
+        """Returns (ipc_handle bytes, device address of this rank's [world * n_local] record array)."""
+        h = (C.c_ubyte * self.IPC_HANDLE_BYTES)()
+        d_all = C.c_void_p()
+        self._check(self.L.mcl3dl_exchange_create(self.h, n_local, world, rank, h, C.byref(d_all)))
+        return bytes(h), d_all.value
+
+    def exchange_open(self, handles):
+        """handles: the world ranks' ipc handles concatenated in rank order (bytes)."""
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        self._check(self.L.mcl3dl_exchange_open(self.h, buf))
+
+    def exchange_records(self, d_local, n_local, stream=0):
+        self._check(self.L.mcl3dl_exchange_records(self.h, d_local, n_local, stream))
+
+    def exchange_failed(self):
+        f = C.c_int(0)
+        self._check(self.L.mcl3dl_exchange_failed(self.h, C.byref(f)))
+        return bool(f.value)
 
     def collect_timing(self, enable=True):
         """Record the per-call CUDA timing events read by last_timing() (off by default: ~28 us per update)."""
