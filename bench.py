@@ -282,7 +282,8 @@ def main():
     if world > 1 and args.exchange == "peer":
         # EXPERIMENT (never run): every rank's records are stored into every rank's buffer by one kernel over NVLink;
         # the CUDA IPC handles of the buffers are the only thing that goes through torch.distributed
-        handle, peer_all = eng.exchange_create(P_rank, world, rank)
+        handle = eng.exchange_create(P_rank, world, rank)
+        peer_all = 0  # device address of the last gathered array, returned by every exchange_records call
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
         gathered = torch.empty(world * len(handle), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(gathered, mine)
@@ -290,12 +291,13 @@ def main():
         dist.barrier()
 
     def step_eager():
+        nonlocal peer_all
         st = torch.cuda.current_stream().cuda_stream
         eng.measure_device(d_p.data_ptr(), P_rank, d_l.data_ptr(), n_lik, d_b.data_ptr(), n_beam,
                            d_o.data_ptr(), len(s["origins"]), d_out.data_ptr(), st)
         if world > 1:
             if peer_all is not None:
-                eng.exchange_records(d_out.data_ptr(), P_rank, st)
+                peer_all = eng.exchange_records(d_out.data_ptr(), P_rank, st)
             else:
                 # the one exchange of the path: all-gather of the per-particle records over NVLink (NCCL)
                 sharding.gather_records_device(d_out, d_all)

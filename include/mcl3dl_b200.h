@@ -223,17 +223,18 @@ int mcl3dl_get_map_info(const mcl3dl_engine*, mcl3dl_map_info* out);
  * 24-byte records, then the unchanged weight update of include/mcl_3dl/pf.h:252-279 on the full array).  Instead of an
  * NCCL all-gather, one kernel per rank stores the rank's records into every rank's buffer over NVLink and waits, on the
  * device, until the other ranks have done the same.  Engines with exactly one device; world <= 8.
- *   create:  allocates this rank's [world * n_local] record buffer (returned in d_all_out, device memory) and writes its
- *            CUDA IPC handle (MCL3DL_IPC_HANDLE_BYTES) for the caller to all-gather between the processes;
+ *   create:  allocates this rank's buffer (two [world * n_local] record arrays used alternately, plus flags) and writes
+ *            its CUDA IPC handle (MCL3DL_IPC_HANDLE_BYTES) for the caller to all-gather between the processes;
  *   open:    maps the other ranks' buffers from the gathered handles (rank order);
  *   records: enqueues the exchange of d_local (n_local records, device memory) on the caller's stream; when it retires,
- *            d_all holds every rank's records in rank order;
+ *            *d_all_out (device memory, valid until the call after next) holds every rank's records in rank order;
  *   failed:  1 if a peer did not show up within the kernel's bounded wait (synchronises).
  * Written after round 1's GPU budget was spent: not yet run on hardware (bench.py --exchange peer). */
 #define MCL3DL_IPC_HANDLE_BYTES 64
-int mcl3dl_exchange_create(mcl3dl_engine*, size_t n_local, int world, int rank, void* ipc_handle_out, void** d_all_out);
+int mcl3dl_exchange_create(mcl3dl_engine*, size_t n_local, int world, int rank, void* ipc_handle_out);
 int mcl3dl_exchange_open(mcl3dl_engine*, const void* ipc_handles);
-int mcl3dl_exchange_records(mcl3dl_engine*, const mcl3dl_result* d_local, size_t n_local, void* cuda_stream);
+int mcl3dl_exchange_records(mcl3dl_engine*, const mcl3dl_result* d_local, size_t n_local, void* cuda_stream,
+                            const mcl3dl_result** d_all_out);
 int mcl3dl_exchange_failed(mcl3dl_engine*, int* failed_out);
 
 /* The near-field screens staged by the last set_map ([0] likelihood search, [1] KD-tree raycaster's marching search):

@@ -1179,13 +1179,13 @@ int mcl3dl_measure_device(mcl3dl_engine* eng, const mcl3dl_pose* d_poses, size_t
 // ---- record exchange over peer memory (bench.py --exchange peer; one process per GPU, one device per engine)
 static size_t xchg_flags_offset(size_t n_local, int world)
 {
-  return (static_cast<size_t>(world) * n_local * sizeof(mcl3dl_result) + 255) & ~size_t(255);
+  return (2 * static_cast<size_t>(world) * n_local * sizeof(mcl3dl_result) + 255) & ~size_t(255);  // two arrays, by step parity
 }
 
-int mcl3dl_exchange_create(mcl3dl_engine* eng, size_t n_local, int world, int rank, void* ipc_handle_out, void** d_all_out)
+int mcl3dl_exchange_create(mcl3dl_engine* eng, size_t n_local, int world, int rank, void* ipc_handle_out)
 {
   if (!eng || eng->devs.size() != 1 || n_local == 0 || world < 1 || world > kMaxPeers || rank < 0 || rank >= world ||
-      !ipc_handle_out || !d_all_out)
+      !ipc_handle_out)
     return MCL3DL_ERR_INVALID_ARG;
   static_assert(sizeof(cudaIpcMemHandle_t) == MCL3DL_IPC_HANDLE_BYTES, "ipc handle size");
   DeviceCtx& c = eng->devs[0];
@@ -1214,7 +1214,6 @@ int mcl3dl_exchange_create(mcl3dl_engine* eng, size_t n_local, int world, int ra
   c.x_local = n_local;
   c.x_step = 0;
   c.x_ready = false;
-  *d_all_out = c.xchg.p;
   return MCL3DL_OK;
 }
 
@@ -1244,7 +1243,8 @@ int mcl3dl_exchange_open(mcl3dl_engine* eng, const void* ipc_handles /* world x 
   return MCL3DL_OK;
 }
 
-int mcl3dl_exchange_records(mcl3dl_engine* eng, const mcl3dl_result* d_local, size_t n_local, void* cuda_stream)
+int mcl3dl_exchange_records(mcl3dl_engine* eng, const mcl3dl_result* d_local, size_t n_local, void* cuda_stream,
+                            const mcl3dl_result** d_all_out)
 {
   if (!eng || eng->devs.size() != 1 || !d_local)
     return MCL3DL_ERR_INVALID_ARG;
@@ -1259,6 +1259,8 @@ int mcl3dl_exchange_records(mcl3dl_engine* eng, const mcl3dl_result* d_local, si
       reinterpret_cast<const uint2*>(d_local), n_units, c.xt, c.x_step, static_cast<unsigned int*>(c.x_ticket.p));
   CK(cudaGetLastError());
   eng->launches++;
+  if (d_all_out)
+    *d_all_out = static_cast<const mcl3dl_result*>(c.xchg.p) + static_cast<size_t>(c.x_step & 1u) * c.xt.world * n_local;
   return MCL3DL_OK;
 }
 

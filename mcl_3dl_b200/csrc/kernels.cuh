@@ -1034,7 +1034,9 @@ __global__ void weight_finish_kernel(WeightPartial* __restrict__ partials, int n
 
 // --------------------------------------------------------------------------------------------
 // Record exchange over peer memory (one process per GPU; replaces the NCCL all-gather of the 24-byte records).
-// Every rank owns a buffer [G * n_local records | G flags] that its peers have mapped (CUDA IPC over NVLink/NVSwitch).
+// Every rank owns a buffer [2 x G * n_local records | G flags] that its peers have mapped (CUDA IPC over NVLink/NVSwitch);
+// the two record arrays alternate by step, so a peer that is already one step ahead writes the OTHER array while this
+// rank still reads the last one (it cannot get two steps ahead: its next exchange waits for this rank's next flag).
 // One launch per rank and step: (1) store the rank's records into slot `rank` of EVERY rank's buffer (plain 8-byte
 // stores, P2P writes for the peers); (2) the last CTA to finish releases flag[rank] = step in every buffer and then
 // spins until all G flags of its OWN buffer show this step — so when the kernel retires, this rank's copy of the whole
@@ -1064,7 +1066,8 @@ __global__ void __launch_bounds__(kBlockThreads)
     exchange_kernel(const uint2* __restrict__ local, size_t n_units /* n_local * 3 */, PeerTable t, uint32_t step,
                     unsigned int* __restrict__ ticket /* [0] ticket, [1] set to 1 if a peer never showed up */)
 {
-  const size_t base = static_cast<size_t>(t.rank) * n_units;
+  // array (step & 1) of every buffer, slot `rank` inside it
+  const size_t base = (static_cast<size_t>(step & 1u) * t.world + t.rank) * n_units;
   for (size_t i = blockIdx.x * static_cast<size_t>(kBlockThreads) + threadIdx.x; i < n_units;
        i += static_cast<size_t>(gridDim.x) * kBlockThreads)
   {

@@ -119,9 +119,9 @@ def load_library(path=None):
     L.mcl3dl_last_error_detail.argtypes = [vp]
     L.mcl3dl_last_error_detail.restype = C.c_char_p
     L.mcl3dl_collect_timing.argtypes = [vp, C.c_int]
-    L.mcl3dl_exchange_create.argtypes = [vp, sz, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.mcl3dl_exchange_create.argtypes = [vp, sz, C.c_int, C.c_int, vp]
     L.mcl3dl_exchange_open.argtypes = [vp, vp]
-    L.mcl3dl_exchange_records.argtypes = [vp, vp, sz, vp]
+    L.mcl3dl_exchange_records.argtypes = [vp, vp, sz, vp, C.POINTER(vp)]
     L.mcl3dl_exchange_failed.argtypes = [vp, C.POINTER(C.c_int)]
     L.mcl3dl_near_field_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
     assert L.mcl3dl_abi_version() == 2
@@ -284,11 +284,10 @@ class Engine:
     IPC_HANDLE_BYTES = 64
 
     def exchange_create(self, n_local, world, rank):
-        """Returns (ipc_handle bytes, device address of this rank's [world * n_local] record array)."""
+        """Allocates this rank's exchange buffer; returns its CUDA IPC handle (bytes) for the ranks to all-gather."""
         h = (C.c_ubyte * self.IPC_HANDLE_BYTES)()
-        d_all = C.c_void_p()
-        self._check(self.L.mcl3dl_exchange_create(self.h, n_local, world, rank, h, C.byref(d_all)))
-        return bytes(h), d_all.value
+        self._check(self.L.mcl3dl_exchange_create(self.h, n_local, world, rank, h))
+        return bytes(h)
 
     def exchange_open(self, handles):
         """handles: the world ranks' ipc handles concatenated in rank order (bytes)."""
@@ -296,7 +295,10 @@ class Engine:
         self._check(self.L.mcl3dl_exchange_open(self.h, buf))
 
     def exchange_records(self, d_local, n_local, stream=0):
-        self._check(self.L.mcl3dl_exchange_records(self.h, d_local, n_local, stream))
+        """Enqueue the exchange; returns the device address that holds all ranks' records once the stream gets there."""
+        d_all = C.c_void_p()
+        self._check(self.L.mcl3dl_exchange_records(self.h, d_local, n_local, stream, C.byref(d_all)))
+        return d_all.value
 
     def exchange_failed(self):
         f = C.c_int(0)
