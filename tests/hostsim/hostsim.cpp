@@ -1,10 +1,11 @@
 // hostsim.cpp — TEST INFRASTRUCTURE ONLY.
 //
 // Compiles the product's per-thread device functions (mcl_3dl_b200/csrc/device_math.cuh, device_funcs.cuh) for the
-// HOST through cuda_shim.h and drives them over host-built copies of the two device grids, one (particle, point) at a
+// HOST through cuda_shim.h and drives them over host-built copies of the device grids, one (particle, point) at a
 // time.  tests/test_hostsim.py compares the result with the oracle: a way to check edits to cast_ray / cast_ray_kd /
-// nn_dist2 / nn_search_arg / the transform without a GPU.  The warp-cooperative parts of the kernels (staging,
-// window-table phase, reductions) are NOT covered here; the GPU parity suite covers those.
+// nn_dist2 / nn_search_arg / the transform / the near-field screens without a GPU.  Of the warp-cooperative kernel
+// code, the rounds of the prepared lik_kernel_wc are emulated lane by lane (hostsim_lik_wc: window-table fetch,
+// descriptor dealing, chunk processing); TMA staging, shuffles and the CTA reductions are only covered by the GPU suite.
 // The grid construction below restates what engine.cu's build kernels do (same cell functions, same stable order).
 #include "cuda_shim.h"
 #ifndef MCL3DL_NEAR_BITS
