@@ -19,7 +19,8 @@ from oracle import cpu_checker as cc
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HS = os.path.join(ROOT, "tests", "hostsim")
 LIB = os.path.join(HS, "libhostsim.so")
-DEPS = [os.path.join(HS, "hostsim.cpp"), os.path.join(HS, "cuda_shim.h"),
+DEPS = [os.path.join(HS, "hostsim.cpp"), os.path.join(HS, "pf_hostsim.cpp"), os.path.join(HS, "cuda_shim.h"),
+        os.path.join(ROOT, "mcl_3dl_b200", "csrc", "pf_funcs.cuh"),
         os.path.join(ROOT, "mcl_3dl_b200", "csrc", "device_funcs.cuh"),
         os.path.join(ROOT, "mcl_3dl_b200", "csrc", "device_math.cuh"), os.path.join(ROOT, "include", "mcl3dl_b200.h")]
 
@@ -28,7 +29,7 @@ DEPS = [os.path.join(HS, "hostsim.cpp"), os.path.join(HS, "cuda_shim.h"),
 def hostsim():
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
         r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB,
-                            os.path.join(HS, "hostsim.cpp")], capture_output=True, text=True)
+                            os.path.join(HS, "hostsim.cpp"), os.path.join(HS, "pf_hostsim.cpp")], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
     L = C.CDLL(LIB)
     vp, sz = C.c_void_p, C.c_size_t
@@ -259,3 +260,197 @@ def test_warp_chunk_overflow_falls_back_to_whole_runs(hostsim, port):
     got, wk = _lik_wc(mp, lik, poses, scan)
     assert np.array_equal(got["match_cnt"], want["match_cnt"]) and np.array_equal(got["score_like"], want["score_like"])
     assert wk[4] > 0 and want["match_cnt"].sum() > 0
+
+
+# ------------------------------------------------------------------ scope row f3 groundwork (csrc/pf_funcs.cuh)
+def _pf_lib():
+    L = C.CDLL(LIB)
+    vp, sz = C.c_void_p, C.c_size_t
+    L.hostsim_pf_predict.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, vp, sz]
+    L.hostsim_pf_resample_ref_rng.argtypes = [vp, vp, sz, C.c_uint, vp, vp, vp, vp, vp, vp]
+    L.hostsim_pf_resample_philox.argtypes = [vp, vp, sz, C.c_float, C.c_uint64, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
+    L.hostsim_philox.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.hostsim_philox.restype = None
+    L.hostsim_noise6.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, vp, vp]
+    L.hostsim_noise6.restype = None
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _motion_states(n, seed):
+    rng = np.random.default_rng(seed)
+    st = np.zeros(n, dtype=cc.MOTION_STATE)
+    st["pos"] = rng.uniform(-20, 20, (n, 3))
+    q = rng.normal(0, 1, (n, 4))
+    st["rot"] = q / np.linalg.norm(q, axis=1, keepdims=True) * rng.uniform(0.98, 1.02, (n, 1))   # nearly unit, as in the node
+    for f in ("noise_ll", "noise_la", "noise_al", "noise_aa"):
+        st[f] = rng.normal(0, 0.05, n)
+    st["odom_err_integ_lin"] = rng.normal(0, 0.1, (n, 3))
+    st["odom_err_integ_ang"] = rng.normal(0, 0.1, (n, 3))
+    return st
+
+
+@pytest.mark.parametrize("seed,turn", [(1, 0.3), (2, -2.9), (3, 0.0), (4, 3.1)])
+def test_pf_predict_on_host_equals_oracle(hostsim, port, seed, turn):
+    """pf_predict + pf_set_odoms (MotionPredictionModelDifferentialDrive::setOdoms / predict) bit for bit against the
+    port, which is pinned to the reference build (test_oracle_golden.py)."""
+    L = _pf_lib()
+    rng = np.random.default_rng(100 + seed)
+    q0 = synth.quat_from_rpy(np.array([[0.02, -0.01, 0.4]]))[0]
+    q1 = synth.quat_from_rpy(np.array([[0.01, 0.03, 0.4 + turn]]))[0]
+    prev = synth.make_poses(np.array([[1.0, 2.0, 0.1]]), q0[None])
+    cur = synth.make_poses(np.array([[1.0, 2.0, 0.1]]) + rng.normal(0, 0.2 if turn else 0.0, (1, 3)), q1[None])
+    st = _motion_states(500, seed)
+    want = port.motion_predict(prev, cur, 0.1, 10.0, 10.0, st.copy())
+    got = st.copy()
+    assert L.hostsim_pf_predict(_ptr(prev), _ptr(cur), 0.1, 10.0, 10.0, _ptr(got), len(got)) == 0
+    assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("n,seed,sigma", [(64, 12345, 0.0), (64, 7, 0.05), (1000, 99, 0.02), (4096, 5, 0.1), (3, 1, 0.3)])
+def test_pf_resample_on_host_equals_oracle(hostsim, port, n, seed, sigma):
+    """pf_pick + pf_add_noise with the reference's random stream: the resampled State6DOF set of
+    pf::ParticleFilter::resample (pf.h:182-225) bit for bit, including which outputs count as duplicates."""
+    L = _pf_lib()
+    rng = np.random.default_rng(seed)
+    probs = rng.uniform(0.05, 1.0, n).astype(np.float32) ** 3        # skewed weights: many duplicates
+    probs /= probs.sum(dtype=np.float32)
+    assert (np.diff(np.cumsum(probs, dtype=np.float32)) > 0).all()   # no accumulated-probability ties (see the test below)
+    st = _motion_states(n, seed + 1)
+    sp = np.array([sigma, sigma, sigma / 2], np.float32)
+    sr = np.array([0.0, sigma / 4, sigma], np.float32)               # one zero sigma: that draw is skipped
+    want_s, want_p = port.pf_resample_6dof(probs, st, seed, sp, sr)
+    got = np.zeros(n, dtype=cc.MOTION_STATE)
+    got_p = np.zeros(n, np.float32)
+    src = np.zeros(n, np.uint32)
+    dup = np.zeros(n, np.uint8)
+    assert L.hostsim_pf_resample_ref_rng(_ptr(probs), _ptr(st), n, seed, _ptr(sp), _ptr(sr), _ptr(got), _ptr(got_p), _ptr(src),
+                                         _ptr(dup)) == 0
+    assert got.tobytes() == want_s.tobytes() and np.array_equal(got_p, want_p)
+    assert (np.diff(src.astype(np.int64)) >= 0).all() and dup.sum() > 0 or n <= 3
+
+
+def test_pf_resample_ties_go_to_the_lowest_index(hostsim, port):
+    """Documented departure: a particle whose weight is below half an ulp of the running sum leaves accum unchanged, so
+    two particles tie in the reference's std::sort key; which of them std::lower_bound then meets first is up to the
+    (unstable) sort.  The device takes the lowest index, i.e. the particle that actually carries the weight.  Outside
+    such tie groups the picks are the reference's."""
+    L = _pf_lib()
+    n, seed = 4096, 5
+    rng = np.random.default_rng(seed)
+    probs = rng.uniform(0.01, 1.0, n).astype(np.float32) ** 4
+    probs /= probs.sum(dtype=np.float32)
+    accum = np.zeros(n, np.float32)
+    a = np.float32(0)
+    for i in range(n):
+        a = np.float32(a + probs[i])
+        accum[i] = a
+    tie_with_prev = np.concatenate([[False], np.diff(accum) == 0])
+    assert tie_with_prev.sum() > 50
+    st = _motion_states(n, seed + 1)
+    zero = np.zeros(3, np.float32)
+    want_s, _ = port.pf_resample_6dof(probs, st, seed, zero, zero)     # sigma 0: picks only
+    got = np.zeros(n, dtype=cc.MOTION_STATE)
+    got_p = np.zeros(n, np.float32)
+    src = np.zeros(n, np.uint32)
+    dup = np.zeros(n, np.uint8)
+    assert L.hostsim_pf_resample_ref_rng(_ptr(probs), _ptr(st), n, seed, _ptr(zero), _ptr(zero), _ptr(got), _ptr(got_p), _ptr(src),
+                                         _ptr(dup)) == 0
+    assert not tie_with_prev[src].any()                                 # never a weightless member of a tie group
+    differs = np.array([got[i].tobytes() != want_s[i].tobytes() for i in range(n)])
+    in_tie_group = tie_with_prev[np.minimum(src + 1, n - 1)]            # the pick heads a tie group
+    dup_b = dup.astype(bool)
+    # a disagreement needs a tie group at the pick; duplicates differ only through normalize() of the copied state
+    assert (~differs | in_tie_group | dup_b).all()
+    assert differs.sum() < tie_with_prev.sum() + dup_b.sum()
+
+
+def test_philox_known_answers(hostsim):
+    """Philox-4x32-10 against the Random123 known-answer vectors."""
+    L = _pf_lib()
+    for ctr, key, want in [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+                           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+                           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+                            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]:
+        c = np.array(ctr, dtype=np.uint32)
+        L.hostsim_philox(_ptr(c), key[0], key[1])
+        assert tuple(int(v) for v in c) == want
+
+
+def test_device_noise_is_normal_and_independent(hostsim):
+    """pf_noise6 (Philox + Box-Muller): zero mean, the requested sigmas, uncorrelated components, different streams per
+    output index and per call, and bit-reproducible."""
+    L = _pf_lib()
+    sigma = np.array([0.1, 0.2, 0.05, 0.0, 0.02, 0.3], np.float32)
+    n = 60_000
+    out = np.zeros((n, 6), np.float32)
+    o = np.zeros(6, np.float32)
+    for i in range(n):
+        L.hostsim_noise6(1234567890123, i, 7, _ptr(sigma), _ptr(o))
+        out[i] = o
+    assert (out[:, 3] == 0).all()                                       # sigma == 0: no noise
+    live = [0, 1, 2, 4, 5]
+    assert np.allclose(out[:, live].mean(0), 0, atol=5 * sigma[live].max() / np.sqrt(n))
+    assert np.allclose(out[:, live].std(0), sigma[live], rtol=0.02)
+    corr = np.corrcoef(out[:, live].T)
+    assert np.abs(corr - np.eye(5)).max() < 0.02
+    from scipy import stats
+    for k in live:
+        assert stats.kstest(out[:, k] / sigma[k], "norm").pvalue > 1e-3
+    L.hostsim_noise6(1234567890123, 5, 7, _ptr(sigma), _ptr(o))
+    assert np.array_equal(o, out[5])                                    # reproducible
+    L.hostsim_noise6(1234567890123, 5, 8, _ptr(sigma), _ptr(o))
+    assert not np.array_equal(o, out[5])                                # next resampling call: new numbers
+
+
+def test_pf_resample_device_semantics(hostsim, port):
+    """The device's own resampling (host-drawn initial offset, Philox noise): the picks equal the reference's systematic
+    picks for the same offset, duplicates get noise of the right size, plain copies are untouched."""
+    L = _pf_lib()
+    n = 2000
+    rng = np.random.default_rng(3)
+    probs = rng.uniform(0.01, 1.0, n).astype(np.float32) ** 3
+    probs /= probs.sum(dtype=np.float32)
+    st = _motion_states(n, 8)
+    sp = np.array([0.05, 0.05, 0.01], np.float32)
+    sr = np.array([0.0, 0.0, 0.02], np.float32)
+    out = np.zeros(n, dtype=cc.MOTION_STATE)
+    out_p = np.zeros(n, np.float32)
+    src = np.zeros(n, np.uint32)
+    dup = np.zeros(n, np.uint8)
+    noise = np.zeros((n, 6), np.float32)
+    assert L.hostsim_pf_resample_philox(_ptr(probs), _ptr(st), n, 0.37, 42, 1, _ptr(sp), _ptr(sr), _ptr(out), _ptr(out_p),
+                                        _ptr(src), _ptr(dup), _ptr(noise)) == 0
+    # systematic picks, restated with numpy on the sequential float prefix sum
+    accum = np.zeros(n, np.float32)
+    a = np.float32(0)
+    for i in range(n):
+        a = np.float32(a + probs[i])
+        accum[i] = a
+    pstep = np.float32(a / np.float32(n))
+    pscan = (pstep * np.arange(n, dtype=np.float32) + np.float32(np.float32(0.37) * pstep)).astype(np.float32)
+    want_src = np.searchsorted(accum, pscan, side="left")
+    assert (want_src < n).all() and np.array_equal(src, want_src)
+    want_dup = np.concatenate([[want_src[0] == 0], want_src[1:] == want_src[:-1]])
+    assert np.array_equal(dup.astype(bool), want_dup)
+    plain = ~want_dup
+    assert out[plain].tobytes() == st[want_src[plain]].tobytes()        # copies are bit-identical
+    d = out["pos"][want_dup] - st["pos"][want_src[want_dup]]
+    assert np.allclose(d, noise[want_dup][:, :3], atol=1e-5)
+    assert 0.8 * sp[0] < d[:, 0].std() < 1.2 * sp[0] and abs(d[:, 0].mean()) < 0.01
+    assert (out["noise_ll"][want_dup] == 0).all()                       # duplicates are fresh states
+    assert np.allclose(np.linalg.norm(out["rot"][want_dup], axis=1), 1.0, atol=1e-5)
+    assert np.all(out_p == np.float32(1.0 / n))
+
+
+def test_pf_funcs_compile_for_sm_100a(tmp_path):
+    """The f3 groundwork is device code: nvcc must accept it for sm_100a with the product's flags (no GPU needed)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-std=c++17", "-c",
+                        "-o", str(tmp_path / "pf.o"), os.path.join(HS, "pf_compile_check.cu")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
