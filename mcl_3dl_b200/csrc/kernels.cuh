@@ -478,6 +478,9 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
 // Warp-chunk likelihood kernel: lik_kernel_wi with phase 2 dealt in chunks of <= 4 map points instead of whole runs
 // (the per-lane pieces and the reasoning are in device_funcs.cuh).  Same results, bit for bit.  Host-verified lane by
 // lane (tests/hostsim: hostsim_lik_wc); not yet run on a GPU, selected with MCL3DL_LIK=chunk in builds that carry it.
+// (Deliberately a copy of lik_kernel_wi around a different round: sharing the body through one device-function template
+// changed the SASS of the validated lik_kernel_wi<256,*> / <32,*> instantiations — profiles/sass_fingerprint.py — so the
+// two are to be merged when a GPU is at hand to re-validate.)
 template <int TPP, bool STAGED>
 __global__ void __launch_bounds__(kBlockThreads, 4)
     lik_kernel_wc(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N, NnGridDev g,
