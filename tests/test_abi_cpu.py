@@ -119,3 +119,25 @@ def test_bound_measure_call_resolves_buffers_once():
     with pytest.raises(ValueError):
         e.bind_measure(s["particles"], s["lik"], None, None, out[:4])           # one record per particle
     e.h = None  # nothing to destroy
+
+
+def test_kernels_match_the_last_gpu_validated_fingerprint():
+    """Informational guard: profiles/r01y_sass_fingerprint.txt holds per-kernel SASS hashes of the build that last ran on
+    a B200.  A kernel that differs has not been validated on hardware yet: re-run the GPU suite, then regenerate the file
+    (python profiles/sass_fingerprint.py).  Reported as xfail, never as a failure."""
+    import shutil
+    import sys
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import sass_fingerprint as sf
+    from mcl_3dl_b200 import engine
+    engine.load_library()   # builds if stale
+    want = dict(line.split() for line in open(os.path.join(ROOT, "profiles", "r01y_sass_fingerprint.txt"))
+                if line.strip() and not line.startswith("#"))
+    got = sf.fingerprints(sf.DEFAULT)
+    changed = sorted(k for k in got if k in want and want[k] != got[k])
+    added = sorted(k for k in got if k not in want)
+    if changed or added:
+        pytest.xfail("kernels not yet validated on a GPU: %d changed, %d new (%s)"
+                     % (len(changed), len(added), ", ".join(n[:40] for n in (changed + added)[:4])))
