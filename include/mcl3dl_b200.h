@@ -219,6 +219,46 @@ void mcl3dl_beam_params_from_reference(mcl3dl_beam_params* out,
 
 int mcl3dl_get_map_info(const mcl3dl_engine*, mcl3dl_map_info* out);
 
+/* ---- Resident particle set (PREPARED in round 1 after the GPU budget was spent: the per-particle
+ * arithmetic is verified on the host bit for bit against the oracle, the kernels and this plumbing have not run yet).
+ * The particles of pf::ParticleFilter<State6DOF> stay in device memory between updates, so an update moves only the
+ * scans and the odometry in and a summary out.  Engines with exactly one device.
+ *
+ * mcl3dl_state = the State6DOF fields that prediction, measurement and resampling touch
+ * (include/mcl_3dl/state_6dof.h:55-63): pos_, rot_ (x y z w), noise_ll_/la_/al_/aa_, odom_err_integ_lin_/_ang_. */
+typedef struct
+{
+  float pos[3];
+  float rot[4];
+  float noise_ll, noise_la, noise_al, noise_aa;
+  float odom_err_integ_lin[3];
+  float odom_err_integ_ang[3];
+} mcl3dl_state; /* 68 bytes */
+
+/* pf_->init()/resizeParticle() happen on the host; set() uploads the result (states + probability_), get() reads the
+ * set back (either pointer may be NULL) — e.g. for pf_->expectationBiased()/covariance(), which stay host code. */
+int mcl3dl_particles_set(mcl3dl_engine*, const mcl3dl_state* states, const float* prob, size_t n_particles);
+int mcl3dl_particles_get(mcl3dl_engine*, mcl3dl_state* states, float* prob, size_t n_particles);
+/* pf_->predict(motion_prediction_model) for MotionPredictionModelDifferentialDrive: setOdoms(odom_prev, odom_current,
+ * time_diff) + predict() per particle (motion_prediction_models/motion_prediction_model_differential_drive.h:46-67;
+ * src/mcl_3dl.cpp:227-232).  odom_* : position + rotation of the two odometry states. */
+int mcl3dl_particles_predict(mcl3dl_engine*, const mcl3dl_pose* odom_prev, const mcl3dl_pose* odom_current, float time_diff,
+                             float odom_err_integ_lin_tc, float odom_err_integ_ang_tc);
+/* pf_->measure(measure_func) of src/mcl_3dl.cpp:398-426 on the resident set: both models, the odometry-error factor
+ * NormalLikelihood(odom_err_integ_lin_sigma)(|odom_err_integ_lin_|) (sigma <= 0: factor 1), prior * likelihood,
+ * normalisation, entropy, match-ratio min/max, arg max.  The posterior replaces the resident probabilities (or the
+ * prior is kept when no particle survives, pf.h:274-278). */
+int mcl3dl_particles_measure_update(mcl3dl_engine*, const mcl3dl_point* lik_pts, size_t n_lik, const mcl3dl_point* beam_pts,
+                                    size_t n_beam, const float* origins_xyz, size_t n_origins, float odom_err_integ_lin_sigma,
+                                    mcl3dl_update_summary* summary);
+/* pf_->resample(State6DOF(sigma_pos, sigma_rpy)) (pf.h:182-225, src/mcl_3dl.cpp:809-815): sequential float prefix sum,
+ * systematic pick from initial_p = initial_frac * pstep (the host draws initial_frac in [0, 1) with the node's engine),
+ * noise on duplicates only, probability 1 / n.  Documented departures: the noise comes from a counter-based generator
+ * (Philox-4x32-10 keyed by seed, output index and call count) instead of std::default_random_engine's stream, and
+ * particles that tie in the accumulated probability are taken by lowest index instead of std::sort's order. */
+int mcl3dl_particles_resample(mcl3dl_engine*, const float sigma_pos[3], const float sigma_rpy[3], float initial_frac,
+                              uint64_t seed);
+
 /* Record exchange over peer memory for the one-process-per-GPU layout (particles sharded, ONE gather of the
  * 24-byte records, then the unchanged weight update of include/mcl_3dl/pf.h:252-279 on the full array).  Instead of an
  * NCCL all-gather, one kernel per rank stores the rank's records into every rank's buffer over NVLink and waits, on the

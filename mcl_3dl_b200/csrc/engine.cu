@@ -16,6 +16,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "kernels.cuh"
+#include "pf_kernels.cuh"
 
 using namespace mcl3dl;
 
@@ -214,6 +215,12 @@ struct DeviceCtx
   DevBuf d_partial, d_tickets;  // lane-per-particle kernels: per-CTA partials + per-group ticket counters
   size_t tickets_zeroed = 0;
   std::vector<const void*> smem_opted;  // kernels already opted in to large dynamic shared memory on this device
+  // resident particle set (mcl3dl_particles_*): two state buffers (resampling writes the other one), probabilities,
+  // prefix sum + pstep, the packed poses / odometry-error factors the measurement kernels read
+  DevBuf r_states[2], r_prob, r_accum, r_poses, r_extra;
+  size_t r_n = 0;
+  int r_cur = 0;
+  uint32_t r_calls = 0;
   // record exchange over peer memory (one process per GPU, mcl3dl_exchange_*): [world * n_local records | world flags]
   DevBuf xchg, x_ticket;
   PeerTable xt{};
@@ -974,6 +981,8 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
       }
     free_buf(c.xchg);
     free_buf(c.x_ticket);
+    for (DevBuf* b : {&c.r_states[0], &c.r_states[1], &c.r_prob, &c.r_accum, &c.r_poses, &c.r_extra})
+      free_buf(*b);
     for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.far_kd, &c.d_poses,
                       &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart})
       free_buf(*b);
@@ -1174,6 +1183,168 @@ int mcl3dl_measure_device(mcl3dl_engine* eng, const mcl3dl_pose* d_poses, size_t
   CK(cudaSetDevice(c.dev));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   return launch_models(eng, c, d_poses, P, d_lik, n_lik, d_beam, n_beam, d_origins_xyz, n_origins, d_out, nullptr, st, false);
+}
+
+// ---- resident particle set (scope row f3; prepared, not yet run on hardware — see include/mcl3dl_b200.h)
+int mcl3dl_particles_set(mcl3dl_engine* eng, const mcl3dl_state* states, const float* prob, size_t n)
+{
+  if (!eng || eng->devs.size() != 1 || !states || !prob || n == 0 || n >= (size_t(1) << 31))
+    return MCL3DL_ERR_INVALID_ARG;
+  DeviceCtx& c = eng->devs[0];
+  CK(cudaSetDevice(c.dev));
+  int rc;
+  if ((rc = reserve(eng, c.r_states[0], n * sizeof(mcl3dl_state))) || (rc = reserve(eng, c.r_states[1], n * sizeof(mcl3dl_state))) ||
+      (rc = reserve(eng, c.r_prob, n * 4)) || (rc = reserve(eng, c.r_accum, (n + 1) * 4)) ||
+      (rc = reserve(eng, c.r_poses, n * sizeof(mcl3dl_pose))) || (rc = reserve(eng, c.r_extra, n * 4)))
+    return rc;
+  CK(cudaMemcpyAsync(c.r_states[0].p, states, n * sizeof(mcl3dl_state), cudaMemcpyHostToDevice, c.stream));
+  CK(cudaMemcpyAsync(c.r_prob.p, prob, n * 4, cudaMemcpyHostToDevice, c.stream));
+  CK(cudaStreamSynchronize(c.stream));  // the caller's buffers are pageable and only read during the call
+  c.r_n = n;
+  c.r_cur = 0;
+  return MCL3DL_OK;
+}
+
+int mcl3dl_particles_get(mcl3dl_engine* eng, mcl3dl_state* states, float* prob, size_t n)
+{
+  if (!eng || eng->devs.size() != 1)
+    return MCL3DL_ERR_INVALID_ARG;
+  DeviceCtx& c = eng->devs[0];
+  if (c.r_n == 0 || n != c.r_n)
+    return MCL3DL_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c.dev));
+  if (states)
+    CK(cudaMemcpyAsync(states, c.r_states[c.r_cur].p, n * sizeof(mcl3dl_state), cudaMemcpyDeviceToHost, c.stream));
+  if (prob)
+    CK(cudaMemcpyAsync(prob, c.r_prob.p, n * 4, cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
+  return MCL3DL_OK;
+}
+
+int mcl3dl_particles_predict(mcl3dl_engine* eng, const mcl3dl_pose* a, const mcl3dl_pose* b, float time_diff, float tc_lin,
+                             float tc_ang)
+{
+  if (!eng || eng->devs.size() != 1 || !a || !b)
+    return MCL3DL_ERR_INVALID_ARG;
+  DeviceCtx& c = eng->devs[0];
+  if (c.r_n == 0)
+    return MCL3DL_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c.dev));
+  const float pp[3] = {a->px, a->py, a->pz}, pq[4] = {a->qx, a->qy, a->qz, a->qw};
+  const float cp[3] = {b->px, b->py, b->pz}, cq[4] = {b->qx, b->qy, b->qz, b->qw};
+  const MotionDev m = pf_set_odoms(pp, pq, cp, cq, time_diff, tc_lin, tc_ang);
+  const uint32_t n = static_cast<uint32_t>(c.r_n);
+  pf_predict_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(static_cast<PfState*>(c.r_states[c.r_cur].p), n, m);
+  CK(cudaGetLastError());
+  eng->launches++;
+  return MCL3DL_OK;  // stream-ordered before whatever comes next; get() / measure_update() synchronise
+}
+
+int mcl3dl_particles_resample(mcl3dl_engine* eng, const float sigma_pos[3], const float sigma_rpy[3], float initial_frac,
+                              uint64_t seed)
+{
+  if (!eng || eng->devs.size() != 1 || !sigma_pos || !sigma_rpy || !(initial_frac >= 0.0f) || !(initial_frac < 1.0f))
+    return MCL3DL_ERR_INVALID_ARG;
+  DeviceCtx& c = eng->devs[0];
+  if (c.r_n == 0)
+    return MCL3DL_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c.dev));
+  const uint32_t n = static_cast<uint32_t>(c.r_n);
+  float* accum = static_cast<float*>(c.r_accum.p);
+  pf_accum_kernel<<<1, 32, 0, c.stream>>>(static_cast<const float*>(c.r_prob.p), n, accum, accum + n);
+  Sigma6 sg;
+  for (int k = 0; k < 3; ++k)
+  {
+    sg.v[k] = sigma_pos[k];
+    sg.v[k + 3] = sigma_rpy[k];
+  }
+  ++c.r_calls;
+  pf_resample_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(static_cast<const PfState*>(c.r_states[c.r_cur].p), accum, accum + n, n,
+                                                           initial_frac, seed, c.r_calls, sg,
+                                                           static_cast<PfState*>(c.r_states[1 - c.r_cur].p),
+                                                           static_cast<float*>(c.r_prob.p));
+  CK(cudaGetLastError());
+  eng->launches += 2;
+  c.r_cur = 1 - c.r_cur;
+  return MCL3DL_OK;
+}
+
+int mcl3dl_particles_measure_update(mcl3dl_engine* eng, const mcl3dl_point* lik_pts, size_t n_lik, const mcl3dl_point* beam_pts,
+                                    size_t n_beam, const float* origins_xyz, size_t n_origins, float odom_err_lin_sigma,
+                                    mcl3dl_update_summary* summary)
+{
+  if (!eng || eng->devs.size() != 1 || !summary)
+    return MCL3DL_ERR_INVALID_ARG;
+  DeviceCtx& c = eng->devs[0];
+  const size_t P = c.r_n;
+  int rc = validate_measure(eng, P, n_lik, n_beam, n_origins);
+  if (rc != MCL3DL_OK)
+    return rc;
+  if (P == 0 || (n_lik && !lik_pts) || (n_beam && (!beam_pts || !origins_xyz)))
+    return MCL3DL_ERR_INVALID_ARG;
+  for (size_t j = 0; j < n_beam; ++j)
+    if (beam_pts[j].label >= n_origins)
+      return MCL3DL_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c.dev));
+  cudaStream_t st = c.stream;
+  // scans + origins up in one block (as in mcl3dl_measure); the poses come from the resident states
+  const size_t o_beam = n_lik * 16, o_org = o_beam + n_beam * 16, in_bytes = o_org + ((n_origins * 12 + 15) & ~size_t(15));
+  const int nblk = static_cast<int>(std::min<size_t>((P + kBlockThreads - 1) / kBlockThreads, static_cast<size_t>(c.sm_count) * 4));
+  if ((rc = reserve_pinned(eng, c, in_bytes + 2 * sizeof(WeightPartial) + 64)) || (rc = reserve(eng, c.d_poses, in_bytes + 16)) ||
+      (rc = reserve(eng, c.d_out, P * sizeof(mcl3dl_result))) || (rc = reserve(eng, c.d_w, P * 4)) ||
+      (rc = reserve(eng, c.d_wpart, 2 * (nblk + 1) * sizeof(WeightPartial))))
+    return rc;
+  char* hp = static_cast<char*>(c.h_pinned);
+  if (n_lik) std::memcpy(hp, lik_pts, n_lik * 16);
+  if (n_beam) std::memcpy(hp + o_beam, beam_pts, n_beam * 16);
+  if (n_origins) std::memcpy(hp + o_org, origins_xyz, n_origins * 12);
+  if (in_bytes) CK(cudaMemcpyAsync(c.d_poses.p, hp, in_bytes, cudaMemcpyHostToDevice, st));
+  // NormalLikelihood(sigma): a_ = float(1 / sqrt(2 pi s^2)), sq2_ = float(2 s^2) (include/mcl_3dl/nd.h:45-49)
+  const bool with_odom = odom_err_lin_sigma > 0.0f;
+  const double sg = static_cast<double>(odom_err_lin_sigma);
+  const float nd_a = with_odom ? static_cast<float>(1.0 / std::sqrt(2.0 * M_PI * sg * sg)) : 1.0f;
+  const float nd_sq2 = with_odom ? static_cast<float>(sg * sg * 2.0) : 1.0f;
+  const uint32_t n32 = static_cast<uint32_t>(P);
+  pf_pack_kernel<<<(n32 + 255) / 256, 256, 0, st>>>(static_cast<const PfState*>(c.r_states[c.r_cur].p), n32, nd_a, nd_sq2,
+                                                  static_cast<mcl3dl_pose*>(c.r_poses.p),
+                                                  with_odom ? static_cast<float*>(c.r_extra.p) : nullptr);
+  CK(cudaGetLastError());
+  eng->launches++;
+  const char* d_in = static_cast<const char*>(c.d_poses.p);
+  rc = launch_models(eng, c, static_cast<const mcl3dl_pose*>(c.r_poses.p), P, reinterpret_cast<const mcl3dl_point*>(d_in), n_lik,
+                     reinterpret_cast<const mcl3dl_point*>(d_in + o_beam), n_beam, reinterpret_cast<const float*>(d_in + o_org),
+                     n_origins, static_cast<mcl3dl_result*>(c.d_out.p), nullptr, st, false);
+  if (rc != MCL3DL_OK)
+    return rc;
+  // prior * likelihood from the resident probabilities; the posterior is written over them (the weights were read
+  // into d_w first); a vanished total leaves them untouched = the reference's "restore" (pf.h:274-278)
+  WeightPartial* parts = static_cast<WeightPartial*>(c.d_wpart.p);
+  WeightPartial* parts2 = parts + nblk + 1;
+  weight_kernel<<<nblk, kBlockThreads, 0, st>>>(static_cast<const mcl3dl_result*>(c.d_out.p), static_cast<const float*>(c.r_prob.p),
+                                               with_odom ? static_cast<const float*>(c.r_extra.p) : nullptr, static_cast<int>(P),
+                                               static_cast<int>(n_lik), static_cast<float*>(c.d_w.p), parts);
+  weight_finish_kernel<<<1, 32, 0, st>>>(parts, nblk);
+  normalize_kernel_dev<<<nblk, kBlockThreads, 0, st>>>(static_cast<const float*>(c.d_w.p), static_cast<int>(P), parts + nblk, 0,
+                                                      static_cast<float*>(c.r_prob.p), parts2);
+  weight_finish_kernel<<<1, 32, 0, st>>>(parts2, nblk);
+  CK(cudaGetLastError());
+  eng->launches += 4;
+  char* h_tot = hp + in_bytes;
+  CK(cudaMemcpyAsync(h_tot, parts + nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_tot + sizeof(WeightPartial), parts2 + nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  WeightPartial w1, w2;
+  std::memcpy(&w1, h_tot, sizeof(w1));
+  std::memcpy(&w2, h_tot + sizeof(w1), sizeof(w2));
+  std::memset(summary, 0, sizeof(*summary));
+  const float total_f = static_cast<float>(w1.sum);
+  summary->weight_sum = total_f;
+  summary->match_ratio_min = std::min(1.0f, w1.qmin);
+  summary->match_ratio_max = std::max(0.0f, w1.qmax);
+  summary->kept = total_f > 0.0f ? 1 : 0;
+  summary->entropy = summary->kept ? static_cast<float>(-w2.sum) : 0.0f;
+  summary->max_index = summary->kept ? w2.best_i : 0;
+  return MCL3DL_OK;
 }
 
 // ---- record exchange over peer memory (bench.py --exchange peer; one process per GPU, one device per engine)

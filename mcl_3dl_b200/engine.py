@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 from . import build as _build
-from .synth import POINT, POSE, RESULT
+from .synth import POINT, POSE, RESULT, STATE
 
 ERR = {0: "ok", -1: "invalid argument", -2: "measure() before set_map()", -3: "CUDA runtime error",
        -4: "no usable CUDA device", -5: "grid exceeds 2^31-1 cells", -6: "search radius out of range"}
@@ -76,7 +76,9 @@ EXPORTED_SYMBOLS = ["mcl3dl_measure_update", "mcl3dl_collect_stats", "mcl3dl_rea
                     "mcl3dl_measure", "mcl3dl_measure_device", "mcl3dl_beam_status",
                     "mcl3dl_beam_params_from_reference", "mcl3dl_get_map_info", "mcl3dl_last_timing",
                     "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_collect_timing",
-                    "mcl3dl_exchange_create", "mcl3dl_exchange_open", "mcl3dl_exchange_records", "mcl3dl_exchange_failed"]
+                    "mcl3dl_exchange_create", "mcl3dl_exchange_open", "mcl3dl_exchange_records", "mcl3dl_exchange_failed",
+                    "mcl3dl_particles_set", "mcl3dl_particles_get", "mcl3dl_particles_predict",
+                    "mcl3dl_particles_measure_update", "mcl3dl_particles_resample"]
 
 _LIBS = {}
 
@@ -119,6 +121,11 @@ def load_library(path=None):
     L.mcl3dl_last_error_detail.argtypes = [vp]
     L.mcl3dl_last_error_detail.restype = C.c_char_p
     L.mcl3dl_collect_timing.argtypes = [vp, C.c_int]
+    L.mcl3dl_particles_set.argtypes = [vp, vp, vp, sz]
+    L.mcl3dl_particles_get.argtypes = [vp, vp, vp, sz]
+    L.mcl3dl_particles_predict.argtypes = [vp, vp, vp, C.c_float, C.c_float, C.c_float]
+    L.mcl3dl_particles_measure_update.argtypes = [vp, vp, sz, vp, sz, vp, sz, C.c_float, vp]
+    L.mcl3dl_particles_resample.argtypes = [vp, vp, vp, C.c_float, C.c_uint64]
     L.mcl3dl_exchange_create.argtypes = [vp, sz, C.c_int, C.c_int, vp]
     L.mcl3dl_exchange_open.argtypes = [vp, vp]
     L.mcl3dl_exchange_records.argtypes = [vp, vp, sz, vp, C.POINTER(vp)]
@@ -279,6 +286,40 @@ class Engine:
         ws = WorkStats()
         self._check(self.L.mcl3dl_read_stats(self.h, C.byref(ws)))
         return ws.as_dict()
+
+    # ---- resident particle set (scope row f3; prepared, see include/mcl3dl_b200.h)
+    def particles_set(self, states, prob):
+        states = np.ascontiguousarray(states, dtype=STATE)
+        prob = np.ascontiguousarray(prob, dtype=np.float32)
+        assert len(states) == len(prob)
+        self._check(self.L.mcl3dl_particles_set(self.h, _ptr(states), _ptr(prob), len(states)))
+        self._n_resident = len(states)
+
+    def particles_get(self):
+        states = np.zeros(self._n_resident, dtype=STATE)
+        prob = np.zeros(self._n_resident, dtype=np.float32)
+        self._check(self.L.mcl3dl_particles_get(self.h, _ptr(states), _ptr(prob), len(states)))
+        return states, prob
+
+    def particles_predict(self, odom_prev, odom_current, time_diff, tc_lin, tc_ang):
+        a = np.ascontiguousarray(odom_prev, dtype=POSE).reshape(1)
+        b = np.ascontiguousarray(odom_current, dtype=POSE).reshape(1)
+        self._check(self.L.mcl3dl_particles_predict(self.h, _ptr(a), _ptr(b), time_diff, tc_lin, tc_ang))
+
+    def particles_measure_update(self, lik_pts, beam_pts, origins, odom_err_integ_lin_sigma=0.0):
+        lik_pts = np.ascontiguousarray(lik_pts if lik_pts is not None else np.zeros(0, POINT), dtype=POINT)
+        beam_pts = np.ascontiguousarray(beam_pts if beam_pts is not None else np.zeros(0, POINT), dtype=POINT)
+        origins = np.ascontiguousarray(origins if origins is not None else np.zeros((0, 3)), dtype=np.float32).reshape(-1, 3)
+        summ = UpdateSummary()
+        self._check(self.L.mcl3dl_particles_measure_update(self.h, _ptr(lik_pts), len(lik_pts), _ptr(beam_pts), len(beam_pts),
+                                                           _ptr(origins), len(origins), odom_err_integ_lin_sigma,
+                                                           C.byref(summ)))
+        return summ.as_dict()
+
+    def particles_resample(self, sigma_pos, sigma_rpy, initial_frac, seed):
+        sp = np.ascontiguousarray(sigma_pos, dtype=np.float32)
+        sr = np.ascontiguousarray(sigma_rpy, dtype=np.float32)
+        self._check(self.L.mcl3dl_particles_resample(self.h, _ptr(sp), _ptr(sr), initial_frac, seed))
 
     # ---- record exchange over peer memory (one process per GPU; see include/mcl3dl_b200.h)
     IPC_HANDLE_BYTES = 64

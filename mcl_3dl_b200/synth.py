@@ -14,6 +14,9 @@ import numpy as np
 POINT = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("label", "<u4")])
 POSE = np.dtype([("px", "<f4"), ("py", "<f4"), ("pz", "<f4"), ("_pad", "<f4"),
                  ("qx", "<f4"), ("qy", "<f4"), ("qz", "<f4"), ("qw", "<f4")])
+# mcl3dl_state: the State6DOF fields the resident particle set keeps (include/mcl3dl_b200.h), 68 bytes
+STATE = np.dtype([("pos", "<f4", 3), ("rot", "<f4", 4), ("noise_ll", "<f4"), ("noise_la", "<f4"), ("noise_al", "<f4"),
+                  ("noise_aa", "<f4"), ("odom_err_integ_lin", "<f4", 3), ("odom_err_integ_ang", "<f4", 3)])
 RESULT = np.dtype([("score_like", "<f4"), ("match_cnt", "<u4"), ("score_beam", "<f4"),
                    ("n_short", "<u4"), ("n_hit", "<u4"), ("n_long", "<u4")])
 
