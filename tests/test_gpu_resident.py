@@ -144,8 +144,10 @@ def test_resample_picks_are_the_reference_systematic_picks(eng_mod, n, frac):
     assert (np.diff(accum) > 0).all()
     pstep = np.float32(a / np.float32(n))
     pscan = (pstep * np.arange(n, dtype=np.float32) + np.float32(np.float32(frac) * pstep)).astype(np.float32)
-    src = np.minimum(np.searchsorted(accum, pscan, side="left"), n - 1)
-    dup = np.concatenate([[src[0] == 0], src[1:] == src[:-1]])
+    ss = np.searchsorted(accum, pscan, side="left")
+    found = ss < n                                                       # past the end: the last particle found (pf.h:208-212)
+    src = np.where(found, ss, ss[found][-1] if found.any() else 0)
+    dup = np.concatenate([[ss[0] == 0], ss[1:] == ss[:-1]]) & found
     plain = ~dup
     assert out[plain].tobytes() == st[src[plain]].tobytes()             # copies are bit-identical
     assert np.all(out_p == np.float32(1.0 / n))

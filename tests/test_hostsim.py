@@ -454,3 +454,67 @@ def test_pf_funcs_compile_for_sm_100a(tmp_path):
     r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-std=c++17", "-c",
                         "-o", str(tmp_path / "pf.o"), os.path.join(HS, "pf_compile_check.cu")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_pf_pick_past_the_end_takes_the_last_particle_found(hostsim):
+    """pstep * i + initial_p can round above the last accumulated probability: the reference then copies the particle of
+    it_prev, without noise (pf.h:208-212).  Forced here with initial_frac one ulp below 1."""
+    L = _pf_lib()
+    frac = np.float32(0.99999994)
+    hits = 0
+    for seed in range(400):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(2, 300))
+        prob = rng.uniform(0.05, 1.0, n).astype(np.float32)
+        acc = np.zeros(n, np.float32)
+        a = np.float32(0)
+        for i in range(n):
+            a = np.float32(a + prob[i])
+            acc[i] = a
+        pstep = np.float32(a / np.float32(n))
+        pscan = (pstep * np.arange(n, dtype=np.float32) + np.float32(frac * pstep)).astype(np.float32)
+        ss = np.searchsorted(acc, pscan, side="left")
+        found = ss < n
+        if found.all():
+            continue
+        hits += 1
+        want = np.where(found, ss, ss[found][-1] if found.any() else 0)
+        want_dup = np.concatenate([[ss[0] == 0], ss[1:] == ss[:-1]]) & found
+        st = np.zeros(n, dtype=cc.MOTION_STATE)
+        st["rot"][:, 3] = 1
+        out = np.zeros(n, dtype=cc.MOTION_STATE)
+        out_p = np.zeros(n, np.float32)
+        src = np.zeros(n, np.uint32)
+        dup = np.zeros(n, np.uint8)
+        z = np.zeros(3, np.float32)
+        assert L.hostsim_pf_resample_philox(_ptr(prob), _ptr(st), n, float(frac), 1, 1, _ptr(z), _ptr(z), _ptr(out), _ptr(out_p),
+                                            _ptr(src), _ptr(dup), None) == 0
+        assert np.array_equal(src, want) and np.array_equal(dup.astype(bool), want_dup)
+    assert hits > 20
+
+
+def test_pf_resample_equals_oracle_on_many_small_sets(hostsim, port):
+    """Several hundred random particle sets of 2..40 particles (unnormalised weights included): bit-identical to the oracle,
+    including the quirk that output 0 counts as a duplicate whenever it picks particle 0."""
+    L = _pf_lib()
+    dup0 = 0
+    for seed in range(600):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(2, 40))
+        prob = (rng.uniform(0.05, 1.0, n) ** int(rng.integers(1, 4))).astype(np.float32)
+        if seed % 3 == 0:
+            prob = (prob / prob.sum(dtype=np.float32)).astype(np.float32)
+        if not (np.diff(np.cumsum(prob, dtype=np.float32)) > 0).all():
+            continue
+        st = _motion_states(n, seed)
+        sg = np.full(3, 0.01 if seed % 2 else 0.0, np.float32)
+        want, _ = port.pf_resample_6dof(prob, st, seed, sg, sg)
+        got = np.zeros(n, dtype=cc.MOTION_STATE)
+        got_p = np.zeros(n, np.float32)
+        src = np.zeros(n, np.uint32)
+        dup = np.zeros(n, np.uint8)
+        assert L.hostsim_pf_resample_ref_rng(_ptr(prob), _ptr(st), n, seed, _ptr(sg), _ptr(sg), _ptr(got), _ptr(got_p), _ptr(src),
+                                             _ptr(dup)) == 0
+        assert got.tobytes() == want.tobytes(), seed
+        dup0 += int(dup[0])
+    assert dup0 > 100
