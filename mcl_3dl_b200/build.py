@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcl3dl_b200.so")
 SOURCES = [os.path.join(CSRC, "engine.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "device_funcs.cuh"),
-                  os.path.join(CSRC, "device_math.cuh"),
+                  os.path.join(CSRC, "device_math.cuh"), os.path.join(CSRC, "pf_kernels.cuh"), os.path.join(CSRC, "pf_funcs.cuh"),
                   os.path.join(os.path.dirname(HERE), "include", "mcl3dl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
