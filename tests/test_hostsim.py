@@ -518,3 +518,22 @@ def test_pf_resample_equals_oracle_on_many_small_sets(hostsim, port):
         assert got.tobytes() == want.tobytes(), seed
         dup0 += int(dup[0])
     assert dup0 > 100
+
+
+def test_screens_and_skip_ahead_randomized_differential(hostsim):
+    """Forty random configurations (map size, metric weights, match radius, map grid, caster, tracking / spread poses):
+    every near-field / skip-ahead setting returns the records and per-ray status of the unscreened searches."""
+    for seed in range(40):
+        rng = np.random.default_rng(seed)
+        n_map = int(rng.choice([500, 5000, 30000]))
+        w = [(1, 1, 1), (1, 1, 5), (2, 1, 3), (0.5, 2, 1)][seed % 4]
+        s = synth.scene(n_map, int(rng.integers(1, 10)), int(rng.integers(1, 60)), int(rng.integers(1, 24)),
+                        spread=(seed % 3 == 0), seed=seed)
+        lik = engine.LikParams(dist_weight=w, match_dist_min=float(rng.choice([0.1, 0.2, 0.35, 0.6])))
+        g = float(rng.choice([0.05, 0.1, 0.2]))
+        beam = engine.beam_params_from_reference(map_grid=(g, g, g * float(rng.choice([1, 2]))), num_points_default=8,
+                                                 use_raycast_using_dda=bool(seed % 2), dda_grid_size=max(0.2, 2 * g))
+        ref, st_ref = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(0, 0), kd_skip=0)
+        for near, skip in (((2, 1), 4), ((1, 2), 16), ((3, 1), 1)):
+            got, st = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=near, kd_skip=skip)
+            assert got.tobytes() == ref.tobytes() and np.array_equal(st, st_ref), (seed, near, skip)
