@@ -35,6 +35,14 @@ def eng(eng_mod, request, monkeypatch):
     e.close()
 
 
+@pytest.fixture
+def eng_mod_engine_tuned(eng_mod, monkeypatch):
+    monkeypatch.delenv("MCL3DL_MAPPING", raising=False)
+    e = eng_mod.Engine((0,))
+    yield e
+    e.close()
+
+
 @pytest.fixture(scope="module")
 def cc():
     from oracle import cpu_checker
@@ -293,6 +301,43 @@ def test_multi_device_engine_matches_single(eng_mod, big_scene):
     e2.close()
 
 
+# ------------------------------------------------------------------ BASELINE configs 4 and 5 against the oracle
+def test_c4_shape_vs_oracle(eng_mod, eng_mod_engine_tuned, cc):
+    """Config 4's shape: a 9.7 M-point map (0.1 m DDA lattice, 4e8 cells; 2.6e8-cell search grid), 16 384 tracking
+    particles x (1024 likelihood points + 1024 beam rays).  The whole job runs on the GPU; a strided 256-particle sample
+    is compared with the oracle, and the sample's records must equal the full job's rows."""
+    eng = eng_mod_engine_tuned
+    s = synth.scene(10_000_000, 16384, 1024, 1024, seed=7)
+    assert len(s["map"]) > 9_000_000
+    cpu = run_both(eng_mod, eng, cc, s, (1, 1, 5), 1024, dda_grid=0.1)
+    info = eng.map_info()
+    assert int(np.prod(np.array(list(info.dda_dims), dtype=np.int64))) > 3e8
+    full = eng.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+    idx = np.arange(0, 16384, 64)
+    want = cpu.measure(s["particles"][idx], s["lik"], s["beam"], s["origins"], n_threads=8)
+    check_records(full[idx], want, 1024)
+    assert np.array_equal(eng.measure(s["particles"][idx], s["lik"], s["beam"], s["origins"]), full[idx])
+    assert want["match_cnt"].sum() > 0 and want["n_hit"].sum() > 0
+
+
+@pytest.mark.parametrize("n_lik,n_beam", [(64, 8), (8, 0)])
+def test_c5_shape_vs_oracle(eng_mod, eng, cc, n_lik, n_beam):
+    """Config 5's shape: 65 536 particles spread over the floor plan x 12 headings (global localisation,
+    src/mcl_3dl.cpp:1039-1099) on the 1 M-point map; (8, 0) is the node's own point budget in that state
+    (num_points_global = 8 likelihood points, 0 beam rays: src/lidar_measurement_model_likelihood.cpp:63-77,
+    parameters.cpp:219-220,255-256).  A strided 512-particle sample against the oracle; the rest of the job through
+    the sample's rows and the permutation property."""
+    s = synth.scene(1_000_000, 65536, n_lik, n_beam, spread=True, seed=57)
+    cpu = run_both(eng_mod, eng, cc, s, (1, 1, 5), max(n_beam, 1))
+    full = eng.measure(s["particles"], s["lik"], s["beam"] if n_beam else None, s["origins"])
+    idx = np.arange(0, 65536, 128)
+    want = cpu.measure(s["particles"][idx], s["lik"], s["beam"] if n_beam else None, s["origins"], n_threads=8)
+    check_records(full[idx], want, n_beam)
+    assert want["match_cnt"].sum() > 0
+    perm = np.random.default_rng(6).permutation(65536)
+    assert np.array_equal(eng.measure(s["particles"][perm], s["lik"], s["beam"] if n_beam else None, s["origins"]), full[perm])
+
+
 # ------------------------------------------------------------------ scope row f2: fused weight update
 @pytest.mark.parametrize("P,seed,with_extra", [(64, 71, False), (1000, 72, True), (65536, 73, True)])
 def test_fused_weight_update_vs_pf_measure(eng_mod, eng, cc, P, seed, with_extra):
@@ -307,6 +352,8 @@ def test_fused_weight_update_vs_pf_measure(eng_mod, eng, cc, P, seed, with_extra
     prior /= prior.sum(dtype=np.float64).astype(np.float32)
     extra = rng.uniform(0.5, 1.0, P).astype(np.float32) if with_extra else None
     post, summ, rec = eng.measure_update(s["particles"], s["lik"], s["beam"], s["origins"], prior, extra, want_records=True)
+    # the records of the fused path against the ORACLE (every particle, 65 536 included), then against the plain entry
+    check_records(rec, cpu.measure(s["particles"], s["lik"], s["beam"], s["origins"], n_threads=8), n_beam)
     want_rec = eng.measure(s["particles"], s["lik"], s["beam"], s["origins"])
     assert np.array_equal(rec, want_rec)
     like = (np.float32(1.0) * want_rec["score_beam"]).astype(np.float32)

@@ -1,17 +1,13 @@
 """Resident particle set (scope row f3, mcl3dl_particles_*): predict, measure + weight update, resample on the device.
 
-Written after round 1's GPU budget was spent: the per-particle arithmetic is checked on the host bit for bit
-(tests/test_hostsim.py::test_pf_*), but these kernels and their plumbing have never run.  Every test here is therefore
-marked `first_run_pending` = xfail(strict=False): a pass shows up as XPASS, a failure as xfail, neither turns the
-suite red.  Remove the marker once the file has run green on a B200.
+First run on a B200: driver record GPUTEST_r01 (10 passed as XPASS); the first-run marker is gone since round 2.
 """
 import numpy as np
 import pytest
 
 from mcl_3dl_b200 import synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first_run_pending: written without GPU time, never executed on hardware")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
