@@ -7,14 +7,23 @@ reference's own CPU path) on BASELINE.json's configs.
 
 One "step" = one measurement update (the hot path) over one batch: every particle x every sampled
 scan point.  Prints ONE JSON line on rank 0 (see the contract in the task statement):
-  value     whole-job particle x point evals/s with all inputs resident in HBM (CUDA events, max over ranks)
-  e2e       same metric through the host-buffer C-ABI call mcl3dl_measure (H2D + kernels + D2H inside)
+  value     whole-job particle x point evals/s with all inputs resident in HBM (CUDA events, max over ranks).
+            N > 1: one process per GPU, particles sharded, map replicated; the ONE exchange of the path (the gather
+            of the 24-byte records) is folded into the measurement kernels, which store every record into every
+            rank's array over NVLink peer memory (csrc/kernels.cuh: RecordSink + exchange_signal_kernel); the
+            whole step is replayed as one CUDA graph.  --exchange nccl keeps the NCCL all-gather for comparison.
+  e2e       same metric through the host-buffer C-ABI call mcl3dl_measure (H2D + kernels + D2H inside).
+            N > 1: ONE host process (rank 0) drives all N GPUs through the in-process multi-device engine
+            (mcl3dl_create with N device ids) and receives every record in one host array — what a ROS node would do.
   roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the reference CPU path (oracle/_ref if present, else the port) on a bounded sample, 1 thread
+  workloads driver-run secondaries: c3 (beam DDA), c3_kd (the node's default raycaster), c5 (65 536 spread particles,
+            strong scaling at N > 1), each with value / kernel times / counted roofline
 Workloads (BASELINE.json configs): c1 64x(96+3)/50k map, c2 1024x512 likelihood/1M map (default, the
 metric's config), c3 4096x256 beam DDA/1M map, c4 16384x1024 lik+beam/10M map, c5 65536 spread lik+beam.
 """
 import argparse
+import functools
 import json
 import math
 import os
@@ -42,6 +51,10 @@ WORKLOADS = {
 FORCE_SPREAD = False
 DIST_WEIGHT = (1.0, 1.0, 5.0)  # the node's default metric (src/parameters.cpp:108-111)
 MAP_VOXEL = 0.1
+USE_DDA = True
+
+# the synthetic map depends on (n_target, seed) only: c2 / c3 / c5 share one 1 M-point map
+synth.warehouse_map = functools.lru_cache(maxsize=2)(synth.warehouse_map)
 
 
 def bytes_per_eval_model(match_dist_min=0.2, w=DIST_WEIGHT, h=MAP_VOXEL):
@@ -111,27 +124,38 @@ def as_u8(a):
     return np.ascontiguousarray(a).view(np.uint8).reshape(-1)
 
 
-def build_scene(workload, rank, world):
+def build_scene(workload, rank, world, all_ranks=False):
+    """The rank's {map, scan, particle shard}.  all_ranks: the particles of every rank concatenated (rank 0's
+    in-process multi-device e2e leg needs the whole job on one host)."""
     n_map, P, n_lik, n_beam, spread, dda, scaling = WORKLOADS[workload]
     spread = spread or FORCE_SPREAD
     P_rank = P if scaling == "weak" else P // world
     s = synth.scene(n_map, P, n_lik, n_beam, spread=spread, n_origins=2, seed=1000)
-    if scaling == "weak":
-        # same map and scan, this rank's own particle draw
+
+    def draw(r):
+        # weak scaling: same map and scan, every rank its own particle draw
         if spread:
-            s["particles"] = synth.spread_particles(P, s["info"], seed=2000 + rank)
-        else:
-            s["particles"] = synth.tracking_particles(P, s["truth_pos"], s["truth_rpy"], seed=2000 + rank)
-    else:
+            return synth.spread_particles(P, s["info"], seed=2000 + r)
+        return synth.tracking_particles(P, s["truth_pos"], s["truth_rpy"], seed=2000 + r)
+    if scaling == "weak":
+        s["particles"] = np.concatenate([draw(r) for r in range(world)]) if all_ranks else draw(rank)
+    elif not all_ranks:
         s["particles"] = s["particles"][rank * P_rank:(rank + 1) * P_rank]
+    else:
+        s["particles"] = s["particles"][:P_rank * world]
     return s, dda, scaling, P_rank
 
 
-USE_DDA = True
+def host_threads():
+    """Threads this process may really use (the lease's CPU set, not the machine's core count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def cpu_arm(workload, s, dda, n_lik, n_beam, target_s, threads, want_kind=None):
-    """Time the reference CPU path on a bounded particle sample.  Returns (evals/s, meta)."""
+    """Time the reference CPU path on a bounded particle sample.  Returns (n_sample, s per pass, handle, meta)."""
     from oracle import cpu_checker as cc
     kind = "reference" if cc.available("reference") else "port"
     if want_kind:
@@ -167,13 +191,15 @@ def cpu_arm(workload, s, dda, n_lik, n_beam, target_s, threads, want_kind=None):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path, all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on the host threads this process may use
+    (the cgroup / affinity set, not os.cpu_count()); the 1-thread figure — what the node really does, it is
+    single-threaded by construction — is printed in the same line."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_map, P, n_lik, n_beam, spread, dda, scaling = WORKLOADS[args.workload]
     s, dda, scaling, P_rank = build_scene(args.workload, 0, 1)
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     unit_pts = n_lik if n_lik else n_beam
     # give every thread enough particles to amortise its start-up: tile the particle set to >= 64 per thread
     need = threads * 64
@@ -190,10 +216,21 @@ def run_reference_arm(args):
     value = n_sample * unit_pts * args.steps / dt
     meta["value"] = value
     meta["unit"] = "evals/s"
+    # the node's real path: one thread (serial loop pf.h:256, ros::spin mcl_3dl.cpp:1466), ~2 s sample
+    n1 = max(4, min(n_sample, int(n_sample / max(threads, 1)) + 1))
+    one = s["particles"][:n1]
+    cpu.measure(one, s["lik"], s["beam"], s["origins"], n_threads=1)
+    reps = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 2.0:
+        cpu.measure(one, s["lik"], s["beam"], s["origins"], n_threads=1)
+        reps += 1
+    meta["value_1_thread"] = n1 * unit_pts * reps / (time.perf_counter() - t0)
+    meta["cores_machine"] = os.cpu_count()
     line = {"impl": "reference", "metric": metric_name(n_lik), "value": value, "unit": "evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args.workload, s, P, n_lik, n_beam, spread, dda, None),
+            "config": config_dict(args.workload, s, P * args.gpus if scaling == "weak" else P, n_lik, n_beam, spread, dda),
             "cpu_baseline": meta,
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -203,123 +240,93 @@ def metric_name(n_lik):
     return "particle x point likelihood evals/s" if n_lik else "particle x ray beam-model evals/s"
 
 
-def config_dict(workload, s, P, n_lik, n_beam, spread, dda, info):
-    d = {"workload": "%s: %d particles x (%d likelihood pts + %d beam rays), %d-pt map @%.1f m voxel, %s particles"
-                     % (workload, P, n_lik, n_beam, len(s["map"]), MAP_VOXEL, "spread" if spread else "tracking"),
-         "dist_weight": list(DIST_WEIGHT), "dda_grid_size": dda, "match_dist_min": 0.2,
-         "raycaster": "RaycastUsingDDA" if USE_DDA else "RaycastUsingKDTree",
-         "l2": "flushed (256 MiB write) before every timed step"}
-    if info is not None:
-        d["nn_grid"] = list(info.nn_dims)
-        d["dda_grid"] = list(info.dda_dims)
-        d["map_device_bytes"] = int(info.device_bytes)
-        d["map_build_ms"] = round(info.build_ms, 3)
-    return d
+def config_dict(workload, s, P, n_lik, n_beam, spread, dda):
+    """Identical keys on both arms (the engine-side map figures live in the line's `map` object)."""
+    return {"workload": "%s: %d particles x (%d likelihood pts + %d beam rays), %d-pt map @%.1f m voxel, %s particles"
+                        % (workload, P, n_lik, n_beam, len(s["map"]), MAP_VOXEL, "spread" if spread else "tracking"),
+            "dist_weight": list(DIST_WEIGHT), "dda_grid_size": dda, "match_dist_min": 0.2,
+            "raycaster": "RaycastUsingDDA" if USE_DDA else "RaycastUsingKDTree",
+            "l2": "flushed (256 MiB write) before every timed step"}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
-                    help="N > 1: how the records are gathered: NCCL all-gather (contract run) or the engine's own "
-                         "peer-memory exchange kernel (experiment, not yet run on hardware)")
-    ap.add_argument("--graph", action="store_true",
-                    help="experiment: replay the device-resident step as one CUDA graph (not part of the contract run)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--raycaster", default="dda", choices=["dda", "kd"],
-                    help="beam raycaster: RaycastUsingDDA (north_star) or RaycastUsingKDTree (the node's default)")
-    ap.add_argument("--spread", action="store_true", help="spread (global-localisation style) particles: the HBM-bound variant")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-    global FORCE_SPREAD, USE_DDA
-    FORCE_SPREAD = args.spread
-    USE_DDA = args.raycaster == "dda"
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
+class Ctx:
+    """Process-wide state of the b200 arm (torch, distributed ranks, flush buffer)."""
+    pass
 
+
+def device_leg(cx, workload, raycaster, steps, warmup, exchange="peer", graph=True, keep_spinning=False):
+    """Device-resident leg of one workload on every rank: value (CUDA events, max over ranks), per-model kernel
+    times, counted roofline.  Returns (result dict, live objects for the e2e leg)."""
     import torch
     import torch.distributed as dist
     from mcl_3dl_b200 import engine, sharding
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("MCL3DL_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-
-    n_map, P, n_lik, n_beam, spread, _, _ = WORKLOADS[args.workload]
-    spread = spread or args.spread
-    s, dda, scaling, P_rank = build_scene(args.workload, rank, world)
-    eng = engine.Engine((local,))  # no fallback: raises without the CUDA library / device
+    global USE_DDA
+    USE_DDA = raycaster == "dda"
+    world, rank, dev = cx.world, cx.rank, cx.dev
+    n_map, P, n_lik, n_beam, spread, _, _ = WORKLOADS[workload]
+    spread = spread or FORCE_SPREAD
+    s, dda, scaling, P_rank = build_scene(workload, rank, world)
+    eng = engine.Engine((cx.local,))  # no fallback: raises without the CUDA library / device
     lik = engine.LikParams(dist_weight=DIST_WEIGHT)
-    use_dda = args.raycaster == "dda"
     beam = engine.beam_params_from_reference(num_points_default=max(n_beam, 1), dda_grid_size=dda,
-                                             use_raycast_using_dda=use_dda)
-    eng.set_map(s["map"], lik if (n_lik or not use_dda) else None, beam if n_beam else None)
+                                             use_raycast_using_dda=USE_DDA)
+    eng.set_map(s["map"], lik if (n_lik or not USE_DDA) else None, beam if n_beam else None)
     info = eng.map_info()
-
     particles = s["particles"]
+    n_org = len(s["origins"])
     d_p = torch.from_numpy(as_u8(particles)).to(dev)
     d_l = torch.from_numpy(as_u8(s["lik"])).to(dev) if n_lik else torch.zeros(16, dtype=torch.uint8, device=dev)
     d_b = torch.from_numpy(as_u8(s["beam"])).to(dev) if n_beam else torch.zeros(16, dtype=torch.uint8, device=dev)
     d_o = torch.from_numpy(np.ascontiguousarray(s["origins"], dtype=np.float32)).to(dev)
     d_out = torch.zeros(P_rank * 24, dtype=torch.uint8, device=dev)
     d_all = torch.zeros(world * P_rank * 24, dtype=torch.uint8, device=dev) if world > 1 else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    flush = cx.flush
 
-    peer_all = None
-    if world > 1 and args.exchange == "peer":
-        # EXPERIMENT (never run): every rank's records are stored into every rank's buffer by one kernel over NVLink;
-        # the CUDA IPC handles of the buffers are the only thing that goes through torch.distributed
+    peer = world > 1 and exchange == "peer"
+    if peer:
+        # the CUDA IPC handles of the exchange buffers are the only thing that goes through torch.distributed
         handle = eng.exchange_create(P_rank, world, rank)
-        peer_all = 0  # device address of the last gathered array, returned by every exchange_records call
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
         gathered = torch.empty(world * len(handle), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(gathered, mine)
         eng.exchange_open(bytes(gathered.cpu().numpy().tobytes()))
         dist.barrier()
 
-    def step_eager():
-        nonlocal peer_all
-        st = torch.cuda.current_stream().cuda_stream
+    def plain_measure(st):
         eng.measure_device(d_p.data_ptr(), P_rank, d_l.data_ptr(), n_lik, d_b.data_ptr(), n_beam,
-                           d_o.data_ptr(), len(s["origins"]), d_out.data_ptr(), st)
-        if world > 1:
-            if peer_all is not None:
-                peer_all = eng.exchange_records(d_out.data_ptr(), P_rank, st)
-            else:
-                # the one exchange of the path: all-gather of the per-particle records over NVLink (NCCL)
-                sharding.gather_records_device(d_out, d_all)
+                           d_o.data_ptr(), n_org, d_out.data_ptr(), st)
 
-    step = step_eager
-    if args.graph and peer_all is not None:
-        raise SystemExit("--graph cannot replay --exchange peer: the step counter is a kernel argument")
-    if args.graph:
-        # EXPERIMENT (added without GPU time left in round 1, never run): replay the step (both kernels, their
-        # fork/join events and the NCCL all-gather) as one CUDA graph, to take the per-step launch work off the CPU
-        for _ in range(3):
-            step_eager()
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step_eager()
-        step = graph.replay
+    def step_eager():
+        st = torch.cuda.current_stream().cuda_stream
+        if peer:
+            # both models + the record exchange: the kernels store into every rank's array, one signal kernel follows
+            eng.measure_exchange_device(d_p.data_ptr(), P_rank, d_l.data_ptr(), n_lik, d_b.data_ptr(), n_beam,
+                                        d_o.data_ptr(), n_org, st)
+        else:
+            plain_measure(st)
+            if world > 1:
+                sharding.gather_records_device(d_out, d_all)  # comparison arm: NCCL all-gather of the records
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    l0 = eng.kernel_launches()
+    for _ in range(3):
+        step_eager()
+    barrier()
+    launches_per_step = (eng.kernel_launches() - l0) // 3
+    step, graphed = step_eager, False
+    if graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step_eager()
+            step, graphed = g.replay, True
+        except Exception as exc:  # keep measuring eagerly, and say so
+            cx.notes.append("CUDA graph capture failed for %s: %s" % (workload, exc))
+            barrier()
 
     def timed(fn, k):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
@@ -330,66 +337,67 @@ def main():
             fn()
             b.record()
         barrier()
-        tot = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([tot], dtype=torch.float64, device=dev)
+        per = [a.elapsed_time(b) for a, b in evs]
+        t = torch.tensor([sum(per)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return float(t.item()), per
 
-    # clocks are sampled from the warm-up to the end of the e2e loop: the timed region alone lasts a few
-    # milliseconds, shorter than one nvidia-smi sampling period
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
-    l0 = eng.kernel_launches()
-    total_ms = timed(step, args.steps)
-    launches = eng.kernel_launches() - l0
-    # the timed region lasts a few milliseconds, shorter than one nvidia-smi period: keep the same step running
-    # (untimed, same count on every rank) for ~0.5 s so that the clock record holds samples taken under this load
-    n_extra = int(min(20000, max(0, 500.0 / max(total_ms / args.steps, 1e-3))))
-    for _ in range(n_extra):
-        step()
-    barrier()
+    total_ms, per_step = timed(step, steps)
+    if keep_spinning:
+        # the timed region lasts a few milliseconds, shorter than one nvidia-smi period: keep the same step running
+        # (untimed, same count on every rank) for ~0.5 s so that the clock record holds samples taken under this load
+        for _ in range(int(min(20000, max(0, 500.0 / max(total_ms / steps, 1e-3))))):
+            step()
+        barrier()
 
     exchange_info = None
     if world > 1:
-        exchange_info = {"mode": args.exchange, "graph": bool(args.graph)}
-        if peer_all is not None:
-            # check the experiment against NCCL on the same records (outside every timed region)
+        exchange_info = {"mode": "peer-memory stores in the kernels' epilogues + signal kernel" if peer else "nccl all_gather",
+                         "graph": graphed, "bytes_per_rank_per_step": P_rank * 24 * (world if peer else 1)}
+        if peer:
+            # the folded exchange against NCCL on the same inputs (outside every timed region), byte for byte
             class _DevView:  # raw device memory as a torch tensor (CUDA array interface)
                 def __init__(self, ptr, nbytes):
                     self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-            step_eager()
+            st = torch.cuda.current_stream().cuda_stream
+            plain_measure(st)
             sharding.gather_records_device(d_out, d_all)
-            torch.cuda.synchronize()
-            t_peer = torch.as_tensor(_DevView(peer_all, world * P_rank * 24), device=dev)
-            exchange_info["matches_nccl"] = bool(torch.equal(t_peer, d_all))
-            exchange_info["peer_wait_timed_out"] = eng.exchange_failed()
+            ptr, failed = eng.exchange_current(st)
+            t_peer = torch.as_tensor(_DevView(ptr, world * P_rank * 24), device=dev)
+            ok = torch.tensor([int(torch.equal(t_peer, d_all))], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            exchange_info["matches_nccl_on_every_rank"] = bool(ok.item())
+            exchange_info["peer_wait_timed_out"] = failed
 
     unit_pts = n_lik if n_lik else n_beam
     evals_step = world * P_rank * unit_pts
-    ms_per_step = total_ms / args.steps
-    value = evals_step / (ms_per_step * 1e-3)
+    ms_per_step = total_ms / steps
+    res = {"value": evals_step / (ms_per_step * 1e-3), "ms_per_step": ms_per_step, "scaling": scaling,
+           "graph": graphed, "launches_per_step": int(launches_per_step),
+           "rank0_step_ms_min_med_max": [float(np.min(per_step)), float(np.median(per_step)), float(np.max(per_step))],
+           "exchange": exchange_info}
 
-    # ---- dominant-kernel roofline: time each model's kernel alone (one launch per call)
+    # ---- each model's kernel alone (one launch per call): the dominant kernel's roofline
+    stream = torch.cuda.current_stream().cuda_stream
     kern = {}
     if n_lik:
         def lik_only():
             eng.measure_device(d_p.data_ptr(), P_rank, d_l.data_ptr(), n_lik, 0, 0, 0, 0, d_out.data_ptr(), stream)
-        kern["lik"] = timed(lik_only, args.steps) / args.steps
+        kern["lik"] = timed(lik_only, steps)[0] / steps
     if n_beam:
         def beam_only():
-            eng.measure_device(d_p.data_ptr(), P_rank, 0, 0, d_b.data_ptr(), n_beam, d_o.data_ptr(), len(s["origins"]),
+            eng.measure_device(d_p.data_ptr(), P_rank, 0, 0, d_b.data_ptr(), n_beam, d_o.data_ptr(), n_org,
                                d_out.data_ptr(), stream)
-        kern["beam"] = timed(beam_only, args.steps) / args.steps
+        kern["beam"] = timed(beam_only, steps)[0] / steps
     peak, peak_src = peaks()
     dom = max(kern, key=kern.get)
     # exact work counters of one (untimed) step: what this layout's algorithm must read, no reuse assumed
     eng.collect_stats(True)
-    step()
+    plain_measure(stream)
     ws = eng.read_stats()
     eng.collect_stats(False)
     io_bytes = P_rank * 32 + P_rank * 24
@@ -397,7 +405,7 @@ def main():
     near = eng.near_field_info()  # [(k, bytes)] likelihood / KD-caster screens; k = 0: not staged
     if dom == "lik":
         alg_bytes = ws["lik_index_rows"] * 8 + ws["lik_points_scanned"] * 16 + io_bytes + n_lik * 16
-        note = ("counted: %.1f CSR rows x 8 B + %.1f map points x 16 B per eval (+ poses/scan/records)"
+        note = ("counted: %.1f index entries x 8 B + %.1f map points x 16 B per eval (+ poses/scan/records)"
                 % (ws["lik_index_rows"] / max(P_rank * n_lik, 1), ws["lik_points_scanned"] / max(P_rank * n_lik, 1)))
         if near[0][0]:
             alg_bytes += P_rank * n_lik * 4
@@ -414,110 +422,248 @@ def main():
                         + io_bytes + n_beam * 16)
         survey_note = "SURVEY 8d beam: 1 B per cell stepped + 8 B CSR + 16 B per point tested"
     achieved = alg_bytes / (kern[dom] * 1e-3) / 1e9
-    traffic, traffic_note = None, None
+    traffic, traffic_src, binding = None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
             ncu = json.load(f)
-        traffic = ncu.get(args.workload, {}).get(dom + "_dram_bytes_per_launch")
-        traffic_note = ncu.get("_note")
+        key = workload + ("" if raycaster == "dda" or not n_beam else "_kd") + ("_spread" if FORCE_SPREAD else "")
+        ent = ncu.get(key, {})
+        traffic = ent.get(dom + "_dram_bytes_per_launch")
+        traffic_src = ent.get(dom + "_source")
+        binding = ent.get(dom + "_binding_resource")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
-                "kernel_ms": kern[dom], "algorithmic_bytes_per_launch": alg_bytes, "model": note,
-                "kernel_ms_all": kern, "work_counters_per_step": ws,
-                "survey_8d_model": {"bytes_per_launch": survey_bytes, "achieved": survey_bytes / (kern[dom] * 1e-3) / 1e9,
-                                    "frac": survey_bytes / (kern[dom] * 1e-3) / 1e9 / peak, "note": survey_note}}
+    res["roofline"] = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                       "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+                       "binding_resource_ncu": binding,
+                       "dram_frac": (traffic / (kern[dom] * 1e-3) / 1e9 / peak) if traffic else None,
+                       "kernel_ms": kern[dom], "algorithmic_bytes_per_launch": alg_bytes, "model": note,
+                       "kernel_ms_all": kern, "work_counters_per_step": ws,
+                       "survey_8d_model": {"bytes_per_launch": survey_bytes,
+                                           "achieved": survey_bytes / (kern[dom] * 1e-3) / 1e9,
+                                           "frac": survey_bytes / (kern[dom] * 1e-3) / 1e9 / peak, "note": survey_note}}
+    res["map"] = {"nn_grid": list(info.nn_dims), "dda_grid": list(info.dda_dims), "device_bytes": int(info.device_bytes),
+                  "build_ms": round(info.build_ms, 3)}
+    live = {"eng": eng, "scene": s, "dda": dda, "P_rank": P_rank, "d_out": d_out, "plain_measure": plain_measure,
+            "n_lik": n_lik, "n_beam": n_beam, "spread": spread, "P": P, "scaling": scaling, "unit_pts": unit_pts}
+    return res, live
 
-    # ---- e2e: the host-buffer C-ABI call (pinned staging + H2D + kernels + D2H inside the call)
-    out_host = np.zeros(P_rank, dtype=synth.RESULT)
-    # the buffer addresses are resolved once (Engine.bind_measure), as a C++ caller's would be: every timed call is
-    # exactly one mcl3dl_measure(host pointers) = staging + H2D + kernels + D2H + synchronise
-    h_in = [np.ascontiguousarray(a, dtype=dt) for a, dt in ((particles, synth.POSE), (s["lik"], synth.POINT),
-                                                             (s["beam"], synth.POINT))]
-    h_org = np.ascontiguousarray(s["origins"], dtype=np.float32).reshape(-1, 3)
-    e2e_call = eng.bind_measure(h_in[0], h_in[1], h_in[2], h_org, out_host)
-    for _ in range(3):
-        e2e_call()
-    barrier()
-    e2e_tot = 0.0
-    for _ in range(args.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_call()
-        e2e_tot += time.perf_counter() - t0
-    eng.collect_timing(True)   # device-side breakdown of one extra, untimed call (the events cost ~28 us per call,
-    e2e_call()                 # so they are off while the e2e loop above is timed)
-    last_call_device_ms = eng.last_timing()
-    eng.collect_timing(False)
-    t = torch.tensor([e2e_tot], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e = {"value": evals_step * args.steps / e2e_s, "unit": "evals/s",
-           "h2d_bytes_per_step": world * (P_rank * 32 + n_lik * 16 + n_beam * 16 + len(s["origins"]) * 16),
-           "d2h_bytes_per_step": world * P_rank * 24, "ms_per_step": 1e3 * e2e_s / args.steps,
-           "timing": "host wall clock around the synchronous call", "last_call_device_ms": last_call_device_ms,
-           "d2h_mode": ("kernels store the records straight into the pinned host block" if P_rank <= 8192
-                        else "one D2H copy of the records")}
 
-    # ---- e2e with the fused weight update (scope row f2): priors up, posteriors (4 B/particle) back
-    prior = np.full(P_rank, 1.0 / max(P_rank, 1), dtype=np.float32)
-    for _ in range(3):
-        eng.measure_update(particles, s["lik"], s["beam"], s["origins"], prior)
-    fused_tot = 0.0
-    for _ in range(args.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        post, summ, _ = eng.measure_update(particles, s["lik"], s["beam"], s["origins"], prior)
-        fused_tot += time.perf_counter() - t0
-    t = torch.tensor([fused_tot], dtype=torch.float64, device=dev)
+def e2e_leg(cx, workload, raycaster, steps, live, fused=True):
+    """End to end through the host-buffer C-ABI call (pinned staging + H2D + kernels + D2H + synchronise inside).
+    N == 1: this process' engine.  N > 1: rank 0 alone drives ALL N GPUs through the in-process multi-device engine and
+    receives every record in one host array; the other ranks wait at the barrier."""
+    import torch
+    import torch.distributed as dist
+    from mcl_3dl_b200 import engine
+    world, rank, dev = cx.world, cx.rank, cx.dev
+    n_lik, n_beam, unit_pts = live["n_lik"], live["n_beam"], live["unit_pts"]
+    out = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e["fused_weight_update"] = {"value": evals_step * args.steps / float(t.item()), "unit": "evals/s",
-                                  "ms_per_step": 1e3 * float(t.item()) / args.steps,
-                                  "h2d_bytes_per_step": e2e["h2d_bytes_per_step"] + world * P_rank * 4,
-                                  "d2h_bytes_per_step": world * P_rank * 4,
-                                  "entropy": summ["entropy"], "kept": summ["kept"]}
+        dist.barrier()
+    if rank == 0:
+        if world == 1:
+            eng, s = live["eng"], live["scene"]
+        else:
+            s, dda, _, _ = build_scene(workload, 0, world, all_ranks=True)
+            eng = engine.Engine(tuple(range(world)))
+            lik = engine.LikParams(dist_weight=DIST_WEIGHT)
+            beam = engine.beam_params_from_reference(num_points_default=max(n_beam, 1), dda_grid_size=dda,
+                                                     use_raycast_using_dda=(raycaster == "dda"))
+            eng.set_map(s["map"], lik if (n_lik or raycaster != "dda") else None, beam if n_beam else None)
+        particles = s["particles"]
+        n_total = len(particles)
+        out_host = np.zeros(n_total, dtype=synth.RESULT)
+        # the buffer addresses are resolved once (Engine.bind_measure), as a C++ caller's would be: every timed call is
+        # exactly one mcl3dl_measure(host pointers) = staging + H2D + kernels + D2H + synchronise
+        h_in = [np.ascontiguousarray(a, dtype=dt) for a, dt in ((particles, synth.POSE), (s["lik"], synth.POINT),
+                                                                 (s["beam"], synth.POINT))]
+        h_org = np.ascontiguousarray(s["origins"], dtype=np.float32).reshape(-1, 3)
+        call = eng.bind_measure(h_in[0], h_in[1], h_in[2], h_org, out_host)
+        flushes = [cx.flush] + [torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", d))
+                                for d in range(world) if d != cx.local]
+
+        def flush_all():
+            for f in flushes:
+                f.fill_(1)
+            for d in range(world if world > 1 else 1):
+                torch.cuda.synchronize(d if world > 1 else dev)
+        for _ in range(3):
+            call()
+        tot = 0.0
+        for _ in range(steps):
+            flush_all()
+            t0 = time.perf_counter()
+            call()
+            tot += time.perf_counter() - t0
+        eng.collect_timing(True)   # device-side breakdown of one extra, untimed call (the events cost ~28 us per call,
+        call()                     # so they are off while the loop above is timed)
+        last = eng.last_timing()
+        eng.collect_timing(False)
+        evals = n_total * unit_pts
+        n_org = len(s["origins"])
+        out = {"value": evals * steps / tot, "unit": "evals/s", "ms_per_step": 1e3 * tot / steps,
+               "h2d_bytes_per_step": n_total * 32 + world * (n_lik * 16 + n_beam * 16 + n_org * 16),
+               "d2h_bytes_per_step": n_total * 24,
+               "timing": "host wall clock around the synchronous call, L2 of every device flushed before it",
+               "last_call_device_ms": last,
+               "path": ("mcl3dl_measure on this process' one-device engine" if world == 1 else
+                        "mcl3dl_measure on ONE in-process engine over %d devices (rank 0; one host thread, every record "
+                        "lands in one host array — the gather is the D2H of each shard)" % world),
+               "d2h_mode": ("kernels store the records straight into the pinned host block" if n_total // world <= 8192
+                            else "one D2H copy of the records per device")}
+        if fused:
+            # the fused weight update (scope row f2): priors up, posteriors (4 B/particle) back
+            prior = np.full(n_total, 1.0 / max(n_total, 1), dtype=np.float32)
+            for _ in range(3):
+                eng.measure_update(particles, s["lik"], s["beam"], s["origins"], prior)
+            ftot = 0.0
+            for _ in range(steps):
+                flush_all()
+                t0 = time.perf_counter()
+                post, summ, _ = eng.measure_update(particles, s["lik"], s["beam"], s["origins"], prior)
+                ftot += time.perf_counter() - t0
+            out["fused_weight_update"] = {"value": evals * steps / ftot, "unit": "evals/s", "ms_per_step": 1e3 * ftot / steps,
+                                          "h2d_bytes_per_step": out["h2d_bytes_per_step"] + n_total * 4,
+                                          "d2h_bytes_per_step": n_total * 4, "entropy": summ["entropy"], "kept": summ["kept"]}
+        live["out_host"] = out_host
+        if world > 1:
+            # the in-process N-device engine against this rank's own device-resident shard (first shard of the job)
+            live["plain_measure"](torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got = np.frombuffer(live["d_out"].cpu().numpy().tobytes(), dtype=synth.RESULT)
+            out["shard0_equals_device_resident"] = bool(np.array_equal(got, out_host[:live["P_rank"]]))
+            eng.close()
+    if world > 1:
+        dist.barrier()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
+    ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
+                    help="N > 1: how the records are gathered: stores into peer memory from the kernels' epilogues "
+                         "(default, the product) or an NCCL all-gather after the kernels (comparison)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the device-resident step eagerly instead of as one CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondaries", action="store_true", help="only the primary workload (profiling runs)")
+    ap.add_argument("--raycaster", default="dda", choices=["dda", "kd"],
+                    help="beam raycaster: RaycastUsingDDA (north_star) or RaycastUsingKDTree (the node's default)")
+    ap.add_argument("--spread", action="store_true", help="spread (global-localisation style) particles: the HBM-bound variant")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    global FORCE_SPREAD, USE_DDA
+    FORCE_SPREAD = args.spread
+    USE_DDA = args.raycaster == "dda"
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    cx = Ctx()
+    cx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.rank = int(os.environ.get("RANK", "0"))
+    cx.local = int(os.environ.get("LOCAL_RANK", "0"))
+    cx.notes = []
+    if cx.world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL_DEBUG is left as the launcher set it (the driver reads the communicator's rank count from NCCL's own log)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", cx.local))
+    torch.cuda.set_device(cx.local)
+    cx.dev = torch.device("cuda", cx.local)
+    cx.flush = torch.empty(256 << 20, dtype=torch.uint8, device=cx.dev)
+    world, rank = cx.world, cx.rank
+
+    # clocks are sampled from the warm-up to the end of the e2e loop: the timed region alone lasts a few
+    # milliseconds, shorter than one nvidia-smi sampling period
+    clocks = ClockSampler(cx.local)
+    if rank == 0:
+        clocks.start()
+    graph = not args.no_graph
+    res, live = device_leg(cx, args.workload, args.raycaster, args.steps, args.warmup, args.exchange, graph, keep_spinning=True)
+    e2e = e2e_leg(cx, args.workload, args.raycaster, args.steps, live)
     clk = clocks.stop() if rank == 0 else None
+    n_lik, n_beam, P_rank, s = live["n_lik"], live["n_beam"], live["P_rank"], live["scene"]
 
-    # ---- sanity: device-resident records == host-path records
-    got = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=synth.RESULT)
-    if n_lik and n_beam:
-        assert np.array_equal(got, out_host), "device-resident and host entry points disagree"
+    # ---- sanity: device-resident records == host-path records (N == 1; at N > 1 the e2e leg checked shard 0)
+    if rank == 0 and world == 1 and n_lik and n_beam:
+        live["plain_measure"](torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = np.frombuffer(live["d_out"].cpu().numpy().tobytes(), dtype=synth.RESULT)
+        assert np.array_equal(got, live["out_host"]), "device-resident and host entry points disagree"
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         try:
-            n_sample, dt, cpu, meta = cpu_arm(args.workload, s, dda, n_lik, n_beam, args.cpu_seconds, 1)
-            meta["value"] = n_sample * unit_pts / dt
+            USE_DDA = args.raycaster == "dda"
+            out_host = live["out_host"]
+            n_sample, dt, cpu, meta = cpu_arm(args.workload, s, live["dda"], n_lik, n_beam, args.cpu_seconds, 1)
+            meta["value"] = n_sample * live["unit_pts"] / dt
             meta["unit"] = "evals/s"
             # parity spot check of this very workload against the checker (first particles of rank 0)
             cpu.set_tally(True)
-            chk = cpu.measure(particles[:16], s["lik"], s["beam"], s["origins"])
+            chk = cpu.measure(s["particles"][:16], s["lik"], s["beam"], s["origins"])
             ok = all(np.array_equal(chk[f], out_host[:16][f]) for f in ("match_cnt", "n_short", "n_hit", "n_long"))
             ok = ok and np.allclose(chk["score_like"], out_host[:16]["score_like"], rtol=1e-4, atol=1e-6)
             meta["parity_spot_check"] = bool(ok)
             cpu_baseline = meta
         except Exception as exc:  # the GPU line must still be printed if the checker cannot be built / loaded
             cpu_baseline = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    live["eng"].close()
+    out_host = live.get("out_host")
+    del live
+
+    # ---- driver-run secondaries (fewer steps; no CPU leg): what north_star names besides the primary metric
+    secondaries = {}
+    if not args.no_secondaries and args.workload == "c2" and not args.spread:
+        sec = [("c5", "c5", "dda")] if world > 1 else [("c3", "c3", "dda"), ("c3_kd", "c3", "kd"), ("c5", "c5", "dda")]
+        k = max(10, min(args.steps, 30))
+        for name, wl, caster in sec:
+            try:
+                r2, live2 = device_leg(cx, wl, caster, k, 3, args.exchange, graph)
+                r2["metric"] = metric_name(live2["n_lik"])
+                r2["unit"] = "evals/s"
+                r2["steps"] = k
+                r2["config"] = config_dict(wl, live2["scene"], live2["P"] if live2["scaling"] == "strong" else live2["P_rank"] * world,
+                                           live2["n_lik"], live2["n_beam"], live2["spread"], live2["dda"])
+                e2 = e2e_leg(cx, wl, caster, k, live2, fused=False)
+                if e2 is not None:
+                    r2["e2e"] = e2
+                live2["eng"].close()
+                del live2
+                secondaries[name] = r2
+            except Exception as exc:
+                secondaries[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        USE_DDA = args.raycaster == "dda"
 
     if rank == 0:
-        line = {"metric": metric_name(n_lik), "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+        scaling = res.pop("scaling")
+        P = WORKLOADS[args.workload][1]
+        spread = WORKLOADS[args.workload][4] or args.spread
+        line = {"metric": metric_name(n_lik), "value": res.pop("value"), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res.pop("ms_per_step"), "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args.workload, s, P if scaling == "strong" else P_rank * world, n_lik, n_beam,
-                                      spread, dda, info),
-                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu_baseline, "exchange": exchange_info,
-                "match_ratio_mean": float(out_host["match_cnt"].mean() / max(n_lik, 1)),
-                "beam_tallies_mean": [float(out_host[f].mean()) for f in ("n_short", "n_hit", "n_long")]}
+                                      spread, WORKLOADS[args.workload][5]),
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(res["launches_per_step"] * args.steps),
+                "roofline": res.pop("roofline"), "cpu_baseline": cpu_baseline, "exchange": res.pop("exchange"),
+                "device_step": res, "workloads": secondaries, "notes": cx.notes,
+                "match_ratio_mean": float(out_host["match_cnt"].mean() / max(n_lik, 1)) if out_host is not None else None,
+                "beam_tallies_mean": ([float(out_host[f].mean()) for f in ("n_short", "n_hit", "n_long")]
+                                      if out_host is not None else None)}
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
-    eng.close()
 
 
 if __name__ == "__main__":

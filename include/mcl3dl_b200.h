@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MCL3DL_ABI_VERSION 2
+#define MCL3DL_ABI_VERSION 3
 
 /* ---- error codes (the reference has none: degenerate inputs yield (1,0); the only
  *      exception is ChunkedKdtree::radiusSearch's runtime_error, chunked_kdtree.h:224) */
@@ -260,22 +260,30 @@ int mcl3dl_particles_resample(mcl3dl_engine*, const float sigma_pos[3], const fl
                               uint64_t seed);
 
 /* Record exchange over peer memory for the one-process-per-GPU layout (particles sharded, ONE gather of the
- * 24-byte records, then the unchanged weight update of include/mcl_3dl/pf.h:252-279 on the full array).  Instead of an
- * NCCL all-gather, one kernel per rank stores the rank's records into every rank's buffer over NVLink and waits, on the
- * device, until the other ranks have done the same.  Engines with exactly one device; world <= 8.
+ * 24-byte records, then the unchanged weight update of include/mcl_3dl/pf.h:252-279 on the full array).  There is no
+ * collective call and no copy: the two measurement kernels store each particle's record straight into slot `rank` of
+ * EVERY rank's gathered array over NVLink (peer memory mapped with CUDA IPC), and one 32-thread kernel then publishes
+ * "rank r finished step s" to every peer and waits, on the device, for the other ranks' flags.  The launch sequence
+ * of a step is identical every time (the step parity is read from device memory), so it can be captured in a CUDA
+ * graph.  Engines with exactly one device; world <= 8; every rank holds n_local particles.
  *   create:  allocates this rank's buffer (two [world * n_local] record arrays used alternately, plus flags) and writes
- *            its CUDA IPC handle (MCL3DL_IPC_HANDLE_BYTES) for the caller to all-gather between the processes;
+ *            its CUDA IPC handle (MCL3DL_IPC_HANDLE_BYTES) for the caller to all-gather between the processes
+ *            (once per engine: the peers keep the buffer mapped);
  *   open:    maps the other ranks' buffers from the gathered handles (rank order);
- *   records: enqueues the exchange of d_local (n_local records, device memory) on the caller's stream; when it retires,
- *            *d_all_out (device memory, valid until the call after next) holds every rank's records in rank order;
- *   failed:  1 if a peer did not show up within the kernel's bounded wait (synchronises).
- * Written after round 1's GPU budget was spent: not yet run on hardware (bench.py --exchange peer). */
+ *   measure_exchange_device: mcl3dl_measure_device for this rank's n_local particles + the exchange, enqueued on the
+ *            caller's stream; when it retires, *d_all_out (device memory, valid until the call after next) holds every
+ *            rank's records in rank order.  *d_all_out assumes eager calls; after CUDA-graph replays ask `current`;
+ *   current: synchronises the stream and returns the array of the last completed step and whether a peer ever failed
+ *            to show up within the signal kernel's bounded wait. */
 #define MCL3DL_IPC_HANDLE_BYTES 64
 int mcl3dl_exchange_create(mcl3dl_engine*, size_t n_local, int world, int rank, void* ipc_handle_out);
 int mcl3dl_exchange_open(mcl3dl_engine*, const void* ipc_handles);
-int mcl3dl_exchange_records(mcl3dl_engine*, const mcl3dl_result* d_local, size_t n_local, void* cuda_stream,
-                            const mcl3dl_result** d_all_out);
-int mcl3dl_exchange_failed(mcl3dl_engine*, int* failed_out);
+int mcl3dl_measure_exchange_device(mcl3dl_engine*, const mcl3dl_pose* d_poses, size_t n_local,
+                                   const mcl3dl_point* d_lik_pts, size_t n_lik,
+                                   const mcl3dl_point* d_beam_pts, size_t n_beam,
+                                   const float* d_origins_xyz, size_t n_origins,
+                                   void* cuda_stream, const mcl3dl_result** d_all_out);
+int mcl3dl_exchange_current(mcl3dl_engine*, void* cuda_stream, const mcl3dl_result** d_all_out, int* failed_out);
 
 /* The near-field screens staged by the last set_map ([0] likelihood search, [1] KD-tree raycaster's marching search):
  * dilation k (0 = no field staged) and bytes per device.  A screen is one bit per fine cell of the map's bounding box,

@@ -17,20 +17,6 @@
 #ifndef MCL3DL_NEAR_BITS
 #define MCL3DL_NEAR_BITS 1
 #endif
-// MCL3DL_KD_SKIP=1 adds a second, coarser field to the KD-tree raycaster that proves several marching steps clear at
-// once (cast_ray_kd).  Host-verified (tests/hostsim), not yet measured on a GPU: off by default.
-#ifndef MCL3DL_KD_SKIP
-#define MCL3DL_KD_SKIP 0
-#endif
-// MCL3DL_LIK_CHUNKS=1 also builds the warp-chunk likelihood kernel (lik_kernel_wc), selected at run time with
-// MCL3DL_LIK=chunk.  Host-verified lane by lane (tests/hostsim), not yet measured on a GPU: off by default.
-#ifndef MCL3DL_LIK_CHUNKS
-#define MCL3DL_LIK_CHUNKS 0
-#endif
-#if MCL3DL_KD_SKIP && !MCL3DL_NEAR_BITS
-#error "MCL3DL_KD_SKIP needs MCL3DL_NEAR_BITS"
-#endif
-
 namespace mcl3dl
 {
 // ---- near field: one bit per FINE cubic cell (edge ef = 1.01 * r / k) of the rescaled space, set when some map
@@ -127,6 +113,33 @@ inline bool near_layout(NearBitsDev& f, float r, int k, const float sc_min[3], c
   return false;
 }
 
+// ---- NN field ("Voronoi voxels"): the exact 1-NN search turned into a two-hop gather.  The rescaled space is cut into
+// FINE voxels of edge e ~ radius / 2 (the near-field lattice with k = 2).  For every voxel the build keeps the list of
+// map points that can be the nearest neighbour (within `radius`) of SOME query inside the voxel: a point is dropped only
+// when another point is PROVABLY closer for every position in the (slightly padded) voxel box — the difference of the
+// two squared distances is affine in the query, so its minimum over the box is evaluated exactly from the box corners,
+// and the proof keeps a relative margin of 1e-5, fifty times the rounding of the float distance evaluation of the query
+// side.  A query therefore reads one 8-byte directory entry (2 x 2 x 2 voxels: first candidate + eight 4-bit counts)
+// and then the few (typically 3-6, contiguous) candidates, instead of walking a 3 x 3 window of CSR rows; the minimum
+// of the float distances over the candidates equals the minimum over ALL map points bit for bit whenever it is below
+// radius^2 (ties included: points that tie can not dominate each other).  Voxels with more than kNnfMaxCand survivors
+// (raw, unfiltered clouds) mark their directory cell and queries there fall back to the CSR window search.
+// No reference counterpart: ChunkedKdtree::radiusSearch (chunked_kdtree.h:218-251) descends a kd-tree per query.
+constexpr int kNnfMaxCand = 14;
+constexpr int kNnfMaxSurv = 40;
+struct NnFieldDev
+{
+  const uint2* dir;    // nullptr = no field.  Per coarse cell: x = index of its first candidate (0xffffffff: overflow
+                       // cell -> generic search), y = 8 nibbles = candidates per fine voxel, sub-index x | y<<1 | z<<2
+  const float4* cand;  // rescaled xyz, w = original map index (bits)
+  int nx, ny, nz;      // FINE voxels per axis
+  int cnx, cny, cnz;   // coarse cells per axis = (n + 1) / 2
+  float ox, oy, oz;    // origin of the lattice (rescaled space)
+  float inv_e, e;      // 1 / fine edge, fine edge
+  float radius;        // searches of radius (window half-width) <= this are exact
+  float pad;           // the build pads every voxel box by this much (float rounding of the voxel index of a query)
+};
+
 // ---- likelihood search grid: cubic cells over the RESCALED map points (p * dist_weight), CSR of
 // cell -> contiguous run in `pts` (x fastest, so an x-row of cells is one contiguous run).
 struct NnGridDev
@@ -146,6 +159,7 @@ struct NnGridDev
 #if MCL3DL_NEAR_BITS
   NearBitsDev near;  // built for the likelihood radius (LikDev::rpad)
 #endif
+  NnFieldDev field;  // exact candidate lists per fine voxel (field.dir == nullptr: not staged)
 };
 
 struct LikDev
@@ -191,10 +205,6 @@ struct KdRayDev
   double sin_den;           // map_grid_min_ * 2.0 (:98)
 #if MCL3DL_NEAR_BITS
   NearBitsDev near;  // built for the marching search radius (r1_pad)
-#endif
-#if MCL3DL_KD_SKIP
-  NearBitsDev far;   // built for a larger radius R2: a clear bit proves the next few marching steps clear as well
-  float far_margin;  // 0.98 * (R2 - r1_pad): how far (rescaled metric) the march may move and still be covered
 #endif
 };
 
@@ -253,168 +263,6 @@ __device__ __forceinline__ float nn_dist2(const NnGridDev& g, const LikDev& lp, 
     }
   }
   return best;
-}
-
-// --------------------------------------------------------------------------------------------
-// Warp-chunk likelihood kernel (lik_kernel_wc, kernels.cuh; -DMCL3DL_LIK_CHUNKS=1): the per-lane pieces.  A warp works
-// on 32 evals per round; the map points their windows contain are cut into CHUNKS of <= 4 consecutive points and the
-// chunks are dealt to the lanes, so every lane of phase 2 has the same amount of work (the run-per-lane kernel
-// lik_kernel_wi leaves half the lanes idle: runs are 1..30 points long, ncu r01x: 13.5 of 32 lanes on the load line).
-// Written as functions of (lane, shared slab) so that tests/hostsim can run the rounds lane by lane on the host.
-constexpr int kWcMaxRows = 9;
-constexpr int kWcMaxDesc = 640;       // >= 9 * 32: one descriptor per run always fits (the overflow fallback)
-constexpr int kWcMaxRunChunks = 127;  // chunk index field of a descriptor: 7 bits
-constexpr int kWcOverflow = 1023;     // a lane reports this chunk count to force the whole-run fallback for its round
-
-struct LikChunkSmem
-{
-  uint2 rows[kWcMaxRows][32];  // non-empty [start, end) runs of each lane's eval, compacted
-  float qx[32], qy[32], qz[32];
-  uint32_t best[32];           // float bits of the running min d^2 (non-negative floats order as uints)
-  uint16_t desc[kWcMaxDesc];   // run k (4 bits) | eval lane (5 bits) << 4 | chunk index (7 bits) << 9
-};
-
-// Phase 1, lane = eval: the runs of the <= 3x3 window of q, from the window table (same fetch as lik_kernel_wi).
-// Returns the number of runs stored to sm.rows[.][lane]; n_chunks = their total number of 4-point chunks, or
-// kWcOverflow if one of the runs is too long for the descriptor's chunk index (very dense cells).
-__device__ __forceinline__ int wc_window(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz, int lane,
-                                         LikChunkSmem& sm, uint32_t& st_rows, uint32_t& st_pts, int& n_chunks)
-{
-  int nr = 0;
-  n_chunks = 0;
-  int lx = __float2int_rd(fmul(fsub(fsub(qx, lp.rpad), g.ox), g.inv_cell));
-  int ly = __float2int_rd(fmul(fsub(fsub(qy, lp.rpad), g.oy), g.inv_cell));
-  int lz = __float2int_rd(fmul(fsub(fsub(qz, lp.rpad), g.oz), g.inv_cell));
-  int hx = __float2int_rd(fmul(fsub(fadd(qx, lp.rpad), g.ox), g.inv_cell));
-  int hy = __float2int_rd(fmul(fsub(fadd(qy, lp.rpad), g.oy), g.inv_cell));
-  int hz = __float2int_rd(fmul(fsub(fadd(qz, lp.rpad), g.oz), g.inv_cell));
-  lx = max(lx, 0);
-  ly = max(ly, 0);
-  lz = max(lz, 0);
-  hx = min(hx, g.nx - 1);
-  hy = min(hy, min(g.ny - 1, ly + 2));
-  hz = min(hz, min(g.nz - 1, lz + 2));
-  if (lx > hx || ly > hy || lz > hz)
-    return 0;
-#if MCL3DL_NEAR_BITS
-  if (!near_maybe(g.near, qx, qy, qz))
-    return 0;
-#endif
-  st_rows += static_cast<uint32_t>((hz - lz + 1) * (hy - ly + 1));
-  // the whole 3x3 window from the y-fastest window table: 2 aligned 16-byte loads per z layer, all issued first
-  const int width = hx - lx + 1;  // 1..3 cells along x
-  const int yb = ly & ~1;
-  const int odd = ly & 1;
-  uint4 ea[3], eb[3];
-#pragma unroll
-  for (int dz = 0; dz < 3; ++dz)
-  {
-    const int iz = min(lz + dz, hz);
-    const uint4* src = reinterpret_cast<const uint4*>(g.row3 + (static_cast<size_t>(iz) * g.nx + lx) * g.nyp + yb);
-    ea[dz] = __ldg(src);
-    eb[dz] = __ldg(src + 1);
-  }
-#pragma unroll
-  for (int dz = 0; dz < 3; ++dz)
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-    {
-      const int iy = ly + dy, iz = lz + dz;
-      if (iy <= hy && iz <= hz)
-      {
-        // entry (iy - yb) of the four fetched ones
-        uint32_t start, packed;
-        if (dy == 0)
-        {
-          start = odd ? ea[dz].z : ea[dz].x;
-          packed = odd ? ea[dz].w : ea[dz].y;
-        }
-        else if (dy == 1)
-        {
-          start = odd ? eb[dz].x : ea[dz].z;
-          packed = odd ? eb[dz].y : ea[dz].w;
-        }
-        else
-        {
-          start = odd ? eb[dz].z : eb[dz].x;
-          packed = odd ? eb[dz].w : eb[dz].y;
-        }
-        uint32_t cnt = width == 3 ? (packed >> 21) : (width == 2 ? ((packed >> 10) & 0x7ffu) : (packed & 0x3ffu));
-        const uint32_t sat = width == 1 ? 0x3ffu : 0x7ffu;
-        if (cnt == sat)
-        {
-          // the count did not fit the packed field (very dense cells): read the CSR bounds themselves
-          const int row = (iz * g.ny + iy) * g.nx;
-          start = __ldg(g.cell_start + row + lx);
-          cnt = __ldg(g.cell_start + row + hx + 1) - start;
-        }
-        if (cnt)
-        {
-          sm.rows[nr][lane] = make_uint2(start, start + cnt);
-          ++nr;
-          st_pts += cnt;
-          const uint32_t c4 = (cnt + 3u) >> 2;
-          n_chunks = (c4 > static_cast<uint32_t>(kWcMaxRunChunks) || n_chunks >= kWcOverflow) ? kWcOverflow :
-                                                                                                 n_chunks + static_cast<int>(c4);
-        }
-      }
-    }
-  return nr;
-}
-
-// After the warp's prefix sum: this lane's descriptors go to sm.desc[offset ...).  `whole` (warp-uniform): the chunk
-// list would not fit (very dense maps), so every run becomes one descriptor and offset comes from the prefix sum of nr.
-__device__ __forceinline__ void wc_write_descs(LikChunkSmem& sm, int lane, int nr, int offset, bool whole)
-{
-  int pos = offset;
-  for (int k = 0; k < nr; ++k)
-  {
-    const uint32_t id = static_cast<uint32_t>(k) | (static_cast<uint32_t>(lane) << 4);
-    if (whole)
-    {
-      sm.desc[pos++] = static_cast<uint16_t>(id);
-      continue;
-    }
-    const uint2 run = sm.rows[k][lane];
-    const uint32_t nc = (run.y - run.x + 3u) >> 2;
-    for (uint32_t c = 0; c < nc; ++c) sm.desc[pos++] = static_cast<uint16_t>(id | (c << 9));
-  }
-}
-
-// Phase 2, lane = descriptor: min d^2 over the chunk's (or, in a `whole` round, the run's) map points, merged into
-// the owner eval's slot.
-__device__ __forceinline__ void wc_process(LikChunkSmem& sm, uint32_t d, bool whole, const NnGridDev& g, const LikDev& lp)
-{
-  const int k = static_cast<int>(d & 15u), e = static_cast<int>((d >> 4) & 31u);
-  const uint2 run = sm.rows[k][e];
-  const float qx = sm.qx[e], qy = sm.qy[e], qz = sm.qz[e];
-  uint32_t s0 = run.x, s1 = run.y;
-  if (!whole)
-  {
-    s0 = run.x + 4u * (d >> 9);
-    s1 = (s0 + 4u < run.y) ? s0 + 4u : run.y;
-  }
-  float best = lp.r2;
-  for (uint32_t s = s0; s < s1; s += 4)
-  {
-    float4 mp[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (s + u < s1)
-        mp[u] = __ldg(g.pts + s + u);
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (s + u < s1)
-      {
-        // flann::L2_Simple: sequential float accumulate of squared differences
-        const float dx = fsub(qx, mp[u].x);
-        const float dy = fsub(qy, mp[u].y);
-        const float dz = fsub(qz, mp[u].z);
-        best = fminf(best, fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz)));  // keep d < worst
-      }
-  }
-  if (best < lp.r2)
-    atomicMin(&sm.best[e], __float_as_uint(best));
 }
 
 // --------------------------------------------------------------------------------------------
@@ -607,6 +455,214 @@ __device__ __forceinline__ bool nn_search_arg(const NnGridDev& g, float qx, floa
   return best_orig != 0xffffffffu;
 }
 
+// --------------------------------------------------------------------------------------------
+// NN field, query side.  Returns the number of candidates of q's voxel and their first index, 0 when q lies outside the
+// lattice (then no map point is within `radius`: the lattice extends 2.5 voxels > radius beyond the map's box) or -1 in
+// an overflow cell.
+__device__ __forceinline__ int nnf_lookup(const NnFieldDev& f, float qx, float qy, float qz, uint32_t& start)
+{
+  const int vx = near_cell(qx, f.ox, f.inv_e), vy = near_cell(qy, f.oy, f.inv_e), vz = near_cell(qz, f.oz, f.inv_e);
+  if (static_cast<unsigned>(vx) >= static_cast<unsigned>(f.nx) || static_cast<unsigned>(vy) >= static_cast<unsigned>(f.ny) ||
+      static_cast<unsigned>(vz) >= static_cast<unsigned>(f.nz))
+    return 0;
+  const uint2 d = __ldg(f.dir + (static_cast<size_t>(vz >> 1) * f.cny + (vy >> 1)) * f.cnx + (vx >> 1));
+  if (d.x == 0xffffffffu)
+    return -1;
+  const int sh = 4 * ((vx & 1) | ((vy & 1) << 1) | ((vz & 1) << 2));
+  const uint32_t below = d.y & ((1u << sh) - 1u);  // nibbles of the voxels stored before this one
+  const uint32_t m = (below & 0x0f0f0f0fu) + ((below >> 4) & 0x0f0f0f0fu);
+  start = d.x + ((m * 0x01010101u) >> 24);
+  return static_cast<int>((d.y >> sh) & 15u);
+}
+
+// nn_dist2 through the field (likelihood model): min over the voxel's candidates, r2 if none is closer.
+__device__ __forceinline__ float nnf_dist2(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz,
+                                           uint32_t& n_rows, uint32_t& n_pts)
+{
+  uint32_t s = 0;
+  const int c = nnf_lookup(g.field, qx, qy, qz, s);
+  if (c < 0)
+    return nn_dist2(g, lp, qx, qy, qz, n_rows, n_pts);
+  ++n_rows;  // one 8-byte directory entry
+  n_pts += static_cast<uint32_t>(c);
+  float best = lp.r2;
+  for (int i = 0; i < c; ++i)
+  {
+    const float4 m = __ldg(g.field.cand + s + i);
+    // flann::L2_Simple: sequential float accumulate of squared differences
+    const float dx = fsub(qx, m.x);
+    const float dy = fsub(qy, m.y);
+    const float dz = fsub(qz, m.z);
+    best = fminf(best, fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz)));  // KNNRadiusResultSet: keep d < worst
+  }
+  return best;
+}
+
+// nn_search_arg through the field (KD-tree raycaster's marching search); any radius the field does not cover, or an
+// overflow cell, goes to the generic window search.  Same winner: smallest float d^2 below r_sq, lowest index on ties.
+__device__ __forceinline__ bool nnf_search_arg(const NnGridDev& g, float qx, float qy, float qz, float rpad, float r_sq,
+                                               float& best, uint32_t& best_orig, uint32_t& n_tested)
+{
+  if (!g.field.dir || rpad > g.field.radius)
+    return nn_search_arg(g, qx, qy, qz, rpad, r_sq, best, best_orig, n_tested);
+  uint32_t s = 0;
+  const int c = nnf_lookup(g.field, qx, qy, qz, s);
+  if (c < 0)
+    return nn_search_arg(g, qx, qy, qz, rpad, r_sq, best, best_orig, n_tested);
+  best = r_sq;
+  best_orig = 0xffffffffu;
+  for (int i = 0; i < c; ++i)
+  {
+    ++n_tested;
+    const float4 m = __ldg(g.field.cand + s + i);
+    const float dx = fsub(qx, m.x);
+    const float dy = fsub(qy, m.y);
+    const float dz = fsub(qz, m.z);
+    const float d = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));  // flann::L2_Simple
+    const uint32_t orig = __float_as_uint(m.w);
+    if (d < best || (d == best && orig < best_orig && best_orig != 0xffffffffu))
+    {
+      best = d;
+      best_orig = orig;
+    }
+  }
+  return best_orig != 0xffffffffu;
+}
+
+// --------------------------------------------------------------------------------------------
+// NN field, build side: the candidates of fine voxel (vx, vy, vz), as positions into the CSR point array g.pts, in CSR
+// order.  Returns their number, or kNnfMaxCand + 1 when more survive (overflow).  All geometry in double, relative to
+// the voxel centre (magnitudes <= ~1, so double rounding is ~1e-16 against margins of >= 1e-8).
+struct NnfPt
+{
+  double x, y, z;
+};
+
+// squared distance from p (centre-relative) to the box [-h, h]^3 / to its farthest corner
+__device__ __forceinline__ double nnf_min2(const NnfPt& p, double h)
+{
+  const double ax = fmax(fabs(p.x) - h, 0.0), ay = fmax(fabs(p.y) - h, 0.0), az = fmax(fabs(p.z) - h, 0.0);
+  return ax * ax + ay * ay + az * az;
+}
+__device__ __forceinline__ double nnf_max2(const NnfPt& p, double h)
+{
+  const double ax = fabs(p.x) + h, ay = fabs(p.y) + h, az = fabs(p.z) + h;
+  return ax * ax + ay * ay + az * az;
+}
+// true when a is closer than p, with margin, for EVERY query in the box: min over the box of |q-p|^2 - |q-a|^2
+// = 2 q.(a-p) + |p|^2 - |a|^2, affine in q, so the minimum sits at the corner that opposes (a - p) axis by axis
+__device__ __forceinline__ bool nnf_dominates(const NnfPt& a, const NnfPt& p, double h)
+{
+  const double dx = a.x - p.x, dy = a.y - p.y, dz = a.z - p.z;
+  const double fmin_ = -2.0 * h * (fabs(dx) + fabs(dy) + fabs(dz)) + (p.x * p.x + p.y * p.y + p.z * p.z) -
+                       (a.x * a.x + a.y * a.y + a.z * a.z);
+  return fmin_ > 1e-5 * nnf_max2(p, h) + 1e-12;
+}
+
+__device__ __forceinline__ int nnf_select(const NnGridDev& g, const NnFieldDev& f, int vx, int vy, int vz, uint32_t* out)
+{
+  // voxel centre and padded half edge; search reach = radius (already padded by the caller's 1.0001 factor) + pad
+  const double e = static_cast<double>(f.e);
+  const double cx = static_cast<double>(f.ox) + (static_cast<double>(vx) + 0.5) * e;
+  const double cy = static_cast<double>(f.oy) + (static_cast<double>(vy) + 0.5) * e;
+  const double cz = static_cast<double>(f.oz) + (static_cast<double>(vz) + 0.5) * e;
+  const double h = 0.5 * e + static_cast<double>(f.pad);
+  const double reach = static_cast<double>(f.radius) * 1.00001 + 1e-7;
+  const double r2 = reach * reach;
+  // CSR cells that can hold such points: the same (monotone) float cell function as the build, on widened float bounds
+  const float w = static_cast<float>(h + reach) * 1.001f + 1e-5f;
+  const float fx = static_cast<float>(cx), fy = static_cast<float>(cy), fz = static_cast<float>(cz);
+  const int lx = max(__float2int_rd(fmul(fsub(fsub(fx, w), g.ox), g.inv_cell)), 0);
+  const int ly = max(__float2int_rd(fmul(fsub(fsub(fy, w), g.oy), g.inv_cell)), 0);
+  const int lz = max(__float2int_rd(fmul(fsub(fsub(fz, w), g.oz), g.inv_cell)), 0);
+  const int hx = min(__float2int_rd(fmul(fsub(fadd(fx, w), g.ox), g.inv_cell)), g.nx - 1);
+  const int hy = min(__float2int_rd(fmul(fsub(fadd(fy, w), g.oy), g.inv_cell)), g.ny - 1);
+  const int hz = min(__float2int_rd(fmul(fsub(fadd(fz, w), g.oz), g.inv_cell)), g.nz - 1);
+  if (lx > hx || ly > hy || lz > hz)
+    return 0;
+  // pass 1: the anchor = the in-reach point whose farthest corner is nearest (it bounds the NN distance of every query)
+  double best_max2 = 1e300;
+  NnfPt anchor;
+  anchor.x = anchor.y = anchor.z = 0.0;
+  uint32_t anchor_s = 0xffffffffu;
+  for (int iz = lz; iz <= hz; ++iz)
+    for (int iy = ly; iy <= hy; ++iy)
+    {
+      const int row = (iz * g.ny + iy) * g.nx;
+      const uint32_t s0 = __ldg(g.cell_start + row + lx), s1 = __ldg(g.cell_start + row + hx + 1);
+      for (uint32_t s = s0; s < s1; ++s)
+      {
+        const float4 m = __ldg(g.pts + s);
+        NnfPt p;
+        p.x = static_cast<double>(m.x) - cx;
+        p.y = static_cast<double>(m.y) - cy;
+        p.z = static_cast<double>(m.z) - cz;
+        if (nnf_min2(p, h) < r2)
+        {
+          const double mx2 = nnf_max2(p, h);
+          if (mx2 < best_max2)
+          {
+            best_max2 = mx2;
+            anchor = p;
+            anchor_s = s;
+          }
+        }
+      }
+    }
+  if (anchor_s == 0xffffffffu)
+    return 0;
+  const double u2 = best_max2 * (1.0 + 2e-5) + 1e-12;
+  // pass 2: survivors of the anchor test, in CSR order
+  uint32_t surv_s[kNnfMaxSurv];
+  NnfPt surv[kNnfMaxSurv];
+  int ns = 0;
+  bool too_many = false;
+  for (int iz = lz; iz <= hz; ++iz)
+    for (int iy = ly; iy <= hy; ++iy)
+    {
+      const int row = (iz * g.ny + iy) * g.nx;
+      const uint32_t s0 = __ldg(g.cell_start + row + lx), s1 = __ldg(g.cell_start + row + hx + 1);
+      for (uint32_t s = s0; s < s1; ++s)
+      {
+        const float4 m = __ldg(g.pts + s);
+        NnfPt p;
+        p.x = static_cast<double>(m.x) - cx;
+        p.y = static_cast<double>(m.y) - cy;
+        p.z = static_cast<double>(m.z) - cz;
+        const double mn2 = nnf_min2(p, h);
+        if (!(mn2 < r2) || mn2 > u2)
+          continue;
+        if (s != anchor_s && nnf_dominates(anchor, p, h))
+          continue;
+        if (ns < kNnfMaxSurv)
+        {
+          surv_s[ns] = s;
+          surv[ns] = p;
+          ++ns;
+        }
+        else
+          too_many = true;
+      }
+    }
+  if (too_many)
+    return kNnfMaxCand + 1;
+  // pass 3: pairwise — drop what any other survivor dominates (dominance is transitive over the box, so testing
+  // against survivors that are themselves dropped later is still sound)
+  int n_out = 0;
+  for (int i = 0; i < ns; ++i)
+  {
+    bool dead = false;
+    for (int j = 0; j < ns && !dead; ++j)
+      dead = (j != i) && nnf_dominates(surv[j], surv[i], h);
+    if (dead)
+      continue;
+    if (n_out == kNnfMaxCand)
+      return kNnfMaxCand + 1;
+    out[n_out++] = surv_s[i];
+  }
+  return n_out;
+}
+
 // One ray with RaycastUsingKDTree (raycasts/raycast_using_kdtree.h:57-110) + getBeamStatus (beam.cpp:157-192).
 __device__ __forceinline__ int cast_ray_kd(const KdRayDev& k, const NnGridDev& nn, const DdaGridDev& g, const F3& b,
                                            const F3& e, uint32_t& n_steps, uint32_t& n_occ, uint32_t& n_tested)
@@ -629,47 +685,18 @@ __device__ __forceinline__ int cast_ray_kd(const KdRayDev& k, const NnGridDev& n
   pos.x = fadd(b.x, inc.x);
   pos.y = fadd(b.y, inc.y);
   pos.z = fadd(b.z, inc.z);
-#if MCL3DL_KD_SKIP
-  // Steps that a clear bit of the far field covers: the march moves |inc * w| per step in the rescaled metric (plus the
-  // rounding of the sequential adds, bounded generously by 1e-5 |q| per step), and a map point within r1 of a later
-  // position would be within far_margin + r1 of this one.
-  const float step_w = __fsqrt_rn(fadd(fadd(fmul(fmul(inc.x, nn.wx), fmul(inc.x, nn.wx)), fmul(fmul(inc.y, nn.wy), fmul(inc.y, nn.wy))),
-                                      fmul(fmul(inc.z, nn.wz), fmul(inc.z, nn.wz))));
-#endif
   // getNextCastResult, :66-110
   for (int count = 1; count < length; ++count)
   {
-#if MCL3DL_KD_SKIP
-    if (k.far.bits)
-    {
-      const float fx = fmul(pos.x, nn.wx), fy = fmul(pos.y, nn.wy), fz = fmul(pos.z, nn.wz);
-      if (!near_maybe(k.far, fx, fy, fz))
-      {
-        const float per_step = fadd(step_w, fmul(1e-5f, fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fmaxf(fabsf(fz), 1.0f))));
-        // this position and the next `extra` ones cannot collide: advance over them with the same sequential adds
-        const int extra = min(__float2int_rz(fdiv(k.far_margin, per_step)), 64);
-        const int adv = min(extra + 1, length - count);
-        for (int i = 0; i < adv; ++i)
-        {
-          ++n_steps;
-          pos.x = fadd(pos.x, inc.x);
-          pos.y = fadd(pos.y, inc.y);
-          pos.z = fadd(pos.z, inc.z);
-        }
-        count += adv - 1;  // the loop header adds the last one
-        continue;
-      }
-    }
-#endif
     ++n_steps;
     float d2;
     uint32_t id;
     const float qx = fmul(pos.x, nn.wx), qy = fmul(pos.y, nn.wy), qz = fmul(pos.z, nn.wz);
 #if MCL3DL_NEAR_BITS
     // free space: the marching search cannot find anything, skip it (most steps of most rays)
-    if (near_maybe(k.near, qx, qy, qz) && nn_search_arg(nn, qx, qy, qz, k.r1_pad, k.r1_sq, d2, id, n_tested))
+    if (near_maybe(k.near, qx, qy, qz) && nnf_search_arg(nn, qx, qy, qz, k.r1_pad, k.r1_sq, d2, id, n_tested))
 #else
-    if (nn_search_arg(nn, qx, qy, qz, k.r1_pad, k.r1_sq, d2, id, n_tested))
+    if (nnf_search_arg(nn, qx, qy, qz, k.r1_pad, k.r1_sq, d2, id, n_tested))
 #endif
     {
       ++n_occ;

@@ -140,7 +140,6 @@ __global__ void nn_row3_kernel(NnGridDev g, uint2* __restrict__ row3, size_t tot
   row3[i] = e;
 }
 
-#if MCL3DL_NEAR_BITS
 // Near field (NearBitsDev): every map point sets the bits of the fine cells within k cells of its own.
 __global__ void near_mark_kernel(const mcl3dl_point* __restrict__ pts, uint32_t n, float wx, float wy, float wz, NearBitsDev f,
                                  uint32_t* __restrict__ bits, int k)
@@ -151,7 +150,84 @@ __global__ void near_mark_kernel(const mcl3dl_point* __restrict__ pts, uint32_t 
   const float4 p = __ldg(reinterpret_cast<const float4*>(pts) + i);
   near_mark_point(f, bits, k, fmul(p.x, wx), fmul(p.y, wy), fmul(p.z, wz));
 }
-#endif
+
+// NN field (device_funcs.cuh: NnFieldDev): one thread per FINE voxel, the 8 voxels of a directory cell in consecutive
+// lanes.  Pass 1 counts the candidates (nibbles + per-cell totals); after an exclusive scan of the totals pass 2 repeats
+// the selection and stores the candidates.  `bits` is the field's own k = 2 near field: a clear bit proves that no map
+// point is within the radius of any query that maps to the voxel, so the (costly) selection only runs near surfaces.
+__device__ __forceinline__ bool nnf_voxel_of_thread(const NnFieldDev& f, size_t n_cells, size_t t, size_t& cell, int& sub, int& vx,
+                                                    int& vy, int& vz)
+{
+  cell = t >> 3;
+  sub = static_cast<int>(t & 7);
+  if (cell >= n_cells)
+    return false;
+  const int cx = static_cast<int>(cell % f.cnx);
+  const size_t r = cell / f.cnx;
+  const int cy = static_cast<int>(r % f.cny), cz = static_cast<int>(r / f.cny);
+  vx = 2 * cx + (sub & 1);
+  vy = 2 * cy + ((sub >> 1) & 1);
+  vz = 2 * cz + (sub >> 2);
+  return vx < f.nx && vy < f.ny && vz < f.nz;
+}
+
+__global__ void __launch_bounds__(256)
+    nnf_count_kernel(NnGridDev g, NnFieldDev f, const uint32_t* __restrict__ bits, int pitch, uint2* __restrict__ dir,
+                     uint32_t* __restrict__ totals, size_t n_cells)
+{
+  const size_t t = blockIdx.x * static_cast<size_t>(256) + threadIdx.x;
+  size_t cell;
+  int sub, vx, vy, vz, cnt = 0;
+  if (nnf_voxel_of_thread(f, n_cells, t, cell, sub, vx, vy, vz) &&
+      ((__ldg(bits + (static_cast<size_t>(vz) * f.ny + vy) * pitch + (vx >> 5)) >> (vx & 31)) & 1u))
+  {
+    uint32_t tmp[kNnfMaxCand];
+    cnt = nnf_select(g, f, vx, vy, vz, tmp);
+  }
+  uint32_t ovf = cnt > kNnfMaxCand ? 1u : 0u;
+  uint32_t nib = ovf ? 0u : (static_cast<uint32_t>(cnt) << (4 * sub));
+  uint32_t tot = ovf ? 0u : static_cast<uint32_t>(cnt);
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1)
+  {
+    nib |= __shfl_xor_sync(0xffffffffu, nib, o);
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    ovf |= __shfl_xor_sync(0xffffffffu, ovf, o);
+  }
+  if (sub == 0 && cell < n_cells)
+  {
+    dir[cell].y = ovf ? 0xffffffffu : nib;  // all-ones (a count of 15 never occurs): overflow cell
+    totals[cell] = ovf ? 0u : tot;
+  }
+}
+
+__global__ void nnf_base_kernel(uint2* __restrict__ dir, const uint32_t* __restrict__ base, size_t n_cells)
+{
+  const size_t c = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (c < n_cells)
+    dir[c].x = dir[c].y == 0xffffffffu ? 0xffffffffu : base[c];
+}
+
+__global__ void __launch_bounds__(256)
+    nnf_fill_kernel(NnGridDev g, NnFieldDev f, const uint32_t* __restrict__ bits, int pitch, const uint2* __restrict__ dir,
+                    float4* __restrict__ cand, size_t n_cells)
+{
+  const size_t t = blockIdx.x * static_cast<size_t>(256) + threadIdx.x;
+  size_t cell;
+  int sub, vx, vy, vz;
+  if (!nnf_voxel_of_thread(f, n_cells, t, cell, sub, vx, vy, vz))
+    return;
+  const uint2 d = dir[cell];
+  const uint32_t want = (d.y >> (4 * sub)) & 15u;
+  if (d.x == 0xffffffffu || want == 0)
+    return;
+  uint32_t pos[kNnfMaxCand];
+  const int cnt = nnf_select(g, f, vx, vy, vz, pos);
+  const uint32_t below = d.y & ((1u << (4 * sub)) - 1u);
+  const uint32_t m = (below & 0x0f0f0f0fu) + ((below >> 4) & 0x0f0f0f0fu);
+  const uint32_t start = d.x + ((m * 0x01010101u) >> 24);
+  for (int i = 0; i < cnt && i < static_cast<int>(want); ++i) cand[start + i] = g.pts[pos[i]];
+}
 
 // DDA grid: RaycastUsingDDA::setExists (raycast_using_dda.h:230-235) for every map point.
 __global__ void dda_key_kernel(const mcl3dl_point* __restrict__ pts, uint32_t n, DdaGridDev g,
@@ -198,9 +274,9 @@ struct DeviceCtx
   DdaGridDev dda{};
   KdRayDev kd{};
   DevBuf raw_pts;  // map points in original order (KD-tree raycaster only)
-  DevBuf near_lik, near_kd, far_kd;  // near-field bits (MCL3DL_NEAR_BITS builds; far_kd: MCL3DL_KD_SKIP builds)
+  DevBuf near_lik, near_kd;  // near-field bits (MCL3DL_NEAR_BITS builds)
+  DevBuf nnf_dir, nnf_cand;  // NN field: directory + candidate lists
   float near_kd_r = 0.0f;            // radius the KD field was built for
-  float far_kd_r = 0.0f;             // radius of the skip-ahead field
   size_t map_bytes = 0;
   // per-update I/O
   DevBuf d_poses /* whole input block of the host path */, d_out, d_status;
@@ -222,8 +298,9 @@ struct DeviceCtx
   int r_cur = 0;
   uint32_t r_calls = 0;
   // record exchange over peer memory (one process per GPU, mcl3dl_exchange_*): [world * n_local records | world flags]
-  DevBuf xchg, x_ticket;
+  DevBuf xchg, x_ticket;  // x_ticket: [0] completed-step counter, [1] error word (device memory, local)
   PeerTable xt{};
+  RecordSink xsink{};
   void* x_opened[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t x_local = 0;   // records per rank
   uint32_t x_step = 0;
@@ -253,18 +330,19 @@ struct mcl3dl_engine
   int near_k = 2;     // near-field dilation of the likelihood screen (MCL3DL_NEAR_K, 0 = no field)
   int near_kd_k = 1;  // same for the KD-tree raycaster's marching search (MCL3DL_NEAR_KD_K)
   size_t near_max_bytes = size_t(256) << 20;  // MCL3DL_NEAR_MAX_MB
-  int kd_skip_steps = 4;  // marching steps (along the least-weighted axis) the skip-ahead field covers; MCL3DL_KD_SKIP_STEPS
-  int near_info_k[3] = {0, 0, 0};  // [2]: skip-ahead field of the KD-tree raycaster
-  uint64_t near_info_bytes[3] = {0, 0, 0};
+  int near_info_k[2] = {0, 0};
+  uint64_t near_info_bytes[2] = {0, 0};
   // Host-path choices measured in profiles/r01y_ab_variants.txt (c2 e2e 102 -> 71 us per update with both):
   int timing = 0;               // the per-call timing events of mcl3dl_last_timing cost ~28 us per update: off unless
                                 // mcl3dl_collect_timing(eng, 1) or MCL3DL_TIMING=1
   size_t zero_copy_max = 8192;  // the kernels of updates with <= this many particles per device store their records
                                 // straight into the pinned result block (no D2H copy launch); MCL3DL_ZEROCOPY_OUT
-  int update_one_sync = 0;  // mcl3dl_measure_update on ONE device: normalise from the device-side total, one host
+  int update_one_sync = 1;  // mcl3dl_measure_update on ONE device: normalise from the device-side total, one host
                             // synchronise instead of two (MCL3DL_UPDATE_ONE_SYNC=1; written without GPU time left in
                             // round 1: off until the f2 parity tests have run with it)
-  int lik_chunks = 0;  // MCL3DL_LIK=chunk in -DMCL3DL_LIK_CHUNKS=1 builds: the warp-chunk likelihood kernel
+  int nnf = 1;  // stage the NN field (exact per-voxel candidate lists) and use lik_kernel_nf; MCL3DL_NNF=0: the CSR window kernels
+  size_t nnf_max_bytes = size_t(32) << 30;  // MCL3DL_NNF_MAX_MB: directory + candidates above this -> no field
+  uint64_t nnf_bytes = 0, nnf_cands = 0, nnf_voxels = 0, nnf_overflow_cells = 0;
   int mapping = 1;  // 1 = tuned kernels (lik_kernel_wi + beam_kernel_pl); 0 = the plain group kernels (MCL3DL_MAPPING=group)
 };
 
@@ -343,47 +421,45 @@ int opt_in_smem(mcl3dl_engine* eng, DeviceCtx& c, K kernel, int bytes)
 
 template <int TPP>
 int launch_lik_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int P, const float4* scan, int N,
-                 mcl3dl_result* out, int beam_defaults, cudaStream_t st)
+                 mcl3dl_result* out, int beam_defaults, cudaStream_t st, const RecordSink& sink)
 {
   constexpr int PPB = kBlockThreads / TPP;
   const int groups = (P + PPB - 1) / PPB;
   const int grid = std::max(1, std::min(groups, c.sm_count * 8));
   const size_t bytes = static_cast<size_t>(N) * 16;
-#if MCL3DL_LIK_CHUNKS
-  if (eng->mapping != 0 && eng->lik_chunks)
+  if (eng->mapping != 0 && c.nn.field.dir)
   {
-    if (bytes <= static_cast<size_t>(kMaxStagedSorted))
+    // NN-field kernel: light on registers and shared memory, so the grid is sized to whole waves of its own occupancy
+    if (bytes <= static_cast<size_t>(kMaxStagedBytes))
     {
-      if (int rc = opt_in_smem(eng, c, lik_kernel_wc<TPP, true>, kMaxStagedSorted)) return rc;
-      lik_kernel_wc<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
+      if (int rc = opt_in_smem(eng, c, lik_kernel_nf<TPP, true>, kMaxStagedBytes)) return rc;
+      lik_kernel_nf<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr(), sink);
     }
     else
     {
-      lik_kernel_wc<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
+      lik_kernel_nf<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr(), sink);
     }
   }
-  else
-#endif
-  if (eng->mapping != 0)
+  else if (eng->mapping != 0)
   {
     if (bytes <= static_cast<size_t>(kMaxStagedSorted))
     {
       if (int rc = opt_in_smem(eng, c, lik_kernel_wi<TPP, true>, kMaxStagedSorted)) return rc;
-      lik_kernel_wi<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
+      lik_kernel_wi<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr(), sink);
     }
     else
     {
-      lik_kernel_wi<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
+      lik_kernel_wi<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr(), sink);
     }
   }
   else if (bytes <= static_cast<size_t>(kMaxStagedBytes))
   {
     if (int rc = opt_in_smem(eng, c, lik_kernel<TPP, true>, kMaxStagedBytes)) return rc;
-    lik_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
+    lik_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr(), sink);
   }
   else
   {
-    lik_kernel<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr());
+    lik_kernel<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr(), sink);
   }
   CK(cudaGetLastError());
   eng->launches++;
@@ -392,7 +468,7 @@ int launch_lik_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int
 
 template <int TPP>
 int launch_beam_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int P, const float4* scan, int N,
-                  const float* origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
+                  const float* origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st, const RecordSink& sink)
 {
   constexpr int PPB = kBlockThreads / TPP;
   const int groups = (P + PPB - 1) / PPB;
@@ -401,11 +477,11 @@ int launch_beam_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, in
   if (bytes <= static_cast<size_t>(kMaxStagedBytes))
   {
     if (int rc = opt_in_smem(eng, c, beam_kernel<TPP, true>, kMaxStagedBytes)) return rc;
-    beam_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, origins, c.dda, out, status, lik_defaults, c.stats_ptr());
+    beam_kernel<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, origins, c.dda, out, status, lik_defaults, c.stats_ptr(), sink);
   }
   else
   {
-    beam_kernel<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, origins, c.dda, out, status, lik_defaults, c.stats_ptr());
+    beam_kernel<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, origins, c.dda, out, status, lik_defaults, c.stats_ptr(), sink);
   }
   CK(cudaGetLastError());
   eng->launches++;
@@ -444,7 +520,8 @@ int prepare_pl_scratch(mcl3dl_engine* eng, DeviceCtx& c, size_t P, const PlShape
 }
 
 int launch_beam_pl(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
-                   const float* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
+                   const float* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st,
+                   const RecordSink& sink)
 {
   const PlShape sh = pick_pl_shape(P, N, c.sm_count);
   int rc = prepare_pl_scratch(eng, c, P, sh, st);
@@ -455,41 +532,42 @@ int launch_beam_pl(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, s
   if (eng->beam.use_raycast_using_dda)
     beam_kernel_pl<false><<<groups * sh.cb, kBlockThreads, smem, st>>>(
         poses, static_cast<int>(P), reinterpret_cast<const float4*>(scan), static_cast<int>(N), origins, c.dda, c.kd, c.nn, out,
-        status, lik_defaults, c.stats_ptr(), sh, static_cast<uint32_t*>(c.d_partial.p), static_cast<unsigned int*>(c.d_tickets.p));
+        status, lik_defaults, c.stats_ptr(), sh, static_cast<uint32_t*>(c.d_partial.p), static_cast<unsigned int*>(c.d_tickets.p), sink);
   else
     beam_kernel_pl<true><<<groups * sh.cb, kBlockThreads, smem, st>>>(
         poses, static_cast<int>(P), reinterpret_cast<const float4*>(scan), static_cast<int>(N), origins, c.dda, c.kd, c.nn, out,
-        status, lik_defaults, c.stats_ptr(), sh, static_cast<uint32_t*>(c.d_partial.p), static_cast<unsigned int*>(c.d_tickets.p));
+        status, lik_defaults, c.stats_ptr(), sh, static_cast<uint32_t*>(c.d_partial.p), static_cast<unsigned int*>(c.d_tickets.p), sink);
   CK(cudaGetLastError());
   eng->launches++;
   return MCL3DL_OK;
 }
 
 int launch_lik(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
-               mcl3dl_result* out, int beam_defaults, cudaStream_t st)
+               mcl3dl_result* out, int beam_defaults, cudaStream_t st, const RecordSink& sink)
 {
   const float4* s4 = reinterpret_cast<const float4*>(scan);
   switch (pick_tpp(P, N, c.sm_count))
   {
-    case 32: return launch_lik_t<32>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), out, beam_defaults, st);
-    case 64: return launch_lik_t<64>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), out, beam_defaults, st);
-    case 128: return launch_lik_t<128>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), out, beam_defaults, st);
-    default: return launch_lik_t<256>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), out, beam_defaults, st);
+    case 32: return launch_lik_t<32>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), out, beam_defaults, st, sink);
+    case 64: return launch_lik_t<64>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), out, beam_defaults, st, sink);
+    case 128: return launch_lik_t<128>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), out, beam_defaults, st, sink);
+    default: return launch_lik_t<256>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), out, beam_defaults, st, sink);
   }
 }
 
 int launch_beam(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
-                const float* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st)
+                const float* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st,
+                const RecordSink& sink)
 {
   if (eng->mapping != 0 || !eng->beam.use_raycast_using_dda)  // the KD-tree caster exists in the pl kernel only
-    return launch_beam_pl(eng, c, poses, P, scan, N, origins, n_origins, out, status, lik_defaults, st);
+    return launch_beam_pl(eng, c, poses, P, scan, N, origins, n_origins, out, status, lik_defaults, st, sink);
   const float4* s4 = reinterpret_cast<const float4*>(scan);
   switch (pick_tpp(P, N, c.sm_count))
   {
-    case 32: return launch_beam_t<32>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), origins, out, status, lik_defaults, st);
-    case 64: return launch_beam_t<64>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), origins, out, status, lik_defaults, st);
-    case 128: return launch_beam_t<128>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), origins, out, status, lik_defaults, st);
-    default: return launch_beam_t<256>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), origins, out, status, lik_defaults, st);
+    case 32: return launch_beam_t<32>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), origins, out, status, lik_defaults, st, sink);
+    case 64: return launch_beam_t<64>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), origins, out, status, lik_defaults, st, sink);
+    case 128: return launch_beam_t<128>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), origins, out, status, lik_defaults, st, sink);
+    default: return launch_beam_t<256>(eng, c, poses, static_cast<int>(P), s4, static_cast<int>(N), origins, out, status, lik_defaults, st, sink);
   }
 }
 
@@ -565,6 +643,118 @@ int build_near_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mc
   return MCL3DL_OK;
 }
 #endif
+
+// NN field (device_funcs.cuh: NnFieldDev) over the finished CSR grid g.  Leaves g.field.dir null when the field is
+// switched off, cannot be laid out, or would exceed the byte cap: the CSR-window kernels then serve the searches.
+int build_nn_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mcl3dl_point* pts, uint32_t n, NnGridDev& g,
+                   float radius, const float sc_min[3], const float sc_max[3])
+{
+  eng->nnf_bytes = eng->nnf_cands = eng->nnf_voxels = eng->nnf_overflow_cells = 0;
+  NearBitsDev lay{};
+  // the lattice of a k = 2 near field for this radius: fine edge 1.01 * radius / 2, origin 2.5 voxels below the box
+  if (!near_layout(lay, radius, 2, sc_min, sc_max, size_t(1) << 40))
+    return MCL3DL_OK;
+  NnFieldDev f{};
+  f.nx = lay.nx;
+  f.ny = lay.ny;
+  f.nz = lay.nz;
+  f.cnx = (lay.nx + 1) / 2;
+  f.cny = (lay.ny + 1) / 2;
+  f.cnz = (lay.nz + 1) / 2;
+  f.ox = lay.ox;
+  f.oy = lay.oy;
+  f.oz = lay.oz;
+  f.inv_e = lay.inv_cell;
+  f.e = 1.0f / lay.inv_cell;
+  f.radius = radius;
+  float ext = 0.0f;
+  for (int k = 0; k < 3; ++k) ext = std::max(ext, std::max(std::fabs(sc_min[k]), std::fabs(sc_max[k])) + 4.0f * f.e);
+  f.pad = 0.01f * f.e + 16.0f * std::numeric_limits<float>::epsilon() * ext;
+  const size_t n_cells = static_cast<size_t>(f.cnx) * f.cny * f.cnz;
+  const size_t bits_bytes = static_cast<size_t>(lay.pitch) * lay.ny * lay.nz * 4;
+  if (n_cells >= (size_t(1) << 31) || n_cells * 8 + bits_bytes > eng->nnf_max_bytes)
+    return MCL3DL_OK;
+  DevBuf d_bits, d_tot, d_tmp;
+  int rc = MCL3DL_OK;
+  auto cleanup = [&]() {
+    free_buf(d_bits);
+    free_buf(d_tot);
+    free_buf(d_tmp);
+  };
+#define CKF(call)                                                                  \
+  do                                                                               \
+  {                                                                                \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess)                                                        \
+    {                                                                              \
+      eng->err = std::string(#call) + ": " + cudaGetErrorString(e__);              \
+      cleanup();                                                                   \
+      return MCL3DL_ERR_CUDA;                                                      \
+    }                                                                              \
+  } while (0)
+  if ((rc = reserve(eng, d_bits, bits_bytes)) || (rc = reserve(eng, d_tot, (n_cells + 1) * 4)) ||
+      (rc = reserve(eng, c.nnf_dir, n_cells * sizeof(uint2))))
+  {
+    cleanup();
+    return rc;
+  }
+  CKF(cudaMemsetAsync(d_bits.p, 0, bits_bytes, st));
+  near_mark_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, g.wx, g.wy, g.wz, lay, static_cast<uint32_t*>(d_bits.p), 2);
+  const unsigned blocks = static_cast<unsigned>((n_cells * 8 + 255) / 256);
+  uint2* dir = static_cast<uint2*>(c.nnf_dir.p);
+  uint32_t* tot = static_cast<uint32_t*>(d_tot.p);
+  nnf_count_kernel<<<blocks, 256, 0, st>>>(g, f, static_cast<const uint32_t*>(d_bits.p), lay.pitch, dir, tot, n_cells);
+  CKF(cudaGetLastError());
+  // exclusive scan of the per-cell totals (in place); the grand total and the last cell's count size the candidates
+  size_t tmp_bytes = 0;
+  CKF(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tot, tot, static_cast<int>(n_cells + 1), st));
+  if ((rc = reserve(eng, d_tmp, tmp_bytes)))
+  {
+    cleanup();
+    return rc;
+  }
+  CKF(cudaMemsetAsync(tot + n_cells, 0, 4, st));
+  // 64-bit guard: sum the totals' upper bound on the host side via a second, 64-bit scan would cost more than it is
+  // worth; the counts are <= 8 * 14 per cell, so the total fits 32 bits when n_cells < 2^32 / 112
+  if (n_cells >= (size_t(0xfffffff0u) / (8 * kNnfMaxCand)))
+  {
+    cleanup();
+    free_buf(c.nnf_dir);
+    return MCL3DL_OK;
+  }
+  tmp_bytes = d_tmp.cap;
+  CKF(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, tot, tot, static_cast<int>(n_cells + 1), st));
+  uint32_t total = 0;
+  CKF(cudaMemcpyAsync(&total, tot + n_cells, 4, cudaMemcpyDeviceToHost, st));
+  CKF(cudaStreamSynchronize(st));
+  const size_t cand_bytes = static_cast<size_t>(total) * sizeof(float4);
+  if (n_cells * 8 + cand_bytes > eng->nnf_max_bytes)
+  {
+    cleanup();
+    free_buf(c.nnf_dir);
+    return MCL3DL_OK;
+  }
+  if ((rc = reserve(eng, c.nnf_cand, std::max<size_t>(cand_bytes, 16))))
+  {
+    cleanup();
+    return rc;
+  }
+  nnf_base_kernel<<<static_cast<unsigned>((n_cells + 255) / 256), 256, 0, st>>>(dir, tot, n_cells);
+  nnf_fill_kernel<<<blocks, 256, 0, st>>>(g, f, static_cast<const uint32_t*>(d_bits.p), lay.pitch, dir,
+                                          static_cast<float4*>(c.nnf_cand.p), n_cells);
+  CKF(cudaGetLastError());
+  CKF(cudaStreamSynchronize(st));
+  eng->launches += 4;
+  f.dir = dir;
+  f.cand = static_cast<const float4*>(c.nnf_cand.p);
+  g.field = f;
+  eng->nnf_bytes = n_cells * 8 + cand_bytes;
+  eng->nnf_cands = total;
+  c.map_bytes += eng->nnf_bytes;
+  cleanup();
+  return MCL3DL_OK;
+#undef CKF
+}
 
 // Build both grids on one device from the uploaded points.
 int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_pts, size_t n)
@@ -716,16 +906,39 @@ int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_
     eng->launches += 3;
     g.cell_start = static_cast<const uint32_t*>(c.nn_cell_start.p);
     g.pts = static_cast<const float4*>(c.nn_pts.p);
-    g.nyp = (g.ny + 4) & ~1;  // even pitch with room for the 4-entry fetch starting at (ly & ~1)
-    const size_t row3_total = static_cast<size_t>(g.nz) * g.nx * g.nyp;
-    CKB(reserve(eng, c.nn_row3, (row3_total + 2) * sizeof(uint2)));
-    g.row3 = static_cast<const uint2*>(c.nn_row3.p);
-    nn_row3_kernel<<<static_cast<unsigned>((row3_total + 255) / 256), 256, 0, st>>>(g, static_cast<uint2*>(c.nn_row3.p), row3_total);
-    CKC(cudaGetLastError());
-    eng->launches++;
 #if MCL3DL_NEAR_BITS
     CKB(build_near_field(eng, c, st, pts, n32, wx, wy, wz, eng->likdev.rpad, eng->near_k, sc_min, sc_max, c.near_lik, g.near, 0));
 #endif
+    // NN field: exact for the likelihood radius and, with the KD-tree raycaster, for its marching radius as well
+    {
+      float radius = eng->likdev.rpad;
+      if (eng->has_beam && !eng->beam.use_raycast_using_dda)
+      {
+        KdRayDev tmp{};
+        fill_kd_scalars(eng->beam, tmp);
+        radius = std::max(radius, tmp.r1_pad);
+      }
+      g.field = NnFieldDev{};
+      if (eng->nnf && eng->mapping != 0)
+        CKB(build_nn_field(eng, c, st, pts, n32, g, radius, sc_min, sc_max));
+    }
+    // window table of the CSR-window kernel (lik_kernel_wi): only when the field is not staged
+    size_t row3_total = 0;
+    g.nyp = (g.ny + 4) & ~1;  // even pitch with room for the 4-entry fetch starting at (ly & ~1)
+    if (!g.field.dir)
+    {
+      row3_total = static_cast<size_t>(g.nz) * g.nx * g.nyp;
+      CKB(reserve(eng, c.nn_row3, (row3_total + 2) * sizeof(uint2)));
+      g.row3 = static_cast<const uint2*>(c.nn_row3.p);
+      nn_row3_kernel<<<static_cast<unsigned>((row3_total + 255) / 256), 256, 0, st>>>(g, static_cast<uint2*>(c.nn_row3.p), row3_total);
+      CKC(cudaGetLastError());
+      eng->launches++;
+    }
+    else
+    {
+      free_buf(c.nn_row3);
+      g.row3 = nullptr;
+    }
     c.nn = g;
     c.map_bytes += (cells + 1) * 4 + n * 16 + row3_total * sizeof(uint2);
     eng->info.nn_dims[0] = g.nx;
@@ -750,17 +963,6 @@ int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_
 #if MCL3DL_NEAR_BITS
     CKB(build_near_field(eng, c, st, pts, n32, wx, wy, wz, c.kd.r1_pad, eng->near_kd_k, sc_min, sc_max, c.near_kd, c.kd.near, 1));
     c.near_kd_r = c.kd.r1_pad;
-#endif
-#if MCL3DL_KD_SKIP
-    {
-      // skip-ahead field: radius = marching radius + kd_skip_steps steps along the least-weighted axis
-      const float wmin = std::min(wx, std::min(wy, wz));
-      const float reach = static_cast<float>(eng->kd_skip_steps) * c.kd.grid_min * wmin;
-      c.far_kd_r = c.kd.r1_pad + reach / 0.98f;
-      CKB(build_near_field(eng, c, st, pts, n32, wx, wy, wz, c.far_kd_r, eng->kd_skip_steps > 0 ? 1 : 0, sc_min, sc_max, c.far_kd,
-                           c.kd.far, 2));
-      c.kd.far_margin = 0.98f * (c.far_kd_r - c.kd.r1_pad);
-    }
 #endif
     free_buf(c.raw_pts);
     c.raw_pts = d_pts;  // keep the upload
@@ -906,8 +1108,6 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     eng->near_k = std::min(std::max(std::atoi(v), 0), 15);
   if (const char* v = std::getenv("MCL3DL_NEAR_KD_K"))
     eng->near_kd_k = std::min(std::max(std::atoi(v), 0), 15);
-  if (const char* v = std::getenv("MCL3DL_KD_SKIP_STEPS"))
-    eng->kd_skip_steps = std::min(std::max(std::atoi(v), 0), 64);
   if (const char* v = std::getenv("MCL3DL_NEAR_MAX_MB"))
     eng->near_max_bytes = static_cast<size_t>(std::max(std::atoi(v), 1)) << 20;
   if (const char* v = std::getenv("MCL3DL_TIMING"))
@@ -916,8 +1116,10 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     eng->zero_copy_max = static_cast<size_t>(std::max(std::atol(v), 0L));
   if (const char* v = std::getenv("MCL3DL_UPDATE_ONE_SYNC"))
     eng->update_one_sync = std::atoi(v) != 0;
-  if (const char* v = std::getenv("MCL3DL_LIK"))
-    eng->lik_chunks = std::strcmp(v, "chunk") == 0;
+  if (const char* v = std::getenv("MCL3DL_NNF"))
+    eng->nnf = std::atoi(v) != 0;
+  if (const char* v = std::getenv("MCL3DL_NNF_MAX_MB"))
+    eng->nnf_max_bytes = static_cast<size_t>(std::max(std::atol(v), 1L)) << 20;
   if (const char* o = std::getenv("MCL3DL_OVERLAP"))
     eng->overlap = std::atoi(o) != 0;
   if (const char* m = std::getenv("MCL3DL_MAPPING"))
@@ -964,6 +1166,8 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
   return MCL3DL_OK;
 }
 
+static void xchg_close(DeviceCtx& c);
+
 void mcl3dl_destroy(mcl3dl_engine* eng)
 {
   if (!eng)
@@ -973,17 +1177,12 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     cudaSetDevice(c.dev);
     if (c.stream)
       cudaStreamSynchronize(c.stream);
-    for (void*& o : c.x_opened)
-      if (o)
-      {
-        cudaIpcCloseMemHandle(o);
-        o = nullptr;
-      }
+    xchg_close(c);
     free_buf(c.xchg);
     free_buf(c.x_ticket);
     for (DevBuf* b : {&c.r_states[0], &c.r_states[1], &c.r_prob, &c.r_accum, &c.r_poses, &c.r_extra})
       free_buf(*b);
-    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.far_kd, &c.d_poses,
+    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.nnf_dir, &c.nnf_cand, &c.d_poses,
                       &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart})
       free_buf(*b);
     if (c.h_pinned)
@@ -1073,11 +1272,6 @@ int mcl3dl_set_params(mcl3dl_engine* eng, const mcl3dl_lik_params* lik, const mc
       if (c.kd.r1_pad > c.near_kd_r)
         c.kd.near.bits = nullptr;  // the field was built for a smaller marching radius: search unscreened
 #endif
-#if MCL3DL_KD_SKIP
-      c.kd.far_margin = 0.98f * (c.far_kd_r - c.kd.r1_pad);  // the step length is read per ray (grid_min may have changed)
-      if (!(c.kd.far_margin > 0.0f))
-        c.kd.far.bits = nullptr;
-#endif
     }
   }
   return MCL3DL_OK;
@@ -1137,9 +1331,10 @@ static int validate_measure(mcl3dl_engine* eng, size_t P, size_t n_lik, size_t n
 // launch: the other kernel writes its (1, 0).  `timed` records ev[2]/ev[3] (likelihood) and ev_b0/ev_b1 (beam).
 static int launch_models(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik,
                          size_t n_lik, const mcl3dl_point* beam, size_t n_beam, const float* origins, size_t n_origins,
-                         mcl3dl_result* out, uint8_t* status, cudaStream_t st, bool timed)
+                         mcl3dl_result* out, uint8_t* status, cudaStream_t st, bool timed, const RecordSink* sink_in = nullptr)
 {
   int rc = MCL3DL_OK;
+  const RecordSink sink = sink_in ? *sink_in : RecordSink{};
   const bool both = n_beam && n_lik && eng->overlap;
   cudaStream_t sb = both ? c.side : st;
   if (n_beam)
@@ -1150,7 +1345,7 @@ static int launch_models(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* po
       CK(cudaStreamWaitEvent(sb, c.ev_fork, 0));
     }
     if (timed) CK(cudaEventRecord(c.ev_b0, sb));
-    rc = launch_beam(eng, c, poses, P, beam, n_beam, origins, static_cast<int>(n_origins), out, status, n_lik == 0, sb);
+    rc = launch_beam(eng, c, poses, P, beam, n_beam, origins, static_cast<int>(n_origins), out, status, n_lik == 0, sb, sink);
     if (rc != MCL3DL_OK)
       return rc;
     if (timed) CK(cudaEventRecord(c.ev_b1, sb));
@@ -1159,7 +1354,7 @@ static int launch_models(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* po
   if (timed) CK(cudaEventRecord(c.ev[2], st));
   if (n_lik || !n_beam)
   {
-    rc = launch_lik(eng, c, poses, P, lik, n_lik, out, n_beam == 0, st);
+    rc = launch_lik(eng, c, poses, P, lik, n_lik, out, n_beam == 0, st, sink);
     if (rc != MCL3DL_OK)
       return rc;
   }
@@ -1347,30 +1542,39 @@ int mcl3dl_particles_measure_update(mcl3dl_engine* eng, const mcl3dl_point* lik_
   return MCL3DL_OK;
 }
 
-// ---- record exchange over peer memory (bench.py --exchange peer; one process per GPU, one device per engine)
+// ---- record exchange over peer memory (one process per GPU, one device per engine; kernels.cuh: RecordSink +
+// exchange_signal_kernel).  Buffer of a rank: [array 0: world * n_local records | array 1 | world flags]; the step
+// counter and the error word live in x_ticket (local only).
 static size_t xchg_flags_offset(size_t n_local, int world)
 {
   return (2 * static_cast<size_t>(world) * n_local * sizeof(mcl3dl_result) + 255) & ~size_t(255);  // two arrays, by step parity
 }
 
-int mcl3dl_exchange_create(mcl3dl_engine* eng, size_t n_local, int world, int rank, void* ipc_handle_out)
+static void xchg_close(DeviceCtx& c)
 {
-  if (!eng || eng->devs.size() != 1 || n_local == 0 || world < 1 || world > kMaxPeers || rank < 0 || rank >= world ||
-      !ipc_handle_out)
-    return MCL3DL_ERR_INVALID_ARG;
-  static_assert(sizeof(cudaIpcMemHandle_t) == MCL3DL_IPC_HANDLE_BYTES, "ipc handle size");
-  DeviceCtx& c = eng->devs[0];
-  CK(cudaSetDevice(c.dev));
-  const size_t flags_off = xchg_flags_offset(n_local, world);
-  const size_t bytes = flags_off + 256;
   for (void*& o : c.x_opened)
     if (o)
     {
       cudaIpcCloseMemHandle(o);
       o = nullptr;
     }
-  free_buf(c.xchg);  // a fresh cudaMalloc: IPC handles name whole allocations
-  int rc = reserve(eng, c.xchg, bytes);
+  c.x_ready = false;
+}
+
+int mcl3dl_exchange_create(mcl3dl_engine* eng, size_t n_local, int world, int rank, void* ipc_handle_out)
+{
+  if (!eng || eng->devs.size() != 1 || n_local == 0 || world < 1 || world > kMaxPeers || rank < 0 || rank >= world ||
+      !ipc_handle_out || static_cast<size_t>(world) * n_local >= (size_t(1) << 30))
+    return MCL3DL_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == MCL3DL_IPC_HANDLE_BYTES, "ipc handle size");
+  DeviceCtx& c = eng->devs[0];
+  // one exchange per engine lifetime: a second create would free a buffer that the peers still have mapped
+  if (c.xchg.p)
+    return MCL3DL_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c.dev));
+  const size_t flags_off = xchg_flags_offset(n_local, world);
+  const size_t bytes = flags_off + 256;
+  int rc = reserve(eng, c.xchg, bytes);  // a fresh cudaMalloc: IPC handles name whole allocations
   if (rc != MCL3DL_OK || (rc = reserve(eng, c.x_ticket, 256)) != MCL3DL_OK)
     return rc;
   CK(cudaMemset(c.xchg.p, 0, c.xchg.cap));
@@ -1382,6 +1586,7 @@ int mcl3dl_exchange_create(mcl3dl_engine* eng, size_t n_local, int world, int ra
   c.xt = PeerTable{};
   c.xt.world = world;
   c.xt.rank = rank;
+  c.xsink = RecordSink{};
   c.x_local = n_local;
   c.x_step = 0;
   c.x_ready = false;
@@ -1393,7 +1598,7 @@ int mcl3dl_exchange_open(mcl3dl_engine* eng, const void* ipc_handles /* world x 
   if (!eng || eng->devs.size() != 1 || !ipc_handles)
     return MCL3DL_ERR_INVALID_ARG;
   DeviceCtx& c = eng->devs[0];
-  if (!c.xchg.p || c.xt.world < 1)
+  if (!c.xchg.p || c.xt.world < 1 || c.x_ready)
     return MCL3DL_ERR_INVALID_ARG;
   CK(cudaSetDevice(c.dev));
   const size_t flags_off = xchg_flags_offset(c.x_local, c.xt.world);
@@ -1404,46 +1609,69 @@ int mcl3dl_exchange_open(mcl3dl_engine* eng, const void* ipc_handles /* world x 
     {
       cudaIpcMemHandle_t h;
       std::memcpy(&h, static_cast<const char*>(ipc_handles) + static_cast<size_t>(g) * sizeof(h), sizeof(h));
-      CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+      const cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+      {
+        eng->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+        xchg_close(c);
+        return MCL3DL_ERR_CUDA;
+      }
       c.x_opened[g] = base;
     }
-    c.xt.records[g] = static_cast<uint2*>(base);
+    // this rank's slot inside rank g's array 0
+    c.xsink.base[g] = static_cast<mcl3dl_result*>(base) + static_cast<size_t>(c.xt.rank) * c.x_local;
     c.xt.flags[g] = reinterpret_cast<uint32_t*>(static_cast<char*>(base) + flags_off);
   }
+  c.xsink.step = static_cast<const uint32_t*>(c.x_ticket.p);
+  c.xsink.parity_stride = static_cast<uint32_t>(static_cast<size_t>(c.xt.world) * c.x_local);
+  c.xsink.world = c.xt.world;
   c.x_ready = true;
   return MCL3DL_OK;
 }
 
-int mcl3dl_exchange_records(mcl3dl_engine* eng, const mcl3dl_result* d_local, size_t n_local, void* cuda_stream,
-                            const mcl3dl_result** d_all_out)
+int mcl3dl_measure_exchange_device(mcl3dl_engine* eng, const mcl3dl_pose* d_poses, size_t P, const mcl3dl_point* d_lik,
+                                   size_t n_lik, const mcl3dl_point* d_beam, size_t n_beam, const float* d_origins_xyz,
+                                   size_t n_origins, void* cuda_stream, const mcl3dl_result** d_all_out)
 {
-  if (!eng || eng->devs.size() != 1 || !d_local)
+  int rc = validate_measure(eng, P, n_lik, n_beam, n_origins);
+  if (rc != MCL3DL_OK)
+    return rc;
+  if (eng->devs.size() != 1 || !d_poses || (n_lik && !d_lik) || (n_beam && (!d_beam || !d_origins_xyz)))
     return MCL3DL_ERR_INVALID_ARG;
   DeviceCtx& c = eng->devs[0];
-  if (!c.x_ready || n_local != c.x_local)
+  if (!c.x_ready || P != c.x_local)
     return MCL3DL_ERR_INVALID_ARG;
   CK(cudaSetDevice(c.dev));
-  const size_t n_units = n_local * (sizeof(mcl3dl_result) / sizeof(uint2));
-  const int grid = static_cast<int>(std::min<size_t>((n_units + kBlockThreads - 1) / kBlockThreads, static_cast<size_t>(c.sm_count)));
-  ++c.x_step;
-  exchange_kernel<<<grid, kBlockThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
-      reinterpret_cast<const uint2*>(d_local), n_units, c.xt, c.x_step, static_cast<unsigned int*>(c.x_ticket.p));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  rc = launch_models(eng, c, d_poses, P, d_lik, n_lik, d_beam, n_beam, d_origins_xyz, n_origins, nullptr, nullptr, st, false,
+                     &c.xsink);
+  if (rc != MCL3DL_OK)
+    return rc;
+  unsigned int* tk = static_cast<unsigned int*>(c.x_ticket.p);
+  exchange_signal_kernel<<<1, 32, 0, st>>>(c.xt, tk, tk + 1);
   CK(cudaGetLastError());
   eng->launches++;
+  ++c.x_step;  // host mirror of the device counter; exact for eager calls, resynchronised by mcl3dl_exchange_current
   if (d_all_out)
-    *d_all_out = static_cast<const mcl3dl_result*>(c.xchg.p) + static_cast<size_t>(c.x_step & 1u) * c.xt.world * n_local;
+    *d_all_out = static_cast<const mcl3dl_result*>(c.xchg.p) + static_cast<size_t>(c.x_step & 1u) * c.xt.world * c.x_local;
   return MCL3DL_OK;
 }
 
-int mcl3dl_exchange_failed(mcl3dl_engine* eng, int* failed_out)
+int mcl3dl_exchange_current(mcl3dl_engine* eng, void* cuda_stream, const mcl3dl_result** d_all_out, int* failed_out)
 {
-  if (!eng || eng->devs.size() != 1 || !failed_out || !eng->devs[0].x_ticket.p)
+  if (!eng || eng->devs.size() != 1 || !eng->devs[0].x_ticket.p)
     return MCL3DL_ERR_INVALID_ARG;
   DeviceCtx& c = eng->devs[0];
   CK(cudaSetDevice(c.dev));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   unsigned int w[2] = {0, 0};
-  CK(cudaMemcpy(w, c.x_ticket.p, sizeof(w), cudaMemcpyDeviceToHost));  // synchronises with the exchanges enqueued so far
-  *failed_out = w[1] != 0;
+  CK(cudaMemcpyAsync(w, c.x_ticket.p, sizeof(w), cudaMemcpyDeviceToHost, st));  // after everything enqueued on the stream
+  CK(cudaStreamSynchronize(st));
+  c.x_step = w[0];  // graph replays advance the device counter without the host mirror
+  if (d_all_out)
+    *d_all_out = static_cast<const mcl3dl_result*>(c.xchg.p) + static_cast<size_t>(c.x_step & 1u) * c.xt.world * c.x_local;
+  if (failed_out)
+    *failed_out = w[1] != 0;
   return MCL3DL_OK;
 }
 

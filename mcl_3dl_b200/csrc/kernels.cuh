@@ -33,6 +33,72 @@ __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v)
   return __reduce_add_sync(0xffffffffu, v);
 }
 
+// --------------------------------------------------------------------------------------------
+// Where a kernel's writer lane stores its particle's record fields.  world == 0: the plain output array `out`.
+// world >= 1 (one process per GPU): the record exchange is folded into the kernels' epilogues — the writer
+// stores the fields straight into slot `rank` of EVERY rank's gathered array over NVLink (peer memory mapped with CUDA
+// IPC), so no collective and no copy kernel follows; exchange_signal_kernel then publishes "rank r finished step s".
+// The gathered array is double-buffered by step parity (a peer may already be one step ahead); the parity of the
+// upcoming step is read from the device-side step counter, so the launch sequence is identical every step (CUDA graph).
+constexpr int kMaxPeers = 8;
+struct RecordSink
+{
+  mcl3dl_result* base[kMaxPeers];  // every rank's array 0, already offset to this rank's slot (own buffer at [rank])
+  const uint32_t* step;            // completed-step counter of this rank (device memory)
+  uint32_t parity_stride;          // records between array 0 and array 1 (= world * n_local)
+  int world;
+};
+
+// offset of particle p's record inside a rank's array 0 (world >= 1) — the parity of the step about to complete
+__device__ __forceinline__ uint32_t sink_offset(const RecordSink& s, int p)
+{
+  return ((__ldcg(s.step) + 1u) & 1u) * s.parity_stride + static_cast<uint32_t>(p);
+}
+
+// likelihood-model fields (+ the beam model's (1, 0) when that model has no scan this update)
+__device__ __forceinline__ void sink_store_lik(const RecordSink& s, mcl3dl_result* out, int p, float score_like,
+                                               uint32_t match_cnt, int write_beam_defaults)
+{
+  const uint32_t off = s.world ? sink_offset(s, p) : 0u;
+#pragma unroll
+  for (int g = 0; g < kMaxPeers; ++g)
+    if (g < max(s.world, 1))
+    {
+      mcl3dl_result* o = s.world ? s.base[g] + off : out + p;  // s.base[g]: a constant-bank read (unrolled)
+      o->score_like = score_like;
+      o->match_cnt = match_cnt;
+      if (write_beam_defaults)
+      {
+        // no beam scan this update: LidarMeasurementResult(1, 0), beam.cpp:130-133
+        o->score_beam = 1.0f;
+        o->n_short = 0;
+        o->n_hit = 0;
+        o->n_long = 0;
+      }
+    }
+}
+
+__device__ __forceinline__ void sink_store_beam(const RecordSink& s, mcl3dl_result* out, int p, float score_beam, uint32_t n_short,
+                                                uint32_t n_hit, uint32_t n_long, int write_lik_defaults)
+{
+  const uint32_t off = s.world ? sink_offset(s, p) : 0u;
+#pragma unroll
+  for (int g = 0; g < kMaxPeers; ++g)
+    if (g < max(s.world, 1))
+    {
+      mcl3dl_result* o = s.world ? s.base[g] + off : out + p;
+      o->score_beam = score_beam;
+      o->n_short = n_short;
+      o->n_hit = n_hit;
+      o->n_long = n_long;
+      if (write_lik_defaults)
+      {
+        // no likelihood scan this update: LidarMeasurementResult(1, 0), likelihood.cpp:111-114
+        o->score_like = 1.0f;
+        o->match_cnt = 0;
+      }
+    }
+}
 
 // --------------------------------------------------------------------------------------------
 // Stage `bytes` (multiple of 16) from global to shared with one TMA bulk copy; all threads wait.
@@ -115,7 +181,7 @@ template <int TPP, bool STAGED>
 __global__ void __launch_bounds__(kBlockThreads)
     lik_kernel(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N, NnGridDev g,
                LikDev lp, mcl3dl_result* __restrict__ out, int write_beam_defaults,
-               unsigned long long* __restrict__ stats)
+               unsigned long long* __restrict__ stats, RecordSink sink)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
@@ -175,20 +241,8 @@ __global__ void __launch_bounds__(kBlockThreads)
       }
     }
     group_reduce<TPP>(score, cnt, z0, z1, red_f, red_u);
-    if (live && l == 0)
-    {
-      // empty scan -> LidarMeasurementResult(1, 0), likelihood.cpp:111-114
-      out[p].score_like = (N == 0) ? 1.0f : score;
-      out[p].match_cnt = cnt;
-      if (write_beam_defaults)
-      {
-        // no beam scan this update: LidarMeasurementResult(1, 0), beam.cpp:130-133
-        out[p].score_beam = 1.0f;
-        out[p].n_short = 0;
-        out[p].n_hit = 0;
-        out[p].n_long = 0;
-      }
-    }
+    if (live && l == 0)  // empty scan -> LidarMeasurementResult(1, 0), likelihood.cpp:111-114
+      sink_store_lik(sink, out, p, (N == 0) ? 1.0f : score, cnt, write_beam_defaults);
   }
   if (stats)
   {
@@ -241,7 +295,7 @@ template <int TPP, bool STAGED>
 __global__ void __launch_bounds__(kBlockThreads, 4)
     lik_kernel_wi(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N, NnGridDev g,
                   LikDev lp, mcl3dl_result* __restrict__ out, int write_beam_defaults,
-                  unsigned long long* __restrict__ stats)
+                  unsigned long long* __restrict__ stats, RecordSink sink)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
@@ -448,20 +502,8 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
       __syncwarp();
     }
     group_reduce<TPP>(score, cnt, z0, z1, red_f, red_u);
-    if (live && l == 0)
-    {
-      // empty scan -> LidarMeasurementResult(1, 0), likelihood.cpp:111-114
-      out[p].score_like = (N == 0) ? 1.0f : score;
-      out[p].match_cnt = cnt;
-      if (write_beam_defaults)
-      {
-        // no beam scan this update: LidarMeasurementResult(1, 0), beam.cpp:130-133
-        out[p].score_beam = 1.0f;
-        out[p].n_short = 0;
-        out[p].n_hit = 0;
-        out[p].n_long = 0;
-      }
-    }
+    if (live && l == 0)  // empty scan -> LidarMeasurementResult(1, 0), likelihood.cpp:111-114
+      sink_store_lik(sink, out, p, (N == 0) ? 1.0f : score, cnt, write_beam_defaults);
   }
   if (stats)
   {
@@ -474,24 +516,37 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
   }
 }
 
-#if MCL3DL_LIK_CHUNKS
-// Warp-chunk likelihood kernel: lik_kernel_wi with phase 2 dealt in chunks of <= 4 map points instead of whole runs
-// (the per-lane pieces and the reasoning are in device_funcs.cuh).  Same results, bit for bit.  Host-verified lane by
-// lane (tests/hostsim: hostsim_lik_wc); not yet run on a GPU, selected with MCL3DL_LIK=chunk in builds that carry it.
-// (Deliberately a copy of lik_kernel_wi around a different round: sharing the body through one device-function template
-// changed the SASS of the validated lik_kernel_wi<256,*> / <32,*> instantiations — profiles/sass_fingerprint.py — so the
-// two are to be merged when a GPU is at hand to re-validate.)
+
+// --------------------------------------------------------------------------------------------
+// NN-field likelihood kernel (the default when set_map staged the field, device_funcs.cuh: NnFieldDev).
+//
+// ncu on lik_kernel_wi (profiles/r02a_ncu_lik_c2.txt / _c5.txt): 36-41 warp instructions per eval at 17-19 live lanes,
+// L1/TEX the busiest unit (48 % on c2, 85 % on c5), DRAM < 1 %: the kernel is bound by the instructions and the
+// gather wavefronts of walking a 3 x 3 window of CSR rows per eval, not by HBM.  With the field an eval is: transform,
+// one 8-byte directory entry, then the 3-6 contiguous candidates of its voxel — two dependent loads, ~1/4 of the
+// instructions, no warp-level dealing.  Lane = eval; two evals per lane and iteration are in flight so that their
+// directory loads overlap.  The per-lane accumulation order (j = l, l + TPP, ...) and the reductions are those of
+// lik_kernel / lik_kernel_wi, so the records are bit-identical to theirs.
+__device__ __noinline__ float nn_dist2_generic(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz,
+                                               uint32_t& n_rows, uint32_t& n_pts)
+{
+  return nn_dist2(g, lp, qx, qy, qz, n_rows, n_pts);
+}
+
+// resident CTAs per SM the compiler must allow (register cap): 4 -> 64 registers, 5 -> 48, 6 -> 40, 8 -> 32
+#ifndef MCL3DL_NF_MINB
+#define MCL3DL_NF_MINB 4
+#endif
 template <int TPP, bool STAGED>
-__global__ void __launch_bounds__(kBlockThreads, 4)
-    lik_kernel_wc(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N, NnGridDev g,
+__global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
+    lik_kernel_nf(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N, NnGridDev g,
                   LikDev lp, mcl3dl_result* __restrict__ out, int write_beam_defaults,
-                  unsigned long long* __restrict__ stats)
+                  unsigned long long* __restrict__ stats, RecordSink sink)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
   __shared__ float red_f[kBlockThreads / 32];
   __shared__ uint32_t red_u[3 * kBlockThreads / 32];
-  __shared__ LikChunkSmem wsm_all[kBlockThreads / 32];
   const float4* pts = scan;
   if (STAGED && N > 0)
   {
@@ -499,13 +554,10 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
     pts = reinterpret_cast<const float4*>(smem_raw);
   }
   constexpr int PPB = kBlockThreads / TPP;
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  LikChunkSmem& sm = wsm_all[tid >> 5];
-  const int sub = tid / TPP;
-  const int l = tid % TPP;
+  const int sub = threadIdx.x / TPP;
+  const int l = threadIdx.x % TPP;
   const int n_groups = (P + PPB - 1) / PPB;
-  const uint32_t r2_bits = __float_as_uint(lp.r2);
+  const NnFieldDev& f = g.field;
   uint32_t st_rows = 0, st_pts = 0;
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
   {
@@ -513,15 +565,11 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
     const bool live = p < P;
     float score = 0.0f;
     uint32_t cnt = 0, z0 = 0, z1 = 0;
-    F3 pos;
-    Q4 rn;
-    pos.x = pos.y = pos.z = 0.0f;
-    rn.x = rn.y = rn.z = 0.0f;
-    rn.w = 1.0f;
     if (live)
     {
       const float4 a = __ldg(reinterpret_cast<const float4*>(poses + p));
       const float4 b = __ldg(reinterpret_cast<const float4*>(poses + p) + 1);
+      F3 pos;
       pos.x = a.x;
       pos.y = a.y;
       pos.z = a.z;
@@ -530,82 +578,76 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
       q.y = b.y;
       q.z = b.z;
       q.w = b.w;
-      rn = qnormalized(q);  // state_6dof.h:217
-    }
-    // a warp's 32 lanes always belong to one particle (TPP >= 32), so the trip count is warp-uniform
-    for (int jbase = 0; jbase < N; jbase += TPP)
-    {
-      const int j = jbase + l;
-      const bool valid = live && j < N;
-      // ---------------- phase 1: lane = eval (device_funcs.cuh: wc_window)
-      int nr = 0, nc = 0;
-      sm.best[lane] = r2_bits;
-      if (valid)
+      const Q4 rn = qnormalized(q);  // state_6dof.h:217
+      for (int j = l; j < N; j += 2 * TPP)
       {
-        const float4 sp = pts[j];
-        F3 v;
-        v.x = sp.x;
-        v.y = sp.y;
-        v.z = sp.z;
-        const F3 t = transform_point(rn, pos, v);
-        // PointRepresentation::vectorize with rescale values (mcl_3dl.cpp:1270)
-        const float qx = fmul(t.x, g.wx), qy = fmul(t.y, g.wy), qz = fmul(t.z, g.wz);
-        sm.qx[lane] = qx;
-        sm.qy[lane] = qy;
-        sm.qz[lane] = qz;
-        nr = wc_window(g, lp, qx, qy, qz, lane, sm, st_rows, st_pts, nc);
-      }
-      // ---------------- deal the warp's 4-point chunks to its lanes: one prefix sum carries the chunk counts (low half,
-      // clamped so that 32 lanes cannot overflow it) and the run counts (high half, for the overflow fallback)
-      const uint32_t mine = static_cast<uint32_t>(min(nc, kWcOverflow)) | (static_cast<uint32_t>(nr) << 16);
-      uint32_t incl = mine;
+        const bool two = j + TPP < N;
+        // ---- both evals' queries and directory entries first (independent loads in flight)
+        float qx[2], qy[2], qz[2];
+        int c[2];
+        uint32_t s[2];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
-      {
-        const uint32_t nbr = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o)
-          incl += nbr;
-      }
-      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-      const bool whole = (total & 0xffffu) > static_cast<uint32_t>(kWcMaxDesc);  // warp-uniform; only very dense maps
-      const int n_desc = static_cast<int>(whole ? (total >> 16) : (total & 0xffffu));
-      const uint32_t excl = incl - mine;
-      wc_write_descs(sm, lane, nr, static_cast<int>(whole ? (excl >> 16) : (excl & 0xffffu)), whole);
-      __syncwarp();
-      // ---------------- phase 2: lane = chunk of <= 4 consecutive map points
-      for (int it = lane; it < n_desc; it += 32) wc_process(sm, sm.desc[it], whole, g, lp);
-      __syncwarp();
-      // ---------------- owner lane: likelihood.cpp:128-133
-      if (valid)
-      {
-        const float d2 = __uint_as_float(sm.best[lane]);
-        if (d2 < lp.r2)
+        for (int u = 0; u < 2; ++u)
         {
-          const float dist = fsub(lp.match_dist_min, fmaxf(__fsqrt_rn(d2), lp.match_dist_flat));
-          if (!(dist < 0.0f))
+          c[u] = 0;
+          s[u] = 0;
+          qx[u] = qy[u] = qz[u] = 0.0f;
+          if (u == 0 || two)
           {
-            score = fadd(score, fmul(dist, lp.match_weight));
-            cnt++;
+            const float4 sp = pts[j + u * TPP];
+            F3 v;
+            v.x = sp.x;
+            v.y = sp.y;
+            v.z = sp.z;
+            const F3 t = transform_point(rn, pos, v);
+            // PointRepresentation::vectorize with rescale values (mcl_3dl.cpp:1270)
+            qx[u] = fmul(t.x, g.wx);
+            qy[u] = fmul(t.y, g.wy);
+            qz[u] = fmul(t.z, g.wz);
+            c[u] = nnf_lookup(f, qx[u], qy[u], qz[u], s[u]);
+            ++st_rows;
+          }
+        }
+        // ---- candidates of both voxels, interleaved
+        float best[2] = {lp.r2, lp.r2};
+        const int cm = max(c[0], c[1]);
+        for (int i = 0; i < cm; ++i)
+        {
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (i < c[u])
+            {
+              const float4 m = __ldg(f.cand + s[u] + i);
+              // flann::L2_Simple: sequential float accumulate of squared differences
+              const float dx = fsub(qx[u], m.x);
+              const float dy = fsub(qy[u], m.y);
+              const float dz = fsub(qz[u], m.z);
+              best[u] = fminf(best[u], fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz)));  // keep d < worst
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+        {
+          if (c[u] < 0)  // overflow cell (raw clouds): the CSR window search
+            best[u] = nn_dist2_generic(g, lp, qx[u], qy[u], qz[u], st_rows, st_pts);
+          else
+            st_pts += static_cast<uint32_t>(c[u]);
+          if ((u == 0 || two) && best[u] < lp.r2)
+          {
+            // likelihood.cpp:128-133
+            const float dist = fsub(lp.match_dist_min, fmaxf(__fsqrt_rn(best[u]), lp.match_dist_flat));
+            if (!(dist < 0.0f))
+            {
+              score = fadd(score, fmul(dist, lp.match_weight));
+              cnt++;
+            }
           }
         }
       }
-      __syncwarp();
     }
     group_reduce<TPP>(score, cnt, z0, z1, red_f, red_u);
-    if (live && l == 0)
-    {
-      // empty scan -> LidarMeasurementResult(1, 0), likelihood.cpp:111-114
-      out[p].score_like = (N == 0) ? 1.0f : score;
-      out[p].match_cnt = cnt;
-      if (write_beam_defaults)
-      {
-        // no beam scan this update: LidarMeasurementResult(1, 0), beam.cpp:130-133
-        out[p].score_beam = 1.0f;
-        out[p].n_short = 0;
-        out[p].n_hit = 0;
-        out[p].n_long = 0;
-      }
-    }
+    if (live && l == 0)  // empty scan -> LidarMeasurementResult(1, 0), likelihood.cpp:111-114
+      sink_store_lik(sink, out, p, (N == 0) ? 1.0f : score, cnt, write_beam_defaults);
   }
   if (stats)
   {
@@ -617,13 +659,12 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
     }
   }
 }
-#endif  // MCL3DL_LIK_CHUNKS
 
 template <int TPP, bool STAGED>
 __global__ void __launch_bounds__(kBlockThreads)
     beam_kernel(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N,
                 const float* __restrict__ origins, DdaGridDev g, mcl3dl_result* __restrict__ out,
-                uint8_t* __restrict__ status, int write_lik_defaults, unsigned long long* __restrict__ stats)
+                uint8_t* __restrict__ status, int write_lik_defaults, unsigned long long* __restrict__ stats, RecordSink sink)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
@@ -689,16 +730,7 @@ __global__ void __launch_bounds__(kBlockThreads)
         if (score < g.beam_likelihood_min)
           score = g.beam_likelihood_min;
       }
-      out[p].score_beam = score;
-      out[p].n_short = n_short;
-      out[p].n_hit = n_hit;
-      out[p].n_long = n_long;
-      if (write_lik_defaults)
-      {
-        // no likelihood scan this update: LidarMeasurementResult(1, 0), likelihood.cpp:111-114
-        out[p].score_like = 1.0f;
-        out[p].match_cnt = 0;
-      }
+      sink_store_beam(sink, out, p, score, n_short, n_hit, n_long, write_lik_defaults);
     }
   }
   if (stats)
@@ -740,7 +772,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
                    const float* __restrict__ origins, DdaGridDev g, KdRayDev kd, NnGridDev nn,
                    mcl3dl_result* __restrict__ out,
                    uint8_t* __restrict__ status, int write_lik_defaults, unsigned long long* __restrict__ stats,
-                   PlShape sh, uint32_t* __restrict__ partial, unsigned int* __restrict__ tickets)
+                   PlShape sh, uint32_t* __restrict__ partial, unsigned int* __restrict__ tickets, RecordSink sink)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar;
@@ -850,15 +882,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
         if (score < g.beam_likelihood_min)
           score = g.beam_likelihood_min;
       }
-      out[p].score_beam = score;
-      out[p].n_short = a;
-      out[p].n_hit = b;
-      out[p].n_long = c;
-      if (write_lik_defaults)
-      {
-        out[p].score_like = 1.0f;
-        out[p].match_cnt = 0;
-      }
+      sink_store_beam(sink, out, p, score, a, b, c, write_lik_defaults);
     }
   }
   if (stats)
@@ -1036,21 +1060,19 @@ __global__ void weight_finish_kernel(WeightPartial* __restrict__ partials, int n
 }
 
 // --------------------------------------------------------------------------------------------
-// Record exchange over peer memory (one process per GPU; replaces the NCCL all-gather of the 24-byte records).
-// Every rank owns a buffer [2 x G * n_local records | G flags] that its peers have mapped (CUDA IPC over NVLink/NVSwitch);
-// the two record arrays alternate by step, so a peer that is already one step ahead writes the OTHER array while this
-// rank still reads the last one (it cannot get two steps ahead: its next exchange waits for this rank's next flag).
-// One launch per rank and step: (1) store the rank's records into slot `rank` of EVERY rank's buffer (plain 8-byte
-// stores, P2P writes for the peers); (2) the last CTA to finish releases flag[rank] = step in every buffer and then
-// spins until all G flags of its OWN buffer show this step — so when the kernel retires, this rank's copy of the whole
-// record array is complete, with no host involvement and no second launch.
-// Ordering: data stores -> __threadfence_system() -> CTA barrier -> ticket -> st.release.sys of the flag; the consumer
-// side is ld.acquire.sys in the spin loop.  Not yet run on hardware (written after round 1's GPU budget was spent).
-constexpr int kMaxPeers = 8;
+// Record exchange over peer memory, the signalling half (the data half is RecordSink: the measurement kernels store
+// their records into every rank's gathered array).  Every rank owns one buffer [2 x world * n_local records | flags]
+// that its peers have mapped (CUDA IPC over NVLink / NVSwitch).  After the two model kernels of step s have retired
+// (stream order; their peer stores are performed by then), ONE warp of this kernel
+//   (1) releases flag[rank] = s in every rank's buffer (fence.sys + st.release.sys), and
+//   (2) spins (ld.acquire.sys, bounded) until all `world` flags of its OWN buffer show >= s,
+// so when it retires this rank's copy of the whole array of step s is complete: no host involvement, no collective
+// library, one 32-thread launch.  Double buffering by step parity: a peer that is already one step ahead writes the
+// OTHER array; it cannot get two steps ahead because its next signal kernel waits for this rank's flag.
+// The step number lives in device memory (this kernel increments it), so a captured CUDA graph replays unchanged.
 struct PeerTable
 {
-  uint2* records[kMaxPeers];    // base of every rank's record array (this rank's own pointer at [rank])
-  uint32_t* flags[kMaxPeers];   // base of every rank's flag array
+  uint32_t* flags[kMaxPeers];  // base of every rank's flag array (this rank's own at [rank])
   int world, rank;
 };
 
@@ -1065,43 +1087,29 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
   return v;
 }
 
-__global__ void __launch_bounds__(kBlockThreads)
-    exchange_kernel(const uint2* __restrict__ local, size_t n_units /* n_local * 3 */, PeerTable t, uint32_t step,
-                    unsigned int* __restrict__ ticket /* [0] ticket, [1] set to 1 if a peer never showed up */)
+__global__ void __launch_bounds__(32)
+    exchange_signal_kernel(PeerTable t, uint32_t* __restrict__ step_ctr, unsigned int* __restrict__ err /* set to 1 on a timeout */)
 {
-  // array (step & 1) of every buffer, slot `rank` inside it
-  const size_t base = (static_cast<size_t>(step & 1u) * t.world + t.rank) * n_units;
-  for (size_t i = blockIdx.x * static_cast<size_t>(kBlockThreads) + threadIdx.x; i < n_units;
-       i += static_cast<size_t>(gridDim.x) * kBlockThreads)
-  {
-    const uint2 v = local[i];
-    for (int g = 0; g < t.world; ++g) t.records[g][base + i] = v;
-  }
-  __threadfence_system();
-  __shared__ bool last;
-  __syncthreads();
-  if (threadIdx.x == 0)
-    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!last)
-    return;
-  if (threadIdx.x == 0)
-    *ticket = 0;  // ready for the next launch (stream order)
-  if (threadIdx.x < t.world)
+  const uint32_t step = *step_ctr + 1u;
+  __syncwarp();
+  if (threadIdx.x < static_cast<unsigned>(t.world))
   {
     __threadfence_system();
     st_release_sys(t.flags[threadIdx.x] + t.rank, step);
     const uint32_t* mine = t.flags[t.rank] + threadIdx.x;
-    // steps increase monotonically; the difference is taken modulo 2^32
-    // (bounded: a peer that died must not hang this GPU — a few seconds at ~1 us per poll, then the error word is set)
+    // steps increase monotonically; the difference is taken modulo 2^32.  Bounded: a peer that died must not hang
+    // this GPU (~2^22 polls of ~1 us, then the error word is set and the step completes with stale data)
     long polls = 0;
     while (static_cast<int32_t>(ld_acquire_sys(mine) - step) < 0)
       if (++polls > (1L << 22))
       {
-        atomicExch(ticket + 1, 1u);
+        atomicExch(err, 1u);
         break;
       }
   }
+  __syncwarp();
+  if (threadIdx.x == 0)
+    *step_ctr = step;
 }
 
 }  // namespace mcl3dl

@@ -76,7 +76,7 @@ EXPORTED_SYMBOLS = ["mcl3dl_measure_update", "mcl3dl_collect_stats", "mcl3dl_rea
                     "mcl3dl_measure", "mcl3dl_measure_device", "mcl3dl_beam_status",
                     "mcl3dl_beam_params_from_reference", "mcl3dl_get_map_info", "mcl3dl_last_timing",
                     "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_collect_timing",
-                    "mcl3dl_exchange_create", "mcl3dl_exchange_open", "mcl3dl_exchange_records", "mcl3dl_exchange_failed",
+                    "mcl3dl_exchange_create", "mcl3dl_exchange_open", "mcl3dl_measure_exchange_device", "mcl3dl_exchange_current",
                     "mcl3dl_particles_set", "mcl3dl_particles_get", "mcl3dl_particles_predict",
                     "mcl3dl_particles_measure_update", "mcl3dl_particles_resample"]
 
@@ -128,10 +128,10 @@ def load_library(path=None):
     L.mcl3dl_particles_resample.argtypes = [vp, vp, vp, C.c_float, C.c_uint64]
     L.mcl3dl_exchange_create.argtypes = [vp, sz, C.c_int, C.c_int, vp]
     L.mcl3dl_exchange_open.argtypes = [vp, vp]
-    L.mcl3dl_exchange_records.argtypes = [vp, vp, sz, vp, C.POINTER(vp)]
-    L.mcl3dl_exchange_failed.argtypes = [vp, C.POINTER(C.c_int)]
+    L.mcl3dl_measure_exchange_device.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, C.POINTER(vp)]
+    L.mcl3dl_exchange_current.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_int)]
     L.mcl3dl_near_field_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
-    assert L.mcl3dl_abi_version() == 2
+    assert L.mcl3dl_abi_version() == 3
     _LIBS[path] = L
     return L
 
@@ -335,16 +335,19 @@ class Engine:
         buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
         self._check(self.L.mcl3dl_exchange_open(self.h, buf))
 
-    def exchange_records(self, d_local, n_local, stream=0):
-        """Enqueue the exchange; returns the device address that holds all ranks' records once the stream gets there."""
+    def measure_exchange_device(self, d_poses, n_local, d_lik, n_lik, d_beam, n_beam, d_origins, n_origins, stream=0):
+        """This rank's shard + the record exchange folded into the kernels (raw device addresses, async on `stream`).
+        Returns the device address that holds ALL ranks' records once the stream gets there (eager calls)."""
         d_all = C.c_void_p()
-        self._check(self.L.mcl3dl_exchange_records(self.h, d_local, n_local, stream, C.byref(d_all)))
+        self._check(self.L.mcl3dl_measure_exchange_device(self.h, d_poses, n_local, d_lik, n_lik, d_beam, n_beam,
+                                                          d_origins, n_origins, stream, C.byref(d_all)))
         return d_all.value
 
-    def exchange_failed(self):
-        f = C.c_int(0)
-        self._check(self.L.mcl3dl_exchange_failed(self.h, C.byref(f)))
-        return bool(f.value)
+    def exchange_current(self, stream=0):
+        """(device address of the last completed gathered array, a peer timed out?) — synchronises `stream`."""
+        d_all, f = C.c_void_p(), C.c_int(0)
+        self._check(self.L.mcl3dl_exchange_current(self.h, stream, C.byref(d_all), C.byref(f)))
+        return d_all.value, bool(f.value)
 
     def collect_timing(self, enable=True):
         """Record the per-call CUDA timing events read by last_timing() (off by default: ~28 us per update)."""

@@ -27,40 +27,32 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 PKG = os.path.join(ROOT, "mcl_3dl_b200")
-NB_LIB = os.path.join(PKG, "libmcl3dl_b200.so")          # the default build (near-field screens compiled in)
-BASE_LIB = os.path.join(PKG, "libmcl3dl_b200_nb0.so")    # build.build(defines=["MCL3DL_NEAR_BITS=0"], out=...)
-KDSKIP_LIB = os.path.join(PKG, "libmcl3dl_b200_kdskip.so")  # defines=["MCL3DL_KD_SKIP=1"]: KD caster skip-ahead field
-LIKCHUNK_LIB = os.path.join(PKG, "libmcl3dl_b200_likchunks.so")  # defines=["MCL3DL_LIK_CHUNKS=1"]: lik_kernel_wc
-OLD_HOST = {"MCL3DL_TIMING": "1", "MCL3DL_ZEROCOPY_OUT": "0"}  # the host path as it was up to r01x
-VARIANT_BUILDS = {BASE_LIB: ["MCL3DL_NEAR_BITS=0"], KDSKIP_LIB: ["MCL3DL_KD_SKIP=1"],
-                  LIKCHUNK_LIB: ["MCL3DL_LIK_CHUNKS=1"]}  # --build-variants (needs nvcc)
+LIB = os.path.join(PKG, "libmcl3dl_b200.so")          # the default build
+MINB5_LIB = os.path.join(PKG, "libmcl3dl_b200_nf5.so")  # lik_kernel_nf capped for 5 / 6 / 8 resident CTAs per SM
+MINB6_LIB = os.path.join(PKG, "libmcl3dl_b200_nf6.so")
+MINB8_LIB = os.path.join(PKG, "libmcl3dl_b200_nf8.so")
+HOST = {"MCL3DL_TIMING": "1", "MCL3DL_ZEROCOPY_OUT": "8192"}  # kernel times wanted: the timing events stay on
+VARIANT_BUILDS = {MINB5_LIB: ["MCL3DL_NF_MINB=5"], MINB6_LIB: ["MCL3DL_NF_MINB=6"], MINB8_LIB: ["MCL3DL_NF_MINB=8"]}
 
-# name -> (library, environment); every variant states the host-path switches explicitly, so the table does not
-# depend on the engine's defaults.  "base" (the r01x engine) must come first: everything is compared with its records.
+# name -> (library, environment).  "base" (the CSR-window kernels of round 1, MCL3DL_NNF=0) must come first: everything
+# is compared with its records byte for byte.
 VARIANTS = [
-    ("base", BASE_LIB, dict(OLD_HOST)),
-    ("nb", NB_LIB, dict(OLD_HOST)),                                   # near-field screens, k = 2 (lik) / 1 (KD)
-    ("nb_fast_host", NB_LIB, {"MCL3DL_TIMING": "0", "MCL3DL_ZEROCOPY_OUT": "8192"}),   # = today's defaults
-    ("timing_off", BASE_LIB, {"MCL3DL_TIMING": "0", "MCL3DL_ZEROCOPY_OUT": "0"}),
-    ("zerocopy", BASE_LIB, {"MCL3DL_TIMING": "1", "MCL3DL_ZEROCOPY_OUT": "1000000"}),
-    ("nb_k1", NB_LIB, dict(OLD_HOST, MCL3DL_NEAR_K="1")),
-    ("nb_k3_kd2", NB_LIB, dict(OLD_HOST, MCL3DL_NEAR_K="3", MCL3DL_NEAR_KD_K="2", MCL3DL_NEAR_MAX_MB="512")),
-    ("nb_group", NB_LIB, dict(OLD_HOST, MCL3DL_MAPPING="group")),     # the plain kernels with the screens
-    ("base_group", BASE_LIB, dict(OLD_HOST, MCL3DL_MAPPING="group")),
-    # prepared in round 1 without GPU time left (host-verified only): KD-tree raycaster skip-ahead, 4 / 8 steps
-    ("one_sync", NB_LIB, dict(OLD_HOST, MCL3DL_UPDATE_ONE_SYNC="1")),  # fused weight update with one synchronise
-    ("kdskip4", KDSKIP_LIB, dict(OLD_HOST)),
-    ("kdskip8", KDSKIP_LIB, dict(OLD_HOST, MCL3DL_KD_SKIP_STEPS="8")),
-    # warp-chunk likelihood kernel (phase 2 dealt in 4-point chunks); host counters say chunks ~ runs on c2 (little to
-    # gain there), 275 chunks vs 192 longer runs per round with isotropic weights
-    ("lik_chunk", LIKCHUNK_LIB, dict(OLD_HOST, MCL3DL_LIK="chunk")),
+    ("base", LIB, dict(HOST, MCL3DL_NNF="0")),
+    ("nnf", LIB, dict(HOST)),                                      # NN field (today's default)
+    ("nnf_minb5", MINB5_LIB, dict(HOST)),
+    ("nnf_minb6", MINB6_LIB, dict(HOST)),
+    ("nnf_minb8", MINB8_LIB, dict(HOST)),
+    ("nnf_nokdbits", LIB, dict(HOST, MCL3DL_NEAR_KD_K="0")),       # KD caster: field only, no near-field screen
+    ("nnf_fast_host", LIB, {"MCL3DL_TIMING": "0", "MCL3DL_ZEROCOPY_OUT": "8192"}),
+    ("base_group", LIB, dict(HOST, MCL3DL_MAPPING="group")),
+    ("two_sync", LIB, dict(HOST, MCL3DL_UPDATE_ONE_SYNC="0")),
 ]
 # workload -> (bench workload, raycaster, spread override)
 WORKLOADS = [("c2", "c2", "dda", False), ("c3kd", "c3", "kd", False), ("c5", "c5", "dda", False),
              ("c1kd", "c1", "kd", False), ("c2s", "c2", "dda", True), ("c3", "c3", "dda", False), ("c2iso", "c2", "dda", False)]
 ISO_WORKLOADS = {"c2iso"}  # dist_weight (1,1,1) instead of the node's (1,1,5): ~3x more map points per eval
 ENV_KEYS = ["MCL3DL_TIMING", "MCL3DL_ZEROCOPY_OUT", "MCL3DL_NEAR_K", "MCL3DL_NEAR_KD_K", "MCL3DL_NEAR_MAX_MB",
-            "MCL3DL_MAPPING", "MCL3DL_KD_SKIP_STEPS", "MCL3DL_UPDATE_ONE_SYNC", "MCL3DL_LIK"]
+            "MCL3DL_MAPPING", "MCL3DL_UPDATE_ONE_SYNC", "MCL3DL_NNF"]
 
 
 def jobs_all():
@@ -147,7 +139,7 @@ def child(job_names, calls):
                     "e2e_units_per_s": units / float(np.median(wall)),
                     "lik_kernel_us": 1e3 * float(np.median(k_lik)) if k_lik and n_lik else None,
                     "beam_kernel_us": 1e3 * float(np.median(k_beam)) if k_beam and n_beam else None,
-                    "near_field": eng.near_field_info(), "build_ms": eng.map_info().build_ms,
+                    "near_field": eng.near_field_info(), "build_ms": eng.map_info().build_ms, "map_device_mb": eng.map_info().device_bytes / 1e6,
                     "match_cnt_sum": int(out["match_cnt"].sum()), "n_hit_sum": int(out["n_hit"].sum()), "calls": calls})
         eng.close()
         print(json.dumps(rec), flush=True)

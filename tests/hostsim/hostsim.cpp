@@ -3,16 +3,12 @@
 // Compiles the product's per-thread device functions (mcl_3dl_b200/csrc/device_math.cuh, device_funcs.cuh) for the
 // HOST through cuda_shim.h and drives them over host-built copies of the device grids, one (particle, point) at a
 // time.  tests/test_hostsim.py compares the result with the oracle: a way to check edits to cast_ray / cast_ray_kd /
-// nn_dist2 / nn_search_arg / the transform / the near-field screens without a GPU.  Of the warp-cooperative kernel
-// code, the rounds of the prepared lik_kernel_wc are emulated lane by lane (hostsim_lik_wc: window-table fetch,
-// descriptor dealing, chunk processing); TMA staging, shuffles and the CTA reductions are only covered by the GPU suite.
+// nn_dist2 / nn_search_arg / the NN field (nnf_select, nnf_dist2, nnf_search_arg) / the transform / the near-field
+// screens without a GPU.  TMA staging, shuffles and the CTA reductions are only covered by the GPU suite.
 // The grid construction below restates what engine.cu's build kernels do (same cell functions, same stable order).
 #include "cuda_shim.h"
 #ifndef MCL3DL_NEAR_BITS
 #define MCL3DL_NEAR_BITS 1  // the host build always carries the near-field screens; near_k = 0 switches them off at run time
-#endif
-#ifndef MCL3DL_KD_SKIP
-#define MCL3DL_KD_SKIP 1     // ... and the KD-tree raycaster's skip-ahead field (kd_skip_steps = 0 switches it off)
 #endif
 
 #include <algorithm>
@@ -30,8 +26,10 @@ struct HostMap
 {
   std::vector<uint32_t> nn_cell_start, dda_cell_start, occ;
   std::vector<float4> nn_pts, dda_pts, raw_pts;
-  std::vector<uint32_t> near_lik, near_kd, far_kd;
-  std::vector<uint2> nn_row3;
+  std::vector<uint32_t> near_lik, near_kd;
+  std::vector<uint2> nnf_dir;
+  std::vector<float4> nnf_cand;
+  uint64_t nnf_voxels = 0, nnf_overflow = 0;
   NnGridDev nn{};
   DdaGridDev dda{};
   KdRayDev kd{};
@@ -54,7 +52,7 @@ void build_near(std::vector<uint32_t>& bits, NearBitsDev& out, const mcl3dl_poin
 }
 
 void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_params* lp, const mcl3dl_beam_params* bp,
-           float cell_factor, int near_k, int near_kd_k, int kd_skip_steps)
+           float cell_factor, int near_k, int near_kd_k, int use_field)
 {
   const float wx = lp ? lp->dist_weight[0] : 1.0f, wy = lp ? lp->dist_weight[1] : 1.0f, wz = lp ? lp->dist_weight[2] : 1.0f;
   float raw_min[3], raw_max[3], sc_min[3], sc_max[3];
@@ -130,23 +128,88 @@ void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_param
     }
     g.cell_start = m.nn_cell_start.data();
     g.pts = m.nn_pts.data();
-    // window table (engine.cu: nn_row3_kernel), read by the lane-by-lane emulation of the warp-chunk kernel below
-    g.nyp = (g.ny + 4) & ~1;
-    m.nn_row3.assign(static_cast<size_t>(g.nz) * g.nx * g.nyp + 2, make_uint2(0u, 0u));
-    for (int z = 0; z < g.nz; ++z)
-      for (int x = 0; x < g.nx; ++x)
-        for (int y = 0; y < g.ny; ++y)
-        {
-          const size_t cell = (static_cast<size_t>(z) * g.ny + y) * g.nx + x;
-          const uint32_t s0 = m.nn_cell_start[cell];
-          const uint32_t c1 = m.nn_cell_start[cell + std::min(1, g.nx - x)] - s0;
-          const uint32_t c2 = m.nn_cell_start[cell + std::min(2, g.nx - x)] - s0;
-          const uint32_t c3 = m.nn_cell_start[cell + std::min(3, g.nx - x)] - s0;
-          m.nn_row3[(static_cast<size_t>(z) * g.nx + x) * g.nyp + y] =
-              make_uint2(s0, std::min(c1, 0x3ffu) | (std::min(c2, 0x7ffu) << 10) | (std::min(c3, 0x7ffu) << 21));
-        }
-    g.row3 = m.nn_row3.data();
     build_near(m.near_lik, g.near, pts, n, wx, wy, wz, m.lik.rpad, near_k, sc_min, sc_max);
+    g.field = NnFieldDev{};
+    if (use_field)
+    {
+      // engine.cu: build_nn_field (same layout, same marking, same per-voxel selection function, same packing)
+      float radius = m.lik.rpad;
+      if (bp && !bp->use_raycast_using_dda)
+      {
+        const float gx = static_cast<float>(bp->map_grid_size[0]), gy = static_cast<float>(bp->map_grid_size[1]),
+                    gz = static_cast<float>(bp->map_grid_size[2]);
+        const float r1 = static_cast<float>(std::sqrt(2.0) * std::max(gx, std::max(gy, gz)) / 2.0);
+        radius = std::max(radius, r1 * 1.0001f + 1e-6f);
+      }
+      NearBitsDev lay{};
+      std::vector<uint32_t> bits;
+      if (near_layout(lay, radius, 2, sc_min, sc_max, size_t(1) << 40))
+      {
+        bits.assign(static_cast<size_t>(lay.pitch) * lay.ny * lay.nz, 0u);
+        for (size_t i = 0; i < n; ++i)
+          near_mark_point(lay, bits.data(), 2, __fmul_rn(pts[i].x, wx), __fmul_rn(pts[i].y, wy), __fmul_rn(pts[i].z, wz));
+        NnFieldDev f{};
+        f.nx = lay.nx;
+        f.ny = lay.ny;
+        f.nz = lay.nz;
+        f.cnx = (lay.nx + 1) / 2;
+        f.cny = (lay.ny + 1) / 2;
+        f.cnz = (lay.nz + 1) / 2;
+        f.ox = lay.ox;
+        f.oy = lay.oy;
+        f.oz = lay.oz;
+        f.inv_e = lay.inv_cell;
+        f.e = 1.0f / lay.inv_cell;
+        f.radius = radius;
+        float ext = 0.0f;
+        for (int k = 0; k < 3; ++k) ext = std::max(ext, std::max(std::fabs(sc_min[k]), std::fabs(sc_max[k])) + 4.0f * f.e);
+        f.pad = 0.01f * f.e + 16.0f * std::numeric_limits<float>::epsilon() * ext;
+        const size_t n_cells = static_cast<size_t>(f.cnx) * f.cny * f.cnz;
+        m.nnf_dir.assign(n_cells, make_uint2(0u, 0u));
+        m.nnf_cand.clear();
+        for (size_t cell = 0; cell < n_cells; ++cell)
+        {
+          const int cx = static_cast<int>(cell % f.cnx), cy = static_cast<int>((cell / f.cnx) % f.cny),
+                    cz = static_cast<int>(cell / (static_cast<size_t>(f.cnx) * f.cny));
+          uint32_t nib = 0;
+          bool ovf = false;
+          std::vector<float4> mine;
+          for (int sub = 0; sub < 8; ++sub)
+          {
+            const int vx = 2 * cx + (sub & 1), vy = 2 * cy + ((sub >> 1) & 1), vz = 2 * cz + (sub >> 2);
+            if (vx >= f.nx || vy >= f.ny || vz >= f.nz)
+              continue;
+            if (!((bits[(static_cast<size_t>(vz) * f.ny + vy) * lay.pitch + (vx >> 5)] >> (vx & 31)) & 1u))
+              continue;
+            uint32_t pos[kNnfMaxCand];
+            const int cnt = nnf_select(g, f, vx, vy, vz, pos);
+            if (cnt > kNnfMaxCand)
+            {
+              ovf = true;
+              continue;
+            }
+            nib |= static_cast<uint32_t>(cnt) << (4 * sub);
+            for (int i = 0; i < cnt; ++i) mine.push_back(g.pts[pos[i]]);
+            m.nnf_voxels += cnt > 0;
+          }
+          if (ovf)
+          {
+            m.nnf_dir[cell] = make_uint2(0xffffffffu, 0xffffffffu);
+            ++m.nnf_overflow;
+          }
+          else
+          {
+            m.nnf_dir[cell] = make_uint2(static_cast<uint32_t>(m.nnf_cand.size()), nib);
+            m.nnf_cand.insert(m.nnf_cand.end(), mine.begin(), mine.end());
+          }
+        }
+        if (m.nnf_cand.empty())
+          m.nnf_cand.push_back(make_float4(0, 0, 0, 0));
+        f.dir = m.nnf_dir.data();
+        f.cand = m.nnf_cand.data();
+        g.field = f;
+      }
+    }
     m.nn = g;
   }
   if (bp)
@@ -216,13 +279,6 @@ void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_param
       k.r2_pad = k.r2 * 1.0001f + 1e-6f;
       k.sin_den = gmin * 2.0;
       build_near(m.near_kd, k.near, pts, n, wx, wy, wz, k.r1_pad, near_kd_k, sc_min, sc_max);
-      {
-        // engine.cu: the skip-ahead field of build_map_on_device
-        const float wmin = std::min(wx, std::min(wy, wz));
-        const float far_r = k.r1_pad + static_cast<float>(kd_skip_steps) * k.grid_min * wmin / 0.98f;
-        build_near(m.far_kd, k.far, pts, n, wx, wy, wz, far_r, kd_skip_steps > 0 ? 1 : 0, sc_min, sc_max);
-        k.far_margin = 0.98f * (far_r - k.r1_pad);
-      }
       m.kd = k;
     }
     m.dda = g;
@@ -236,7 +292,8 @@ extern "C" int hostsim_measure_nf(const mcl3dl_point* map, size_t n, const mcl3d
                                   size_t n_lik, const mcl3dl_point* beam_pts, size_t n_beam, const float* origins_xyz,
                                   size_t n_origins, mcl3dl_result* out, uint8_t* status, int near_k, int near_kd_k,
                                   uint64_t* work /* [5]: nn rows, nn pts, steps, occupied, tested; may be NULL */,
-                                  int kd_skip_steps)
+                                  int use_field /* 1: stage the NN field; the likelihood evals and the KD caster's
+                                                   marching search go through it (nnf_dist2 / nnf_search_arg) */)
 {
   if ((n_lik && !lp) || (n_beam && !bp) || (bp && !bp->use_raycast_using_dda && !lp))
     return -1;
@@ -244,7 +301,7 @@ extern "C" int hostsim_measure_nf(const mcl3dl_point* map, size_t n, const mcl3d
     if (beam_pts[j].label >= n_origins)
       return -1;
   HostMap m;
-  build(m, map, n, lp, bp, cell_factor, near_k, near_kd_k, kd_skip_steps);
+  build(m, map, n, lp, bp, cell_factor, near_k, near_kd_k, use_field);
   uint64_t wk[5] = {0, 0, 0, 0, 0};
   for (size_t p = 0; p < P; ++p)
   {
@@ -307,7 +364,8 @@ extern "C" int hostsim_measure_nf(const mcl3dl_point* map, size_t n, const mcl3d
         v.y = lik_pts[j].y;
         v.z = lik_pts[j].z;
         const F3 t = transform_point(rn, pos, v);
-        const float d2 = nn_dist2(m.nn, m.lik, fmul(t.x, m.nn.wx), fmul(t.y, m.nn.wy), fmul(t.z, m.nn.wz), rows, npts);
+        const float sx = fmul(t.x, m.nn.wx), sy = fmul(t.y, m.nn.wy), sz = fmul(t.z, m.nn.wz);
+        const float d2 = m.nn.field.dir ? nnf_dist2(m.nn, m.lik, sx, sy, sz, rows, npts) : nn_dist2(m.nn, m.lik, sx, sy, sz, rows, npts);
         if (d2 < m.lik.r2)
         {
           const float dist = fsub(m.lik.match_dist_min, fmaxf(__fsqrt_rn(d2), m.lik.match_dist_flat));
@@ -326,7 +384,12 @@ extern "C" int hostsim_measure_nf(const mcl3dl_point* map, size_t n, const mcl3d
     if (out) out[p] = r;
   }
   if (work)
+  {
     for (int i = 0; i < 5; ++i) work[i] = wk[i];
+    work[5] = m.nnf_cand.size();
+    work[6] = m.nnf_voxels;
+    work[7] = m.nnf_overflow;
+  }
   return 0;
 }
 
@@ -336,7 +399,7 @@ extern "C" int hostsim_measure(const mcl3dl_point* map, size_t n, const mcl3dl_l
                                size_t n_origins, mcl3dl_result* out, uint8_t* status)
 {
   return hostsim_measure_nf(map, n, lp, bp, cell_factor, poses, P, lik_pts, n_lik, beam_pts, n_beam, origins_xyz, n_origins, out,
-                            status, 2, 1, nullptr, 4);
+                            status, 2, 1, nullptr, 1);
 }
 
 // The near field on its own: build it for radius r / dilation k over `map` (rescaled by w) and evaluate near_maybe for
@@ -381,113 +444,3 @@ extern "C" int hostsim_near_query(const mcl3dl_point* map, size_t n, const float
 }
 
 
-// Lane-by-lane emulation of lik_kernel_wc (kernels.cuh, -DMCL3DL_LIK_CHUNKS=1) with TPP = 32: a warp owns a particle and
-// works on 32 evals per round; the phases between two __syncwarp()s are run for lanes 0..31 in turn, the shuffle prefix
-// sum is a loop.  The per-lane functions are the very ones the kernel calls (device_funcs.cuh: wc_window,
-// wc_write_descs, wc_process).  Scores are summed in scan order, so they must equal the oracle's bit for bit.
-// work[0..4] = window rows, map points scanned, descriptors processed, rounds, rounds that fell back to whole runs.
-extern "C" int hostsim_lik_wc(const mcl3dl_point* map, size_t n, const mcl3dl_lik_params* lp, float cell_factor,
-                              const mcl3dl_pose* poses, size_t P, const mcl3dl_point* lik_pts, size_t n_lik,
-                              mcl3dl_result* out, int near_k, uint64_t* work)
-{
-  if (!lp || !out)
-    return -1;
-  HostMap m;
-  build(m, map, n, lp, nullptr, cell_factor, near_k, 0, 0);
-  const NnGridDev& g = m.nn;
-  const LikDev& likp = m.lik;
-  uint64_t wk[5] = {0, 0, 0, 0, 0};
-  const uint32_t r2_bits = __float_as_uint(likp.r2);
-  for (size_t p = 0; p < P; ++p)
-  {
-    F3 pos;
-    pos.x = poses[p].px;
-    pos.y = poses[p].py;
-    pos.z = poses[p].pz;
-    Q4 q;
-    q.x = poses[p].qx;
-    q.y = poses[p].qy;
-    q.z = poses[p].qz;
-    q.w = poses[p].qw;
-    const Q4 rn = qnormalized(q);
-    float score = 0.0f;
-    uint32_t cnt = 0;
-    LikChunkSmem sm;
-    for (size_t jbase = 0; jbase < n_lik; jbase += 32)
-    {
-      int nr[32], nc[32];
-      uint32_t st_rows = 0, st_pts = 0;
-      for (uint16_t& d : sm.desc) d = 0xffffu;  // (k = 15 never occurs: at most 9 runs per eval)
-      // phase 1
-      for (int lane = 0; lane < 32; ++lane)
-      {
-        nr[lane] = nc[lane] = 0;
-        sm.best[lane] = r2_bits;
-        const size_t j = jbase + lane;
-        if (j >= n_lik)
-          continue;
-        F3 v;
-        v.x = lik_pts[j].x;
-        v.y = lik_pts[j].y;
-        v.z = lik_pts[j].z;
-        const F3 t = transform_point(rn, pos, v);
-        const float qx = fmul(t.x, g.wx), qy = fmul(t.y, g.wy), qz = fmul(t.z, g.wz);
-        sm.qx[lane] = qx;
-        sm.qy[lane] = qy;
-        sm.qz[lane] = qz;
-        nr[lane] = wc_window(g, likp, qx, qy, qz, lane, sm, st_rows, st_pts, nc[lane]);
-        if (nr[lane] > kWcMaxRows)
-          return -2;
-      }
-      // the prefix sum of the kernel (chunk counts clamped to 1023 in the low half, run counts in the high half)
-      uint32_t mine[32], incl[32], acc = 0;
-      for (int lane = 0; lane < 32; ++lane)
-      {
-        mine[lane] = static_cast<uint32_t>(std::min(nc[lane], kWcOverflow)) | (static_cast<uint32_t>(nr[lane]) << 16);
-        acc += mine[lane];
-        incl[lane] = acc;
-      }
-      const uint32_t total = incl[31];
-      const bool whole = (total & 0xffffu) > static_cast<uint32_t>(kWcMaxDesc);
-      const int n_desc = static_cast<int>(whole ? (total >> 16) : (total & 0xffffu));
-      if (n_desc > kWcMaxDesc)
-        return -3;
-      for (int lane = 0; lane < 32; ++lane)
-      {
-        const uint32_t excl = incl[lane] - mine[lane];
-        wc_write_descs(sm, lane, nr[lane], static_cast<int>(whole ? (excl >> 16) : (excl & 0xffffu)), whole);
-      }
-      for (int i = 0; i < kWcMaxDesc; ++i)
-        if ((i < n_desc) == (sm.desc[i] == 0xffffu))
-          return -4;  // a hole in, or a write beyond, the descriptor list
-      // phase 2 (any order: the merge is a min)
-      for (int it = n_desc - 1; it >= 0; --it) wc_process(sm, sm.desc[it], whole, g, likp);
-      // owner lanes, in scan order
-      for (int lane = 0; lane < 32 && jbase + lane < n_lik; ++lane)
-      {
-        const float d2 = __uint_as_float(sm.best[lane]);
-        if (d2 < likp.r2)
-        {
-          const float dist = fsub(likp.match_dist_min, fmaxf(__fsqrt_rn(d2), likp.match_dist_flat));
-          if (!(dist < 0.0f))
-          {
-            score = fadd(score, fmul(dist, likp.match_weight));
-            cnt++;
-          }
-        }
-      }
-      wk[0] += st_rows;
-      wk[1] += st_pts;
-      wk[2] += static_cast<uint64_t>(n_desc);
-      wk[3] += 1;
-      wk[4] += whole ? 1 : 0;
-    }
-    std::memset(&out[p], 0, sizeof(out[p]));
-    out[p].score_like = n_lik ? score : 1.0f;
-    out[p].match_cnt = cnt;
-    out[p].score_beam = 1.0f;
-  }
-  if (work)
-    for (int i = 0; i < 5; ++i) work[i] = wk[i];
-  return 0;
-}

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert sorted(engine.EXPORTED_SYMBOLS) == names
-    assert L.mcl3dl_abi_version() == 2
+    assert L.mcl3dl_abi_version() == 3
     assert L.mcl3dl_strerror(-2).decode().startswith("measure()")
 
 

@@ -316,7 +316,12 @@ def test_c4_shape_vs_oracle(eng_mod, eng_mod_engine_tuned, cc):
     idx = np.arange(0, 16384, 64)
     want = cpu.measure(s["particles"][idx], s["lik"], s["beam"], s["origins"], n_threads=8)
     check_records(full[idx], want, 1024)
-    assert np.array_equal(eng.measure(s["particles"][idx], s["lik"], s["beam"], s["origins"]), full[idx])
+    # the sample run on its own: 256 particles get more threads per particle than 16 384 do, so the likelihood sums are
+    # reduced in another order (scores to rounding, everything integer exactly)
+    alone = eng.measure(s["particles"][idx], s["lik"], s["beam"], s["origins"])
+    check_records(alone, want, 1024)
+    for f in ("match_cnt", "n_short", "n_hit", "n_long", "score_beam"):
+        assert np.array_equal(alone[f], full[idx][f]), f
     assert want["match_cnt"].sum() > 0 and want["n_hit"].sum() > 0
 
 

@@ -36,9 +36,11 @@ def hostsim():
     L.hostsim_measure_nf.argtypes = [vp, sz, vp, vp, C.c_float, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp, C.c_int, C.c_int, vp,
                                      C.c_int]
 
-    def run(map_pts, lik, beam, poses, lik_pts, beam_pts, origins, near=(2, 1), work=False, kd_skip=4):
+    def run(map_pts, lik, beam, poses, lik_pts, beam_pts, origins, near=(2, 1), work=False, field=1):
         """near = dilation of the (likelihood, KD-caster) near-field screens; 0 = the unscreened searches.
-        kd_skip = marching steps covered by the KD caster's skip-ahead field (MCL3DL_KD_SKIP builds); 0 = off."""
+        field = 1: stage the NN field (per-voxel candidate lists) and search through it, as the engine does by default;
+        0: the CSR window searches.  work: [nn index entries, nn pts, steps, occupied, tested, field candidates stored,
+        field voxels with candidates, field overflow cells]."""
         map_pts = np.ascontiguousarray(map_pts, dtype=synth.POINT)
         poses = np.ascontiguousarray(poses, dtype=synth.POSE)
         lik_pts = np.ascontiguousarray(lik_pts if lik_pts is not None else np.zeros(0, synth.POINT), dtype=synth.POINT)
@@ -46,12 +48,12 @@ def hostsim():
         origins = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
         out = np.zeros(len(poses), dtype=synth.RESULT)
         st = np.zeros((len(poses), max(len(beam_pts), 1)), dtype=np.uint8)
-        wk = np.zeros(5, dtype=np.uint64)
+        wk = np.zeros(8, dtype=np.uint64)
         p = lambda a: a.ctypes.data_as(vp) if a.size else None  # noqa: E731
         rc = L.hostsim_measure_nf(p(map_pts), len(map_pts), C.byref(lik) if lik is not None else None,
                                   C.byref(beam) if beam is not None else None, 1.0, p(poses), len(poses), p(lik_pts),
                                   len(lik_pts), p(beam_pts), len(beam_pts), p(origins), len(origins), p(out), p(st),
-                                  near[0], near[1], p(wk), kd_skip)
+                                  near[0], near[1], p(wk), field)
         assert rc == 0
         if work:
             return out, st[:, :len(beam_pts)], wk
@@ -101,8 +103,9 @@ def test_near_field_screens_change_no_result(hostsim, near, seed, w, spread, use
     s = synth.scene(30_000, 24, 40, 16, spread=spread, seed=seed)
     lik = engine.LikParams(dist_weight=w, match_dist_min=0.2 if seed % 2 else 0.35)
     beam = engine.beam_params_from_reference(num_points_default=16, use_raycast_using_dda=use_dda)
-    ref, st_ref, wk_ref = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(0, 0), work=True)
-    got, st, wk = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=near, work=True)
+    ref, st_ref, wk_ref = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(0, 0), work=True,
+                                  field=0)
+    got, st, wk = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=near, work=True, field=0)
     assert got.tobytes() == ref.tobytes()
     assert np.array_equal(st, st_ref)
     assert wk[0] < wk_ref[0] and wk[1] <= wk_ref[1]          # likelihood: fewer windows opened
@@ -110,21 +113,43 @@ def test_near_field_screens_change_no_result(hostsim, near, seed, w, spread, use
         assert wk[4] < wk_ref[4] and wk[3] == wk_ref[3]      # KD caster: fewer points tested, same collisions
 
 
-@pytest.mark.parametrize("skip", [1, 4, 16])
-@pytest.mark.parametrize("seed,w,spread", [(21, (1, 1, 1), False), (22, (1, 1, 5), True), (23, (2, 1, 3), False)])
-def test_kd_skip_ahead_changes_no_result(hostsim, skip, seed, w, spread):
-    """The KD-tree raycaster's skip-ahead field (MCL3DL_KD_SKIP builds) jumps over marching steps that a coarser near
-    field proves clear: same records, same per-ray status, same step count, fewer points tested."""
-    s = synth.scene(30_000, 24, 8, 40, spread=spread, seed=seed)
-    lik = engine.LikParams(dist_weight=w)
-    beam = engine.beam_params_from_reference(num_points_default=40, use_raycast_using_dda=False)
-    ref, st_ref, wk_ref = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(0, 0),
-                                  work=True, kd_skip=0)
-    got, st, wk = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(2, 1), work=True,
-                          kd_skip=skip)
+@pytest.mark.parametrize("seed,w,spread,use_dda,r", [(21, (1, 1, 1), False, False, 0.2), (22, (1, 1, 5), True, False, 0.2),
+                                                      (23, (2, 1, 3), False, True, 0.35), (24, (1, 1, 5), False, True, 0.2),
+                                                      (25, (0.5, 2, 1), True, False, 0.1)])
+def test_nn_field_changes_no_result(hostsim, seed, w, spread, use_dda, r):
+    """The NN field (per-voxel candidate lists, device_funcs.cuh: nnf_select / nnf_dist2 / nnf_search_arg) against the
+    CSR window searches: records — likelihood scores bit for bit — and per-ray status are identical, and far fewer map
+    points are distance-tested."""
+    s = synth.scene(30_000, 24, 64, 24, spread=spread, seed=seed)
+    lik = engine.LikParams(dist_weight=w, match_dist_min=r)
+    beam = engine.beam_params_from_reference(num_points_default=24, use_raycast_using_dda=use_dda)
+    ref, st_ref, wk_ref = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(0, 0), work=True,
+                                  field=0)
+    got, st, wk = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(2, 1), work=True, field=1)
     assert got.tobytes() == ref.tobytes()
     assert np.array_equal(st, st_ref)
-    assert wk[2] == wk_ref[2] and wk[3] == wk_ref[3] and wk[4] < wk_ref[4]
+    assert wk[5] > 0 and wk[6] > 0 and wk[7] * 1000 < wk[6]   # candidates stored, (almost) no overflow cell on a voxel-filtered map
+    assert wk[1] < wk_ref[1]                                  # fewer map points tested by the likelihood evals
+    assert wk[5] / wk[6] < 8.0                                # a handful of candidates per voxel
+    if not use_dda:
+        assert wk[4] < wk_ref[4] and wk[3] == wk_ref[3]      # KD caster: fewer points tested, same collisions
+
+
+def test_nn_field_overflow_cells_fall_back(hostsim, port):
+    """A raw cloud with thousands of points per voxel: more than 14 candidates survive, the directory cells are marked
+    and the queries there run the CSR window search — same records as the oracle."""
+    rng = np.random.default_rng(91)
+    pts = rng.uniform(0.0, 1.0, (20_000, 3)).astype(np.float32)
+    mp = synth.make_points(pts)
+    P, n_lik = 5, 40
+    poses = synth.make_poses(rng.uniform(0.3, 0.7, (P, 3)), synth.quat_from_rpy(rng.normal(0, 0.3, (P, 3))))
+    scan = synth.make_points(rng.uniform(-0.7, 0.7, (n_lik, 3)))
+    lik = engine.LikParams(dist_weight=(1, 1, 1))
+    cpu = port.create(mp, cc.lik_params(dist_weight=(1, 1, 1)), None, 20.0, 0.4)
+    want = cpu.measure(poses, scan, None, np.zeros((1, 3), np.float32))
+    got, _, wk = hostsim(mp, lik, None, poses, scan, None, np.zeros((1, 3), np.float32), work=True, field=1)
+    assert np.array_equal(got["match_cnt"], want["match_cnt"]) and np.array_equal(got["score_like"], want["score_like"])
+    assert wk[7] > 0 and want["match_cnt"].sum() > 0
 
 
 def test_device_functions_survive_garbage_inputs_under_sanitizers(tmp_path):
@@ -201,65 +226,6 @@ def test_near_field_degenerate_maps(hostsim):
     huge = np.array([[0, 0, 0], [3e38, 0, 0]], np.float32)
     maybe, lay, cell = _near_query(huge, (1, 1, 1), 0.2, 2, [[0, 0, 0], [1e30, 5, 5]])
     assert cell == 0.0 and maybe.all()
-
-
-def _lik_wc(map_pts, lik, poses, lik_pts, near_k=2):
-    hs_lib = C.CDLL(LIB)
-    vp, sz = C.c_void_p, C.c_size_t
-    hs_lib.hostsim_lik_wc.argtypes = [vp, sz, vp, C.c_float, vp, sz, vp, sz, vp, C.c_int, vp]
-    map_pts = np.ascontiguousarray(map_pts, dtype=synth.POINT)
-    poses = np.ascontiguousarray(poses, dtype=synth.POSE)
-    lik_pts = np.ascontiguousarray(lik_pts, dtype=synth.POINT)
-    out = np.zeros(len(poses), dtype=synth.RESULT)
-    wk = np.zeros(5, dtype=np.uint64)
-    p = lambda a: a.ctypes.data_as(vp) if a.size else None  # noqa: E731
-    rc = hs_lib.hostsim_lik_wc(p(map_pts), len(map_pts), C.byref(lik), 1.0, p(poses), len(poses), p(lik_pts), len(lik_pts),
-                               p(out), near_k, p(wk))
-    assert rc == 0, rc
-    return out, wk
-
-
-@pytest.mark.parametrize("seed,w,spread,n_lik,near_k", [(31, (1, 1, 1), False, 96, 2), (32, (1, 1, 5), False, 70, 0),
-                                                        (33, (1, 1, 5), True, 33, 2), (34, (2, 1, 3), True, 128, 1)])
-def test_warp_chunk_likelihood_rounds_match_oracle(hostsim, port, seed, w, spread, n_lik, near_k):
-    """lik_kernel_wc emulated lane by lane (window-table fetch, chunk dealing, chunk processing, owner update) against
-    the oracle: bit-exact, since the emulation sums in scan order.  n_lik not a multiple of 32 leaves idle lanes."""
-    s = synth.scene(40_000, 24, n_lik, 0, spread=spread, seed=seed)
-    lik = engine.LikParams(dist_weight=w)
-    cpu = port.create(s["map"], cc.lik_params(dist_weight=w), None, 20.0, 0.4 if min(w) >= 1 else 1.0)
-    want = cpu.measure(s["particles"], s["lik"], None, s["origins"])
-    got, wk = _lik_wc(s["map"], lik, s["particles"], s["lik"], near_k)
-    assert np.array_equal(got["match_cnt"], want["match_cnt"]) and np.array_equal(got["score_like"], want["score_like"])
-    assert want["match_cnt"].sum() > 0 and wk[4] == 0          # no overflow fallback on voxel-filtered maps
-    plain, _, wk_plain = hostsim(s["map"], lik, None, s["particles"], s["lik"], None, s["origins"], near=(near_k, 0), work=True)
-    assert np.array_equal(plain["score_like"], got["score_like"])
-    assert wk[1] == wk_plain[1]                                 # the same map points are scanned, just dealt differently
-
-
-@pytest.mark.parametrize("name", ["room_iso", "room_aniso", "room_spread"])
-def test_warp_chunk_likelihood_rounds_match_reference_goldens(hostsim, name):
-    g = golden(name + ".npz")
-    lik = engine.LikParams(dist_weight=tuple(float(v) for v in g["dist_weight"]))
-    got, _ = _lik_wc(g["map"], lik, g["particles"], g["lik"])
-    assert np.array_equal(got["match_cnt"], g["result"]["match_cnt"])
-    assert np.allclose(got["score_like"], g["result"]["score_like"], rtol=1e-6)   # the reference sums in the same order
-
-
-def test_warp_chunk_overflow_falls_back_to_whole_runs(hostsim, port):
-    """A raw cloud with thousands of points per cell: the 4-point chunk list does not fit, the round is dealt run by
-    run (and the window table's packed counts saturate, so the CSR bounds are read) — same result as the oracle."""
-    rng = np.random.default_rng(91)
-    pts = rng.uniform(0.0, 1.0, (60_000, 3)).astype(np.float32)
-    mp = synth.make_points(pts)
-    P, n_lik = 5, 40
-    poses = synth.make_poses(rng.uniform(0.3, 0.7, (P, 3)), synth.quat_from_rpy(rng.normal(0, 0.3, (P, 3))))
-    scan = synth.make_points(rng.uniform(-0.7, 0.7, (n_lik, 3)))
-    lik = engine.LikParams(dist_weight=(1, 1, 1))
-    cpu = port.create(mp, cc.lik_params(dist_weight=(1, 1, 1)), None, 20.0, 0.4)
-    want = cpu.measure(poses, scan, None, np.zeros((1, 3), np.float32))
-    got, wk = _lik_wc(mp, lik, poses, scan)
-    assert np.array_equal(got["match_cnt"], want["match_cnt"]) and np.array_equal(got["score_like"], want["score_like"])
-    assert wk[4] > 0 and want["match_cnt"].sum() > 0
 
 
 # ------------------------------------------------------------------ scope row f3 groundwork (csrc/pf_funcs.cuh)
@@ -520,9 +486,10 @@ def test_pf_resample_equals_oracle_on_many_small_sets(hostsim, port):
     assert dup0 > 100
 
 
-def test_screens_and_skip_ahead_randomized_differential(hostsim):
+def test_screens_and_nn_field_randomized_differential(hostsim):
     """Forty random configurations (map size, metric weights, match radius, map grid, caster, tracking / spread poses):
-    every near-field / skip-ahead setting returns the records and per-ray status of the unscreened searches."""
+    every near-field setting, with and without the NN field, returns the records and per-ray status of the unscreened
+    CSR window searches."""
     for seed in range(40):
         rng = np.random.default_rng(seed)
         n_map = int(rng.choice([500, 5000, 30000]))
@@ -533,7 +500,7 @@ def test_screens_and_skip_ahead_randomized_differential(hostsim):
         g = float(rng.choice([0.05, 0.1, 0.2]))
         beam = engine.beam_params_from_reference(map_grid=(g, g, g * float(rng.choice([1, 2]))), num_points_default=8,
                                                  use_raycast_using_dda=bool(seed % 2), dda_grid_size=max(0.2, 2 * g))
-        ref, st_ref = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(0, 0), kd_skip=0)
-        for near, skip in (((2, 1), 4), ((1, 2), 16), ((3, 1), 1)):
-            got, st = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=near, kd_skip=skip)
-            assert got.tobytes() == ref.tobytes() and np.array_equal(st, st_ref), (seed, near, skip)
+        ref, st_ref = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(0, 0), field=0)
+        for near, field in (((2, 1), 1), ((1, 2), 0), ((3, 1), 1)):
+            got, st = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=near, field=field)
+            assert got.tobytes() == ref.tobytes() and np.array_equal(st, st_ref), (seed, near, field)
