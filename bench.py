@@ -407,7 +407,11 @@ def device_leg(cx, workload, raycaster, steps, warmup, exchange="peer", graph=Tr
         alg_bytes = ws["lik_index_rows"] * 8 + ws["lik_points_scanned"] * 16 + io_bytes + n_lik * 16
         note = ("counted: %.1f index entries x 8 B + %.1f map points x 16 B per eval (+ poses/scan/records)"
                 % (ws["lik_index_rows"] / max(P_rank * n_lik, 1), ws["lik_points_scanned"] / max(P_rank * n_lik, 1)))
-        if near[0][0]:
+        nnf = eng.nn_field_info()
+        if nnf["bytes"]:
+            note += "; NN field %.0f MB, %.1f M candidates, %d overflow cells" % (nnf["bytes"] / 1e6, nnf["candidates"] / 1e6,
+                                                                                 nnf["overflow_cells"])
+        elif near[0][0]:
             alg_bytes += P_rank * n_lik * 4
             note += " + one 4 B near-field word per eval (k=%d, %.0f MB)" % (near[0][0], near[0][1] / 1e6)
         survey_bytes = P_rank * n_lik * bpe + io_bytes + n_lik * 16

@@ -292,6 +292,13 @@ int mcl3dl_exchange_current(mcl3dl_engine*, void* cuda_stream, const mcl3dl_resu
  * descends the tree).  Environment: MCL3DL_NEAR_K / MCL3DL_NEAR_KD_K (0 disables), MCL3DL_NEAR_MAX_MB. */
 int mcl3dl_near_field_info(const mcl3dl_engine*, int32_t k_out[2], uint64_t bytes_out[2]);
 
+/* The NN field staged by the last set_map (exact per-voxel candidate lists, the default likelihood search structure;
+ * no reference counterpart — ChunkedKdtree::radiusSearch, chunked_kdtree.h:218-251, descends a kd-tree per query):
+ * out[0] = bytes per device (0: not staged, the CSR-window kernels serve the searches), out[1] = candidates stored,
+ * out[2] = directory cells that overflowed (queries there fall back to the CSR window search), out[3] = fine voxel edge
+ * in micrometres of the rescaled space.  Environment: MCL3DL_NNF=0 disables, MCL3DL_NNF_MAX_MB caps the size. */
+int mcl3dl_nn_field_info(const mcl3dl_engine*, uint64_t out[4]);
+
 /* Enable (and zero) / disable the work counters; read them (synchronises the devices). */
 int mcl3dl_collect_stats(mcl3dl_engine*, int enable);
 int mcl3dl_read_stats(mcl3dl_engine*, mcl3dl_work_stats* out);

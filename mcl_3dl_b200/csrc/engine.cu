@@ -173,7 +173,7 @@ __device__ __forceinline__ bool nnf_voxel_of_thread(const NnFieldDev& f, size_t 
 
 __global__ void __launch_bounds__(256)
     nnf_count_kernel(NnGridDev g, NnFieldDev f, const uint32_t* __restrict__ bits, int pitch, uint2* __restrict__ dir,
-                     uint32_t* __restrict__ totals, size_t n_cells)
+                     uint32_t* __restrict__ totals, size_t n_cells, uint32_t* __restrict__ n_overflow)
 {
   const size_t t = blockIdx.x * static_cast<size_t>(256) + threadIdx.x;
   size_t cell;
@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(256)
   {
     dir[cell].y = ovf ? 0xffffffffu : nib;  // all-ones (a count of 15 never occurs): overflow cell
     totals[cell] = ovf ? 0u : tot;
+    if (ovf)
+      atomicAdd(n_overflow, 1u);
   }
 }
 
@@ -342,7 +344,7 @@ struct mcl3dl_engine
                             // round 1: off until the f2 parity tests have run with it)
   int nnf = 1;  // stage the NN field (exact per-voxel candidate lists) and use lik_kernel_nf; MCL3DL_NNF=0: the CSR window kernels
   size_t nnf_max_bytes = size_t(32) << 30;  // MCL3DL_NNF_MAX_MB: directory + candidates above this -> no field
-  uint64_t nnf_bytes = 0, nnf_cands = 0, nnf_voxels = 0, nnf_overflow_cells = 0;
+  uint64_t nnf_bytes = 0, nnf_cands = 0, nnf_overflow_cells = 0;
   int mapping = 1;  // 1 = tuned kernels (lik_kernel_wi + beam_kernel_pl); 0 = the plain group kernels (MCL3DL_MAPPING=group)
 };
 
@@ -427,20 +429,7 @@ int launch_lik_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int
   const int groups = (P + PPB - 1) / PPB;
   const int grid = std::max(1, std::min(groups, c.sm_count * 8));
   const size_t bytes = static_cast<size_t>(N) * 16;
-  if (eng->mapping != 0 && c.nn.field.dir)
-  {
-    // NN-field kernel: light on registers and shared memory, so the grid is sized to whole waves of its own occupancy
-    if (bytes <= static_cast<size_t>(kMaxStagedBytes))
-    {
-      if (int rc = opt_in_smem(eng, c, lik_kernel_nf<TPP, true>, kMaxStagedBytes)) return rc;
-      lik_kernel_nf<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr(), sink);
-    }
-    else
-    {
-      lik_kernel_nf<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr(), sink);
-    }
-  }
-  else if (eng->mapping != 0)
+  if (eng->mapping != 0)
   {
     if (bytes <= static_cast<size_t>(kMaxStagedSorted))
     {
@@ -489,17 +478,92 @@ int launch_beam_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, in
 }
 
 
+// ---- NN-field likelihood kernel: lanes per particle, staging and grid (kernels.cuh: lik_kernel_nf)
+constexpr int kNfCtasPerSm = MCL3DL_NF_MINB;
+
+int pick_tpp_nf(size_t P, size_t N, int sm_count)
+{
+  const size_t slots = static_cast<size_t>(sm_count) * kNfCtasPerSm;
+  auto ctas = [&](int tpp) { return (P * tpp + kBlockThreads - 1) / kBlockThreads; };
+  // ~kNfU evals per lane and particle ...
+  int tpp = 8;
+  while (tpp < kBlockThreads && static_cast<size_t>(tpp) * kNfU < N) tpp *= 2;
+  // ... unless that leaves SMs without a CTA: then more lanes per particle (fewer evals per lane)
+  while (tpp < kBlockThreads && static_cast<size_t>(tpp) < N && ctas(tpp) * 2 <= static_cast<size_t>(sm_count)) tpp *= 2;
+  // a grid a little larger than the resident slots would run a mostly empty second wave: fewer, longer CTAs instead
+  while (tpp > 8 && ctas(tpp) > slots && ctas(tpp) < 2 * slots) tpp /= 2;
+  return tpp;
+}
+
+template <int TPP>
+int launch_lik_nf_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int P, const float4* scan, int N,
+                    mcl3dl_result* out, int beam_defaults, cudaStream_t st, const RecordSink& sink)
+{
+  constexpr int PPB = kBlockThreads / TPP;
+  const int groups = (P + PPB - 1) / PPB;
+  // every CTA resident at once; CTAs loop when there are more particle groups than slots
+  const int grid = std::max(1, std::min(groups, c.sm_count * kNfCtasPerSm));
+  const size_t bytes = static_cast<size_t>(N) * 16;
+  const bool ovf = eng->nnf_overflow_cells != 0;
+  // the tile pays when several particles of the CTA (or several loop trips) read it; otherwise the scan comes from L2
+  const bool staged = bytes <= static_cast<size_t>(kMaxStagedBytes) / 2 && (PPB >= 4 || groups > grid);
+#define NF_LAUNCH(S, O)                                                                                                    \
+  do                                                                                                                       \
+  {                                                                                                                        \
+    if (S)                                                                                                                 \
+      if (int rc = opt_in_smem(eng, c, lik_kernel_nf<TPP, S, O>, kMaxStagedBytes / 2)) return rc;                          \
+    lik_kernel_nf<TPP, S, O><<<grid, kBlockThreads, (S) ? bytes : 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out,       \
+                                                                           beam_defaults, c.stats_ptr(), sink);            \
+  } while (0)
+  if (staged && ovf) NF_LAUNCH(true, true);
+  else if (staged) NF_LAUNCH(true, false);
+  else if (ovf) NF_LAUNCH(false, true);
+  else NF_LAUNCH(false, false);
+#undef NF_LAUNCH
+  CK(cudaGetLastError());
+  eng->launches++;
+  return MCL3DL_OK;
+}
+
+int launch_lik_nf(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
+                  mcl3dl_result* out, int beam_defaults, cudaStream_t st, const RecordSink& sink)
+{
+  const float4* s4 = reinterpret_cast<const float4*>(scan);
+  const int p = static_cast<int>(P), n = static_cast<int>(N);
+  switch (pick_tpp_nf(P, N, c.sm_count))
+  {
+    case 8: return launch_lik_nf_t<8>(eng, c, poses, p, s4, n, out, beam_defaults, st, sink);
+    case 16: return launch_lik_nf_t<16>(eng, c, poses, p, s4, n, out, beam_defaults, st, sink);
+    case 32: return launch_lik_nf_t<32>(eng, c, poses, p, s4, n, out, beam_defaults, st, sink);
+    case 64: return launch_lik_nf_t<64>(eng, c, poses, p, s4, n, out, beam_defaults, st, sink);
+    case 128: return launch_lik_nf_t<128>(eng, c, poses, p, s4, n, out, beam_defaults, st, sink);
+    default: return launch_lik_nf_t<256>(eng, c, poses, p, s4, n, out, beam_defaults, st, sink);
+  }
+}
+
 PlShape pick_pl_shape(size_t P, size_t N, int sm_count)
 {
-  // enough warps to fill the chip (~48 per SM), each lane walking `ppl` consecutive scan points
+  // Every warp walks `ppl` consecutive scan points for 32 particles.  The kernels hold 4 CTAs = 32 warps per SM
+  // (64 registers), and a grid slightly larger than the resident slots runs a mostly empty second wave (c3 and c5 both
+  // sat at 1.73 waves, profiles/r02a_ncu_beam_c*.txt): size the chunks so that the whole grid is resident at once when
+  // the job allows it, and otherwise make it many waves deep.
   const size_t groups = (P + 31) / 32;
-  const size_t target = static_cast<size_t>(sm_count) * 48;
-  size_t ppl = (N * groups) / std::max<size_t>(target, 1);
-  ppl = std::min<size_t>(std::max<size_t>(ppl, 1), 64);
-  const size_t chunks = std::max<size_t>((N + ppl - 1) / ppl, 1);
+  const size_t slots = static_cast<size_t>(sm_count) * 4;  // resident CTAs
   PlShape sh;
-  sh.ppl = static_cast<int>(ppl);
-  sh.cb = static_cast<int>((chunks + kPlWarps - 1) / kPlWarps);
+  auto ctas_for = [&](size_t ppl, PlShape& o) {
+    const size_t chunks = std::max<size_t>((N + ppl - 1) / ppl, 1);
+    int cpg = kPlWarps;
+    while (cpg > 1 && static_cast<size_t>(cpg) / 2 >= chunks) cpg /= 2;  // smallest power of two >= chunks (<= 8)
+    o.ppl = static_cast<int>(ppl);
+    o.cpg = cpg;
+    o.cb = cpg == kPlWarps ? static_cast<int>((chunks + kPlWarps - 1) / kPlWarps) : 1;
+    const size_t gpc = kPlWarps / cpg;
+    return (groups + gpc - 1) / gpc * o.cb;
+  };
+  size_t ppl = std::max<size_t>((N * groups + slots * kPlWarps - 1) / std::max<size_t>(slots * kPlWarps, 1), 1);
+  ppl = std::min<size_t>(ppl, 64);
+  size_t n = ctas_for(ppl, sh);
+  while (n > slots && n < 3 * slots && ppl < 64) n = ctas_for(++ppl, sh);
   return sh;
 }
 
@@ -527,7 +591,8 @@ int launch_beam_pl(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, s
   int rc = prepare_pl_scratch(eng, c, P, sh, st);
   if (rc != MCL3DL_OK)
     return rc;
-  const int groups = static_cast<int>((P + 31) / 32);
+  const int gpc = kPlWarps / sh.cpg;
+  const int groups = static_cast<int>(((P + 31) / 32 + gpc - 1) / gpc);
   const size_t smem = static_cast<size_t>(kPlWarps) * sh.ppl * 16;
   if (eng->beam.use_raycast_using_dda)
     beam_kernel_pl<false><<<groups * sh.cb, kBlockThreads, smem, st>>>(
@@ -545,6 +610,8 @@ int launch_beam_pl(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, s
 int launch_lik(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
                mcl3dl_result* out, int beam_defaults, cudaStream_t st, const RecordSink& sink)
 {
+  if (eng->mapping != 0 && c.nn.field.dir)
+    return launch_lik_nf(eng, c, poses, P, scan, N, out, beam_defaults, st, sink);
   const float4* s4 = reinterpret_cast<const float4*>(scan);
   switch (pick_tpp(P, N, c.sm_count))
   {
@@ -649,7 +716,7 @@ int build_near_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mc
 int build_nn_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mcl3dl_point* pts, uint32_t n, NnGridDev& g,
                    float radius, const float sc_min[3], const float sc_max[3])
 {
-  eng->nnf_bytes = eng->nnf_cands = eng->nnf_voxels = eng->nnf_overflow_cells = 0;
+  eng->nnf_bytes = eng->nnf_cands = eng->nnf_overflow_cells = 0;
   NearBitsDev lay{};
   // the lattice of a k = 2 near field for this radius: fine edge 1.01 * radius / 2, origin 2.5 voxels below the box
   if (!near_layout(lay, radius, 2, sc_min, sc_max, size_t(1) << 40))
@@ -692,7 +759,7 @@ int build_nn_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mcl3
       return MCL3DL_ERR_CUDA;                                                      \
     }                                                                              \
   } while (0)
-  if ((rc = reserve(eng, d_bits, bits_bytes)) || (rc = reserve(eng, d_tot, (n_cells + 1) * 4)) ||
+  if ((rc = reserve(eng, d_bits, bits_bytes)) || (rc = reserve(eng, d_tot, (n_cells + 4) * 4)) ||
       (rc = reserve(eng, c.nnf_dir, n_cells * sizeof(uint2))))
   {
     cleanup();
@@ -703,7 +770,9 @@ int build_nn_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mcl3
   const unsigned blocks = static_cast<unsigned>((n_cells * 8 + 255) / 256);
   uint2* dir = static_cast<uint2*>(c.nnf_dir.p);
   uint32_t* tot = static_cast<uint32_t*>(d_tot.p);
-  nnf_count_kernel<<<blocks, 256, 0, st>>>(g, f, static_cast<const uint32_t*>(d_bits.p), lay.pitch, dir, tot, n_cells);
+  CKF(cudaMemsetAsync(tot + n_cells, 0, 16, st));  // [n_cells]: scan tail, [n_cells + 2]: overflow-cell counter
+  nnf_count_kernel<<<blocks, 256, 0, st>>>(g, f, static_cast<const uint32_t*>(d_bits.p), lay.pitch, dir, tot, n_cells,
+                                           tot + n_cells + 2);
   CKF(cudaGetLastError());
   // exclusive scan of the per-cell totals (in place); the grand total and the last cell's count size the candidates
   size_t tmp_bytes = 0;
@@ -713,7 +782,6 @@ int build_nn_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mcl3
     cleanup();
     return rc;
   }
-  CKF(cudaMemsetAsync(tot + n_cells, 0, 4, st));
   // 64-bit guard: sum the totals' upper bound on the host side via a second, 64-bit scan would cost more than it is
   // worth; the counts are <= 8 * 14 per cell, so the total fits 32 bits when n_cells < 2^32 / 112
   if (n_cells >= (size_t(0xfffffff0u) / (8 * kNnfMaxCand)))
@@ -724,9 +792,11 @@ int build_nn_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mcl3
   }
   tmp_bytes = d_tmp.cap;
   CKF(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, tot, tot, static_cast<int>(n_cells + 1), st));
-  uint32_t total = 0;
-  CKF(cudaMemcpyAsync(&total, tot + n_cells, 4, cudaMemcpyDeviceToHost, st));
+  uint32_t tail[3] = {0, 0, 0};
+  CKF(cudaMemcpyAsync(tail, tot + n_cells, sizeof(tail), cudaMemcpyDeviceToHost, st));
   CKF(cudaStreamSynchronize(st));
+  const uint32_t total = tail[0];
+  eng->nnf_overflow_cells = tail[2];
   const size_t cand_bytes = static_cast<size_t>(total) * sizeof(float4);
   if (n_cells * 8 + cand_bytes > eng->nnf_max_bytes)
   {
@@ -1286,6 +1356,18 @@ int mcl3dl_near_field_info(const mcl3dl_engine* eng, int32_t k_out[2], uint64_t 
     k_out[i] = eng->near_info_k[i];
     bytes_out[i] = eng->near_info_bytes[i];
   }
+  return MCL3DL_OK;
+}
+
+int mcl3dl_nn_field_info(const mcl3dl_engine* eng, uint64_t out[4])
+{
+  if (!eng || !out)
+    return MCL3DL_ERR_INVALID_ARG;
+  const bool on = !eng->devs.empty() && eng->devs[0].nn.field.dir != nullptr;
+  out[0] = on ? eng->nnf_bytes : 0;
+  out[1] = on ? eng->nnf_cands : 0;
+  out[2] = on ? eng->nnf_overflow_cells : 0;
+  out[3] = on ? static_cast<uint64_t>(eng->devs[0].nn.field.e * 1e6f) : 0;
   return MCL3DL_OK;
 }
 

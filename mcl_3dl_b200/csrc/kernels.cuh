@@ -521,23 +521,81 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
 // NN-field likelihood kernel (the default when set_map staged the field, device_funcs.cuh: NnFieldDev).
 //
 // ncu on lik_kernel_wi (profiles/r02a_ncu_lik_c2.txt / _c5.txt): 36-41 warp instructions per eval at 17-19 live lanes,
-// L1/TEX the busiest unit (48 % on c2, 85 % on c5), DRAM < 1 %: the kernel is bound by the instructions and the
-// gather wavefronts of walking a 3 x 3 window of CSR rows per eval, not by HBM.  With the field an eval is: transform,
-// one 8-byte directory entry, then the 3-6 contiguous candidates of its voxel — two dependent loads, ~1/4 of the
-// instructions, no warp-level dealing.  Lane = eval; two evals per lane and iteration are in flight so that their
-// directory loads overlap.  The per-lane accumulation order (j = l, l + TPP, ...) and the reductions are those of
-// lik_kernel / lik_kernel_wi, so the records are bit-identical to theirs.
-__device__ __noinline__ float nn_dist2_generic(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz,
-                                               uint32_t& n_rows, uint32_t& n_pts)
+// L1/TEX the busiest unit (48 % on c2, 85 % on c5), DRAM < 1 %: bound by the instructions and gather wavefronts of
+// walking a 3 x 3 window of CSR rows per eval.  With the field an eval is: transform, one 8-byte directory entry, then
+// the 1-6 contiguous candidates of its voxel — two dependent loads and ~1/4 of the instructions.  What is left is
+// latency (profiles/r02b_ncu_lik_c2.txt: issue 32 %, long scoreboard 10 per issue, SMs active 60 % of the launch), so
+// the kernel is built around loads in flight:
+//   * lane = eval, kNfU = 4 evals per lane in flight (their directory loads, then their candidate loads, overlap);
+//   * TPP in {8 .. 256} lanes per particle, chosen on the host so that a particle's scan gives every lane ~4 evals and
+//     the whole grid is resident in ONE wave where the job is small (c2: 128 lanes x 2 particles x 512 CTAs);
+//   * the TMA copy of the scan tile is issued first and waited for only after the pose is loaded and normalised
+//     (fp64 division); CTAs whose tile would be used by < 4 particles read the scan straight from L2 instead;
+//   * the overflow fallback (raw clouds) is a template flag, so maps without overflow cells carry none of its code.
+// Per-lane accumulation runs in scan order (j = l, l + TPP, ...), lanes are folded by the xor-shuffle tree and warps in
+// order: deterministic, and bit-identical to lik_kernel / lik_kernel_wi whenever those run with the same TPP.
+constexpr int kNfU = 4;
+// resident CTAs per SM the compiler must allow (register cap): 3 -> 80 registers, 4 -> 64, 5 -> 48, 6 -> 40
+#ifndef MCL3DL_NF_MINB
+#define MCL3DL_NF_MINB 3
+#endif
+
+__device__ __forceinline__ void stage_issue(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
 {
-  return nn_dist2(g, lp, qx, qy, qz, n_rows, n_pts);
+  const uint32_t bar_a = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  const uint32_t dst_a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  if (threadIdx.x == 0)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+        "l"(gsrc), "r"(bytes), "r"(bar_a)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void stage_wait(uint64_t* bar)
+{
+  const uint32_t bar_a = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  __syncthreads();  // the barrier's initialisation (thread 0) is visible to every waiter
+  uint32_t done = 0;
+  while (!done)
+  {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar_a)
+        : "memory");
+  }
 }
 
-// resident CTAs per SM the compiler must allow (register cap): 4 -> 64 registers, 5 -> 48, 6 -> 40, 8 -> 32
-#ifndef MCL3DL_NF_MINB
-#define MCL3DL_NF_MINB 4
-#endif
-template <int TPP, bool STAGED>
+// fold one value per lane over the TPP lanes that own a particle (TPP < 32: the particle's lanes are an aligned
+// sub-group of the warp; TPP >= 32: group_reduce's warp tree + fixed-order shared-memory pass)
+template <int TPP>
+__device__ __forceinline__ void nf_reduce(float& f, uint32_t& a, float* red_f, uint32_t* red_u)
+{
+  if (TPP >= 32)
+  {
+    uint32_t z0 = 0, z1 = 0;
+    group_reduce<TPP>(f, a, z0, z1, red_f, red_u);
+  }
+  else
+  {
+#pragma unroll
+    for (int o = TPP / 2; o > 0; o >>= 1)
+    {
+      f = fadd(f, __shfl_xor_sync(0xffffffffu, f, o));
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+    }
+  }
+}
+
+template <int TPP, bool STAGED, bool OVF>
 __global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
     lik_kernel_nf(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N, NnGridDev g,
                   LikDev lp, mcl3dl_result* __restrict__ out, int write_beam_defaults,
@@ -547,29 +605,30 @@ __global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
   __shared__ uint64_t bar;
   __shared__ float red_f[kBlockThreads / 32];
   __shared__ uint32_t red_u[3 * kBlockThreads / 32];
-  const float4* pts = scan;
   if (STAGED && N > 0)
-  {
-    stage_tile(smem_raw, scan, static_cast<uint32_t>(N) * 16u, &bar);
-    pts = reinterpret_cast<const float4*>(smem_raw);
-  }
+    stage_issue(smem_raw, scan, static_cast<uint32_t>(N) * 16u, &bar);
   constexpr int PPB = kBlockThreads / TPP;
   const int sub = threadIdx.x / TPP;
   const int l = threadIdx.x % TPP;
   const int n_groups = (P + PPB - 1) / PPB;
   const NnFieldDev& f = g.field;
   uint32_t st_rows = 0, st_pts = 0;
+  bool staged_ready = !(STAGED && N > 0);
   for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
   {
     const int p = grp * PPB + sub;
     const bool live = p < P;
     float score = 0.0f;
-    uint32_t cnt = 0, z0 = 0, z1 = 0;
+    uint32_t cnt = 0;
+    F3 pos;
+    Q4 rn;
+    pos.x = pos.y = pos.z = 0.0f;
+    rn.x = rn.y = rn.z = 0.0f;
+    rn.w = 1.0f;
     if (live)
     {
       const float4 a = __ldg(reinterpret_cast<const float4*>(poses + p));
       const float4 b = __ldg(reinterpret_cast<const float4*>(poses + p) + 1);
-      F3 pos;
       pos.x = a.x;
       pos.y = a.y;
       pos.z = a.z;
@@ -578,23 +637,32 @@ __global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
       q.y = b.y;
       q.z = b.z;
       q.w = b.w;
-      const Q4 rn = qnormalized(q);  // state_6dof.h:217
-      for (int j = l; j < N; j += 2 * TPP)
+      rn = qnormalized(q);  // state_6dof.h:217
+    }
+    if (!staged_ready)
+    {
+      stage_wait(&bar);  // the tile has been in flight since the kernel started
+      staged_ready = true;
+    }
+    const float4* pts = STAGED ? reinterpret_cast<const float4*>(smem_raw) : scan;
+    if (live)
+    {
+      for (int j = l; j < N; j += kNfU * TPP)
       {
-        const bool two = j + TPP < N;
-        // ---- both evals' queries and directory entries first (independent loads in flight)
-        float qx[2], qy[2], qz[2];
-        int c[2];
-        uint32_t s[2];
+        // ---- the queries and directory entries of up to kNfU evals (independent loads in flight)
+        float qx[kNfU], qy[kNfU], qz[kNfU];
+        int c[kNfU];
+        uint32_t s[kNfU];
+        int cm = 0;
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < kNfU; ++u)
         {
           c[u] = 0;
           s[u] = 0;
           qx[u] = qy[u] = qz[u] = 0.0f;
-          if (u == 0 || two)
+          if (j + u * TPP < N)
           {
-            const float4 sp = pts[j + u * TPP];
+            const float4 sp = STAGED ? pts[j + u * TPP] : __ldg(pts + j + u * TPP);
             F3 v;
             v.x = sp.x;
             v.y = sp.y;
@@ -606,15 +674,17 @@ __global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
             qz[u] = fmul(t.z, g.wz);
             c[u] = nnf_lookup(f, qx[u], qy[u], qz[u], s[u]);
             ++st_rows;
+            cm = max(cm, c[u]);
           }
         }
-        // ---- candidates of both voxels, interleaved
-        float best[2] = {lp.r2, lp.r2};
-        const int cm = max(c[0], c[1]);
+        // ---- candidates of the voxels, interleaved
+        float best[kNfU];
+#pragma unroll
+        for (int u = 0; u < kNfU; ++u) best[u] = lp.r2;
         for (int i = 0; i < cm; ++i)
         {
 #pragma unroll
-          for (int u = 0; u < 2; ++u)
+          for (int u = 0; u < kNfU; ++u)
             if (i < c[u])
             {
               const float4 m = __ldg(f.cand + s[u] + i);
@@ -626,13 +696,13 @@ __global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < kNfU; ++u)
         {
-          if (c[u] < 0)  // overflow cell (raw clouds): the CSR window search
-            best[u] = nn_dist2_generic(g, lp, qx[u], qy[u], qz[u], st_rows, st_pts);
+          if (OVF && c[u] < 0)  // overflow cell (raw clouds): the CSR window search
+            best[u] = nn_dist2(g, lp, qx[u], qy[u], qz[u], st_rows, st_pts);
           else
-            st_pts += static_cast<uint32_t>(c[u]);
-          if ((u == 0 || two) && best[u] < lp.r2)
+            st_pts += static_cast<uint32_t>(max(c[u], 0));
+          if (best[u] < lp.r2)  // (evals beyond N keep best = r2)
           {
             // likelihood.cpp:128-133
             const float dist = fsub(lp.match_dist_min, fmaxf(__fsqrt_rn(best[u]), lp.match_dist_flat));
@@ -645,10 +715,12 @@ __global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
         }
       }
     }
-    group_reduce<TPP>(score, cnt, z0, z1, red_f, red_u);
+    nf_reduce<TPP>(score, cnt, red_f, red_u);
     if (live && l == 0)  // empty scan -> LidarMeasurementResult(1, 0), likelihood.cpp:111-114
       sink_store_lik(sink, out, p, (N == 0) ? 1.0f : score, cnt, write_beam_defaults);
   }
+  if (!staged_ready)
+    stage_wait(&bar);  // never leave with the bulk copy in flight
   if (stats)
   {
     const uint32_t r = warp_sum_u32(st_rows), q = warp_sum_u32(st_pts);
@@ -763,7 +835,8 @@ constexpr int kPlWarps = kBlockThreads / 32;
 struct PlShape
 {
   int ppl;  // scan points per lane (chunk length)
-  int cb;   // CTAs per particle group (each covers kPlWarps chunks)
+  int cb;   // CTAs per particle group (each covers kPlWarps chunks); > 1 only when cpg == kPlWarps
+  int cpg;  // chunks (= warps) a CTA spends on one particle group: 1, 2, 4 or 8; the CTA covers kPlWarps / cpg groups
 };
 
 template <bool KD>
@@ -778,15 +851,19 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
   __shared__ uint64_t bar;
   __shared__ uint32_t red[kPlWarps][3][32];
   __shared__ unsigned int s_ticket;
-  const int group = blockIdx.x / sh.cb;
-  const int cblk = blockIdx.x % sh.cb;
+  // short scans (few chunks per group): the CTA's warps are spread over kPlWarps / cpg particle groups, so that no warp
+  // is left without rays (c5: 8 rays per particle = 4 chunks; half of every CTA used to idle at the barrier)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gpc = kPlWarps / sh.cpg;
+  const int group = (blockIdx.x / sh.cb) * gpc + warp / sh.cpg;
+  const int cblk = blockIdx.x % sh.cb;
+  const int wchunk = warp % sh.cpg;
   const int base = cblk * kPlWarps * sh.ppl;
-  const int slice = max(0, min(N - base, kPlWarps * sh.ppl));
+  const int slice = max(0, min(N - base, sh.cpg * sh.ppl));
   const float4* tile = reinterpret_cast<const float4*>(smem_raw);
   if (slice > 0)
     stage_tile(smem_raw, scan + base, static_cast<uint32_t>(slice) * 16u, &bar);
-  const int j0 = warp * sh.ppl;
+  const int j0 = wchunk * sh.ppl;
   const int j1 = min(slice, j0 + sh.ppl);
   const int p = group * 32 + lane;
   const bool live = p < P;
@@ -827,15 +904,14 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
   red[warp][1][lane] = n_hit;
   red[warp][2][lane] = n_long;
   __syncthreads();
-  if (warp == 0)
+  if (wchunk == 0)
   {
     uint32_t a = 0, b = 0, c = 0;
-#pragma unroll
-    for (int k = 0; k < kPlWarps; ++k)
+    for (int k = 0; k < sh.cpg; ++k)
     {
-      a += red[k][0][lane];
-      b += red[k][1][lane];
-      c += red[k][2][lane];
+      a += red[warp + k][0][lane];
+      b += red[warp + k][1][lane];
+      c += red[warp + k][2][lane];
     }
     bool writer = sh.cb == 1;
     if (sh.cb > 1)

@@ -75,7 +75,7 @@ class WorkStats(C.Structure):
 EXPORTED_SYMBOLS = ["mcl3dl_measure_update", "mcl3dl_collect_stats", "mcl3dl_read_stats", "mcl3dl_abi_version", "mcl3dl_create", "mcl3dl_destroy", "mcl3dl_set_map", "mcl3dl_set_params",
                     "mcl3dl_measure", "mcl3dl_measure_device", "mcl3dl_beam_status",
                     "mcl3dl_beam_params_from_reference", "mcl3dl_get_map_info", "mcl3dl_last_timing",
-                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_collect_timing",
+                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_nn_field_info", "mcl3dl_collect_timing",
                     "mcl3dl_exchange_create", "mcl3dl_exchange_open", "mcl3dl_measure_exchange_device", "mcl3dl_exchange_current",
                     "mcl3dl_particles_set", "mcl3dl_particles_get", "mcl3dl_particles_predict",
                     "mcl3dl_particles_measure_update", "mcl3dl_particles_resample"]
@@ -131,6 +131,7 @@ def load_library(path=None):
     L.mcl3dl_measure_exchange_device.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, C.POINTER(vp)]
     L.mcl3dl_exchange_current.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_int)]
     L.mcl3dl_near_field_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+    L.mcl3dl_nn_field_info.argtypes = [vp, C.POINTER(C.c_uint64)]
     assert L.mcl3dl_abi_version() == 3
     _LIBS[path] = L
     return L
@@ -204,6 +205,12 @@ class Engine:
         b = (C.c_uint64 * 2)()
         self._check(self.L.mcl3dl_near_field_info(self.h, k, b))
         return [(int(k[0]), int(b[0])), (int(k[1]), int(b[1]))]
+
+    def nn_field_info(self):
+        """The NN field of the staged map: {"bytes", "candidates", "overflow_cells", "voxel_edge"} (bytes 0: not staged)."""
+        v = (C.c_uint64 * 4)()
+        self._check(self.L.mcl3dl_nn_field_info(self.h, v))
+        return {"bytes": int(v[0]), "candidates": int(v[1]), "overflow_cells": int(v[2]), "voxel_edge": v[3] * 1e-6}
 
     def measure(self, poses, lik_pts=None, beam_pts=None, origins=None, out=None):
         poses = np.ascontiguousarray(poses, dtype=POSE)

@@ -3,7 +3,7 @@
 #   1 GPU :  gpurun --timeout 1200 -- 'bash profiles/r02b.sh one'
 #   2 GPUs:  gpurun --gpus 2 --timeout 900 -- 'bash profiles/r02b.sh two'
 MODE=${1:-one}
-TAG=${2:-r02b}
+TAG=${2:-r02c}
 OUT=gpurun_out
 mkdir -p $OUT
 if [ "$MODE" = one ]; then

@@ -440,7 +440,7 @@ def test_options_change_no_record(eng_mod, monkeypatch, use_dda):
     beam = eng_mod.beam_params_from_reference(num_points_default=24, dda_grid_size=0.2, use_raycast_using_dda=use_dda)
 
     def run(env, timing=False):
-        for k in ("MCL3DL_NEAR_K", "MCL3DL_NEAR_KD_K", "MCL3DL_ZEROCOPY_OUT", "MCL3DL_TIMING", "MCL3DL_MAPPING"):
+        for k in ("MCL3DL_NEAR_K", "MCL3DL_NEAR_KD_K", "MCL3DL_ZEROCOPY_OUT", "MCL3DL_TIMING", "MCL3DL_MAPPING", "MCL3DL_NNF"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -462,5 +462,11 @@ def test_options_change_no_record(eng_mod, monkeypatch, use_dda):
     timed, _, t1 = run({"MCL3DL_NEAR_K": "1", "MCL3DL_ZEROCOPY_OUT": "100"}, timing=True)   # 300 particles > 100: bulk D2H copy
     assert timed.tobytes() == plain.tobytes()
     assert t1["lik_ms"] > 0.0 and t1["beam_ms"] > 0.0 and t1["h2d_ms"] > 0.0
+    def same(a, b):  # another kernel generation may sum a particle's likelihood terms in another order
+        for f in ("match_cnt", "score_beam", "n_short", "n_hit", "n_long"):
+            assert np.array_equal(a[f], b[f]), f
+        assert np.allclose(a["score_like"], b["score_like"], rtol=2e-6, atol=1e-6)
     group, _, _ = run({"MCL3DL_MAPPING": "group", "MCL3DL_NEAR_K": "3", "MCL3DL_NEAR_KD_K": "2"})
-    assert group.tobytes() == plain.tobytes()
+    same(group, plain)
+    csr, _, _ = run({"MCL3DL_NNF": "0"})                      # the CSR-window kernels of round 1 (no NN field)
+    same(csr, plain)
