@@ -492,6 +492,12 @@ int pick_tpp_nf(size_t P, size_t N, int sm_count)
   while (tpp < kBlockThreads && static_cast<size_t>(tpp) < N && ctas(tpp) * 2 <= static_cast<size_t>(sm_count)) tpp *= 2;
   // a grid a little larger than the resident slots would run a mostly empty second wave: fewer, longer CTAs instead
   while (tpp > 8 && ctas(tpp) > slots && ctas(tpp) < 2 * slots) tpp /= 2;
+  if (const char* v = std::getenv("MCL3DL_NF_TPP"))  // experiments
+  {
+    const int t = std::atoi(v);
+    if (t == 8 || t == 16 || t == 32 || t == 64 || t == 128 || t == 256)
+      tpp = t;
+  }
   return tpp;
 }
 
@@ -506,7 +512,9 @@ int launch_lik_nf_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, 
   const size_t bytes = static_cast<size_t>(N) * 16;
   const bool ovf = eng->nnf_overflow_cells != 0;
   // the tile pays when several particles of the CTA (or several loop trips) read it; otherwise the scan comes from L2
-  const bool staged = bytes <= static_cast<size_t>(kMaxStagedBytes) / 2 && (PPB >= 4 || groups > grid);
+  bool staged = bytes <= static_cast<size_t>(kMaxStagedBytes) / 2 && (PPB >= 4 || groups > grid);
+  if (const char* v = std::getenv("MCL3DL_NF_STAGE"))  // experiments
+    staged = bytes <= static_cast<size_t>(kMaxStagedBytes) / 2 && std::atoi(v) != 0;
 #define NF_LAUNCH(S, O)                                                                                                    \
   do                                                                                                                       \
   {                                                                                                                        \

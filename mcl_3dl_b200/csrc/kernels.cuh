@@ -534,10 +534,14 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
 //   * the overflow fallback (raw clouds) is a template flag, so maps without overflow cells carry none of its code.
 // Per-lane accumulation runs in scan order (j = l, l + TPP, ...), lanes are folded by the xor-shuffle tree and warps in
 // order: deterministic, and bit-identical to lik_kernel / lik_kernel_wi whenever those run with the same TPP.
-constexpr int kNfU = 4;
+#ifndef MCL3DL_NF_U
+#define MCL3DL_NF_U 4
+#endif
+constexpr int kNfU = MCL3DL_NF_U;
 // resident CTAs per SM the compiler must allow (register cap): 3 -> 80 registers, 4 -> 64, 5 -> 48, 6 -> 40
+// (measured, profiles/r02c_ab.jsonl: 4 beats 3 and 5 on every workload)
 #ifndef MCL3DL_NF_MINB
-#define MCL3DL_NF_MINB 3
+#define MCL3DL_NF_MINB 4
 #endif
 
 __device__ __forceinline__ void stage_issue(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
