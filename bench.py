@@ -246,7 +246,7 @@ def config_dict(workload, s, P, n_lik, n_beam, spread, dda):
                         % (workload, P, n_lik, n_beam, len(s["map"]), MAP_VOXEL, "spread" if spread else "tracking"),
             "dist_weight": list(DIST_WEIGHT), "dda_grid_size": dda, "match_dist_min": 0.2,
             "raycaster": "RaycastUsingDDA" if USE_DDA else "RaycastUsingKDTree",
-            "l2": "flushed (256 MiB write) before every timed step"}
+            "l2": "flushed (256 MiB write) before every timed step; N > 1: ranks re-aligned (untimed) after the flush"}
 
 
 class Ctx:
@@ -254,7 +254,7 @@ class Ctx:
     pass
 
 
-def device_leg(cx, workload, raycaster, steps, warmup, exchange="peer", graph=True, keep_spinning=False):
+def device_leg(cx, workload, raycaster, steps, warmup, exchange="peer", graph=True, keep_spinning=False, field=False):
     """Device-resident leg of one workload on every rank: value (CUDA events, max over ranks), per-model kernel
     times, counted roofline.  Returns (result dict, live objects for the e2e leg)."""
     import torch
@@ -296,6 +296,33 @@ def device_leg(cx, workload, raycaster, steps, warmup, exchange="peer", graph=Tr
         eng.measure_device(d_p.data_ptr(), P_rank, d_l.data_ptr(), n_lik, d_b.data_ptr(), n_beam,
                            d_o.data_ptr(), n_org, d_out.data_ptr(), st)
 
+    field_info = None
+    if field:
+        # the opt-in, inexact field mode (dense distance volume + trilinear lookup, north_star's literal kernel): its
+        # records against the exact ones of the same engine (which are oracle-checked), then everything below runs in it
+        st0 = torch.cuda.current_stream().cuda_stream
+        plain_measure(st0)
+        torch.cuda.synchronize()
+        exact = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=synth.RESULT).copy()
+        t0 = time.perf_counter()
+        eng.field_mode(True)
+        stage_s = time.perf_counter() - t0
+        plain_measure(st0)
+        torch.cuda.synchronize()
+        got = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=synth.RESULT).copy()
+        rel = np.abs(got["score_like"] - exact["score_like"]) / np.maximum(np.abs(exact["score_like"]), 1e-3)
+        nodes, _, edge, dims = eng.field_nodes(download=False)
+        field_info = {"score_like_rel_err_vs_exact": {"mean": float(rel.mean()), "p99": float(np.quantile(rel, 0.99)),
+                                                      "max": float(rel.max())},
+                      "match_cnt_mismatch_fraction": float(np.mean(got["match_cnt"] != exact["match_cnt"])),
+                      "match_cnt_mean_abs_diff": float(np.mean(np.abs(got["match_cnt"].astype(np.int64)
+                                                                      - exact["match_cnt"].astype(np.int64)))),
+                      "lattice_nodes": list(dims), "lattice_edge": edge,
+                      "volume_bytes": int((dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1) * 32),
+                      "stage_ms": round(1e3 * stage_s, 2),
+                      "note": "exact = this engine's NN-field search (oracle-checked by the -m gpu tests); the field mode "
+                              "is reported, not gated: interpolating a distance field at this lattice cannot meet 1e-4"}
+
     def step_eager():
         st = torch.cuda.current_stream().cuda_stream
         if peer:
@@ -328,11 +355,17 @@ def device_leg(cx, workload, raycaster, steps, warmup, exchange="peer", graph=Tr
             cx.notes.append("CUDA graph capture failed for %s: %s" % (workload, exc))
             barrier()
 
+    align = torch.zeros(1, device=dev)
+
     def timed(fn, k):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
         barrier()
         for a, b in evs:
             flush.fill_(1)          # L2 flush, outside the timed span
+            if world > 1:
+                # the 256 MiB flush does not take the same time on every rank: line the ranks up again (a tiny NCCL
+                # all-reduce on the stream, untimed) so that a timed step does not include waiting for a peer's flush
+                dist.all_reduce(align)
             a.record()
             fn()
             b.record()
@@ -380,6 +413,8 @@ def device_leg(cx, workload, raycaster, steps, warmup, exchange="peer", graph=Tr
            "graph": graphed, "launches_per_step": int(launches_per_step),
            "rank0_step_ms_min_med_max": [float(np.min(per_step)), float(np.median(per_step)), float(np.max(per_step))],
            "exchange": exchange_info}
+    if field_info:
+        res["field_mode"] = field_info
 
     # ---- each model's kernel alone (one launch per call): the dominant kernel's roofline
     stream = torch.cuda.current_stream().cuda_stream
@@ -464,7 +499,8 @@ def e2e_leg(cx, workload, raycaster, steps, live, fused=True):
     n_lik, n_beam, unit_pts = live["n_lik"], live["n_beam"], live["unit_pts"]
     out = None
     if world > 1:
-        dist.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=cx.cpu_group)  # gloo: the waiting ranks leave their GPUs idle
     if rank == 0:
         if world == 1:
             eng, s = live["eng"], live["scene"]
@@ -539,7 +575,7 @@ def e2e_leg(cx, workload, raycaster, steps, live, fused=True):
             out["shard0_equals_device_resident"] = bool(np.array_equal(got, out_host[:live["P_rank"]]))
             eng.close()
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=cx.cpu_group)
     return out
 
 
@@ -581,6 +617,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL_DEBUG is left as the launcher set it (the driver reads the communicator's rank count from NCCL's own log)
         dist.init_process_group("nccl", device_id=torch.device("cuda", cx.local))
+        # host-side waits (a rank that idles while rank 0 drives every GPU must not park an NCCL kernel on its device)
+        cx.cpu_group = dist.new_group(backend="gloo")
     torch.cuda.set_device(cx.local)
     cx.dev = torch.device("cuda", cx.local)
     cx.flush = torch.empty(256 << 20, dtype=torch.uint8, device=cx.dev)
@@ -628,11 +666,12 @@ def main():
     # ---- driver-run secondaries (fewer steps; no CPU leg): what north_star names besides the primary metric
     secondaries = {}
     if not args.no_secondaries and args.workload == "c2" and not args.spread:
-        sec = [("c5", "c5", "dda")] if world > 1 else [("c3", "c3", "dda"), ("c3_kd", "c3", "kd"), ("c5", "c5", "dda")]
+        sec = ([("c5", "c5", "dda")] if world > 1 else
+               [("c3", "c3", "dda"), ("c3_kd", "c3", "kd"), ("c5", "c5", "dda"), ("c5_field", "c5", "dda")])
         k = max(10, min(args.steps, 30))
         for name, wl, caster in sec:
             try:
-                r2, live2 = device_leg(cx, wl, caster, k, 3, args.exchange, graph)
+                r2, live2 = device_leg(cx, wl, caster, k, 3, args.exchange, graph, field=name.endswith("_field"))
                 r2["metric"] = metric_name(live2["n_lik"])
                 r2["unit"] = "evals/s"
                 r2["steps"] = k

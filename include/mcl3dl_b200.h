@@ -299,6 +299,23 @@ int mcl3dl_near_field_info(const mcl3dl_engine*, int32_t k_out[2], uint64_t byte
  * in micrometres of the rescaled space.  Environment: MCL3DL_NNF=0 disables, MCL3DL_NNF_MAX_MB caps the size. */
 int mcl3dl_nn_field_info(const mcl3dl_engine*, uint64_t out[4]);
 
+/* Field mode (BASELINE.json north_star's literal likelihood kernel; OPT-IN and INEXACT): a dense Euclidean-distance
+ * volume over the NN field's lattice, read by trilinear interpolation, replaces the exact nearest-neighbour distance of
+ * LidarMeasurementModelLikelihood::measure (src/lidar_measurement_model_likelihood.cpp:124-135).  Interpolating a
+ * distance field at 0.1 m voxels deviates by ~1e-1 relative from the reference's scores (SURVEY hard part 1), so the
+ * engine never selects it on its own; bench.py / the tests report its deviation.  The beam model is unaffected.
+ *   field_mode(1): stage the volume (once per map: node distances from the NN field on the device, a cudaMalloc3D
+ *                  volume) and route the likelihood kernel through it; field_mode(0): back to the exact search.
+ *                  Needs the NN field (MCL3DL_NNF != 0) and lik params; MCL3DL_ERR_TOO_LARGE above MCL3DL_FIELD_MAX_MB.
+ *                  Environment: MCL3DL_LIK_MODE=field = field_mode(1) at create.
+ *   field_nodes:   dims (nodes per axis), origin and edge of the lattice (rescaled space); nodes_out != NULL also
+ *                  copies the node volume to the host (cudaMemcpy3D), x fastest, dims[0]*dims[1]*dims[2] floats.
+ *   field_upload:  replace the node volume by host values of the same dims (cudaMemcpy3D H2D), e.g. an EDT computed
+ *                  elsewhere; the per-cell corner layout the kernel reads is rebuilt on the device. */
+int mcl3dl_field_mode(mcl3dl_engine*, int enable);
+int mcl3dl_field_nodes(mcl3dl_engine*, float* nodes_out, int32_t dims_out[3], float origin_out[3], float* edge_out);
+int mcl3dl_field_upload(mcl3dl_engine*, const float* nodes, const int32_t dims[3]);
+
 /* Enable (and zero) / disable the work counters; read them (synchronises the devices). */
 int mcl3dl_collect_stats(mcl3dl_engine*, int enable);
 int mcl3dl_read_stats(mcl3dl_engine*, mcl3dl_work_stats* out);

@@ -140,6 +140,21 @@ struct NnFieldDev
   float pad;           // the build pads every voxel box by this much (float rounding of the voxel index of a query)
 };
 
+// ---- distance field ("field mode", BASELINE.json north_star): a dense Euclidean-distance volume over the NN field's
+// fine lattice, looked up by trilinear interpolation.  NOT exact (a distance field is a cone around every point;
+// interpolating it at 0.1 m voxels is off by 1e-1 relative, SURVEY hard part 1), so it is an opt-in, reported variant:
+// the one kernel of this path that is a pure HBM gather — one 32-byte sector per eval.  Layout: every lattice cell
+// stores its 8 corner distances itself (2 x float4, 32-byte aligned), i.e. the node volume replicated 8x, so an eval
+// reads exactly one sector instead of four (the corner rows of a plain volume are nx and nx * ny floats apart).
+struct FieldDev
+{
+  const float4* cells;  // nullptr = not staged.  [cell][2]: {d000, d100, d010, d110}, {d001, d101, d011, d111}
+  int nx, ny, nz;       // cells per axis (nodes: n + 1)
+  float ox, oy, oz;     // position of node (0, 0, 0) in the rescaled space
+  float inv_e;          // 1 / lattice edge
+  float clamp;          // node values are min(exact distance, clamp); queries outside the lattice read clamp
+};
+
 // ---- likelihood search grid: cubic cells over the RESCALED map points (p * dist_weight), CSR of
 // cell -> contiguous run in `pts` (x fastest, so an x-row of cells is one contiguous run).
 struct NnGridDev
@@ -160,6 +175,7 @@ struct NnGridDev
   NearBitsDev near;  // built for the likelihood radius (LikDev::rpad)
 #endif
   NnFieldDev field;  // exact candidate lists per fine voxel (field.dir == nullptr: not staged)
+  FieldDev fld;      // trilinear distance volume of the opt-in field mode (fld.cells == nullptr: not staged)
 };
 
 struct LikDev
@@ -527,6 +543,24 @@ __device__ __forceinline__ bool nnf_search_arg(const NnGridDev& g, float qx, flo
     }
   }
   return best_orig != 0xffffffffu;
+}
+
+// --------------------------------------------------------------------------------------------
+// Field mode: trilinearly interpolated distance at q (rescaled space); `clamp` outside the lattice.
+__device__ __forceinline__ float field_dist(const FieldDev& f, float qx, float qy, float qz)
+{
+  const float tx = fmul(fsub(qx, f.ox), f.inv_e), ty = fmul(fsub(qy, f.oy), f.inv_e), tz = fmul(fsub(qz, f.oz), f.inv_e);
+  const int ix = __float2int_rd(tx), iy = __float2int_rd(ty), iz = __float2int_rd(tz);
+  if (static_cast<unsigned>(ix) >= static_cast<unsigned>(f.nx) || static_cast<unsigned>(iy) >= static_cast<unsigned>(f.ny) ||
+      static_cast<unsigned>(iz) >= static_cast<unsigned>(f.nz))
+    return f.clamp;
+  const float fx = fsub(tx, static_cast<float>(ix)), fy = fsub(ty, static_cast<float>(iy)), fz = fsub(tz, static_cast<float>(iz));
+  const size_t cell = (static_cast<size_t>(iz) * f.ny + iy) * f.nx + ix;
+  const float4 a = __ldg(f.cells + 2 * cell), b = __ldg(f.cells + 2 * cell + 1);
+  const float c00 = fadd(a.x, fmul(fx, fsub(a.y, a.x))), c10 = fadd(a.z, fmul(fx, fsub(a.w, a.z)));
+  const float c01 = fadd(b.x, fmul(fx, fsub(b.y, b.x))), c11 = fadd(b.z, fmul(fx, fsub(b.w, b.z)));
+  const float c0 = fadd(c00, fmul(fy, fsub(c10, c00))), c1 = fadd(c01, fmul(fy, fsub(c11, c01)));
+  return fadd(c0, fmul(fz, fsub(c1, c0)));
 }
 
 // --------------------------------------------------------------------------------------------

@@ -231,6 +231,44 @@ __global__ void __launch_bounds__(256)
   for (int i = 0; i < cnt && i < static_cast<int>(want); ++i) cand[start + i] = g.pts[pos[i]];
 }
 
+// Field mode (device_funcs.cuh: FieldDev).  Node volume: exact distance (clamped) from every lattice node to the
+// nearest map point, through the NN field; a pitched cudaMalloc3D volume so that cudaMemcpy3D moves it to / from the host.
+__global__ void field_nodes_kernel(NnGridDev g, LikDev lp, cudaPitchedPtr vol, int nnx, int nny, int nnz, float clamp)
+{
+  const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(nnx) * nny * nnz;
+  if (t >= total)
+    return;
+  const int i = static_cast<int>(t % nnx);
+  const size_t r = t / nnx;
+  const int j = static_cast<int>(r % nny), k = static_cast<int>(r / nny);
+  const NnFieldDev& f = g.field;
+  const float qx = fadd(f.ox, fmul(static_cast<float>(i), f.e)), qy = fadd(f.oy, fmul(static_cast<float>(j), f.e)),
+              qz = fadd(f.oz, fmul(static_cast<float>(k), f.e));
+  uint32_t a = 0, b = 0;
+  const float d2 = nnf_dist2(g, lp, qx, qy, qz, a, b);
+  float* row = reinterpret_cast<float*>(static_cast<char*>(vol.ptr) + (static_cast<size_t>(k) * nny + j) * vol.pitch);
+  row[i] = d2 < lp.r2 ? fminf(__fsqrt_rn(d2), clamp) : clamp;
+}
+
+// cell (i, j, k) <- its 8 corner nodes, x fastest inside each float4
+__global__ void field_expand_kernel(cudaPitchedPtr vol, int nx, int ny, int nz, float4* __restrict__ cells)
+{
+  const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(nx) * ny * nz;
+  if (t >= total)
+    return;
+  const int i = static_cast<int>(t % nx);
+  const size_t r = t / nx;
+  const int j = static_cast<int>(r % ny), k = static_cast<int>(r / ny);
+  const int nny = ny + 1;
+  auto node = [&](int a, int b, int c) {
+    return reinterpret_cast<const float*>(static_cast<const char*>(vol.ptr) + (static_cast<size_t>(c) * nny + b) * vol.pitch)[a];
+  };
+  cells[2 * t] = make_float4(node(i, j, k), node(i + 1, j, k), node(i, j + 1, k), node(i + 1, j + 1, k));
+  cells[2 * t + 1] = make_float4(node(i, j, k + 1), node(i + 1, j, k + 1), node(i, j + 1, k + 1), node(i + 1, j + 1, k + 1));
+}
+
 // DDA grid: RaycastUsingDDA::setExists (raycast_using_dda.h:230-235) for every map point.
 __global__ void dda_key_kernel(const mcl3dl_point* __restrict__ pts, uint32_t n, DdaGridDev g,
                                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
@@ -278,6 +316,9 @@ struct DeviceCtx
   DevBuf raw_pts;  // map points in original order (KD-tree raycaster only)
   DevBuf near_lik, near_kd;  // near-field bits (MCL3DL_NEAR_BITS builds)
   DevBuf nnf_dir, nnf_cand;  // NN field: directory + candidate lists
+  DevBuf fld_cells;          // field mode: 8 corner distances per lattice cell
+  cudaPitchedPtr fld_nodes{};  // field mode: node volume (cudaMalloc3D)
+  bool fld_nodes_valid = false;
   float near_kd_r = 0.0f;            // radius the KD field was built for
   size_t map_bytes = 0;
   // per-update I/O
@@ -342,6 +383,8 @@ struct mcl3dl_engine
   int update_one_sync = 1;  // mcl3dl_measure_update on ONE device: normalise from the device-side total, one host
                             // synchronise instead of two (MCL3DL_UPDATE_ONE_SYNC=1; written without GPU time left in
                             // round 1: off until the f2 parity tests have run with it)
+  int field_mode = 0;  // 1: the likelihood model reads the trilinear distance volume (opt-in, inexact; MCL3DL_LIK_MODE=field)
+  size_t field_max_bytes = size_t(24) << 30;  // MCL3DL_FIELD_MAX_MB
   int nnf = 1;  // stage the NN field (exact per-voxel candidate lists) and use lik_kernel_nf; MCL3DL_NNF=0: the CSR window kernels
   size_t nnf_max_bytes = size_t(32) << 30;  // MCL3DL_NNF_MAX_MB: directory + candidates above this -> no field
   uint64_t nnf_bytes = 0, nnf_cands = 0, nnf_overflow_cells = 0;
@@ -549,6 +592,106 @@ int launch_lik_nf(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, si
   }
 }
 
+// ---- field mode: staging and launch
+// Stage (or re-stage from host node values) the distance volume of one device.  host_nodes == nullptr: the nodes are
+// computed on the device from the NN field.  Either way the node volume is a cudaMalloc3D allocation and host <-> device
+// moves go through cudaMemcpy3D (north_star: "staged once to HBM via cudaMemcpy3D").
+int stage_field(mcl3dl_engine* eng, DeviceCtx& c, const float* host_nodes)
+{
+  const NnFieldDev& f = c.nn.field;
+  if (!f.dir)
+    return MCL3DL_ERR_INVALID_ARG;  // field mode sits on the NN field's lattice
+  CK(cudaSetDevice(c.dev));
+  const int nnx = f.nx + 1, nny = f.ny + 1, nnz = f.nz + 1;
+  const size_t n_cells = static_cast<size_t>(f.nx) * f.ny * f.nz;
+  if (n_cells * 32 > eng->field_max_bytes)
+    return MCL3DL_ERR_TOO_LARGE;
+  cudaStream_t st = c.stream;
+  if (!c.fld_nodes.ptr)
+  {
+    const cudaExtent ext = make_cudaExtent(static_cast<size_t>(nnx) * sizeof(float), nny, nnz);
+    CK(cudaMalloc3D(&c.fld_nodes, ext));
+  }
+  int rc = reserve(eng, c.fld_cells, n_cells * 32);
+  if (rc != MCL3DL_OK)
+    return rc;
+  const float clamp = f.radius;
+  if (host_nodes)
+  {
+    cudaMemcpy3DParms cp{};
+    cp.srcPtr = make_cudaPitchedPtr(const_cast<float*>(host_nodes), static_cast<size_t>(nnx) * sizeof(float), nnx, nny);
+    cp.dstPtr = c.fld_nodes;
+    cp.extent = make_cudaExtent(static_cast<size_t>(nnx) * sizeof(float), nny, nnz);
+    cp.kind = cudaMemcpyHostToDevice;
+    CK(cudaMemcpy3DAsync(&cp, st));
+  }
+  else
+  {
+    LikDev lp = eng->likdev;
+    lp.rpad = f.radius;
+    lp.r2 = static_cast<float>(static_cast<double>(clamp) * static_cast<double>(clamp));
+    const size_t total = static_cast<size_t>(nnx) * nny * nnz;
+    field_nodes_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(c.nn, lp, c.fld_nodes, nnx, nny, nnz, clamp);
+    CK(cudaGetLastError());
+    eng->launches++;
+  }
+  field_expand_kernel<<<static_cast<unsigned>((n_cells + 255) / 256), 256, 0, st>>>(c.fld_nodes, f.nx, f.ny, f.nz,
+                                                                                    static_cast<float4*>(c.fld_cells.p));
+  CK(cudaGetLastError());
+  eng->launches++;
+  CK(cudaStreamSynchronize(st));
+  FieldDev d{};
+  d.cells = static_cast<const float4*>(c.fld_cells.p);
+  d.nx = f.nx;
+  d.ny = f.ny;
+  d.nz = f.nz;
+  d.ox = f.ox;
+  d.oy = f.oy;
+  d.oz = f.oz;
+  d.inv_e = f.inv_e;
+  d.clamp = clamp;
+  c.nn.fld = d;
+  c.fld_nodes_valid = true;
+  return MCL3DL_OK;
+}
+
+template <int TPP>
+int launch_lik_field_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, int P, const float4* scan, int N,
+                       mcl3dl_result* out, int beam_defaults, cudaStream_t st, const RecordSink& sink)
+{
+  constexpr int PPB = kBlockThreads / TPP;
+  const int groups = (P + PPB - 1) / PPB;
+  const int grid = std::max(1, std::min(groups, c.sm_count * kNfCtasPerSm));
+  const size_t bytes = static_cast<size_t>(N) * 16;
+  const bool staged = bytes <= static_cast<size_t>(kMaxStagedBytes) / 2 && (PPB >= 4 || groups > grid);
+  if (staged)
+  {
+    if (int rc = opt_in_smem(eng, c, lik_kernel_field<TPP, true>, kMaxStagedBytes / 2)) return rc;
+    lik_kernel_field<TPP, true><<<grid, kBlockThreads, bytes, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr(), sink);
+  }
+  else
+    lik_kernel_field<TPP, false><<<grid, kBlockThreads, 0, st>>>(poses, P, scan, N, c.nn, eng->likdev, out, beam_defaults, c.stats_ptr(), sink);
+  CK(cudaGetLastError());
+  eng->launches++;
+  return MCL3DL_OK;
+}
+
+int launch_lik_field(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
+                     mcl3dl_result* out, int beam_defaults, cudaStream_t st, const RecordSink& sink)
+{
+  const float4* s4 = reinterpret_cast<const float4*>(scan);
+  const int p = static_cast<int>(P), n = static_cast<int>(N);
+  switch (pick_tpp_nf(P, N, c.sm_count))
+  {
+    case 8: return launch_lik_field_t<8>(eng, c, poses, p, s4, n, out, beam_defaults, st, sink);
+    case 16: return launch_lik_field_t<16>(eng, c, poses, p, s4, n, out, beam_defaults, st, sink);
+    case 32: return launch_lik_field_t<32>(eng, c, poses, p, s4, n, out, beam_defaults, st, sink);
+    case 64: return launch_lik_field_t<64>(eng, c, poses, p, s4, n, out, beam_defaults, st, sink);
+    case 128: return launch_lik_field_t<128>(eng, c, poses, p, s4, n, out, beam_defaults, st, sink);
+    default: return launch_lik_field_t<256>(eng, c, poses, p, s4, n, out, beam_defaults, st, sink);
+  }
+}
+
 PlShape pick_pl_shape(size_t P, size_t N, int sm_count)
 {
   // Every warp walks `ppl` consecutive scan points for 32 particles.  The kernels hold 4 CTAs = 32 warps per SM
@@ -618,6 +761,8 @@ int launch_beam_pl(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, s
 int launch_lik(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
                mcl3dl_result* out, int beam_defaults, cudaStream_t st, const RecordSink& sink)
 {
+  if (eng->field_mode && c.nn.fld.cells)
+    return launch_lik_field(eng, c, poses, P, scan, N, out, beam_defaults, st, sink);
   if (eng->mapping != 0 && c.nn.field.dir)
     return launch_lik_nf(eng, c, poses, P, scan, N, out, beam_defaults, st, sink);
   const float4* s4 = reinterpret_cast<const float4*>(scan);
@@ -1196,6 +1341,10 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     eng->update_one_sync = std::atoi(v) != 0;
   if (const char* v = std::getenv("MCL3DL_NNF"))
     eng->nnf = std::atoi(v) != 0;
+  if (const char* v = std::getenv("MCL3DL_LIK_MODE"))
+    eng->field_mode = std::strcmp(v, "field") == 0;
+  if (const char* v = std::getenv("MCL3DL_FIELD_MAX_MB"))
+    eng->field_max_bytes = static_cast<size_t>(std::max(std::atol(v), 1L)) << 20;
   if (const char* v = std::getenv("MCL3DL_NNF_MAX_MB"))
     eng->nnf_max_bytes = static_cast<size_t>(std::max(std::atol(v), 1L)) << 20;
   if (const char* o = std::getenv("MCL3DL_OVERLAP"))
@@ -1260,9 +1409,11 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     free_buf(c.x_ticket);
     for (DevBuf* b : {&c.r_states[0], &c.r_states[1], &c.r_prob, &c.r_accum, &c.r_poses, &c.r_extra})
       free_buf(*b);
-    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.nnf_dir, &c.nnf_cand, &c.d_poses,
+    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.nnf_dir, &c.nnf_cand, &c.fld_cells, &c.d_poses,
                       &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart})
       free_buf(*b);
+    if (c.fld_nodes.ptr)
+      cudaFree(c.fld_nodes.ptr);
     if (c.h_pinned)
       cudaFreeHost(c.h_pinned);
     for (auto& e : c.ev)
@@ -1312,8 +1463,16 @@ int mcl3dl_set_map(mcl3dl_engine* eng, const mcl3dl_point* pts, size_t n, uint64
   eng->info.n_points = n;
   for (DeviceCtx& c : eng->devs)
   {
-    const int rc = build_map_on_device(eng, c, pts, n);
+    int rc = build_map_on_device(eng, c, pts, n);
     if (rc != MCL3DL_OK)
+      return rc;
+    c.fld_nodes_valid = false;  // a volume of the previous map is stale
+    if (c.fld_nodes.ptr)
+    {
+      cudaFree(c.fld_nodes.ptr);
+      c.fld_nodes = cudaPitchedPtr{};
+    }
+    if (eng->field_mode && eng->has_lik && (rc = stage_field(eng, c, nullptr)) != MCL3DL_OK)
       return rc;
   }
   eng->has_map = true;
@@ -1363,6 +1522,87 @@ int mcl3dl_near_field_info(const mcl3dl_engine* eng, int32_t k_out[2], uint64_t 
   {
     k_out[i] = eng->near_info_k[i];
     bytes_out[i] = eng->near_info_bytes[i];
+  }
+  return MCL3DL_OK;
+}
+
+int mcl3dl_field_mode(mcl3dl_engine* eng, int enable)
+{
+  if (!eng)
+    return MCL3DL_ERR_INVALID_ARG;
+  if (!enable)
+  {
+    eng->field_mode = 0;
+    return MCL3DL_OK;
+  }
+  if (eng->has_map)
+  {
+    if (!eng->has_lik)
+      return MCL3DL_ERR_INVALID_ARG;
+    for (DeviceCtx& c : eng->devs)
+      if (!c.fld_nodes_valid)
+      {
+        const int rc = stage_field(eng, c, nullptr);
+        if (rc != MCL3DL_OK)
+          return rc;
+      }
+  }
+  eng->field_mode = 1;  // (no map yet: the next set_map stages the volume)
+  return MCL3DL_OK;
+}
+
+int mcl3dl_field_nodes(mcl3dl_engine* eng, float* nodes_out, int32_t dims_out[3], float origin_out[3], float* edge_out)
+{
+  if (!eng || !eng->has_map || eng->devs.empty())
+    return MCL3DL_ERR_NO_MAP;
+  DeviceCtx& c = eng->devs[0];
+  const NnFieldDev& f = c.nn.field;
+  if (!f.dir)
+    return MCL3DL_ERR_INVALID_ARG;
+  const int nnx = f.nx + 1, nny = f.ny + 1, nnz = f.nz + 1;
+  if (dims_out)
+  {
+    dims_out[0] = nnx;
+    dims_out[1] = nny;
+    dims_out[2] = nnz;
+  }
+  if (origin_out)
+  {
+    origin_out[0] = f.ox;
+    origin_out[1] = f.oy;
+    origin_out[2] = f.oz;
+  }
+  if (edge_out)
+    *edge_out = f.e;
+  if (!nodes_out)
+    return MCL3DL_OK;
+  if (!c.fld_nodes_valid)
+    return MCL3DL_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c.dev));
+  cudaMemcpy3DParms cp{};
+  cp.srcPtr = c.fld_nodes;
+  cp.dstPtr = make_cudaPitchedPtr(nodes_out, static_cast<size_t>(nnx) * sizeof(float), nnx, nny);
+  cp.extent = make_cudaExtent(static_cast<size_t>(nnx) * sizeof(float), nny, nnz);
+  cp.kind = cudaMemcpyDeviceToHost;
+  CK(cudaMemcpy3DAsync(&cp, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
+  return MCL3DL_OK;
+}
+
+int mcl3dl_field_upload(mcl3dl_engine* eng, const float* nodes, const int32_t dims[3])
+{
+  if (!eng || !nodes || !dims)
+    return MCL3DL_ERR_INVALID_ARG;
+  if (!eng->has_map || !eng->has_lik)
+    return MCL3DL_ERR_NO_MAP;
+  for (DeviceCtx& c : eng->devs)
+  {
+    const NnFieldDev& f = c.nn.field;
+    if (!f.dir || dims[0] != f.nx + 1 || dims[1] != f.ny + 1 || dims[2] != f.nz + 1)
+      return MCL3DL_ERR_INVALID_ARG;
+    const int rc = stage_field(eng, c, nodes);
+    if (rc != MCL3DL_OK)
+      return rc;
   }
   return MCL3DL_OK;
 }

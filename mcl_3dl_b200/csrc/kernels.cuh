@@ -736,6 +736,109 @@ __global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// Field-mode likelihood kernel (opt-in, mcl3dl_field_mode; device_funcs.cuh: FieldDev): same mapping and reductions as
+// lik_kernel_nf, but an eval is the transform plus ONE 32-byte gather (the 8 corner distances of its lattice cell) and a
+// trilinear blend — BASELINE.json north_star's literal kernel.  Its scores deviate from the reference's exact
+// nearest-neighbour distances (reported by bench.py / tests, not gated); 32 algorithmic bytes per eval.
+template <int TPP, bool STAGED>
+__global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
+    lik_kernel_field(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N, NnGridDev g,
+                     LikDev lp, mcl3dl_result* __restrict__ out, int write_beam_defaults,
+                     unsigned long long* __restrict__ stats, RecordSink sink)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ float red_f[kBlockThreads / 32];
+  __shared__ uint32_t red_u[3 * kBlockThreads / 32];
+  if (STAGED && N > 0)
+    stage_issue(smem_raw, scan, static_cast<uint32_t>(N) * 16u, &bar);
+  constexpr int PPB = kBlockThreads / TPP;
+  const int sub = threadIdx.x / TPP;
+  const int l = threadIdx.x % TPP;
+  const int n_groups = (P + PPB - 1) / PPB;
+  uint32_t st_rows = 0;
+  bool staged_ready = !(STAGED && N > 0);
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
+  {
+    const int p = grp * PPB + sub;
+    const bool live = p < P;
+    float score = 0.0f;
+    uint32_t cnt = 0;
+    F3 pos;
+    Q4 rn;
+    pos.x = pos.y = pos.z = 0.0f;
+    rn.x = rn.y = rn.z = 0.0f;
+    rn.w = 1.0f;
+    if (live)
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(poses + p));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(poses + p) + 1);
+      pos.x = a.x;
+      pos.y = a.y;
+      pos.z = a.z;
+      Q4 q;
+      q.x = b.x;
+      q.y = b.y;
+      q.z = b.z;
+      q.w = b.w;
+      rn = qnormalized(q);  // state_6dof.h:217
+    }
+    if (!staged_ready)
+    {
+      stage_wait(&bar);
+      staged_ready = true;
+    }
+    const float4* pts = STAGED ? reinterpret_cast<const float4*>(smem_raw) : scan;
+    if (live)
+    {
+      for (int j = l; j < N; j += kNfU * TPP)
+      {
+        float d[kNfU];
+#pragma unroll
+        for (int u = 0; u < kNfU; ++u)
+        {
+          d[u] = lp.match_dist_min;  // "no neighbour"
+          if (j + u * TPP < N)
+          {
+            const float4 sp = STAGED ? pts[j + u * TPP] : __ldg(pts + j + u * TPP);
+            F3 v;
+            v.x = sp.x;
+            v.y = sp.y;
+            v.z = sp.z;
+            const F3 t = transform_point(rn, pos, v);
+            d[u] = field_dist(g.fld, fmul(t.x, g.wx), fmul(t.y, g.wy), fmul(t.z, g.wz));
+            ++st_rows;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kNfU; ++u)
+          if (d[u] < lp.match_dist_min)
+          {
+            // likelihood.cpp:128-133 with the interpolated distance in place of sqrt(sqdist[0])
+            const float dist = fsub(lp.match_dist_min, fmaxf(d[u], lp.match_dist_flat));
+            if (!(dist < 0.0f))
+            {
+              score = fadd(score, fmul(dist, lp.match_weight));
+              cnt++;
+            }
+          }
+      }
+    }
+    nf_reduce<TPP>(score, cnt, red_f, red_u);
+    if (live && l == 0)
+      sink_store_lik(sink, out, p, (N == 0) ? 1.0f : score, cnt, write_beam_defaults);
+  }
+  if (!staged_ready)
+    stage_wait(&bar);
+  if (stats)
+  {
+    const uint32_t r = warp_sum_u32(st_rows);
+    if ((threadIdx.x & 31) == 0)
+      atomicAdd(stats + 0, static_cast<unsigned long long>(r) * 4ull);  // counted as 8-byte index entries: 32 B per eval
+  }
+}
+
 template <int TPP, bool STAGED>
 __global__ void __launch_bounds__(kBlockThreads)
     beam_kernel(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N,

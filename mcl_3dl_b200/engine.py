@@ -75,7 +75,7 @@ class WorkStats(C.Structure):
 EXPORTED_SYMBOLS = ["mcl3dl_measure_update", "mcl3dl_collect_stats", "mcl3dl_read_stats", "mcl3dl_abi_version", "mcl3dl_create", "mcl3dl_destroy", "mcl3dl_set_map", "mcl3dl_set_params",
                     "mcl3dl_measure", "mcl3dl_measure_device", "mcl3dl_beam_status",
                     "mcl3dl_beam_params_from_reference", "mcl3dl_get_map_info", "mcl3dl_last_timing",
-                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_nn_field_info", "mcl3dl_collect_timing",
+                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_nn_field_info", "mcl3dl_field_mode", "mcl3dl_field_nodes", "mcl3dl_field_upload", "mcl3dl_collect_timing",
                     "mcl3dl_exchange_create", "mcl3dl_exchange_open", "mcl3dl_measure_exchange_device", "mcl3dl_exchange_current",
                     "mcl3dl_particles_set", "mcl3dl_particles_get", "mcl3dl_particles_predict",
                     "mcl3dl_particles_measure_update", "mcl3dl_particles_resample"]
@@ -132,6 +132,9 @@ def load_library(path=None):
     L.mcl3dl_exchange_current.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_int)]
     L.mcl3dl_near_field_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
     L.mcl3dl_nn_field_info.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.mcl3dl_field_mode.argtypes = [vp, C.c_int]
+    L.mcl3dl_field_nodes.argtypes = [vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.mcl3dl_field_upload.argtypes = [vp, vp, C.POINTER(C.c_int32)]
     assert L.mcl3dl_abi_version() == 3
     _LIBS[path] = L
     return L
@@ -211,6 +214,25 @@ class Engine:
         v = (C.c_uint64 * 4)()
         self._check(self.L.mcl3dl_nn_field_info(self.h, v))
         return {"bytes": int(v[0]), "candidates": int(v[1]), "overflow_cells": int(v[2]), "voxel_edge": v[3] * 1e-6}
+
+    def field_mode(self, enable=True):
+        """Opt-in, inexact: route the likelihood model through the trilinear distance volume (include/mcl3dl_b200.h)."""
+        self._check(self.L.mcl3dl_field_mode(self.h, 1 if enable else 0))
+
+    def field_nodes(self, download=True):
+        """(nodes float32[nz, ny, nx] or None, origin[3], edge) of the field-mode lattice (rescaled space)."""
+        dims, org, edge = (C.c_int32 * 3)(), (C.c_float * 3)(), C.c_float(0)
+        self._check(self.L.mcl3dl_field_nodes(self.h, None, dims, org, C.byref(edge)))
+        nodes = None
+        if download:
+            nodes = np.zeros((dims[2], dims[1], dims[0]), dtype=np.float32)
+            self._check(self.L.mcl3dl_field_nodes(self.h, _ptr(nodes), dims, org, C.byref(edge)))
+        return nodes, np.array(list(org), np.float32), float(edge.value), tuple(int(d) for d in dims)
+
+    def field_upload(self, nodes):
+        nodes = np.ascontiguousarray(nodes, dtype=np.float32)
+        dims = (C.c_int32 * 3)(nodes.shape[2], nodes.shape[1], nodes.shape[0])
+        self._check(self.L.mcl3dl_field_upload(self.h, _ptr(nodes), dims))
 
     def measure(self, poses, lik_pts=None, beam_pts=None, origins=None, out=None):
         poses = np.ascontiguousarray(poses, dtype=POSE)

@@ -444,3 +444,35 @@ extern "C" int hostsim_near_query(const mcl3dl_point* map, size_t n, const float
 }
 
 
+
+// Field mode: field_dist (device_funcs.cuh) over a host copy of the per-cell corner layout built from a node volume
+// (x fastest, dims = nodes per axis), exactly as engine.cu's field_expand_kernel lays it out.
+extern "C" int hostsim_field_dist(const float* nodes, const int32_t dims[3], const float origin[3], float edge, float clamp,
+                                  const float* queries_xyz, size_t nq, float* out)
+{
+  const int nx = dims[0] - 1, ny = dims[1] - 1, nz = dims[2] - 1;
+  if (nx < 1 || ny < 1 || nz < 1)
+    return -1;
+  std::vector<float4> cells(static_cast<size_t>(nx) * ny * nz * 2);
+  auto node = [&](int a, int b, int c) { return nodes[(static_cast<size_t>(c) * dims[1] + b) * dims[0] + a]; };
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < ny; ++j)
+      for (int i = 0; i < nx; ++i)
+      {
+        const size_t t = (static_cast<size_t>(k) * ny + j) * nx + i;
+        cells[2 * t] = make_float4(node(i, j, k), node(i + 1, j, k), node(i, j + 1, k), node(i + 1, j + 1, k));
+        cells[2 * t + 1] = make_float4(node(i, j, k + 1), node(i + 1, j, k + 1), node(i, j + 1, k + 1), node(i + 1, j + 1, k + 1));
+      }
+  FieldDev f{};
+  f.cells = cells.data();
+  f.nx = nx;
+  f.ny = ny;
+  f.nz = nz;
+  f.ox = origin[0];
+  f.oy = origin[1];
+  f.oz = origin[2];
+  f.inv_e = 1.0f / edge;
+  f.clamp = clamp;
+  for (size_t q = 0; q < nq; ++q) out[q] = field_dist(f, queries_xyz[3 * q], queries_xyz[3 * q + 1], queries_xyz[3 * q + 2]);
+  return 0;
+}

@@ -504,3 +504,35 @@ def test_screens_and_nn_field_randomized_differential(hostsim):
         for near, field in (((2, 1), 1), ((1, 2), 0), ((3, 1), 1)):
             got, st = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=near, field=field)
             assert got.tobytes() == ref.tobytes() and np.array_equal(st, st_ref), (seed, near, field)
+
+
+def test_field_mode_trilinear_lookup_on_host(hostsim):
+    """field_dist (the opt-in field mode's lookup, device_funcs.cuh) against a numpy trilinear interpolation of the same
+    node volume: inside the lattice to float rounding, `clamp` outside, exact at the nodes."""
+    L = C.CDLL(LIB)
+    vp, sz = C.c_void_p, C.c_size_t
+    L.hostsim_field_dist.argtypes = [vp, vp, vp, C.c_float, C.c_float, vp, sz, vp]
+    rng = np.random.default_rng(3)
+    dims = np.array([9, 7, 6], np.int32)            # nodes per axis (x, y, z)
+    nodes = rng.uniform(0.0, 0.2, (dims[2], dims[1], dims[0])).astype(np.float32)
+    org, e, clamp = np.array([-1.0, 2.0, 0.5], np.float32), np.float32(0.101), np.float32(0.2)
+    q = np.concatenate([rng.uniform(org, org + (dims - 1) * e, (500, 3)),
+                        rng.uniform(org - 1.0, org - 0.01, (20, 3)),           # outside
+                        org + np.array([[3, 2, 1], [0, 0, 0], [7, 5, 4]]) * e]).astype(np.float32)   # on nodes
+    out = np.zeros(len(q), np.float32)
+    p = lambda a: a.ctypes.data_as(vp)  # noqa: E731
+    assert L.hostsim_field_dist(p(nodes), p(dims), p(org), e, clamp, p(q), len(q), p(out)) == 0
+    t = (q.astype(np.float64) - org) / np.float64(e)
+    i = np.floor(t).astype(int)
+    inside = ((i >= 0) & (i < dims - 1)).all(axis=1)
+    f = t - i
+    want = np.full(len(q), clamp, np.float64)
+    for n in np.nonzero(inside)[0]:
+        x, y, z = i[n]
+        c = nodes[z:z + 2, y:y + 2, x:x + 2].astype(np.float64)
+        cz = c[0] * (1 - f[n, 2]) + c[1] * f[n, 2]
+        cy = cz[0] * (1 - f[n, 1]) + cz[1] * f[n, 1]
+        want[n] = cy[0] * (1 - f[n, 0]) + cy[1] * f[n, 0]
+    assert inside[:500].all() and not inside[500:520].any()
+    assert np.allclose(out, want, rtol=0, atol=2e-5)
+    assert np.allclose(out[-3:], [nodes[1, 2, 3], nodes[0, 0, 0], nodes[4, 5, 7]], atol=2e-5)
