@@ -579,6 +579,64 @@ def e2e_leg(cx, workload, raycaster, steps, live, fused=True):
     return out
 
 
+def resident_leg(cx, workload, steps):
+    """Scope row f3: whole localisation cycles on the engine's RESIDENT particle set (N = 1).  Every cycle = predict
+    (odometry step) + measurement update of both models with the weight update + pose estimate (biased mean, max,
+    covariance) + resampling, all on the device: only the scans and an odometry pair go in, only summaries come out.
+    Host wall clock around the four C-ABI calls, L2 flushed before every cycle."""
+    import torch
+    from mcl_3dl_b200 import engine
+    global USE_DDA
+    USE_DDA = True
+    n_map, P, n_lik, n_beam, spread, dda, _ = WORKLOADS[workload]
+    s, dda, _, _ = build_scene(workload, 0, 1)
+    eng = engine.Engine((cx.local,))
+    eng.set_map(s["map"], engine.LikParams(dist_weight=DIST_WEIGHT),
+                engine.beam_params_from_reference(num_points_default=max(n_beam, 1), dda_grid_size=dda))
+    st = np.zeros(P, dtype=synth.STATE)
+    st["pos"] = np.stack([s["particles"]["px"], s["particles"]["py"], s["particles"]["pz"]], axis=1)
+    st["rot"] = np.stack([s["particles"][k] for k in ("qx", "qy", "qz", "qw")], axis=1)
+    eng.particles_set(st, np.full(P, 1.0 / P, np.float32))
+    a = synth.make_poses([[0, 0, 0]], [[0, 0, 0, 1]])
+    b = synth.make_poses([[0.02, 0, 0]], synth.quat_from_rpy([[0, 0, 0.01]]))
+    sp, sr = np.array([0.05, 0.05, 0.01], np.float32), np.array([0.005, 0.005, 0.02], np.float32)
+    parts = {"predict": 0.0, "measure_update": 0.0, "estimate": 0.0, "resample": 0.0}
+
+    def cycle(k, timed):
+        t0 = time.perf_counter()
+        eng.particles_predict(a, b, 0.1, 10.0, 10.0)
+        t1 = time.perf_counter()
+        summ = eng.particles_measure_update(s["lik"], s["beam"], s["origins"], 0.05)
+        t2 = time.perf_counter()
+        est = eng.particles_estimate(None)
+        t3 = time.perf_counter()
+        eng.particles_resample(sp, sr, 0.5, seed=1000 + k)
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        if timed:
+            for name, dt in zip(parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                parts[name] += dt
+        return summ, est, t4 - t0
+    for k in range(3):
+        cycle(k, False)
+    tot = 0.0
+    for k in range(steps):
+        cx.flush.fill_(1)
+        torch.cuda.synchronize()
+        summ, est, dt = cycle(10 + k, True)
+        tot += dt
+    eng.close()
+    n_org = len(s["origins"])
+    return {"metric": metric_name(n_lik), "value": P * n_lik * steps / tot, "unit": "evals/s", "ms_per_cycle": 1e3 * tot / steps,
+            "ms_per_call": {k: 1e3 * v / steps for k, v in parts.items()}, "steps": steps,
+            "h2d_bytes_per_cycle": n_lik * 16 + n_beam * 16 + n_org * 12 + 64, "d2h_bytes_per_cycle": 24 + 256 + 68,
+            "cycle": "mcl3dl_particles_predict + _measure_update (both models, odometry-error term, normalise, entropy) + "
+                     "_estimate (biased mean, max, 6x6 covariance) + _resample, %d particles resident on the device" % P,
+            "last_summary": {"entropy": summ["entropy"], "kept": summ["kept"], "mean_xy": [float(est["mean_biased"]["px"][0]),
+                                                                                           float(est["mean_biased"]["py"][0])]},
+            "config": config_dict(workload, s, P, n_lik, n_beam, spread, dda)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -685,6 +743,11 @@ def main():
                 secondaries[name] = r2
             except Exception as exc:
                 secondaries[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        if world == 1:
+            try:
+                secondaries["c5_resident"] = resident_leg(cx, "c5", max(10, min(args.steps, 30)))
+            except Exception as exc:
+                secondaries["c5_resident"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         USE_DDA = args.raycaster == "dda"
 
     if rank == 0:

@@ -219,8 +219,8 @@ void mcl3dl_beam_params_from_reference(mcl3dl_beam_params* out,
 
 int mcl3dl_get_map_info(const mcl3dl_engine*, mcl3dl_map_info* out);
 
-/* ---- Resident particle set (PREPARED in round 1 after the GPU budget was spent: the per-particle
- * arithmetic is verified on the host bit for bit against the oracle, the kernels and this plumbing have not run yet).
+/* ---- Resident particle set (the per-particle arithmetic is verified on the host bit for bit
+ * against the oracle, the kernels by tests/test_gpu_resident.py on a B200).
  * The particles of pf::ParticleFilter<State6DOF> stay in device memory between updates, so an update moves only the
  * scans and the odometry in and a summary out.  Engines with exactly one device.
  *
@@ -258,6 +258,27 @@ int mcl3dl_particles_measure_update(mcl3dl_engine*, const mcl3dl_point* lik_pts,
  * particles that tie in the accumulated probability are taken by lowest index instead of std::sort's order. */
 int mcl3dl_particles_resample(mcl3dl_engine*, const float sigma_pos[3], const float sigma_rpy[3], float initial_frac,
                               uint64_t seed);
+
+/* The pose estimate the node takes from the filter after every measurement, on the resident set
+ * (src/mcl_3dl.cpp:428-452,704-724): pf_->bias(bias_func) + pf_->expectationBiased() (pf.h:246-251,294-303;
+ * ParticleWeightedMeanQuat, state_6dof.h:316-355), pf_->max() (pf.h:361-374) and pf_->covariance(1.0, .) (pf.h:304-360,
+ * State6DOF::covElement state_6dof.h:162-184).  Only this summary leaves the device.
+ *   state_prev == NULL: bias 1 for every particle (the node's branch for more particles than num_particles, :428-434);
+ *   otherwise bias = NormalLikelihood(bias_var_dist)(|pos - prev.pos|) * NormalLikelihood(bias_var_ang)(angle) + 1e-6.
+ * Sums are accumulated in double with a fixed tree (the reference: sequential float), so the values agree with the
+ * reference to ~1e-5 relative.  Documented departures: the covariance always uses every particle (the reference
+ * subsamples randomly above num_particles "to reduce calculation cost", and its expectation(1.0) / covariance(1.0) stop
+ * early if the float running total of the probabilities passes 1.0 before the last particle). */
+typedef struct
+{
+  mcl3dl_pose mean_biased;  /* expectationBiased(): pos, rot as built by Quat(front, up) — normalise as the node does (:462) */
+  mcl3dl_pose max_state;    /* max(): pos + raw rot of the first particle with the largest probability */
+  uint32_t max_index;
+  float weight_sum_biased;  /* sum of probability * bias */
+  float cov[36];            /* row-major 6 x 6: x y z roll pitch yaw */
+} mcl3dl_estimate;
+int mcl3dl_particles_estimate(mcl3dl_engine*, const mcl3dl_pose* state_prev, float bias_var_dist, float bias_var_ang,
+                              mcl3dl_estimate* out);
 
 /* Record exchange over peer memory for the one-process-per-GPU layout (particles sharded, ONE gather of the
  * 24-byte records, then the unchanged weight update of include/mcl_3dl/pf.h:252-279 on the full array).  There is no

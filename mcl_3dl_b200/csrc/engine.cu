@@ -336,7 +336,7 @@ struct DeviceCtx
   std::vector<const void*> smem_opted;  // kernels already opted in to large dynamic shared memory on this device
   // resident particle set (mcl3dl_particles_*): two state buffers (resampling writes the other one), probabilities,
   // prefix sum + pstep, the packed poses / odometry-error factors the measurement kernels read
-  DevBuf r_states[2], r_prob, r_accum, r_poses, r_extra;
+  DevBuf r_states[2], r_prob, r_accum, r_poses, r_extra, r_est;  // r_est: EstHeader + per-CTA partial sums
   size_t r_n = 0;
   int r_cur = 0;
   uint32_t r_calls = 0;
@@ -1407,7 +1407,7 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     xchg_close(c);
     free_buf(c.xchg);
     free_buf(c.x_ticket);
-    for (DevBuf* b : {&c.r_states[0], &c.r_states[1], &c.r_prob, &c.r_accum, &c.r_poses, &c.r_extra})
+    for (DevBuf* b : {&c.r_states[0], &c.r_states[1], &c.r_prob, &c.r_accum, &c.r_poses, &c.r_extra, &c.r_est})
       free_buf(*b);
     for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.nnf_dir, &c.nnf_cand, &c.fld_cells, &c.d_poses,
                       &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart})
@@ -1869,6 +1869,74 @@ int mcl3dl_particles_measure_update(mcl3dl_engine* eng, const mcl3dl_point* lik_
   summary->kept = total_f > 0.0f ? 1 : 0;
   summary->entropy = summary->kept ? static_cast<float>(-w2.sum) : 0.0f;
   summary->max_index = summary->kept ? w2.best_i : 0;
+  return MCL3DL_OK;
+}
+
+int mcl3dl_particles_estimate(mcl3dl_engine* eng, const mcl3dl_pose* prev, float bias_var_dist, float bias_var_ang,
+                              mcl3dl_estimate* out)
+{
+  if (!eng || eng->devs.size() != 1 || !out)
+    return MCL3DL_ERR_INVALID_ARG;
+  DeviceCtx& c = eng->devs[0];
+  if (c.r_n == 0)
+    return MCL3DL_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c.dev));
+  cudaStream_t st = c.stream;
+  const uint32_t n = static_cast<uint32_t>(c.r_n);
+  const int grid = static_cast<int>(std::min<size_t>((c.r_n + 255) / 256, static_cast<size_t>(c.sm_count) * 4));
+  const size_t part_doubles = static_cast<size_t>(grid) * (kEstSums + 2);
+  const size_t hdr = (sizeof(EstHeader) + 255) & ~size_t(255);
+  int rc;
+  if ((rc = reserve(eng, c.r_est, hdr + part_doubles * sizeof(double))) || (rc = reserve_pinned(eng, c, sizeof(EstHeader) + sizeof(PfState) + 64)))
+    return rc;
+  BiasDev b{};
+  if (prev)
+  {
+    b.enabled = 1;
+    b.prev_pos[0] = prev->px;
+    b.prev_pos[1] = prev->py;
+    b.prev_pos[2] = prev->pz;
+    // state_prev_.rot_.inv() = conj() / dot(*this), quat.h:187-190 (operator/(s) multiplies by float(1.0 / s))
+    const float d = prev->qx * prev->qx + prev->qy * prev->qy + prev->qz * prev->qz + prev->qw * prev->qw;
+    const float id = static_cast<float>(1.0 / d);
+    b.prev_inv = Q4{-prev->qx * id, -prev->qy * id, -prev->qz * id, prev->qw * id};
+    // NormalLikelihood<float>(sigma): a_ = float(1 / sqrt(2 pi s^2)), sq2_ = float(2 s^2), nd.h:45-49
+    const double sl = bias_var_dist, sa = bias_var_ang;
+    b.lin_a = static_cast<float>(1.0 / std::sqrt(2.0 * M_PI * sl * sl));
+    b.lin_sq2 = static_cast<float>(sl * sl * 2.0);
+    b.ang_a = static_cast<float>(1.0 / std::sqrt(2.0 * M_PI * sa * sa));
+    b.ang_sq2 = static_cast<float>(sa * sa * 2.0);
+  }
+  EstHeader* h = static_cast<EstHeader*>(c.r_est.p);
+  double* parts = reinterpret_cast<double*>(static_cast<char*>(c.r_est.p) + hdr);
+  const PfState* states = static_cast<const PfState*>(c.r_states[c.r_cur].p);
+  const float* probs = static_cast<const float*>(c.r_prob.p);
+  pf_est_pass1_kernel<<<grid, 256, 0, st>>>(states, probs, n, b, parts);
+  pf_est_finish1_kernel<<<1, 32, 0, st>>>(parts, grid, h);
+  pf_est_pass2_kernel<<<grid, 256, 0, st>>>(states, probs, n, h, parts);
+  pf_est_finish2_kernel<<<1, 32, 0, st>>>(parts, grid, h);
+  CK(cudaGetLastError());
+  eng->launches += 4;
+  char* hp = static_cast<char*>(c.h_pinned);
+  CK(cudaMemcpyAsync(hp, h, sizeof(EstHeader), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  EstHeader hh;
+  std::memcpy(&hh, hp, sizeof(hh));
+  // the state of the best particle (one 68-byte read, after the index is known)
+  PfState best{};
+  if (hh.max_index < n)
+  {
+    CK(cudaMemcpyAsync(hp + sizeof(EstHeader), states + hh.max_index, sizeof(PfState), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::memcpy(&best, hp + sizeof(EstHeader), sizeof(best));
+  }
+  std::memset(out, 0, sizeof(*out));
+  out->mean_biased = mcl3dl_pose{hh.mean_b_pos[0], hh.mean_b_pos[1], hh.mean_b_pos[2], 0.0f,
+                                 hh.mean_b_rot[0], hh.mean_b_rot[1], hh.mean_b_rot[2], hh.mean_b_rot[3]};
+  out->max_state = mcl3dl_pose{best.pos[0], best.pos[1], best.pos[2], 0.0f, best.rot[0], best.rot[1], best.rot[2], best.rot[3]};
+  out->max_index = hh.max_index;
+  out->weight_sum_biased = hh.weight_sum_biased;
+  std::memcpy(out->cov, hh.cov, sizeof(hh.cov));
   return MCL3DL_OK;
 }
 

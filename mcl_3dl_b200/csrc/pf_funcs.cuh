@@ -1,7 +1,7 @@
-// pf_funcs.cuh — per-particle pieces of scope row f3: motion prediction, systematic resampling and the
-// State6DOF noise, as per-thread device functions.  GROUNDWORK: nothing in the engine calls them yet (a resident
-// particle set, its kernels and its C ABI are round-2 work); they are compiled for the host by tests/hostsim and
-// checked there against the oracle pieces that are pinned bit for bit to the reference build (tests/test_hostsim.py).
+// pf_funcs.cuh — per-particle pieces of scope row f3: motion prediction, systematic resampling, the
+// State6DOF noise and the terms of the pose estimate, as per-thread device functions called by the kernels of
+// pf_kernels.cuh (the resident particle set, mcl3dl_particles_*).  They are also compiled for the host by tests/hostsim
+// and checked there against the oracle pieces that are pinned bit for bit to the reference build (tests/test_hostsim.py).
 //
 // Float rules as in device_math.cuh: explicit round-to-nearest operations in the reference's operand order.
 // sinf / cosf / logf are the device's own (a few ulp from glibc's): on the GPU predict() and the noise quaternion are
@@ -281,6 +281,127 @@ __device__ __forceinline__ void pf_noise6(uint64_t seed, uint32_t index, uint32_
     const float phi = fmul(6.283185307179586f, u01(w[2 * pair + 1]));
     org[2 * pair] = sigma[2 * pair] == 0.0f ? 0.0f : fmul(fmul(rad, cosf(phi)), sigma[2 * pair]);
     org[2 * pair + 1] = sigma[2 * pair + 1] == 0.0f ? 0.0f : fmul(fmul(rad, sinf(phi)), sigma[2 * pair + 1]);
+  }
+}
+
+// ---- pose estimate (src/mcl_3dl.cpp:428-452,704-724): per-particle terms
+// The bias of pf_->bias(bias_func), mcl_3dl.cpp:436-449: NormalLikelihood(bias_var_dist)(|pos - prev.pos|) *
+// NormalLikelihood(bias_var_ang)(angle of rot * prev.rot.inv()) + 1e-6; nd.h:45-53 (a, sq2 as floats).
+struct BiasDev
+{
+  float prev_pos[3];
+  Q4 prev_inv;  // state_prev_.rot_.inv(), computed once on the host
+  float lin_a, lin_sq2, ang_a, ang_sq2;
+  int enabled;  // 0: the constant bias 1 of the global-localisation branch (mcl_3dl.cpp:428-434)
+};
+
+__device__ __forceinline__ float pf_bias(const PfState& s, const BiasDev& b)
+{
+  if (!b.enabled)
+    return 1.0f;
+  F3 d;
+  d.x = fsub(s.pos[0], b.prev_pos[0]);
+  d.y = fsub(s.pos[1], b.prev_pos[1]);
+  d.z = fsub(s.pos[2], b.prev_pos[2]);
+  const float lin_diff = __fsqrt_rn(dot3(d, d));
+  Q4 r;
+  r.x = s.rot[0];
+  r.y = s.rot[1];
+  r.z = s.rot[2];
+  r.w = s.rot[3];
+  const Q4 q = qmul(r, b.prev_inv);
+  // Quat::getAxisAng, quat.h:226-239 (only the angle)
+  float ang = 0.0f;
+  if (!(fabs(static_cast<double>(q.w)) >= 1.0 - 0.000001))
+  {
+    ang = __double2float_rn(dmul(static_cast<double>(acosf(q.w)), 2.0));
+    if (static_cast<double>(ang) > M_PI)
+      ang = __double2float_rn(dsub(static_cast<double>(ang), 2.0 * M_PI));
+  }
+  const float nl = fmul(b.lin_a, expf(fdiv(fmul(-lin_diff, lin_diff), b.lin_sq2)));
+  const float na = fmul(b.ang_a, expf(fdiv(fmul(-ang, ang), b.ang_sq2)));
+  return __double2float_rn(dadd(static_cast<double>(fmul(nl, na)), 1e-6));
+}
+
+// Quat::getRPY, quat.h:191-201: double expressions narrowed to float, float atan2 / asin
+__device__ __forceinline__ void pf_rpy(const float rot[4], float rpy[3])
+{
+  const float x = rot[0], y = rot[1], z = rot[2], w = rot[3];
+  const float ysq = fmul(y, y);
+  const float t0 = __double2float_rn(dadd(dmul(-2.0, static_cast<double>(fadd(ysq, fmul(z, z)))), 1.0));
+  const float t1 = __double2float_rn(dmul(2.0, static_cast<double>(fadd(fmul(x, y), fmul(w, z)))));
+  const double t2d = dmul(-2.0, static_cast<double>(fsub(fmul(x, z), fmul(w, y))));
+  const float t2 = __double2float_rn(fmax(-1.0, fmin(1.0, t2d)));
+  const float t3 = __double2float_rn(dmul(2.0, static_cast<double>(fadd(fmul(y, z), fmul(w, x)))));
+  const float t4 = __double2float_rn(dadd(dmul(-2.0, static_cast<double>(fadd(fmul(x, x), ysq))), 1.0));
+  rpy[0] = atan2f(t3, t4);
+  rpy[1] = asinf(t2);
+  rpy[2] = atan2f(t1, t0);
+}
+
+// the terms ParticleWeightedMeanQuat::add accumulates (state_6dof.h:327-341): pos, rot * (1,0,0), rot * (0,0,1) (RAW rot)
+__device__ __forceinline__ void pf_mean_terms(const PfState& s, float out[9])
+{
+  Q4 r;
+  r.x = s.rot[0];
+  r.y = s.rot[1];
+  r.z = s.rot[2];
+  r.w = s.rot[3];
+  F3 ex, ez;
+  ex.x = 1.0f;
+  ex.y = 0.0f;
+  ex.z = 0.0f;
+  ez.x = 0.0f;
+  ez.y = 0.0f;
+  ez.z = 1.0f;
+  const F3 front = qrot(r, ex), up = qrot(r, ez);
+  out[0] = s.pos[0];
+  out[1] = s.pos[1];
+  out[2] = s.pos[2];
+  out[3] = front.x;
+  out[4] = front.y;
+  out[5] = front.z;
+  out[6] = up.x;
+  out[7] = up.y;
+  out[8] = up.z;
+}
+
+// Quat(forward, up_raw), quat.h:59-75, from double sums (the filter's sums are float; the device sums in double)
+__device__ __forceinline__ void pf_quat_from_front_up(const double f[3], const double u[3], float q[4])
+{
+  auto unit = [](double v[3]) {
+    const double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    v[0] /= n;
+    v[1] /= n;
+    v[2] /= n;
+  };
+  double xv[3] = {f[0], f[1], f[2]};
+  unit(xv);
+  double yv[3] = {u[1] * xv[2] - u[2] * xv[1], u[2] * xv[0] - u[0] * xv[2], u[0] * xv[1] - u[1] * xv[0]};
+  unit(yv);
+  double zv[3] = {xv[1] * yv[2] - xv[2] * yv[1], xv[2] * yv[0] - xv[0] * yv[2], xv[0] * yv[1] - xv[1] * yv[0]};
+  unit(zv);
+  q[3] = static_cast<float>(sqrt(fmax(0.0, 1.0 + xv[0] + yv[1] + zv[2])) / 2.0);
+  q[0] = static_cast<float>(sqrt(fmax(0.0, 1.0 + xv[0] - yv[1] - zv[2])) / 2.0);
+  q[1] = static_cast<float>(sqrt(fmax(0.0, 1.0 - xv[0] + yv[1] - zv[2])) / 2.0);
+  q[2] = static_cast<float>(sqrt(fmax(0.0, 1.0 - xv[0] - yv[1] + zv[2])) / 2.0);
+  if (zv[1] - yv[2] > 0) q[0] = -q[0];
+  if (xv[2] - zv[0] > 0) q[1] = -q[1];
+  if (yv[0] - xv[1] > 0) q[2] = -q[2];
+}
+
+// State6DOF::covElement's differences against the expectation (state_6dof.h:162-184): position, then RPY wrapped to +-pi
+__device__ __forceinline__ void pf_cov_diff(const PfState& s, const float e_pos[3], const float e_rpy[3], float d[6])
+{
+  float rpy[3];
+  pf_rpy(s.rot, rpy);
+  for (int a = 0; a < 3; ++a)
+  {
+    d[a] = fsub(s.pos[a], e_pos[a]);
+    float diff = fsub(rpy[a], e_rpy[a]);
+    while (static_cast<double>(diff) > M_PI) diff = __double2float_rn(dsub(static_cast<double>(diff), 2 * M_PI));
+    while (static_cast<double>(diff) < -M_PI) diff = __double2float_rn(dadd(static_cast<double>(diff), 2 * M_PI));
+    d[3 + a] = diff;
   }
 }
 

@@ -1,6 +1,5 @@
 // pf_kernels.cuh — kernels of the resident particle set (scope row f3): one thread per particle around the
-// host-verified per-particle functions of pf_funcs.cuh.  Written after round 1's GPU budget was spent: the functions are
-// checked on the host bit for bit against the oracle, these kernels and their plumbing have not run on hardware yet.
+// host-verified per-particle functions of pf_funcs.cuh (first run on a B200: driver record GPUTEST_r01).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -91,6 +90,187 @@ __global__ void pf_resample_kernel(const PfState* __restrict__ in, const float* 
   }
   out[i] = s;
   out_probs[i] = __double2float_rn(ddiv(1.0, static_cast<double>(n)));
+}
+
+// ---- pose estimate on the resident set (mcl3dl_particles_estimate): pf_->bias + expectationBiased + max + covariance
+// (src/mcl_3dl.cpp:428-452,704-724; pf.h:246-251,281-374).  Two passes of double sums with a fixed tree (lanes by
+// shuffles, warps and CTAs in order), so the result is deterministic; the reference sums sequentially in float, hence
+// agreement to ~1e-5 relative, not bitwise.
+constexpr int kEstSums = 20;  // biased: w, w*pos(3), w*front(3), w*up(3); unbiased: the same ten with p
+constexpr int kCovSums = 22;  // p, 21 upper-triangle products p * d_j * d_k
+struct EstHeader
+{
+  float mean_b_pos[3], mean_b_rot[4];  // expectationBiased()
+  float mean_u_pos[3], mean_u_rpy[3];  // expectation(1.0): the centre of covariance()
+  float weight_sum_biased, weight_sum;
+  float max_prob;
+  uint32_t max_index;
+  float cov[36];
+};
+
+template <int NS>
+__device__ __forceinline__ void est_block_reduce(double (&v)[NS], double* __restrict__ slot, double (*sm)[NS])
+{
+#pragma unroll
+  for (int k = 0; k < NS; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] = dadd(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < NS; ++k) sm[warp][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < NS)
+  {
+    double t = sm[0][threadIdx.x];
+    for (int w = 1; w < 8; ++w) t = dadd(t, sm[w][threadIdx.x]);
+    slot[threadIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    pf_est_pass1_kernel(const PfState* __restrict__ states, const float* __restrict__ probs, uint32_t n, BiasDev bias,
+                        double* __restrict__ partials /* [grid][kEstSums + 2] */)
+{
+  __shared__ double sm[8][kEstSums];
+  __shared__ float sm_best[8];
+  __shared__ uint32_t sm_best_i[8];
+  double v[kEstSums];
+#pragma unroll
+  for (int k = 0; k < kEstSums; ++k) v[k] = 0.0;
+  float best = -1.0f;
+  uint32_t best_i = 0xffffffffu;
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u)
+  {
+    const PfState s = states[i];
+    const float p = probs[i];
+    const float w = fmul(p, pf_bias(s, bias));  // mean.add(p.state_, p.probability_ * p.probability_bias_), pf.h:300
+    float t[9];
+    pf_mean_terms(s, t);
+    v[0] = dadd(v[0], static_cast<double>(w));
+    v[10] = dadd(v[10], static_cast<double>(p));
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+    {
+      v[1 + k] = dadd(v[1 + k], static_cast<double>(fmul(t[k], w)));   // e1.pos_ * prob etc.: float products, as the reference
+      v[11 + k] = dadd(v[11 + k], static_cast<double>(fmul(t[k], p)));
+    }
+    if (p > best)  // pf.h:361-374: the first particle with the largest probability
+    {
+      best = p;
+      best_i = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const uint32_t oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i))
+    {
+      best = ob;
+      best_i = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0)
+  {
+    sm_best[threadIdx.x >> 5] = best;
+    sm_best_i[threadIdx.x >> 5] = best_i;
+  }
+  double* slot = partials + static_cast<size_t>(blockIdx.x) * (kEstSums + 2);
+  est_block_reduce<kEstSums>(v, slot, sm);
+  if (threadIdx.x == 0)
+  {
+    float b = sm_best[0];
+    uint32_t bi = sm_best_i[0];
+    for (int w = 1; w < 8; ++w)
+      if (sm_best[w] > b || (sm_best[w] == b && sm_best_i[w] < bi))
+      {
+        b = sm_best[w];
+        bi = sm_best_i[w];
+      }
+    slot[kEstSums] = static_cast<double>(b);
+    slot[kEstSums + 1] = static_cast<double>(bi);
+  }
+}
+
+__global__ void pf_est_finish1_kernel(const double* __restrict__ partials, int n_slots, EstHeader* __restrict__ h)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  double v[kEstSums];
+  for (int k = 0; k < kEstSums; ++k) v[k] = 0.0;
+  double best = -1.0, best_i = 4294967295.0;
+  for (int s = 0; s < n_slots; ++s)
+  {
+    const double* slot = partials + static_cast<size_t>(s) * (kEstSums + 2);
+    for (int k = 0; k < kEstSums; ++k) v[k] = dadd(v[k], slot[k]);
+    if (slot[kEstSums] > best || (slot[kEstSums] == best && slot[kEstSums + 1] < best_i))
+    {
+      best = slot[kEstSums];
+      best_i = slot[kEstSums + 1];
+    }
+  }
+  for (int a = 0; a < 3; ++a)
+  {
+    h->mean_b_pos[a] = static_cast<float>(v[1 + a] / v[0]);   // e_.pos_ / p_sum_, state_6dof.h:347
+    h->mean_u_pos[a] = static_cast<float>(v[11 + a] / v[10]);
+  }
+  pf_quat_from_front_up(v + 4, v + 7, h->mean_b_rot);
+  float qu[4];
+  pf_quat_from_front_up(v + 14, v + 17, qu);
+  pf_rpy(qu, h->mean_u_rpy);
+  h->weight_sum_biased = static_cast<float>(v[0]);
+  h->weight_sum = static_cast<float>(v[10]);
+  h->max_prob = static_cast<float>(best);
+  h->max_index = static_cast<uint32_t>(best_i);
+}
+
+__global__ void __launch_bounds__(256)
+    pf_est_pass2_kernel(const PfState* __restrict__ states, const float* __restrict__ probs, uint32_t n,
+                        const EstHeader* __restrict__ h, double* __restrict__ partials /* [grid][kCovSums] */)
+{
+  __shared__ double sm[8][kCovSums];
+  const float e_pos[3] = {h->mean_u_pos[0], h->mean_u_pos[1], h->mean_u_pos[2]};
+  const float e_rpy[3] = {h->mean_u_rpy[0], h->mean_u_rpy[1], h->mean_u_rpy[2]};
+  double v[kCovSums];
+#pragma unroll
+  for (int k = 0; k < kCovSums; ++k) v[k] = 0.0;
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u)
+  {
+    const PfState s = states[i];
+    const float p = probs[i];
+    float d[6];
+    pf_cov_diff(s, e_pos, e_rpy, d);
+    v[0] = dadd(v[0], static_cast<double>(p));
+    int t = 1;
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int k = j; k < 6; ++k)
+      {
+        v[t] = dadd(v[t], static_cast<double>(fmul(fmul(fmul(1.0f, d[j]), d[k]), p)));  // covElement(e, j, k) * probability_
+        ++t;
+      }
+  }
+  est_block_reduce<kCovSums>(v, partials + static_cast<size_t>(blockIdx.x) * kCovSums, sm);
+}
+
+__global__ void pf_est_finish2_kernel(const double* __restrict__ partials, int n_slots, EstHeader* __restrict__ h)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  double v[kCovSums];
+  for (int k = 0; k < kCovSums; ++k) v[k] = 0.0;
+  for (int s = 0; s < n_slots; ++s)
+    for (int k = 0; k < kCovSums; ++k) v[k] = dadd(v[k], partials[static_cast<size_t>(s) * kCovSums + k]);
+  int t = 1;
+  for (int j = 0; j < 6; ++j)
+    for (int k = j; k < 6; ++k)
+    {
+      const float c = static_cast<float>(v[t++] / v[0]);  // cov[k][j] /= p_sum, pf.h:352-358
+      h->cov[j * 6 + k] = c;
+      h->cov[k * 6 + j] = c;
+    }
 }
 
 }  // namespace mcl3dl

@@ -63,6 +63,12 @@ class UpdateSummary(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Estimate(C.Structure):
+    """mcl3dl_estimate"""
+    _fields_ = [("mean_biased", C.c_float * 8), ("max_state", C.c_float * 8), ("max_index", C.c_uint32),
+                ("weight_sum_biased", C.c_float), ("cov", C.c_float * 36)]
+
+
 class WorkStats(C.Structure):
     _fields_ = [("lik_index_rows", C.c_uint64), ("lik_points_scanned", C.c_uint64),
                 ("beam_cells_stepped", C.c_uint64), ("beam_cells_occupied", C.c_uint64),
@@ -78,7 +84,7 @@ EXPORTED_SYMBOLS = ["mcl3dl_measure_update", "mcl3dl_collect_stats", "mcl3dl_rea
                     "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_nn_field_info", "mcl3dl_field_mode", "mcl3dl_field_nodes", "mcl3dl_field_upload", "mcl3dl_collect_timing",
                     "mcl3dl_exchange_create", "mcl3dl_exchange_open", "mcl3dl_measure_exchange_device", "mcl3dl_exchange_current",
                     "mcl3dl_particles_set", "mcl3dl_particles_get", "mcl3dl_particles_predict",
-                    "mcl3dl_particles_measure_update", "mcl3dl_particles_resample"]
+                    "mcl3dl_particles_measure_update", "mcl3dl_particles_resample", "mcl3dl_particles_estimate"]
 
 _LIBS = {}
 
@@ -126,6 +132,7 @@ def load_library(path=None):
     L.mcl3dl_particles_predict.argtypes = [vp, vp, vp, C.c_float, C.c_float, C.c_float]
     L.mcl3dl_particles_measure_update.argtypes = [vp, vp, sz, vp, sz, vp, sz, C.c_float, vp]
     L.mcl3dl_particles_resample.argtypes = [vp, vp, vp, C.c_float, C.c_uint64]
+    L.mcl3dl_particles_estimate.argtypes = [vp, vp, C.c_float, C.c_float, vp]
     L.mcl3dl_exchange_create.argtypes = [vp, sz, C.c_int, C.c_int, vp]
     L.mcl3dl_exchange_open.argtypes = [vp, vp]
     L.mcl3dl_measure_exchange_device.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, C.POINTER(vp)]
@@ -349,6 +356,17 @@ class Engine:
         sp = np.ascontiguousarray(sigma_pos, dtype=np.float32)
         sr = np.ascontiguousarray(sigma_rpy, dtype=np.float32)
         self._check(self.L.mcl3dl_particles_resample(self.h, _ptr(sp), _ptr(sr), initial_frac, seed))
+
+    def particles_estimate(self, state_prev=None, bias_var_dist=1.0, bias_var_ang=1.0):
+        """The node's pose estimate on the resident set: {"mean_biased": POSE[1], "max_state": POSE[1], "max_index",
+        "weight_sum_biased", "cov": float32[6, 6]} (include/mcl3dl_b200.h: mcl3dl_particles_estimate)."""
+        prev = np.ascontiguousarray(state_prev, dtype=POSE).reshape(1) if state_prev is not None else None
+        e = Estimate()
+        self._check(self.L.mcl3dl_particles_estimate(self.h, _ptr(prev) if prev is not None else None, bias_var_dist,
+                                                     bias_var_ang, C.byref(e)))
+        return {"mean_biased": np.frombuffer(bytes(e.mean_biased), dtype=POSE).copy(),
+                "max_state": np.frombuffer(bytes(e.max_state), dtype=POSE).copy(), "max_index": int(e.max_index),
+                "weight_sum_biased": float(e.weight_sum_biased), "cov": np.array(list(e.cov), np.float32).reshape(6, 6)}
 
     # ---- record exchange over peer memory (one process per GPU; see include/mcl3dl_b200.h)
     IPC_HANDLE_BYTES = 64

@@ -140,6 +140,30 @@ public:
                                 extra.empty() ? nullptr : extra.data(), posterior.data(), nullptr, summary),
           "mcl3dl_measure_update");
   }
+  // Scope row f3: the same update on the engine's RESIDENT particle set (nothing per particle crosses the bus).
+  void measureResident(ChunkedKdtree<PointType>::Ptr& kdtree, const Cloud::ConstPtr& pc_lik, const Cloud::ConstPtr& pc_beam,
+                       const std::vector<Vec3>& origins, float odom_err_integ_lin_sigma, mcl3dl_update_summary* summary)
+  {
+    lik_cloud_ = pc_lik;
+    beam_cloud_ = pc_beam;
+    valid_ = false;
+    stageMap(kdtree);
+    if (!staged_map_)
+      stageMap(kdtree);
+    pack(lik_cloud_, lik_pts_);
+    pack(beam_cloud_, beam_pts_);
+    std::vector<float> o(origins.size() * 3);
+    for (size_t k = 0; k < origins.size(); ++k)
+    {
+      o[3 * k] = origins[k].x_;
+      o[3 * k + 1] = origins[k].y_;
+      o[3 * k + 2] = origins[k].z_;
+    }
+    check(mcl3dl_particles_measure_update(engine_, lik_pts_.data(), lik_pts_.size(), beam_pts_.data(), beam_pts_.size(), o.data(),
+                                          origins.size(), odom_err_integ_lin_sigma, summary),
+          "mcl3dl_particles_measure_update");
+  }
+  void checked(int rc, const char* what) const { check(rc, what); }
   size_t likPoints() const { return lik_cloud_ ? lik_cloud_->size() : 0; }
   mcl3dl_engine* engine() { return engine_; }
 
@@ -382,6 +406,114 @@ public:
       entropy_ = s.entropy;
     }
     return UpdateResult{s.match_ratio_min, s.match_ratio_max, s.kept != 0};
+  }
+
+  // ---- Scope row f3: the particle set kept RESIDENT on the device between updates.  The node's cycle
+  //   pf_->predict(model) / pf_->measure(lambda) / pf_->bias + expectationBiased + max + covariance / pf_->resample(sigma)
+  // (src/mcl_3dl.cpp:227-232,402-452,704-724,809-815) becomes predictResident / measureResident / estimateResident /
+  // resampleResident; only scans, odometry and summaries cross the bus.  uploadResident() after init() / resizeParticle() /
+  // any host-side edit of particles_, downloadResident() whenever host code needs the particles (markers, expansion
+  // resetting).  Documented departures (include/mcl3dl_b200.h): counter-based noise instead of the std engine's stream,
+  // ties of the accumulated probability go to the lowest index, sums in double.
+  static mcl3dl_state toState(const State6DOF& s)
+  {
+    mcl3dl_state o;
+    o.pos[0] = s.pos_.x_;
+    o.pos[1] = s.pos_.y_;
+    o.pos[2] = s.pos_.z_;
+    o.rot[0] = s.rot_.x_;
+    o.rot[1] = s.rot_.y_;
+    o.rot[2] = s.rot_.z_;
+    o.rot[3] = s.rot_.w_;
+    o.noise_ll = s.noise_ll_;
+    o.noise_la = s.noise_la_;
+    o.noise_al = s.noise_al_;
+    o.noise_aa = s.noise_aa_;
+    for (int k = 0; k < 3; ++k)
+    {
+      o.odom_err_integ_lin[k] = s.odom_err_integ_lin_[k];
+      o.odom_err_integ_ang[k] = s.odom_err_integ_ang_[k];
+    }
+    return o;
+  }
+  static void fromState(const mcl3dl_state& o, State6DOF& s)
+  {
+    s.pos_ = Vec3(o.pos[0], o.pos[1], o.pos[2]);
+    s.rot_ = mcl_3dl::Quat(o.rot[0], o.rot[1], o.rot[2], o.rot[3]);
+    s.noise_ll_ = o.noise_ll;
+    s.noise_la_ = o.noise_la;
+    s.noise_al_ = o.noise_al;
+    s.noise_aa_ = o.noise_aa;
+    s.odom_err_integ_lin_ = Vec3(o.odom_err_integ_lin[0], o.odom_err_integ_lin[1], o.odom_err_integ_lin[2]);
+    s.odom_err_integ_ang_ = Vec3(o.odom_err_integ_ang[0], o.odom_err_integ_ang[1], o.odom_err_integ_ang[2]);
+  }
+  void uploadResident(MeasurementBatcher& batcher)
+  {
+    std::vector<mcl3dl_state> st;
+    std::vector<float> prob;
+    st.reserve(particles_.size());
+    prob.reserve(particles_.size());
+    for (const auto& p : particles_)
+    {
+      st.push_back(toState(p.state_));
+      prob.push_back(p.probability_);
+    }
+    batcher.checked(mcl3dl_particles_set(batcher.engine(), st.data(), prob.data(), st.size()), "mcl3dl_particles_set");
+  }
+  void downloadResident(MeasurementBatcher& batcher)
+  {
+    std::vector<mcl3dl_state> st(particles_.size());
+    std::vector<float> prob(particles_.size());
+    batcher.checked(mcl3dl_particles_get(batcher.engine(), st.data(), prob.data(), st.size()), "mcl3dl_particles_get");
+    for (size_t i = 0; i < particles_.size(); ++i)
+    {
+      fromState(st[i], particles_[i].state_);
+      particles_[i].probability_ = prob[i];
+    }
+  }
+  // pf_->predict(motion_prediction_model) after model->setOdoms(odom_prev, odom_current, dt) (src/mcl_3dl.cpp:227-232)
+  void predictResident(MeasurementBatcher& batcher, const State6DOF& odom_prev, const State6DOF& odom_current, float time_diff,
+                       float odom_err_integ_lin_tc, float odom_err_integ_ang_tc)
+  {
+    const mcl3dl_pose a{odom_prev.pos_.x_, odom_prev.pos_.y_, odom_prev.pos_.z_, 0.0f, odom_prev.rot_.x_, odom_prev.rot_.y_,
+                        odom_prev.rot_.z_, odom_prev.rot_.w_};
+    const mcl3dl_pose b{odom_current.pos_.x_, odom_current.pos_.y_, odom_current.pos_.z_, 0.0f, odom_current.rot_.x_,
+                        odom_current.rot_.y_, odom_current.rot_.z_, odom_current.rot_.w_};
+    batcher.checked(mcl3dl_particles_predict(batcher.engine(), &a, &b, time_diff, odom_err_integ_lin_tc, odom_err_integ_ang_tc),
+                    "mcl3dl_particles_predict");
+  }
+  // pf_->measure(measure_func) with the node's lambda, odometry-error term included (src/mcl_3dl.cpp:398-426)
+  UpdateResult measureResident(MeasurementBatcher& batcher, ChunkedKdtree<PointType>::Ptr& kdtree, const Cloud::ConstPtr& pc_likelihood,
+                               const Cloud::ConstPtr& pc_beam, const std::vector<Vec3>& origins, float odom_err_integ_lin_sigma)
+  {
+    mcl3dl_update_summary s;
+    batcher.measureResident(kdtree, pc_likelihood, pc_beam, origins, odom_err_integ_lin_sigma, &s);
+    if (s.kept)
+      entropy_ = s.entropy;
+    return UpdateResult{s.match_ratio_min, s.match_ratio_max, s.kept != 0};
+  }
+  // pf_->bias(...) + expectationBiased() + max() + covariance(1.0, .) (src/mcl_3dl.cpp:428-452,704-724)
+  mcl3dl_estimate estimateResident(MeasurementBatcher& batcher, const State6DOF* state_prev, float bias_var_dist, float bias_var_ang)
+  {
+    mcl3dl_estimate e;
+    mcl3dl_pose prev;
+    if (state_prev)
+      prev = mcl3dl_pose{state_prev->pos_.x_, state_prev->pos_.y_, state_prev->pos_.z_, 0.0f, state_prev->rot_.x_,
+                         state_prev->rot_.y_, state_prev->rot_.z_, state_prev->rot_.w_};
+    batcher.checked(mcl3dl_particles_estimate(batcher.engine(), state_prev ? &prev : nullptr, bias_var_dist, bias_var_ang, &e),
+                    "mcl3dl_particles_estimate");
+    return e;
+  }
+  // pf_->resample(State6DOF(sigma_pos, sigma_rpy)) (src/mcl_3dl.cpp:809-815); the host draws the start of the systematic scan
+  // with the filter's own engine, exactly where pf.h:200 draws it
+  void resampleResident(MeasurementBatcher& batcher, const Vec3& sigma_pos, const Vec3& sigma_rpy, uint64_t seed)
+  {
+    std::uniform_real_distribution<float> ud(0.0f, 1.0f);
+    float frac = ud(engine_);
+    if (!(frac < 1.0f))
+      frac = 0.0f;
+    const float sp[3] = {sigma_pos.x_, sigma_pos.y_, sigma_pos.z_}, sr[3] = {sigma_rpy.x_, sigma_rpy.y_, sigma_rpy.z_};
+    batcher.checked(mcl3dl_particles_resample(batcher.engine(), sp, sr, frac, seed), "mcl3dl_particles_resample");
   }
 };
 

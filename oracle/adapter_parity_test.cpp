@@ -17,6 +17,8 @@
 #include <mcl_3dl/chunked_kdtree.h>
 #include <mcl_3dl/lidar_measurement_models/lidar_measurement_model_beam.h>
 #include <mcl_3dl/lidar_measurement_models/lidar_measurement_model_likelihood.h>
+#include <mcl_3dl/motion_prediction_models/motion_prediction_model_differential_drive.h>
+#include <mcl_3dl/nd.h>
 #include <mcl_3dl/pf.h>
 #include <mcl_3dl/point_cloud_random_sampler.h>
 #include <mcl_3dl/state_6dof.h>
@@ -291,6 +293,115 @@ int main(int argc, char** argv)
            "fused entropy %g vs %g", pf_ref.getEntropy(), pf_fused.getEntropy());
     std::printf("fused update: worst relative posterior diff %.3g, entropy %g vs %g\n", worst, pf_ref.getEntropy(),
                 pf_fused.getEntropy());
+  }
+  // scope row f3: three cycles on the RESIDENT particle set (predict / measure / estimate / resample on the device)
+  // against the reference filter doing the same on the host.  Resampling draws different noise (documented departure),
+  // so after every cycle the device set is re-uploaded from the reference filter; what is compared per cycle is
+  // predict (states), the posterior + entropy + match ratios, and the pose estimate.
+  {
+    mcl_3dl_b200::ParticleFilterB200 pf_res(n_particles, 7);
+    pf_res.init(mean, sigma);
+    auto batcher3 = std::make_shared<mcl_3dl_b200::MeasurementBatcher>(&pf_res, std::vector<int>{0}, lik_params, beam_params,
+                                                                      dist_weight);
+    MotionPredictionModelDifferentialDrive motion(10.0f, 10.0f);
+    const float sigma_odom = 0.05f;
+    NormalLikelihood<float> odom_nd(sigma_odom);
+    State6DOF odom_prev(Vec3(0.f, 0.f, 0.f), Quat(0.f, 0.f, 0.f, 1.f));
+    for (int cycle = 0; cycle < 3; ++cycle)
+    {
+      auto ir = pf_ref.begin();
+      auto ig = pf_res.begin();
+      for (; ir != pf_ref.end(); ++ir, ++ig)
+      {
+        ir->state_.noise_ll_ = 0.01f * n01(rng);
+        ir->state_.noise_la_ = 0.01f * n01(rng);
+        ir->state_.noise_al_ = 0.01f * n01(rng);
+        ir->state_.noise_aa_ = 0.01f * n01(rng);
+        *ig = *ir;
+      }
+      pf_res.uploadResident(*batcher3);
+      // predict
+      State6DOF odom_cur(odom_prev.pos_ + Vec3(0.05f, 0.01f * cycle, 0.f), Quat(Vec3(0.f, 0.f, 1.f), 0.02f * (cycle + 1)) * odom_prev.rot_);
+      motion.setOdoms(odom_prev, odom_cur, 0.1f);
+      pf_ref.predict([&motion](State6DOF& s) { motion.predict(s); });  // src/mcl_3dl.cpp:227-232
+      pf_res.predictResident(*batcher3, odom_prev, odom_cur, 0.1f, 10.0f, 10.0f);
+      odom_prev = odom_cur;
+      // measure (the node's lambda with the odometry-error term)
+      std::map<std::string, Cloud::Ptr> pc_locals;
+      for (const auto& lm : ref.lm)
+      {
+        lm.second->setGlobalLocalizationStatus(n_particles, pf_ref.getParticleSize());
+        pc_locals[lm.first] = lm.second->filter(scan, sampler);
+      }
+      float rmin = 1.0, rmax = 0.0;
+      pf_ref.measure([&](const State6DOF& s) -> float
+      {
+        float likelihood = 1;
+        std::map<std::string, float> qualities;
+        for (const auto& lm : ref.lm)
+        {
+          const LidarMeasurementResult result = lm.second->measure(kdtree, pc_locals[lm.first], origins, s);
+          likelihood *= result.likelihood;
+          qualities[lm.first] = result.quality;
+        }
+        if (rmin > qualities["likelihood"]) rmin = qualities["likelihood"];
+        if (rmax < qualities["likelihood"]) rmax = qualities["likelihood"];
+        return likelihood * odom_nd(s.odom_err_integ_lin_.norm());
+      });
+      const auto res = pf_res.measureResident(*batcher3, kdtree, pc_locals["likelihood"], pc_locals["beam"], origins, sigma_odom);
+      EXPECT(res.kept, "resident update kept (cycle %d)", cycle);
+      EXPECT(res.match_ratio_min == rmin && res.match_ratio_max == rmax, "resident match ratio %g/%g vs %g/%g", res.match_ratio_min,
+             res.match_ratio_max, rmin, rmax);
+      // estimate: bias + expectationBiased + max + covariance on the device vs the reference filter
+      const State6DOF state_prev = pf_ref.expectation(1.0);
+      NormalLikelihood<float> nl_lin(0.2f), nl_ang(0.3f);
+      pf_ref.bias([&](const State6DOF& s, float& p_bias) -> void
+      {
+        const float lin_diff = (s.pos_ - state_prev.pos_).norm();
+        Vec3 axis;
+        float ang_diff;
+        (s.rot_ * state_prev.rot_.inv()).getAxisAng(axis, ang_diff);
+        p_bias = nl_lin(lin_diff) * nl_ang(ang_diff) + 1e-6;
+      });
+      const State6DOF e_ref = pf_ref.expectationBiased();
+      const std::vector<State6DOF> cov_ref = pf_ref.covariance(1.0, 1.0);
+      const mcl3dl_estimate est = pf_res.estimateResident(*batcher3, &state_prev, 0.2f, 0.3f);
+      EXPECT(std::fabs(est.mean_biased.px - e_ref.pos_.x_) < 1e-4 && std::fabs(est.mean_biased.py - e_ref.pos_.y_) < 1e-4 &&
+                 std::fabs(est.mean_biased.pz - e_ref.pos_.z_) < 1e-4,
+             "resident mean pos (%g %g %g) vs (%g %g %g)", est.mean_biased.px, est.mean_biased.py, est.mean_biased.pz, e_ref.pos_.x_,
+             e_ref.pos_.y_, e_ref.pos_.z_);
+      EXPECT(std::fabs(est.mean_biased.qz - e_ref.rot_.z_) < 5e-5 && std::fabs(est.mean_biased.qw - e_ref.rot_.w_) < 5e-5,
+             "resident mean rot z w (%g %g) vs (%g %g)", est.mean_biased.qz, est.mean_biased.qw, e_ref.rot_.z_, e_ref.rot_.w_);
+      for (int j = 0; j < 6; ++j)
+        EXPECT(std::fabs(est.cov[j * 6 + j] - cov_ref[j][j]) <= 5e-3 * std::fabs(cov_ref[j][j]) + 1e-8, "resident cov[%d][%d] %g vs %g",
+               j, j, est.cov[j * 6 + j], cov_ref[j][j]);
+      // states after predict and posterior after measure, per particle
+      pf_res.downloadResident(*batcher3);
+      ir = pf_ref.begin();
+      ig = pf_res.begin();
+      double worst_p = 0, worst_s = 0;
+      for (; ir != pf_ref.end(); ++ir, ++ig)
+      {
+        const double rel = std::fabs(ir->probability_ - ig->probability_) / std::max(1e-12, static_cast<double>(ir->probability_));
+        worst_p = std::max(worst_p, rel);
+        EXPECT(rel <= 2e-4, "resident posterior %g vs %g", ir->probability_, ig->probability_);
+        const double ds = std::fabs(ir->state_.pos_.x_ - ig->state_.pos_.x_) + std::fabs(ir->state_.pos_.y_ - ig->state_.pos_.y_) +
+                          std::fabs(ir->state_.rot_.z_ - ig->state_.rot_.z_) + std::fabs(ir->state_.rot_.w_ - ig->state_.rot_.w_);
+        worst_s = std::max(worst_s, ds);
+        EXPECT(ds <= 1e-4, "resident predicted state differs by %g", ds);
+      }
+      EXPECT(std::fabs(pf_ref.getEntropy() - pf_res.getEntropy()) <= 2e-4 * std::fabs(pf_ref.getEntropy()) + 1e-6,
+             "resident entropy %g vs %g", pf_ref.getEntropy(), pf_res.getEntropy());
+      std::printf("resident cycle %d: worst posterior diff %.3g, worst state diff %.3g, mean (%g %g), cov xx %g vs %g\n", cycle,
+                  worst_p, worst_s, est.mean_biased.px, est.mean_biased.py, est.cov[0], cov_ref[0][0]);
+      // resample: on the device (exercised, checked for sanity) and on the reference filter (kept as the next cycle's input)
+      pf_res.resampleResident(*batcher3, Vec3(0.05f, 0.05f, 0.01f), Vec3(0.005f, 0.005f, 0.02f), 100 + cycle);
+      pf_res.downloadResident(*batcher3);
+      float psum = 0;
+      for (auto it = pf_res.begin(); it != pf_res.end(); ++it) psum += it->probability_;
+      EXPECT(std::fabs(psum - 1.0f) < 1e-3, "resident resample: probabilities sum to %g", psum);
+      pf_ref.resample(State6DOF(Vec3(0.05f, 0.05f, 0.01f), Vec3(0.005f, 0.005f, 0.02f)));
+    }
   }
   // a state that is not a particle (mean pose): served by a one-particle engine call
   {

@@ -154,6 +154,8 @@ class CpuChecker:
         L.mcl3dl_cpu_quat_rotate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcl3dl_cpu_transform_point.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcl3dl_cpu_pf_update.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.mcl3dl_cpu_pf_estimate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_float, C.c_float,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
         L.mcl3dl_cpu_filter_clip.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.mcl3dl_cpu_global_localization_points.argtypes = [C.c_size_t] * 4
         L.mcl3dl_cpu_global_localization_points.restype = C.c_size_t
@@ -250,6 +252,19 @@ class CpuChecker:
         self.lib.mcl3dl_cpu_pf_resample_6dof(_ptr(probs), _ptr(states), len(probs), seed, _ptr(sp), _ptr(sr), _ptr(out),
                                              _ptr(out_p))
         return out, out_p
+
+    def pf_estimate(self, probs, states, state_prev=None, bias_var_dist=1.0, bias_var_ang=1.0):
+        """(mean_biased POSE[1], max_index, cov float32[6, 6]) = the node's pose estimate (oracle_api.h)."""
+        probs = np.ascontiguousarray(probs, dtype=np.float32)
+        states = np.ascontiguousarray(states, dtype=MOTION_STATE)
+        prev = np.ascontiguousarray(state_prev, dtype=POSE).reshape(1) if state_prev is not None else None
+        mean = np.zeros(1, dtype=POSE)
+        best = C.c_uint32(0)
+        cov = np.zeros(36, dtype=np.float32)
+        rc = self.lib.mcl3dl_cpu_pf_estimate(_ptr(probs), _ptr(states), len(probs), _ptr(prev) if prev is not None else None,
+                                             bias_var_dist, bias_var_ang, _ptr(mean), C.byref(best), _ptr(cov))
+        assert rc == 0, rc
+        return mean, int(best.value), cov.reshape(6, 6)
 
     def pf_update(self, prob, lik):
         prob = np.array(prob, dtype=np.float32)

@@ -124,6 +124,17 @@ int mcl3dl_cpu_pf_resample_6dof(const float* probs, const mcl3dl_cpu_motion_stat
                                 const float sigma_pos[3], const float sigma_rpy[3], mcl3dl_cpu_motion_state* out_states,
                                 float* out_probs);
 
+/* The pose estimate the node takes from the filter after every measurement (src/mcl_3dl.cpp:428-452,704-724):
+ *   pf_->bias(f)  with f = NormalLikelihood(bias_var_dist)(|pos - prev.pos|) * NormalLikelihood(bias_var_ang)(angle of
+ *                 rot * prev.rot.inv()) + 1e-6   (state_prev == NULL: the constant 1 of the global-localisation branch),
+ *   pf_->expectationBiased()  (pf.h:294-303, ParticleWeightedMeanQuat state_6dof.h:316-355),
+ *   pf_->max()                (pf.h:361-374: first particle with the largest probability_),
+ *   pf_->covariance(1.0, 1.0) (pf.h:304-360 around expectation(1.0); State6DOF::covElement state_6dof.h:162-184).
+ * mean_biased: pos + rot as returned (NOT normalised; the node normalises afterwards, mcl_3dl.cpp:462). */
+int mcl3dl_cpu_pf_estimate(const float* probs, const mcl3dl_cpu_motion_state* states, size_t n,
+                           const mcl3dl_pose* state_prev, float bias_var_dist, float bias_var_ang,
+                           mcl3dl_pose* mean_biased, uint32_t* max_index, float cov[36]);
+
 #ifdef __cplusplus
 }
 #endif

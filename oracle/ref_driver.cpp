@@ -22,6 +22,7 @@
 #include <mcl_3dl/lidar_measurement_models/lidar_measurement_model_likelihood.h>
 #include <mcl_3dl/motion_prediction_models/motion_prediction_model_differential_drive.h>
 #include <mcl_3dl/parameters.h>
+#include <mcl_3dl/nd.h>
 #include <mcl_3dl/pf.h>
 #include <mcl_3dl/point_types.h>
 #include <mcl_3dl/quat.h>
@@ -579,6 +580,69 @@ int mcl3dl_cpu_pf_resample_6dof(const float* probs, const mcl3dl_cpu_motion_stat
     }
     out_probs[i] = it->probability_;
   }
+  return MCL3DL_OK;
+}
+
+int mcl3dl_cpu_pf_estimate(const float* probs, const mcl3dl_cpu_motion_state* st, size_t n, const mcl3dl_pose* prev,
+                           float bias_var_dist, float bias_var_ang, mcl3dl_pose* mean_biased, uint32_t* max_index, float cov[36])
+{
+  mcl_3dl::pf::ParticleFilter<State6DOF, float, mcl_3dl::ParticleWeightedMeanQuat, std::default_random_engine> pf(
+      static_cast<int>(n), 1);
+  size_t i = 0;
+  for (auto it = pf.begin(); it != pf.end(); ++it, ++i)
+  {
+    it->state_ = State6DOF(Vec3(st[i].pos[0], st[i].pos[1], st[i].pos[2]), Quat(st[i].rot[0], st[i].rot[1], st[i].rot[2], st[i].rot[3]));
+    it->probability_ = probs[i];
+  }
+  if (prev)
+  {
+    // src/mcl_3dl.cpp:436-449
+    const State6DOF state_prev(Vec3(prev->px, prev->py, prev->pz), Quat(prev->qx, prev->qy, prev->qz, prev->qw));
+    mcl_3dl::NormalLikelihood<float> nl_lin(bias_var_dist);
+    mcl_3dl::NormalLikelihood<float> nl_ang(bias_var_ang);
+    const auto bias_func = [&state_prev, &nl_lin, &nl_ang](const State6DOF& s, float& p_bias) -> void
+    {
+      const float lin_diff = (s.pos_ - state_prev.pos_).norm();
+      Vec3 axis;
+      float ang_diff;
+      (s.rot_ * state_prev.rot_.inv()).getAxisAng(axis, ang_diff);
+      p_bias = nl_lin(lin_diff) * nl_ang(ang_diff) + 1e-6;
+    };
+    pf.bias(bias_func);
+  }
+  else
+  {
+    const auto bias_func = [](const State6DOF& s, float& p_bias) -> void
+    {
+      p_bias = 1.0;
+    };
+    pf.bias(bias_func);
+  }
+  const State6DOF e = pf.expectationBiased();
+  mean_biased->px = e.pos_.x_;
+  mean_biased->py = e.pos_.y_;
+  mean_biased->pz = e.pos_.z_;
+  mean_biased->_pad = 0.0f;
+  mean_biased->qx = e.rot_.x_;
+  mean_biased->qy = e.rot_.y_;
+  mean_biased->qz = e.rot_.z_;
+  mean_biased->qw = e.rot_.w_;
+  // pf.max() returns the state; recover its index (first maximum, pf.h:361-374)
+  uint32_t best = 0;
+  float bp = probs[0];
+  for (size_t k = 0; k < n; ++k)
+    if (bp < probs[k])
+    {
+      bp = probs[k];
+      best = static_cast<uint32_t>(k);
+    }
+  const State6DOF m = pf.max();
+  if (!(m.pos_ == State6DOF(Vec3(st[best].pos[0], st[best].pos[1], st[best].pos[2]), Quat()).pos_))
+    return MCL3DL_ERR_INVALID_ARG;
+  *max_index = best;
+  const std::vector<State6DOF> c = pf.covariance(1.0, 1.0);
+  for (int j = 0; j < 6; ++j)
+    for (int k = 0; k < 6; ++k) cov[j * 6 + k] = c[j][k];
   return MCL3DL_OK;
 }
 

@@ -26,6 +26,7 @@ class Engine:
         L.hostsim_measure.argtypes = [vp, sz, vp, vp, C.c_float, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp]
         L.hostsim_pf_predict.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float, vp, sz]
         L.hostsim_pf_resample_philox.argtypes = [vp, vp, sz, C.c_float, C.c_uint64, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
+        L.hostsim_pf_estimate.argtypes = [vp, vp, sz, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp]
         self.L = L
         self.calls = 0
 
@@ -112,3 +113,13 @@ class Engine:
         assert self.L.hostsim_pf_resample_philox(_ptr(self.prob), _ptr(self.states), n, initial_frac, seed, self.calls, _ptr(sp),
                                                  _ptr(sr), _ptr(out), _ptr(out_p), None, None, None) == 0
         self.states, self.prob = out, out_p
+
+    def particles_estimate(self, state_prev=None, bias_var_dist=1.0, bias_var_ang=1.0):
+        prev = np.ascontiguousarray(state_prev, dtype=synth.POSE).reshape(1) if state_prev is not None else None
+        pos, rot, cov = np.zeros(3, np.float32), np.zeros(4, np.float32), np.zeros(36, np.float32)
+        best, wsum = C.c_uint32(0), C.c_float(0)
+        assert self.L.hostsim_pf_estimate(_ptr(self.prob), _ptr(self.states), len(self.states), _ptr(prev) if prev is not None else None,
+                                          bias_var_dist, bias_var_ang, _ptr(pos), _ptr(rot), C.byref(best), C.byref(wsum), _ptr(cov)) == 0
+        i = int(best.value)
+        return {"mean_biased": synth.make_poses([pos], [rot]), "max_state": synth.make_poses([self.states["pos"][i]], [self.states["rot"][i]]),
+                "max_index": i, "weight_sum_biased": float(wsum.value), "cov": cov.reshape(6, 6)}

@@ -115,3 +115,77 @@ extern "C" void hostsim_noise6(uint64_t seed, uint32_t index, uint32_t call, con
 {
   pf_noise6(seed, index, call, sigma, org);
 }
+
+// The pose estimate (pf_kernels.cuh: pf_est_pass1/finish1/pass2/finish2) with the device's per-particle functions and
+// double sums in particle order (the kernels fold the same double terms with a fixed tree: equal to ~1e-16 relative).
+// out: mean_b pos[3] rot[4] | max_index | weight_sum_biased | cov[36]  (45 floats; max_index stored as float bits)
+extern "C" int hostsim_pf_estimate(const float* probs, const PfState* states, size_t n, const mcl3dl_pose* prev, float bias_var_dist,
+                                   float bias_var_ang, float* mean_pos, float* mean_rot, uint32_t* max_index, float* wsum, float* cov)
+{
+  BiasDev b{};
+  if (prev)
+  {
+    b.enabled = 1;
+    b.prev_pos[0] = prev->px;
+    b.prev_pos[1] = prev->py;
+    b.prev_pos[2] = prev->pz;
+    const float d = prev->qx * prev->qx + prev->qy * prev->qy + prev->qz * prev->qz + prev->qw * prev->qw;
+    const float id = static_cast<float>(1.0 / d);
+    b.prev_inv = Q4{-prev->qx * id, -prev->qy * id, -prev->qz * id, prev->qw * id};
+    const double sl = bias_var_dist, sa = bias_var_ang;
+    b.lin_a = static_cast<float>(1.0 / std::sqrt(2.0 * M_PI * sl * sl));
+    b.lin_sq2 = static_cast<float>(sl * sl * 2.0);
+    b.ang_a = static_cast<float>(1.0 / std::sqrt(2.0 * M_PI * sa * sa));
+    b.ang_sq2 = static_cast<float>(sa * sa * 2.0);
+  }
+  double v[20] = {0};
+  float best = -1.0f;
+  uint32_t best_i = 0;
+  for (size_t i = 0; i < n; ++i)
+  {
+    const float p = probs[i], w = p * pf_bias(states[i], b);
+    float t[9];
+    pf_mean_terms(states[i], t);
+    v[0] += w;
+    v[10] += p;
+    for (int k = 0; k < 9; ++k)
+    {
+      v[1 + k] += static_cast<double>(t[k] * w);
+      v[11 + k] += static_cast<double>(t[k] * p);
+    }
+    if (p > best)
+    {
+      best = p;
+      best_i = static_cast<uint32_t>(i);
+    }
+  }
+  float e_pos[3], e_rpy[3], qu[4];
+  for (int a = 0; a < 3; ++a)
+  {
+    mean_pos[a] = static_cast<float>(v[1 + a] / v[0]);
+    e_pos[a] = static_cast<float>(v[11 + a] / v[10]);
+  }
+  pf_quat_from_front_up(v + 4, v + 7, mean_rot);
+  pf_quat_from_front_up(v + 14, v + 17, qu);
+  pf_rpy(qu, e_rpy);
+  *max_index = best_i;
+  *wsum = static_cast<float>(v[0]);
+  double c[22] = {0};
+  for (size_t i = 0; i < n; ++i)
+  {
+    float d[6];
+    pf_cov_diff(states[i], e_pos, e_rpy, d);
+    c[0] += probs[i];
+    int t = 1;
+    for (int j = 0; j < 6; ++j)
+      for (int k = j; k < 6; ++k) c[t++] += static_cast<double>(1.0f * d[j] * d[k] * probs[i]);
+  }
+  int t = 1;
+  for (int j = 0; j < 6; ++j)
+    for (int k = j; k < 6; ++k)
+    {
+      cov[j * 6 + k] = cov[k * 6 + j] = static_cast<float>(c[t] / c[0]);
+      ++t;
+    }
+  return 0;
+}

@@ -156,6 +156,35 @@ def test_resample_picks_are_the_reference_systematic_picks(eng_mod, n, frac):
     e.close()
 
 
+@pytest.mark.parametrize("n,with_prev", [(64, True), (5000, False), (65536, True)])
+def test_estimate_matches_the_filter(eng_mod, cc, n, with_prev):
+    """mcl3dl_particles_estimate == pf_->bias + expectationBiased + max + covariance(1.0, 1.0) of the reference filter
+    (the oracle port, pinned bit for bit to the reference build by tests/test_oracle_golden.py).  The device sums in
+    double with a fixed tree, the reference sequentially in float: 1e-4 relative is the bar."""
+    port = cc.CpuChecker("port")
+    rng = np.random.default_rng(n)
+    st = make_states(n, 21)
+    st["pos"] = rng.normal([3.0, -4.0, 0.5], [0.3, 0.2, 0.05], (n, 3))
+    st["rot"] = synth.quat_from_rpy(rng.normal([0.01, -0.02, 2.9], [0.02, 0.02, 0.2], (n, 3)))   # yaw wraps past pi
+    st["rot"] *= (1.0 + rng.normal(0, 1e-3, (n, 1))).astype(np.float32)                          # rot_ is not exactly unit
+    prob = rng.uniform(0.1, 1.0, n).astype(np.float32)
+    prob /= prob.sum(dtype=np.float64).astype(np.float32) * np.float32(1.001)     # total < 1: the reference adds every particle
+    prev = synth.make_poses([[3.1, -4.0, 0.5]], synth.quat_from_rpy([[0.0, 0.0, 2.95]])) if with_prev else None
+    e = eng_mod.Engine((0,))
+    e.particles_set(st, prob)
+    got = e.particles_estimate(prev, 0.2, 0.25)
+    mean, best, cov = port.pf_estimate(prob, st.view(cc.MOTION_STATE), prev, 0.2, 0.25)
+    assert got["max_index"] == best == int(np.argmax(prob))
+    assert got["max_state"]["px"][0] == st["pos"][best, 0] and got["max_state"]["qw"][0] == st["rot"][best, 3]
+    for f in ("px", "py", "pz"):
+        assert abs(got["mean_biased"][f][0] - mean[f][0]) < 1e-4 * max(1.0, abs(mean[f][0])), f
+    for f in ("qx", "qy", "qz", "qw"):
+        assert abs(got["mean_biased"][f][0] - mean[f][0]) < 2e-5, f
+    assert np.allclose(got["cov"], cov, rtol=2e-3, atol=1e-7)
+    assert np.allclose(got["cov"], got["cov"].T) and (np.diag(got["cov"]) > 0).all()
+    e.close()
+
+
 def test_cycle_predict_measure_resample(eng_mod):
     """Three localisation cycles on the device: the weight mass moves to the particles near the true pose."""
     s = synth.scene(60_000, 2000, 96, 8, seed=151)
@@ -172,7 +201,9 @@ def test_cycle_predict_measure_resample(eng_mod):
         assert summ["kept"] == 1
         ent.append(summ["entropy"])
         e.particles_resample(np.full(3, 0.01, np.float32), np.array([0, 0, 0.005], np.float32), 0.5, seed=7 + k)
+    est = e.particles_estimate(None)
     out, prob = e.particles_get()
+    assert np.linalg.norm([est["mean_biased"]["px"][0] - out["pos"][:, 0].mean(), est["mean_biased"]["py"][0] - out["pos"][:, 1].mean()]) < 1e-3
     d = np.linalg.norm(out["pos"][:, :2] - np.asarray(s["truth_pos"])[:2], axis=1)
     d0 = np.linalg.norm(st["pos"][:, :2] - np.asarray(s["truth_pos"])[:2], axis=1)
     assert np.median(d) < np.median(d0)

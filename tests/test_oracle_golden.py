@@ -383,3 +383,23 @@ def test_port_equals_reference_build(port, reference, seed, w, spread, use_dda):
     for m in (a, b):
         r = m.measure(s["particles"][:3], None, None, s["origins"])
         assert (r["score_like"] == 1).all() and (r["score_beam"] == 1).all() and (r["match_cnt"] == 0).all()
+
+
+def test_pose_estimate_port_equals_reference_build(port, reference):
+    """bias + expectationBiased + max + covariance (src/mcl_3dl.cpp:428-452,704-724; pf.h:246-251,281-374): the port's
+    restatement against the reference's own pf::ParticleFilter / ParticleWeightedMeanQuat / State6DOF::covElement /
+    NormalLikelihood, bit for bit."""
+    from oracle import cpu_checker as cc
+    from mcl_3dl_b200 import synth
+    for seed, n, with_prev in ((1, 64, True), (2, 777, False), (3, 4096, True)):
+        rng = np.random.default_rng(seed)
+        st = np.zeros(n, dtype=cc.MOTION_STATE)
+        st["pos"] = rng.normal([3, 4, 0.5], [0.2, 0.2, 0.05], (n, 3))
+        st["rot"] = synth.quat_from_rpy(rng.normal([0, 0, 3.0], [0.02, 0.02, 0.3], (n, 3))) * \
+            (1 + rng.normal(0, 1e-3, (n, 1))).astype(np.float32)
+        p = rng.uniform(0.1, 1, n).astype(np.float32)
+        p /= p.sum()
+        prev = synth.make_poses([[3.1, 4.0, 0.5]], synth.quat_from_rpy([[0, 0, 3.05]])) if with_prev else None
+        a = port.pf_estimate(p, st, prev, 0.2, 0.1)
+        b = reference.pf_estimate(p, st, prev, 0.2, 0.1)
+        assert a[0].tobytes() == b[0].tobytes() and a[1] == b[1] and a[2].tobytes() == b[2].tobytes()

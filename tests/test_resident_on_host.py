@@ -37,5 +37,10 @@ def test_resample(hostsim, n, frac):  # noqa: F811
     T.test_resample_picks_are_the_reference_systematic_picks(fake_engine, n, frac)
 
 
+@pytest.mark.parametrize("n,with_prev", [(64, True), (5000, False), (65536, True)])
+def test_estimate(hostsim, cc, n, with_prev):  # noqa: F811
+    T.test_estimate_matches_the_filter(fake_engine, cc, n, with_prev)
+
+
 def test_cycle(hostsim):  # noqa: F811
     T.test_cycle_predict_measure_resample(fake_engine)
