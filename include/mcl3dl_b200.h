@@ -280,6 +280,33 @@ typedef struct
 int mcl3dl_particles_estimate(mcl3dl_engine*, const mcl3dl_pose* state_prev, float bias_var_dist, float bias_var_ang,
                               mcl3dl_estimate* out);
 
+/* ---- Scan preprocessing on the device (scan half): the node's per-update treatment of the
+ * accumulated raw cloud (src/mcl_3dl.cpp:363-383): pcl::VoxelGrid downsample (:363-367), then per model filter() = clip
+ * by planar range and z window (src/lidar_measurement_model_likelihood.cpp:79-103, _beam.cpp:98-122) and
+ * PointCloudUniformSampler::sample (point_cloud_uniform_sampler.h:56-74).  The prepared scans stay on the device for
+ * mcl3dl_particles_measure_update_prepared; scan_get reads any stage back.  num_points are the values
+ * setGlobalLocalizationStatus computed on the host (likelihood.cpp:63-77).  Departures: PCL's VoxelGrid is third-party
+ * and unpinned (restated from its published algorithm; centroid float sums in input order, majority label); the
+ * sampler's draws come from Philox-4x32-10 (the reference seeds from std::random_device: not reproducible either). */
+typedef struct
+{
+  float downsample[3]; /* VoxelGrid leaf size; any component <= 0: no downsampling */
+  float lik_clip_near, lik_clip_far, lik_clip_z_min, lik_clip_z_max;
+  float beam_clip_near, beam_clip_far, beam_clip_z_min, beam_clip_z_max;
+  uint32_t lik_num_points, beam_num_points; /* sample sizes (0: that model gets an empty scan) */
+  uint64_t seed;
+} mcl3dl_scan_params;
+typedef struct
+{
+  uint32_t n_raw, n_downsampled, n_lik_clipped, n_beam_clipped, n_lik, n_beam;
+} mcl3dl_scan_info;
+int mcl3dl_scan_prepare(mcl3dl_engine*, const mcl3dl_point* raw, size_t n_raw, const mcl3dl_scan_params*, mcl3dl_scan_info* info);
+/* which: 0 downsampled cloud, 1 / 2 clipped cloud of the likelihood / beam model, 3 / 4 their sampled scans. */
+int mcl3dl_scan_get(mcl3dl_engine*, int which, mcl3dl_point* out, size_t capacity, size_t* n_out);
+/* mcl3dl_particles_measure_update on the scans left on the device by the last mcl3dl_scan_prepare. */
+int mcl3dl_particles_measure_update_prepared(mcl3dl_engine*, const float* origins_xyz, size_t n_origins,
+                                             float odom_err_integ_lin_sigma, mcl3dl_update_summary* summary);
+
 /* Record exchange over peer memory for the one-process-per-GPU layout (particles sharded, ONE gather of the
  * 24-byte records, then the unchanged weight update of include/mcl_3dl/pf.h:252-279 on the full array).  There is no
  * collective call and no copy: the two measurement kernels store each particle's record straight into slot `rank` of

@@ -17,6 +17,7 @@
 
 #include "kernels.cuh"
 #include "pf_kernels.cuh"
+#include "scan_kernels.cuh"
 
 using namespace mcl3dl;
 
@@ -336,6 +337,11 @@ struct DeviceCtx
   std::vector<const void*> smem_opted;  // kernels already opted in to large dynamic shared memory on this device
   // resident particle set (mcl3dl_particles_*): two state buffers (resampling writes the other one), probabilities,
   // prefix sum + pstep, the packed poses / odometry-error factors the measurement kernels read
+  // scan preprocessing (mcl3dl_scan_prepare): raw cloud, sort keys / values (x2), flags + scan positions (x2), the
+  // downsampled cloud, the two clipped clouds, the two sampled scans, cub scratch, device-side counts
+  DevBuf s_raw, s_keys[2], s_vals[2], s_flags[2], s_pos[2], s_ds, s_clip[2], s_out[2], s_tmp, s_counts;
+  mcl3dl_scan_info s_info{};
+  bool s_valid = false;
   DevBuf r_states[2], r_prob, r_accum, r_poses, r_extra, r_est;  // r_est: EstHeader + per-CTA partial sums
   size_t r_n = 0;
   int r_cur = 0;
@@ -1407,7 +1413,9 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     xchg_close(c);
     free_buf(c.xchg);
     free_buf(c.x_ticket);
-    for (DevBuf* b : {&c.r_states[0], &c.r_states[1], &c.r_prob, &c.r_accum, &c.r_poses, &c.r_extra, &c.r_est})
+    for (DevBuf* b : {&c.r_states[0], &c.r_states[1], &c.r_prob, &c.r_accum, &c.r_poses, &c.r_extra, &c.r_est, &c.s_raw, &c.s_keys[0],
+                      &c.s_keys[1], &c.s_vals[0], &c.s_vals[1], &c.s_flags[0], &c.s_flags[1], &c.s_pos[0], &c.s_pos[1], &c.s_ds,
+                      &c.s_clip[0], &c.s_clip[1], &c.s_out[0], &c.s_out[1], &c.s_tmp, &c.s_counts})
       free_buf(*b);
     for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.nnf_dir, &c.nnf_cand, &c.fld_cells, &c.d_poses,
                       &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart})
@@ -1776,7 +1784,7 @@ int mcl3dl_particles_resample(mcl3dl_engine* eng, const float sigma_pos[3], cons
   CK(cudaSetDevice(c.dev));
   const uint32_t n = static_cast<uint32_t>(c.r_n);
   float* accum = static_cast<float*>(c.r_accum.p);
-  pf_accum_kernel<<<1, 32, 0, c.stream>>>(static_cast<const float*>(c.r_prob.p), n, accum, accum + n);
+  pf_accum_kernel<<<1, 32, 0, c.stream>>>(static_cast<const float*>(c.r_prob.p), n, accum, accum + n);  // one warp, in order
   Sigma6 sg;
   for (int k = 0; k < 3; ++k)
   {
@@ -1791,6 +1799,65 @@ int mcl3dl_particles_resample(mcl3dl_engine* eng, const float sigma_pos[3], cons
   CK(cudaGetLastError());
   eng->launches += 2;
   c.r_cur = 1 - c.r_cur;
+  return MCL3DL_OK;
+}
+
+// The resident update with every input already on the device: pose pack -> both models -> prior * likelihood * odometry
+// term -> normalise; one synchronise.  `stage` = bytes of host inputs waiting in the pinned block for one H2D copy.
+static int resident_update(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* d_lik, size_t n_lik, const mcl3dl_point* d_beam,
+                           size_t n_beam, const float* d_org, size_t n_origins, float odom_err_lin_sigma, size_t pinned_off,
+                           mcl3dl_update_summary* summary)
+{
+  const size_t P = c.r_n;
+  cudaStream_t st = c.stream;
+  int rc;
+  const int nblk = static_cast<int>(std::min<size_t>((P + kBlockThreads - 1) / kBlockThreads, static_cast<size_t>(c.sm_count) * 4));
+  if ((rc = reserve(eng, c.d_out, P * sizeof(mcl3dl_result))) || (rc = reserve(eng, c.d_w, P * 4)) ||
+      (rc = reserve(eng, c.d_wpart, 2 * (nblk + 1) * sizeof(WeightPartial))))
+    return rc;
+  // NormalLikelihood(sigma): a_ = float(1 / sqrt(2 pi s^2)), sq2_ = float(2 s^2) (include/mcl_3dl/nd.h:45-49)
+  const bool with_odom = odom_err_lin_sigma > 0.0f;
+  const double sg = static_cast<double>(odom_err_lin_sigma);
+  const float nd_a = with_odom ? static_cast<float>(1.0 / std::sqrt(2.0 * M_PI * sg * sg)) : 1.0f;
+  const float nd_sq2 = with_odom ? static_cast<float>(sg * sg * 2.0) : 1.0f;
+  const uint32_t n32 = static_cast<uint32_t>(P);
+  pf_pack_kernel<<<(n32 + 255) / 256, 256, 0, st>>>(static_cast<const PfState*>(c.r_states[c.r_cur].p), n32, nd_a, nd_sq2,
+                                                  static_cast<mcl3dl_pose*>(c.r_poses.p),
+                                                  with_odom ? static_cast<float*>(c.r_extra.p) : nullptr);
+  CK(cudaGetLastError());
+  eng->launches++;
+  rc = launch_models(eng, c, static_cast<const mcl3dl_pose*>(c.r_poses.p), P, d_lik, n_lik, d_beam, n_beam, d_org, n_origins,
+                     static_cast<mcl3dl_result*>(c.d_out.p), nullptr, st, false);
+  if (rc != MCL3DL_OK)
+    return rc;
+  // prior * likelihood from the resident probabilities; the posterior is written over them (the weights were read
+  // into d_w first); a vanished total leaves them untouched = the reference's "restore" (pf.h:274-278)
+  WeightPartial* parts = static_cast<WeightPartial*>(c.d_wpart.p);
+  WeightPartial* parts2 = parts + nblk + 1;
+  weight_kernel<<<nblk, kBlockThreads, 0, st>>>(static_cast<const mcl3dl_result*>(c.d_out.p), static_cast<const float*>(c.r_prob.p),
+                                               with_odom ? static_cast<const float*>(c.r_extra.p) : nullptr, static_cast<int>(P),
+                                               static_cast<int>(n_lik), static_cast<float*>(c.d_w.p), parts);
+  weight_finish_kernel<<<1, 32, 0, st>>>(parts, nblk);
+  normalize_kernel_dev<<<nblk, kBlockThreads, 0, st>>>(static_cast<const float*>(c.d_w.p), static_cast<int>(P), parts + nblk, 0,
+                                                      static_cast<float*>(c.r_prob.p), parts2);
+  weight_finish_kernel<<<1, 32, 0, st>>>(parts2, nblk);
+  CK(cudaGetLastError());
+  eng->launches += 4;
+  char* h_tot = static_cast<char*>(c.h_pinned) + pinned_off;
+  CK(cudaMemcpyAsync(h_tot, parts + nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h_tot + sizeof(WeightPartial), parts2 + nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  WeightPartial w1, w2;
+  std::memcpy(&w1, h_tot, sizeof(w1));
+  std::memcpy(&w2, h_tot + sizeof(w1), sizeof(w2));
+  std::memset(summary, 0, sizeof(*summary));
+  const float total_f = static_cast<float>(w1.sum);
+  summary->weight_sum = total_f;
+  summary->match_ratio_min = std::min(1.0f, w1.qmin);
+  summary->match_ratio_max = std::max(0.0f, w1.qmax);
+  summary->kept = total_f > 0.0f ? 1 : 0;
+  summary->entropy = summary->kept ? static_cast<float>(-w2.sum) : 0.0f;
+  summary->max_index = summary->kept ? w2.best_i : 0;
   return MCL3DL_OK;
 }
 
@@ -1811,64 +1878,202 @@ int mcl3dl_particles_measure_update(mcl3dl_engine* eng, const mcl3dl_point* lik_
     if (beam_pts[j].label >= n_origins)
       return MCL3DL_ERR_INVALID_ARG;
   CK(cudaSetDevice(c.dev));
-  cudaStream_t st = c.stream;
   // scans + origins up in one block (as in mcl3dl_measure); the poses come from the resident states
   const size_t o_beam = n_lik * 16, o_org = o_beam + n_beam * 16, in_bytes = o_org + ((n_origins * 12 + 15) & ~size_t(15));
-  const int nblk = static_cast<int>(std::min<size_t>((P + kBlockThreads - 1) / kBlockThreads, static_cast<size_t>(c.sm_count) * 4));
-  if ((rc = reserve_pinned(eng, c, in_bytes + 2 * sizeof(WeightPartial) + 64)) || (rc = reserve(eng, c.d_poses, in_bytes + 16)) ||
-      (rc = reserve(eng, c.d_out, P * sizeof(mcl3dl_result))) || (rc = reserve(eng, c.d_w, P * 4)) ||
-      (rc = reserve(eng, c.d_wpart, 2 * (nblk + 1) * sizeof(WeightPartial))))
+  if ((rc = reserve_pinned(eng, c, in_bytes + 2 * sizeof(WeightPartial) + 64)) || (rc = reserve(eng, c.d_poses, in_bytes + 16)))
     return rc;
   char* hp = static_cast<char*>(c.h_pinned);
   if (n_lik) std::memcpy(hp, lik_pts, n_lik * 16);
   if (n_beam) std::memcpy(hp + o_beam, beam_pts, n_beam * 16);
   if (n_origins) std::memcpy(hp + o_org, origins_xyz, n_origins * 12);
-  if (in_bytes) CK(cudaMemcpyAsync(c.d_poses.p, hp, in_bytes, cudaMemcpyHostToDevice, st));
-  // NormalLikelihood(sigma): a_ = float(1 / sqrt(2 pi s^2)), sq2_ = float(2 s^2) (include/mcl_3dl/nd.h:45-49)
-  const bool with_odom = odom_err_lin_sigma > 0.0f;
-  const double sg = static_cast<double>(odom_err_lin_sigma);
-  const float nd_a = with_odom ? static_cast<float>(1.0 / std::sqrt(2.0 * M_PI * sg * sg)) : 1.0f;
-  const float nd_sq2 = with_odom ? static_cast<float>(sg * sg * 2.0) : 1.0f;
-  const uint32_t n32 = static_cast<uint32_t>(P);
-  pf_pack_kernel<<<(n32 + 255) / 256, 256, 0, st>>>(static_cast<const PfState*>(c.r_states[c.r_cur].p), n32, nd_a, nd_sq2,
-                                                  static_cast<mcl3dl_pose*>(c.r_poses.p),
-                                                  with_odom ? static_cast<float*>(c.r_extra.p) : nullptr);
-  CK(cudaGetLastError());
-  eng->launches++;
+  if (in_bytes) CK(cudaMemcpyAsync(c.d_poses.p, hp, in_bytes, cudaMemcpyHostToDevice, c.stream));
   const char* d_in = static_cast<const char*>(c.d_poses.p);
-  rc = launch_models(eng, c, static_cast<const mcl3dl_pose*>(c.r_poses.p), P, reinterpret_cast<const mcl3dl_point*>(d_in), n_lik,
-                     reinterpret_cast<const mcl3dl_point*>(d_in + o_beam), n_beam, reinterpret_cast<const float*>(d_in + o_org),
-                     n_origins, static_cast<mcl3dl_result*>(c.d_out.p), nullptr, st, false);
+  return resident_update(eng, c, reinterpret_cast<const mcl3dl_point*>(d_in), n_lik, reinterpret_cast<const mcl3dl_point*>(d_in + o_beam),
+                         n_beam, reinterpret_cast<const float*>(d_in + o_org), n_origins, odom_err_lin_sigma, in_bytes, summary);
+}
+
+int mcl3dl_particles_measure_update_prepared(mcl3dl_engine* eng, const float* origins_xyz, size_t n_origins, float odom_err_lin_sigma,
+                                             mcl3dl_update_summary* summary)
+{
+  if (!eng || eng->devs.size() != 1 || !summary)
+    return MCL3DL_ERR_INVALID_ARG;
+  DeviceCtx& c = eng->devs[0];
+  if (!c.s_valid)
+    return MCL3DL_ERR_INVALID_ARG;  // no mcl3dl_scan_prepare before
+  const size_t P = c.r_n, n_lik = c.s_info.n_lik, n_beam = c.s_info.n_beam;
+  int rc = validate_measure(eng, P, n_lik, n_beam, n_origins);
   if (rc != MCL3DL_OK)
     return rc;
-  // prior * likelihood from the resident probabilities; the posterior is written over them (the weights were read
-  // into d_w first); a vanished total leaves them untouched = the reference's "restore" (pf.h:274-278)
-  WeightPartial* parts = static_cast<WeightPartial*>(c.d_wpart.p);
-  WeightPartial* parts2 = parts + nblk + 1;
-  weight_kernel<<<nblk, kBlockThreads, 0, st>>>(static_cast<const mcl3dl_result*>(c.d_out.p), static_cast<const float*>(c.r_prob.p),
-                                               with_odom ? static_cast<const float*>(c.r_extra.p) : nullptr, static_cast<int>(P),
-                                               static_cast<int>(n_lik), static_cast<float*>(c.d_w.p), parts);
-  weight_finish_kernel<<<1, 32, 0, st>>>(parts, nblk);
-  normalize_kernel_dev<<<nblk, kBlockThreads, 0, st>>>(static_cast<const float*>(c.d_w.p), static_cast<int>(P), parts + nblk, 0,
-                                                      static_cast<float*>(c.r_prob.p), parts2);
-  weight_finish_kernel<<<1, 32, 0, st>>>(parts2, nblk);
+  if (P == 0 || (n_beam && !origins_xyz))
+    return MCL3DL_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c.dev));
+  const size_t in_bytes = (n_origins * 12 + 15) & ~size_t(15);
+  if ((rc = reserve_pinned(eng, c, in_bytes + 2 * sizeof(WeightPartial) + 64)) || (rc = reserve(eng, c.d_poses, in_bytes + 16)))
+    return rc;
+  if (n_origins)
+  {
+    std::memcpy(c.h_pinned, origins_xyz, n_origins * 12);
+    CK(cudaMemcpyAsync(c.d_poses.p, c.h_pinned, in_bytes, cudaMemcpyHostToDevice, c.stream));
+  }
+  // (beam labels are the raw cloud's, voted per voxel: the caller's origins must cover them, as in the node)
+  return resident_update(eng, c, static_cast<const mcl3dl_point*>(c.s_out[0].p), n_lik, static_cast<const mcl3dl_point*>(c.s_out[1].p),
+                         n_beam, static_cast<const float*>(c.d_poses.p), n_origins, odom_err_lin_sigma, in_bytes, summary);
+}
+
+// ---- scan preprocessing on the device (scan_kernels.cuh)
+int mcl3dl_scan_prepare(mcl3dl_engine* eng, const mcl3dl_point* raw, size_t n_raw, const mcl3dl_scan_params* sp, mcl3dl_scan_info* info)
+{
+  if (!eng || eng->devs.size() != 1 || !sp || (n_raw && !raw) || n_raw >= (size_t(1) << 30))
+    return MCL3DL_ERR_INVALID_ARG;
+  DeviceCtx& c = eng->devs[0];
+  CK(cudaSetDevice(c.dev));
+  cudaStream_t st = c.stream;
+  c.s_valid = false;
+  c.s_info = mcl3dl_scan_info{};
+  c.s_info.n_raw = static_cast<uint32_t>(n_raw);
+  const uint32_t n = static_cast<uint32_t>(n_raw);
+  const uint32_t num[2] = {sp->lik_num_points, sp->beam_num_points};
+  int rc;
+  const size_t cap = std::max<size_t>(n_raw, 1);
+  if ((rc = reserve(eng, c.s_raw, cap * 16)) || (rc = reserve(eng, c.s_ds, cap * 16)) || (rc = reserve(eng, c.s_counts, 64)) ||
+      (rc = reserve(eng, c.s_out[0], std::max<size_t>(num[0], 1) * 16)) || (rc = reserve(eng, c.s_out[1], std::max<size_t>(num[1], 1) * 16)))
+    return rc;
+  for (int k = 0; k < 2; ++k)
+    if ((rc = reserve(eng, c.s_keys[k], cap * 4)) || (rc = reserve(eng, c.s_vals[k], cap * 4)) || (rc = reserve(eng, c.s_flags[k], cap * 4)) ||
+        (rc = reserve(eng, c.s_pos[k], cap * 4)) || (rc = reserve(eng, c.s_clip[k], cap * 16)))
+      return rc;
+  uint32_t* counts = static_cast<uint32_t*>(c.s_counts.p);  // [0] downsampled, [1] [2] clipped, [3] [4] sampled
+  CK(cudaMemsetAsync(counts, 0, 64, st));
+  if (n == 0)
+  {
+    c.s_valid = true;
+    if (info) *info = c.s_info;
+    return MCL3DL_OK;
+  }
+  if ((rc = reserve_pinned(eng, c, 256)))
+    return rc;
+  CK(cudaMemcpyAsync(c.s_raw.p, raw, n_raw * 16, cudaMemcpyHostToDevice, st));
+  const mcl3dl_point* d_raw = static_cast<const mcl3dl_point*>(c.s_raw.p);
+  const mcl3dl_point* d_ds = d_raw;
+  const int nb = static_cast<int>((n + 255) / 256);
+  const bool downsample = sp->downsample[0] > 0.0f && sp->downsample[1] > 0.0f && sp->downsample[2] > 0.0f;
+  bool ds_done = false;
+  if (downsample)
+  {
+    // bounding box -> VoxelGrid lattice (getMinMax3D; min_b / max_b / div_b of voxel_grid.hpp)
+    uint32_t h_bbox[12];
+    for (int k = 0; k < 3; ++k)
+    {
+      h_bbox[k] = 0xffffffffu;
+      h_bbox[3 + k] = 0u;
+      h_bbox[6 + k] = 0xffffffffu;
+      h_bbox[9 + k] = 0u;
+    }
+    if ((rc = reserve(eng, c.s_tmp, 4096)))
+      return rc;
+    uint32_t* bb = static_cast<uint32_t*>(c.s_tmp.p);
+    CK(cudaMemcpyAsync(bb, h_bbox, sizeof(h_bbox), cudaMemcpyHostToDevice, st));
+    bbox_kernel<<<std::min(nb, c.sm_count * 8), 256, 0, st>>>(d_raw, n_raw, 1.0f, 1.0f, 1.0f, bb);
+    CK(cudaGetLastError());
+    eng->launches++;
+    CK(cudaMemcpyAsync(h_bbox, bb, sizeof(h_bbox), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    VoxelGridDev g{};
+    double cells = 1.0;
+    for (int k = 0; k < 3; ++k)
+    {
+      g.inv_leaf[k] = 1.0f / sp->downsample[k];
+      const float mn = ord2f(h_bbox[k]), mx = ord2f(h_bbox[3 + k]);
+      g.min_b[k] = static_cast<int>(std::floor(mn * g.inv_leaf[k]));
+      const int max_b = static_cast<int>(std::floor(mx * g.inv_leaf[k]));
+      g.div_b[k] = max_b - g.min_b[k] + 1;
+      cells *= static_cast<double>(g.div_b[k]);
+    }
+    if (cells < 4294967295.0)  // (PCL itself refuses above INT_MAX voxels and returns the cloud unfiltered)
+    {
+      uint32_t *k0 = static_cast<uint32_t*>(c.s_keys[0].p), *k1 = static_cast<uint32_t*>(c.s_keys[1].p);
+      uint32_t *v0 = static_cast<uint32_t*>(c.s_vals[0].p), *v1 = static_cast<uint32_t*>(c.s_vals[1].p);
+      uint32_t *fl = static_cast<uint32_t*>(c.s_flags[0].p), *ps = static_cast<uint32_t*>(c.s_pos[0].p);
+      scan_key_kernel<<<nb, 256, 0, st>>>(d_raw, n, g, k0, v0);
+      size_t t_sort = 0, t_scan = 0;
+      int end_bit = 1;
+      while ((1.0 * (uint64_t(1) << end_bit)) < cells && end_bit < 32) ++end_bit;
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, k0, k1, v0, v1, n, 0, end_bit, st));
+      CK(cub::DeviceScan::ExclusiveSum(nullptr, t_scan, fl, ps, n, st));
+      if ((rc = reserve(eng, c.s_tmp, std::max(t_sort, t_scan) + 256)))
+        return rc;
+      size_t tsz = c.s_tmp.cap;
+      CK(cub::DeviceRadixSort::SortPairs(c.s_tmp.p, tsz, k0, k1, v0, v1, n, 0, end_bit, st));  // stable: input order inside a voxel
+      scan_heads_kernel<<<nb, 256, 0, st>>>(k1, n, fl);
+      tsz = c.s_tmp.cap;
+      CK(cub::DeviceScan::ExclusiveSum(c.s_tmp.p, tsz, fl, ps, n, st));
+      scan_centroid_kernel<<<nb, 256, 0, st>>>(d_raw, k1, v1, fl, ps, n, static_cast<mcl3dl_point*>(c.s_ds.p), counts + 0);
+      CK(cudaGetLastError());
+      eng->launches += 5;
+      d_ds = static_cast<const mcl3dl_point*>(c.s_ds.p);
+      ds_done = true;
+    }
+  }
+  if (!ds_done)
+  {
+    CK(cudaMemcpyAsync(c.s_ds.p, c.s_raw.p, n_raw * 16, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(counts, &c.s_info.n_raw, 4, cudaMemcpyHostToDevice, st));
+    d_ds = static_cast<const mcl3dl_point*>(c.s_ds.p);
+  }
+  // clip (both models at once), compaction in order, then the uniform sample
+  const ClipDev ca{sp->lik_clip_near * sp->lik_clip_near, sp->lik_clip_far * sp->lik_clip_far, sp->lik_clip_z_min, sp->lik_clip_z_max};
+  const ClipDev cb{sp->beam_clip_near * sp->beam_clip_near, sp->beam_clip_far * sp->beam_clip_far, sp->beam_clip_z_min, sp->beam_clip_z_max};
+  uint32_t *fa = static_cast<uint32_t*>(c.s_flags[0].p), *fb = static_cast<uint32_t*>(c.s_flags[1].p);
+  uint32_t *pa = static_cast<uint32_t*>(c.s_pos[0].p), *pb = static_cast<uint32_t*>(c.s_pos[1].p);
+  scan_clip_flags_kernel<<<nb, 256, 0, st>>>(d_ds, counts + 0, ca, cb, fa, fb, n);
+  size_t t_scan = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, t_scan, fa, pa, n, st));
+  if ((rc = reserve(eng, c.s_tmp, t_scan + 256)))
+    return rc;
+  size_t tsz = c.s_tmp.cap;
+  CK(cub::DeviceScan::ExclusiveSum(c.s_tmp.p, tsz, fa, pa, n, st));
+  tsz = c.s_tmp.cap;
+  CK(cub::DeviceScan::ExclusiveSum(c.s_tmp.p, tsz, fb, pb, n, st));
+  scan_compact_kernel<<<nb, 256, 0, st>>>(d_ds, fa, pa, n, static_cast<mcl3dl_point*>(c.s_clip[0].p), counts + 1);
+  scan_compact_kernel<<<nb, 256, 0, st>>>(d_ds, fb, pb, n, static_cast<mcl3dl_point*>(c.s_clip[1].p), counts + 2);
+  for (int k = 0; k < 2; ++k)
+    if (num[k])
+      scan_sample_kernel<<<(num[k] + 255) / 256, 256, 0, st>>>(static_cast<const mcl3dl_point*>(c.s_clip[k].p), counts + 1 + k, num[k],
+                                                             sp->seed, static_cast<uint32_t>(k),
+                                                             static_cast<mcl3dl_point*>(c.s_out[k].p), counts + 3 + k);
   CK(cudaGetLastError());
-  eng->launches += 4;
-  char* h_tot = hp + in_bytes;
-  CK(cudaMemcpyAsync(h_tot, parts + nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(h_tot + sizeof(WeightPartial), parts2 + nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+  eng->launches += 5;
+  uint32_t h_counts[5];
+  CK(cudaMemcpyAsync(c.h_pinned, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  WeightPartial w1, w2;
-  std::memcpy(&w1, h_tot, sizeof(w1));
-  std::memcpy(&w2, h_tot + sizeof(w1), sizeof(w2));
-  std::memset(summary, 0, sizeof(*summary));
-  const float total_f = static_cast<float>(w1.sum);
-  summary->weight_sum = total_f;
-  summary->match_ratio_min = std::min(1.0f, w1.qmin);
-  summary->match_ratio_max = std::max(0.0f, w1.qmax);
-  summary->kept = total_f > 0.0f ? 1 : 0;
-  summary->entropy = summary->kept ? static_cast<float>(-w2.sum) : 0.0f;
-  summary->max_index = summary->kept ? w2.best_i : 0;
+  std::memcpy(h_counts, c.h_pinned, sizeof(h_counts));
+  c.s_info.n_downsampled = h_counts[0];
+  c.s_info.n_lik_clipped = h_counts[1];
+  c.s_info.n_beam_clipped = h_counts[2];
+  c.s_info.n_lik = h_counts[3];
+  c.s_info.n_beam = h_counts[4];
+  c.s_valid = true;
+  if (info) *info = c.s_info;
+  return MCL3DL_OK;
+}
+
+int mcl3dl_scan_get(mcl3dl_engine* eng, int which, mcl3dl_point* out, size_t capacity, size_t* n_out)
+{
+  if (!eng || eng->devs.size() != 1 || which < 0 || which > 4 || !n_out)
+    return MCL3DL_ERR_INVALID_ARG;
+  DeviceCtx& c = eng->devs[0];
+  if (!c.s_valid)
+    return MCL3DL_ERR_INVALID_ARG;
+  const uint32_t n[5] = {c.s_info.n_downsampled, c.s_info.n_lik_clipped, c.s_info.n_beam_clipped, c.s_info.n_lik, c.s_info.n_beam};
+  const DevBuf* src[5] = {&c.s_ds, &c.s_clip[0], &c.s_clip[1], &c.s_out[0], &c.s_out[1]};
+  *n_out = n[which];
+  if (!out || n[which] == 0)
+    return MCL3DL_OK;
+  if (capacity < n[which])
+    return MCL3DL_ERR_INVALID_ARG;
+  CK(cudaSetDevice(c.dev));
+  CK(cudaMemcpyAsync(out, src[which]->p, static_cast<size_t>(n[which]) * 16, cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
   return MCL3DL_OK;
 }
 

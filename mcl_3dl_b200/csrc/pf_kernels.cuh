@@ -50,19 +50,40 @@ __global__ void pf_pack_kernel(const PfState* __restrict__ states, uint32_t n, f
   }
 }
 
-// The sequential float prefix sum of pf.h:189-194 and pstep of :197 — one thread, in order: a parallel scan rounds
-// differently and would move picks at the interval boundaries (65 536 dependent adds ~ 0.15 ms).
-__global__ void pf_accum_kernel(const float* __restrict__ probs, uint32_t n, float* __restrict__ accum, float* __restrict__ pstep)
+// The sequential float prefix sum of pf.h:189-194 and pstep of :197 — strictly in order: a parallel scan rounds
+// differently and would move picks at the interval boundaries.  One warp: the lanes stream the probabilities through
+// shared memory in coalesced 1024-element tiles, lane 0 runs the dependent add chain on the tile (65 536 adds at the
+// 4-cycle add latency ~ 0.15 ms; the first version read global memory inside the chain and took 1.1 ms), the lanes
+// write the sums back coalesced.
+__global__ void __launch_bounds__(32) pf_accum_kernel(const float* __restrict__ probs, uint32_t n, float* __restrict__ accum,
+                                                      float* __restrict__ pstep)
 {
-  if (blockIdx.x != 0 || threadIdx.x != 0)
+  constexpr uint32_t kTile = 1024;
+  __shared__ float tile[kTile];
+  if (blockIdx.x != 0)
     return;
+  const uint32_t lane = threadIdx.x;
   float a = 0.0f;
-  for (uint32_t i = 0; i < n; ++i)
+  for (uint32_t base = 0; base < n; base += kTile)
   {
-    a = fadd(a, probs[i]);
-    accum[i] = a;
+    const uint32_t m = min(kTile, n - base);
+    for (uint32_t i = lane; i < m; i += 32) tile[i] = probs[base + i];
+    __syncwarp();
+    if (lane == 0)
+    {
+#pragma unroll 8
+      for (uint32_t i = 0; i < m; ++i)
+      {
+        a = fadd(a, tile[i]);
+        tile[i] = a;
+      }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < m; i += 32) accum[base + i] = tile[i];
+    __syncwarp();
   }
-  *pstep = fdiv(a, static_cast<float>(n));
+  if (lane == 0)
+    *pstep = fdiv(a, static_cast<float>(n));
 }
 
 struct Sigma6
@@ -193,23 +214,37 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__global__ void pf_est_finish1_kernel(const double* __restrict__ partials, int n_slots, EstHeader* __restrict__ h)
+// fold the per-CTA slots: one thread per column, slots in order (deterministic), then thread 0 derives the means
+__global__ void __launch_bounds__(32) pf_est_finish1_kernel(const double* __restrict__ partials, int n_slots, EstHeader* __restrict__ h)
 {
-  if (threadIdx.x != 0 || blockIdx.x != 0)
+  __shared__ double v[kEstSums];
+  __shared__ double sm_best[2];
+  if (blockIdx.x != 0)
     return;
-  double v[kEstSums];
-  for (int k = 0; k < kEstSums; ++k) v[k] = 0.0;
-  double best = -1.0, best_i = 4294967295.0;
-  for (int s = 0; s < n_slots; ++s)
+  if (threadIdx.x < kEstSums)
   {
-    const double* slot = partials + static_cast<size_t>(s) * (kEstSums + 2);
-    for (int k = 0; k < kEstSums; ++k) v[k] = dadd(v[k], slot[k]);
-    if (slot[kEstSums] > best || (slot[kEstSums] == best && slot[kEstSums + 1] < best_i))
-    {
-      best = slot[kEstSums];
-      best_i = slot[kEstSums + 1];
-    }
+    double t = 0.0;
+    for (int s = 0; s < n_slots; ++s) t = dadd(t, partials[static_cast<size_t>(s) * (kEstSums + 2) + threadIdx.x]);
+    v[threadIdx.x] = t;
   }
+  else if (threadIdx.x == kEstSums)
+  {
+    double best = -1.0, best_i = 4294967295.0;
+    for (int s = 0; s < n_slots; ++s)
+    {
+      const double* slot = partials + static_cast<size_t>(s) * (kEstSums + 2);
+      if (slot[kEstSums] > best || (slot[kEstSums] == best && slot[kEstSums + 1] < best_i))
+      {
+        best = slot[kEstSums];
+        best_i = slot[kEstSums + 1];
+      }
+    }
+    sm_best[0] = best;
+    sm_best[1] = best_i;
+  }
+  __syncwarp();
+  if (threadIdx.x != 0)
+    return;
   for (int a = 0; a < 3; ++a)
   {
     h->mean_b_pos[a] = static_cast<float>(v[1 + a] / v[0]);   // e_.pos_ / p_sum_, state_6dof.h:347
@@ -221,8 +256,8 @@ __global__ void pf_est_finish1_kernel(const double* __restrict__ partials, int n
   pf_rpy(qu, h->mean_u_rpy);
   h->weight_sum_biased = static_cast<float>(v[0]);
   h->weight_sum = static_cast<float>(v[10]);
-  h->max_prob = static_cast<float>(best);
-  h->max_index = static_cast<uint32_t>(best_i);
+  h->max_prob = static_cast<float>(sm_best[0]);
+  h->max_index = static_cast<uint32_t>(sm_best[1]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -255,14 +290,20 @@ __global__ void __launch_bounds__(256)
   est_block_reduce<kCovSums>(v, partials + static_cast<size_t>(blockIdx.x) * kCovSums, sm);
 }
 
-__global__ void pf_est_finish2_kernel(const double* __restrict__ partials, int n_slots, EstHeader* __restrict__ h)
+__global__ void __launch_bounds__(32) pf_est_finish2_kernel(const double* __restrict__ partials, int n_slots, EstHeader* __restrict__ h)
 {
-  if (threadIdx.x != 0 || blockIdx.x != 0)
+  __shared__ double v[kCovSums];
+  if (blockIdx.x != 0)
     return;
-  double v[kCovSums];
-  for (int k = 0; k < kCovSums; ++k) v[k] = 0.0;
-  for (int s = 0; s < n_slots; ++s)
-    for (int k = 0; k < kCovSums; ++k) v[k] = dadd(v[k], partials[static_cast<size_t>(s) * kCovSums + k]);
+  if (threadIdx.x < kCovSums)
+  {
+    double t = 0.0;
+    for (int s = 0; s < n_slots; ++s) t = dadd(t, partials[static_cast<size_t>(s) * kCovSums + threadIdx.x]);
+    v[threadIdx.x] = t;
+  }
+  __syncwarp();
+  if (threadIdx.x != 0)
+    return;
   int t = 1;
   for (int j = 0; j < 6; ++j)
     for (int k = j; k < 6; ++k)

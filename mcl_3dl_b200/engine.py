@@ -63,6 +63,29 @@ class UpdateSummary(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class ScanParams(C.Structure):
+    """mcl3dl_scan_params; defaults = parameters.h:67-77,95-103 and the node's downsample_x/y/z (parameters.cpp:85-87)."""
+    _fields_ = [("downsample", C.c_float * 3),
+                ("lik_clip_near", C.c_float), ("lik_clip_far", C.c_float), ("lik_clip_z_min", C.c_float), ("lik_clip_z_max", C.c_float),
+                ("beam_clip_near", C.c_float), ("beam_clip_far", C.c_float), ("beam_clip_z_min", C.c_float), ("beam_clip_z_max", C.c_float),
+                ("lik_num_points", C.c_uint32), ("beam_num_points", C.c_uint32), ("seed", C.c_uint64)]
+
+    def __init__(self, downsample=(0.1, 0.1, 0.1), lik_clip=(0.5, 10.0, -2.0, 2.0), beam_clip=(0.5, 4.0, -2.0, 2.0),
+                 lik_num_points=96, beam_num_points=3, seed=1):
+        super().__init__()
+        self.downsample[:] = downsample
+        self.lik_clip_near, self.lik_clip_far, self.lik_clip_z_min, self.lik_clip_z_max = lik_clip
+        self.beam_clip_near, self.beam_clip_far, self.beam_clip_z_min, self.beam_clip_z_max = beam_clip
+        self.lik_num_points, self.beam_num_points, self.seed = lik_num_points, beam_num_points, seed
+
+
+class ScanInfo(C.Structure):
+    _fields_ = [(k, C.c_uint32) for k in ("n_raw", "n_downsampled", "n_lik_clipped", "n_beam_clipped", "n_lik", "n_beam")]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
 class Estimate(C.Structure):
     """mcl3dl_estimate"""
     _fields_ = [("mean_biased", C.c_float * 8), ("max_state", C.c_float * 8), ("max_index", C.c_uint32),
@@ -84,7 +107,8 @@ EXPORTED_SYMBOLS = ["mcl3dl_measure_update", "mcl3dl_collect_stats", "mcl3dl_rea
                     "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_nn_field_info", "mcl3dl_field_mode", "mcl3dl_field_nodes", "mcl3dl_field_upload", "mcl3dl_collect_timing",
                     "mcl3dl_exchange_create", "mcl3dl_exchange_open", "mcl3dl_measure_exchange_device", "mcl3dl_exchange_current",
                     "mcl3dl_particles_set", "mcl3dl_particles_get", "mcl3dl_particles_predict",
-                    "mcl3dl_particles_measure_update", "mcl3dl_particles_resample", "mcl3dl_particles_estimate"]
+                    "mcl3dl_particles_measure_update", "mcl3dl_particles_resample", "mcl3dl_particles_estimate", "mcl3dl_scan_prepare", "mcl3dl_scan_get",
+                    "mcl3dl_particles_measure_update_prepared"]
 
 _LIBS = {}
 
@@ -133,6 +157,9 @@ def load_library(path=None):
     L.mcl3dl_particles_measure_update.argtypes = [vp, vp, sz, vp, sz, vp, sz, C.c_float, vp]
     L.mcl3dl_particles_resample.argtypes = [vp, vp, vp, C.c_float, C.c_uint64]
     L.mcl3dl_particles_estimate.argtypes = [vp, vp, C.c_float, C.c_float, vp]
+    L.mcl3dl_scan_prepare.argtypes = [vp, vp, sz, vp, vp]
+    L.mcl3dl_scan_get.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
+    L.mcl3dl_particles_measure_update_prepared.argtypes = [vp, vp, sz, C.c_float, vp]
     L.mcl3dl_exchange_create.argtypes = [vp, sz, C.c_int, C.c_int, vp]
     L.mcl3dl_exchange_open.argtypes = [vp, vp]
     L.mcl3dl_measure_exchange_device.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, C.POINTER(vp)]
@@ -356,6 +383,29 @@ class Engine:
         sp = np.ascontiguousarray(sigma_pos, dtype=np.float32)
         sr = np.ascontiguousarray(sigma_rpy, dtype=np.float32)
         self._check(self.L.mcl3dl_particles_resample(self.h, _ptr(sp), _ptr(sr), initial_frac, seed))
+
+    # ---- scan preprocessing on the device (scope row f4; include/mcl3dl_b200.h)
+    def scan_prepare(self, raw_pts, params):
+        raw_pts = np.ascontiguousarray(raw_pts, dtype=POINT)
+        info = ScanInfo()
+        self._check(self.L.mcl3dl_scan_prepare(self.h, _ptr(raw_pts), len(raw_pts), C.byref(params), C.byref(info)))
+        return info.as_dict()
+
+    def scan_get(self, which):
+        """which: 0 downsampled, 1 / 2 clipped (likelihood / beam), 3 / 4 sampled scans."""
+        n = C.c_size_t(0)
+        self._check(self.L.mcl3dl_scan_get(self.h, which, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=POINT)
+        if n.value:
+            self._check(self.L.mcl3dl_scan_get(self.h, which, _ptr(out), len(out), C.byref(n)))
+        return out
+
+    def particles_measure_update_prepared(self, origins, odom_err_integ_lin_sigma=0.0):
+        origins = np.ascontiguousarray(origins if origins is not None else np.zeros((0, 3)), dtype=np.float32).reshape(-1, 3)
+        summ = UpdateSummary()
+        self._check(self.L.mcl3dl_particles_measure_update_prepared(self.h, _ptr(origins), len(origins), odom_err_integ_lin_sigma,
+                                                                    C.byref(summ)))
+        return summ.as_dict()
 
     def particles_estimate(self, state_prev=None, bias_var_dist=1.0, bias_var_ang=1.0):
         """The node's pose estimate on the resident set: {"mean_biased": POSE[1], "max_state": POSE[1], "max_index",
