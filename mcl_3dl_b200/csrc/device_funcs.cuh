@@ -300,13 +300,34 @@ __device__ __forceinline__ int dda_to_index(float v, float mn, double grid)
 //     the per-sensor ray origin, or screening the cone test in float changed nothing measurable
 //     (the kernel is latency/occupancy bound, not fp64 bound) and were dropped again;
 //   * occupancy matters most: __launch_bounds__(256, 4) (<= 64 registers) 200 -> 165 us.
-__device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const F3& e, uint32_t& n_steps,
-                                        uint32_t& n_occ, uint32_t& n_tested)
+//
+// The ray is cut into three per-lane pieces so that the kernel can run them phase by phase over a warp (all lanes walk
+// to their next occupied cell, THEN all lanes that found one run the fp64 cone test together — profiles/r02a_ncu_beam_c3:
+// the test used to execute with 2-3 live lanes and took a quarter of the samples): dda_setup (setRay), dda_advance
+// (getNextCastResult up to the next occupied cell), dda_test_cell (hasIntersection + getBeamStatus).  cast_ray runs
+// them in sequence for one ray; every operation of a lane is the same either way.
+struct DdaRay
 {
+  F3 b, e, dir;
+  float e0x, e0y, e0z, tdx, tdy, tdz;  // initial_edges_, t_delta_
+  float tx, ty, tz;                    // t_max_
+  float kx, ky, kz;                    // float(|current - begin|): small integers, exact in float
+  int cx, cy, cz, sx, sy, sz;
+  int pos, max_movement;
+  int last_w, cell;
+  uint32_t word;
+};
+
+// setRay, :66-104.  Returns ST_LONG when the ray never starts (begin outside the map box, :70-75), else -1.
+__device__ __forceinline__ int dda_setup(const DdaGridDev& g, const F3& b, const F3& e, DdaRay& r)
+{
+  r.b = b;
+  r.e = e;
+  r.pos = 1;
+  r.max_movement = 0;
   // isPointWithinMap, :260-270
   if (b.x < g.min_x || g.max_x < b.x || b.y < g.min_y || g.max_y < b.y || b.z < g.min_z || g.max_z < b.z)
     return ST_LONG;
-  // setRay, :66-104
   F3 d;
   d.x = fsub(e.x, b.x);
   d.y = fsub(e.y, b.y);
@@ -316,6 +337,7 @@ __device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const 
   dir.x = fdiv(d.x, nrm);
   dir.y = fdiv(d.y, nrm);
   dir.z = fdiv(d.z, nrm);
+  r.dir = dir;
   const float ex = fadd(e.x, fmul(dir.x, g.hit_tolerance));
   const float ey = fadd(e.y, fmul(dir.y, g.hit_tolerance));
   const float ez = fadd(e.z, fmul(dir.z, g.hit_tolerance));
@@ -328,101 +350,140 @@ __device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const 
   const int dix = max(-kIdxLim, min(kIdxLim, dda_to_index(ex, g.min_x, g.grid))) - bx;
   const int diy = max(-kIdxLim, min(kIdxLim, dda_to_index(ey, g.min_y, g.grid))) - by;
   const int diz = max(-kIdxLim, min(kIdxLim, dda_to_index(ez, g.min_z, g.grid))) - bz;
-  const int max_movement = abs(dix) + abs(diy) + abs(diz);
-  const int sx = dix < 0 ? -1 : 1, sy = diy < 0 ? -1 : 1, sz = diz < 0 ? -1 : 1;
+  r.max_movement = abs(dix) + abs(diy) + abs(diz);
+  r.sx = dix < 0 ? -1 : 1;
+  r.sy = diy < 0 ? -1 : 1;
+  r.sz = diz < 0 ? -1 : 1;
   const float inf = __int_as_float(0x7f800000);
-  float e0x = inf, e0y = inf, e0z = inf, tdx = inf, tdy = inf, tdz = inf;
+  r.e0x = r.e0y = r.e0z = r.tdx = r.tdy = r.tdz = inf;
   if (dix != 0)
   {
     // nearest = index * grid + min_p in double; |(nearest - begin) / dir| and |grid / dir| stored as float (:94-99)
     const double nearest = dadd(dmul(static_cast<double>(dir.x < 0 ? bx : bx + 1), g.grid), static_cast<double>(g.min_x));
-    e0x = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.x)), static_cast<double>(dir.x))));
-    tdx = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.x))));
+    r.e0x = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.x)), static_cast<double>(dir.x))));
+    r.tdx = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.x))));
   }
   if (diy != 0)
   {
     const double nearest = dadd(dmul(static_cast<double>(dir.y < 0 ? by : by + 1), g.grid), static_cast<double>(g.min_y));
-    e0y = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.y)), static_cast<double>(dir.y))));
-    tdy = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.y))));
+    r.e0y = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.y)), static_cast<double>(dir.y))));
+    r.tdy = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.y))));
   }
   if (diz != 0)
   {
     const double nearest = dadd(dmul(static_cast<double>(dir.z < 0 ? bz : bz + 1), g.grid), static_cast<double>(g.min_z));
-    e0z = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.z)), static_cast<double>(dir.z))));
-    tdz = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.z))));
+    r.e0z = __double2float_rn(fabs(ddiv(dsub(nearest, static_cast<double>(b.z)), static_cast<double>(dir.z))));
+    r.tdz = __double2float_rn(fabs(ddiv(g.grid, static_cast<double>(dir.z))));
   }
-  float tx = e0x, ty = e0y, tz = e0z;
-  int cx = bx, cy = by, cz = bz;
-  float kx = 0.0f, ky = 0.0f, kz = 0.0f;  // float(|current - begin|): small integers, exact in float
+  r.tx = r.e0x;
+  r.ty = r.e0y;
+  r.tz = r.e0z;
+  r.cx = bx;
+  r.cy = by;
+  r.cz = bz;
+  r.kx = r.ky = r.kz = 0.0f;
+  r.last_w = -1;
+  r.word = 0;
+  r.cell = 0;
+  return -1;
+}
+
+// getNextCastResult, :106-159, up to the next OCCUPIED cell: returns -1 with r.cell set, or ST_LONG when the ray is
+// exhausted / leaves the grid.  At most max_movement-1 cells; begin and end cells are never tested.
+__device__ __forceinline__ int dda_advance(const DdaGridDev& g, DdaRay& r, uint32_t& n_steps)
+{
   const int nxy = g.nx * g.ny;
-  int last_w = -1;
-  uint32_t word = 0;
-  // getNextCastResult, :106-159: at most max_movement-1 cells; begin and end cells are never tested
-  for (int pos = 1; pos < max_movement; ++pos)
+  for (; r.pos < r.max_movement;)
   {
+    ++r.pos;
     ++n_steps;
     // strict-'<' ladder (:114-147): x if tx<ty && tx<tz; y if !(tx<ty) && ty<tz; else z (on ties z beats
     // y beats x).  incrementIndex (:192-203) recomputes t_max from the start:
     // float(edge0) + float(t_delta) * float(|index - begin|).
-    const bool lt_xy = tx < ty;
-    const bool ax = lt_xy && (tx < tz);
-    const bool ay = !lt_xy && (ty < tz);
+    const bool lt_xy = r.tx < r.ty;
+    const bool ax = lt_xy && (r.tx < r.tz);
+    const bool ay = !lt_xy && (r.ty < r.tz);
     const bool az = !ax && !ay;
-    cx += ax ? sx : 0;
-    cy += ay ? sy : 0;
-    cz += az ? sz : 0;
-    kx = ax ? fadd(kx, 1.0f) : kx;
-    ky = ay ? fadd(ky, 1.0f) : ky;
-    kz = az ? fadd(kz, 1.0f) : kz;
-    tx = ax ? fadd(e0x, fmul(tdx, kx)) : tx;
-    ty = ay ? fadd(e0y, fmul(tdy, ky)) : ty;
-    tz = az ? fadd(e0z, fmul(tdz, kz)) : tz;
-    if (static_cast<unsigned>(cx) >= static_cast<unsigned>(g.nx) || static_cast<unsigned>(cy) >= static_cast<unsigned>(g.ny) ||
-        static_cast<unsigned>(cz) >= static_cast<unsigned>(g.nz))
+    r.cx += ax ? r.sx : 0;
+    r.cy += ay ? r.sy : 0;
+    r.cz += az ? r.sz : 0;
+    r.kx = ax ? fadd(r.kx, 1.0f) : r.kx;
+    r.ky = ay ? fadd(r.ky, 1.0f) : r.ky;
+    r.kz = az ? fadd(r.kz, 1.0f) : r.kz;
+    r.tx = ax ? fadd(r.e0x, fmul(r.tdx, r.kx)) : r.tx;
+    r.ty = ay ? fadd(r.e0y, fmul(r.tdy, r.ky)) : r.ty;
+    r.tz = az ? fadd(r.e0z, fmul(r.tdz, r.kz)) : r.tz;
+    if (static_cast<unsigned>(r.cx) >= static_cast<unsigned>(g.nx) || static_cast<unsigned>(r.cy) >= static_cast<unsigned>(g.ny) ||
+        static_cast<unsigned>(r.cz) >= static_cast<unsigned>(g.nz))
+    {
+      r.pos = r.max_movement;
       return ST_LONG;  // left the grid (:197-201)
-    const int cell = cx + cy * g.nx + cz * nxy;
-    const int w = cell >> 5;
-    if (w != last_w)
-    {
-      word = __ldg(g.occ + w);
-      last_w = w;
     }
-    if (!((word >> (cell & 31)) & 1u))
-      continue;
-    // hasIntersection, :237-258: first point of the cell, in map order, inside the cone
-    const uint32_t s0 = __ldg(g.cell_start + cell);
-    const uint32_t s1 = __ldg(g.cell_start + cell + 1);
-    ++n_occ;
-    for (uint32_t s = s0; s < s1; ++s)
+    const int cell = r.cx + r.cy * g.nx + r.cz * nxy;
+    const int w = cell >> 5;
+    if (w != r.last_w)
     {
-      ++n_tested;
-      const float4 m = __ldg(g.pts + s);
-      F3 rel;
-      rel.x = fsub(m.x, b.x);
-      rel.y = fsub(m.y, b.y);
-      rel.z = fsub(m.z, b.z);
-      const double foot = static_cast<double>(fabsf(dot3(rel, dir)));
-      const double a0 = dmul(g.ray_angle_half, foot);
-      const double thr = fmax(dmul(a0, a0), g.min_dist_thr_sq);
-      const double dsq = dsub(static_cast<double>(dot3(rel, rel)), dmul(foot, foot));
-      if (dsq < thr)
-      {
-        // getBeamStatus, beam.cpp:164-189
-        if (__float_as_uint(m.w) > g.filter_label_max)
-          break;  // this cell's collision is filtered; the walk continues with the next cell
-        if (1.0f > g.sin_total_ref)
-        {
-          const double ddx = static_cast<double>(fsub(e.x, m.x));
-          const double ddy = static_cast<double>(fsub(e.y, m.y));
-          const double ddz = static_cast<double>(fsub(e.z, m.z));
-          const float dist_sq = __double2float_rn(dadd(dadd(dmul(ddx, ddx), dmul(ddy, ddy)), dmul(ddz, ddz)));
-          return dist_sq < g.hit_range_sq ? ST_HIT : ST_SHORT;
-        }
-        return ST_TOTAL_REFLECTION;
-      }
+      r.word = __ldg(g.occ + w);
+      r.last_w = w;
+    }
+    if ((r.word >> (cell & 31)) & 1u)
+    {
+      r.cell = cell;
+      return -1;
     }
   }
   return ST_LONG;
+}
+
+// hasIntersection, :237-258 (first point of the cell, in map order, inside the cone) + getBeamStatus, beam.cpp:164-189.
+// Returns the ray's status, or -1: no (unfiltered) collision in this cell, the walk continues.
+__device__ __forceinline__ int dda_test_cell(const DdaGridDev& g, const DdaRay& r, uint32_t& n_occ, uint32_t& n_tested)
+{
+  const uint32_t s0 = __ldg(g.cell_start + r.cell);
+  const uint32_t s1 = __ldg(g.cell_start + r.cell + 1);
+  ++n_occ;
+  for (uint32_t s = s0; s < s1; ++s)
+  {
+    ++n_tested;
+    const float4 m = __ldg(g.pts + s);
+    F3 rel;
+    rel.x = fsub(m.x, r.b.x);
+    rel.y = fsub(m.y, r.b.y);
+    rel.z = fsub(m.z, r.b.z);
+    const double foot = static_cast<double>(fabsf(dot3(rel, r.dir)));
+    const double a0 = dmul(g.ray_angle_half, foot);
+    const double thr = fmax(dmul(a0, a0), g.min_dist_thr_sq);
+    const double dsq = dsub(static_cast<double>(dot3(rel, rel)), dmul(foot, foot));
+    if (dsq < thr)
+    {
+      if (__float_as_uint(m.w) > g.filter_label_max)
+        return -1;  // this cell's collision is filtered; the walk continues with the next cell
+      if (1.0f > g.sin_total_ref)
+      {
+        const double ddx = static_cast<double>(fsub(r.e.x, m.x));
+        const double ddy = static_cast<double>(fsub(r.e.y, m.y));
+        const double ddz = static_cast<double>(fsub(r.e.z, m.z));
+        const float dist_sq = __double2float_rn(dadd(dadd(dmul(ddx, ddx), dmul(ddy, ddy)), dmul(ddz, ddz)));
+        return dist_sq < g.hit_range_sq ? ST_HIT : ST_SHORT;
+      }
+      return ST_TOTAL_REFLECTION;
+    }
+  }
+  return -1;
+}
+
+__device__ __forceinline__ int cast_ray(const DdaGridDev& g, const F3& b, const F3& e, uint32_t& n_steps,
+                                        uint32_t& n_occ, uint32_t& n_tested)
+{
+  DdaRay r;
+  int st = dda_setup(g, b, e, r);
+  while (st < 0)
+  {
+    st = dda_advance(g, r, n_steps);
+    if (st < 0)
+      st = dda_test_cell(g, r, n_occ, n_tested);
+  }
+  return st;
 }
 
 // 1-NN within a radius with the index of the winner (ChunkedKdtree::radiusSearch(p, r, id, d2, 1)); ties go to
@@ -697,11 +758,21 @@ __device__ __forceinline__ int nnf_select(const NnGridDev& g, const NnFieldDev& 
   return n_out;
 }
 
-// One ray with RaycastUsingKDTree (raycasts/raycast_using_kdtree.h:57-110) + getBeamStatus (beam.cpp:157-192).
-__device__ __forceinline__ int cast_ray_kd(const KdRayDev& k, const NnGridDev& nn, const DdaGridDev& g, const F3& b,
-                                           const F3& e, uint32_t& n_steps, uint32_t& n_occ, uint32_t& n_tested)
+// One ray with RaycastUsingKDTree (raycasts/raycast_using_kdtree.h:57-110) + getBeamStatus (beam.cpp:157-192), cut into
+// per-lane phases like the DDA caster: kd_setup (setRay), kd_march (the marching steps up to the next position whose
+// near-field bit is set: a 1-NN search could succeed there) and kd_probe (the search and, on a collision, the second
+// search + getBeamStatus).  The kernel runs march / probe phase by phase over a warp, so the searches of the lanes execute
+// together instead of one lane at a time (profiles/r02c_ncu_beam_kd_c3.txt: 3-7 live lanes on the search lines).
+struct KdRay
 {
-  // setRay, :57-64
+  F3 e;        // end point
+  F3 pos, inc; // pos_, inc_
+  int count, length;
+};
+
+// setRay, :57-64
+__device__ __forceinline__ void kd_setup(const KdRayDev& k, const F3& b, const F3& e, KdRay& r)
+{
   F3 d;
   d.x = fsub(e.x, b.x);
   d.y = fsub(e.y, b.y);
@@ -710,60 +781,94 @@ __device__ __forceinline__ int cast_ray_kd(const KdRayDev& k, const NnGridDev& n
   // The march is capped at 65 536 steps (6.5 km at the default 0.1 m step; the node clips scans at <= 10 m): an end
   // point at 1e30 or +inf must not keep a warp busy for 2^31 steps.  (The reference's float -> int conversion of such a
   // length is undefined; on x86 it yields INT_MIN, i.e. no march at all.)
-  const int length = min(__float2int_rz(floorf(fdiv(fadd(nrm, k.hit_tolerance), k.grid_min))), 65536);
-  F3 inc;
-  inc.x = fmul(fdiv(d.x, nrm), k.grid_min);
-  inc.y = fmul(fdiv(d.y, nrm), k.grid_min);
-  inc.z = fmul(fdiv(d.z, nrm), k.grid_min);
-  F3 pos;
-  pos.x = fadd(b.x, inc.x);
-  pos.y = fadd(b.y, inc.y);
-  pos.z = fadd(b.z, inc.z);
-  // getNextCastResult, :66-110
-  for (int count = 1; count < length; ++count)
+  r.length = min(__float2int_rz(floorf(fdiv(fadd(nrm, k.hit_tolerance), k.grid_min))), 65536);
+  r.inc.x = fmul(fdiv(d.x, nrm), k.grid_min);
+  r.inc.y = fmul(fdiv(d.y, nrm), k.grid_min);
+  r.inc.z = fmul(fdiv(d.z, nrm), k.grid_min);
+  r.pos.x = fadd(b.x, r.inc.x);
+  r.pos.y = fadd(b.y, r.inc.y);
+  r.pos.z = fadd(b.z, r.inc.z);
+  r.e = e;
+  r.count = 1;
+}
+
+// getNextCastResult's loop, :66-110, over the steps that cannot collide (near-field bit clear: free space, most steps
+// of most rays).  Returns -1 at a position that needs the search (r.pos / r.count stay on it), ST_LONG at the ray's end.
+__device__ __forceinline__ int kd_march(const KdRayDev& k, const NnGridDev& nn, KdRay& r, uint32_t& n_steps)
+{
+  for (; r.count < r.length; ++r.count)
   {
     ++n_steps;
-    float d2;
-    uint32_t id;
-    const float qx = fmul(pos.x, nn.wx), qy = fmul(pos.y, nn.wy), qz = fmul(pos.z, nn.wz);
 #if MCL3DL_NEAR_BITS
-    // free space: the marching search cannot find anything, skip it (most steps of most rays)
-    if (near_maybe(k.near, qx, qy, qz) && nnf_search_arg(nn, qx, qy, qz, k.r1_pad, k.r1_sq, d2, id, n_tested))
+    if (near_maybe(k.near, fmul(r.pos.x, nn.wx), fmul(r.pos.y, nn.wy), fmul(r.pos.z, nn.wz)))
+      return -1;
+    r.pos.x = fadd(r.pos.x, r.inc.x);
+    r.pos.y = fadd(r.pos.y, r.inc.y);
+    r.pos.z = fadd(r.pos.z, r.inc.z);
 #else
-    if (nnf_search_arg(nn, qx, qy, qz, k.r1_pad, k.r1_sq, d2, id, n_tested))
+    return -1;
 #endif
-    {
-      ++n_occ;
-      const float4 m = __ldg(k.raw_pts + id);
-      if (!(__float_as_uint(m.w) > g.filter_label_max))  // beam.cpp:168
-      {
-        const float d0 = __fsqrt_rn(d2);
-        // pos_prev = pos_ - inc_ * 2.0 (:91), second search radius grid_min*2 + sqrt(2)*grid_max/2 (:95)
-        const float px = fsub(pos.x, fmul(inc.x, 2.0f)), py = fsub(pos.y, fmul(inc.y, 2.0f)), pz = fsub(pos.z, fmul(inc.z, 2.0f));
-        float d2b;
-        uint32_t idb;
-        float sin_ang = 1.0f;
-        if (nn_search_arg(nn, fmul(px, nn.wx), fmul(py, nn.wy), fmul(pz, nn.wz), k.r2_pad, k.r2_sq, d2b, idb, n_tested))
-        {
-          const float d1 = __fsqrt_rn(d2b);
-          sin_ang = __double2float_rn(ddiv(fabs(static_cast<double>(fsub(d1, d0))), k.sin_den));  // :98
-        }
-        if (sin_ang > g.sin_total_ref)
-        {
-          const double ddx = static_cast<double>(fsub(e.x, m.x));
-          const double ddy = static_cast<double>(fsub(e.y, m.y));
-          const double ddz = static_cast<double>(fsub(e.z, m.z));
-          const float dist_sq = __double2float_rn(dadd(dadd(dmul(ddx, ddx), dmul(ddy, ddy)), dmul(ddz, ddz)));
-          return dist_sq < g.hit_range_sq ? ST_HIT : ST_SHORT;
-        }
-        return ST_TOTAL_REFLECTION;
-      }
-    }
-    pos.x = fadd(pos.x, inc.x);
-    pos.y = fadd(pos.y, inc.y);
-    pos.z = fadd(pos.z, inc.z);
   }
   return ST_LONG;
+}
+
+// The search at the current marching position (:83) and, on a collision with an unfiltered point, the second search two
+// steps back for sin_angle_ (:91-98) + getBeamStatus's decision.  Returns the status, or -1 after advancing one step.
+__device__ __forceinline__ int kd_probe(const KdRayDev& k, const NnGridDev& nn, const DdaGridDev& g, KdRay& r, uint32_t& n_occ,
+                                        uint32_t& n_tested)
+{
+  float d2;
+  uint32_t id;
+  const float qx = fmul(r.pos.x, nn.wx), qy = fmul(r.pos.y, nn.wy), qz = fmul(r.pos.z, nn.wz);
+  if (nnf_search_arg(nn, qx, qy, qz, k.r1_pad, k.r1_sq, d2, id, n_tested))
+  {
+    ++n_occ;
+    const float4 m = __ldg(k.raw_pts + id);
+    if (!(__float_as_uint(m.w) > g.filter_label_max))  // beam.cpp:168
+    {
+      const float d0 = __fsqrt_rn(d2);
+      // pos_prev = pos_ - inc_ * 2.0 (:91), second search radius grid_min*2 + sqrt(2)*grid_max/2 (:95)
+      const float px = fsub(r.pos.x, fmul(r.inc.x, 2.0f)), py = fsub(r.pos.y, fmul(r.inc.y, 2.0f)),
+                  pz = fsub(r.pos.z, fmul(r.inc.z, 2.0f));
+      float d2b;
+      uint32_t idb;
+      float sin_ang = 1.0f;
+      if (nnf_search_arg(nn, fmul(px, nn.wx), fmul(py, nn.wy), fmul(pz, nn.wz), k.r2_pad, k.r2_sq, d2b, idb, n_tested))
+      {
+        const float d1 = __fsqrt_rn(d2b);
+        sin_ang = __double2float_rn(ddiv(fabs(static_cast<double>(fsub(d1, d0))), k.sin_den));  // :98
+      }
+      if (sin_ang > g.sin_total_ref)
+      {
+        const double ddx = static_cast<double>(fsub(r.e.x, m.x));
+        const double ddy = static_cast<double>(fsub(r.e.y, m.y));
+        const double ddz = static_cast<double>(fsub(r.e.z, m.z));
+        const float dist_sq = __double2float_rn(dadd(dadd(dmul(ddx, ddx), dmul(ddy, ddy)), dmul(ddz, ddz)));
+        return dist_sq < g.hit_range_sq ? ST_HIT : ST_SHORT;
+      }
+      return ST_TOTAL_REFLECTION;
+    }
+  }
+  r.pos.x = fadd(r.pos.x, r.inc.x);
+  r.pos.y = fadd(r.pos.y, r.inc.y);
+  r.pos.z = fadd(r.pos.z, r.inc.z);
+  ++r.count;
+  return -1;
+}
+
+__device__ __forceinline__ int cast_ray_kd(const KdRayDev& k, const NnGridDev& nn, const DdaGridDev& g, const F3& b,
+                                           const F3& e, uint32_t& n_steps, uint32_t& n_occ, uint32_t& n_tested)
+{
+  KdRay r;
+  kd_setup(k, b, e, r);
+  int st = -1;
+  while (st < 0)
+  {
+    st = kd_march(k, nn, r, n_steps);
+    if (st < 0)
+      st = kd_probe(k, nn, g, r, n_occ, n_tested);
+  }
+  return st;
 }
 
 // begin = s.pos_ + s.rot_ * origins[label] with the RAW rot_ (beam.cpp:145)

@@ -391,6 +391,7 @@ struct mcl3dl_engine
                             // round 1: off until the f2 parity tests have run with it)
   int field_mode = 0;  // 1: the likelihood model reads the trilinear distance volume (opt-in, inexact; MCL3DL_LIK_MODE=field)
   size_t field_max_bytes = size_t(24) << 30;  // MCL3DL_FIELD_MAX_MB
+  int nnf_kd_r2 = 0;  // MCL3DL_NNF_KD_R2=1: the NN field also covers the KD-tree raycaster's second search radius
   int nnf = 1;  // stage the NN field (exact per-voxel candidate lists) and use lik_kernel_nf; MCL3DL_NNF=0: the CSR window kernels
   size_t nnf_max_bytes = size_t(32) << 30;  // MCL3DL_NNF_MAX_MB: directory + candidates above this -> no field
   uint64_t nnf_bytes = 0, nnf_cands = 0, nnf_overflow_cells = 0;
@@ -1145,7 +1146,9 @@ int build_map_on_device(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point* h_
       {
         KdRayDev tmp{};
         fill_kd_scalars(eng->beam, tmp);
-        radius = std::max(radius, tmp.r1_pad);
+        // the marching search always; the second (sin_angle_) search as well when asked for — it runs once per colliding
+        // ray, through the CSR window search otherwise (a wider field means longer candidate lists for every query)
+        radius = std::max(radius, eng->nnf_kd_r2 ? tmp.r2_pad : tmp.r1_pad);
       }
       g.field = NnFieldDev{};
       if (eng->nnf && eng->mapping != 0)
@@ -1347,6 +1350,8 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     eng->update_one_sync = std::atoi(v) != 0;
   if (const char* v = std::getenv("MCL3DL_NNF"))
     eng->nnf = std::atoi(v) != 0;
+  if (const char* v = std::getenv("MCL3DL_NNF_KD_R2"))
+    eng->nnf_kd_r2 = std::atoi(v) != 0;
   if (const char* v = std::getenv("MCL3DL_LIK_MODE"))
     eng->field_mode = std::strcmp(v, "field") == 0;
   if (const char* v = std::getenv("MCL3DL_FIELD_MAX_MB"))

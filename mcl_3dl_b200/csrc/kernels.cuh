@@ -975,19 +975,25 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
   const int p = group * 32 + lane;
   const bool live = p < P;
   uint32_t n_short = 0, n_hit = 0, n_long = 0, st_steps = 0, st_occ = 0, st_tested = 0;
-  if (live && j0 < j1)
+  if (j0 < j1)  // warp-uniform
   {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(poses + p));
-    const float4 bq = __ldg(reinterpret_cast<const float4*>(poses + p) + 1);
     F3 pos;
-    pos.x = a.x;
-    pos.y = a.y;
-    pos.z = a.z;
     Q4 q;
-    q.x = bq.x;
-    q.y = bq.y;
-    q.z = bq.z;
-    q.w = bq.w;
+    pos.x = pos.y = pos.z = 0.0f;
+    q.x = q.y = q.z = 0.0f;
+    q.w = 1.0f;
+    if (live)
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(poses + p));
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(poses + p) + 1);
+      pos.x = a.x;
+      pos.y = a.y;
+      pos.z = a.z;
+      q.x = bq.x;
+      q.y = bq.y;
+      q.z = bq.z;
+      q.w = bq.w;
+    }
     const Q4 rn = qnormalized(q);
     for (int j = j0; j < j1; ++j)
     {
@@ -998,13 +1004,47 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
       v.z = sp.z;
       const F3 end = transform_point(rn, pos, v);  // beam.cpp:138-139
       const F3 begin = ray_origin(pos, q, origins, __float_as_uint(sp.w));
-      const int st = KD ? cast_ray_kd(kd, nn, g, begin, end, st_steps, st_occ, st_tested) :
-                          cast_ray(g, begin, end, st_steps, st_occ, st_tested);
-      n_short += (st == ST_SHORT);
-      n_hit += (st == ST_HIT);
-      n_long += (st == ST_LONG);
-      if (status)
-        status[static_cast<size_t>(p) * N + base + j] = static_cast<uint8_t>(st);
+      // The ray runs in warp-wide phases: every lane walks to the next place where something may be hit, THEN the lanes
+      // that found one run the expensive step (fp64 cone test / nearest-neighbour searches) together.  A lane's own
+      // sequence of operations is that of cast_ray / cast_ray_kd, so its result is the same bit for bit.
+      int st;
+      if (KD)
+      {
+        KdRay r;
+        kd_setup(kd, begin, end, r);
+        st = live ? -1 : ST_LONG;
+        while (__any_sync(0xffffffffu, st < 0))
+        {
+          if (st < 0)
+            st = kd_march(kd, nn, r, st_steps);
+          __syncwarp();
+          if (st < 0)
+            st = kd_probe(kd, nn, g, r, st_occ, st_tested);
+        }
+      }
+      else
+      {
+        DdaRay r;
+        st = dda_setup(g, begin, end, r);
+        if (!live)
+          st = ST_LONG;
+        while (__any_sync(0xffffffffu, st < 0))
+        {
+          if (st < 0)
+            st = dda_advance(g, r, st_steps);
+          __syncwarp();
+          if (st < 0)
+            st = dda_test_cell(g, r, st_occ, st_tested);
+        }
+      }
+      if (live)
+      {
+        n_short += (st == ST_SHORT);
+        n_hit += (st == ST_HIT);
+        n_long += (st == ST_LONG);
+        if (status)
+          status[static_cast<size_t>(p) * N + base + j] = static_cast<uint8_t>(st);
+      }
     }
   }
   red[warp][0][lane] = n_short;

@@ -71,8 +71,23 @@ __global__ void __launch_bounds__(32) pf_accum_kernel(const float* __restrict__ 
     __syncwarp();
     if (lane == 0)
     {
-#pragma unroll 8
-      for (uint32_t i = 0; i < m; ++i)
+      // 16 values at a time through registers: the loads and stores stay off the dependent add chain
+      uint32_t i = 0;
+      for (; i + 16 <= m; i += 16)
+      {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = tile[i + k];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+        {
+          a = fadd(a, v[k]);
+          v[k] = a;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) tile[i + k] = v[k];
+      }
+      for (; i < m; ++i)
       {
         a = fadd(a, tile[i]);
         tile[i] = a;

@@ -30,31 +30,24 @@ PKG = os.path.join(ROOT, "mcl_3dl_b200")
 LIB = os.path.join(PKG, "libmcl3dl_b200.so")          # the default build
 U2_LIB = os.path.join(PKG, "libmcl3dl_b200_nfu2.so")  # lik_kernel_nf with 2 instead of 4 evals per lane in flight
 HOST = {"MCL3DL_TIMING": "1", "MCL3DL_ZEROCOPY_OUT": "8192"}  # kernel times wanted: the timing events stay on
-VARIANT_BUILDS = {U2_LIB: ["MCL3DL_NF_U=2"]}
+VARIANT_BUILDS = {}
 
 # name -> (library, environment).  "base" (the CSR-window kernels of round 1, MCL3DL_NNF=0) must come first: everything
 # is compared with its records byte for byte.
 VARIANTS = [
     ("base", LIB, dict(HOST, MCL3DL_NNF="0")),
     ("nnf", LIB, dict(HOST)),                                      # NN field (today's default)
-    ("nnf_u2", U2_LIB, dict(HOST)),
-    ("nnf_nostage", LIB, dict(HOST, MCL3DL_NF_STAGE="0")),
-    ("nnf_stage", LIB, dict(HOST, MCL3DL_NF_STAGE="1")),
-    ("nnf_tpp256", LIB, dict(HOST, MCL3DL_NF_TPP="256")),
-    ("nnf_tpp128", LIB, dict(HOST, MCL3DL_NF_TPP="128")),
-    ("nnf_tpp64", LIB, dict(HOST, MCL3DL_NF_TPP="64")),
-    ("nnf_tpp32", LIB, dict(HOST, MCL3DL_NF_TPP="32")),
-    ("nnf_tpp16", LIB, dict(HOST, MCL3DL_NF_TPP="16")),
+    ("nnf_kd_r2", LIB, dict(HOST, MCL3DL_NNF_KD_R2="1")),          # the field also covers the KD caster's second search
+    ("nnf_nokdbits", LIB, dict(HOST, MCL3DL_NEAR_KD_K="0")),
     ("nnf_fast_host", LIB, {"MCL3DL_TIMING": "0", "MCL3DL_ZEROCOPY_OUT": "8192"}),
     ("base_group", LIB, dict(HOST, MCL3DL_MAPPING="group")),
-    ("two_sync", LIB, dict(HOST, MCL3DL_UPDATE_ONE_SYNC="0")),
 ]
 # workload -> (bench workload, raycaster, spread override)
 WORKLOADS = [("c2", "c2", "dda", False), ("c3kd", "c3", "kd", False), ("c5", "c5", "dda", False),
              ("c1kd", "c1", "kd", False), ("c2s", "c2", "dda", True), ("c3", "c3", "dda", False), ("c2iso", "c2", "dda", False)]
 ISO_WORKLOADS = {"c2iso"}  # dist_weight (1,1,1) instead of the node's (1,1,5): ~3x more map points per eval
 ENV_KEYS = ["MCL3DL_TIMING", "MCL3DL_ZEROCOPY_OUT", "MCL3DL_NEAR_K", "MCL3DL_NEAR_KD_K", "MCL3DL_NEAR_MAX_MB",
-            "MCL3DL_MAPPING", "MCL3DL_UPDATE_ONE_SYNC", "MCL3DL_NNF", "MCL3DL_NF_STAGE", "MCL3DL_NF_TPP"]
+            "MCL3DL_MAPPING", "MCL3DL_UPDATE_ONE_SYNC", "MCL3DL_NNF", "MCL3DL_NF_STAGE", "MCL3DL_NF_TPP", "MCL3DL_NNF_KD_R2"]
 
 
 def jobs_all():
