@@ -301,11 +301,11 @@ __device__ __forceinline__ int dda_to_index(float v, float mn, double grid)
 //     (the kernel is latency/occupancy bound, not fp64 bound) and were dropped again;
 //   * occupancy matters most: __launch_bounds__(256, 4) (<= 64 registers) 200 -> 165 us.
 //
-// The ray is cut into three per-lane pieces so that the kernel can run them phase by phase over a warp (all lanes walk
-// to their next occupied cell, THEN all lanes that found one run the fp64 cone test together — profiles/r02a_ncu_beam_c3:
-// the test used to execute with 2-3 live lanes and took a quarter of the samples): dda_setup (setRay), dda_advance
-// (getNextCastResult up to the next occupied cell), dda_test_cell (hasIntersection + getBeamStatus).  cast_ray runs
-// them in sequence for one ray; every operation of a lane is the same either way.
+// The ray is cut into three pieces: dda_setup (setRay), dda_advance (getNextCastResult up to the next occupied cell: a
+// tight stepping loop with nothing else in it) and dda_test_cell (hasIntersection + getBeamStatus, fp64).  With the cone
+// test inside the stepping loop it executed with 2-3 live lanes and took a quarter of the samples
+// (profiles/r02a_ncu_beam_c3.txt); as a loop of "advance, then test" the lanes of a warp reconverge after the walk and
+// test together: c3 155 -> 117 us (profiles/r02i_*), same operations per lane, same bits.
 struct DdaRay
 {
   F3 b, e, dir;
@@ -759,10 +759,9 @@ __device__ __forceinline__ int nnf_select(const NnGridDev& g, const NnFieldDev& 
 }
 
 // One ray with RaycastUsingKDTree (raycasts/raycast_using_kdtree.h:57-110) + getBeamStatus (beam.cpp:157-192), cut into
-// per-lane phases like the DDA caster: kd_setup (setRay), kd_march (the marching steps up to the next position whose
-// near-field bit is set: a 1-NN search could succeed there) and kd_probe (the search and, on a collision, the second
-// search + getBeamStatus).  The kernel runs march / probe phase by phase over a warp, so the searches of the lanes execute
-// together instead of one lane at a time (profiles/r02c_ncu_beam_kd_c3.txt: 3-7 live lanes on the search lines).
+// pieces like the DDA caster: kd_setup (setRay), kd_march (the marching steps up to the next position whose near-field
+// bit is set: a 1-NN search could succeed there) and kd_probe (the search and, on a collision, the second search +
+// getBeamStatus), so that the lanes of a warp reconverge between marching and searching.
 struct KdRay
 {
   F3 e;        // end point

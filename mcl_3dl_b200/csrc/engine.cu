@@ -391,7 +391,7 @@ struct mcl3dl_engine
                             // round 1: off until the f2 parity tests have run with it)
   int field_mode = 0;  // 1: the likelihood model reads the trilinear distance volume (opt-in, inexact; MCL3DL_LIK_MODE=field)
   size_t field_max_bytes = size_t(24) << 30;  // MCL3DL_FIELD_MAX_MB
-  int nnf_kd_r2 = 0;  // MCL3DL_NNF_KD_R2=1: the NN field also covers the KD-tree raycaster's second search radius
+  int nnf_kd_r2 = 1;  // MCL3DL_NNF_KD_R2=0: the NN field also covers the KD-tree raycaster's second search radius
   int nnf = 1;  // stage the NN field (exact per-voxel candidate lists) and use lik_kernel_nf; MCL3DL_NNF=0: the CSR window kernels
   size_t nnf_max_bytes = size_t(32) << 30;  // MCL3DL_NNF_MAX_MB: directory + candidates above this -> no field
   uint64_t nnf_bytes = 0, nnf_cands = 0, nnf_overflow_cells = 0;
@@ -752,14 +752,15 @@ int launch_beam_pl(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, s
   const int gpc = kPlWarps / sh.cpg;
   const int groups = static_cast<int>(((P + 31) / 32 + gpc - 1) / gpc);
   const size_t smem = static_cast<size_t>(kPlWarps) * sh.ppl * 16;
+#define PL_LAUNCH(KD)                                                                                                             \
+  beam_kernel_pl<KD><<<groups * sh.cb, kBlockThreads, smem, st>>>(                                                                \
+      poses, static_cast<int>(P), reinterpret_cast<const float4*>(scan), static_cast<int>(N), origins, c.dda, c.kd, c.nn, out, status, \
+      lik_defaults, c.stats_ptr(), sh, static_cast<uint32_t*>(c.d_partial.p), static_cast<unsigned int*>(c.d_tickets.p), sink)
   if (eng->beam.use_raycast_using_dda)
-    beam_kernel_pl<false><<<groups * sh.cb, kBlockThreads, smem, st>>>(
-        poses, static_cast<int>(P), reinterpret_cast<const float4*>(scan), static_cast<int>(N), origins, c.dda, c.kd, c.nn, out,
-        status, lik_defaults, c.stats_ptr(), sh, static_cast<uint32_t*>(c.d_partial.p), static_cast<unsigned int*>(c.d_tickets.p), sink);
+    PL_LAUNCH(false);
   else
-    beam_kernel_pl<true><<<groups * sh.cb, kBlockThreads, smem, st>>>(
-        poses, static_cast<int>(P), reinterpret_cast<const float4*>(scan), static_cast<int>(N), origins, c.dda, c.kd, c.nn, out,
-        status, lik_defaults, c.stats_ptr(), sh, static_cast<uint32_t*>(c.d_partial.p), static_cast<unsigned int*>(c.d_tickets.p), sink);
+    PL_LAUNCH(true);
+#undef PL_LAUNCH
   CK(cudaGetLastError());
   eng->launches++;
   return MCL3DL_OK;

@@ -1004,39 +1004,13 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
       v.z = sp.z;
       const F3 end = transform_point(rn, pos, v);  // beam.cpp:138-139
       const F3 begin = ray_origin(pos, q, origins, __float_as_uint(sp.w));
-      // The ray runs in warp-wide phases: every lane walks to the next place where something may be hit, THEN the lanes
-      // that found one run the expensive step (fp64 cone test / nearest-neighbour searches) together.  A lane's own
-      // sequence of operations is that of cast_ray / cast_ray_kd, so its result is the same bit for bit.
-      int st;
-      if (KD)
-      {
-        KdRay r;
-        kd_setup(kd, begin, end, r);
-        st = live ? -1 : ST_LONG;
-        while (__any_sync(0xffffffffu, st < 0))
-        {
-          if (st < 0)
-            st = kd_march(kd, nn, r, st_steps);
-          __syncwarp();
-          if (st < 0)
-            st = kd_probe(kd, nn, g, r, st_occ, st_tested);
-        }
-      }
-      else
-      {
-        DdaRay r;
-        st = dda_setup(g, begin, end, r);
-        if (!live)
-          st = ST_LONG;
-        while (__any_sync(0xffffffffu, st < 0))
-        {
-          if (st < 0)
-            st = dda_advance(g, r, st_steps);
-          __syncwarp();
-          if (st < 0)
-            st = dda_test_cell(g, r, st_occ, st_tested);
-        }
-      }
+      // cast_ray / cast_ray_kd are loops of "walk to the next candidate cell / marching position" followed by the
+      // expensive test (fp64 cone test / nearest-neighbour searches): the lanes of the warp reconverge after the walk, so
+      // the tests of the lanes that found a candidate run together.  (An explicit warp-wide phase loop around the
+      // split functions measured the same, profiles/r02j_ab.jsonl, and was dropped.)
+      int st = ST_LONG;
+      if (live)
+        st = KD ? cast_ray_kd(kd, nn, g, begin, end, st_steps, st_occ, st_tested) : cast_ray(g, begin, end, st_steps, st_occ, st_tested);
       if (live)
       {
         n_short += (st == ST_SHORT);

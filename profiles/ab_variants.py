@@ -35,12 +35,11 @@ VARIANT_BUILDS = {}
 # name -> (library, environment).  "base" (the CSR-window kernels of round 1, MCL3DL_NNF=0) must come first: everything
 # is compared with its records byte for byte.
 VARIANTS = [
-    ("base", LIB, dict(HOST, MCL3DL_NNF="0")),
-    ("nnf", LIB, dict(HOST)),                                      # NN field (today's default)
-    ("nnf_kd_r2", LIB, dict(HOST, MCL3DL_NNF_KD_R2="1")),          # the field also covers the KD caster's second search
-    ("nnf_nokdbits", LIB, dict(HOST, MCL3DL_NEAR_KD_K="0")),
-    ("nnf_fast_host", LIB, {"MCL3DL_TIMING": "0", "MCL3DL_ZEROCOPY_OUT": "8192"}),
-    ("base_group", LIB, dict(HOST, MCL3DL_MAPPING="group")),
+    ("base", LIB, dict(HOST, MCL3DL_NNF="0")),                      # the CSR-window searches of round 1
+    ("dflt", LIB, dict(HOST)),                                      # today's defaults
+    ("kd_nor2", LIB, dict(HOST, MCL3DL_NNF_KD_R2="0")),
+    ("fast_host", LIB, {"MCL3DL_TIMING": "0", "MCL3DL_ZEROCOPY_OUT": "8192"}),
+    ("group", LIB, dict(HOST, MCL3DL_MAPPING="group")),
 ]
 # workload -> (bench workload, raycaster, spread override)
 WORKLOADS = [("c2", "c2", "dda", False), ("c3kd", "c3", "kd", False), ("c5", "c5", "dda", False),
