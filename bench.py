@@ -10,8 +10,7 @@ scan point.  Prints ONE JSON line on rank 0 (see the contract in the task statem
   value     whole-job particle x point evals/s with all inputs resident in HBM (CUDA events, max over ranks).
             N > 1: one process per GPU, particles sharded, map replicated; the ONE exchange of the path (the gather
             of the 24-byte records) is folded into the measurement kernels, which store every record into every
-            rank's array over NVLink peer memory and signal / await the peers from their last CTA (csrc/kernels.cuh:
-            RecordSink + sink_finish); the
+            rank's array over NVLink peer memory (csrc/kernels.cuh: RecordSink + exchange_signal_kernel); the
             whole step is replayed as one CUDA graph.  --exchange nccl keeps the NCCL all-gather for comparison.
   e2e       same metric through the host-buffer C-ABI call mcl3dl_measure (H2D + kernels + D2H inside).
             N > 1: ONE host process (rank 0) drives all N GPUs through the in-process multi-device engine
@@ -390,7 +389,7 @@ def device_leg(cx, workload, raycaster, steps, warmup, exchange="peer", graph=Tr
 
     exchange_info = None
     if world > 1:
-        exchange_info = {"mode": "peer-memory stores + flag exchange in the kernels' epilogues (no extra launch)" if peer else "nccl all_gather",
+        exchange_info = {"mode": "peer-memory stores in the kernels' epilogues + signal kernel" if peer else "nccl all_gather",
                          "graph": graphed, "bytes_per_rank_per_step": P_rank * 24 * (world if peer else 1)}
         if peer:
             # the folded exchange against NCCL on the same inputs (outside every timed region), byte for byte

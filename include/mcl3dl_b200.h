@@ -310,9 +310,8 @@ int mcl3dl_particles_measure_update_prepared(mcl3dl_engine*, const float* origin
 /* Record exchange over peer memory for the one-process-per-GPU layout (particles sharded, ONE gather of the
  * 24-byte records, then the unchanged weight update of include/mcl_3dl/pf.h:252-279 on the full array).  There is no
  * collective call and no copy: the two measurement kernels store each particle's record straight into slot `rank` of
- * EVERY rank's gathered array over NVLink (peer memory mapped with CUDA IPC), and the last CTA of the step's last kernel
- * publishes "rank r finished step s" to every peer and waits, on the device, for the other ranks' flags: no extra
- * launch.  The launch sequence
+ * EVERY rank's gathered array over NVLink (peer memory mapped with CUDA IPC), and one 32-thread kernel then publishes
+ * "rank r finished step s" to every peer and waits, on the device, for the other ranks' flags.  The launch sequence
  * of a step is identical every time (the step parity is read from device memory), so it can be captured in a CUDA
  * graph.  Engines with exactly one device; world <= 8; every rank holds n_local particles.
  *   create:  allocates this rank's buffer (two [world * n_local] record arrays used alternately, plus flags) and writes
@@ -323,7 +322,7 @@ int mcl3dl_particles_measure_update_prepared(mcl3dl_engine*, const float* origin
  *            caller's stream; when it retires, *d_all_out (device memory, valid until the call after next) holds every
  *            rank's records in rank order.  *d_all_out assumes eager calls; after CUDA-graph replays ask `current`;
  *   current: synchronises the stream and returns the array of the last completed step and whether a peer ever failed
- *            to show up within the bounded wait. */
+ *            to show up within the signal kernel's bounded wait. */
 #define MCL3DL_IPC_HANDLE_BYTES 64
 int mcl3dl_exchange_create(mcl3dl_engine*, size_t n_local, int world, int rank, void* ipc_handle_out);
 int mcl3dl_exchange_open(mcl3dl_engine*, const void* ipc_handles);

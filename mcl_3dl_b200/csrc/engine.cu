@@ -347,7 +347,8 @@ struct DeviceCtx
   int r_cur = 0;
   uint32_t r_calls = 0;
   // record exchange over peer memory (one process per GPU, mcl3dl_exchange_*): [world * n_local records | world flags]
-  DevBuf xchg, x_ticket;  // x_ticket: [0] completed-step counter, [4..7] RecordSink::sync (tickets, arrivals, error word)
+  DevBuf xchg, x_ticket;  // x_ticket: [0] completed-step counter, [1] error word (device memory, local)
+  PeerTable xt{};
   RecordSink xsink{};
   void* x_opened[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t x_local = 0;   // records per rank
@@ -1677,8 +1678,7 @@ static int launch_models(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* po
                          mcl3dl_result* out, uint8_t* status, cudaStream_t st, bool timed, const RecordSink* sink_in = nullptr)
 {
   int rc = MCL3DL_OK;
-  RecordSink sink = sink_in ? *sink_in : RecordSink{};
-  sink.n_kernels = (n_beam ? 1 : 0) + ((n_lik || !n_beam) ? 1 : 0);
+  const RecordSink sink = sink_in ? *sink_in : RecordSink{};
   const bool both = n_beam && n_lik && eng->overlap;
   cudaStream_t sb = both ? c.side : st;
   if (n_beam)
@@ -1689,7 +1689,6 @@ static int launch_models(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* po
       CK(cudaStreamWaitEvent(sb, c.ev_fork, 0));
     }
     if (timed) CK(cudaEventRecord(c.ev_b0, sb));
-    sink.slot = 1;
     rc = launch_beam(eng, c, poses, P, beam, n_beam, origins, static_cast<int>(n_origins), out, status, n_lik == 0, sb, sink);
     if (rc != MCL3DL_OK)
       return rc;
@@ -1699,7 +1698,6 @@ static int launch_models(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* po
   if (timed) CK(cudaEventRecord(c.ev[2], st));
   if (n_lik || !n_beam)
   {
-    sink.slot = 0;
     rc = launch_lik(eng, c, poses, P, lik, n_lik, out, n_beam == 0, st, sink);
     if (rc != MCL3DL_OK)
       return rc;
@@ -2154,7 +2152,7 @@ int mcl3dl_particles_estimate(mcl3dl_engine* eng, const mcl3dl_pose* prev, float
 }
 
 // ---- record exchange over peer memory (one process per GPU, one device per engine; kernels.cuh: RecordSink +
-// sink_finish).  Buffer of a rank: [array 0: world * n_local records | array 1 | world flags]; the step
+// exchange_signal_kernel).  Buffer of a rank: [array 0: world * n_local records | array 1 | world flags]; the step
 // counter and the error word live in x_ticket (local only).
 static size_t xchg_flags_offset(size_t n_local, int world)
 {
@@ -2194,9 +2192,10 @@ int mcl3dl_exchange_create(mcl3dl_engine* eng, size_t n_local, int world, int ra
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, c.xchg.p));
   std::memcpy(ipc_handle_out, &h, sizeof(h));
+  c.xt = PeerTable{};
+  c.xt.world = world;
+  c.xt.rank = rank;
   c.xsink = RecordSink{};
-  c.xsink.world = world;  // (completed by exchange_open)
-  c.xsink.rank = rank;
   c.x_local = n_local;
   c.x_step = 0;
   c.x_ready = false;
@@ -2208,15 +2207,14 @@ int mcl3dl_exchange_open(mcl3dl_engine* eng, const void* ipc_handles /* world x 
   if (!eng || eng->devs.size() != 1 || !ipc_handles)
     return MCL3DL_ERR_INVALID_ARG;
   DeviceCtx& c = eng->devs[0];
-  if (!c.xchg.p || c.xsink.world < 1 || c.x_ready)
+  if (!c.xchg.p || c.xt.world < 1 || c.x_ready)
     return MCL3DL_ERR_INVALID_ARG;
   CK(cudaSetDevice(c.dev));
-  const int world = c.xsink.world, rank = c.xsink.rank;
-  const size_t flags_off = xchg_flags_offset(c.x_local, world);
-  for (int g = 0; g < world; ++g)
+  const size_t flags_off = xchg_flags_offset(c.x_local, c.xt.world);
+  for (int g = 0; g < c.xt.world; ++g)
   {
     void* base = c.xchg.p;
-    if (g != rank)
+    if (g != c.xt.rank)
     {
       cudaIpcMemHandle_t h;
       std::memcpy(&h, static_cast<const char*>(ipc_handles) + static_cast<size_t>(g) * sizeof(h), sizeof(h));
@@ -2230,12 +2228,12 @@ int mcl3dl_exchange_open(mcl3dl_engine* eng, const void* ipc_handles /* world x 
       c.x_opened[g] = base;
     }
     // this rank's slot inside rank g's array 0
-    c.xsink.base[g] = static_cast<mcl3dl_result*>(base) + static_cast<size_t>(rank) * c.x_local;
-    c.xsink.flags[g] = reinterpret_cast<uint32_t*>(static_cast<char*>(base) + flags_off);
+    c.xsink.base[g] = static_cast<mcl3dl_result*>(base) + static_cast<size_t>(c.xt.rank) * c.x_local;
+    c.xt.flags[g] = reinterpret_cast<uint32_t*>(static_cast<char*>(base) + flags_off);
   }
-  c.xsink.step = static_cast<uint32_t*>(c.x_ticket.p);
-  c.xsink.sync = static_cast<unsigned int*>(c.x_ticket.p) + 4;
-  c.xsink.parity_stride = static_cast<uint32_t>(static_cast<size_t>(world) * c.x_local);
+  c.xsink.step = static_cast<const uint32_t*>(c.x_ticket.p);
+  c.xsink.parity_stride = static_cast<uint32_t>(static_cast<size_t>(c.xt.world) * c.x_local);
+  c.xsink.world = c.xt.world;
   c.x_ready = true;
   return MCL3DL_OK;
 }
@@ -2258,9 +2256,13 @@ int mcl3dl_measure_exchange_device(mcl3dl_engine* eng, const mcl3dl_pose* d_pose
                      &c.xsink);
   if (rc != MCL3DL_OK)
     return rc;
+  unsigned int* tk = static_cast<unsigned int*>(c.x_ticket.p);
+  exchange_signal_kernel<<<1, 32, 0, st>>>(c.xt, tk, tk + 1);
+  CK(cudaGetLastError());
+  eng->launches++;
   ++c.x_step;  // host mirror of the device counter; exact for eager calls, resynchronised by mcl3dl_exchange_current
   if (d_all_out)
-    *d_all_out = static_cast<const mcl3dl_result*>(c.xchg.p) + static_cast<size_t>(c.x_step & 1u) * c.xsink.world * c.x_local;
+    *d_all_out = static_cast<const mcl3dl_result*>(c.xchg.p) + static_cast<size_t>(c.x_step & 1u) * c.xt.world * c.x_local;
   return MCL3DL_OK;
 }
 
@@ -2271,14 +2273,14 @@ int mcl3dl_exchange_current(mcl3dl_engine* eng, void* cuda_stream, const mcl3dl_
   DeviceCtx& c = eng->devs[0];
   CK(cudaSetDevice(c.dev));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  unsigned int w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned int w[2] = {0, 0};
   CK(cudaMemcpyAsync(w, c.x_ticket.p, sizeof(w), cudaMemcpyDeviceToHost, st));  // after everything enqueued on the stream
   CK(cudaStreamSynchronize(st));
   c.x_step = w[0];  // graph replays advance the device counter without the host mirror
   if (d_all_out)
-    *d_all_out = static_cast<const mcl3dl_result*>(c.xchg.p) + static_cast<size_t>(c.x_step & 1u) * c.xsink.world * c.x_local;
+    *d_all_out = static_cast<const mcl3dl_result*>(c.xchg.p) + static_cast<size_t>(c.x_step & 1u) * c.xt.world * c.x_local;
   if (failed_out)
-    *failed_out = w[7] != 0;
+    *failed_out = w[1] != 0;
   return MCL3DL_OK;
 }
 

@@ -37,27 +37,22 @@ __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v)
 // Where a kernel's writer lane stores its particle's record fields.  world == 0: the plain output array `out`.
 // world >= 1 (one process per GPU): the record exchange is folded into the kernels' epilogues — the writer
 // stores the fields straight into slot `rank` of EVERY rank's gathered array over NVLink (peer memory mapped with CUDA
-// IPC), so no collective and no copy kernel follows; sink_finish (below), run by the last CTA of the step's last kernel,
-// then publishes "rank r finished step s" and waits for the peers.
+// IPC), so no collective and no copy kernel follows; exchange_signal_kernel then publishes "rank r finished step s".
 // The gathered array is double-buffered by step parity (a peer may already be one step ahead); the parity of the
 // upcoming step is read from the device-side step counter, so the launch sequence is identical every step (CUDA graph).
 constexpr int kMaxPeers = 8;
 struct RecordSink
 {
   mcl3dl_result* base[kMaxPeers];  // every rank's array 0, already offset to this rank's slot (own buffer at [rank])
-  uint32_t* flags[kMaxPeers];      // base of every rank's flag array (this rank's own at [rank])
-  uint32_t* step;                  // completed-step counter of this rank (device memory; written by the signalling CTA)
-  unsigned int* sync;              // [0] [1] per-kernel CTA tickets (likelihood, beam), [2] kernels arrived, [3] error word
+  const uint32_t* step;            // completed-step counter of this rank (device memory)
   uint32_t parity_stride;          // records between array 0 and array 1 (= world * n_local)
-  int world, rank;
-  int n_kernels;                   // kernels of this step that carry the sink (1 or 2)
-  int slot;                        // this kernel's ticket slot: 0 likelihood, 1 beam
+  int world;
 };
 
 // offset of particle p's record inside a rank's array 0 (world >= 1) — the parity of the step about to complete
 __device__ __forceinline__ uint32_t sink_offset(const RecordSink& s, int p)
 {
-  return ((__ldcg(static_cast<const uint32_t*>(s.step)) + 1u) & 1u) * s.parity_stride + static_cast<uint32_t>(p);
+  return ((__ldcg(s.step) + 1u) & 1u) * s.parity_stride + static_cast<uint32_t>(p);
 }
 
 // likelihood-model fields (+ the beam model's (1, 0) when that model has no scan this update)
@@ -103,72 +98,6 @@ __device__ __forceinline__ void sink_store_beam(const RecordSink& s, mcl3dl_resu
         o->match_cnt = 0;
       }
     }
-}
-
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
-{
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
-{
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// The signalling half of the folded record exchange, called by EVERY thread at the end of a measurement kernel.
-// world == 0: nothing.  Otherwise the classic last-block pattern at system scope: every thread fences its (peer) stores,
-// the CTA takes a ticket, the last CTA of the kernel reports the kernel as arrived, and the last CTA of the LAST kernel of
-// the step (the two models run concurrently on two streams)
-//   (1) releases flag[rank] = step in every rank's buffer (fence.sys + st.release.sys), and
-//   (2) spins (ld.acquire.sys, bounded) until the `world` flags of its OWN buffer show >= step,
-// so when the step's kernels have retired, this rank's copy of the whole record array is complete: no collective, no
-// extra launch, no host.  Double buffering by step parity (sink_offset): a peer that is already one step ahead writes
-// the OTHER array; it cannot get two steps ahead because its next step waits for this rank's flag.  The step number
-// lives in device memory, so a captured CUDA graph replays unchanged.  (Measured at 2 GPUs, profiles/r02k_*: a separate
-// 32-thread signal kernel after the join cost ~10 us per step on a 28 us kernel.)
-__device__ __forceinline__ void sink_finish(const RecordSink& s)
-{
-  if (s.world == 0)
-    return;
-  __shared__ int role;
-  __threadfence_system();  // this thread's record stores (peer memory included) are performed
-  __syncthreads();
-  if (threadIdx.x == 0)
-  {
-    role = 0;
-    if (atomicAdd(s.sync + s.slot, 1u) == gridDim.x - 1)
-    {
-      s.sync[s.slot] = 0;  // ready for the next step (its kernels start after this step's have retired)
-      if (atomicAdd(s.sync + 2, 1u) == static_cast<unsigned>(s.n_kernels - 1))
-      {
-        s.sync[2] = 0;
-        role = 1;
-      }
-    }
-  }
-  __syncthreads();
-  if (!role)
-    return;
-  const uint32_t step = *s.step + 1u;
-  if (threadIdx.x < static_cast<unsigned>(s.world))
-  {
-    __threadfence_system();
-    st_release_sys(s.flags[threadIdx.x] + s.rank, step);
-    const uint32_t* mine = s.flags[s.rank] + threadIdx.x;
-    // steps increase monotonically; the difference is taken modulo 2^32.  Bounded: a peer that died must not hang
-    // this GPU (~2^22 polls of ~1 us, then the error word is set and the step completes with stale data)
-    long polls = 0;
-    while (static_cast<int32_t>(ld_acquire_sys(mine) - step) < 0)
-      if (++polls > (1L << 22))
-      {
-        atomicExch(s.sync + 3, 1u);
-        break;
-      }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0)
-    *s.step = step;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -325,7 +254,6 @@ __global__ void __launch_bounds__(kBlockThreads)
       atomicAdd(stats + 1, static_cast<unsigned long long>(q));
     }
   }
-  sink_finish(sink);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -586,7 +514,6 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
       atomicAdd(stats + 1, static_cast<unsigned long long>(q));
     }
   }
-  sink_finish(sink);
 }
 
 
@@ -807,7 +734,6 @@ __global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
       atomicAdd(stats + 1, static_cast<unsigned long long>(q));
     }
   }
-  sink_finish(sink);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -911,7 +837,6 @@ __global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
     if ((threadIdx.x & 31) == 0)
       atomicAdd(stats + 0, static_cast<unsigned long long>(r) * 4ull);  // counted as 8-byte index entries: 32 B per eval
   }
-  sink_finish(sink);
 }
 
 template <int TPP, bool STAGED>
@@ -997,7 +922,6 @@ __global__ void __launch_bounds__(kBlockThreads)
       atomicAdd(stats + 4, static_cast<unsigned long long>(c));
     }
   }
-  sink_finish(sink);
 }
 
 
@@ -1168,7 +1092,6 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
       atomicAdd(stats + 4, static_cast<unsigned long long>(z));
     }
   }
-  sink_finish(sink);
 }
 
 
@@ -1331,6 +1254,59 @@ __global__ void weight_finish_kernel(WeightPartial* __restrict__ partials, int n
     }
   }
   partials[n] = t;
+}
+
+// --------------------------------------------------------------------------------------------
+// Record exchange over peer memory, the signalling half (the data half is RecordSink: the measurement kernels store
+// their records into every rank's gathered array).  Every rank owns one buffer [2 x world * n_local records | flags]
+// that its peers have mapped (CUDA IPC over NVLink / NVSwitch).  After the two model kernels of step s have retired
+// (stream order; their peer stores are performed by then), ONE warp of this kernel
+//   (1) releases flag[rank] = s in every rank's buffer (fence.sys + st.release.sys), and
+//   (2) spins (ld.acquire.sys, bounded) until all `world` flags of its OWN buffer show >= s,
+// so when it retires this rank's copy of the whole array of step s is complete: no host involvement, no collective
+// library, one 32-thread launch.  Double buffering by step parity: a peer that is already one step ahead writes the
+// OTHER array; it cannot get two steps ahead because its next signal kernel waits for this rank's flag.
+// The step number lives in device memory (this kernel increments it), so a captured CUDA graph replays unchanged.
+struct PeerTable
+{
+  uint32_t* flags[kMaxPeers];  // base of every rank's flag array (this rank's own at [rank])
+  int world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(32)
+    exchange_signal_kernel(PeerTable t, uint32_t* __restrict__ step_ctr, unsigned int* __restrict__ err /* set to 1 on a timeout */)
+{
+  const uint32_t step = *step_ctr + 1u;
+  __syncwarp();
+  if (threadIdx.x < static_cast<unsigned>(t.world))
+  {
+    __threadfence_system();
+    st_release_sys(t.flags[threadIdx.x] + t.rank, step);
+    const uint32_t* mine = t.flags[t.rank] + threadIdx.x;
+    // steps increase monotonically; the difference is taken modulo 2^32.  Bounded: a peer that died must not hang
+    // this GPU (~2^22 polls of ~1 us, then the error word is set and the step completes with stale data)
+    long polls = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(mine) - step) < 0)
+      if (++polls > (1L << 22))
+      {
+        atomicExch(err, 1u);
+        break;
+      }
+  }
+  __syncwarp();
+  if (threadIdx.x == 0)
+    *step_ctr = step;
 }
 
 }  // namespace mcl3dl

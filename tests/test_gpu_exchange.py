@@ -1,5 +1,5 @@
 """The record exchange folded into the measurement kernels (csrc/kernels.cuh: RecordSink +
-sink_finish) against an NCCL all-gather, byte for byte — needs >= 2 GPUs on the box."""
+exchange_signal_kernel) against an NCCL all-gather, byte for byte — needs >= 2 GPUs on the box."""
 import os
 import subprocess
 import sys
