@@ -391,6 +391,7 @@ struct mcl3dl_engine
                             // round 1: off until the f2 parity tests have run with it)
   int field_mode = 0;  // 1: the likelihood model reads the trilinear distance volume (opt-in, inexact; MCL3DL_LIK_MODE=field)
   size_t field_max_bytes = size_t(24) << 30;  // MCL3DL_FIELD_MAX_MB
+  int lik_share = 4;  // CTA slots per SM the likelihood kernel takes while the beam kernel runs next to it (MCL3DL_LIK_SHARE)
   int nnf_kd_r2 = 1;  // MCL3DL_NNF_KD_R2=0: the NN field also covers the KD-tree raycaster's second search radius
   int nnf = 1;  // stage the NN field (exact per-voxel candidate lists) and use lik_kernel_nf; MCL3DL_NNF=0: the CSR window kernels
   size_t nnf_max_bytes = size_t(32) << 30;  // MCL3DL_NNF_MAX_MB: directory + candidates above this -> no field
@@ -557,8 +558,11 @@ int launch_lik_nf_t(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, 
 {
   constexpr int PPB = kBlockThreads / TPP;
   const int groups = (P + PPB - 1) / PPB;
-  // every CTA resident at once; CTAs loop when there are more particle groups than slots
-  const int grid = std::max(1, std::min(groups, c.sm_count * kNfCtasPerSm));
+  // every CTA resident at once; CTAs loop when there are more particle groups than slots.  When the beam kernel runs
+  // concurrently on the side stream (beam_defaults == 0: both models have a scan), the likelihood kernel takes only
+  // `lik_share` of the 4 CTA slots per SM, so that beam CTAs become resident next to it instead of behind it.
+  const int per_sm = beam_defaults ? kNfCtasPerSm : std::max(1, std::min(kNfCtasPerSm, eng->lik_share));
+  const int grid = std::max(1, std::min(groups, c.sm_count * per_sm));
   const size_t bytes = static_cast<size_t>(N) * 16;
   const bool ovf = eng->nnf_overflow_cells != 0;
   // the tile pays when several particles of the CTA (or several loop trips) read it; otherwise the scan comes from L2
@@ -1351,6 +1355,8 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     eng->update_one_sync = std::atoi(v) != 0;
   if (const char* v = std::getenv("MCL3DL_NNF"))
     eng->nnf = std::atoi(v) != 0;
+  if (const char* v = std::getenv("MCL3DL_LIK_SHARE"))
+    eng->lik_share = std::min(std::max(std::atoi(v), 1), 8);
   if (const char* v = std::getenv("MCL3DL_NNF_KD_R2"))
     eng->nnf_kd_r2 = std::atoi(v) != 0;
   if (const char* v = std::getenv("MCL3DL_LIK_MODE"))
