@@ -465,7 +465,8 @@ def device_leg(cx, workload, raycaster, steps, warmup, exchange="peer", graph=Tr
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
             ncu = json.load(f)
-        key = workload + ("" if raycaster == "dda" or not n_beam else "_kd") + ("_spread" if FORCE_SPREAD else "")
+        key = (workload + ("" if raycaster == "dda" or not n_beam else "_kd") + ("_spread" if FORCE_SPREAD else "")
+               + ("_field" if field else ""))
         ent = ncu.get(key, {})
         traffic = ent.get(dom + "_dram_bytes_per_launch")
         traffic_src = ent.get(dom + "_source")
