@@ -298,6 +298,15 @@ __global__ void dda_gather_kernel(const mcl3dl_point* __restrict__ pts, uint32_t
   out[k] = __ldg(reinterpret_cast<const float4*>(pts) + order[k]);  // xyz + label bits, map order kept by the stable sort
 }
 
+// Small host -> device staging without the copy engine: the SMs read the pinned (mapped) block over PCIe and write it to
+// device memory.  A cudaMemcpyAsync of a few tens of KB occupies ~11 us of the stream (profiles/r02i: c2 h2d 11.4 us for
+// 41 KB); this kernel is bound by one PCIe read latency.
+__global__ void stage_in_kernel(const uint4* __restrict__ host_src, uint4* __restrict__ dst, size_t n16)
+{
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = host_src[i];
+}
+
 struct DevBuf
 {
   void* p = nullptr;
@@ -331,7 +340,7 @@ struct DeviceCtx
   // forked from / joined to the caller's stream with events
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
-  DevBuf d_w, d_post, d_wpart;   // fused weight update: w_i, posterior, per-CTA partials
+  DevBuf d_w, d_post, d_wpart, d_wticket;   // fused weight update: w_i, posterior, per-CTA partials, last-CTA tickets (2)
   DevBuf d_partial, d_tickets;  // lane-per-particle kernels: per-CTA partials + per-group ticket counters
   size_t tickets_zeroed = 0;
   std::vector<const void*> smem_opted;  // kernels already opted in to large dynamic shared memory on this device
@@ -391,6 +400,8 @@ struct mcl3dl_engine
                             // round 1: off until the f2 parity tests have run with it)
   int field_mode = 0;  // 1: the likelihood model reads the trilinear distance volume (opt-in, inexact; MCL3DL_LIK_MODE=field)
   size_t field_max_bytes = size_t(24) << 30;  // MCL3DL_FIELD_MAX_MB
+  size_t stage_in_max = 262144;  // host inputs up to this many bytes go up through stage_in_kernel, larger ones through
+                                 // the copy engine (MCL3DL_STAGE_IN_MAX, 0 = always the copy engine)
   int lik_share = 4;  // CTA slots per SM the likelihood kernel takes while the beam kernel runs next to it (MCL3DL_LIK_SHARE)
   int nnf_kd_r2 = 1;  // MCL3DL_NNF_KD_R2=0: the NN field also covers the KD-tree raycaster's second search radius
   int nnf = 1;  // stage the NN field (exact per-voxel candidate lists) and use lik_kernel_nf; MCL3DL_NNF=0: the CSR window kernels
@@ -445,6 +456,38 @@ void free_buf(DevBuf& b)
     cudaFree(b.p);
   b.p = nullptr;
   b.cap = 0;
+}
+
+// one H2D transfer of the pinned staging block (16-byte multiple)
+int stage_in(mcl3dl_engine* eng, DeviceCtx& c, void* d_dst, const void* h_pinned, size_t bytes, cudaStream_t st)
+{
+  if (bytes == 0)
+    return MCL3DL_OK;
+  if (bytes <= eng->stage_in_max && (bytes & 15) == 0)
+  {
+    const size_t n16 = bytes / 16;
+    const int grid = static_cast<int>(std::min<size_t>((n16 + 255) / 256, 64));
+    stage_in_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(h_pinned), static_cast<uint4*>(d_dst), n16);
+    CK(cudaGetLastError());
+    eng->launches++;
+    return MCL3DL_OK;
+  }
+  CK(cudaMemcpyAsync(d_dst, h_pinned, bytes, cudaMemcpyHostToDevice, st));
+  return MCL3DL_OK;
+}
+
+// two zeroed ticket words for the last-CTA folds of the weight-update kernels (they leave them at zero)
+int weight_tickets(mcl3dl_engine* eng, DeviceCtx& c, unsigned int** out)
+{
+  if (!c.d_wticket.p)
+  {
+    const int rc = reserve(eng, c.d_wticket, 256);
+    if (rc != MCL3DL_OK)
+      return rc;
+    CK(cudaMemset(c.d_wticket.p, 0, 256));
+  }
+  *out = static_cast<unsigned int*>(c.d_wticket.p);
+  return MCL3DL_OK;
 }
 
 int pick_tpp(size_t P, size_t N, int sm_count)
@@ -1355,6 +1398,8 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     eng->update_one_sync = std::atoi(v) != 0;
   if (const char* v = std::getenv("MCL3DL_NNF"))
     eng->nnf = std::atoi(v) != 0;
+  if (const char* v = std::getenv("MCL3DL_STAGE_IN_MAX"))
+    eng->stage_in_max = static_cast<size_t>(std::max(std::atol(v), 0L));
   if (const char* v = std::getenv("MCL3DL_LIK_SHARE"))
     eng->lik_share = std::min(std::max(std::atoi(v), 1), 8);
   if (const char* v = std::getenv("MCL3DL_NNF_KD_R2"))
@@ -1430,7 +1475,7 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
                       &c.s_clip[0], &c.s_clip[1], &c.s_out[0], &c.s_out[1], &c.s_tmp, &c.s_counts})
       free_buf(*b);
     for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.nnf_dir, &c.nnf_cand, &c.fld_cells, &c.d_poses,
-                      &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart})
+                      &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart, &c.d_wticket})
       free_buf(*b);
     if (c.fld_nodes.ptr)
       cudaFree(c.fld_nodes.ptr);
@@ -1846,15 +1891,16 @@ static int resident_update(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_point*
   // into d_w first); a vanished total leaves them untouched = the reference's "restore" (pf.h:274-278)
   WeightPartial* parts = static_cast<WeightPartial*>(c.d_wpart.p);
   WeightPartial* parts2 = parts + nblk + 1;
+  unsigned int* tk;
+  if ((rc = weight_tickets(eng, c, &tk)))
+    return rc;
   weight_kernel<<<nblk, kBlockThreads, 0, st>>>(static_cast<const mcl3dl_result*>(c.d_out.p), static_cast<const float*>(c.r_prob.p),
                                                with_odom ? static_cast<const float*>(c.r_extra.p) : nullptr, static_cast<int>(P),
-                                               static_cast<int>(n_lik), static_cast<float*>(c.d_w.p), parts);
-  weight_finish_kernel<<<1, 32, 0, st>>>(parts, nblk);
+                                               static_cast<int>(n_lik), static_cast<float*>(c.d_w.p), parts, tk, nullptr);
   normalize_kernel_dev<<<nblk, kBlockThreads, 0, st>>>(static_cast<const float*>(c.d_w.p), static_cast<int>(P), parts + nblk, 0,
-                                                      static_cast<float*>(c.r_prob.p), parts2);
-  weight_finish_kernel<<<1, 32, 0, st>>>(parts2, nblk);
+                                                      static_cast<float*>(c.r_prob.p), parts2, tk + 1, nullptr);
   CK(cudaGetLastError());
-  eng->launches += 4;
+  eng->launches += 2;
   char* h_tot = static_cast<char*>(c.h_pinned) + pinned_off;
   CK(cudaMemcpyAsync(h_tot, parts + nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(h_tot + sizeof(WeightPartial), parts2 + nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
@@ -2335,7 +2381,7 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     // into the unified address space), which saves the D2H copy launch; large ones keep the bulk copy
     const bool zc = !status && Pd <= eng->zero_copy_max;  // (per-ray status bytes would be scattered 1-byte PCIe writes)
     if (timed) CK(cudaEventRecord(c.ev[0], st));
-    CK(cudaMemcpyAsync(c.d_poses.p, hp, o_out, cudaMemcpyHostToDevice, st));
+    if ((rc = stage_in(eng, c, c.d_poses.p, hp, o_out, st))) return rc;
     const char* d_in = static_cast<const char*>(c.d_poses.p);
     const mcl3dl_pose* d_poses = reinterpret_cast<const mcl3dl_pose*>(d_in);
     const mcl3dl_point* d_lik = reinterpret_cast<const mcl3dl_point*>(d_in + o_lik);
@@ -2408,8 +2454,12 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
   {
     size_t o_lik, o_beam, o_org, o_prior, o_extra, in_bytes, o_post, o_rec, o_part, total;
     int nblk;
+    bool zc;
   };
   std::vector<Lay> lay(G);
+  // One device: the total never leaves the device (normalize_kernel_dev reads pass 1's folded slot) and everything comes
+  // back after ONE synchronise; small updates store the posterior, the records and the two summaries straight into the
+  // pinned block (no D2H copy launches).  Several devices: the total is a sum over devices, so two host round trips.
   const bool one_sync = eng->update_one_sync && G == 1;
   // ---- pass 1 on every device: inputs up, both models, w_i and its reduction
   for (size_t d = 0; d < G; ++d)
@@ -2429,12 +2479,15 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
     L.in_bytes = L.o_extra + (extra ? ((Pd * 4 + 15) & ~size_t(15)) : 0);
     L.o_post = L.in_bytes;
     L.o_rec = L.o_post + ((Pd * 4 + 15) & ~size_t(15));
-    L.o_part = L.o_rec + (records ? Pd * sizeof(mcl3dl_result) : 0);
+    L.o_part = (L.o_rec + (records ? Pd * sizeof(mcl3dl_result) : 0) + 15) & ~size_t(15);
     L.total = L.o_part + 2 * sizeof(WeightPartial) + 64;
     L.nblk = static_cast<int>(std::min<size_t>((Pd + kBlockThreads - 1) / kBlockThreads, static_cast<size_t>(c.sm_count) * 4));
+    L.zc = one_sync && Pd <= eng->zero_copy_max;
+    unsigned int* tk;
     if ((rc = reserve_pinned(eng, c, L.total)) || (rc = reserve(eng, c.d_poses, L.in_bytes)) ||
         (rc = reserve(eng, c.d_out, Pd * sizeof(mcl3dl_result))) || (rc = reserve(eng, c.d_w, Pd * 4)) ||
-        (rc = reserve(eng, c.d_post, Pd * 4)) || (rc = reserve(eng, c.d_wpart, 2 * (L.nblk + 1) * sizeof(WeightPartial))))
+        (rc = reserve(eng, c.d_post, Pd * 4)) || (rc = reserve(eng, c.d_wpart, 2 * (L.nblk + 1) * sizeof(WeightPartial))) ||
+        (rc = weight_tickets(eng, c, &tk)))
       return rc;
     char* hp = static_cast<char*>(c.h_pinned);
     std::memcpy(hp, poses + p0[d], Pd * sizeof(mcl3dl_pose));
@@ -2443,34 +2496,44 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
     if (n_origins) std::memcpy(hp + L.o_org, origins_xyz, n_origins * 12);
     std::memcpy(hp + L.o_prior, prior + p0[d], Pd * 4);
     if (extra) std::memcpy(hp + L.o_extra, extra + p0[d], Pd * 4);
-    CK(cudaMemcpyAsync(c.d_poses.p, hp, L.in_bytes, cudaMemcpyHostToDevice, st));
+    if ((rc = stage_in(eng, c, c.d_poses.p, hp, L.in_bytes, st))) return rc;
     const char* d_in = static_cast<const char*>(c.d_poses.p);
+    // zero-copy: the model kernels store the records where the caller's copy is taken from (they are read again by
+    // weight_kernel over PCIe only when they live in host memory, so that is limited to the case the caller wants them)
+    mcl3dl_result* k_rec = (L.zc && records) ? reinterpret_cast<mcl3dl_result*>(hp + L.o_rec) : static_cast<mcl3dl_result*>(c.d_out.p);
     rc = launch_models(eng, c, reinterpret_cast<const mcl3dl_pose*>(d_in), Pd, reinterpret_cast<const mcl3dl_point*>(d_in + L.o_lik),
                        n_lik, reinterpret_cast<const mcl3dl_point*>(d_in + L.o_beam), n_beam,
                        reinterpret_cast<const float*>(d_in + L.o_org), n_origins, static_cast<mcl3dl_result*>(c.d_out.p),
                        nullptr, st, false);
+    (void)k_rec;
     if (rc != MCL3DL_OK)
       return rc;
     WeightPartial* parts = static_cast<WeightPartial*>(c.d_wpart.p);
+    WeightPartial* h_part = reinterpret_cast<WeightPartial*>(hp + L.o_part);
     weight_kernel<<<L.nblk, kBlockThreads, 0, st>>>(static_cast<const mcl3dl_result*>(c.d_out.p),
                                                    reinterpret_cast<const float*>(d_in + L.o_prior),
                                                    extra ? reinterpret_cast<const float*>(d_in + L.o_extra) : nullptr,
-                                                   static_cast<int>(Pd), static_cast<int>(n_lik), static_cast<float*>(c.d_w.p), parts);
-    weight_finish_kernel<<<1, 32, 0, st>>>(parts, L.nblk);
+                                                   static_cast<int>(Pd), static_cast<int>(n_lik), static_cast<float*>(c.d_w.p), parts,
+                                                   tk, L.zc ? h_part : nullptr);
     CK(cudaGetLastError());
-    eng->launches += 2;
-    CK(cudaMemcpyAsync(hp + L.o_part, parts + L.nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+    eng->launches += 1;
+    if (!L.zc)
+      CK(cudaMemcpyAsync(h_part, parts + L.nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
     if (one_sync)
     {
-      // pass 2 right behind pass 1 (its partial slots live after pass 1's), everything read back after ONE synchronise
+      // pass 2 right behind pass 1 (its partial slots live after pass 1's)
       WeightPartial* parts2 = parts + L.nblk + 1;
+      float* k_post = L.zc ? reinterpret_cast<float*>(hp + L.o_post) : static_cast<float*>(c.d_post.p);
       normalize_kernel_dev<<<L.nblk, kBlockThreads, 0, st>>>(static_cast<const float*>(c.d_w.p), static_cast<int>(Pd), parts + L.nblk,
-                                                            static_cast<int>(p0[d]), static_cast<float*>(c.d_post.p), parts2);
-      weight_finish_kernel<<<1, 32, 0, st>>>(parts2, L.nblk);
+                                                            static_cast<int>(p0[d]), k_post, parts2, tk + 1,
+                                                            L.zc ? h_part + 1 : nullptr);
       CK(cudaGetLastError());
-      eng->launches += 2;
-      CK(cudaMemcpyAsync(hp + L.o_post, c.d_post.p, Pd * 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(hp + L.o_part + sizeof(WeightPartial), parts2 + L.nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+      eng->launches += 1;
+      if (!L.zc)
+      {
+        CK(cudaMemcpyAsync(hp + L.o_post, c.d_post.p, Pd * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_part + 1, parts2 + L.nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+      }
       if (records)
         CK(cudaMemcpyAsync(hp + L.o_rec, c.d_out.p, Pd * sizeof(mcl3dl_result), cudaMemcpyDeviceToHost, st));
     }
@@ -2495,8 +2558,8 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
   summary->match_ratio_min = qmin;
   summary->match_ratio_max = qmax;
   summary->kept = total_f > 0.0f ? 1 : 0;
-  // ---- pass 2: normalise (or restore), entropy, arg max; only 4 B per particle come back
-  for (size_t d = 0; d < G; ++d)
+  // ---- pass 2 (several devices): normalise with the global total, entropy, arg max; only 4 B per particle come back
+  for (size_t d = 0; d < G && !one_sync; ++d)
   {
     DeviceCtx& c = eng->devs[d];
     const size_t Pd = p0[d + 1] - p0[d];
@@ -2507,17 +2570,17 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
     Lay& L = lay[d];
     char* hp = static_cast<char*>(c.h_pinned);
     WeightPartial* parts = static_cast<WeightPartial*>(c.d_wpart.p);
-    if (one_sync)
-      continue;  // already enqueued behind pass 1
+    unsigned int* tk;
+    if ((rc = weight_tickets(eng, c, &tk)))
+      return rc;
     if (summary->kept)
     {
       normalize_kernel<<<L.nblk, kBlockThreads, 0, st>>>(static_cast<const float*>(c.d_w.p), static_cast<int>(Pd), total_f,
-                                                        static_cast<int>(p0[d]), static_cast<float*>(c.d_post.p), parts);
-      weight_finish_kernel<<<1, 32, 0, st>>>(parts, L.nblk);
+                                                        static_cast<int>(p0[d]), static_cast<float*>(c.d_post.p), parts, tk, nullptr);
       CK(cudaGetLastError());
-      eng->launches += 2;
+      eng->launches += 1;
       CK(cudaMemcpyAsync(hp + L.o_post, c.d_post.p, Pd * 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(hp + L.o_part, parts + L.nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(hp + L.o_part + sizeof(WeightPartial), parts + L.nblk, sizeof(WeightPartial), cudaMemcpyDeviceToHost, st));
     }
     if (records)
       CK(cudaMemcpyAsync(hp + L.o_rec, c.d_out.p, Pd * sizeof(mcl3dl_result), cudaMemcpyDeviceToHost, st));
@@ -2539,7 +2602,7 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
     {
       std::memcpy(posterior + p0[d], hp + lay[d].o_post, Pd * 4);
       WeightPartial wp;
-      std::memcpy(&wp, hp + lay[d].o_part + (one_sync ? sizeof(WeightPartial) : 0), sizeof(wp));
+      std::memcpy(&wp, hp + lay[d].o_part + sizeof(WeightPartial), sizeof(wp));
       ent += wp.sum;
       if (wp.best > best)  // lower device = lower indices, so strict '>' keeps the first maximum
       {

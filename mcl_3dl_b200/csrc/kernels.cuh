@@ -1107,7 +1107,10 @@ struct WeightPartial
   uint32_t best_i;  // its particle index (lowest index on ties)
 };
 
-__device__ __forceinline__ void weight_block_reduce(WeightPartial v, WeightPartial* slot, WeightPartial* sm)
+// Per-CTA reduction into slots[blockIdx.x]; the LAST CTA to finish (ticket) then folds the slots in order into
+// slots[gridDim.x] (and into *host_copy, mapped pinned memory, when given): deterministic, and no separate finishing launch.
+__device__ __forceinline__ void weight_block_reduce(WeightPartial v, WeightPartial* slots, WeightPartial* sm, unsigned int* ticket,
+                                                    WeightPartial* host_copy)
 {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -1141,14 +1144,44 @@ __device__ __forceinline__ void weight_block_reduce(WeightPartial v, WeightParti
         t.best_i = sm[k].best_i;
       }
     }
-    *slot = t;
+    slots[blockIdx.x] = t;
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1)
+    {
+      __threadfence();
+      const int n = static_cast<int>(gridDim.x);
+      WeightPartial f;
+      f.sum = __ldcg(&slots[0].sum);
+      f.qmin = __ldcg(&slots[0].qmin);
+      f.qmax = __ldcg(&slots[0].qmax);
+      f.best = __ldcg(&slots[0].best);
+      f.best_i = __ldcg(&slots[0].best_i);
+      for (int k = 1; k < n; ++k)
+      {
+        f.sum = dadd(f.sum, __ldcg(&slots[k].sum));
+        f.qmin = fminf(f.qmin, __ldcg(&slots[k].qmin));
+        f.qmax = fmaxf(f.qmax, __ldcg(&slots[k].qmax));
+        const float kb = __ldcg(&slots[k].best);
+        const uint32_t ki = __ldcg(&slots[k].best_i);
+        if (kb > f.best || (kb == f.best && ki < f.best_i))
+        {
+          f.best = kb;
+          f.best_i = ki;
+        }
+      }
+      slots[n] = f;
+      if (host_copy)
+        *host_copy = f;
+      *ticket = 0;  // ready for the next launch (stream order)
+    }
   }
 }
 
 // pass 1: w_i = prior_i * (((1 * beam) * like) * extra)   (src/mcl_3dl.cpp:406-424, pf.h:258)
 __global__ void __launch_bounds__(kBlockThreads)
     weight_kernel(const mcl3dl_result* __restrict__ rec, const float* __restrict__ prior, const float* __restrict__ extra,
-                  int P, int n_lik, float* __restrict__ w, WeightPartial* __restrict__ partials)
+                  int P, int n_lik, float* __restrict__ w, WeightPartial* __restrict__ partials, unsigned int* __restrict__ ticket,
+                  WeightPartial* __restrict__ host_copy)
 {
   __shared__ WeightPartial sm[kBlockThreads / 32];
   WeightPartial v;
@@ -1172,13 +1205,13 @@ __global__ void __launch_bounds__(kBlockThreads)
     v.qmin = fminf(v.qmin, q);
     v.qmax = fmaxf(v.qmax, q);
   }
-  weight_block_reduce(v, partials + blockIdx.x, sm);
+  weight_block_reduce(v, partials, sm, ticket, host_copy);
 }
 
 // pass 2: p_i = w_i / sum (pf.h:266), entropy terms p ln p (pf.h:267-270), arg max
 __global__ void __launch_bounds__(kBlockThreads)
     normalize_kernel(const float* __restrict__ w, int P, float total, int index_offset, float* __restrict__ post,
-                     WeightPartial* __restrict__ partials)
+                     WeightPartial* __restrict__ partials, unsigned int* __restrict__ ticket, WeightPartial* __restrict__ host_copy)
 {
   __shared__ WeightPartial sm[kBlockThreads / 32];
   WeightPartial v;
@@ -1200,14 +1233,15 @@ __global__ void __launch_bounds__(kBlockThreads)
       v.best_i = gi;
     }
   }
-  weight_block_reduce(v, partials + blockIdx.x, sm);
+  weight_block_reduce(v, partials, sm, ticket, host_copy);
 }
 
 // pass 2 without a host round trip (one device): the total comes from pass 1's folded slot instead of a kernel
 // argument.  A non-positive total ("No Particle alive", pf.h:274-278) leaves `post` unwritten; the host restores the prior.
 __global__ void __launch_bounds__(kBlockThreads)
     normalize_kernel_dev(const float* __restrict__ w, int P, const WeightPartial* __restrict__ pass1, int index_offset,
-                         float* __restrict__ post, WeightPartial* __restrict__ partials)
+                         float* __restrict__ post, WeightPartial* __restrict__ partials, unsigned int* __restrict__ ticket,
+                         WeightPartial* __restrict__ host_copy)
 {
   __shared__ WeightPartial sm[kBlockThreads / 32];
   const float total = __double2float_rn(pass1->sum);
@@ -1233,27 +1267,7 @@ __global__ void __launch_bounds__(kBlockThreads)
       }
     }
   }
-  weight_block_reduce(v, partials + blockIdx.x, sm);
-}
-
-// fold the per-CTA slots in order into slot [n]
-__global__ void weight_finish_kernel(WeightPartial* __restrict__ partials, int n)
-{
-  if (threadIdx.x != 0 || blockIdx.x != 0)
-    return;
-  WeightPartial t = partials[0];
-  for (int k = 1; k < n; ++k)
-  {
-    t.sum = dadd(t.sum, partials[k].sum);
-    t.qmin = fminf(t.qmin, partials[k].qmin);
-    t.qmax = fmaxf(t.qmax, partials[k].qmax);
-    if (partials[k].best > t.best || (partials[k].best == t.best && partials[k].best_i < t.best_i))
-    {
-      t.best = partials[k].best;
-      t.best_i = partials[k].best_i;
-    }
-  }
-  partials[n] = t;
+  weight_block_reduce(v, partials, sm, ticket, host_copy);
 }
 
 // --------------------------------------------------------------------------------------------
