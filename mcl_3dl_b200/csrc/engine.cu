@@ -298,15 +298,6 @@ __global__ void dda_gather_kernel(const mcl3dl_point* __restrict__ pts, uint32_t
   out[k] = __ldg(reinterpret_cast<const float4*>(pts) + order[k]);  // xyz + label bits, map order kept by the stable sort
 }
 
-// Small host -> device staging without the copy engine: the SMs read the pinned (mapped) block over PCIe and write it to
-// device memory.  A cudaMemcpyAsync of a few tens of KB occupies ~11 us of the stream (profiles/r02i: c2 h2d 11.4 us for
-// 41 KB); this kernel is bound by one PCIe read latency.
-__global__ void stage_in_kernel(const uint4* __restrict__ host_src, uint4* __restrict__ dst, size_t n16)
-{
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    dst[i] = host_src[i];
-}
-
 struct DevBuf
 {
   void* p = nullptr;
@@ -400,8 +391,6 @@ struct mcl3dl_engine
                             // round 1: off until the f2 parity tests have run with it)
   int field_mode = 0;  // 1: the likelihood model reads the trilinear distance volume (opt-in, inexact; MCL3DL_LIK_MODE=field)
   size_t field_max_bytes = size_t(24) << 30;  // MCL3DL_FIELD_MAX_MB
-  size_t stage_in_max = 262144;  // host inputs up to this many bytes go up through stage_in_kernel, larger ones through
-                                 // the copy engine (MCL3DL_STAGE_IN_MAX, 0 = always the copy engine)
   int lik_share = 4;  // CTA slots per SM the likelihood kernel takes while the beam kernel runs next to it (MCL3DL_LIK_SHARE)
   int nnf_kd_r2 = 1;  // MCL3DL_NNF_KD_R2=0: the NN field also covers the KD-tree raycaster's second search radius
   int nnf = 1;  // stage the NN field (exact per-voxel candidate lists) and use lik_kernel_nf; MCL3DL_NNF=0: the CSR window kernels
@@ -456,24 +445,6 @@ void free_buf(DevBuf& b)
     cudaFree(b.p);
   b.p = nullptr;
   b.cap = 0;
-}
-
-// one H2D transfer of the pinned staging block (16-byte multiple)
-int stage_in(mcl3dl_engine* eng, DeviceCtx& c, void* d_dst, const void* h_pinned, size_t bytes, cudaStream_t st)
-{
-  if (bytes == 0)
-    return MCL3DL_OK;
-  if (bytes <= eng->stage_in_max && (bytes & 15) == 0)
-  {
-    const size_t n16 = bytes / 16;
-    const int grid = static_cast<int>(std::min<size_t>((n16 + 255) / 256, 64));
-    stage_in_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(h_pinned), static_cast<uint4*>(d_dst), n16);
-    CK(cudaGetLastError());
-    eng->launches++;
-    return MCL3DL_OK;
-  }
-  CK(cudaMemcpyAsync(d_dst, h_pinned, bytes, cudaMemcpyHostToDevice, st));
-  return MCL3DL_OK;
 }
 
 // two zeroed ticket words for the last-CTA folds of the weight-update kernels (they leave them at zero)
@@ -1398,8 +1369,6 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     eng->update_one_sync = std::atoi(v) != 0;
   if (const char* v = std::getenv("MCL3DL_NNF"))
     eng->nnf = std::atoi(v) != 0;
-  if (const char* v = std::getenv("MCL3DL_STAGE_IN_MAX"))
-    eng->stage_in_max = static_cast<size_t>(std::max(std::atol(v), 0L));
   if (const char* v = std::getenv("MCL3DL_LIK_SHARE"))
     eng->lik_share = std::min(std::max(std::atoi(v), 1), 8);
   if (const char* v = std::getenv("MCL3DL_NNF_KD_R2"))
@@ -2381,7 +2350,8 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     // into the unified address space), which saves the D2H copy launch; large ones keep the bulk copy
     const bool zc = !status && Pd <= eng->zero_copy_max;  // (per-ray status bytes would be scattered 1-byte PCIe writes)
     if (timed) CK(cudaEventRecord(c.ev[0], st));
-    if ((rc = stage_in(eng, c, c.d_poses.p, hp, o_out, st))) return rc;
+    // (an SM copy kernel reading the mapped block instead of the copy engine measured the same: profiles/r02p_e2e.txt)
+    CK(cudaMemcpyAsync(c.d_poses.p, hp, o_out, cudaMemcpyHostToDevice, st));
     const char* d_in = static_cast<const char*>(c.d_poses.p);
     const mcl3dl_pose* d_poses = reinterpret_cast<const mcl3dl_pose*>(d_in);
     const mcl3dl_point* d_lik = reinterpret_cast<const mcl3dl_point*>(d_in + o_lik);
@@ -2496,7 +2466,7 @@ int mcl3dl_measure_update(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P
     if (n_origins) std::memcpy(hp + L.o_org, origins_xyz, n_origins * 12);
     std::memcpy(hp + L.o_prior, prior + p0[d], Pd * 4);
     if (extra) std::memcpy(hp + L.o_extra, extra + p0[d], Pd * 4);
-    if ((rc = stage_in(eng, c, c.d_poses.p, hp, L.in_bytes, st))) return rc;
+    CK(cudaMemcpyAsync(c.d_poses.p, hp, L.in_bytes, cudaMemcpyHostToDevice, st));
     const char* d_in = static_cast<const char*>(c.d_poses.p);
     // zero-copy: the model kernels store the records where the caller's copy is taken from (they are read again by
     // weight_kernel over PCIe only when they live in host memory, so that is limited to the case the caller wants them)
