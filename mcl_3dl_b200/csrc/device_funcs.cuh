@@ -77,7 +77,7 @@ __device__ __forceinline__ void near_mark_point(const NearBitsDev& f, uint32_t* 
 }
 
 // Host side: extent of a field for search radius r (> 0) and dilation k (1..15) over the rescaled bounding box.
-// The cell edge is doubled until the field fits max_bytes and 65 536 cells per axis (coarser is still conservative).
+// The cell edge is doubled until the field fits max_bytes and 16 384 * k cells per axis (coarser is still conservative).
 inline bool near_layout(NearBitsDev& f, float r, int k, const float sc_min[3], const float sc_max[3], size_t max_bytes)
 {
   if (!(r > 0.0f) || k < 1 || k > 15)
@@ -92,7 +92,10 @@ inline bool near_layout(NearBitsDev& f, float r, int k, const float sc_min[3], c
     {
       org[a] = sc_min[a] - (static_cast<float>(k) + 0.5f) * ef;
       dims[a] = floor((static_cast<double>(sc_max[a]) - org[a]) / ef) + k + 2;
-      ok = ok && dims[a] >= 1.0 && dims[a] <= 65536.0;
+      // the 1 % margin of the cell edge must cover the float rounding of near_cell() (a subtraction and a multiplication:
+      // ~1.2e-7 x the cell index each, twice for a difference of two cells) against 0.01 cells / k of slack per cell of
+      // distance: indices up to 2^14 * k keep the error below 0.4 of the margin
+      ok = ok && dims[a] >= 1.0 && dims[a] <= 16384.0 * k;
     }
     if (!ok)
       continue;

@@ -1720,7 +1720,11 @@ static int launch_models(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* po
   {
     rc = launch_lik(eng, c, poses, P, lik, n_lik, out, n_beam == 0, st, sink);
     if (rc != MCL3DL_OK)
+    {
+      if (both)
+        cudaStreamWaitEvent(st, c.ev_join, 0);  // the side stream is joined on the error path as well
       return rc;
+    }
   }
   if (timed) CK(cudaEventRecord(c.ev[3], st));
   if (both) CK(cudaStreamWaitEvent(st, c.ev_join, 0));

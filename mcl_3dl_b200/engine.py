@@ -221,8 +221,13 @@ class Engine:
         except Exception:
             pass
 
-    def set_map(self, map_pts, lik=None, beam=None, stamp=1):
+    def set_map(self, map_pts, lik=None, beam=None, stamp=None):
+        """stamp: the cloud's header.stamp, the reference's rebuild trigger (same stamp, size and params = no-op).
+        None: a fresh stamp per call (as the C++ adapter does), so that a different cloud is never mistaken for the old."""
         map_pts = np.ascontiguousarray(map_pts, dtype=POINT)
+        if stamp is None:
+            self._stamp = getattr(self, "_stamp", 0) + 1
+            stamp = (1 << 40) + self._stamp
         self._check(self.L.mcl3dl_set_map(self.h, _ptr(map_pts), len(map_pts), stamp,
                                           C.byref(lik) if lik is not None else None,
                                           C.byref(beam) if beam is not None else None))

@@ -13,6 +13,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_usable():
+    """A CUDA device and the engine library: without them `gpu`-marked tests are skipped, not failed."""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return False
+    except Exception:
+        return False
+    return os.path.exists(os.path.join(ROOT, "mcl_3dl_b200", "libmcl3dl_b200.so"))
+
+
+def pytest_collection_modifyitems(config, items):
+    if any(it.get_closest_marker("gpu") for it in items) and not _cuda_usable():
+        skip = pytest.mark.skip(reason="needs a CUDA device (run on the B200 box with -m gpu)")
+        for it in items:
+            if it.get_closest_marker("gpu"):
+                it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def port():
     """The repo-owned CPU restatement (oracle/libmcl3dl_oracle.so), built on demand."""
