@@ -333,6 +333,8 @@ struct DeviceCtx
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
   DevBuf d_w, d_post, d_wpart, d_wticket;   // fused weight update: w_i, posterior, per-CTA partials, last-CTA tickets (2)
   DevBuf d_partial, d_tickets;  // lane-per-particle kernels: per-CTA partials + per-group ticket counters
+  DevBuf d_tally, d_queue;      // dynamic-queue beam kernel: per-particle integer tallies, item counter (left at zero)
+  size_t tally_zeroed = 0;
   size_t tickets_zeroed = 0;
   std::vector<const void*> smem_opted;  // kernels already opted in to large dynamic shared memory on this device
   // resident particle set (mcl3dl_particles_*): two state buffers (resampling writes the other one), probabilities,
@@ -391,6 +393,9 @@ struct mcl3dl_engine
                             // round 1: off until the f2 parity tests have run with it)
   int field_mode = 0;  // 1: the likelihood model reads the trilinear distance volume (opt-in, inexact; MCL3DL_LIK_MODE=field)
   size_t field_max_bytes = size_t(24) << 30;  // MCL3DL_FIELD_MAX_MB
+  int beam_dq = 2;  // beam kernel: 2 = by job size (dynamic queue from 16 384 rays up: c3 118 -> 107 us, c3_kd 266 -> 232 us,
+                    // profiles/r02r_ab.jsonl; the static kernel is a little faster on tiny jobs), 1 = MCL3DL_BEAM=dq, 0 = MCL3DL_BEAM=pl
+  int beam_dq_ppl = 0;  // MCL3DL_BEAM_DQ_PPL: rays per item (0 = chosen from the job size)
   int lik_share = 4;  // CTA slots per SM the likelihood kernel takes while the beam kernel runs next to it (MCL3DL_LIK_SHARE)
   int nnf_kd_r2 = 1;  // MCL3DL_NNF_KD_R2=0: the NN field also covers the KD-tree raycaster's second search radius
   int nnf = 1;  // stage the NN field (exact per-voxel candidate lists) and use lik_kernel_nf; MCL3DL_NNF=0: the CSR window kernels
@@ -784,6 +789,52 @@ int launch_beam_pl(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, s
   return MCL3DL_OK;
 }
 
+int launch_beam_dq(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
+                   const float* origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st, const RecordSink& sink)
+{
+  const size_t groups = (P + 31) / 32;
+  const int grid = c.sm_count * 4;  // the resident CTAs (64 registers)
+  const size_t warps = static_cast<size_t>(grid) * kPlWarps;
+  // ~4 items per resident warp so that the queue can balance, 1..16 rays per item
+  size_t ppl = eng->beam_dq_ppl ? static_cast<size_t>(eng->beam_dq_ppl) : (N * groups + 4 * warps - 1) / (4 * warps);
+  ppl = std::min<size_t>(std::max<size_t>(ppl, 1), 16);
+  const int n_chunks = static_cast<int>(std::max<size_t>((N + ppl - 1) / ppl, 1));
+  int rc;
+  const size_t tally_bytes = std::max<size_t>(P, 1) * 12, ticket_bytes = std::max<size_t>(groups * 4, 4096);
+  if (tally_bytes > c.d_tally.cap || !c.d_tally.p)
+  {
+    if ((rc = reserve(eng, c.d_tally, tally_bytes)))
+      return rc;
+    CK(cudaMemsetAsync(c.d_tally.p, 0, c.d_tally.cap, st));  // the kernel leaves them at zero afterwards
+  }
+  if (ticket_bytes > c.d_tickets.cap || !c.d_tickets.p)
+  {
+    if ((rc = reserve(eng, c.d_tickets, ticket_bytes)))
+      return rc;
+    CK(cudaMemsetAsync(c.d_tickets.p, 0, c.d_tickets.cap, st));
+  }
+  if (!c.d_queue.p)
+  {
+    if ((rc = reserve(eng, c.d_queue, 256)))
+      return rc;
+    CK(cudaMemsetAsync(c.d_queue.p, 0, 256, st));
+  }
+#define DQ_LAUNCH(KD)                                                                                                              \
+  beam_kernel_dq<KD><<<grid, kBlockThreads, 0, st>>>(poses, static_cast<int>(P), reinterpret_cast<const float4*>(scan),             \
+                                                     static_cast<int>(N), origins, c.dda, c.kd, c.nn, out, status, lik_defaults,   \
+                                                     c.stats_ptr(), static_cast<int>(ppl), n_chunks,                               \
+                                                     static_cast<uint32_t*>(c.d_tally.p), static_cast<unsigned int*>(c.d_tickets.p), \
+                                                     static_cast<unsigned int*>(c.d_queue.p), sink)
+  if (eng->beam.use_raycast_using_dda)
+    DQ_LAUNCH(false);
+  else
+    DQ_LAUNCH(true);
+#undef DQ_LAUNCH
+  CK(cudaGetLastError());
+  eng->launches++;
+  return MCL3DL_OK;
+}
+
 int launch_lik(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size_t P, const mcl3dl_point* scan, size_t N,
                mcl3dl_result* out, int beam_defaults, cudaStream_t st, const RecordSink& sink)
 {
@@ -805,6 +856,8 @@ int launch_beam(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size
                 const float* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st,
                 const RecordSink& sink)
 {
+  if (eng->mapping != 0 && (eng->beam_dq == 1 || (eng->beam_dq == 2 && P * N >= 16384)))
+    return launch_beam_dq(eng, c, poses, P, scan, N, origins, out, status, lik_defaults, st, sink);
   if (eng->mapping != 0 || !eng->beam.use_raycast_using_dda)  // the KD-tree caster exists in the pl kernel only
     return launch_beam_pl(eng, c, poses, P, scan, N, origins, n_origins, out, status, lik_defaults, st, sink);
   const float4* s4 = reinterpret_cast<const float4*>(scan);
@@ -1369,6 +1422,10 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     eng->update_one_sync = std::atoi(v) != 0;
   if (const char* v = std::getenv("MCL3DL_NNF"))
     eng->nnf = std::atoi(v) != 0;
+  if (const char* v = std::getenv("MCL3DL_BEAM"))
+    eng->beam_dq = std::strcmp(v, "dq") == 0 ? 1 : (std::strcmp(v, "pl") == 0 ? 0 : 2);
+  if (const char* v = std::getenv("MCL3DL_BEAM_DQ_PPL"))
+    eng->beam_dq_ppl = std::min(std::max(std::atoi(v), 0), 64);
   if (const char* v = std::getenv("MCL3DL_LIK_SHARE"))
     eng->lik_share = std::min(std::max(std::atoi(v), 1), 8);
   if (const char* v = std::getenv("MCL3DL_NNF_KD_R2"))
@@ -1444,7 +1501,7 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
                       &c.s_clip[0], &c.s_clip[1], &c.s_out[0], &c.s_out[1], &c.s_tmp, &c.s_counts})
       free_buf(*b);
     for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.nnf_dir, &c.nnf_cand, &c.fld_cells, &c.d_poses,
-                      &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_w, &c.d_post, &c.d_wpart, &c.d_wticket})
+                      &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_tally, &c.d_queue, &c.d_w, &c.d_post, &c.d_wpart, &c.d_wticket})
       free_buf(*b);
     if (c.fld_nodes.ptr)
       cudaFree(c.fld_nodes.ptr);

@@ -1096,6 +1096,132 @@ __global__ void __launch_bounds__(kBlockThreads, 4)
 
 
 // ============================================================================================
+// Dynamic-queue variant of the lane-per-particle beam kernel (MCL3DL_BEAM=dq; A/B in profiles/).
+//
+// beam_kernel_pl gives every CTA a fixed set of (particle group, ray chunk) pairs and folds the tallies at a CTA barrier:
+// ncu shows 15.6 % of the samples of c3 waiting there (rays differ in length, the CTA waits for its slowest warp), and
+// whole-wave grids leave nothing to fill the tail with.  Here the grid is the resident warps; every warp pulls
+// (group, chunk) items from one global counter until the queue is empty, adds its integer tallies to the particles'
+// global counters (integers: the order of the additions cannot change a bit) and the warp that completes a group's
+// last chunk (per-group ticket) computes the score and stores the record.  No CTA barrier, no shared-memory tile (a
+// chunk's scan points are read by one warp: L1/L2 serve them).  Queue, tickets and tallies are left at zero.
+template <bool KD>
+__global__ void __launch_bounds__(kBlockThreads, 4)
+    beam_kernel_dq(const mcl3dl_pose* __restrict__ poses, int P, const float4* __restrict__ scan, int N,
+                   const float* __restrict__ origins, DdaGridDev g, KdRayDev kd, NnGridDev nn, mcl3dl_result* __restrict__ out,
+                   uint8_t* __restrict__ status, int write_lik_defaults, unsigned long long* __restrict__ stats, int ppl,
+                   int n_chunks, uint32_t* __restrict__ tally /* [P][3] */, unsigned int* __restrict__ tickets /* [groups] */,
+                   unsigned int* __restrict__ queue /* [0] next item, [1] warps finished */, RecordSink sink)
+{
+  const int lane = threadIdx.x & 31;
+  const int n_groups = (P + 31) / 32;
+  const unsigned int total = static_cast<unsigned int>(n_groups) * static_cast<unsigned int>(n_chunks);
+  uint32_t st_steps = 0, st_occ = 0, st_tested = 0;
+  for (;;)
+  {
+    unsigned int item = 0;
+    if (lane == 0)
+      item = atomicAdd(queue, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total)
+      break;
+    // consecutive items = consecutive groups of the same chunk: neighbouring warps read the same scan points
+    const int group = static_cast<int>(item % static_cast<unsigned int>(n_groups));
+    const int chunk = static_cast<int>(item / static_cast<unsigned int>(n_groups));
+    const int p = group * 32 + lane;
+    const bool live = p < P;
+    uint32_t n_short = 0, n_hit = 0, n_long = 0;
+    if (live)
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(poses + p));
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(poses + p) + 1);
+      F3 pos;
+      pos.x = a.x;
+      pos.y = a.y;
+      pos.z = a.z;
+      Q4 q;
+      q.x = bq.x;
+      q.y = bq.y;
+      q.z = bq.z;
+      q.w = bq.w;
+      const Q4 rn = qnormalized(q);
+      const int j0 = chunk * ppl, j1 = min(N, j0 + ppl);
+      for (int j = j0; j < j1; ++j)
+      {
+        const float4 sp = __ldg(scan + j);
+        F3 v;
+        v.x = sp.x;
+        v.y = sp.y;
+        v.z = sp.z;
+        const F3 end = transform_point(rn, pos, v);  // beam.cpp:138-139
+        const F3 begin = ray_origin(pos, q, origins, __float_as_uint(sp.w));
+        const int st = KD ? cast_ray_kd(kd, nn, g, begin, end, st_steps, st_occ, st_tested) :
+                            cast_ray(g, begin, end, st_steps, st_occ, st_tested);
+        n_short += (st == ST_SHORT);
+        n_hit += (st == ST_HIT);
+        n_long += (st == ST_LONG);
+        if (status)
+          status[static_cast<size_t>(p) * N + j] = static_cast<uint8_t>(st);
+      }
+      uint32_t* t = tally + static_cast<size_t>(p) * 3;
+      if (n_short) atomicAdd(t, n_short);
+      if (n_hit) atomicAdd(t + 1, n_hit);
+      if (n_long) atomicAdd(t + 2, n_long);
+    }
+    __threadfence();
+    __syncwarp();
+    unsigned int ticket = 0;
+    if (lane == 0)
+      ticket = atomicAdd(tickets + group, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket == static_cast<unsigned int>(n_chunks - 1))
+    {
+      __threadfence();
+      if (live)
+      {
+        uint32_t* t = tally + static_cast<size_t>(p) * 3;
+        const uint32_t a = __ldcg(t), b = __ldcg(t + 1), c = __ldcg(t + 2);
+        t[0] = 0;
+        t[1] = 0;
+        t[2] = 0;
+        // beam.cpp:146-152: the same factor multiplied in sequentially, then the floor
+        float score = 1.0f;
+        if (N > 0)
+        {
+          const uint32_t k = a + (g.short_only ? 0u : c);
+          for (uint32_t i = 0; i < k; ++i) score = fmul(score, g.beam_likelihood);
+          if (score < g.beam_likelihood_min)
+            score = g.beam_likelihood_min;
+        }
+        sink_store_beam(sink, out, p, score, a, b, c, write_lik_defaults);
+      }
+      if (lane == 0)
+        tickets[group] = 0;
+    }
+  }
+  // the last warp of the grid to leave resets the queue for the next launch
+  if (lane == 0)
+  {
+    const unsigned int warps = gridDim.x * (kBlockThreads / 32);
+    if (atomicAdd(queue + 1, 1u) == warps - 1)
+    {
+      queue[0] = 0;
+      queue[1] = 0;
+    }
+  }
+  if (stats)
+  {
+    const uint32_t x = warp_sum_u32(st_steps), y = warp_sum_u32(st_occ), z = warp_sum_u32(st_tested);
+    if (lane == 0)
+    {
+      atomicAdd(stats + 2, static_cast<unsigned long long>(x));
+      atomicAdd(stats + 3, static_cast<unsigned long long>(y));
+      atomicAdd(stats + 4, static_cast<unsigned long long>(z));
+    }
+  }
+}
+
+// ============================================================================================
 // Fused weight update (scope row f2): pf::ParticleFilter::measure's arithmetic on the records that
 // the two kernels above left on the device.  Deterministic: every reduction has a fixed tree
 // (warp shuffles -> per-CTA slot -> one finishing CTA walks the slots in order).

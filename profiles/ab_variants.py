@@ -35,8 +35,10 @@ VARIANT_BUILDS = {}
 # name -> (library, environment).  "base" (the CSR-window kernels of round 1, MCL3DL_NNF=0) must come first: everything
 # is compared with its records byte for byte.
 VARIANTS = [
-    ("base", LIB, dict(HOST, MCL3DL_NNF="0")),                      # the CSR-window searches of round 1
+    ("base", LIB, dict(HOST, MCL3DL_NNF="0", MCL3DL_BEAM="pl")),   # round-1 search structures, static beam kernel
     ("dflt", LIB, dict(HOST)),                                      # today's defaults
+    ("beam_pl", LIB, dict(HOST, MCL3DL_BEAM="pl")),
+    ("beam_dq", LIB, dict(HOST, MCL3DL_BEAM="dq")),
     ("kd_nor2", LIB, dict(HOST, MCL3DL_NNF_KD_R2="0")),
     ("fast_host", LIB, {"MCL3DL_TIMING": "0", "MCL3DL_ZEROCOPY_OUT": "8192"}),
     ("group", LIB, dict(HOST, MCL3DL_MAPPING="group")),
@@ -46,7 +48,7 @@ WORKLOADS = [("c2", "c2", "dda", False), ("c3kd", "c3", "kd", False), ("c5", "c5
              ("c1kd", "c1", "kd", False), ("c2s", "c2", "dda", True), ("c3", "c3", "dda", False), ("c2iso", "c2", "dda", False)]
 ISO_WORKLOADS = {"c2iso"}  # dist_weight (1,1,1) instead of the node's (1,1,5): ~3x more map points per eval
 ENV_KEYS = ["MCL3DL_TIMING", "MCL3DL_ZEROCOPY_OUT", "MCL3DL_NEAR_K", "MCL3DL_NEAR_KD_K", "MCL3DL_NEAR_MAX_MB",
-            "MCL3DL_MAPPING", "MCL3DL_UPDATE_ONE_SYNC", "MCL3DL_NNF", "MCL3DL_NF_STAGE", "MCL3DL_NF_TPP", "MCL3DL_NNF_KD_R2"]
+            "MCL3DL_MAPPING", "MCL3DL_UPDATE_ONE_SYNC", "MCL3DL_NNF", "MCL3DL_NF_STAGE", "MCL3DL_NF_TPP", "MCL3DL_NNF_KD_R2", "MCL3DL_BEAM", "MCL3DL_BEAM_DQ_PPL"]
 
 
 def jobs_all():

@@ -440,7 +440,8 @@ def test_options_change_no_record(eng_mod, monkeypatch, use_dda):
     beam = eng_mod.beam_params_from_reference(num_points_default=24, dda_grid_size=0.2, use_raycast_using_dda=use_dda)
 
     def run(env, timing=False):
-        for k in ("MCL3DL_NEAR_K", "MCL3DL_NEAR_KD_K", "MCL3DL_ZEROCOPY_OUT", "MCL3DL_TIMING", "MCL3DL_MAPPING", "MCL3DL_NNF"):
+        for k in ("MCL3DL_NEAR_K", "MCL3DL_NEAR_KD_K", "MCL3DL_ZEROCOPY_OUT", "MCL3DL_TIMING", "MCL3DL_MAPPING", "MCL3DL_NNF",
+                  "MCL3DL_BEAM", "MCL3DL_BEAM_DQ_PPL"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -470,3 +471,8 @@ def test_options_change_no_record(eng_mod, monkeypatch, use_dda):
     same(group, plain)
     csr, _, _ = run({"MCL3DL_NNF": "0"})                      # the CSR-window kernels of round 1 (no NN field)
     same(csr, plain)
+    # both beam kernels (static CTA mapping / dynamic queue with several item sizes): integer tallies, so byte-identical
+    for env in ({"MCL3DL_BEAM": "pl"}, {"MCL3DL_BEAM": "dq"}, {"MCL3DL_BEAM": "dq", "MCL3DL_BEAM_DQ_PPL": "1"},
+                {"MCL3DL_BEAM": "dq", "MCL3DL_BEAM_DQ_PPL": "7"}):
+        got, _, _ = run(env)
+        assert got.tobytes() == dflt.tobytes(), env
