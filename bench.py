@@ -47,6 +47,7 @@ WORKLOADS = {
     "c3": (1_000_000, 4096, 0, 256, False, 0.2, "weak"),
     "c4": (10_000_000, 16384, 1024, 1024, False, 0.1, "strong"),
     "c5": (1_000_000, 65536, 64, 8, True, 0.2, "strong"),
+    "c5e": (1_000_000, 8192, 64, 8, True, 0.2, "weak"),   # one GPU's share of c5 at 8 GPUs (kernel experiments)
 }
 FORCE_SPREAD = False
 DIST_WEIGHT = (1.0, 1.0, 5.0)  # the node's default metric (src/parameters.cpp:108-111)

@@ -393,8 +393,8 @@ struct mcl3dl_engine
                             // round 1: off until the f2 parity tests have run with it)
   int field_mode = 0;  // 1: the likelihood model reads the trilinear distance volume (opt-in, inexact; MCL3DL_LIK_MODE=field)
   size_t field_max_bytes = size_t(24) << 30;  // MCL3DL_FIELD_MAX_MB
-  int beam_dq = 2;  // beam kernel: 2 = by job size (dynamic queue from 16 384 rays up: c3 118 -> 107 us, c3_kd 266 -> 232 us,
-                    // profiles/r02r_ab.jsonl; the static kernel is a little faster on tiny jobs), 1 = MCL3DL_BEAM=dq, 0 = MCL3DL_BEAM=pl
+  int beam_dq = 2;  // beam kernel: 2 = by job size (dynamic queue from 262 144 rays up: c3 118 -> 107 us, c3_kd 266 -> 232 us,
+                    // profiles/r02r_ab.jsonl; the static kernel is faster on small jobs, profiles/r02s_c5e.txt), 1 = MCL3DL_BEAM=dq, 0 = MCL3DL_BEAM=pl
   int beam_dq_ppl = 0;  // MCL3DL_BEAM_DQ_PPL: rays per item (0 = chosen from the job size)
   int lik_share = 4;  // CTA slots per SM the likelihood kernel takes while the beam kernel runs next to it (MCL3DL_LIK_SHARE)
   int nnf_kd_r2 = 1;  // MCL3DL_NNF_KD_R2=0: the NN field also covers the KD-tree raycaster's second search radius
@@ -856,7 +856,7 @@ int launch_beam(mcl3dl_engine* eng, DeviceCtx& c, const mcl3dl_pose* poses, size
                 const float* origins, int n_origins, mcl3dl_result* out, uint8_t* status, int lik_defaults, cudaStream_t st,
                 const RecordSink& sink)
 {
-  if (eng->mapping != 0 && (eng->beam_dq == 1 || (eng->beam_dq == 2 && P * N >= 16384)))
+  if (eng->mapping != 0 && (eng->beam_dq == 1 || (eng->beam_dq == 2 && P * N >= 262144)))
     return launch_beam_dq(eng, c, poses, P, scan, N, origins, out, status, lik_defaults, st, sink);
   if (eng->mapping != 0 || !eng->beam.use_raycast_using_dda)  // the KD-tree caster exists in the pl kernel only
     return launch_beam_pl(eng, c, poses, P, scan, N, origins, n_origins, out, status, lik_defaults, st, sink);
