@@ -1431,7 +1431,8 @@ __global__ void __launch_bounds__(32)
   __syncwarp();
   if (threadIdx.x < static_cast<unsigned>(t.world))
   {
-    __threadfence_system();
+    // st.release.sys = fence.acq_rel.sys + store: the records of the model kernels (visible to this kernel through the
+    // kernel boundary) are ordered before the flag for the acquiring peer; no separate membar.sys in front of it
     st_release_sys(t.flags[threadIdx.x] + t.rank, step);
     const uint32_t* mine = t.flags[t.rank] + threadIdx.x;
     // steps increase monotonically; the difference is taken modulo 2^32.  Bounded: a peer that died must not hang
