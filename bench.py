@@ -445,8 +445,8 @@ def device_leg(cx, workload, raycaster, steps, warmup, exchange="peer", graph=Tr
                 % (ws["lik_index_rows"] / max(P_rank * n_lik, 1), ws["lik_points_scanned"] / max(P_rank * n_lik, 1)))
         nnf = eng.nn_field_info()
         if nnf["bytes"]:
-            note += "; NN field %.0f MB, %.1f M candidates, %d overflow cells" % (nnf["bytes"] / 1e6, nnf["candidates"] / 1e6,
-                                                                                 nnf["overflow_cells"])
+            note += "; NN field %.0f MB, %.1f M candidates, %d wide / %d overflow cells" % (
+                nnf["bytes"] / 1e6, nnf["candidates"] / 1e6, nnf["wide_cells"], nnf["overflow_cells"])
         elif near[0][0]:
             alg_bytes += P_rank * n_lik * 4
             note += " + one 4 B near-field word per eval (k=%d, %.0f MB)" % (near[0][0], near[0][1] / 1e6)

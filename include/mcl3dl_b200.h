@@ -343,9 +343,11 @@ int mcl3dl_near_field_info(const mcl3dl_engine*, int32_t k_out[2], uint64_t byte
 /* The NN field staged by the last set_map (exact per-voxel candidate lists, the default likelihood search structure;
  * no reference counterpart — ChunkedKdtree::radiusSearch, chunked_kdtree.h:218-251, descends a kd-tree per query):
  * out[0] = bytes per device (0: not staged, the CSR-window kernels serve the searches), out[1] = candidates stored,
- * out[2] = directory cells that overflowed (queries there fall back to the CSR window search), out[3] = fine voxel edge
- * in micrometres of the rescaled space.  Environment: MCL3DL_NNF=0 disables, MCL3DL_NNF_MAX_MB caps the size. */
-int mcl3dl_nn_field_info(const mcl3dl_engine*, uint64_t out[4]);
+ * out[2] = directory cells that overflowed (a voxel with more than 40 candidates: queries there fall back to the CSR
+ * window search), out[3] = fine voxel edge in micrometres of the rescaled space, out[4] = wide cells (a voxel with 15..40
+ * candidates: counts in a side table, one more dependent load).  A voxel-filtered map has neither kind.
+ * Environment: MCL3DL_NNF=0 disables, MCL3DL_NNF_MAX_MB caps the size. */
+int mcl3dl_nn_field_info(const mcl3dl_engine*, uint64_t out[5]);
 
 /* Field mode (BASELINE.json north_star's literal likelihood kernel; OPT-IN and INEXACT): a dense Euclidean-distance
  * volume over the NN field's lattice, read by trilinear interpolation, replaces the exact nearest-neighbour distance of

@@ -128,12 +128,16 @@ inline bool near_layout(NearBitsDev& f, float r, int k, const float sc_min[3], c
 // radius^2 (ties included: points that tie can not dominate each other).  Voxels with more than kNnfMaxCand survivors
 // (raw, unfiltered clouds) mark their directory cell and queries there fall back to the CSR window search.
 // No reference counterpart: ChunkedKdtree::radiusSearch (chunked_kdtree.h:218-251) descends a kd-tree per query.
-constexpr int kNnfMaxCand = 14;
-constexpr int kNnfMaxSurv = 40;
+constexpr int kNnfMaxCand = 14;  // per voxel in a regular directory cell (4-bit counts)
+constexpr int kNnfMaxSurv = 40;  // per voxel in a wide cell (8-bit counts, side table); more: overflow cell
 struct NnFieldDev
 {
-  const uint2* dir;    // nullptr = no field.  Per coarse cell: x = index of its first candidate (0xffffffff: overflow
-                       // cell -> generic search), y = 8 nibbles = candidates per fine voxel, sub-index x | y<<1 | z<<2
+  const uint2* dir;    // nullptr = no field.  Per coarse cell: x = index of its first candidate, y = 8 nibbles = candidates
+                       // per fine voxel (sub-index x | y<<1 | z<<2).  x with bit 31 set: 0xffffffff = overflow cell
+                       // (generic search), else a WIDE cell = index into `wide` (some voxel has 15..40 candidates: three
+                       // surfaces meeting; 41 of 22 M cells on the synthetic map — keeping them out of the overflow class
+                       // lets regular maps run the kernel variant without any fallback code, 22 % faster on c2)
+  const uint4* wide;   // wide cells: x = first candidate, y / z = byte counts of voxels 0..3 / 4..7
   const float4* cand;  // rescaled xyz, w = original map index (bits)
   int nx, ny, nz;      // FINE voxels per axis
   int cnx, cny, cnz;   // coarse cells per axis = (n + 1) / 2
@@ -536,6 +540,31 @@ __device__ __forceinline__ bool nn_search_arg(const NnGridDev& g, float qx, floa
 }
 
 // --------------------------------------------------------------------------------------------
+// NN field: candidate count and first index of voxel `sub` of a directory entry; -1 in an overflow cell.
+__device__ __forceinline__ int nnf_slot(const NnFieldDev& f, uint2 d, int sub, uint32_t& start)
+{
+  if (d.x & 0x80000000u)
+  {
+    if (d.x == 0xffffffffu)
+      return -1;
+    // wide cell (rare): byte counts from the side table
+    const uint4 w = __ldg(f.wide + (d.x & 0x7fffffffu));
+    const uint32_t word = sub < 4 ? w.y : w.z;
+    const int sh8 = 8 * (sub & 3);
+    const uint32_t part = word & ((1u << sh8) - 1u);  // bytes of this word before the voxel's
+    const uint32_t full = sub < 4 ? 0u : w.y;        // the whole first word when the voxel sits in the second
+    const uint32_t s0 = ((part & 0x00ff00ffu) + ((part >> 8) & 0x00ff00ffu)) * 0x00010001u >> 16;
+    const uint32_t s1 = ((full & 0x00ff00ffu) + ((full >> 8) & 0x00ff00ffu)) * 0x00010001u >> 16;
+    start = w.x + s0 + s1;
+    return static_cast<int>((word >> sh8) & 255u);
+  }
+  const int sh = 4 * sub;
+  const uint32_t below = d.y & ((1u << sh) - 1u);  // nibbles of the voxels stored before this one
+  const uint32_t m = (below & 0x0f0f0f0fu) + ((below >> 4) & 0x0f0f0f0fu);
+  start = d.x + ((m * 0x01010101u) >> 24);
+  return static_cast<int>((d.y >> sh) & 15u);
+}
+
 // NN field, query side.  Returns the number of candidates of q's voxel and their first index, 0 when q lies outside the
 // lattice (then no map point is within `radius`: the lattice extends 2.5 voxels > radius beyond the map's box) or -1 in
 // an overflow cell.
@@ -546,13 +575,7 @@ __device__ __forceinline__ int nnf_lookup(const NnFieldDev& f, float qx, float q
       static_cast<unsigned>(vz) >= static_cast<unsigned>(f.nz))
     return 0;
   const uint2 d = __ldg(f.dir + (static_cast<size_t>(vz >> 1) * f.cny + (vy >> 1)) * f.cnx + (vx >> 1));
-  if (d.x == 0xffffffffu)
-    return -1;
-  const int sh = 4 * ((vx & 1) | ((vy & 1) << 1) | ((vz & 1) << 2));
-  const uint32_t below = d.y & ((1u << sh) - 1u);  // nibbles of the voxels stored before this one
-  const uint32_t m = (below & 0x0f0f0f0fu) + ((below >> 4) & 0x0f0f0f0fu);
-  start = d.x + ((m * 0x01010101u) >> 24);
-  return static_cast<int>((d.y >> sh) & 15u);
+  return nnf_slot(f, d, (vx & 1) | ((vy & 1) << 1) | ((vz & 1) << 2), start);
 }
 
 // nn_dist2 through the field (likelihood model): min over the voxel's candidates, r2 if none is closer.
@@ -629,7 +652,7 @@ __device__ __forceinline__ float field_dist(const FieldDev& f, float qx, float q
 
 // --------------------------------------------------------------------------------------------
 // NN field, build side: the candidates of fine voxel (vx, vy, vz), as positions into the CSR point array g.pts, in CSR
-// order.  Returns their number, or kNnfMaxCand + 1 when more survive (overflow).  All geometry in double, relative to
+// order (out holds kNnfMaxSurv entries).  Returns their number, or kNnfMaxSurv + 1 when more survive (overflow).  All geometry in double, relative to
 // the voxel centre (magnitudes <= ~1, so double rounding is ~1e-16 against margins of >= 1e-8).
 struct NnfPt
 {
@@ -743,7 +766,7 @@ __device__ __forceinline__ int nnf_select(const NnGridDev& g, const NnFieldDev& 
       }
     }
   if (too_many)
-    return kNnfMaxCand + 1;
+    return kNnfMaxSurv + 1;
   // pass 3: pairwise — drop what any other survivor dominates (dominance is transitive over the box, so testing
   // against survivors that are themselves dropped later is still sound)
   int n_out = 0;
@@ -754,8 +777,6 @@ __device__ __forceinline__ int nnf_select(const NnGridDev& g, const NnFieldDev& 
       dead = (j != i) && nnf_dominates(surv[j], surv[i], h);
     if (dead)
       continue;
-    if (n_out == kNnfMaxCand)
-      return kNnfMaxCand + 1;
     out[n_out++] = surv_s[i];
   }
   return n_out;

@@ -13,7 +13,9 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_reduce.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include "kernels.cuh"
 #include "pf_kernels.cuh"
@@ -174,7 +176,8 @@ __device__ __forceinline__ bool nnf_voxel_of_thread(const NnFieldDev& f, size_t 
 
 __global__ void __launch_bounds__(256)
     nnf_count_kernel(NnGridDev g, NnFieldDev f, const uint32_t* __restrict__ bits, int pitch, uint2* __restrict__ dir,
-                     uint32_t* __restrict__ totals, size_t n_cells, uint32_t* __restrict__ n_overflow)
+                     uint32_t* __restrict__ totals, size_t n_cells, uint4* __restrict__ wide, uint32_t wide_cap,
+                     uint32_t* __restrict__ counters /* [0] wide cells used, [1] overflow cells */)
 {
   const size_t t = blockIdx.x * static_cast<size_t>(256) + threadIdx.x;
   size_t cell;
@@ -182,33 +185,69 @@ __global__ void __launch_bounds__(256)
   if (nnf_voxel_of_thread(f, n_cells, t, cell, sub, vx, vy, vz) &&
       ((__ldg(bits + (static_cast<size_t>(vz) * f.ny + vy) * pitch + (vx >> 5)) >> (vx & 31)) & 1u))
   {
-    uint32_t tmp[kNnfMaxCand];
+    uint32_t tmp[kNnfMaxSurv];
     cnt = nnf_select(g, f, vx, vy, vz, tmp);
   }
-  uint32_t ovf = cnt > kNnfMaxCand ? 1u : 0u;
-  uint32_t nib = ovf ? 0u : (static_cast<uint32_t>(cnt) << (4 * sub));
-  uint32_t tot = ovf ? 0u : static_cast<uint32_t>(cnt);
+  uint32_t ovf = cnt > kNnfMaxSurv ? 1u : 0u;
+  uint32_t big = cnt > kNnfMaxCand ? 1u : 0u;
+  const uint32_t c8 = static_cast<uint32_t>(min(cnt, 255));
+  uint32_t lo = sub < 4 ? c8 << (8 * sub) : 0u, hi = sub >= 4 ? c8 << (8 * (sub - 4)) : 0u;
+  uint32_t tot = static_cast<uint32_t>(cnt);
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1)
   {
-    nib |= __shfl_xor_sync(0xffffffffu, nib, o);
+    lo |= __shfl_xor_sync(0xffffffffu, lo, o);
+    hi |= __shfl_xor_sync(0xffffffffu, hi, o);
     tot += __shfl_xor_sync(0xffffffffu, tot, o);
     ovf |= __shfl_xor_sync(0xffffffffu, ovf, o);
+    big |= __shfl_xor_sync(0xffffffffu, big, o);
   }
-  if (sub == 0 && cell < n_cells)
+  if (sub != 0 || cell >= n_cells)
+    return;
+  // dir[cell].y: nibbles | 0xfffffffe = wide cell (dir[cell].x already holds 0x80000000 | index) | 0xffffffff = overflow
+  if (!ovf && big)
   {
-    dir[cell].y = ovf ? 0xffffffffu : nib;  // all-ones (a count of 15 never occurs): overflow cell
-    totals[cell] = ovf ? 0u : tot;
-    if (ovf)
-      atomicAdd(n_overflow, 1u);
+    const uint32_t idx = atomicAdd(counters, 1u);
+    if (idx < wide_cap)
+    {
+      wide[idx] = make_uint4(0u, lo, hi, 0u);  // x = first candidate, filled in by nnf_base_kernel
+      dir[cell] = make_uint2(0x80000000u | idx, 0xfffffffeu);
+      totals[cell] = tot;
+      return;
+    }
+    ovf = 1u;  // side table full: treat as an overflow cell
   }
+  if (ovf)
+  {
+    dir[cell].y = 0xffffffffu;
+    totals[cell] = 0u;
+    atomicAdd(counters + 1, 1u);
+    return;
+  }
+  uint32_t nib = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) nib |= (((lo >> (8 * k)) & 15u) << (4 * k)) | (((hi >> (8 * k)) & 15u) << (4 * (k + 4)));
+  dir[cell].y = nib;
+  totals[cell] = tot;
 }
 
-__global__ void nnf_base_kernel(uint2* __restrict__ dir, const uint32_t* __restrict__ base, size_t n_cells)
+struct WidenU32
+{
+  __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; }
+};
+
+__global__ void nnf_base_kernel(uint2* __restrict__ dir, const uint32_t* __restrict__ base, size_t n_cells, uint4* __restrict__ wide)
 {
   const size_t c = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (c < n_cells)
-    dir[c].x = dir[c].y == 0xffffffffu ? 0xffffffffu : base[c];
+  if (c >= n_cells)
+    return;
+  const uint32_t y = dir[c].y;
+  if (y == 0xffffffffu)
+    dir[c].x = 0xffffffffu;
+  else if (y == 0xfffffffeu)
+    wide[dir[c].x & 0x7fffffffu].x = base[c];
+  else
+    dir[c].x = base[c];
 }
 
 __global__ void __launch_bounds__(256)
@@ -220,16 +259,13 @@ __global__ void __launch_bounds__(256)
   int sub, vx, vy, vz;
   if (!nnf_voxel_of_thread(f, n_cells, t, cell, sub, vx, vy, vz))
     return;
-  const uint2 d = dir[cell];
-  const uint32_t want = (d.y >> (4 * sub)) & 15u;
-  if (d.x == 0xffffffffu || want == 0)
+  uint32_t start = 0;
+  const int want = nnf_slot(f, dir[cell], sub, start);
+  if (want <= 0)
     return;
-  uint32_t pos[kNnfMaxCand];
+  uint32_t pos[kNnfMaxSurv];
   const int cnt = nnf_select(g, f, vx, vy, vz, pos);
-  const uint32_t below = d.y & ((1u << (4 * sub)) - 1u);
-  const uint32_t m = (below & 0x0f0f0f0fu) + ((below >> 4) & 0x0f0f0f0fu);
-  const uint32_t start = d.x + ((m * 0x01010101u) >> 24);
-  for (int i = 0; i < cnt && i < static_cast<int>(want); ++i) cand[start + i] = g.pts[pos[i]];
+  for (int i = 0; i < cnt && i < want; ++i) cand[start + i] = g.pts[pos[i]];
 }
 
 // Field mode (device_funcs.cuh: FieldDev).  Node volume: exact distance (clamped) from every lattice node to the
@@ -316,7 +352,7 @@ struct DeviceCtx
   KdRayDev kd{};
   DevBuf raw_pts;  // map points in original order (KD-tree raycaster only)
   DevBuf near_lik, near_kd;  // near-field bits (MCL3DL_NEAR_BITS builds)
-  DevBuf nnf_dir, nnf_cand;  // NN field: directory + candidate lists
+  DevBuf nnf_dir, nnf_cand, nnf_wide;  // NN field: directory, candidate lists, side table of the wide cells
   DevBuf fld_cells;          // field mode: 8 corner distances per lattice cell
   cudaPitchedPtr fld_nodes{};  // field mode: node volume (cudaMalloc3D)
   bool fld_nodes_valid = false;
@@ -400,7 +436,7 @@ struct mcl3dl_engine
   int nnf_kd_r2 = 1;  // MCL3DL_NNF_KD_R2=0: the NN field also covers the KD-tree raycaster's second search radius
   int nnf = 1;  // stage the NN field (exact per-voxel candidate lists) and use lik_kernel_nf; MCL3DL_NNF=0: the CSR window kernels
   size_t nnf_max_bytes = size_t(32) << 30;  // MCL3DL_NNF_MAX_MB: directory + candidates above this -> no field
-  uint64_t nnf_bytes = 0, nnf_cands = 0, nnf_overflow_cells = 0;
+  uint64_t nnf_bytes = 0, nnf_cands = 0, nnf_overflow_cells = 0, nnf_wide_cells = 0;
   int mapping = 1;  // 1 = tuned kernels (lik_kernel_wi + beam_kernel_pl); 0 = the plain group kernels (MCL3DL_MAPPING=group)
 };
 
@@ -948,7 +984,7 @@ int build_near_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mc
 int build_nn_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mcl3dl_point* pts, uint32_t n, NnGridDev& g,
                    float radius, const float sc_min[3], const float sc_max[3])
 {
-  eng->nnf_bytes = eng->nnf_cands = eng->nnf_overflow_cells = 0;
+  eng->nnf_bytes = eng->nnf_cands = eng->nnf_overflow_cells = eng->nnf_wide_cells = 0;
   NearBitsDev lay{};
   // the lattice of a k = 2 near field for this radius: fine edge 1.01 * radius / 2, origin 2.5 voxels below the box
   if (!near_layout(lay, radius, 2, sc_min, sc_max, size_t(1) << 40))
@@ -991,8 +1027,10 @@ int build_nn_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mcl3
       return MCL3DL_ERR_CUDA;                                                      \
     }                                                                              \
   } while (0)
-  if ((rc = reserve(eng, d_bits, bits_bytes)) || (rc = reserve(eng, d_tot, (n_cells + 4) * 4)) ||
-      (rc = reserve(eng, c.nnf_dir, n_cells * sizeof(uint2))))
+  const uint32_t wide_cap = static_cast<uint32_t>(std::min<size_t>(n_cells, size_t(1) << 18));
+  const size_t sum_at = (n_cells + 5) & ~size_t(1);  // 64-bit grand total, 8-byte aligned behind the tail words
+  if ((rc = reserve(eng, d_bits, bits_bytes)) || (rc = reserve(eng, d_tot, (sum_at + 2) * 4)) ||
+      (rc = reserve(eng, c.nnf_dir, n_cells * sizeof(uint2))) || (rc = reserve(eng, c.nnf_wide, static_cast<size_t>(wide_cap) * sizeof(uint4))))
   {
     cleanup();
     return rc;
@@ -1002,38 +1040,49 @@ int build_nn_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mcl3
   const unsigned blocks = static_cast<unsigned>((n_cells * 8 + 255) / 256);
   uint2* dir = static_cast<uint2*>(c.nnf_dir.p);
   uint32_t* tot = static_cast<uint32_t*>(d_tot.p);
-  CKF(cudaMemsetAsync(tot + n_cells, 0, 16, st));  // [n_cells]: scan tail, [n_cells + 2]: overflow-cell counter
+  CKF(cudaMemsetAsync(tot + n_cells, 0, 16, st));  // [n_cells]: scan tail, [n_cells + 2] wide cells, [n_cells + 3] overflow cells
+  f.wide = static_cast<const uint4*>(c.nnf_wide.p);
   nnf_count_kernel<<<blocks, 256, 0, st>>>(g, f, static_cast<const uint32_t*>(d_bits.p), lay.pitch, dir, tot, n_cells,
-                                           tot + n_cells + 2);
+                                           static_cast<uint4*>(c.nnf_wide.p), wide_cap, tot + n_cells + 2);
   CKF(cudaGetLastError());
-  // exclusive scan of the per-cell totals (in place); the grand total and the last cell's count size the candidates
-  size_t tmp_bytes = 0;
+  // exclusive scan of the per-cell totals (in place); the grand total sizes the candidate array.  A candidate index
+  // must stay below 2^31 (bit 31 of a directory entry marks wide / overflow cells): the total is first summed in 64 bits.
+  cub::TransformInputIterator<unsigned long long, WidenU32, const uint32_t*> wide_in(tot, WidenU32());
+  unsigned long long* d_sum = reinterpret_cast<unsigned long long*>(tot + sum_at);
+  size_t tmp_bytes = 0, tmp_sum = 0;
   CKF(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tot, tot, static_cast<int>(n_cells + 1), st));
-  if ((rc = reserve(eng, d_tmp, tmp_bytes)))
+  CKF(cub::DeviceReduce::Sum(nullptr, tmp_sum, wide_in, d_sum, static_cast<int>(n_cells), st));
+  if ((rc = reserve(eng, d_tmp, std::max(tmp_bytes, tmp_sum))))
   {
     cleanup();
     return rc;
   }
-  // 64-bit guard: sum the totals' upper bound on the host side via a second, 64-bit scan would cost more than it is
-  // worth; the counts are <= 8 * 14 per cell, so the total fits 32 bits when n_cells < 2^32 / 112
-  if (n_cells >= (size_t(0xfffffff0u) / (8 * kNnfMaxCand)))
+  tmp_sum = d_tmp.cap;
+  CKF(cub::DeviceReduce::Sum(d_tmp.p, tmp_sum, wide_in, d_sum, static_cast<int>(n_cells), st));
+  unsigned long long sum64 = 0;
+  CKF(cudaMemcpyAsync(&sum64, d_sum, 8, cudaMemcpyDeviceToHost, st));
+  CKF(cudaStreamSynchronize(st));
+  if (sum64 >= (1ull << 31))
   {
     cleanup();
     free_buf(c.nnf_dir);
+    free_buf(c.nnf_wide);
     return MCL3DL_OK;
   }
   tmp_bytes = d_tmp.cap;
   CKF(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, tot, tot, static_cast<int>(n_cells + 1), st));
-  uint32_t tail[3] = {0, 0, 0};
+  uint32_t tail[4] = {0, 0, 0, 0};
   CKF(cudaMemcpyAsync(tail, tot + n_cells, sizeof(tail), cudaMemcpyDeviceToHost, st));
   CKF(cudaStreamSynchronize(st));
   const uint32_t total = tail[0];
-  eng->nnf_overflow_cells = tail[2];
+  eng->nnf_wide_cells = std::min<uint32_t>(tail[2], wide_cap);
+  eng->nnf_overflow_cells = tail[3];
   const size_t cand_bytes = static_cast<size_t>(total) * sizeof(float4);
   if (n_cells * 8 + cand_bytes > eng->nnf_max_bytes)
   {
     cleanup();
     free_buf(c.nnf_dir);
+    free_buf(c.nnf_wide);
     return MCL3DL_OK;
   }
   if ((rc = reserve(eng, c.nnf_cand, std::max<size_t>(cand_bytes, 16))))
@@ -1041,7 +1090,7 @@ int build_nn_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mcl3
     cleanup();
     return rc;
   }
-  nnf_base_kernel<<<static_cast<unsigned>((n_cells + 255) / 256), 256, 0, st>>>(dir, tot, n_cells);
+  nnf_base_kernel<<<static_cast<unsigned>((n_cells + 255) / 256), 256, 0, st>>>(dir, tot, n_cells, static_cast<uint4*>(c.nnf_wide.p));
   nnf_fill_kernel<<<blocks, 256, 0, st>>>(g, f, static_cast<const uint32_t*>(d_bits.p), lay.pitch, dir,
                                           static_cast<float4*>(c.nnf_cand.p), n_cells);
   CKF(cudaGetLastError());
@@ -1050,7 +1099,7 @@ int build_nn_field(mcl3dl_engine* eng, DeviceCtx& c, cudaStream_t st, const mcl3
   f.dir = dir;
   f.cand = static_cast<const float4*>(c.nnf_cand.p);
   g.field = f;
-  eng->nnf_bytes = n_cells * 8 + cand_bytes;
+  eng->nnf_bytes = n_cells * 8 + cand_bytes + static_cast<size_t>(wide_cap) * sizeof(uint4);
   eng->nnf_cands = total;
   c.map_bytes += eng->nnf_bytes;
   cleanup();
@@ -1500,7 +1549,7 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
                       &c.s_keys[1], &c.s_vals[0], &c.s_vals[1], &c.s_flags[0], &c.s_flags[1], &c.s_pos[0], &c.s_pos[1], &c.s_ds,
                       &c.s_clip[0], &c.s_clip[1], &c.s_out[0], &c.s_out[1], &c.s_tmp, &c.s_counts})
       free_buf(*b);
-    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.nnf_dir, &c.nnf_cand, &c.fld_cells, &c.d_poses,
+    for (DevBuf* b : {&c.nn_cell_start, &c.nn_pts, &c.nn_row3, &c.dda_occ, &c.dda_cell_start, &c.dda_pts, &c.raw_pts, &c.near_lik, &c.near_kd, &c.nnf_dir, &c.nnf_cand, &c.nnf_wide, &c.fld_cells, &c.d_poses,
                       &c.d_out, &c.d_status, &c.d_stats, &c.d_partial, &c.d_tickets, &c.d_tally, &c.d_queue, &c.d_w, &c.d_post, &c.d_wpart, &c.d_wticket})
       free_buf(*b);
     if (c.fld_nodes.ptr)
@@ -1698,7 +1747,7 @@ int mcl3dl_field_upload(mcl3dl_engine* eng, const float* nodes, const int32_t di
   return MCL3DL_OK;
 }
 
-int mcl3dl_nn_field_info(const mcl3dl_engine* eng, uint64_t out[4])
+int mcl3dl_nn_field_info(const mcl3dl_engine* eng, uint64_t out[5])
 {
   if (!eng || !out)
     return MCL3DL_ERR_INVALID_ARG;
@@ -1707,6 +1756,7 @@ int mcl3dl_nn_field_info(const mcl3dl_engine* eng, uint64_t out[4])
   out[1] = on ? eng->nnf_cands : 0;
   out[2] = on ? eng->nnf_overflow_cells : 0;
   out[3] = on ? static_cast<uint64_t>(eng->devs[0].nn.field.e * 1e6f) : 0;
+  out[4] = on ? eng->nnf_wide_cells : 0;
   return MCL3DL_OK;
 }
 

@@ -249,10 +249,12 @@ class Engine:
         return [(int(k[0]), int(b[0])), (int(k[1]), int(b[1]))]
 
     def nn_field_info(self):
-        """The NN field of the staged map: {"bytes", "candidates", "overflow_cells", "voxel_edge"} (bytes 0: not staged)."""
-        v = (C.c_uint64 * 4)()
+        """The NN field of the staged map: {"bytes", "candidates", "overflow_cells", "voxel_edge", "wide_cells"} (bytes 0:
+        not staged)."""
+        v = (C.c_uint64 * 5)()
         self._check(self.L.mcl3dl_nn_field_info(self.h, v))
-        return {"bytes": int(v[0]), "candidates": int(v[1]), "overflow_cells": int(v[2]), "voxel_edge": v[3] * 1e-6}
+        return {"bytes": int(v[0]), "candidates": int(v[1]), "overflow_cells": int(v[2]), "voxel_edge": v[3] * 1e-6,
+                "wide_cells": int(v[4])}
 
     def field_mode(self, enable=True):
         """Opt-in, inexact: route the likelihood model through the trilinear distance volume (include/mcl3dl_b200.h)."""

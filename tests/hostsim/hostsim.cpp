@@ -29,7 +29,8 @@ struct HostMap
   std::vector<uint32_t> near_lik, near_kd;
   std::vector<uint2> nnf_dir;
   std::vector<float4> nnf_cand;
-  uint64_t nnf_voxels = 0, nnf_overflow = 0;
+  std::vector<uint4> nnf_wide;
+  uint64_t nnf_voxels = 0, nnf_overflow = 0, nnf_wide_cells = 0;
   NnGridDev nn{};
   DdaGridDev dda{};
   KdRayDev kd{};
@@ -167,12 +168,13 @@ void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_param
         const size_t n_cells = static_cast<size_t>(f.cnx) * f.cny * f.cnz;
         m.nnf_dir.assign(n_cells, make_uint2(0u, 0u));
         m.nnf_cand.clear();
+        m.nnf_wide.clear();
         for (size_t cell = 0; cell < n_cells; ++cell)
         {
           const int cx = static_cast<int>(cell % f.cnx), cy = static_cast<int>((cell / f.cnx) % f.cny),
                     cz = static_cast<int>(cell / (static_cast<size_t>(f.cnx) * f.cny));
-          uint32_t nib = 0;
-          bool ovf = false;
+          uint32_t nib = 0, lo = 0, hi = 0;
+          bool ovf = false, big = false;
           std::vector<float4> mine;
           for (int sub = 0; sub < 8; ++sub)
           {
@@ -181,14 +183,16 @@ void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_param
               continue;
             if (!((bits[(static_cast<size_t>(vz) * f.ny + vy) * lay.pitch + (vx >> 5)] >> (vx & 31)) & 1u))
               continue;
-            uint32_t pos[kNnfMaxCand];
+            uint32_t pos[kNnfMaxSurv];
             const int cnt = nnf_select(g, f, vx, vy, vz, pos);
-            if (cnt > kNnfMaxCand)
+            if (cnt > kNnfMaxSurv)
             {
               ovf = true;
               continue;
             }
-            nib |= static_cast<uint32_t>(cnt) << (4 * sub);
+            big |= cnt > kNnfMaxCand;
+            nib |= (static_cast<uint32_t>(cnt) & 15u) << (4 * sub);
+            (sub < 4 ? lo : hi) |= static_cast<uint32_t>(cnt) << (8 * (sub & 3));
             for (int i = 0; i < cnt; ++i) mine.push_back(g.pts[pos[i]]);
             m.nnf_voxels += cnt > 0;
           }
@@ -196,6 +200,14 @@ void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_param
           {
             m.nnf_dir[cell] = make_uint2(0xffffffffu, 0xffffffffu);
             ++m.nnf_overflow;
+          }
+          else if (big)
+          {
+            // wide cell: byte counts in the side table (engine.cu: nnf_count_kernel / nnf_base_kernel)
+            m.nnf_dir[cell] = make_uint2(0x80000000u | static_cast<uint32_t>(m.nnf_wide.size()), 0xfffffffeu);
+            m.nnf_wide.push_back(make_uint4(static_cast<uint32_t>(m.nnf_cand.size()), lo, hi, 0u));
+            ++m.nnf_wide_cells;
+            m.nnf_cand.insert(m.nnf_cand.end(), mine.begin(), mine.end());
           }
           else
           {
@@ -205,7 +217,10 @@ void build(HostMap& m, const mcl3dl_point* pts, size_t n, const mcl3dl_lik_param
         }
         if (m.nnf_cand.empty())
           m.nnf_cand.push_back(make_float4(0, 0, 0, 0));
+        if (m.nnf_wide.empty())
+          m.nnf_wide.push_back(make_uint4(0, 0, 0, 0));
         f.dir = m.nnf_dir.data();
+        f.wide = m.nnf_wide.data();
         f.cand = m.nnf_cand.data();
         g.field = f;
       }
@@ -389,6 +404,7 @@ extern "C" int hostsim_measure_nf(const mcl3dl_point* map, size_t n, const mcl3d
     work[5] = m.nnf_cand.size();
     work[6] = m.nnf_voxels;
     work[7] = m.nnf_overflow;
+    work[8] = m.nnf_wide_cells;
   }
   return 0;
 }

@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star): beam HIT/SHORT/LONG tallies and per-ray BeamSta
 match counts bit-exact; likelihood scores within 1e-4 relative (the per-particle float sum is
 reduced in a different order than the reference's sequential loop).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -428,6 +430,28 @@ def test_dense_cloud_overflows_the_window_table(eng_mod, eng, cc):
     assert want["match_cnt"].sum() > 0
     assert np.array_equal(eng.beam_status(s["particles"], s["beam"], s["origins"]),
                           cpu.beam_status(s["particles"], s["beam"], s["origins"]))
+
+
+def test_wide_cells_of_the_nn_field(eng_mod, eng, cc):
+    """A sparse volume cloud: some voxels keep 15..40 nearest-neighbour candidates (wide cells: byte counts in the side
+    table), none more (no overflow cell, so the lean likelihood kernel without the window-search fallback runs)."""
+    rng = np.random.default_rng(92)
+    s = {"map": synth.make_points(rng.uniform(0.0, 1.0, (600, 3)).astype(np.float32))}
+    P, n_lik = 64, 64
+    s["particles"] = synth.make_poses(rng.uniform(0.3, 0.7, (P, 3)), synth.quat_from_rpy(rng.normal(0, 0.3, (P, 3))))
+    s["lik"] = synth.make_points(rng.uniform(-0.7, 0.7, (n_lik, 3)))
+    s["beam"] = synth.make_points(rng.uniform(-0.6, 0.6, (8, 3)))
+    s["origins"] = np.zeros((1, 3), np.float32)
+    for use_dda in (True, False):  # the KD-tree caster's marching search reads the same lists
+        cpu = run_both(eng_mod, eng, cc, s, (1, 1, 1), 8, dda_grid=0.2, use_dda=use_dda)
+        info = eng.nn_field_info()
+        if os.environ.get("MCL3DL_MAPPING") != "group":  # (the plain kernels search the CSR windows: no field staged)
+            assert info["bytes"] > 0 and info["wide_cells"] > 0
+            assert not use_dda or info["overflow_cells"] == 0  # (the KD caster's larger search radius may overflow a few)
+        want = cpu.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+        got = eng.measure(s["particles"], s["lik"], s["beam"], s["origins"])
+        check_records(got, want, 8)
+        assert want["match_cnt"].sum() > 0
 
 
 # ------------------------------------------------------------------ engine options (profiles/r01y_ab_variants.txt)

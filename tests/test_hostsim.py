@@ -40,7 +40,7 @@ def hostsim():
         """near = dilation of the (likelihood, KD-caster) near-field screens; 0 = the unscreened searches.
         field = 1: stage the NN field (per-voxel candidate lists) and search through it, as the engine does by default;
         0: the CSR window searches.  work: [nn index entries, nn pts, steps, occupied, tested, field candidates stored,
-        field voxels with candidates, field overflow cells]."""
+        field voxels with candidates, field overflow cells, field wide cells]."""
         map_pts = np.ascontiguousarray(map_pts, dtype=synth.POINT)
         poses = np.ascontiguousarray(poses, dtype=synth.POSE)
         lik_pts = np.ascontiguousarray(lik_pts if lik_pts is not None else np.zeros(0, synth.POINT), dtype=synth.POINT)
@@ -48,7 +48,7 @@ def hostsim():
         origins = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
         out = np.zeros(len(poses), dtype=synth.RESULT)
         st = np.zeros((len(poses), max(len(beam_pts), 1)), dtype=np.uint8)
-        wk = np.zeros(8, dtype=np.uint64)
+        wk = np.zeros(9, dtype=np.uint64)
         p = lambda a: a.ctypes.data_as(vp) if a.size else None  # noqa: E731
         rc = L.hostsim_measure_nf(p(map_pts), len(map_pts), C.byref(lik) if lik is not None else None,
                                   C.byref(beam) if beam is not None else None, 1.0, p(poses), len(poses), p(lik_pts),
@@ -128,7 +128,7 @@ def test_nn_field_changes_no_result(hostsim, seed, w, spread, use_dda, r):
     got, st, wk = hostsim(s["map"], lik, beam, s["particles"], s["lik"], s["beam"], s["origins"], near=(2, 1), work=True, field=1)
     assert got.tobytes() == ref.tobytes()
     assert np.array_equal(st, st_ref)
-    assert wk[5] > 0 and wk[6] > 0 and wk[7] * 1000 < wk[6]   # candidates stored, (almost) no overflow cell on a voxel-filtered map
+    assert wk[5] > 0 and wk[6] > 0 and wk[7] == 0             # candidates stored, no overflow cell on a voxel-filtered map
     assert wk[1] < wk_ref[1]                                  # fewer map points tested by the likelihood evals
     assert wk[5] / wk[6] < 8.0                                # a handful of candidates per voxel
     if not use_dda:
@@ -136,8 +136,9 @@ def test_nn_field_changes_no_result(hostsim, seed, w, spread, use_dda, r):
 
 
 def test_nn_field_overflow_cells_fall_back(hostsim, port):
-    """A raw cloud with thousands of points per voxel: more than 14 candidates survive, the directory cells are marked
-    and the queries there run the CSR window search — same records as the oracle."""
+    """A raw cloud with thousands of points per voxel: more than 14 candidates survive in most voxels (wide cells, byte
+    counts in the side table) and more than 40 in some (overflow cells: the queries there run the CSR window search) —
+    same records as the oracle."""
     rng = np.random.default_rng(91)
     pts = rng.uniform(0.0, 1.0, (20_000, 3)).astype(np.float32)
     mp = synth.make_points(pts)
@@ -149,7 +150,28 @@ def test_nn_field_overflow_cells_fall_back(hostsim, port):
     want = cpu.measure(poses, scan, None, np.zeros((1, 3), np.float32))
     got, _, wk = hostsim(mp, lik, None, poses, scan, None, np.zeros((1, 3), np.float32), work=True, field=1)
     assert np.array_equal(got["match_cnt"], want["match_cnt"]) and np.array_equal(got["score_like"], want["score_like"])
-    assert wk[7] > 0 and want["match_cnt"].sum() > 0
+    assert wk[7] > 0 and wk[8] > 0 and want["match_cnt"].sum() > 0
+
+
+def _sparse_volume_scene(n_map=600, P=64, n_lik=64, seed=92):
+    """A uniform random cloud sparse enough that no voxel keeps more than 40 candidates but some keep more than 14."""
+    rng = np.random.default_rng(seed)
+    mp = synth.make_points(rng.uniform(0.0, 1.0, (n_map, 3)).astype(np.float32))
+    poses = synth.make_poses(rng.uniform(0.3, 0.7, (P, 3)), synth.quat_from_rpy(rng.normal(0, 0.3, (P, 3))))
+    scan = synth.make_points(rng.uniform(-0.7, 0.7, (n_lik, 3)))
+    return mp, poses, scan
+
+
+def test_nn_field_wide_cells_change_no_result(hostsim):
+    """Voxels with 15..40 candidates live in wide cells (byte counts in a side table, device_funcs.cuh: nnf_slot): the
+    records equal the CSR window search's bit for bit and no cell overflows."""
+    mp, poses, scan = _sparse_volume_scene()
+    lik = engine.LikParams(dist_weight=(1, 1, 1))
+    org = np.zeros((1, 3), np.float32)
+    ref, _ = hostsim(mp, lik, None, poses, scan, None, org, near=(0, 0), field=0)
+    got, _, wk = hostsim(mp, lik, None, poses, scan, None, org, work=True, field=1)
+    assert got.tobytes() == ref.tobytes()
+    assert wk[8] > 0 and wk[7] == 0 and ref["match_cnt"].sum() > 0
 
 
 def test_device_functions_survive_garbage_inputs_under_sanitizers(tmp_path):
