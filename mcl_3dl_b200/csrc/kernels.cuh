@@ -677,7 +677,6 @@ __global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
             qy[u] = fmul(t.y, g.wy);
             qz[u] = fmul(t.z, g.wz);
             c[u] = nnf_lookup(f, qx[u], qy[u], qz[u], s[u]);
-            ++st_rows;
             cm = max(cm, c[u]);
           }
         }
@@ -719,6 +718,8 @@ __global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
         }
       }
     }
+    if (live && l < N)
+      st_rows += static_cast<uint32_t>((N - l + TPP - 1) / TPP);  // one directory entry per eval of this lane
     nf_reduce<TPP>(score, cnt, red_f, red_u);
     if (live && l == 0)  // empty scan -> LidarMeasurementResult(1, 0), likelihood.cpp:111-114
       sink_store_lik(sink, out, p, (N == 0) ? 1.0f : score, cnt, write_beam_defaults);
