@@ -578,6 +578,36 @@ __device__ __forceinline__ int nnf_lookup(const NnFieldDev& f, float qx, float q
   return nnf_slot(f, d, (vx & 1) | ((vy & 1) << 1) | ((vz & 1) << 2), start);
 }
 
+// A voxel's candidate list is walked 16 bytes at a time, one 32-byte sector per two records and every new sector a fresh
+// L2 / DRAM latency when the list is cold.  Ask for the sectors behind the first one as soon as the directory entry is
+// decoded (no registers held; lists of up to 7-8 records are covered).  c2 15.0 -> 13.3 us, c5 likelihood kernel
+// 137 -> 108 us (profiles/r02ac_summary.txt).  MCL3DL_NF_PREFETCH: 0 off, 1 prefetch.global.L1, 2 prefetch.global.L2.
+// (The KD caster's marching search gains nothing from it: c3_kd 234 -> 239 us, profiles/r02ad_summary.txt.)
+#ifndef MCL3DL_NF_PREFETCH
+#define MCL3DL_NF_PREFETCH 2
+#endif
+__device__ __forceinline__ void nnf_prefetch_list(const NnFieldDev& f, uint32_t start, int count)
+{
+#if defined(__CUDA_ARCH__) && MCL3DL_NF_PREFETCH
+  const float4* cp = f.cand + start;
+  const int i0 = 2 - static_cast<int>(start & 1u);  // first record of the next sector
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (i0 + 2 * k < count)
+    {
+#if MCL3DL_NF_PREFETCH == 1
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(cp + i0 + 2 * k));
+#else
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + i0 + 2 * k));
+#endif
+    }
+#else
+  (void)f;
+  (void)start;
+  (void)count;
+#endif
+}
+
 // nn_dist2 through the field (likelihood model): min over the voxel's candidates, r2 if none is closer.
 __device__ __forceinline__ float nnf_dist2(const NnGridDev& g, const LikDev& lp, float qx, float qy, float qz,
                                            uint32_t& n_rows, uint32_t& n_pts)

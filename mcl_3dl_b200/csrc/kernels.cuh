@@ -678,6 +678,9 @@ __global__ void __launch_bounds__(kBlockThreads, MCL3DL_NF_MINB)
             qz[u] = fmul(t.z, g.wz);
             c[u] = nnf_lookup(f, qx[u], qy[u], qz[u], s[u]);
             cm = max(cm, c[u]);
+#if MCL3DL_NF_PREFETCH
+            nnf_prefetch_list(f, s[u], c[u]);  // the candidate loop below then finds the list's later sectors in flight
+#endif
           }
         }
         // ---- candidates of the voxels, interleaved
