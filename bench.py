@@ -656,8 +656,12 @@ def e2e_leg(cx, workload, raycaster, steps, live, fused=True):
         out_host = np.zeros(n_total, dtype=synth.RESULT)
         # the buffer addresses are resolved once (Engine.bind_measure), as a C++ caller's would be: every timed call is
         # exactly one mcl3dl_measure(host pointers) = staging + H2D + kernels + D2H + synchronise
-        h_in = [np.ascontiguousarray(a, dtype=dt) for a, dt in ((particles, synth.POSE), (s["lik"], synth.POINT),
-                                                                 (s["beam"], synth.POINT))]
+        # the caller's pose and record arrays live in page-locked memory (mcl3dl_host_alloc), as the adapter's do: they
+        # are transferred in place; the scans and origins are ordinary memory and go through the engine's staging block
+        h_poses = eng.host_array(n_total, synth.POSE)
+        h_poses[...] = np.ascontiguousarray(particles, dtype=synth.POSE)
+        out_host = eng.host_array(n_total, synth.RESULT)
+        h_in = [h_poses] + [np.ascontiguousarray(a, dtype=dt) for a, dt in ((s["lik"], synth.POINT), (s["beam"], synth.POINT))]
         h_org = np.ascontiguousarray(s["origins"], dtype=np.float32).reshape(-1, 3)
         call = eng.bind_measure(h_in[0], h_in[1], h_in[2], h_org, out_host)
         flushes = [cx.flush] + [torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", d))
@@ -686,6 +690,8 @@ def e2e_leg(cx, workload, raycaster, steps, live, fused=True):
                "h2d_bytes_per_step": n_total * 32 + world * (n_lik * 16 + n_beam * 16 + n_org * 16),
                "d2h_bytes_per_step": n_total * 24,
                "timing": "host wall clock around the synchronous call, L2 of every device flushed before it",
+               "host_buffers": "poses and records in page-locked memory from mcl3dl_host_alloc (transferred in place); scans "
+                               "and origins in ordinary memory (staged)",
                "last_call_device_ms": last,
                "path": ("mcl3dl_measure on this process' one-device engine" if world == 1 else
                         "mcl3dl_measure on ONE in-process engine over %d devices (rank 0; one host thread, every record "
@@ -706,6 +712,7 @@ def e2e_leg(cx, workload, raycaster, steps, live, fused=True):
             out["fused_weight_update"] = {"value": evals * steps / ftot, "unit": "evals/s", "ms_per_step": 1e3 * ftot / steps,
                                           "h2d_bytes_per_step": out["h2d_bytes_per_step"] + n_total * 4,
                                           "d2h_bytes_per_step": n_total * 4, "entropy": summ["entropy"], "kept": summ["kept"]}
+        out_host = out_host.copy()  # (the page-locked block goes away with the engine)
         live["out_host"] = out_host
         if world > 1:
             # the in-process N-device engine against this rank's own device-resident shard (first shard of the job)

@@ -150,6 +150,16 @@ int mcl3dl_set_map(mcl3dl_engine*, const mcl3dl_point* pts, size_t n, uint64_t s
  * match_dist_min, dist_weight and dda_grid_size are unchanged; otherwise returns INVALID_ARG. */
 int mcl3dl_set_params(mcl3dl_engine*, const mcl3dl_lik_params* lik, const mcl3dl_beam_params* beam);
 
+/* Page-locked host memory for the caller's pose and record arrays (optional).  mcl3dl_measure recognises arrays that lie
+ * inside such a block: a pose array of >= 64 KB is DMA-ed from where it lies and the records are written where the caller
+ * reads them (by the D2H copy, or by the kernels themselves for small updates) - the staging memcpy on both sides of the
+ * call goes away (65 536 particles: 3.5 MB per update).  Any other host pointer keeps working through the engine's own
+ * staging block.  No reference counterpart: pf::ParticleFilter keeps std::vector<Particle> (include/mcl_3dl/pf.h:395);
+ * the adapter packs State6DOF into mcl3dl_pose anyway (host/lidar_measurement_model_b200.h) and can pack into this.
+ * mcl3dl_host_free waits for the engine's streams; blocks still allocated at mcl3dl_destroy are freed there. */
+int mcl3dl_host_alloc(mcl3dl_engine*, size_t bytes, void** out);
+int mcl3dl_host_free(mcl3dl_engine*, void* block);
+
 /* One measurement update for P particles: replaces the P x {beam, likelihood} calls
  *   lm.second->measure(kdtree_, pc_locals[name], origins, s)     (src/mcl_3dl.cpp:409-415)
  * that pf::ParticleFilter::measure makes one particle at a time (include/mcl_3dl/pf.h:256-260).

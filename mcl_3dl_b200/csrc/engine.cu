@@ -438,7 +438,22 @@ struct mcl3dl_engine
   size_t nnf_max_bytes = size_t(32) << 30;  // MCL3DL_NNF_MAX_MB: directory + candidates above this -> no field
   uint64_t nnf_bytes = 0, nnf_cands = 0, nnf_overflow_cells = 0, nnf_wide_cells = 0;
   int mapping = 1;  // 1 = tuned kernels (lik_kernel_wi + beam_kernel_pl); 0 = the plain group kernels (MCL3DL_MAPPING=group)
+  // page-locked blocks handed to the caller by mcl3dl_host_alloc: pose / record arrays that live in one of them are
+  // DMA-ed (or, small updates, written by the kernels) in place instead of going through the engine's staging block
+  std::vector<std::pair<char*, size_t>> host_blocks;
+  size_t direct_min_bytes = size_t(64) << 10;  // smaller pose arrays ride in the staging block's single copy: a second DMA
+                                               // operation costs more than their memcpy (c2, 32 KB: 36.6 vs 40.7 us;
+                                               // c3, 128 KB: 130 -> 126 us; profiles/r02ae_summary.txt); MCL3DL_DIRECT_MIN_KB
 };
+
+static bool in_host_block(const mcl3dl_engine* eng, const void* p, size_t bytes)
+{
+  const char* q = static_cast<const char*>(p);
+  for (const auto& b : eng->host_blocks)
+    if (q >= b.first && q + bytes <= b.first + b.second)
+      return true;
+  return false;
+}
 
 namespace
 {
@@ -1467,6 +1482,8 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
     eng->timing = std::atoi(v) != 0;
   if (const char* v = std::getenv("MCL3DL_ZEROCOPY_OUT"))
     eng->zero_copy_max = static_cast<size_t>(std::max(std::atol(v), 0L));
+  if (const char* v = std::getenv("MCL3DL_DIRECT_MIN_KB"))  // -1: never copy from / to the caller's page-locked arrays in place
+    eng->direct_min_bytes = std::atoi(v) < 0 ? ~size_t(0) : static_cast<size_t>(std::atoi(v)) << 10;
   if (const char* v = std::getenv("MCL3DL_UPDATE_ONE_SYNC"))
     eng->update_one_sync = std::atoi(v) != 0;
   if (const char* v = std::getenv("MCL3DL_NNF"))
@@ -1533,6 +1550,40 @@ int mcl3dl_create(mcl3dl_engine** out, const int* device_ids, int n_devices)
 
 static void xchg_close(DeviceCtx& c);
 
+int mcl3dl_host_alloc(mcl3dl_engine* eng, size_t bytes, void** out)
+{
+  if (!eng || !out || bytes == 0 || eng->devs.empty())
+    return MCL3DL_ERR_INVALID_ARG;
+  *out = nullptr;
+  CK(cudaSetDevice(eng->devs[0].dev));
+  void* p = nullptr;
+  // portable: page-locked for every device of a multi-device engine; mapped into the unified address space, so that the
+  // kernels of small updates can store their records into it
+  CK(cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+  eng->host_blocks.emplace_back(static_cast<char*>(p), bytes);
+  *out = p;
+  return MCL3DL_OK;
+}
+
+int mcl3dl_host_free(mcl3dl_engine* eng, void* p)
+{
+  if (!eng || !p)
+    return MCL3DL_ERR_INVALID_ARG;
+  for (size_t i = 0; i < eng->host_blocks.size(); ++i)
+    if (eng->host_blocks[i].first == p)
+    {
+      for (DeviceCtx& c : eng->devs)  // nothing of this engine may still be reading or writing the block
+      {
+        CK(cudaSetDevice(c.dev));
+        if (c.stream) CK(cudaStreamSynchronize(c.stream));
+      }
+      eng->host_blocks.erase(eng->host_blocks.begin() + static_cast<std::ptrdiff_t>(i));
+      CK(cudaFreeHost(p));
+      return MCL3DL_OK;
+    }
+  return MCL3DL_ERR_INVALID_ARG;
+}
+
 void mcl3dl_destroy(mcl3dl_engine* eng)
 {
   if (!eng)
@@ -1570,6 +1621,8 @@ void mcl3dl_destroy(mcl3dl_engine* eng)
     if (c.stream)
       cudaStreamDestroy(c.stream);
   }
+  for (auto& b : eng->host_blocks)  // (blocks the caller did not return; its pointers into them dangle from here on)
+    cudaFreeHost(b.first);
   delete eng;
 }
 
@@ -2452,7 +2505,11 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     if ((rc = reserve(eng, c.d_poses, o_out)) || (rc = reserve(eng, c.d_out, b_out)) || (rc = reserve(eng, c.d_status, b_status)))
       return rc;
     char* hp = static_cast<char*>(c.h_pinned);
-    std::memcpy(hp, poses + p0[d], b_poses);
+    // caller arrays inside a mcl3dl_host_alloc block are page-locked: a large pose array is DMA-ed from where it lies
+    // and the records land where the caller reads them, without the staging memcpy on either side
+    const bool poses_direct = b_poses >= eng->direct_min_bytes && in_host_block(eng, poses + p0[d], b_poses);
+    const bool out_direct = out && eng->direct_min_bytes != ~size_t(0) && in_host_block(eng, out + p0[d], b_out);
+    if (!poses_direct) std::memcpy(hp, poses + p0[d], b_poses);
     if (b_lik) std::memcpy(hp + o_lik, lik_pts, b_lik);
     if (b_beam) std::memcpy(hp + o_beam, beam_pts, b_beam);
     if (n_origins) std::memcpy(hp + o_org, origins_xyz, n_origins * 12);
@@ -2462,21 +2519,29 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     const bool zc = !status && Pd <= eng->zero_copy_max;  // (per-ray status bytes would be scattered 1-byte PCIe writes)
     if (timed) CK(cudaEventRecord(c.ev[0], st));
     // (an SM copy kernel reading the mapped block instead of the copy engine measured the same: profiles/r02p_e2e.txt)
-    CK(cudaMemcpyAsync(c.d_poses.p, hp, o_out, cudaMemcpyHostToDevice, st));
+    if (poses_direct)
+    {
+      CK(cudaMemcpyAsync(c.d_poses.p, poses + p0[d], b_poses, cudaMemcpyHostToDevice, st));
+      if (o_out > o_lik)
+        CK(cudaMemcpyAsync(static_cast<char*>(c.d_poses.p) + o_lik, hp + o_lik, o_out - o_lik, cudaMemcpyHostToDevice, st));
+    }
+    else
+      CK(cudaMemcpyAsync(c.d_poses.p, hp, o_out, cudaMemcpyHostToDevice, st));
     const char* d_in = static_cast<const char*>(c.d_poses.p);
     const mcl3dl_pose* d_poses = reinterpret_cast<const mcl3dl_pose*>(d_in);
     const mcl3dl_point* d_lik = reinterpret_cast<const mcl3dl_point*>(d_in + o_lik);
     const mcl3dl_point* d_beam = reinterpret_cast<const mcl3dl_point*>(d_in + o_beam);
     const float* d_org = reinterpret_cast<const float*>(d_in + o_org);
     if (timed) CK(cudaEventRecord(c.ev[1], st));
-    mcl3dl_result* k_out = zc ? reinterpret_cast<mcl3dl_result*>(hp + o_out) : static_cast<mcl3dl_result*>(c.d_out.p);
+    mcl3dl_result* h_out = out_direct ? out + p0[d] : reinterpret_cast<mcl3dl_result*>(hp + o_out);
+    mcl3dl_result* k_out = zc ? h_out : static_cast<mcl3dl_result*>(c.d_out.p);
     uint8_t* k_status = status ? static_cast<uint8_t*>(c.d_status.p) : nullptr;
     rc = launch_models(eng, c, d_poses, Pd, d_lik, n_lik, d_beam, n_beam, d_org, n_origins, k_out, k_status, st, timed);
     if (rc != MCL3DL_OK) return rc;
     if (timed) CK(cudaEventRecord(c.ev[5], st));
     if (!zc)
     {
-      CK(cudaMemcpyAsync(hp + o_out, c.d_out.p, b_out, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(h_out, c.d_out.p, b_out, cudaMemcpyDeviceToHost, st));
       if (b_status) CK(cudaMemcpyAsync(hp + o_status, c.d_status.p, b_status, cudaMemcpyDeviceToHost, st));
     }
     if (timed) CK(cudaEventRecord(c.ev[4], st));
@@ -2493,7 +2558,8 @@ static int measure_host(mcl3dl_engine* eng, const mcl3dl_pose* poses, size_t P, 
     const size_t o_out = Pd * sizeof(mcl3dl_pose) + n_lik * 16 + n_beam * 16 + ((n_origins * 12 + 15) & ~size_t(15));
     const size_t o_status = o_out + Pd * sizeof(mcl3dl_result);
     const char* hp = static_cast<const char*>(c.h_pinned);
-    if (out) std::memcpy(out + p0[d], hp + o_out, Pd * sizeof(mcl3dl_result));
+    if (out && !(eng->direct_min_bytes != ~size_t(0) && in_host_block(eng, out + p0[d], Pd * sizeof(mcl3dl_result))))  // (else: already there)
+      std::memcpy(out + p0[d], hp + o_out, Pd * sizeof(mcl3dl_result));
     if (status) std::memcpy(status + p0[d] * n_beam, hp + o_status, Pd * n_beam);
     float ms_h2d = 0, ms_lik = 0, ms_beam = 0, ms_d2h = 0;
     if (eng->timing)

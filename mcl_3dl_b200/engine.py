@@ -104,7 +104,7 @@ class WorkStats(C.Structure):
 EXPORTED_SYMBOLS = ["mcl3dl_measure_update", "mcl3dl_collect_stats", "mcl3dl_read_stats", "mcl3dl_abi_version", "mcl3dl_create", "mcl3dl_destroy", "mcl3dl_set_map", "mcl3dl_set_params",
                     "mcl3dl_measure", "mcl3dl_measure_device", "mcl3dl_beam_status",
                     "mcl3dl_beam_params_from_reference", "mcl3dl_get_map_info", "mcl3dl_last_timing",
-                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_nn_field_info", "mcl3dl_field_mode", "mcl3dl_field_nodes", "mcl3dl_field_upload", "mcl3dl_collect_timing",
+                    "mcl3dl_kernel_launches", "mcl3dl_strerror", "mcl3dl_last_error_detail", "mcl3dl_near_field_info", "mcl3dl_nn_field_info", "mcl3dl_host_alloc", "mcl3dl_host_free", "mcl3dl_field_mode", "mcl3dl_field_nodes", "mcl3dl_field_upload", "mcl3dl_collect_timing",
                     "mcl3dl_exchange_create", "mcl3dl_exchange_open", "mcl3dl_measure_exchange_device", "mcl3dl_exchange_current",
                     "mcl3dl_particles_set", "mcl3dl_particles_get", "mcl3dl_particles_predict",
                     "mcl3dl_particles_measure_update", "mcl3dl_particles_resample", "mcl3dl_particles_estimate", "mcl3dl_scan_prepare", "mcl3dl_scan_get",
@@ -169,6 +169,8 @@ def load_library(path=None):
     L.mcl3dl_field_mode.argtypes = [vp, C.c_int]
     L.mcl3dl_field_nodes.argtypes = [vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.mcl3dl_field_upload.argtypes = [vp, vp, C.POINTER(C.c_int32)]
+    L.mcl3dl_host_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.mcl3dl_host_free.argtypes = [vp, vp]
     assert L.mcl3dl_abi_version() == 3
     _LIBS[path] = L
     return L
@@ -286,6 +288,22 @@ class Engine:
         self._check(self.L.mcl3dl_measure(self.h, _ptr(poses), len(poses), _ptr(lik_pts), len(lik_pts),
                                           _ptr(beam_pts), len(beam_pts), _ptr(origins), len(origins), _ptr(out)))
         return out
+
+    def host_array(self, n, dtype):
+        """A zeroed numpy array of n items in page-locked memory of this engine (mcl3dl_host_alloc): pose and record
+        arrays passed to measure / bind_measure from such memory are transferred in place, without the staging memcpy.
+        The memory is returned by host_free(array) or when the engine is closed - do not use the array after that."""
+        dtype = np.dtype(dtype)
+        nbytes = max(1, int(n) * dtype.itemsize)
+        p = C.c_void_p()
+        self._check(self.L.mcl3dl_host_alloc(self.h, nbytes, C.byref(p)))
+        buf = (C.c_char * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+        arr[...] = np.zeros((), dtype)
+        return arr
+
+    def host_free(self, arr):
+        self._check(self.L.mcl3dl_host_free(self.h, arr.ctypes.data))
 
     def bind_measure(self, poses, lik_pts, beam_pts, origins, out):
         """A repeated update over the SAME host arrays (their contents may change between calls): resolves the buffer

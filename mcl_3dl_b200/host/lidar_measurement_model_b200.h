@@ -18,6 +18,7 @@
 #ifndef MCL_3DL_B200_LIDAR_MEASUREMENT_MODEL_B200_H
 #define MCL_3DL_B200_LIDAR_MEASUREMENT_MODEL_B200_H
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <random>
@@ -49,6 +50,71 @@ using ParticleFilter =
 
 // State shared by the two model adapters of one node: the engine handle, the particle filter whose
 // particles are batched, the clouds of the current cycle and the cached per-particle records.
+// A growable array in page-locked memory of the engine (mcl3dl_host_alloc): mcl3dl_measure transfers pose and record
+// arrays that live there in place, without a staging copy on either side of the call.
+template <typename T>
+class PinnedArray
+{
+public:
+  PinnedArray() = default;
+  PinnedArray(const PinnedArray&) = delete;
+  PinnedArray& operator=(const PinnedArray&) = delete;
+  ~PinnedArray()
+  {
+    release();
+  }
+  void bind(mcl3dl_engine* engine)
+  {
+    engine_ = engine;
+  }
+  // Must run before mcl3dl_destroy of the bound engine.
+  void release()
+  {
+    if (data_)
+      mcl3dl_host_free(engine_, data_);
+    data_ = nullptr;
+    size_ = cap_ = 0;
+  }
+  // Contents are unspecified after a resize that grows the block (every user refills the array).
+  void resize(size_t n)
+  {
+    if (n > cap_)
+    {
+      const size_t cap = std::max(n, cap_ * 2);
+      void* p = nullptr;
+      const int rc = mcl3dl_host_alloc(engine_, cap * sizeof(T), &p);
+      if (rc != MCL3DL_OK)
+        throw std::runtime_error(std::string("mcl3dl_host_alloc: ") + mcl3dl_strerror(rc));
+      if (data_)
+        mcl3dl_host_free(engine_, data_);
+      data_ = static_cast<T*>(p);
+      cap_ = cap;
+    }
+    size_ = n;
+  }
+  size_t size() const
+  {
+    return size_;
+  }
+  T* data()
+  {
+    return data_;
+  }
+  T& operator[](size_t i)
+  {
+    return data_[i];
+  }
+  const T& operator[](size_t i) const
+  {
+    return data_[i];
+  }
+
+private:
+  mcl3dl_engine* engine_ = nullptr;
+  T* data_ = nullptr;
+  size_t size_ = 0, cap_ = 0;
+};
+
 class MeasurementBatcher
 {
 public:
@@ -65,9 +131,13 @@ public:
                                  devices.empty() ? 1 : static_cast<int>(devices.size()));
     if (rc != MCL3DL_OK)  // no CPU fallback: the node must not start without its device
       throw std::runtime_error(std::string("mcl3dl_create: ") + mcl3dl_strerror(rc));
+    poses_.bind(engine_);
+    results_.bind(engine_);
   }
   ~MeasurementBatcher()
   {
+    poses_.release();
+    results_.release();
     mcl3dl_destroy(engine_);
   }
   MeasurementBatcher(const MeasurementBatcher&) = delete;
@@ -125,8 +195,7 @@ public:
       stageMap(kdtree);
     pack(lik_cloud_, lik_pts_);
     pack(beam_cloud_, beam_pts_);
-    poses_.clear();
-    for (auto it = pf_->begin(); it != pf_->end(); ++it) poses_.push_back(toPose(it->state_));
+    packPoses();
     posterior.assign(poses_.size(), 0.0f);
     std::vector<float> o(origins.size() * 3);
     for (size_t k = 0; k < origins.size(); ++k)
@@ -264,6 +333,13 @@ private:
                          o.data(), origins.size(), out),
           "mcl3dl_measure");
   }
+  // State6DOF -> mcl3dl_pose for every particle, straight into the page-locked array the engine copies from
+  void packPoses()
+  {
+    poses_.resize(pf_->getParticleSize());
+    size_t i = 0;
+    for (auto it = pf_->begin(); it != pf_->end(); ++it) poses_[i++] = toPose(it->state_);
+  }
   void runBatch(ChunkedKdtree<PointType>::Ptr& kdtree, const std::vector<Vec3>& origins)
   {
     stageMap(kdtree);
@@ -271,9 +347,8 @@ private:
       stageMap(kdtree);
     pack(lik_cloud_, lik_pts_);
     pack(beam_cloud_, beam_pts_);
-    poses_.clear();
-    for (auto it = pf_->begin(); it != pf_->end(); ++it) poses_.push_back(toPose(it->state_));
-    results_.assign(poses_.size(), mcl3dl_result());
+    packPoses();
+    results_.resize(poses_.size());
     callEngine(poses_.data(), poses_.size(), origins, results_.data());
     origins_.resize(origins.size() * 3);
     for (size_t k = 0; k < origins.size(); ++k)
@@ -299,8 +374,8 @@ private:
   uint64_t stamp_counter_ = 0;
   Cloud::ConstPtr lik_cloud_, beam_cloud_;
   std::vector<mcl3dl_point> lik_pts_, beam_pts_;
-  std::vector<mcl3dl_pose> poses_;
-  std::vector<mcl3dl_result> results_;
+  PinnedArray<mcl3dl_pose> poses_;
+  PinnedArray<mcl3dl_result> results_;
   std::vector<float> origins_;
   size_t cursor_lik_ = 0, cursor_beam_ = 0;
   bool valid_ = false;

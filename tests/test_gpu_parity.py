@@ -454,6 +454,34 @@ def test_wide_cells_of_the_nn_field(eng_mod, eng, cc):
         assert want["match_cnt"].sum() > 0
 
 
+@pytest.mark.parametrize("P", [64, 4096, 20000])
+def test_page_locked_caller_arrays_are_transferred_in_place(eng_mod, eng_mod_engine_tuned, P):
+    """Pose / record arrays from mcl3dl_host_alloc skip the staging copies (poses of >= 64 KB are DMA-ed from where they
+    lie; the records are stored - by the kernels up to 8192 particles, by the D2H copy above - where the caller reads
+    them): same bytes as the same call on ordinary memory, also after the block went back (ordinary path again)."""
+    eng = eng_mod_engine_tuned
+    s = synth.scene(40_000, P, 48, 8, seed=77)
+    eng.set_map(s["map"], eng_mod.LikParams(dist_weight=(1, 1, 5)),
+                eng_mod.beam_params_from_reference(num_points_default=8, dda_grid_size=0.2))
+    want = eng.measure(s["particles"], s["lik"], s["beam"], s["origins"]).copy()
+    h_p = eng.host_array(P, synth.POSE)
+    h_p[...] = s["particles"]
+    h_o = eng.host_array(P, synth.RESULT)
+    got = eng.measure(h_p, s["lik"], s["beam"], s["origins"], out=h_o)
+    assert got.ctypes.data == h_o.ctypes.data            # no hidden copy on the Python side
+    assert got.tobytes() == want.tobytes()
+    # a slice of a block is still inside the block; results of a second call overwrite the first
+    h_o[...] = np.zeros((), synth.RESULT)
+    half = P // 2
+    want2 = eng.measure(s["particles"][half:], s["lik"], s["beam"], s["origins"]).copy()  # (another P: other lane counts)
+    got2 = eng.measure(h_p[half:], s["lik"], s["beam"], s["origins"], out=h_o[half:])
+    assert got2.tobytes() == want2.tobytes() and not h_o[:half].tobytes().strip(b"\0")
+    keep = h_p.copy()
+    eng.host_free(h_p)
+    eng.host_free(h_o)
+    assert eng.measure(keep, s["lik"], s["beam"], s["origins"]).tobytes() == want.tobytes()
+
+
 # ------------------------------------------------------------------ engine options (profiles/r01y_ab_variants.txt)
 @pytest.mark.parametrize("use_dda", [True, False])
 def test_options_change_no_record(eng_mod, monkeypatch, use_dda):
