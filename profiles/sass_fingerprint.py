@@ -2,7 +2,7 @@
 """Per-kernel SASS fingerprints of a built library (addresses stripped), to tell whether an edit touched a kernel's code.
 
     python profiles/sass_fingerprint.py [lib.so] > profiles/<tag>_sass_fingerprint.txt
-    python profiles/sass_fingerprint.py --diff profiles/r01y_sass_fingerprint.txt [lib.so]
+    python profiles/sass_fingerprint.py --diff profiles/r02_sass_fingerprint.txt [lib.so]
 """
 import hashlib
 import os
@@ -39,6 +39,6 @@ if __name__ == "__main__":
         print("# %d kernels, %d identical" % (len(new), sum(1 for k in new if old.get(k) == new[k])))
     else:
         fp = fingerprints(args[0] if args else DEFAULT)
-        print("# sha256[:16] of each kernel's SASS text (cuobjdump -sass, addresses stripped)")
+        print("# <kernel> <sha256[:16] of its SASS text (cuobjdump -sass, addresses stripped)>")
         for k in sorted(fp):
-            print(fp[k], k)
+            print(k, fp[k])
