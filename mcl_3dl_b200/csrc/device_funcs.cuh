@@ -582,7 +582,8 @@ __device__ __forceinline__ int nnf_lookup(const NnFieldDev& f, float qx, float q
 // L2 / DRAM latency when the list is cold.  Ask for the sectors behind the first one as soon as the directory entry is
 // decoded (no registers held; lists of up to 7-8 records are covered).  c2 15.0 -> 13.3 us, c5 likelihood kernel
 // 137 -> 108 us (profiles/r02ac_summary.txt).  MCL3DL_NF_PREFETCH: 0 off, 1 prefetch.global.L1, 2 prefetch.global.L2.
-// (The KD caster's marching search gains nothing from it: c3_kd 234 -> 239 us, profiles/r02ad_summary.txt.)
+// (The KD caster's marching search gains nothing from it: c3_kd 234 -> 239 us, profiles/r02ad_summary.txt; neither do a
+// deeper list prefetch or a prefetch of the next trip's poses: profiles/r02af_summary.txt.)
 #ifndef MCL3DL_NF_PREFETCH
 #define MCL3DL_NF_PREFETCH 2
 #endif
@@ -591,8 +592,11 @@ __device__ __forceinline__ void nnf_prefetch_list(const NnFieldDev& f, uint32_t 
 #if defined(__CUDA_ARCH__) && MCL3DL_NF_PREFETCH
   const float4* cp = f.cand + start;
   const int i0 = 2 - static_cast<int>(start & 1u);  // first record of the next sector
+#ifndef MCL3DL_NF_PREFETCH_DEPTH
+#define MCL3DL_NF_PREFETCH_DEPTH 3
+#endif
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
+  for (int k = 0; k < MCL3DL_NF_PREFETCH_DEPTH; ++k)
     if (i0 + 2 * k < count)
     {
 #if MCL3DL_NF_PREFETCH == 1
