@@ -29,3 +29,26 @@ def test_reference_arm_other_ranks_exit_quietly():
                         "--gpus", "2", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300,
                        cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_rotating_input_sets_of_the_back_to_back_protocol():
+    """bench.py --l2 rotate: the stations are distinct places of the same map with their own scan and particle cloud
+    (tracking workloads), every rank its own shard; station 0 is the scene itself; both arms name the same protocol."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    s, _, scaling, P_rank = bench.build_scene("c1", 0, 1)
+    st = bench.build_stations("c1", 0, 1, s, 8)
+    assert len(st) == 8 and st[0]["particles"] is s["particles"] and st[0]["lik"] is s["lik"]
+    centres = np.array([[x["particles"]["px"].mean(), x["particles"]["py"].mean()] for x in st])
+    d = np.linalg.norm(centres[:, None] - centres[None], axis=2) + np.eye(8) * 1e9
+    assert d.min() > 0.5                                     # no two stations at the same place
+    for x in st:
+        assert len(x["particles"]) == P_rank and len(x["lik"]) == len(s["lik"]) and len(x["beam"]) == len(s["beam"])
+        assert x["particles"].dtype == s["particles"].dtype and x["lik"].dtype == s["lik"].dtype
+    assert not np.array_equal(st[1]["lik"], st[2]["lik"])
+    # weak scaling: another rank draws other particles around the same stations
+    st_r1 = bench.build_stations("c1", 1, 2, bench.build_scene("c1", 1, 2)[0], 8)
+    assert not np.array_equal(st_r1[1]["particles"], st[1]["particles"])
+    assert np.allclose(st_r1[1]["particles"]["px"].mean(), st[1]["particles"]["px"].mean(), atol=0.2)
+    assert bench.config_dict("c1", s, 64, 96, 3, False, 0.2)["l2"] == bench.L2_TEXT[bench.L2_MODE]
