@@ -492,3 +492,19 @@ extern "C" int hostsim_field_dist(const float* nodes, const int32_t dims[3], con
   for (size_t q = 0; q < nq; ++q) out[q] = field_dist(f, queries_xyz[3 * q], queries_xyz[3 * q + 1], queries_xyz[3 * q + 2]);
   return 0;
 }
+
+// nnf_slot alone (device_funcs.cuh): the (count, first candidate) of voxel `sub` of one directory entry; wide entries
+// read `wide` (one uint4).  Returns the count (-1: overflow cell).
+extern "C" int hostsim_nnf_slot(uint32_t dir_x, uint32_t dir_y, const uint32_t wide[4], int sub, uint32_t* start)
+{
+  NnFieldDev f{};
+  const uint4 w = make_uint4(wide[0], wide[1], wide[2], wide[3]);
+  // a wide entry indexes the side table: give it a table whose entry (dir_x & 0x7fffffff) is `w`
+  std::vector<uint4> table((dir_x & 0x80000000u) && dir_x != 0xffffffffu ? (dir_x & 0x7fffffffu) + 1 : 1, make_uint4(0, 0, 0, 0));
+  table.back() = w;
+  f.wide = table.data();
+  uint32_t s = 0;
+  const int c = nnf_slot(f, make_uint2(dir_x, dir_y), sub, s);
+  *start = s;
+  return c;
+}

@@ -174,6 +174,38 @@ def test_nn_field_wide_cells_change_no_result(hostsim):
     assert wk[8] > 0 and wk[7] == 0 and ref["match_cnt"].sum() > 0
 
 
+def test_nn_field_directory_decoding(hostsim):
+    """nnf_slot: nibble counts of a regular cell, byte counts of a wide cell (side table), the overflow marker - against
+    plain prefix sums, for every voxel position and random counts up to the caps (14 / 40, and up to 255 per byte)."""
+    L = C.CDLL(LIB)
+    L.hostsim_nnf_slot.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]
+    rng = np.random.default_rng(5)
+    none = (C.c_uint32 * 4)(0, 0, 0, 0)
+    for trial in range(300):
+        first = int(rng.integers(0, 2 ** 31 - 400))
+        # regular cell
+        cnt = rng.integers(0, 15, 8)
+        nib = 0
+        for k in range(8):
+            nib |= int(cnt[k]) << (4 * k)
+        for sub in range(8):
+            st = C.c_uint32(0)
+            assert L.hostsim_nnf_slot(first, nib, none, sub, C.byref(st)) == cnt[sub]
+            assert st.value == first + int(cnt[:sub].sum())
+        # wide cell: entry `idx` of the side table holds {first, counts 0..3, counts 4..7}
+        cnt = rng.integers(0, 256 if trial % 3 == 0 else 41, 8)
+        lo = sum(int(cnt[k]) << (8 * k) for k in range(4))
+        hi = sum(int(cnt[4 + k]) << (8 * k) for k in range(4))
+        idx = int(rng.integers(0, 1000))
+        w = (C.c_uint32 * 4)(first, lo, hi, 0)
+        for sub in range(8):
+            st = C.c_uint32(0)
+            assert L.hostsim_nnf_slot(0x80000000 | idx, 0xfffffffe, w, sub, C.byref(st)) == cnt[sub]
+            assert st.value == first + int(cnt[:sub].sum())
+    st = C.c_uint32(0)
+    assert L.hostsim_nnf_slot(0xffffffff, 0xffffffff, none, 3, C.byref(st)) == -1
+
+
 def test_device_functions_survive_garbage_inputs_under_sanitizers(tmp_path):
     """NaN / inf / 1e30 poses and scan points, one-point maps, zero-length rays: no out-of-bounds access, no signed
     overflow and bounded work in the per-thread device functions (ASan + UBSan build of tests/hostsim/fuzz_main.cpp)."""
