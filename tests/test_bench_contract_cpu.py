@@ -52,3 +52,22 @@ def test_rotating_input_sets_of_the_back_to_back_protocol():
     assert not np.array_equal(st_r1[1]["particles"], st[1]["particles"])
     assert np.allclose(st_r1[1]["particles"]["px"].mean(), st[1]["particles"]["px"].mean(), atol=0.2)
     assert bench.config_dict("c1", s, 64, 96, 3, False, 0.2)["l2"] == bench.L2_TEXT[bench.L2_MODE]
+
+
+def test_rotating_input_sets_shard_like_the_scene_under_strong_scaling():
+    """c5 (strong scaling, spread particles): every station is one particle draw cut into the ranks' contiguous shards,
+    exactly as build_scene cuts the scene itself; the scans are the scene's."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    P = bench.WORKLOADS["c5"][1]
+    shards = []
+    for rank in range(2):
+        s, _, scaling, P_rank = bench.build_scene("c5", rank, 2)
+        st = bench.build_stations("c5", rank, 2, s, 3)
+        assert scaling == "strong" and P_rank == P // 2 and all(len(x["particles"]) == P_rank for x in st)
+        assert st[1]["lik"] is s["lik"] and st[2]["beam"] is s["beam"]
+        shards.append(st)
+    full = bench.synth.spread_particles(P, bench.build_scene("c5", 0, 1)[0]["info"], seed=3000 + 17)
+    assert np.array_equal(np.concatenate([shards[0][1]["particles"], shards[1][1]["particles"]]), full)
+    assert not np.array_equal(shards[0][1]["particles"], shards[0][2]["particles"])
