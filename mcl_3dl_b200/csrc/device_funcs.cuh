@@ -125,8 +125,8 @@ inline bool near_layout(NearBitsDev& f, float r, int k, const float sc_min[3], c
 // side.  A query therefore reads one 8-byte directory entry (2 x 2 x 2 voxels: first candidate + eight 4-bit counts)
 // and then the few (typically 3-6, contiguous) candidates, instead of walking a 3 x 3 window of CSR rows; the minimum
 // of the float distances over the candidates equals the minimum over ALL map points bit for bit whenever it is below
-// radius^2 (ties included: points that tie can not dominate each other).  Voxels with more than kNnfMaxCand survivors
-// (raw, unfiltered clouds) mark their directory cell and queries there fall back to the CSR window search.
+// radius^2 (ties included: points that tie can not dominate each other).  A voxel with more than kNnfMaxCand survivors
+// makes its cell a wide cell (counts in a side table); more than kNnfMaxSurv (raw clouds): CSR window search there.
 // No reference counterpart: ChunkedKdtree::radiusSearch (chunked_kdtree.h:218-251) descends a kd-tree per query.
 constexpr int kNnfMaxCand = 14;  // per voxel in a regular directory cell (4-bit counts)
 constexpr int kNnfMaxSurv = 40;  // per voxel in a wide cell (8-bit counts, side table); more: overflow cell
