@@ -560,6 +560,34 @@ def test_screens_and_nn_field_randomized_differential(hostsim):
             assert got.tobytes() == ref.tobytes() and np.array_equal(st, st_ref), (seed, near, field)
 
 
+def test_nn_field_volume_clouds_randomized_differential(hostsim):
+    """Uniform VOLUME clouds of random density (the maps above are surfaces): regular, wide and overflow cells all occur,
+    for both casters (the KD caster's searches go through the same lists at its own radius) — records and per-ray
+    status equal the unscreened CSR window searches'."""
+    seen_wide = seen_ovf = 0
+    for seed in range(16):
+        rng = np.random.default_rng(700 + seed)
+        n_map = int(rng.choice([150, 400, 900, 2500, 8000]))
+        ext = float(rng.choice([1.0, 2.0]))
+        mp = synth.make_points(rng.uniform(0.0, ext, (n_map, 3)).astype(np.float32), rng.integers(0, 2, n_map))
+        P, n_lik, n_beam = int(rng.integers(2, 12)), int(rng.integers(8, 48)), int(rng.integers(1, 10))
+        poses = synth.make_poses(rng.uniform(0.2 * ext, 0.8 * ext, (P, 3)), synth.quat_from_rpy(rng.normal(0, 0.4, (P, 3))))
+        lik_pts = synth.make_points(rng.uniform(-0.7 * ext, 0.7 * ext, (n_lik, 3)))
+        beam_pts = synth.make_points(rng.uniform(-0.6 * ext, 0.6 * ext, (n_beam, 3)))
+        org = np.array([[0.0, 0.0, 0.05]], np.float32)
+        w = [(1, 1, 1), (1, 1, 5), (2, 1, 3)][seed % 3]
+        lik = engine.LikParams(dist_weight=w, match_dist_min=float(rng.choice([0.1, 0.2, 0.3])))
+        g = float(rng.choice([0.05, 0.1]))
+        beam = engine.beam_params_from_reference(map_grid=(g, g, g), num_points_default=n_beam,
+                                                 use_raycast_using_dda=bool(seed % 2), dda_grid_size=0.2)
+        ref, st_ref = hostsim(mp, lik, beam, poses, lik_pts, beam_pts, org, near=(0, 0), field=0)
+        got, st, wk = hostsim(mp, lik, beam, poses, lik_pts, beam_pts, org, near=(2, 1), field=1, work=True)
+        assert got.tobytes() == ref.tobytes() and np.array_equal(st, st_ref), seed
+        seen_wide += int(wk[8] > 0)
+        seen_ovf += int(wk[7] > 0)
+    assert seen_wide >= 3 and seen_ovf >= 2   # the draw does exercise both special cell kinds
+
+
 def test_field_mode_trilinear_lookup_on_host(hostsim):
     """field_dist (the opt-in field mode's lookup, device_funcs.cuh) against a numpy trilinear interpolation of the same
     node volume: inside the lattice to float rounding, `clamp` outside, exact at the nodes."""
