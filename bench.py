@@ -10,9 +10,14 @@ scan point.  Prints ONE JSON line on rank 0 (see the contract in the task statem
   value     whole-job particle x point evals/s with all inputs resident in HBM (CUDA events, max over ranks).
             N > 1: one process per GPU, particles sharded, map replicated; the ONE exchange of the path (the gather
             of the 24-byte records) is folded into the measurement kernels, which store every record into every
-            rank's array over NVLink peer memory (csrc/kernels.cuh: RecordSink + exchange_signal_kernel); the
-            whole step is replayed as one CUDA graph.  --exchange nccl keeps the NCCL all-gather for comparison.
-  e2e       same metric through the host-buffer C-ABI call mcl3dl_measure (H2D + kernels + D2H inside).
+            rank's array over NVLink peer memory (csrc/kernels.cuh: RecordSink + exchange_signal_kernel).
+            --exchange nccl keeps the NCCL all-gather for comparison.
+            Timing (--l2 rotate, default): all K steps are ONE CUDA graph between one pair of events, step i on input
+            set i mod 32 (32 places of the map with their own scan and particles: inputs larger than L2).  --l2 flush:
+            a 256 MiB L2 flush before every step and an event pair around each (also always reported, in
+            device_step.flushed_step_ms_min_med_max; an event pair + graph launch alone read ~6 us there).
+  e2e       same metric through the host-array C-ABI call mcl3dl_measure (H2D + kernels + D2H inside; pose / record
+            arrays page-locked via mcl3dl_host_alloc, scans in ordinary memory; L2 flushed before every call).
             N > 1: ONE host process (rank 0) drives all N GPUs through the in-process multi-device engine
             (mcl3dl_create with N device ids) and receives every record in one host array — what a ROS node would do.
   roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
@@ -696,7 +701,7 @@ def e2e_leg(cx, workload, raycaster, steps, live, fused=True):
                "path": ("mcl3dl_measure on this process' one-device engine" if world == 1 else
                         "mcl3dl_measure on ONE in-process engine over %d devices (rank 0; one host thread, every record "
                         "lands in one host array — the gather is the D2H of each shard)" % world),
-               "d2h_mode": ("kernels store the records straight into the pinned host block" if n_total // world <= 8192
+               "d2h_mode": ("kernels store the records straight into the caller's page-locked array" if n_total // world <= 8192
                             else "one D2H copy of the records per device")}
         if fused:
             # the fused weight update (scope row f2): priors up, posteriors (4 B/particle) back
