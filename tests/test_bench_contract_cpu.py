@@ -71,3 +71,59 @@ def test_rotating_input_sets_shard_like_the_scene_under_strong_scaling():
     full = bench.synth.spread_particles(P, bench.build_scene("c5", 0, 1)[0]["info"], seed=3000 + 17)
     assert np.array_equal(np.concatenate([shards[0][1]["particles"], shards[1][1]["particles"]]), full)
     assert not np.array_equal(shards[0][1]["particles"], shards[0][2]["particles"])
+
+
+def test_e2e_leg_flow_and_its_fallback_to_ordinary_arrays(monkeypatch):
+    """The Python side of bench.py's e2e leg with a stand-in engine (no GPU): page-locked caller arrays by default; if
+    that path raises, the same measurement runs on ordinary arrays and the line carries a note."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    from mcl_3dl_b200 import synth
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+
+    class Eng:
+        def __init__(self, fail_pinned):
+            self.fail_pinned, self.pinned_arrays, self.calls = fail_pinned, 0, 0
+
+        def host_array(self, n, dt):
+            if self.fail_pinned:
+                raise RuntimeError("no page-locked memory")
+            self.pinned_arrays += 1
+            return np.zeros(n, dt)
+
+        def bind_measure(self, poses, lik, beam, org, out):
+            assert poses.dtype == synth.POSE and out.dtype == synth.RESULT and len(out) == len(poses)
+
+            def call():
+                self.calls += 1
+                out["match_cnt"] = 7
+                return out
+            return call
+
+        def collect_timing(self, on):
+            pass
+
+        def last_timing(self):
+            return {"h2d_ms": 0.0}
+
+        def measure_update(self, poses, lik, beam, org, prior):
+            return np.asarray(prior), {"entropy": 1.0, "kept": 1}, None
+
+    class Cx:
+        pass
+    for fail in (False, True):
+        cx = Cx()
+        cx.world, cx.rank, cx.local, cx.dev, cx.notes = 1, 0, 0, torch.device("cpu"), []
+        cx.flush = torch.zeros(8, dtype=torch.uint8)
+        s, dda, _, P_rank = bench.build_scene("c1", 0, 1)
+        eng = Eng(fail)
+        live = {"eng": eng, "scene": s, "n_lik": len(s["lik"]), "n_beam": len(s["beam"]), "unit_pts": len(s["lik"]),
+                "P_rank": P_rank}
+        out = bench.e2e_leg(cx, "c1", "dda", 4, live)
+        assert out["value"] > 0 and out["h2d_bytes_per_step"] == P_rank * 32 + (len(s["lik"]) + len(s["beam"]) + 2) * 16
+        assert out["d2h_bytes_per_step"] == P_rank * 24 and out["fused_weight_update"]["kept"] == 1
+        assert eng.calls == 3 + 4 + 1 and (live["out_host"]["match_cnt"] == 7).all()
+        assert ("page-locked memory from mcl3dl_host_alloc" in out["host_buffers"]) == (not fail)
+        assert eng.pinned_arrays == (0 if fail else 2) and len(cx.notes) == (1 if fail else 0)
